@@ -1,0 +1,208 @@
+// Shared device primitives for the jodo_b200 kernels (sm_100a only).
+//
+//  * tcgen05 tensor-core MMA (kind::tf32, M=128, cta_group::1) with accumulators in TMEM
+//  * TMEM allocation / tcgen05.ld / tcgen05.st
+//  * mbarrier + cp.async.bulk (TMA engine, 1-D bulk copies of pre-swizzled operand images)
+//  * the "operand image" layout shared by HBM and shared memory
+//
+// Operand image (K-major, SWIZZLE_128B, 4-byte elements): a [rows x K] operand is stored as
+// K/32 chunks; chunk kc holds columns [32kc, 32kc+32) of every row, one 128-byte line per row,
+// line r at byte r*128, and inside a line the 16-byte piece p = (col%32)/4 sits at piece slot
+// p ^ (r & 7).  With a 1024-byte aligned base this is exactly the canonical UMMA K-major
+// SWIZZLE_128B layout (8-row x 128-byte atoms, SBO = 1024 B), so an image can be copied from HBM
+// to shared memory with one linear bulk copy and handed to tcgen05.mma through a descriptor.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jodo {
+
+constexpr int TILE_ROWS = 128;           // rows per edge tile == UMMA M
+constexpr int CHUNK_COLS = 32;           // fp32/tf32 columns per 128-byte swizzle line
+constexpr int CHUNK_BYTES_A = TILE_ROWS * 128;   // one K-chunk of a 128-row A operand (16 KB)
+
+// ---------------------------------------------------------------- small helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float to_tf32(float x) {       // round-to-nearest tf32, returned as fp32 bits
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float tanh_f(float x) {         // accurate to ~1e-6 abs (2 MUFU)
+  float e = __expf(-2.0f * fabsf(x));
+  float t = (1.0f - e) / (1.0f + e);
+  return copysignf(t, x);
+}
+
+// byte offset of element (row, col) inside an operand image whose chunks are `chunk_bytes` apart
+__device__ __host__ __forceinline__ uint32_t img_off(int row, int col, uint32_t chunk_bytes) {
+  return (uint32_t)(col >> 5) * chunk_bytes + (uint32_t)row * 128u +
+         ((((uint32_t)(col & 31) >> 2) ^ ((uint32_t)row & 7u)) << 4) + (((uint32_t)col & 3u) << 2);
+}
+// byte offset of the 16-byte piece `p` (0..7) of row `row` in chunk `kc`
+__device__ __forceinline__ uint32_t img_piece(int row, int kc, int p, uint32_t chunk_bytes) {
+  return (uint32_t)kc * chunk_bytes + (uint32_t)row * 128u + ((((uint32_t)p) ^ ((uint32_t)row & 7u)) << 4);
+}
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Spin on the phase with parity `parity`.  A barrier that never completes is a bug; trap after ~4 s
+// instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && (spin & 0xFFFu) == 0xFFFu) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ll) __trap();
+    }
+  }
+}
+
+// ---------------------------------------------------------------- bulk async copy (TMA engine, 1-D)
+// global -> shared::cta, completion counted in bytes on `bar`.  size % 16 == 0, 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// make generic-proxy writes to shared memory visible to the async proxy (TMA engine / tensor core)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------- TMEM
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {   // one full warp
+  static_assert(NCOLS == 32 || NCOLS == 64 || NCOLS == 128 || NCOLS == 256 || NCOLS == 512, "pow2 >= 32");
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {     // same warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive columns -> 32 registers; thread i of warp w reads TMEM lane 32*(w%4)+i
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- UMMA descriptors + issue
+// Shared-memory matrix descriptor, K-major SWIZZLE_128B (see cute/arch/mma_sm100_desc.hpp):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64: 1024 B)
+//   | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major, M=128, N=n:
+//   [4,6) c_format=1(F32) | [7,10) a_format=2(TF32) | [10,13) b_format=2 | [17,23) N>>3 | [24,29) M>>4
+__device__ __host__ constexpr uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// all previously issued tcgen05.mma of this thread arrive on `bar` when complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// D[128 x N] (TMEM, fp32) (+)= A[128 x 32*nchunks] * W[N x 32*nchunks]^T; both operands are images in
+// shared memory (A chunks CHUNK_BYTES_A apart, W chunks N*128 bytes apart).  One thread calls this.
+__device__ __forceinline__ void mma_tile(uint32_t tmem_d, uint32_t a_saddr, uint32_t w_saddr, int n, int nchunks,
+                                         bool accumulate) {
+  const uint32_t idesc = umma_idesc_tf32(n);
+  uint32_t acc = accumulate ? 1u : 0u;
+  for (int kc = 0; kc < nchunks; ++kc) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {   // 4 x (K=8 tf32 = 32 bytes) per 128-byte swizzle line
+      uint64_t ad = umma_desc_sw128(a_saddr + kc * CHUNK_BYTES_A + kk * 32);
+      uint64_t bd = umma_desc_sw128(w_saddr + kc * (n * 128) + kk * 32);
+      umma_tf32(tmem_d, ad, bd, idesc, acc);
+      acc = 1u;
+    }
+  }
+}
+
+// TMEM address of (lane base of this warp, column)
+__device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int col) {
+  return base + (((uint32_t)(threadIdx.x >> 5) & 3u) << 21) + (uint32_t)col;   // (warp%4)*32 lanes << 16
+}
+
+}  // namespace jodo

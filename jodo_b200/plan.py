@@ -1,0 +1,126 @@
+"""Varlen plan: how one batch of molecules is laid out for the kernels.
+
+The reference turns the padded dense batch into a sparse edge list on every forward
+(``adj_mask.nonzero`` + ``dense_to_sparse``, reference models/mol_gnn.py:512-514, two host syncs).
+Here the layout depends only on the node mask, so it is built once per mask and reused for every
+denoiser call of a sampling run:
+
+* atoms are packed (padding removed) in (molecule, atom) order -> node index in [0, Nn);
+* directed edges live in tiles of 128 rows (= one tcgen05 M tile).  A *group* is the set of all
+  (n-1) partners of one atom; groups are packed greedily into tiles and never split, so every
+  per-atom reduction over partners (softmax over sources, message sum, coordinate sum) is local to
+  a tile.  Row (g, j) stands for the ordered pair whose group atom is g and partner is j; because
+  every edge feature is symmetric the same stored row serves as edge
+  (r=j -> c=g) in the attention pass and as (r=g, c=j) in the coordinate update.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+TILE = 128
+
+
+class Plan:
+    def __init__(self, node_mask: torch.Tensor, device=None):
+        """node_mask: [B, N, 1] or [B, N] (0/1).  Built on the host (one D2H copy of the mask)."""
+        m = node_mask.detach()
+        if m.dim() == 3:
+            m = m[..., 0]
+        m = (m > 0).cpu().numpy()
+        B, N = m.shape
+        self.B, self.N = B, N
+        n = m.sum(1).astype(np.int64)
+        self.n_nodes = n
+        if n.max(initial=0) - 1 > TILE:
+            raise ValueError(f'molecules with more than {TILE + 1} atoms are not supported (got {int(n.max())})')
+        if n.min(initial=1) < 1:
+            raise ValueError('every molecule needs at least one atom')
+        bb, ii = np.nonzero(m)                                   # (b, i) lexicographic == packed order
+        self.Nn = int(bb.shape[0])
+        node_mol = bb.astype(np.int32)
+        node_dense = (bb * N + ii).astype(np.int32)
+        mol_start = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(n, out=mol_start[1:])
+        # ---- greedy group -> tile assignment (sequential over molecules; groups of a molecule share gl)
+        gl_node = (n[bb] - 1).astype(np.int64)                   # group length per packed atom
+        g_tile = np.zeros(self.Nn, dtype=np.int64)
+        g_start = np.zeros(self.Nn, dtype=np.int64)
+        g_idx = np.zeros(self.Nn, dtype=np.int64)
+        tile, fill, ng = 0, 0, 0
+        ngroups = []
+        for b in range(B):
+            gl = int(n[b]) - 1
+            if gl <= 0:
+                continue
+            s = int(mol_start[b])
+            for v in range(s, s + int(n[b])):
+                if fill + gl > TILE:
+                    ngroups.append(ng)
+                    tile, fill, ng = tile + 1, 0, 0
+                g_tile[v], g_start[v], g_idx[v] = tile, fill, ng
+                fill += gl
+                ng += 1
+        ngroups.append(ng)
+        self.n_tiles = tile + 1
+        R = self.n_tiles * TILE
+        row_g = np.full(R, -1, dtype=np.int32)
+        row_j = np.full(R, -1, dtype=np.int32)
+        row_meta = np.zeros(R, dtype=np.uint32)
+        has = gl_node > 0
+        v_ids = np.nonzero(has)[0]
+        gl_v = gl_node[v_ids]
+        tot = int(gl_v.sum())
+        self.n_edges = tot
+        if tot:
+            grp = np.repeat(np.arange(v_ids.shape[0]), gl_v)     # group id per row
+            first = np.zeros(v_ids.shape[0], dtype=np.int64)
+            np.cumsum(gl_v[:-1], out=first[1:])
+            k = np.arange(tot) - first[grp]                      # partner ordinal inside the group
+            v = v_ids[grp]
+            s = mol_start[bb[v]]
+            j = s + k + (k >= (v - s))                           # skip the atom itself
+            rows = g_tile[v] * TILE + g_start[v] + k
+            row_g[rows] = v
+            row_j[rows] = j
+            row_meta[rows] = (g_start[v] | (gl_node[v] << 8) | (g_idx[v] << 16)).astype(np.uint32)
+        self.utilization = tot / float(R)
+        dev = device if device is not None else node_mask.device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.node_mol = t(node_mol)
+        self.node_dense = t(node_dense)
+        self.mol_start = t(mol_start.astype(np.int32))
+        self.row_g = t(row_g)
+        self.row_j = t(row_j)
+        self.row_meta = t(row_meta.view(np.int32))
+        self.tile_ngroups = t(np.asarray(ngroups, dtype=np.int32))
+        self.device = dev
+
+    # ---- helpers used by tests (pure index bookkeeping) -------------------------------------------
+    def dense_to_rows(self, dense_bnn: torch.Tensor, group_first=True) -> torch.Tensor:
+        """Gather a dense [B,N,N,C] tensor into tile-row order [R, C] (padding rows = 0).
+        group_first: row (g, j) reads dense[b, i_g, i_j]; else dense[b, i_j, i_g]."""
+        B, N = self.B, self.N
+        C = dense_bnn.shape[-1]
+        flat = dense_bnn.reshape(B * N * N, C)
+        valid = self.row_g >= 0
+        g = self.node_dense[self.row_g.clamp(min=0).long()].long()
+        j = self.node_dense[self.row_j.clamp(min=0).long()].long()
+        b = g // N
+        ig, ij = g % N, j % N
+        idx = b * N * N + (ig * N + ij if group_first else ij * N + ig)
+        out = flat[idx] * valid[:, None].to(flat.dtype)
+        return out
+
+    def rows_to_dense(self, rows: torch.Tensor, group_first=True) -> torch.Tensor:
+        B, N = self.B, self.N
+        C = rows.shape[-1]
+        out = torch.zeros(B * N * N, C, dtype=rows.dtype, device=rows.device)
+        valid = self.row_g >= 0
+        g = self.node_dense[self.row_g[valid].long()].long()
+        j = self.node_dense[self.row_j[valid].long()].long()
+        b = g // N
+        ig, ij = g % N, j % N
+        idx = b * N * N + (ig * N + ij if group_first else ij * N + ig)
+        out[idx] = rows[valid]
+        return out.reshape(B, N, N, C)

@@ -1,0 +1,63 @@
+"""GPU unit test of the tcgen05 tile-GEMM primitive through jodo_rowlinear (C ABI)."""
+import pytest
+import torch
+
+from jodo_b200 import _lib
+from jodo_b200.pack import round_tf32, weight_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, W, b, act_in=None):
+    A = A.double()
+    if act_in == 'silu':
+        A = torch.nn.functional.silu(A)
+    return (round_tf32(A.float()).double() @ round_tf32(W).double().t() + (0 if b is None else b.double())).float()
+
+
+@pytest.mark.parametrize('M,K,N,NT', [(128, 32, 16, 16), (128, 64, 64, 64), (300, 256, 768, 256), (77, 1024, 512, 128),
+                                     (1000, 128, 32, 32), (257, 768, 256, 256)])
+def test_rowlinear_matches_fp64(M, K, N, NT):
+    g = torch.Generator(device='cuda').manual_seed(M * 7 + K)
+    A = torch.randn(M, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) / K ** 0.5
+    b = torch.randn(N, device='cuda', generator=g)
+    C = torch.full((M, N), float('nan'), device='cuda')
+    _lib.rowlinear(A, K, weight_image(W, NT), b, C, N, NT)
+    torch.cuda.synchronize()
+    ref = _ref(A, W, b)
+    err = float((C - ref).abs().max())
+    assert err < 2e-4, err          # operands are identically tf32-rounded: only fp32 accumulation order differs
+
+
+def test_rowlinear_epilogues_and_strides():
+    g = torch.Generator(device='cuda').manual_seed(5)
+    M, K, N, NT = 333, 256, 256, 128
+    Abig = torch.randn(M, K + 64, device='cuda', generator=g)
+    A = Abig[:, 32:32 + K]                                   # lda != K, offset view
+    W = torch.randn(N, K, device='cuda', generator=g) / 16
+    b = torch.randn(N, device='cuda', generator=g)
+    Wi = weight_image(W, NT)
+    # SiLU on input, GELU on output, strided output
+    Cbig = torch.zeros(M, N + 128, device='cuda')
+    _lib.rowlinear(A, K, Wi, b, Cbig[:, 64:64 + N], N, NT, act_in=_lib.ACT_SILU, epi=_lib.EPI_ACT, act_out=_lib.ACT_GELU)
+    ref = torch.nn.functional.gelu(_ref(A, W, b, 'silu'))
+    assert float((Cbig[:, 64:64 + N] - ref).abs().max()) < 5e-4
+    assert float(Cbig[:, :64].abs().max()) == 0 and float(Cbig[:, 64 + N:].abs().max()) == 0
+    # gated residual
+    mol = torch.randint(0, 7, (M,), device='cuda', dtype=torch.int32, generator=g)
+    gate = torch.randn(7, N, device='cuda', generator=g)
+    res = torch.randn(M, N, device='cuda', generator=g)
+    C = torch.empty(M, N, device='cuda')
+    _lib.rowlinear(A, K, Wi, b, C, N, NT, epi=_lib.EPI_GATED_RES, aux=res, gate=gate, row_mol=mol)
+    ref = res + gate[mol.long()] * _ref(A, W, b)
+    assert float((C - ref).abs().max()) < 5e-4
+    # add
+    _lib.rowlinear(A, K, Wi, None, C, N, NT, epi=_lib.EPI_ADD, aux=res)
+    assert float((C - (res + _ref(A, W, None))).abs().max()) < 5e-4
+
+
+def test_rowlinear_rejects_bad_args():
+    A = torch.zeros(8, 40, device='cuda')
+    with pytest.raises(_lib.JodoError):
+        _lib.rowlinear(A, 40, A, None, A, 16, 16)
