@@ -11,6 +11,7 @@
 #ifndef JODO_B200_H
 #define JODO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -46,6 +47,105 @@ int jodo_abi_version(void);
 int jodo_rowlinear(const float* A, int lda, int M, int K, const float* Wimg, const float* bias, float* C, int ldc,
                    int N, int NT, int act_in, int epi, int act_out, const float* aux, int ld_aux, const float* gate,
                    int ld_gate, const int* row_mol, void* stream);
+
+
+/* ---- varlen plan and argument blocks of the edge-tile kernels ------------------------------------
+ * Atoms are packed (padding removed); directed edges live in tiles of 128 rows; a group = all partners
+ * of one atom, never split across tiles (built by jodo_b200/plan.py once per node mask; replaces the
+ * per-forward adj_mask.nonzero() + dense_to_sparse of reference models/mol_gnn.py:512-514). */
+typedef struct jodo_plan {
+  int B, Nn, n_tiles, N;                 /* molecules, packed atoms, edge tiles, dense padded size */
+  const int* node_mol;                   /* [Nn] molecule of a packed atom */
+  const int* node_dense;                 /* [Nn] b*N + i */
+  const int* mol_start;                  /* [B+1] first packed atom of a molecule */
+  const int* row_g;                      /* [n_tiles*128] packed atom that owns the row's group, -1 = padding */
+  const int* row_j;                      /* [n_tiles*128] the partner atom */
+  const uint32_t* row_meta;              /* group start row (8b) | group length (8b) << 8 | group index in tile (8b) << 16 */
+  const int* tile_ngroups;               /* [n_tiles] */
+} jodo_plan;
+
+typedef struct jodo_edge_embed_args {                    /* model-level edge embedding (reference models/mol_gnn.py:517-557) */
+  jodo_plan p;
+  const float* edge_x; const float* cond_edge_x; const float* cond_x;   /* dense inputs; cond_* null on the first call */
+  int ch, inn; float edge_th, spatial_cut;
+  int* dist_flag;                         /* device int, set by the kernel's first phase: any cond distance != 0 */
+  const float* tab; int ld_tab;           /* per-molecule tables (model-level GBF scale/shift at [0],[1]) */
+  const float* gbf;                       /* GBF constants {mu, 1/sg, 1/(a sg)} x 64 */
+  const float* w_img; const float* bias;  /* edge_emb image (N=64, K=96: [dist 64 | edge_x | cond_edge_x | 0]), bias[64] */
+  float* eh_img; size_t eh_tile_bytes;    /* out: columns [0,64) of the concatenated edge-hidden image */
+  uint8_t* extra;                         /* out: [R] bit0 = 2-D adjacency head, bit1 = spatial adjacency head */
+} jodo_edge_embed_args;
+
+typedef struct jodo_attn_args {                         /* TransMixLayer on edge tiles (reference models/layers.py:131-186) */
+  jodo_plan p;
+  const float* e_in; size_t e_tile_bytes; /* block input edge features (tile images, 64 columns) */
+  const float* pos;                       /* [Nn] float4 */
+  const float* qkv; int ldq;              /* [Nn, 3D]: q | k | v of LN-modulated atoms */
+  const float* tab; int ld_tab; int tab_off;   /* table base of this layer */
+  const uint8_t* extra;
+  const float* gbf;                       /* this layer's GBF constants */
+  const float* w_emb_img; const float* b_emb;  /* block edge_emb (N=64, K=128: [dist | e]) */
+  const float* w0_img; const float* w1_img;    /* lin_edge0 (N=256 padded, K=64), lin_edge1 (N=256, K=64) */
+  float* hnode;                           /* out [Nn, 256] */
+} jodo_attn_args;
+
+typedef struct jodo_edge_update_args {                   /* edge residual + FFN + edge_l (reference models/mol_gnn.py:304-305,313-317,568) */
+  jodo_plan p;
+  const float* e_in; size_t e_tile_bytes;
+  float* e_out;                           /* tile images, 32 KB per tile */
+  const float* P; int ldp;                /* [Nn, 64] node2edge_lin(hnode) without bias */
+  const float* b_n2e;                     /* [64] */
+  const float* tab; int ld_tab; int tab_off;
+  int r;                                  /* mlp_ratio: hidden = 64 r, processed in chunks of 64 */
+  const float* w3_img; const float* b3;   /* r images (N=64, K=64), bias [64 r] */
+  const float* w4_img; const float* b4;   /* r images (N=64, K=64), bias [64] */
+  const float* wl_img; const float* bl;   /* edge_l image (N=16, K=64), bias [16] */
+  float* eh_img; size_t eh_tile_bytes; int eh_col; int ce;   /* out: columns [eh_col, eh_col+ce) of the edge-hidden image */
+} jodo_edge_update_args;
+
+typedef struct jodo_equi_args {                         /* MultiCondEquiUpdate (reference models/mol_gnn.py:71-94) */
+  jodo_plan p;
+  const float* e; size_t e_tile_bytes;    /* updated edge features */
+  const float* pos_in; float* pos_out;    /* [Nn] float4 */
+  const float* AB; int ldab;              /* [Nn, >=512]: input_lin[:, :D] h | input_lin[:, D:2D] h */
+  const float* tab; int ld_tab; int tab_off;
+  const uint8_t* extra;
+  const float* gbf;
+  const float* win_img; const float* b_in;     /* input_lin edge part (N=256, K=128: [e | dist]), bias [256] */
+  const float* wc0_img; const float* b_c0;     /* coord_mlp.0 (N=256, K=256) as 8 K-chunks of 32 KB, bias [256] */
+  const float* wc2;                            /* coord_mlp.2 [3, 256] */
+  float coord_scale;                           /* CoorsNorm.scale */
+} jodo_equi_args;
+
+typedef struct jodo_edge_head_args {                     /* edge_exist_mlp | edge_type_mlp (reference models/mol_gnn.py:466-479,574-578) */
+  jodo_plan p;
+  const float* eh_img; size_t eh_tile_bytes; int keh;    /* concatenated edge hiddens (keh = 192) */
+  const float* w0_img; const float* b0;   /* [exist.0 ; type.0]  (N=128, K=keh) */
+  const float* w2_img; const float* b2;   /* block-diag [exist.2 ; type.2] (N=64, K=128) */
+  const float* w4; const float* b4;       /* [ch, 32] rows: exist.4, type.4...; bias [ch] */
+  int ch;
+  float* out_dense;                       /* [B,N,N,ch], zero-filled by the caller */
+} jodo_edge_head_args;
+
+
+/* per-atom / per-molecule elementwise kernels */
+int jodo_time_features(const float* noise_level, const float* w8, float* feat32, int B, void* stream);
+int jodo_cond_in(const float* ctx, const float* w0, const float* b0, float* out, int rows, int D, void* stream);
+int jodo_gather_nodes(const float* xh, const float* cond_x, const jodo_plan* p, int inn, int kin, float* xin, float* pos4,
+                      void* stream);
+int jodo_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
+                int off_shift, int off_scale, const jodo_plan* p, float* out, int ldo, void* stream);
+int jodo_com(float* pos4, const jodo_plan* p, void* stream);
+int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, int inn,
+                  float* out_dense, void* stream);
+int jodo_sym_edges(const float* tmp, float* out, int B, int N, int ch, void* stream);
+
+/* edge-tile kernels (tcgen05 + TMEM + bulk-copied operand images); see the structs above */
+int jodo_edge_embed(const jodo_edge_embed_args* a, void* stream);
+int jodo_attn(const jodo_attn_args* a, void* stream);
+int jodo_edge_update(const jodo_edge_update_args* a, void* stream);
+int jodo_equi(const jodo_equi_args* a, void* stream);
+int jodo_edge_head(const jodo_edge_head_args* a, void* stream);
 
 #ifdef __cplusplus
 }

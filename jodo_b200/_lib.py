@@ -60,3 +60,59 @@ def rowlinear(A, K, Wimg, bias, C, N, NT, act_in=ACT_NONE, epi=EPI_STORE, act_ou
                               c_int(0 if gate is None else gate.stride(0)), ptr(row_mol),
                               stream if stream is not None else stream_ptr())
     check(rc, 'jodo_rowlinear')
+
+
+# ---- argument blocks (mirror include/jodo_b200.h field by field) -----------------------------------
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+_Z = ctypes.c_size_t
+
+
+class PlanStruct(ctypes.Structure):
+    _fields_ = [('B', _I), ('Nn', _I), ('n_tiles', _I), ('N', _I), ('node_mol', _P), ('node_dense', _P),
+                ('mol_start', _P), ('row_g', _P), ('row_j', _P), ('row_meta', _P), ('tile_ngroups', _P)]
+
+
+class EdgeEmbedArgs(ctypes.Structure):
+    _fields_ = [('p', PlanStruct), ('edge_x', _P), ('cond_edge_x', _P), ('cond_x', _P), ('ch', _I), ('inn', _I),
+                ('edge_th', _F), ('spatial_cut', _F), ('dist_flag', _P), ('tab', _P), ('ld_tab', _I), ('gbf', _P),
+                ('w_img', _P), ('bias', _P), ('eh_img', _P), ('eh_tile_bytes', _Z), ('extra', _P)]
+
+
+class AttnArgs(ctypes.Structure):
+    _fields_ = [('p', PlanStruct), ('e_in', _P), ('e_tile_bytes', _Z), ('pos', _P), ('qkv', _P), ('ldq', _I),
+                ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P), ('gbf', _P), ('w_emb_img', _P),
+                ('b_emb', _P), ('w0_img', _P), ('w1_img', _P), ('hnode', _P)]
+
+
+class EdgeUpdateArgs(ctypes.Structure):
+    _fields_ = [('p', PlanStruct), ('e_in', _P), ('e_tile_bytes', _Z), ('e_out', _P), ('P', _P), ('ldp', _I),
+                ('b_n2e', _P), ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('r', _I), ('w3_img', _P), ('b3', _P),
+                ('w4_img', _P), ('b4', _P), ('wl_img', _P), ('bl', _P), ('eh_img', _P), ('eh_tile_bytes', _Z),
+                ('eh_col', _I), ('ce', _I)]
+
+
+class EquiArgs(ctypes.Structure):
+    _fields_ = [('p', PlanStruct), ('e', _P), ('e_tile_bytes', _Z), ('pos_in', _P), ('pos_out', _P), ('AB', _P),
+                ('ldab', _I), ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P), ('gbf', _P),
+                ('win_img', _P), ('b_in', _P), ('wc0_img', _P), ('b_c0', _P), ('wc2', _P), ('coord_scale', _F)]
+
+
+class EdgeHeadArgs(ctypes.Structure):
+    _fields_ = [('p', PlanStruct), ('eh_img', _P), ('eh_tile_bytes', _Z), ('keh', _I), ('w0_img', _P), ('b0', _P),
+                ('w2_img', _P), ('b2', _P), ('w4', _P), ('b4', _P), ('ch', _I), ('out_dense', _P)]
+
+
+def dp(t):
+    """raw device address (int) of a tensor, 0 for None"""
+    return 0 if t is None else t.data_ptr()
+
+
+def plan_struct(plan):
+    return PlanStruct(plan.B, plan.Nn, plan.n_tiles, plan.N, dp(plan.node_mol), dp(plan.node_dense),
+                      dp(plan.mol_start), dp(plan.row_g), dp(plan.row_j), dp(plan.row_meta), dp(plan.tile_ngroups))
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,116 @@
+// Helpers shared by the edge-tile kernels: row metadata, operand-row I/O, GBF, LayerNorm.
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+namespace jodo {
+
+constexpr int ET = 128;                   // threads per edge CTA == rows per tile
+constexpr int D_ = 256;                   // node width the edge kernels are built for (config.model.nf)
+constexpr int ED_ = 64;                   // edge width  (nf / 4)
+constexpr int E_TILE_BYTES = 2 * CHUNK_BYTES_A;     // one [128 x 64] fp32 edge tile image (32 KB)
+
+struct RowInfo {
+  int g, j;          // packed atoms (clamped to 0 on padding rows so that loads stay in bounds)
+  int gs, gl, gi;    // group start row, group length, group index inside the tile
+  int mol;
+  bool valid;
+};
+
+__device__ __forceinline__ RowInfo load_row(const Plan& p, int tile, int t) {
+  RowInfo r;
+  const int R = tile * TILE_ROWS + t;
+  const int g = p.row_g[R];
+  r.valid = g >= 0;
+  r.g = r.valid ? g : 0;
+  r.j = r.valid ? p.row_j[R] : 0;
+  const uint32_t m = p.row_meta[R];
+  r.gs = m & 255u; r.gl = (m >> 8) & 255u; r.gi = (m >> 16) & 255u;
+  r.mol = p.node_mol[r.g];
+  return r;
+}
+
+__device__ __forceinline__ void sync_tc() {   // CTA barrier that also orders tcgen05 traffic around it
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+// store 64 consecutive columns (2 chunks starting at chunk kc0) of row `row` into an operand image in smem
+template <bool ROUND>
+__device__ __forceinline__ void st_row64(uint8_t* img, int row, int kc0, const float (&v)[64]) {
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    float4 o;
+    o.x = ROUND ? to_tf32(v[4 * p]) : v[4 * p];
+    o.y = ROUND ? to_tf32(v[4 * p + 1]) : v[4 * p + 1];
+    o.z = ROUND ? to_tf32(v[4 * p + 2]) : v[4 * p + 2];
+    o.w = ROUND ? to_tf32(v[4 * p + 3]) : v[4 * p + 3];
+    *reinterpret_cast<float4*>(img + img_piece(row, kc0 + (p >> 3), p & 7, CHUNK_BYTES_A)) = o;
+  }
+}
+__device__ __forceinline__ void ld_row64(const uint8_t* img, int row, int kc0, float (&v)[64]) {
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const float4 o = *reinterpret_cast<const float4*>(img + img_piece(row, kc0 + (p >> 3), p & 7, CHUNK_BYTES_A));
+    v[4 * p] = o.x; v[4 * p + 1] = o.y; v[4 * p + 2] = o.z; v[4 * p + 3] = o.w;
+  }
+}
+// 32 consecutive columns = one chunk
+template <bool ROUND>
+__device__ __forceinline__ void st_row32(uint8_t* img, int row, int kc, const float (&v)[32]) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    float4 o;
+    o.x = ROUND ? to_tf32(v[4 * p]) : v[4 * p];
+    o.y = ROUND ? to_tf32(v[4 * p + 1]) : v[4 * p + 1];
+    o.z = ROUND ? to_tf32(v[4 * p + 2]) : v[4 * p + 2];
+    o.w = ROUND ? to_tf32(v[4 * p + 3]) : v[4 * p + 3];
+    *reinterpret_cast<float4*>(img + img_piece(row, kc, p, CHUNK_BYTES_A)) = o;
+  }
+}
+
+// CondGaussianLayer (reference models/layers.py:291-295,328-334): x = d*(1+scale)+shift;
+// out = [x, exp(-0.5((x-mu_k)/sg_k)^2) / (a*sg_k)], k < 63.  c = {mu[64], 1/sg[64], 1/(a*sg)[64]} (packer).
+__device__ __forceinline__ void gbf_eval(float d, float scale, float shift, const float* __restrict__ c, float (&out)[64]) {
+  const float x = d * (scale + 1.0f) + shift;
+  out[0] = x;
+#pragma unroll
+  for (int k = 0; k < 63; ++k) {
+    const float z = (x - c[k]) * c[64 + k];
+    out[1 + k] = __expf(-0.5f * z * z) * c[128 + k];
+  }
+}
+
+// LayerNorm (no affine, eps 1e-6) + modulate over 64 thread-local values
+__device__ __forceinline__ void ln_mod64(float (&x)[64], const float* __restrict__ shift, const float* __restrict__ scale) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) s += x[i];
+  const float mean = s * (1.0f / 64.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) { const float d = x[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(q * (1.0f / 64.0f) + 1e-6f);
+#pragma unroll
+  for (int i = 0; i < 64; i += 4) {
+    const float4 sh = *reinterpret_cast<const float4*>(shift + i);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + i);
+    x[i] = (x[i] - mean) * rstd * (1.0f + sc.x) + sh.x;
+    x[i + 1] = (x[i + 1] - mean) * rstd * (1.0f + sc.y) + sh.y;
+    x[i + 2] = (x[i + 2] - mean) * rstd * (1.0f + sc.z) + sh.z;
+    x[i + 3] = (x[i + 3] - mean) * rstd * (1.0f + sc.w) + sh.w;
+  }
+}
+
+__device__ __forceinline__ float sq_dist(const float4 a, const float4 b) {
+  const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+  return dx * dx + dy * dy + dz * dz;
+}
+
+// trap if the dynamic shared memory window is not 1024-byte aligned (SWIZZLE_128B atoms need it)
+__device__ __forceinline__ void require_smem_alignment(const void* base) {
+  if ((smem_u32(base) & 1023u) != 0u) __trap();
+}
+
+}  // namespace jodo

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "../../include/jodo_b200.h"
 
 namespace jodo {
 
@@ -38,16 +39,7 @@ __host__ __device__ constexpr int tab_gbf(int D) { return 6 * D + 6 * (D / 4) + 
 // ---- varlen plan (built by the host once per node mask) -------------------------------------------
 // Atoms are packed (padding removed): node index in [0, Nn).  Directed edges are laid out in tiles of
 // 128 rows; every group = all (n-1) partners of one atom, never split across tiles.
-struct Plan {
-  int B, Nn, n_tiles, N;                 // molecules, packed atoms, edge tiles, dense padded size
-  const int* node_mol;                   // [Nn] molecule of a packed atom
-  const int* node_dense;                 // [Nn] b*N + i
-  const int* mol_start;                  // [B+1] first packed atom of a molecule
-  const int* row_g;                      // [n_tiles*128] packed atom that owns the row's group, -1 = padding
-  const int* row_j;                      // [n_tiles*128] the partner atom
-  const uint32_t* row_meta;              // group start row (8b) | group length (8b) << 8 | group index in tile (8b) << 16
-  const int* tile_ngroups;               // [n_tiles]
-};
+using Plan = ::jodo_plan;
 
 struct ModelDims {
   int D, ed, T, L, r, S, sc, qk, C, inn, ch, cn, ce, cond_ch;
@@ -55,5 +47,36 @@ struct ModelDims {
   int ld_ah;                             // row stride of the concatenated atom hidden buffer
   int keh;                               // columns (multiple of 32) of the concatenated edge hidden image
 };
+
+// ---- node / molecule elementwise kernels (node_kernels.cu) -----------------------------------------
+cudaError_t launch_time_features(const float* nl, const float* w, float* feat, int B, cudaStream_t st);
+cudaError_t launch_cond_in(const float* ctx, const float* w0, const float* b0, float* out, int rows, int D, cudaStream_t st);
+cudaError_t launch_gather_nodes(const float* xh, const float* cond_x, const Plan& p, int inn, int kin, float* xin,
+                                float* pos, cudaStream_t st);
+cudaError_t launch_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab,
+                          int off_gate, int off_shift, int off_scale, const Plan& p, float* out, int ldo,
+                          cudaStream_t st);
+cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st);
+cudaError_t launch_nan_flag(const float* pos, int Nn, int* flag, cudaStream_t st);
+cudaError_t launch_node_out(const float* pos, const float* atom_pred, int ldp, const Plan& p, const int* nan_flag,
+                            int inn, float* out, cudaStream_t st);
+cudaError_t launch_sym_edges(const float* tmp, float* out, int B, int N, int ch, cudaStream_t st);
+
+// ---- edge-tile kernels (edge_kernels.cu); all built for nf = 256 (ed = 64, 14+2 heads) --------------
+using EdgeEmbedArgs = ::jodo_edge_embed_args;
+cudaError_t launch_dist_flag(const EdgeEmbedArgs& a, cudaStream_t st);
+cudaError_t launch_edge_embed(const EdgeEmbedArgs& a, int num_sms, cudaStream_t st);
+
+using AttnArgs = ::jodo_attn_args;
+cudaError_t launch_attn(const AttnArgs& a, int num_sms, cudaStream_t st);
+
+using EdgeUpdateArgs = ::jodo_edge_update_args;
+cudaError_t launch_edge_update(const EdgeUpdateArgs& a, int num_sms, cudaStream_t st);
+
+using EquiArgs = ::jodo_equi_args;
+cudaError_t launch_equi(const EquiArgs& a, int num_sms, cudaStream_t st);
+
+using EdgeHeadArgs = ::jodo_edge_head_args;
+cudaError_t launch_edge_head(const EdgeHeadArgs& a, int num_sms, cudaStream_t st);
 
 }  // namespace jodo

@@ -1,0 +1,216 @@
+// Per-atom / per-molecule elementwise kernels around the tensor-core row-linears.
+// All tensors are in the packed (varlen) atom layout of kernels.h::Plan unless noted "dense".
+#include "common.cuh"
+#include "kernels.h"
+
+namespace jodo {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// feat[b, 0:17] = (nl, sin(nl*w*2pi) x8, cos(nl*w*2pi) x8), padded with zeros to 32 columns.
+// LearnedSinusodialposEmb.forward, reference models/layers.py:283-288.
+__global__ void k_time_features(const float* __restrict__ nl, const float* __restrict__ w, float* __restrict__ feat, int B) {
+  int b = blockIdx.x * blockDim.x / 32 + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float x = nl[b];
+  float v = 0.f;
+  if (lane == 0) v = x;
+  else if (lane <= 16) {
+    float f = x * w[(lane - 1) & 7];
+    f = f * 2.0f;
+    f = f * 3.14159265358979323846f;
+    v = (lane <= 8) ? sinf(f) : cosf(f);
+  }
+  feat[(size_t)b * 32 + lane] = v;
+}
+
+// c1[row, d] = GELU(ctx[row] * w0[d] + b0[d]);  cond_mlp.0 + GELU, reference models/mol_gnn.py:679-681,729-730
+__global__ void k_cond_in(const float* __restrict__ ctx, const float* __restrict__ w0, const float* __restrict__ b0,
+                          float* __restrict__ out, int rows, int D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  int r = i / D, d = i - r * D;
+  out[i] = gelu_f(ctx[r] * w0[d] + b0[d]);
+}
+
+// Packed node inputs from the dense padded batch: xin[v] = (h[b,i,:], cond_h[b,i,:], 0...), pos[v] = xh[b,i,0:3].
+// reference models/mol_gnn.py:509-510, 528-530.
+__global__ void k_gather_nodes(const float* __restrict__ xh, const float* __restrict__ cond_x,
+                               const int* __restrict__ node_dense, int Nn, int inn, int kin, float* __restrict__ xin,
+                               float4* __restrict__ pos) {
+  int v = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (v >= Nn) return;
+  const int row = node_dense[v];
+  const int w = 3 + inn;
+  const float* x = xh + (size_t)row * w;
+  const float* c = cond_x ? cond_x + (size_t)row * w : nullptr;
+  for (int k = lane; k < kin; k += 32) {
+    float val = 0.f;
+    if (k < inn) val = x[3 + k];
+    else if (k < 2 * inn) val = c ? c[3 + k - inn] : 0.f;
+    xin[(size_t)v * kin + k] = val;
+  }
+  if (lane == 0) pos[v] = make_float4(x[0], x[1], x[2], 0.f);
+}
+
+// out[v,:] = LN(x[v,:] + gate[mol]*y[v,:]) * (1 + scale[mol]) + shift[mol]      (one warp per atom)
+// norm1_node + modulate (reference models/mol_gnn.py:296) when y == null;
+// gated residual + norm2_node + modulate (:307-308) otherwise.  LayerNorm eps = 1e-6, no affine (:234,240).
+template <int D>
+__global__ void k_ln_mod(const float* __restrict__ x, int ldx, const float* __restrict__ y, int ldy,
+                         const float* __restrict__ tab, int ld_tab, int off_gate, int off_shift, int off_scale,
+                         const int* __restrict__ node_mol, int Nn, float* __restrict__ out, int ldo) {
+  constexpr int PER = D / 32;
+  int v = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (v >= Nn) return;
+  const float* t = tab + (size_t)node_mol[v] * ld_tab;
+  float a[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    int c = lane + 32 * i;
+    float val = x[(size_t)v * ldx + c];
+    if (y) val += t[off_gate + c] * y[(size_t)v * ldy + c];
+    a[i] = val;
+    s += val;
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { float d = a[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-6f);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    int c = lane + 32 * i;
+    out[(size_t)v * ldo + c] = (a[i] - mean) * rstd * (1.0f + t[off_scale + c]) + t[off_shift + c];
+  }
+}
+
+// Per-molecule centre-of-mass removal of the block's coordinate update, in place on pos_new
+// (remove_mean_with_mask, reference models/utils.py:38-45; call site models/mol_gnn.py:565-566).
+// A single-atom molecule has no edges, so no kernel wrote pos_new for it: x - mean(x) = 0.
+__global__ void k_com(float4* __restrict__ pos_new, const int* __restrict__ mol_start, int B) {
+  int b = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int s = mol_start[b], e = mol_start[b + 1];
+  const int n = e - s;
+  if (n == 1) {
+    if (lane == 0) pos_new[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int v = s + lane; v < e; v += 32) { float4 p = pos_new[v]; sx += p.x; sy += p.y; sz += p.z; }
+  sx = warp_sum(sx) / n; sy = warp_sum(sy) / n; sz = warp_sum(sz) / n;
+  for (int v = s + lane; v < e; v += 32) {
+    float4 p = pos_new[v];
+    pos_new[v] = make_float4(p.x - sx, p.y - sy, p.z - sz, 0.f);
+  }
+}
+
+// flag |= any NaN in pos   (batch-global guard, reference models/mol_gnn.py:587)
+__global__ void k_nan_flag(const float4* __restrict__ pos, int Nn, int* __restrict__ flag) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= Nn) return;
+  float4 p = pos[v];
+  if (isnan(p.x) || isnan(p.y) || isnan(p.z)) atomicOr(flag, 1);
+}
+
+// Dense node output [B,N,3+inn]: positions (zeroed if the NaN flag is set, then CoM-free again) and atom
+// logits; padded atoms stay 0 (the buffer is zero-filled by the caller).  reference models/mol_gnn.py:573,582-594.
+__global__ void k_node_out(const float4* __restrict__ pos, const float* __restrict__ atom_pred, int ldp,
+                           const int* __restrict__ mol_start, const int* __restrict__ node_dense,
+                           const int* __restrict__ nan_flag, int B, int inn, float* __restrict__ out) {
+  int b = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int s = mol_start[b], e = mol_start[b + 1];
+  const int n = e - s;
+  const bool zero = *nan_flag != 0;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  if (!zero)
+    for (int v = s + lane; v < e; v += 32) { float4 p = pos[v]; sx += p.x; sy += p.y; sz += p.z; }
+  sx = warp_sum(sx) / n; sy = warp_sum(sy) / n; sz = warp_sum(sz) / n;
+  const int w = 3 + inn;
+  for (int v = s + lane; v < e; v += 32) {
+    float4 p = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : pos[v];
+    float* o = out + (size_t)node_dense[v] * w;
+    o[0] = p.x - sx; o[1] = p.y - sy; o[2] = p.z - sz;
+    for (int k = 0; k < inn; ++k) o[3 + k] = atom_pred[(size_t)v * ldp + k];
+  }
+}
+
+// out[b,i,j,:] = 0.5 * (tmp[b,i,j,:] + tmp[b,j,i,:])      (reference models/mol_gnn.py:579)
+__global__ void k_sym_edges(const float* __restrict__ tmp, float* __restrict__ out, int B, int N, int ch) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * N * N * ch;
+  if (i >= total) return;
+  int c = (int)(i % ch);
+  long long e = i / ch;
+  int jj = (int)(e % N);
+  long long r = e / N;
+  int ii = (int)(r % N);
+  long long b = r / N;
+  out[i] = 0.5f * (tmp[i] + tmp[((b * N + jj) * N + ii) * ch + c]);
+}
+
+}  // namespace
+
+#define LAUNCH_OK() cudaGetLastError()
+
+cudaError_t launch_time_features(const float* nl, const float* w, float* feat, int B, cudaStream_t st) {
+  k_time_features<<<(B + 3) / 4, 128, 0, st>>>(nl, w, feat, B);
+  return LAUNCH_OK();
+}
+cudaError_t launch_cond_in(const float* ctx, const float* w0, const float* b0, float* out, int rows, int D, cudaStream_t st) {
+  k_cond_in<<<(rows * D + 255) / 256, 256, 0, st>>>(ctx, w0, b0, out, rows, D);
+  return LAUNCH_OK();
+}
+cudaError_t launch_gather_nodes(const float* xh, const float* cond_x, const Plan& p, int inn, int kin, float* xin,
+                                float* pos, cudaStream_t st) {
+  k_gather_nodes<<<(p.Nn + 7) / 8, 256, 0, st>>>(xh, cond_x, p.node_dense, p.Nn, inn, kin, xin,
+                                                  reinterpret_cast<float4*>(pos));
+  return LAUNCH_OK();
+}
+cudaError_t launch_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab,
+                          int off_gate, int off_shift, int off_scale, const Plan& p, float* out, int ldo,
+                          cudaStream_t st) {
+  dim3 grid((p.Nn + 7) / 8);
+  if (D == 256)
+    k_ln_mod<256><<<grid, 256, 0, st>>>(x, ldx, y, ldy, tab, ld_tab, off_gate, off_shift, off_scale, p.node_mol, p.Nn, out, ldo);
+  else if (D == 384)
+    k_ln_mod<384><<<grid, 256, 0, st>>>(x, ldx, y, ldy, tab, ld_tab, off_gate, off_shift, off_scale, p.node_mol, p.Nn, out, ldo);
+  else
+    return cudaErrorInvalidValue;
+  return LAUNCH_OK();
+}
+cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st) {
+  k_com<<<(p.B + 7) / 8, 256, 0, st>>>(reinterpret_cast<float4*>(pos_new), p.mol_start, p.B);
+  return LAUNCH_OK();
+}
+cudaError_t launch_nan_flag(const float* pos, int Nn, int* flag, cudaStream_t st) {
+  k_nan_flag<<<(Nn + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(pos), Nn, flag);
+  return LAUNCH_OK();
+}
+cudaError_t launch_node_out(const float* pos, const float* atom_pred, int ldp, const Plan& p, const int* nan_flag,
+                            int inn, float* out, cudaStream_t st) {
+  k_node_out<<<(p.B + 7) / 8, 256, 0, st>>>(reinterpret_cast<const float4*>(pos), atom_pred, ldp, p.mol_start,
+                                             p.node_dense, nan_flag, p.B, inn, out);
+  return LAUNCH_OK();
+}
+cudaError_t launch_sym_edges(const float* tmp, float* out, int B, int N, int ch, cudaStream_t st) {
+  long long total = (long long)B * N * N * ch;
+  k_sym_edges<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tmp, out, B, N, ch);
+  return LAUNCH_OK();
+}
+
+}  // namespace jodo

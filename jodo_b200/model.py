@@ -1,0 +1,253 @@
+"""Drop-in replacements for the reference's ``DGT_concat`` / ``Cond_DGT_concat`` denoisers.
+
+Boundary: same constructor (``__init__(config)`` reading the reference's config
+keys), same parameter names / shapes / registration order (reference checkpoints load with
+``strict=True`` and EMA's positional ``copy_to`` works), same call
+``model(t, xh, node_mask, edge_mask, context=None, edge_x=..., noise_level=..., cond_x=...,
+cond_edge_x=...) -> (x_hat [B,N,3+in], e_hat [B,N,N,ch])`` as reference
+models/mol_gnn.py:491-594 / 687-794.  The forward itself is a fixed sequence of launches of the
+hand-written sm_100a kernels in libjodo_b200.so through its C ABI; there is no PyTorch or CPU
+fallback: without the library (or without a CUDA device) the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _lib
+from .pack import TAB_HEAD, pack_model, tab_layer_stride
+from .params import build_param_tree, check_supported, dims_from_config, param_spec, synth_state_dict
+from .plan import Plan
+
+_c = ctypes.c_int
+
+
+class _Workspace:
+    """Device buffers for one plan (sizes depend on the packed atom / tile counts only)."""
+
+    def __init__(self, plan: Plan, d, meta, dev):
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        zf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        B, Nn, nt = plan.B, plan.Nn, plan.n_tiles
+        D, T = d.D, d.T
+        self.feat = f(B, 32)
+        self.t1 = f(B, T)
+        self.temb = f(B, T)
+        if d.cond_ch:
+            self.c1 = f(B * d.cond_ch, D)
+            self.c2 = f(B * d.cond_ch, D)
+            self.ctx = f(B, T)
+        self.tab = f(B, meta['ld_tab'])
+        self.kin = meta['node_emb']['K']
+        self.xin = f(Nn, self.kin)
+        self.pos = [zf(Nn, 4), zf(Nn, 4)]
+        self.ah = zf(Nn, meta['ld_ah'])                    # concatenated atom hiddens (pads stay 0)
+        self.h = [f(Nn, D), f(Nn, D)]
+        self.hn = f(Nn, D)
+        self.qkv = f(Nn, 3 * D)
+        self.hnode = zf(Nn, D)                             # atoms without partners are never written: stay 0
+        self.pbuf = f(Nn, 64)
+        self.h2 = f(Nn, D)
+        self.ff = f(Nn, d.r * D)
+        self.ab = f(Nn, 2 * D)
+        self.n1 = f(Nn, D)
+        self.n2 = f(Nn, D // 2)
+        self.ap = f(Nn, meta['npred4']['N'])
+        self.eh_tile_bytes = (meta['keh'] // 32) * 128 * 128
+        self.eh = torch.zeros(nt * self.eh_tile_bytes // 4, device=dev, dtype=torch.float32)
+        self.e = torch.zeros(nt * 8192, device=dev, dtype=torch.float32)      # 32 KB per tile
+        self.extra = torch.zeros(nt * 128, device=dev, dtype=torch.uint8)
+        self.flags = torch.zeros(4, device=dev, dtype=torch.int32)            # [0] dist flag, [1] nan flag
+
+
+class _DGTBase(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        check_supported(config)
+        self.dims = dims_from_config(config)
+        if self.dims.D != 256:
+            raise NotImplementedError(f'jodo_b200 kernels are built for model.nf = 256 (got {self.dims.D})')
+        if self.dims.ce % 4 or self.dims.ce > 16:
+            raise NotImplementedError('unsupported n_layers (edge hidden slice must be a multiple of 4 <= 16)')
+        self.edge_th = float(config.model.edge_quan_th)
+        self.spatial_cut_off = float(config.model.spatial_cut_off)
+        self.n_layers = self.dims.L
+        self._spec = param_spec(config)
+        build_param_tree(self, self._spec)
+        self.load_state_dict(synth_state_dict(self._spec, seed=int(getattr(config, 'seed', 0))))
+        self._packed = None
+        self._packed_key = None
+        self._plans = {}
+        self.debug = None          # set to a dict to capture intermediates (tests)
+
+    # ---- caches -------------------------------------------------------------------------------------
+    def _weights(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is None or key != self._packed_key:
+            sd = {k: v for k, v in self.state_dict().items()}
+            dev = next(self.parameters()).device
+            self._packed = pack_model(sd, self.dims, dev)
+            self._packed_key = key
+        return self._packed
+
+    def _plan(self, node_mask, edge_mask):
+        key = (node_mask.data_ptr(), tuple(node_mask.shape), node_mask._version, edge_mask.data_ptr())
+        hit = self._plans.get(key)
+        if hit is None:
+            plan = Plan(node_mask)
+            B, N = plan.B, plan.N
+            nm = (node_mask.reshape(B, N) > 0).float()
+            want = nm[:, :, None] * nm[:, None, :] * (1 - torch.eye(N, device=nm.device))[None]
+            if not torch.equal((edge_mask.reshape(B, N, N) > 0).float(), want):
+                raise ValueError('edge_mask must be node_mask x node_mask without the diagonal '
+                                 '(reference sampling.py:197-199)')
+            ws = _Workspace(plan, self.dims, self._weights().meta, node_mask.device)
+            if len(self._plans) > 4:
+                self._plans.clear()
+            hit = self._plans[key] = (plan, ws, _lib.plan_struct(plan))
+        return hit
+
+    # ---- forward ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, t, xh, node_mask, edge_mask, context=None, *args, **kwargs):
+        if self.training:
+            raise RuntimeError('jodo_b200 implements the inference path (call model.eval())')
+        edge_x = kwargs['edge_x']
+        noise_level = kwargs['noise_level']
+        cond_x = kwargs.get('cond_x')
+        cond_edge_x = kwargs.get('cond_edge_x')
+        if not xh.is_cuda:
+            raise _lib.JodoError('jodo_b200 runs on CUDA tensors only (no CPU fallback)')
+        d = self.dims
+        if d.cond_ch and context is None:
+            raise ValueError('cond_DGT_concat needs a context')
+        pk = self._weights()
+        meta = pk.meta
+        plan, ws, ps = self._plan(node_mask, edge_mask)
+        B, N = plan.B, plan.N
+        st = _lib.stream_ptr()
+        L = _lib.lib()
+        dbg = self.debug
+        c32 = lambda x: x.contiguous().float()
+        xh, edge_x, noise_level = c32(xh), c32(edge_x), c32(noise_level)
+        if cond_x is not None:
+            cond_x, cond_edge_x = c32(cond_x), c32(cond_edge_x)
+        D, T, ld_tab = d.D, d.T, meta['ld_tab']
+
+        def lin(name, A, C, M=None, **kw):
+            m = meta[name]
+            _lib.rowlinear(A, m['K'], pk[name + '.img'], pk[name + '.b'], C, m['N'], m['NT'], M=M, stream=st, **kw)
+
+        # ---- per molecule: noise-level embedding (+ context) and all AdaLN tables
+        _lib.call('jodo_time_features', _lib.ptr(noise_level), _lib.ptr(pk['time.w8']), _lib.ptr(ws.feat), _c(B), st)
+        lin('time1', ws.feat, ws.t1, epi=_lib.EPI_ACT, act_out=_lib.ACT_GELU)
+        if d.cond_ch:
+            ctx = c32(context).reshape(B * d.cond_ch)
+            _lib.call('jodo_cond_in', _lib.ptr(ctx), _lib.ptr(pk['cond0.w']), _lib.ptr(pk['cond0.b']), _lib.ptr(ws.c1),
+                      _c(B * d.cond_ch), _c(D), st)
+            lin('cond2', ws.c1, ws.c2)
+            lin('condlin', ws.c2.view(B, d.cond_ch * D), ws.ctx)
+            lin('time3', ws.t1, ws.temb, epi=_lib.EPI_ADD, aux=ws.ctx)
+        else:
+            lin('time3', ws.t1, ws.temb)
+        lin('tab', ws.temb, ws.tab, act_in=_lib.ACT_SILU)
+        # ---- per atom: packed inputs, node embedding (slice 0 of the concatenated atom hiddens)
+        _lib.call('jodo_gather_nodes', _lib.ptr(xh), _lib.ptr(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin),
+                  _lib.ptr(ws.xin), _lib.ptr(ws.pos[0]), st)
+        lin('node_emb', ws.xin, ws.ah[:, :D])
+        # ---- per edge: model-level embedding + adjacency heads
+        ea = _lib.EdgeEmbedArgs(ps, _lib.dp(edge_x), _lib.dp(cond_edge_x), _lib.dp(cond_x), d.ch, d.inn, self.edge_th,
+                                self.spatial_cut_off, _lib.dp(ws.flags), _lib.dp(ws.tab), ld_tab, pk.ptr('gbf'),
+                                pk.ptr('edge_emb.img'), pk.ptr('edge_emb.b'), _lib.dp(ws.eh), ws.eh_tile_bytes,
+                                _lib.dp(ws.extra))
+        _lib.call('jodo_edge_embed', ctypes.byref(ea), st)
+
+        h, ldh_view = ws.ah[:, :D], None
+        e_in_ptr, e_in_stride = _lib.dp(ws.eh), ws.eh_tile_bytes
+        stride = tab_layer_stride(D)
+        for l in range(d.L):
+            p = f'b{l}.'
+            off = TAB_HEAD + l * stride
+            pin, pout = ws.pos[l & 1], ws.pos[(l + 1) & 1]
+            hout = ws.h[l & 1]
+            # norm1_node + modulate, q/k/v
+            _lib.call('jodo_ln_mod', _c(D), _lib.ptr(h), _c(h.stride(0)), None, _c(0), _lib.ptr(ws.tab), _c(ld_tab),
+                      _c(0), _c(off), _c(off + D), ctypes.byref(ps), _lib.ptr(ws.hn), _c(D), st)
+            lin(p + 'qkv', ws.hn, ws.qkv)
+            aa = _lib.AttnArgs(ps, e_in_ptr, e_in_stride, _lib.dp(pin), _lib.dp(ws.qkv), 3 * D, _lib.dp(ws.tab), ld_tab,
+                               off, _lib.dp(ws.extra), pk.ptr(p + 'gbf'), pk.ptr(p + 'emb.img'), pk.ptr(p + 'emb.b'),
+                               pk.ptr(p + 'e0.img'), pk.ptr(p + 'e1.img'), _lib.dp(ws.hnode))
+            _lib.call('jodo_attn', ctypes.byref(aa), st)
+            # node path: hoisted node2edge, gated residual + norm2 + FFN, hoisted input_lin parts, node_l
+            lin(p + 'n2e', ws.hnode, ws.pbuf)
+            _lib.call('jodo_ln_mod', _c(D), _lib.ptr(h), _c(h.stride(0)), _lib.ptr(ws.hnode), _c(D), _lib.ptr(ws.tab),
+                      _c(ld_tab), _c(off + 2 * D), _c(off + 3 * D), _c(off + 4 * D), ctypes.byref(ps), _lib.ptr(ws.h2),
+                      _c(D), st)
+            lin(p + 'ff1', ws.h2, ws.ff, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)
+            lin(p + 'ff2', ws.ff, hout, epi=_lib.EPI_GATED_RES, aux=ws.h2, gate=ws.tab[:, off + 5 * D:],
+                row_mol=plan.node_mol)
+            lin(p + 'ab', hout, ws.ab)
+            lin(p + 'node_l', hout, ws.ah[:, D + l * meta['cnp']:])
+            # edge path
+            ua = _lib.EdgeUpdateArgs(ps, e_in_ptr, e_in_stride, _lib.dp(ws.e), _lib.dp(ws.pbuf), 64, pk.ptr(p + 'n2e.bias'),
+                                     _lib.dp(ws.tab), ld_tab, off, d.r, pk.ptr(p + 'ff3.img'), pk.ptr(p + 'ff3.b'),
+                                     pk.ptr(p + 'ff4.img'), pk.ptr(p + 'ff4.b'), pk.ptr(p + 'edge_l.img'),
+                                     pk.ptr(p + 'edge_l.b'), _lib.dp(ws.eh), ws.eh_tile_bytes, d.ed + l * d.ce, d.ce)
+            _lib.call('jodo_edge_update', ctypes.byref(ua), st)
+            qa = _lib.EquiArgs(ps, _lib.dp(ws.e), 32768, _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), 2 * D,
+                               _lib.dp(ws.tab), ld_tab, off, _lib.dp(ws.extra), pk.ptr(p + 'gbf'), pk.ptr(p + 'win.img'),
+                               pk.ptr(p + 'win.b'), pk.ptr(p + 'wc0.img'), pk.ptr(p + 'wc0.b'), pk.ptr(p + 'wc2'),
+                               meta['coord_scale'][l])
+            _lib.call('jodo_equi', ctypes.byref(qa), st)
+            _lib.call('jodo_com', _lib.ptr(pout), ctypes.byref(ps), st)
+            if dbg is not None:
+                dbg.setdefault('blocks', []).append(dict(hnode=ws.hnode.clone(), h=hout.clone(), e=ws.e.clone(),
+                                                         pos=pout.clone(), qkv=ws.qkv.clone(), hn=ws.hn.clone()))
+            h = hout
+            e_in_ptr, e_in_stride = _lib.dp(ws.e), 32768
+        # ---- heads
+        lin('npred0', ws.ah, ws.n1, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)
+        lin('npred2', ws.n1, ws.n2, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)
+        lin('npred4', ws.n2, ws.ap)
+        out_x = torch.zeros(B, N, 3 + d.inn, device=xh.device, dtype=torch.float32)
+        _lib.call('jodo_node_out', _lib.ptr(ws.pos[d.L & 1]), _lib.ptr(ws.ap), _c(ws.ap.stride(0)), ctypes.byref(ps),
+                  ctypes.c_void_p(ws.flags.data_ptr() + 4), _c(d.inn), _lib.ptr(out_x), st)
+        tmp = torch.zeros(B, N, N, d.ch, device=xh.device, dtype=torch.float32)
+        ha = _lib.EdgeHeadArgs(ps, _lib.dp(ws.eh), ws.eh_tile_bytes, meta['keh'], pk.ptr('ehead0.img'), pk.ptr('ehead0.b'),
+                               pk.ptr('ehead2.img'), pk.ptr('ehead2.b'), pk.ptr('ehead4.w'), pk.ptr('ehead4.b'), d.ch,
+                               _lib.dp(tmp))
+        _lib.call('jodo_edge_head', ctypes.byref(ha), st)
+        out_e = torch.empty_like(tmp)
+        _lib.call('jodo_sym_edges', _lib.ptr(tmp), _lib.ptr(out_e), _c(B), _c(N), _c(d.ch), st)
+        if dbg is not None:
+            dbg.update(tab=ws.tab.clone(), temb=ws.temb.clone(), ah=ws.ah.clone(), eh=ws.eh.clone(),
+                       extra=ws.extra.clone(), plan=plan, flags=ws.flags.clone())
+        return out_x, out_e
+
+
+class DGT_concat(_DGTBase):
+    """B200-native drop-in for the reference ``DGT_concat`` (models/mol_gnn.py:410-594)."""
+
+
+class Cond_DGT_concat(_DGTBase):
+    """B200-native drop-in for the reference ``Cond_DGT_concat`` (models/mol_gnn.py:597-794)."""
+
+
+MODELS = {'DGT_concat': DGT_concat, 'cond_DGT_concat': Cond_DGT_concat}
+
+
+def create_model(config, device='cuda'):
+    """Same role as reference models/utils.py:24-28 (without the DataParallel wrapper: multi-GPU is one
+    process per GPU here)."""
+    return MODELS[config.model.name](config).to(device).eval()
+
+
+def register_into_reference(models_utils_module, suffix='_b200'):
+    """Make ``config.model.name = 'DGT_concat_b200'`` / ``'cond_DGT_concat_b200'`` resolve to this
+    implementation inside the reference's registry (reference models/utils.py:5-21)."""
+    for name, cls in MODELS.items():
+        key = name + suffix
+        if key not in models_utils_module._MODELS:
+            models_utils_module.register_model(cls, name=key)

@@ -55,3 +55,183 @@ def matrix_to_image(m: torch.Tensor) -> torch.Tensor:
     """[rows, k] -> one tile image [k/32][rows][8 slots][4] (no tf32 rounding)."""
     rows, k = m.shape
     return weight_image(m, rows, tf32=False)
+
+
+# =====================================================================================================
+# Whole-model packing: reference state dict -> one flat fp32 device buffer + named offsets
+# =====================================================================================================
+TAB_HEAD = 16
+
+
+def tab_layer_stride(D):
+    return 6 * D + 6 * (D // 4) + 2 * D + 16
+
+
+class Packed:
+    """Flat fp32 buffer with named, 256-byte aligned pieces."""
+
+    def __init__(self, device):
+        self.device = device
+        self._pieces = []
+        self._off = {}
+        self._size = 0
+        self.buf = None
+        self.meta = {}
+
+    def add(self, name, t):
+        t = t.detach().to(self.device, torch.float32).reshape(-1)
+        self._off[name] = (self._size, t.numel())
+        self._pieces.append(t)
+        pad = (-t.numel()) % 64
+        if pad:
+            self._pieces.append(torch.zeros(pad, device=self.device))
+        self._size += t.numel() + pad
+
+    def finish(self):
+        self.buf = torch.cat(self._pieces)
+        self._pieces = None
+        return self
+
+    def __getitem__(self, name):
+        o, n = self._off[name]
+        return self.buf[o:o + n]
+
+    def ptr(self, name):
+        return self.buf.data_ptr() + 4 * self._off[name][0]
+
+
+def _gbf_consts(sd, prefix, dev):
+    """{mu, 1/sg, 1/(a sg)} x 64 with the reference's fp32 arithmetic (models/layers.py:291-295,332-333)."""
+    mu = sd[prefix + '.means.weight'].float().view(-1)
+    sg = sd[prefix + '.stds.weight'].float().view(-1).abs() + 1e-5
+    a = (2 * 3.14159) ** 0.5
+    asg = a * sg
+    out = torch.zeros(192, device=dev)
+    k = mu.numel()
+    out[0:k] = mu
+    out[64:64 + k] = 1.0 / sg
+    out[128:128 + k] = 1.0 / asg
+    return out
+
+
+def pack_model(sd, dims, device):
+    """sd: name -> tensor (reference names, no 'module.' prefix); dims: jodo_b200.params.Dims."""
+    d = dims
+    D, ed, T, L = d.D, d.ed, d.T, d.L
+    assert D == 256 and ed == 64, 'edge kernels are built for nf = 256'
+    sd = {k: v.detach().to(device, torch.float32) for k, v in sd.items()}
+    pk = Packed(device)
+    W = lambda n: sd[n + '.weight']
+    Bv = lambda n: sd[n + '.bias']
+    z = lambda *s: torch.zeros(*s, device=device)
+
+    def add_lin(name, w, b, nt, n_pad=None, k_pad=None):
+        n, k = w.shape
+        n_pad = ceil_to(n, nt) if n_pad is None else n_pad
+        k_pad = ceil_to(k, 32) if k_pad is None else k_pad
+        pk.add(name + '.img', weight_image(pad2(w, n_pad, k_pad), nt))
+        bb = z(n_pad)
+        if b is not None:
+            bb[:n] = b
+        pk.add(name + '.b', bb)
+        pk.meta[name] = dict(N=n_pad, K=k_pad, NT=nt)
+
+    # ---- molecule level
+    pk.add('time.w8', sd['time_mlp.0.weights'])
+    add_lin('time1', W('time_mlp.1'), Bv('time_mlp.1'), 256)
+    add_lin('time3', W('time_mlp.3'), Bv('time_mlp.3'), 256)
+    if d.cond_ch:
+        pk.add('cond0.w', W('cond_mlp.0').reshape(-1))
+        pk.add('cond0.b', Bv('cond_mlp.0'))
+        add_lin('cond2', W('cond_mlp.2'), Bv('cond_mlp.2'), 256)
+        add_lin('condlin', W('cond_lin'), Bv('cond_lin'), 256)
+    # per-molecule tables: one GEMM  [B, T] x [T, ld_tab]
+    stride = tab_layer_stride(D)
+    ld_tab = ceil_to(TAB_HEAD + L * stride, 256)
+    wt, bt = z(ld_tab, T), z(ld_tab)
+    wt[0:2], bt[0:2] = W('dist_layer.time_mlp.1'), Bv('dist_layer.time_mlp.1')
+    for l in range(L):
+        b = f'e_block_{l}'
+        o = TAB_HEAD + l * stride
+        for name, n in ((f'{b}.node_time_mlp.1', 6 * D), (f'{b}.edge_time_mlp.1', 6 * ed),
+                        (f'{b}.equi_update.time_mlp.1', 2 * D), (f'{b}.dist_layer.time_mlp.1', 2)):
+            wt[o:o + n], bt[o:o + n] = W(name), Bv(name)
+            o += n
+    add_lin('tab', wt, bt, 256)
+    pk.meta['ld_tab'] = ld_tab
+    # ---- atom level
+    add_lin('node_emb', W('node_emb'), Bv('node_emb'), 256)
+    cnp = ceil_to(d.cn, 4)
+    k_ah = ceil_to(D + L * cnp, 32)
+    pk.meta.update(cnp=cnp, k_ah=k_ah, ld_ah=k_ah + 64)
+    w0 = W('node_pred_mlp.0')
+    w0p = z(D, k_ah)
+    w0p[:, :D] = w0[:, :D]
+    for l in range(L):
+        w0p[:, D + l * cnp:D + l * cnp + d.cn] = w0[:, D + l * d.cn:D + (l + 1) * d.cn]
+    add_lin('npred0', w0p, Bv('node_pred_mlp.0'), 256)
+    add_lin('npred2', W('node_pred_mlp.2'), Bv('node_pred_mlp.2'), 128)
+    add_lin('npred4', W('node_pred_mlp.4'), Bv('node_pred_mlp.4'), 16)
+    # ---- edge level (model)
+    pk.add('gbf', _gbf_consts(sd, 'dist_layer', device))
+    we = W('edge_emb')                                         # [ed, 2ch + ed]: [edge_x | cond_edge_x | dist]
+    wep = z(ed, 96)
+    wep[:, :ed] = we[:, 2 * d.ch:]
+    wep[:, ed:ed + 2 * d.ch] = we[:, :2 * d.ch]
+    pk.add('edge_emb.img', weight_image(wep, ed))
+    pk.add('edge_emb.b', Bv('edge_emb'))
+    keh = ceil_to(ed + L * d.ce, 32)
+    assert keh == 192, keh
+    pk.meta['keh'] = keh
+    wh0 = z(2 * ed, keh)
+    wh0[:ed, :d.edge_cat] = W('edge_exist_mlp.0')
+    wh0[ed:, :d.edge_cat] = W('edge_type_mlp.0')
+    pk.add('ehead0.img', weight_image(wh0, 2 * ed))
+    pk.add('ehead0.b', torch.cat([Bv('edge_exist_mlp.0'), Bv('edge_type_mlp.0')]))
+    wh2 = z(ed, 2 * ed)
+    wh2[:ed // 2, :ed] = W('edge_exist_mlp.2')
+    wh2[ed // 2:, ed:] = W('edge_type_mlp.2')
+    pk.add('ehead2.img', weight_image(wh2, ed))
+    pk.add('ehead2.b', torch.cat([Bv('edge_exist_mlp.2'), Bv('edge_type_mlp.2')]))
+    pk.add('ehead4.w', torch.cat([W('edge_exist_mlp.4'), W('edge_type_mlp.4')], dim=0))     # [ch, 32]
+    pk.add('ehead4.b', torch.cat([Bv('edge_exist_mlp.4'), Bv('edge_type_mlp.4')]))
+    # ---- blocks
+    scales = []
+    for l in range(L):
+        b = f'e_block_{l}'
+        p = f'b{l}.'
+        wq = z(3 * D, D)
+        bq = z(3 * D)
+        wq[:d.qk], bq[:d.qk] = W(f'{b}.attn_mpnn.lin_query'), Bv(f'{b}.attn_mpnn.lin_query')
+        wq[D:D + d.qk], bq[D:D + d.qk] = W(f'{b}.attn_mpnn.lin_key'), Bv(f'{b}.attn_mpnn.lin_key')
+        wq[2 * D:], bq[2 * D:] = W(f'{b}.attn_mpnn.lin_value'), Bv(f'{b}.attn_mpnn.lin_value')
+        add_lin(p + 'qkv', wq, bq, 256)
+        add_lin(p + 'n2e', W(f'{b}.node2edge_lin'), None, 64)
+        pk.add(p + 'n2e.bias', Bv(f'{b}.node2edge_lin'))
+        add_lin(p + 'ff1', W(f'{b}.ff_linear1'), Bv(f'{b}.ff_linear1'), 256)
+        add_lin(p + 'ff2', W(f'{b}.ff_linear2'), Bv(f'{b}.ff_linear2'), 256)
+        wi = W(f'{b}.equi_update.input_lin')                   # [D, 2D + 2ed]: [h_row | h_col | e | dist]
+        add_lin(p + 'ab', torch.cat([wi[:, :D], wi[:, D:2 * D]], dim=0), None, 256)
+        add_lin(p + 'node_l', W(f'node_{l}'), Bv(f'node_{l}'), 64, n_pad=64)
+        pk.add(p + 'gbf', _gbf_consts(sd, f'{b}.dist_layer', device))
+        pk.add(p + 'emb.img', weight_image(W(f'{b}.edge_emb'), ed))                       # [64, 128]: [dist | e]
+        pk.add(p + 'emb.b', Bv(f'{b}.edge_emb'))
+        pk.add(p + 'e0.img', weight_image(pad2(W(f'{b}.attn_mpnn.lin_edge0'), D, ed), D))
+        pk.add(p + 'e1.img', weight_image(W(f'{b}.attn_mpnn.lin_edge1'), D))
+        w3, w4 = W(f'{b}.ff_linear3'), W(f'{b}.ff_linear4')    # [ed r, ed], [ed, ed r]
+        pk.add(p + 'ff3.img', weight_image(w3, ed))
+        pk.add(p + 'ff3.b', Bv(f'{b}.ff_linear3'))
+        pk.add(p + 'ff4.img', torch.cat([weight_image(w4[:, ed * i:ed * (i + 1)].contiguous(), ed) for i in range(d.r)]))
+        pk.add(p + 'ff4.b', Bv(f'{b}.ff_linear4'))
+        pk.add(p + 'edge_l.img', weight_image(pad2(W(f'edge_{l}'), 16, ed), 16))
+        bl = z(16)
+        bl[:d.ce] = Bv(f'edge_{l}')
+        pk.add(p + 'edge_l.b', bl)
+        pk.add(p + 'win.img', weight_image(wi[:, 2 * D:].contiguous(), D))                # [256, 128]: [e | dist]
+        pk.add(p + 'win.b', Bv(f'{b}.equi_update.input_lin'))
+        pk.add(p + 'wc0.img', weight_image(W(f'{b}.equi_update.coord_mlp.0'), D))
+        pk.add(p + 'wc0.b', Bv(f'{b}.equi_update.coord_mlp.0'))
+        pk.add(p + 'wc2', W(f'{b}.equi_update.coord_mlp.2'))                               # [3, 256]
+        scales.append(sd[f'{b}.equi_update.coord_norm.scale'].reshape(()))
+    pk.meta['coord_scale'] = [float(s) for s in torch.stack(scales).cpu()]
+    return pk.finish()

@@ -76,7 +76,7 @@ def cond_gbf(sd, prefix, d, st):
     return torch.cat([x, g], dim=-1)
 
 
-def trans_mix(sd, prefix, hn, en, extra, em, dims):
+def trans_mix(sd, prefix, hn, en, extra, em, dims, trace=None):
     """TransMixLayer.forward/message (models/layers.py:131-186) on a dense grid.
     hn [B,N,D], en [B,N,N,ed], extra [B,N,N,X], em [B,N,N,1] -> [B,N,D]."""
     B, N, D = hn.shape
@@ -96,6 +96,8 @@ def trans_mix(sd, prefix, hn, en, extra, em, dims):
     al = ex / (ex.sum(dim=1, keepdim=True) + 1e-16)                   # PyG softmax (:178)
     g1 = torch.tanh(_lin(sd, prefix + '.lin_edge1', en)).reshape(B, N, N, H, C)    # :183
     msg = v[:, :, None, :, :] * g1 * al[..., None]                    # :182-184
+    if trace is not None:
+        trace.update(q=q.reshape(B, N, -1), k=k.reshape(B, N, -1), v=v.reshape(B, N, -1), alpha=al)
     return msg.sum(dim=1).reshape(B, N, D)                            # aggr='add' onto target c (:101)
 
 
@@ -117,7 +119,7 @@ def equi_update(sd, prefix, hout, pos, eout, df, st, extra, em):
     return pos + (dl * inv * em).sum(dim=2)                           # scatter-add on row (:90-92)
 
 
-def mix_block(sd, prefix, pos, h, e, extra, m, em, st, dims):
+def mix_block(sd, prefix, pos, h, e, extra, m, em, st, dims, trace=None):
     """EquivariantMixBlock.forward (models/mol_gnn.py:270-322)."""
     diff = pos[:, :, None, :] - pos[:, None, :, :]
     d = (diff ** 2).sum(-1, keepdim=True)                             # coord2dist (models/utils.py:122-126)
@@ -129,7 +131,7 @@ def mix_block(sd, prefix, pos, h, e, extra, m, em, st, dims):
     esm, ecm, egm, esf, ecf, egf = [t[:, None, None, :] for t in et.chunk(6, dim=1)]
     hn = _modulate(_ln(h), nsm, ncm)                                  # :296
     en = _modulate(_ln(e1), esm, ecm)                                 # :297
-    hnode = trans_mix(sd, prefix + '.attn_mpnn', hn, en, extra, em, dims)          # :303
+    hnode = trans_mix(sd, prefix + '.attn_mpnn', hn, en, extra, em, dims, trace)   # :303
     hedge = _lin(sd, prefix + '.node2edge_lin', hnode[:, :, None, :] + hnode[:, None, :, :])  # :304-305
     h1 = h + ngm * hnode                                              # :307
     h2 = _modulate(_ln(h1), nsf, ncf) * m                             # :308
@@ -137,6 +139,8 @@ def mix_block(sd, prefix, pos, h, e, extra, m, em, st, dims):
     e2 = _modulate(_ln(e + egm * hedge), esf, ecf)                    # :313-314 (residual from block input e)
     eout = e2 + egf * _lin(sd, prefix + '.ff_linear4', F.silu(_lin(sd, prefix + '.ff_linear3', e2)))  # :316
     pos = equi_update(sd, prefix + '.equi_update', hout, pos, eout, df, st, extra, em)       # :320
+    if trace is not None:
+        trace.update(hn=hn, en=en, e1=e1, hnode=hnode, h2=h2, hedge=hedge, df=df)
     return hout, eout, pos
 
 
@@ -153,7 +157,7 @@ def dims_of(config):
 
 @torch.no_grad()
 def dgt_forward(sd, config, t, xh, node_mask, edge_mask, context=None, edge_x=None, noise_level=None,
-                cond_x=None, cond_edge_x=None, collect=None):
+                cond_x=None, cond_edge_x=None, collect=None, trace=None):
     """DGT_concat.forward (models/mol_gnn.py:491-594) / Cond_DGT_concat.forward (:687-794).
     `collect`, if a list, receives (h, e, pos) after every block for stage-level debugging."""
     dims = dims_of(config)
@@ -185,15 +189,23 @@ def dgt_forward(sd, config, t, xh, node_mask, edge_mask, context=None, edge_x=No
     e = _lin(sd, 'edge_emb', torch.cat([edge_x, cond_edge_x, dist0], dim=-1))      # :553,557
     h = _lin(sd, 'node_emb', h)                                       # :556
     atom_hids, edge_hids = [h], [e]
+    if trace is not None:
+        trace.update(temb=temb, h0=h, e0=e, extra=extra, dist0=dist0)
     for i in range(dims['L']):                                        # :562-568
-        h, e, pos = mix_block(sd, f'e_block_{i}', pos, h, e, extra, m, em, st, dims)
+        bt = {} if trace is not None else None
+        h, e, pos = mix_block(sd, f'e_block_{i}', pos, h, e, extra, m, em, st, dims, bt)
         pos = remove_mean_with_mask(pos, m)                           # config.model.CoM (:565-566)
         atom_hids.append(_lin(sd, f'node_{i}', h))
         edge_hids.append(_lin(sd, f'edge_{i}', e))
         if collect is not None:
             collect.append((h.clone(), e.clone(), pos.clone()))
+        if trace is not None:
+            bt.update(h=h, e=e, pos=pos)
+            trace.setdefault('blocks', []).append(bt)
     ah = torch.cat(atom_hids, dim=-1)
     eh = torch.cat(edge_hids, dim=-1)
+    if trace is not None:
+        trace.update(ah=ah, eh=eh)
     atom_pred = _mlp3(sd, 'node_pred_mlp', ah) * m                    # :573
     ep = torch.cat([_mlp3(sd, 'edge_exist_mlp', eh), _mlp3(sd, 'edge_type_mlp', eh)], dim=-1) * em  # :574-578
     ef = 0.5 * (ep + ep.permute(0, 2, 1, 3))                          # :579
