@@ -40,6 +40,27 @@ def check(rc, what):
         raise JodoError(f'{what} failed ({rc}): {lib().jodo_last_error_string().decode()}')
 
 
+# ---- launch accounting / per-call device timing (bench.py, profiling) ------------------------------
+# kernels launched per C-ABI call (everything else launches exactly one)
+KERNELS_PER_CALL = {'jodo_edge_embed': 2, 'jodo_node_out': 2}
+LAUNCHES = 0           # kernels launched through this binding since import
+TRACE = None           # set to a list to record (name, start_event, end_event) around every call
+
+
+def _account(name, fn):
+    global LAUNCHES
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
+    if TRACE is None:
+        return fn()
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn()
+    e1.record()
+    TRACE.append((name, e0, e1))
+    return rc
+
+
 def ptr(t):
     """Device pointer of a torch tensor (or None)."""
     return None if t is None else ctypes.c_void_p(t.data_ptr())
@@ -51,14 +72,15 @@ def stream_ptr():
 
 
 def rowlinear(A, K, Wimg, bias, C, N, NT, act_in=ACT_NONE, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None,
-              row_mol=None, M=None, stream=None):
+              row_mol=None, M=None, stream=None, tag=None):
     """C[:, :N] = epi(act_in(A[:, :K]) W^T + bias); A, C, aux, gate are 2-D row-major views (stride(1)==1)."""
     M = A.shape[0] if M is None else M
-    rc = lib().jodo_rowlinear(ptr(A), c_int(A.stride(0)), c_int(M), c_int(K), ptr(Wimg), ptr(bias), ptr(C),
-                              c_int(C.stride(0)), c_int(N), c_int(NT), c_int(act_in), c_int(epi), c_int(act_out),
-                              ptr(aux), c_int(0 if aux is None else aux.stride(0)), ptr(gate),
-                              c_int(0 if gate is None else gate.stride(0)), ptr(row_mol),
-                              stream if stream is not None else stream_ptr())
+    f = lib().jodo_rowlinear
+    st = stream if stream is not None else stream_ptr()
+    rc = _account(tag or 'jodo_rowlinear', lambda: f(
+        ptr(A), c_int(A.stride(0)), c_int(M), c_int(K), ptr(Wimg), ptr(bias), ptr(C), c_int(C.stride(0)), c_int(N),
+        c_int(NT), c_int(act_in), c_int(epi), c_int(act_out), ptr(aux), c_int(0 if aux is None else aux.stride(0)),
+        ptr(gate), c_int(0 if gate is None else gate.stride(0)), ptr(row_mol), st))
     check(rc, 'jodo_rowlinear')
 
 
@@ -115,4 +137,5 @@ def plan_struct(plan):
 
 
 def call(name, *args):
-    check(getattr(lib(), name)(*args), name)
+    f = getattr(lib(), name)
+    check(_account(name, lambda: f(*args)), name)
