@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the DGT denoiser hot path: denoiser steps/sec (molecules x steps / s).
+
+    python bench.py --gpus N --steps K --warmup W [--workload qm9|geom] [--impl reference]
+
+A "step" is one reverse-SDE step of the reference's ancestral sampler on one batch of synthetic
+molecules: one denoiser call (DGT forward, self-conditioned) + posterior-mean update + fresh noise
+(reference sampling.py:535-589).  N=1 workload = BASELINE.json configs[1]: QM9 uncond architecture,
+batch 2500, N<=29, first K steps of the 1000-step grid, random-init weights, synthetic inputs drawn the
+way sampling_fn draws them.  N>1: every rank runs its own 2500 molecules (weak scaling), no collective
+in the loop, one NCCL all_gather of the final samples after the timed region.
+
+One JSON line on stdout (rank 0).  `value` = whole-job throughput with state resident in HBM;
+`e2e` = same step driven through the public API with HOST (pinned) buffers, H2D of the step's inputs
+and D2H of its results inside the timed region; `roofline` = the dominant kernel against the measured
+peak; `cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
+--impl reference times the CPU implementation (oracle port of the reference; the Python reference
+itself cannot travel to the GPU box) on rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'denoiser steps/sec (molecules x steps / s)'
+UNIT = 'mol-steps/s'
+WORKLOADS = {
+    # name -> (config factory name, per-GPU batch, max n, description)
+    'qm9': ('qm9_uncond', 2500, None, 'QM9 uncond 1000-step ancestral sampling, batch 2500, N<=29'),
+    'geom': ('geom_l8', 512, 80, 'GEOM-Drugs uncond medium (n_layers=8, nf=256), batch 512, N<=80'),
+}
+CPU_SAMPLE = {'qm9': 64, 'geom': 4}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='qm9', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch override (debug)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=float(d['hbm_gbs']), tf_burst=float(d['bf16_tflops']),
+                    tf_sustained=float(d.get('bf16_tflops_sustained', d['bf16_tflops'])), src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src='fallback')
+
+
+# ---- clocks ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0]))
+            mx.append(int(f[1]))
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nme)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---- workload ----------------------------------------------------------------------------------------
+def make_state(cfg, batch, max_n, seed, device):
+    from jodo_b200 import synth
+    b = synth.make_batch(cfg, batch, seed=seed, max_n=max_n)
+    return b
+
+
+def cpu_step_rate(cfg, wl, n_steps, threads):
+    """CPU arm: the oracle port (fp32, all host threads) driving the same ancestral step on a bounded
+    sample of the workload.  Returns (mol-steps/s, sample description)."""
+    from jodo_b200 import sampler as S, synth
+    from jodo_b200.params import param_spec, synth_state_dict
+    from oracle.dgt_dense import dgt_forward
+    torch.set_num_threads(threads)
+    bs = CPU_SAMPLE[wl]
+    _, _, max_n, _ = WORKLOADS[wl]
+    b = synth.make_batch(cfg, bs, seed=42, max_n=max_n)
+    sd = synth_state_dict(param_spec(cfg), seed=int(cfg.seed))
+
+    def model(t, xh, node_mask, edge_mask, **kw):
+        return dgt_forward(sd, cfg, t, xh, node_mask, edge_mask, **kw)
+
+    smp = S.AncestralSampler(S.CosineVP(), torch.linspace(0.9946, 1e-3, 1000), generator=torch.Generator().manual_seed(1))
+    x, ex, cx, cex = b['xh'], b['edge_x'], None, None
+    with torch.no_grad():
+        x, ex, _, _, cx, cex = smp.step(model, 0, x, ex, b['node_mask'], b['edge_mask'], cx, cex)      # warm-up
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            x, ex, _, _, cx, cex = smp.step(model, 1 + i, x, ex, b['node_mask'], b['edge_mask'], cx, cex)
+        dt = time.perf_counter() - t0
+    return bs * n_steps / dt, f'{bs} molecules (same histogram, seed 42) x {n_steps} ancestral steps, oracle port fp32'
+
+
+def run_reference(args):
+    from jodo_b200 import configs
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cfg_name, batch, max_n, desc = WORKLOADS[args.workload]
+    cfg = configs.NAMED[cfg_name]()
+    threads = os.cpu_count() or 1
+    n = max(1, args.steps)
+    t0 = time.perf_counter()
+    rate, sample = cpu_step_rate(cfg, args.workload, n, threads)
+    wall = time.perf_counter() - t0
+    out = {
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * CPU_SAMPLE[args.workload] / rate, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': desc, 'per_gpu_batch': batch},
+        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'wall_s': wall,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from jodo_b200 import _lib, configs, roofline, sampler as S, synth
+    from jodo_b200.model import create_model
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the DGT hot path has no CPU fallback; use --impl reference)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cfg_name, batch, max_n, desc = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    cfg = configs.NAMED[cfg_name]()
+    model = create_model(cfg, dev)
+    d = model.dims
+    b = synth.make_batch(cfg, batch, seed=42 + rank, max_n=max_n)
+    n_nodes = b['n_nodes']
+    N = int(n_nodes.max())
+    tot = roofline.batch_totals(n_nodes, d)
+    node_mask, edge_mask = b['node_mask'].to(dev), b['edge_mask'].to(dev)
+    grid = torch.linspace(0.9946, 1e-3, 1000)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    smp = S.AncestralSampler(S.CosineVP(), grid, generator=gen)
+    K, W = args.steps, args.warmup
+    if W + K > len(grid):
+        raise SystemExit('warmup + steps must not exceed the 1000-step grid')
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident run ------------------------------------------------------------------------
+    state = dict(x=b['xh'].to(dev), ex=b['edge_x'].to(dev), cx=None, cex=None)
+
+    def step(i):
+        x, ex, xm, em, cx, cex = smp.step(model, i, state['x'], state['ex'], node_mask, edge_mask, state['cx'], state['cex'])
+        state.update(x=x, ex=ex, cx=cx, cex=cex, xm=xm, em=em)
+
+    for i in range(W):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        step(i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    launches = _lib.LAUNCHES - l0
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    ok = bool(torch.isfinite(state['xm']).all()) and bool(torch.isfinite(state['em']).all())
+
+    # ---- end to end: host buffers, H2D + D2H every step ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+        host = dict(x=pin(state['x']), ex=pin(state['ex']), cx=pin(state['cx']), cex=pin(state['cex']))
+        h2d = sum(v.numel() * 4 for v in host.values())
+        outh = dict(x=torch.empty_like(host['x']).pin_memory(), ex=torch.empty_like(host['ex']).pin_memory(),
+                    cx=torch.empty_like(host['cx']).pin_memory(), cex=torch.empty_like(host['cex']).pin_memory())
+        d2h = sum(v.numel() * 4 for v in outh.values())
+
+        def e2e_step(i):
+            dv = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            x, ex, _, _, cx, cex = smp.step(model, i, dv['x'], dv['ex'], node_mask, edge_mask, dv['cx'], dv['cex'])
+            outh['x'].copy_(x, non_blocking=True)
+            outh['ex'].copy_(ex, non_blocking=True)
+            outh['cx'].copy_(cx, non_blocking=True)
+            outh['cex'].copy_(cex, non_blocking=True)
+            torch.cuda.current_stream().synchronize()           # the caller reads the result on the host
+            for k in host:
+                host[k], outh[k] = outh[k], host[k]
+
+        ke = max(3, min(K, 20))
+        for i in range(2):
+            e2e_step(W + K - 1)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(ke):
+            e2e_step(W + K - 1)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {'value': batch * world * ke / float(dt), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'steps': ke}
+
+    # ---- per-kernel device times (CUDA events around every C-ABI call, outside the timed region) -------
+    _lib.TRACE = []
+    reps = 3
+    for i in range(reps):
+        step(W + K - 1)
+    torch.cuda.synchronize()
+    per = {}
+    for name, a, z in _lib.TRACE:
+        t, c = per.get(name, (0.0, 0))
+        per[name] = (t + a.elapsed_time(z), c + 1)
+    _lib.TRACE = None
+    total_traced = sum(t for t, _ in per.values())
+    top = max(per, key=lambda k: per[k][0])
+    pk = peaks()
+    kf = roofline.per_edge_kernel_flops(d)
+    kb = roofline.per_edge_kernel_bytes(d)
+    kernels = {}
+    for name, (t, c) in sorted(per.items(), key=lambda kv: -kv[1][0]):
+        avg_ms = t / c
+        ent = {'launches_per_step': c // reps, 'avg_ms': round(avg_ms, 4), 'share': round(t / total_traced, 4)}
+        if name in kf:
+            ent['tflops'] = round(kf[name] * tot['edges'] / (avg_ms * 1e-3) / 1e12, 2)
+            ent['gbs'] = round(kb[name] * tot['edges'] / (avg_ms * 1e-3) / 1e9, 1)
+        kernels[name] = ent
+    roof = None
+    if top in kf:
+        ach = kf[top] * tot['edges'] / (per[top][0] / per[top][1] * 1e-3) / 1e12
+        roof = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
+                'frac': ach / pk['tf_sustained'], 'traffic': None,
+                'peak_source': pk['src'] + ' bf16 sustained (kernels run kind::tf32: nominal ceiling is half of it)',
+                'share_of_step': per[top][0] / total_traced}
+    whole = {'tflops': tot['flops'] * K / (ms * 1e-3) / 1e12, 'hbm_gbs_alg': tot['bytes'] * K / (ms * 1e-3) / 1e9}
+    whole['tensor_frac'] = whole['tflops'] / pk['tf_sustained']
+    whole['hbm_frac'] = whole['hbm_gbs_alg'] / pk['hbm']
+
+    # ---- the one collective: gather the final samples ------------------------------------------------
+    gathered = None
+    if world > 1:
+        Ng = torch.tensor([N], device=dev)
+        dist.all_reduce(Ng, op=dist.ReduceOp.MAX)
+        idx = torch.arange(batch) + rank * batch
+        gx, ge = S.gather_samples(state['xm'], state['em'], idx, batch * world, int(Ng))
+        gathered = [list(gx.shape), list(ge.shape)]
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, sample = cpu_step_rate(cfg, args.workload, 8, threads)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample}
+
+    if rank == 0:
+        out = {
+            'metric': METRIC, 'value': batch * world * K / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': K,
+            'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'tf32 operands / f32 accumulate + f32 elementwise', 'data': 'synthetic',
+            'config': {'workload': desc, 'per_gpu_batch': batch, 'N': N, 'atoms': tot['atoms'], 'edges': tot['edges'],
+                       'arch': cfg_name, 'weights': 'random init (seed 42)', 'l2': 'inputs larger than L2 '
+                       '(edge state %.0f MB per step)' % (tot['bytes'] / 1e6), 'parallelism': f'dp{world} (independent molecules)'},
+            'e2e': e2e, 'gpu_launches': launches, 'clocks': clk, 'roofline': roof, 'whole_step': whole,
+            'kernels': kernels, 'cpu_baseline': cpu, 'finite': ok, 'gathered': gathered,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -8,33 +8,38 @@
 // A tile holds complete groups: group atom g = attention TARGET c, partner j = SOURCE r.
 // Per tile:  A0 = [GBF(d) | e]  --MMA1--> e1 --LN/modulate--> en  --MMA2--> g0 (TMEM 0..255)
 //                                                               --MMA3--> g1 (TMEM 256..511)
-//   logits (thread per row, k[j] . q[g] . tanh(g0)), softmax per group through shared memory,
+//   logits (k[j] . q[g] . tanh(g0)), softmax per group through shared memory,
 //   msg = v[j] * tanh(g1) * alpha, summed per group, written to hnode[g].
+//
+// 256 threads: warp w works on tile rows 32*(w&3)..+31 (its TMEM lane quarter) and on column half (w>>2) of every
+// row vector (32 of 64 edge features, 128 of 256 q/k/g0 columns = 7 of 14 heads, 128 of 256 value columns = 8 of 16
+// heads).  Each CTA walks a contiguous range of tiles so that the q/k/v rows of a molecule stay hot in L1/L2.
 #include "edge_common.cuh"
 
 namespace jodo {
 
 namespace {
 
-constexpr int AT_A0 = 0;                          // 64 KB: chunks 0,1 = GBF(d) then en; chunks 2,3 = e, later scratch
+constexpr int AT_THREADS = 256;
+constexpr int AT_A0 = 0;                          // 64 KB: chunks 0,1 = GBF(d) then en, later S; chunks 2,3 = e, later scratch
 constexpr int AT_WE = 65536;                      // 32 KB: block edge_emb image (N=64, K=128)
 constexpr int AT_W0 = AT_WE + 32768;              // 64 KB: lin_edge0 image (N=256, K=64)
 constexpr int AT_W1 = AT_W0 + 65536;              // 64 KB: lin_edge1 image
 constexpr int AT_MISC = AT_W1 + 65536;            // barriers, tmem slot, GBF constants, bias, group table
 constexpr int AT_SMEM = AT_MISC + 128 + 768 + 256 + 512 + 512;
-// scratch inside A0 chunks 2,3 (free once MMA1 has completed)
-constexpr int AT_LG = 32768;                      // logits [128][17] fp32
-constexpr int AT_GM = AT_LG + 128 * 17 * 4;       // group max  [128][16]
-constexpr int AT_GS = AT_GM + 128 * 16 * 4;       // group sum  [128][16]
-constexpr int AT_S = 32768;                       // message staging [128][33] fp32 (aliases LG/GM/GS)
-static_assert(AT_GS + 128 * 16 * 4 <= 65536, "softmax scratch overflows A0");
-static_assert(AT_S + 128 * 33 * 4 <= 65536, "staging overflows A0");
+// scratch inside A0 chunks 2,3 (free between the completion of MMA1 and the prefetch of the next e tile)
+constexpr int AT_LG = 32768;                      // logits / exp values [128][17] fp32
+constexpr int AT_GI = AT_LG + 128 * 17 * 4;       // 1 / (sum + 1e-16) per (group, head)  [128][16]
+constexpr int AT_LN = AT_GI + 128 * 16 * 4;       // LayerNorm partial sums [128][2] float2
+static_assert(AT_LN + 128 * 2 * 8 <= 65536, "softmax scratch overflows A0");
+// message staging inside A0 chunks 0,1 (free once MMA2/MMA3 completed): per column half [128 rows][32] fp32, xor-swizzled
+constexpr int AT_S = 0;
 static_assert(AT_SMEM <= 232448, "shared memory budget");
 
 constexpr int SC = 18;        // sub_channels = 256 // 14   (models/layers.py:112)
-constexpr int QK = 252;       // 14 * 18
+constexpr int HQ = 126;       // q/k/g0 columns of one half = 7 heads x 18
 
-__global__ void __launch_bounds__(ET, 1) k_attn(AttnArgs a) {
+__global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
   uint8_t* A0 = smem + AT_A0;
@@ -45,11 +50,18 @@ __global__ void __launch_bounds__(ET, 1) k_attn(AttnArgs a) {
   uint32_t* gt_meta = reinterpret_cast<uint32_t*>(bemb + 64);     // [128] group start | len << 8
   int* gt_node = reinterpret_cast<int*>(gt_meta + 128);           // [128] group atom
   float* LG = reinterpret_cast<float*>(smem + AT_LG);
-  float* GM = reinterpret_cast<float*>(smem + AT_GM);
-  float* GS = reinterpret_cast<float*>(smem + AT_GS);
-  float* S = reinterpret_cast<float*>(smem + AT_S);
+  float* GI = reinterpret_cast<float*>(smem + AT_GI);
+  float2* LNS = reinterpret_cast<float2*>(smem + AT_LN);
 
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int rq = warp & 3, half = warp >> 2;
+  const int row = rq * 32 + lane;
+  float* S = reinterpret_cast<float*>(smem + AT_S) + half * (128 * 32);
+
+  const int per = (a.p.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile0 = blockIdx.x * per;
+  const int tile1 = min(tile0 + per, a.p.n_tiles);
+
   if (t == 0) {
     for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
@@ -57,68 +69,75 @@ __global__ void __launch_bounds__(ET, 1) k_attn(AttnArgs a) {
     bulk_g2s(smem + AT_WE, a.w_emb_img, 32768, &bars[0]);
     bulk_g2s(smem + AT_W0, a.w0_img, 65536, &bars[0]);
     bulk_g2s(smem + AT_W1, a.w1_img, 65536, &bars[0]);
+    if (tile0 < tile1) {
+      mbar_expect_tx(&bars[1], E_TILE_BYTES);
+      bulk_g2s(A0 + 32768, reinterpret_cast<const uint8_t*>(a.e_in) + (size_t)tile0 * a.e_tile_bytes, E_TILE_BYTES, &bars[1]);
+    }
   }
-  for (int i = t; i < 192; i += ET) gbf[i] = a.gbf[i];
+  for (int i = t; i < 192; i += AT_THREADS) gbf[i] = a.gbf[i];
   if (t < 64) bemb[t] = a.b_emb[t];
-  if (t < 32) tmem_alloc<512>(tmem_slot);
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
   sync_tc();
   const uint32_t tmem = *tmem_slot;
-  uint32_t par_e = 0, par1 = 0, par2 = 0, par3 = 0;
-  bool first = true;
+  uint32_t par = 0;
   const float4* pos = reinterpret_cast<const float4*>(a.pos);
 
-  for (int tile = blockIdx.x; tile < a.p.n_tiles; tile += gridDim.x) {
-    const RowInfo r = load_row(a.p, tile, t);
+  for (int tile = tile0; tile < tile1; ++tile) {
+    const RowInfo r = load_row(a.p, tile, row);
     const int ng = a.p.tile_ngroups[tile];
-    if (r.valid && t == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
-    if (t == 0) {
-      mbar_expect_tx(&bars[1], E_TILE_BYTES);
-      bulk_g2s(A0 + 32768, reinterpret_cast<const uint8_t*>(a.e_in) + (size_t)tile * a.e_tile_bytes, E_TILE_BYTES, &bars[1]);
-    }
+    if (half == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
     const float* tr = a.tab + (size_t)r.mol * a.ld_tab + a.tab_off;
-    const uint8_t ex = a.extra[(size_t)tile * TILE_ROWS + t];
+    const uint8_t ex = a.extra[(size_t)tile * TILE_ROWS + row];
 
-    // ---- distance features -> A0 chunks 0,1
+    // ---- distance features -> A0 chunk `half`
     {
-      float df[64];
+      float df[32];
       if (r.valid) {
         const float d = sq_dist(pos[r.j], pos[r.g]);
-        gbf_eval(d, tr[tab_gbf(D_)], tr[tab_gbf(D_) + 1], gbf, df);
+        gbf_eval_half(d, tr[tab_gbf(D_)], tr[tab_gbf(D_) + 1], gbf, half, df);
       } else {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) df[i] = 0.f;
+        for (int i = 0; i < 32; ++i) df[i] = 0.f;
       }
-      st_row64<true>(A0, t, 0, df);
+      st_row32<true>(A0, row, half, df);
     }
     fence_async_smem();
     sync_tc();
     if (t == 0) {
-      if (first) mbar_wait(&bars[0], 0);
-      mbar_wait(&bars[1], par_e);
+      if (tile == tile0) mbar_wait(&bars[0], 0);
+      mbar_wait(&bars[1], par);
       tc_fence_after();
-      mma_tile(tmem, smem_u32(A0), smem_u32(smem + AT_WE), 64, 4, false);     // e1 = edge_emb([dist | e])
+      mma_tile(tmem + 256, smem_u32(A0), smem_u32(smem + AT_WE), 64, 4, false);     // e1 = edge_emb([dist | e])
       umma_commit(&bars[2]);
     }
-    first = false;
-    par_e ^= 1;
-    mbar_wait(&bars[2], par1);
-    par1 ^= 1;
+    mbar_wait(&bars[2], par);
     tc_fence_after();
 
-    // ---- en = LN(e1) * (1 + scale_msa) + shift_msa  -> A0 chunks 0,1
+    // ---- en = LN(e1) * (1 + scale_msa) + shift_msa  -> A0 chunk `half`   (e tile region is scratch from here on)
     {
-      float x[64];
-      float h0[32], h1[32];
-      tmem_ld32(tmem_addr(tmem, 0), h0);
-      tmem_ld32(tmem_addr(tmem, 32), h1);
+      float x[32];
+      tmem_ld32(tmem_addr(tmem, 256 + 32 * half), x);
+      float s = 0.f, q = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { x[i] = h0[i] + bemb[i]; x[32 + i] = h1[i] + bemb[32 + i]; }
-      ln_mod64(x, tr + tab_edge(D_), tr + tab_edge(D_) + ED_);
-      if (!r.valid) {
+      for (int i = 0; i < 32; ++i) { x[i] += bemb[32 * half + i]; s += x[i]; q = fmaf(x[i], x[i], q); }
+      LNS[row * 2 + half] = make_float2(s, q);
+      __syncthreads();
+      const float2 o = LNS[row * 2 + (half ^ 1)];
+      const float mean = (s + o.x) * (1.0f / 64.0f);
+      const float var = fmaxf((q + o.y) * (1.0f / 64.0f) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + 1e-6f);
+      const float* shift = tr + tab_edge(D_) + 32 * half;
+      const float* scale = shift + ED_;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) x[i] = 0.f;
+      for (int i = 0; i < 32; i += 4) {
+        const float4 sh = *reinterpret_cast<const float4*>(shift + i);
+        const float4 sc = *reinterpret_cast<const float4*>(scale + i);
+        x[i] = r.valid ? fmaf((x[i] - mean) * rstd, 1.0f + sc.x, sh.x) : 0.f;
+        x[i + 1] = r.valid ? fmaf((x[i + 1] - mean) * rstd, 1.0f + sc.y, sh.y) : 0.f;
+        x[i + 2] = r.valid ? fmaf((x[i + 2] - mean) * rstd, 1.0f + sc.z, sh.z) : 0.f;
+        x[i + 3] = r.valid ? fmaf((x[i + 3] - mean) * rstd, 1.0f + sc.w, sh.w) : 0.f;
       }
-      st_row64<true>(A0, t, 0, x);
+      st_row32<true>(A0, row, half, x);
     }
     fence_async_smem();
     sync_tc();
@@ -128,92 +147,114 @@ __global__ void __launch_bounds__(ET, 1) k_attn(AttnArgs a) {
       mma_tile(tmem + 256, smem_u32(A0), smem_u32(smem + AT_W1), 256, 2, false);  // g1 pre-activation
       umma_commit(&bars[4]);
     }
-    mbar_wait(&bars[3], par2);
-    par2 ^= 1;
+    mbar_wait(&bars[3], par);
     tc_fence_after();
 
-    // ---- logits: a[s] = sum_ch q[g,s,ch] k[j,s,ch] tanh(g0[s,ch]) / sqrt(16)
-    float lg[14];
-#pragma unroll
-    for (int s = 0; s < 14; ++s) lg[s] = 0.f;
+    // ---- logits of this half's 7 heads: a[s] = sum_ch q[g,s,ch] k[j,s,ch] tanh(g0[s,ch]) / sqrt(16)
     {
-      const float* qrow = a.qkv + (size_t)r.g * a.ldq;
-      const float* krow = a.qkv + (size_t)r.j * a.ldq + D_;
+      float lg[7];
+#pragma unroll
+      for (int s = 0; s < 7; ++s) lg[s] = 0.f;
+      const float* qrow = a.qkv + (size_t)r.g * a.ldq + 128 * half;
+      const float* krow = a.qkv + (size_t)r.j * a.ldq + D_ + 128 * half;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float acc[32];
-        tmem_ld32(tmem_addr(tmem, c * 32), acc);
+        float4 q4[4], k4[4];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const int col = c * 32 + i;
-          if (col < QK) {
-            const float4 q4 = *reinterpret_cast<const float4*>(qrow + col);
-            const float4 k4 = *reinterpret_cast<const float4*>(krow + col);
-            lg[col / SC] += q4.x * k4.x * tanh_f(acc[i]);
-            if (col + 1 < QK) lg[(col + 1) / SC] += q4.y * k4.y * tanh_f(acc[i + 1]);
-            if (col + 2 < QK) lg[(col + 2) / SC] += q4.z * k4.z * tanh_f(acc[i + 2]);
-            if (col + 3 < QK) lg[(col + 3) / SC] += q4.w * k4.w * tanh_f(acc[i + 3]);
-          }
+        for (int i = 0; i < 4; ++i) {
+          q4[i] = __ldg(reinterpret_cast<const float4*>(qrow + c * 16) + i);
+          k4[i] = __ldg(reinterpret_cast<const float4*>(krow + c * 16) + i);
+        }
+        float acc[16];
+        tmem_ld16(tmem_addr(tmem, 128 * half + c * 16), acc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = c * 16 + 4 * i;
+          if (col < HQ) lg[col / SC] = fmaf(q4[i].x * k4[i].x, tanh_fast(acc[4 * i]), lg[col / SC]);
+          if (col + 1 < HQ) lg[(col + 1) / SC] = fmaf(q4[i].y * k4[i].y, tanh_fast(acc[4 * i + 1]), lg[(col + 1) / SC]);
+          if (col + 2 < HQ) lg[(col + 2) / SC] = fmaf(q4[i].z * k4[i].z, tanh_fast(acc[4 * i + 2]), lg[(col + 2) / SC]);
+          if (col + 3 < HQ) lg[(col + 3) / SC] = fmaf(q4[i].w * k4[i].w, tanh_fast(acc[4 * i + 3]), lg[(col + 3) / SC]);
         }
       }
-    }
-    // extra heads first: 1 where adjacent, -1e10 otherwise (models/layers.py:170-174)
-    LG[t * 17 + 0] = (ex & 1) ? 1.0f : -1e10f;
-    LG[t * 17 + 1] = (ex & 2) ? 1.0f : -1e10f;
+      // head order of the reference: the two adjacency heads first (1 where adjacent, -1e10 otherwise,
+      // models/layers.py:170-174), then the 14 computed heads
+      LG[row * 17 + half] = ((ex >> half) & 1) ? 1.0f : -1e10f;
 #pragma unroll
-    for (int s = 0; s < 14; ++s) LG[t * 17 + 2 + s] = lg[s] * 0.25f;
+      for (int s = 0; s < 7; ++s) LG[row * 17 + 2 + 7 * half + s] = lg[s] * 0.25f;
+    }
     __syncthreads();
-    for (int it = t; it < ng * 16; it += ET) {       // (group, head) -> max and sum of exp over the group's rows
+    // (group, head): max, exp in place, 1 / (sum + 1e-16)      (PyG softmax, models/layers.py:178)
+    for (int it = t; it < ng * 16; it += AT_THREADS) {
       const int gi = it >> 4, h = it & 15;
       const int gs = gt_meta[gi] & 255u, gl = (gt_meta[gi] >> 8) & 255u;
       float m = -INFINITY;
       for (int rr = gs; rr < gs + gl; ++rr) m = fmaxf(m, LG[rr * 17 + h]);
       float s = 0.f;
-      for (int rr = gs; rr < gs + gl; ++rr) s += __expf(LG[rr * 17 + h] - m);
-      GM[gi * 16 + h] = m;
-      GS[gi * 16 + h] = s;
+      for (int rr = gs; rr < gs + gl; ++rr) {
+        const float e = ex2_fast((LG[rr * 17 + h] - m) * 1.4426950408889634f);
+        LG[rr * 17 + h] = e;
+        s += e;
+      }
+      GI[gi * 16 + h] = 1.0f / (s + 1e-16f);
     }
     __syncthreads();
-    float alpha[16];
+    float alpha[8];
 #pragma unroll
-    for (int h = 0; h < 16; ++h)
-      alpha[h] = r.valid ? __expf(LG[t * 17 + h] - GM[r.gi * 16 + h]) / (GS[r.gi * 16 + h] + 1e-16f) : 0.f;
-    __syncthreads();                                  // S aliases LG/GM/GS
+    for (int h = 0; h < 8; ++h) alpha[h] = r.valid ? LG[row * 17 + 8 * half + h] * GI[r.gi * 16 + 8 * half + h] : 0.f;
+    // groups whose first row lies in this warp's 32 rows are summed by this warp
+    const uint32_t starts = __ballot_sync(0xffffffffu, r.valid && row == r.gs);
+    fence_async_smem();
+    __syncthreads();                                  // the scratch in the e region is dead: prefetch the next e tile
+    if (t == 0 && tile + 1 < tile1) {
+      mbar_expect_tx(&bars[1], E_TILE_BYTES);
+      bulk_g2s(A0 + 32768, reinterpret_cast<const uint8_t*>(a.e_in) + (size_t)(tile + 1) * a.e_tile_bytes, E_TILE_BYTES, &bars[1]);
+    }
 
     // ---- messages and per-group sums
-    mbar_wait(&bars[4], par3);
-    par3 ^= 1;
+    mbar_wait(&bars[4], par);
     tc_fence_after();
     {
-      const float* vrow = a.qkv + (size_t)r.j * a.ldq + 2 * D_;
-      const int ch = t & 31, slot = t >> 5;
+      const float* vrow = a.qkv + (size_t)r.j * a.ldq + 2 * D_ + 128 * half;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float4 v4[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+        for (int i = 0; i < 8; ++i) v4[i] = __ldg(reinterpret_cast<const float4*>(vrow + c * 32) + i);
         float acc[32];
-        tmem_ld32(tmem_addr(tmem, 256 + c * 32), acc);
+        tmem_ld32(tmem_addr(tmem, 256 + 128 * half + c * 32), acc);
+        const float al0 = c == 0 ? alpha[0] : c == 1 ? alpha[2] : c == 2 ? alpha[4] : alpha[6];
+        const float al1 = c == 0 ? alpha[1] : c == 1 ? alpha[3] : c == 2 ? alpha[5] : alpha[7];
+        float* srow = S + row * 32;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 v4 = *reinterpret_cast<const float4*>(vrow + c * 32 + i);
-          const float al = alpha[(c * 32 + i) / 16];
-          S[t * 33 + i] = v4.x * tanh_f(acc[i]) * al;
-          S[t * 33 + i + 1] = v4.y * tanh_f(acc[i + 1]) * al;
-          S[t * 33 + i + 2] = v4.z * tanh_f(acc[i + 2]) * al;
-          S[t * 33 + i + 3] = v4.w * tanh_f(acc[i + 3]) * al;
+        for (int i = 0; i < 8; ++i) {
+          const float al = i < 4 ? al0 : al1;
+          srow[(4 * i) ^ lane] = v4[i].x * tanh_fast(acc[4 * i]) * al;
+          srow[(4 * i + 1) ^ lane] = v4[i].y * tanh_fast(acc[4 * i + 1]) * al;
+          srow[(4 * i + 2) ^ lane] = v4[i].z * tanh_fast(acc[4 * i + 2]) * al;
+          srow[(4 * i + 3) ^ lane] = v4[i].w * tanh_fast(acc[4 * i + 3]) * al;
         }
-        __syncthreads();
-        for (int gi = slot; gi < ng; gi += 4) {
-          const int gs = gt_meta[gi] & 255u, gl = (gt_meta[gi] >> 8) & 255u;
+        named_bar_sync(1 + half, 128);
+        uint32_t m = starts;
+        while (m) {
+          const int r0 = __ffs(m) - 1;
+          m &= m - 1;
+          const int gl = __shfl_sync(0xffffffffu, r.gl, r0);
+          const int node = __shfl_sync(0xffffffffu, r.g, r0);
+          const int R0 = rq * 32 + r0;
           float sum = 0.f;
-          for (int rr = gs; rr < gs + gl; ++rr) sum += S[rr * 33 + ch];
-          a.hnode[(size_t)gt_node[gi] * D_ + c * 32 + ch] = sum;
+          for (int rr = R0; rr < R0 + gl; ++rr) sum += S[rr * 32 + (lane ^ (rr & 31))];
+          a.hnode[(size_t)node * D_ + 128 * half + c * 32 + lane] = sum;
         }
-        __syncthreads();
+        named_bar_sync(1 + half, 128);
       }
     }
-    fence_async_smem();        // scratch written above is overwritten by the next tile's bulk copy
+    fence_async_smem();        // S is overwritten by the next tile's operand rows
     sync_tc();
+    par ^= 1;
   }
-  if (t < 32) tmem_dealloc<512>(tmem);
+  if (tile0 >= tile1 && t == 0) mbar_wait(&bars[0], 0);   // never leave with bulk copies in flight
+  sync_tc();
+  if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace
@@ -226,7 +267,7 @@ cudaError_t launch_attn(const AttnArgs& a, int num_sms, cudaStream_t st) {
     attr = true;
   }
   const int grid = a.p.n_tiles < num_sms ? a.p.n_tiles : num_sms;
-  k_attn<<<grid, ET, AT_SMEM, st>>>(a);
+  k_attn<<<grid, AT_THREADS, AT_SMEM, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -71,14 +71,29 @@ __device__ __forceinline__ void st_row32(uint8_t* img, int row, int kc, const fl
 }
 
 // CondGaussianLayer (reference models/layers.py:291-295,328-334): x = d*(1+scale)+shift;
-// out = [x, exp(-0.5((x-mu_k)/sg_k)^2) / (a*sg_k)], k < 63.  c = {mu[64], 1/sg[64], 1/(a*sg)[64]} (packer).
+// out = [x, exp(-0.5((x-mu_k)/sg_k)^2) / (a*sg_k)], k < 63.
+// c = {mu[64], sqrt(0.5*log2(e))/sg[64], 1/(a*sg)[64]} (packer), so that exp(-0.5 z^2) = 2^(-(w*w)), w = (x-mu)*c1.
+__device__ __forceinline__ float gbf_one(float x, const float* __restrict__ c, int k) {
+  const float w = (x - c[k]) * c[64 + k];
+  return ex2_fast(-(w * w)) * c[128 + k];
+}
 __device__ __forceinline__ void gbf_eval(float d, float scale, float shift, const float* __restrict__ c, float (&out)[64]) {
-  const float x = d * (scale + 1.0f) + shift;
+  const float x = fmaf(d, scale, d) + shift;
   out[0] = x;
 #pragma unroll
-  for (int k = 0; k < 63; ++k) {
-    const float z = (x - c[k]) * c[64 + k];
-    out[1 + k] = __expf(-0.5f * z * z) * c[128 + k];
+  for (int k = 0; k < 63; ++k) out[1 + k] = gbf_one(x, c, k);
+}
+// columns [32*half, 32*half + 32) of the same feature row (two threads share one edge row)
+__device__ __forceinline__ void gbf_eval_half(float d, float scale, float shift, const float* __restrict__ c, int half,
+                                              float (&out)[32]) {
+  const float x = fmaf(d, scale, d) + shift;
+  if (half == 0) {
+    out[0] = x;
+#pragma unroll
+    for (int k = 0; k < 31; ++k) out[1 + k] = gbf_one(x, c, k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) out[k] = gbf_one(x, c, 31 + k);
   }
 }
 

@@ -100,8 +100,20 @@ class Packed:
         return self.buf.data_ptr() + 4 * self._off[name][0]
 
 
+def split_heads(w, D, qk):
+    """Rows [qk, ...] of lin_query / lin_key / lin_edge0 -> [D, ...]: heads 0..S/2-1 at rows [0, qk/2), heads
+    S/2..S-1 at rows [D/2, D/2 + qk/2), zeros elsewhere, so that each half of the attention CTA (csrc/attn.cu) owns
+    one 128-column half of the q / k / g0 rows."""
+    h = qk // 2
+    out = torch.zeros((D,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+    out[:h] = w[:h]
+    out[D // 2:D // 2 + h] = w[h:]
+    return out
+
+
 def _gbf_consts(sd, prefix, dev):
-    """{mu, 1/sg, 1/(a sg)} x 64 with the reference's fp32 arithmetic (models/layers.py:291-295,332-333)."""
+    """{mu, sqrt(0.5 log2 e)/sg, 1/(a sg)} x 64 from the reference's fp32 mu / sg (models/layers.py:291-295,332-333):
+    exp(-0.5 ((x-mu)/sg)^2) / (a sg) = 2^(-((x-mu) c1)^2) * c2."""
     mu = sd[prefix + '.means.weight'].float().view(-1)
     sg = sd[prefix + '.stds.weight'].float().view(-1).abs() + 1e-5
     a = (2 * 3.14159) ** 0.5
@@ -109,7 +121,7 @@ def _gbf_consts(sd, prefix, dev):
     out = torch.zeros(192, device=dev)
     k = mu.numel()
     out[0:k] = mu
-    out[64:64 + k] = 1.0 / sg
+    out[64:64 + k] = (0.5 * 1.4426950408889634) ** 0.5 / sg
     out[128:128 + k] = 1.0 / asg
     return out
 
@@ -202,8 +214,10 @@ def pack_model(sd, dims, device):
         p = f'b{l}.'
         wq = z(3 * D, D)
         bq = z(3 * D)
-        wq[:d.qk], bq[:d.qk] = W(f'{b}.attn_mpnn.lin_query'), Bv(f'{b}.attn_mpnn.lin_query')
-        wq[D:D + d.qk], bq[D:D + d.qk] = W(f'{b}.attn_mpnn.lin_key'), Bv(f'{b}.attn_mpnn.lin_key')
+        wq[:D], bq[:D] = (split_heads(W(f'{b}.attn_mpnn.lin_query'), D, d.qk),
+                          split_heads(Bv(f'{b}.attn_mpnn.lin_query'), D, d.qk))
+        wq[D:2 * D], bq[D:2 * D] = (split_heads(W(f'{b}.attn_mpnn.lin_key'), D, d.qk),
+                                    split_heads(Bv(f'{b}.attn_mpnn.lin_key'), D, d.qk))
         wq[2 * D:], bq[2 * D:] = W(f'{b}.attn_mpnn.lin_value'), Bv(f'{b}.attn_mpnn.lin_value')
         add_lin(p + 'qkv', wq, bq, 256)
         add_lin(p + 'n2e', W(f'{b}.node2edge_lin'), None, 64)
@@ -216,7 +230,7 @@ def pack_model(sd, dims, device):
         pk.add(p + 'gbf', _gbf_consts(sd, f'{b}.dist_layer', device))
         pk.add(p + 'emb.img', weight_image(W(f'{b}.edge_emb'), ed))                       # [64, 128]: [dist | e]
         pk.add(p + 'emb.b', Bv(f'{b}.edge_emb'))
-        pk.add(p + 'e0.img', weight_image(pad2(W(f'{b}.attn_mpnn.lin_edge0'), D, ed), D))
+        pk.add(p + 'e0.img', weight_image(split_heads(W(f'{b}.attn_mpnn.lin_edge0'), D, d.qk), D))
         pk.add(p + 'e1.img', weight_image(W(f'{b}.attn_mpnn.lin_edge1'), D))
         w3, w4 = W(f'{b}.ff_linear3'), W(f'{b}.ff_linear4')    # [ed r, ed], [ed, ed r]
         pk.add(p + 'ff3.img', weight_image(w3, ed))
