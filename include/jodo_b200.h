@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 1
+#define JODO_ABI_VERSION 2
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -64,64 +64,71 @@ typedef struct jodo_plan {
   const int* tile_ngroups;               /* [n_tiles] */
 } jodo_plan;
 
+/* Edge state between kernels (per tile of 128 rows):
+ *   e32  fp32 master copy, image [2 chunks][128 rows][32 cols] (32 KB per tile) -- the residual stream, read and
+ *        rewritten in place by jodo_edge_update;
+ *   e16  fp16 operand copy, image [128 rows][64 cols] (16 KB per tile) -- what the tensor-core kernels load;
+ *   eh   fp16 image of the concatenated edge hiddens [keh/64 chunks][128][64]: chunk 0 = model-level embedding,
+ *        then ce columns per block (edge_i projections), consumed by jodo_edge_head.
+ * fp16 operands carry the same 10-bit mantissa as tf32 ones (values beyond +-65504 saturate). */
 typedef struct jodo_edge_embed_args {                    /* model-level edge embedding (reference models/mol_gnn.py:517-557) */
   jodo_plan p;
   const float* edge_x; const float* cond_edge_x; const float* cond_x;   /* dense inputs; cond_* null on the first call */
   int ch, inn; float edge_th, spatial_cut;
   int* dist_flag;                         /* device int, set by the kernel's first phase: any cond distance != 0 */
   const float* tab; int ld_tab;           /* per-molecule tables (model-level GBF scale/shift at [0],[1]) */
-  const float* gbf;                       /* GBF constants {mu, 1/sg, 1/(a sg)} x 64 */
-  const float* w_img; const float* bias;  /* edge_emb image (N=64, K=96: [dist 64 | edge_x | cond_edge_x | 0]), bias[64] */
-  float* eh_img; size_t eh_tile_bytes;    /* out: columns [0,64) of the concatenated edge-hidden image */
+  const float* gbf;                       /* GBF constants {mu, c1, c2} x 64 */
+  const float* w_img; const float* bias;  /* edge_emb tf32 image (N=64, K=96: [dist 64 | edge_x | cond_edge_x | 0]), bias[64] */
+  float* e32; void* e16;                  /* out: edge state */
+  void* eh; size_t eh_tile_bytes;         /* out: chunk 0 of the edge-hidden image */
   uint8_t* extra;                         /* out: [R] bit0 = 2-D adjacency head, bit1 = spatial adjacency head */
 } jodo_edge_embed_args;
 
 typedef struct jodo_attn_args {                         /* TransMixLayer on edge tiles (reference models/layers.py:131-186) */
   jodo_plan p;
-  const float* e_in; size_t e_tile_bytes; /* block input edge features (tile images, 64 columns) */
+  const void* e16;                        /* block input edge features */
   const float* pos;                       /* [Nn] float4 */
-  const float* qkv; int ldq;              /* [Nn, 3D]: q | k | v of LN-modulated atoms */
+  const float* qkv; int ldq;              /* [Nn, 3D]: q | k | v of LN-modulated atoms (q, k in split-head layout) */
   const float* tab; int ld_tab; int tab_off;   /* table base of this layer */
   const uint8_t* extra;
   const float* gbf;                       /* this layer's GBF constants */
-  const float* w_emb_img; const float* b_emb;  /* block edge_emb (N=64, K=128: [dist | e]) */
-  const float* w0_img; const float* w1_img;    /* lin_edge0 (N=256 padded, K=64), lin_edge1 (N=256, K=64) */
+  const void* w_emb_img; const float* b_emb;   /* block edge_emb fp16 image (N=64, K=128: [dist | e]) */
+  const void* w0_img; const void* w1_img;      /* lin_edge0 (N=256 split-head, K=64), lin_edge1 (N=256, K=64), fp16 */
   float* hnode;                           /* out [Nn, 256] */
 } jodo_attn_args;
 
 typedef struct jodo_edge_update_args {                   /* edge residual + FFN + edge_l (reference models/mol_gnn.py:304-305,313-317,568) */
   jodo_plan p;
-  const float* e_in; size_t e_tile_bytes;
-  float* e_out;                           /* tile images, 32 KB per tile */
+  float* e32; void* e16;                  /* in/out fp32 state (in place), out fp16 copy */
   const float* P; int ldp;                /* [Nn, 64] node2edge_lin(hnode) without bias */
   const float* b_n2e;                     /* [64] */
   const float* tab; int ld_tab; int tab_off;
-  int r;                                  /* mlp_ratio: hidden = 64 r, processed in chunks of 64 */
-  const float* w3_img; const float* b3;   /* r images (N=64, K=64), bias [64 r] */
-  const float* w4_img; const float* b4;   /* r images (N=64, K=64), bias [64] */
-  const float* wl_img; const float* bl;   /* edge_l image (N=16, K=64), bias [16] */
-  float* eh_img; size_t eh_tile_bytes; int eh_col; int ce;   /* out: columns [eh_col, eh_col+ce) of the edge-hidden image */
+  int r;                                  /* mlp_ratio: hidden = 64 r */
+  const void* w3_img; const float* b3;    /* fp16 image (N=64 r, K=64), bias [64 r] */
+  const void* w4_img; const float* b4;    /* fp16 image (N=64, K=64 r), bias [64] */
+  const void* wl_img; const float* bl;    /* edge_l fp16 image (N=16, K=64), bias [16] */
+  void* eh; size_t eh_tile_bytes; int eh_col; int ce;   /* out: columns [eh_col, eh_col+ce) of the edge-hidden image */
 } jodo_edge_update_args;
 
 typedef struct jodo_equi_args {                         /* MultiCondEquiUpdate (reference models/mol_gnn.py:71-94) */
   jodo_plan p;
-  const float* e; size_t e_tile_bytes;    /* updated edge features */
+  const void* e16;                        /* updated edge features */
   const float* pos_in; float* pos_out;    /* [Nn] float4 */
   const float* AB; int ldab;              /* [Nn, >=512]: input_lin[:, :D] h | input_lin[:, D:2D] h */
   const float* tab; int ld_tab; int tab_off;
   const uint8_t* extra;
   const float* gbf;
-  const float* win_img; const float* b_in;     /* input_lin edge part (N=256, K=128: [e | dist]), bias [256] */
-  const float* wc0_img; const float* b_c0;     /* coord_mlp.0 (N=256, K=256) as 8 K-chunks of 32 KB, bias [256] */
+  const void* win_img; const float* b_in;      /* input_lin edge part fp16 image (N=256, K=128: [e | dist]), bias [256] */
+  const void* wc0_img; const float* b_c0;      /* coord_mlp.0 fp16 image (N=256, K=256), bias [256] */
   const float* wc2;                            /* coord_mlp.2 [3, 256] */
   float coord_scale;                           /* CoorsNorm.scale */
 } jodo_equi_args;
 
 typedef struct jodo_edge_head_args {                     /* edge_exist_mlp | edge_type_mlp (reference models/mol_gnn.py:466-479,574-578) */
   jodo_plan p;
-  const float* eh_img; size_t eh_tile_bytes; int keh;    /* concatenated edge hiddens (keh = 192) */
-  const float* w0_img; const float* b0;   /* [exist.0 ; type.0]  (N=128, K=keh) */
-  const float* w2_img; const float* b2;   /* block-diag [exist.2 ; type.2] (N=64, K=128) */
+  const void* eh; size_t eh_tile_bytes; int keh;         /* concatenated edge hiddens (keh = 192) */
+  const void* w0_img; const float* b0;    /* [exist.0 ; type.0]  fp16 image (N=128, K=keh) */
+  const void* w2_img; const float* b2;    /* block-diag [exist.2 ; type.2] fp16 image (N=64, K=128) */
   const float* w4; const float* b4;       /* [ch, 32] rows: exist.4, type.4...; bias [ch] */
   int ch;
   float* out_dense;                       /* [B,N,N,ch], zero-filled by the caller */

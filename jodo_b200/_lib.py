@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 1:
+        if _lib.jodo_abi_version() != 2:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -99,30 +99,30 @@ class PlanStruct(ctypes.Structure):
 class EdgeEmbedArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('edge_x', _P), ('cond_edge_x', _P), ('cond_x', _P), ('ch', _I), ('inn', _I),
                 ('edge_th', _F), ('spatial_cut', _F), ('dist_flag', _P), ('tab', _P), ('ld_tab', _I), ('gbf', _P),
-                ('w_img', _P), ('bias', _P), ('eh_img', _P), ('eh_tile_bytes', _Z), ('extra', _P)]
+                ('w_img', _P), ('bias', _P), ('e32', _P), ('e16', _P), ('eh', _P), ('eh_tile_bytes', _Z), ('extra', _P)]
 
 
 class AttnArgs(ctypes.Structure):
-    _fields_ = [('p', PlanStruct), ('e_in', _P), ('e_tile_bytes', _Z), ('pos', _P), ('qkv', _P), ('ldq', _I),
+    _fields_ = [('p', PlanStruct), ('e16', _P), ('pos', _P), ('qkv', _P), ('ldq', _I),
                 ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P), ('gbf', _P), ('w_emb_img', _P),
                 ('b_emb', _P), ('w0_img', _P), ('w1_img', _P), ('hnode', _P)]
 
 
 class EdgeUpdateArgs(ctypes.Structure):
-    _fields_ = [('p', PlanStruct), ('e_in', _P), ('e_tile_bytes', _Z), ('e_out', _P), ('P', _P), ('ldp', _I),
+    _fields_ = [('p', PlanStruct), ('e32', _P), ('e16', _P), ('P', _P), ('ldp', _I),
                 ('b_n2e', _P), ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('r', _I), ('w3_img', _P), ('b3', _P),
-                ('w4_img', _P), ('b4', _P), ('wl_img', _P), ('bl', _P), ('eh_img', _P), ('eh_tile_bytes', _Z),
+                ('w4_img', _P), ('b4', _P), ('wl_img', _P), ('bl', _P), ('eh', _P), ('eh_tile_bytes', _Z),
                 ('eh_col', _I), ('ce', _I)]
 
 
 class EquiArgs(ctypes.Structure):
-    _fields_ = [('p', PlanStruct), ('e', _P), ('e_tile_bytes', _Z), ('pos_in', _P), ('pos_out', _P), ('AB', _P),
+    _fields_ = [('p', PlanStruct), ('e16', _P), ('pos_in', _P), ('pos_out', _P), ('AB', _P),
                 ('ldab', _I), ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P), ('gbf', _P),
                 ('win_img', _P), ('b_in', _P), ('wc0_img', _P), ('b_c0', _P), ('wc2', _P), ('coord_scale', _F)]
 
 
 class EdgeHeadArgs(ctypes.Structure):
-    _fields_ = [('p', PlanStruct), ('eh_img', _P), ('eh_tile_bytes', _Z), ('keh', _I), ('w0_img', _P), ('b0', _P),
+    _fields_ = [('p', PlanStruct), ('eh', _P), ('eh_tile_bytes', _Z), ('keh', _I), ('w0_img', _P), ('b0', _P),
                 ('w2_img', _P), ('b2', _P), ('w4', _P), ('b4', _P), ('ch', _I), ('out_dense', _P)]
 
 

@@ -8,6 +8,7 @@
 // A tile holds complete groups: group atom g = attention TARGET c, partner j = SOURCE r.
 // Per tile:  A0 = [GBF(d) | e]  --MMA1--> e1 --LN/modulate--> en  --MMA2--> g0 (TMEM 0..255)
 //                                                               --MMA3--> g1 (TMEM 256..511)
+//   (fp16 operand images, fp32 accumulation: same mantissa as tf32 at half the shared memory and twice the rate)
 //   logits (k[j] . q[g] . tanh(g0)), softmax per group through shared memory,
 //   msg = v[j] * tanh(g1) * alpha, summed per group, written to hnode[g].
 //
@@ -21,19 +22,16 @@ namespace jodo {
 namespace {
 
 constexpr int AT_THREADS = 256;
-constexpr int AT_A0 = 0;                          // 64 KB: chunks 0,1 = GBF(d) then en, later S; chunks 2,3 = e, later scratch
-constexpr int AT_WE = 65536;                      // 32 KB: block edge_emb image (N=64, K=128)
-constexpr int AT_W0 = AT_WE + 32768;              // 64 KB: lin_edge0 image (N=256, K=64)
-constexpr int AT_W1 = AT_W0 + 65536;              // 64 KB: lin_edge1 image
-constexpr int AT_MISC = AT_W1 + 65536;            // barriers, tmem slot, GBF constants, bias, group table
-constexpr int AT_SMEM = AT_MISC + 128 + 768 + 256 + 512 + 512;
-// scratch inside A0 chunks 2,3 (free between the completion of MMA1 and the prefetch of the next e tile)
-constexpr int AT_LG = 32768;                      // logits / exp values [128][17] fp32
+constexpr int AT_A0 = 0;                          // 32 KB fp16: chunk 0 = GBF(d) then en; chunk 1 = e (bulk-copied)
+constexpr int AT_WE = 32768;                      // 16 KB: block edge_emb image (N=64, K=128)
+constexpr int AT_W0 = AT_WE + 16384;              // 32 KB: lin_edge0 image (N=256, K=64)
+constexpr int AT_W1 = AT_W0 + 32768;              // 32 KB: lin_edge1 image
+constexpr int AT_S = AT_W1 + 32768;               // 32 KB: message staging, per column half [128 rows][32] fp32, xor-swizzled
+constexpr int AT_LG = AT_S + 32768;               // logits / exp values [128][17] fp32
 constexpr int AT_GI = AT_LG + 128 * 17 * 4;       // 1 / (sum + 1e-16) per (group, head)  [128][16]
 constexpr int AT_LN = AT_GI + 128 * 16 * 4;       // LayerNorm partial sums [128][2] float2
-static_assert(AT_LN + 128 * 2 * 8 <= 65536, "softmax scratch overflows A0");
-// message staging inside A0 chunks 0,1 (free once MMA2/MMA3 completed): per column half [128 rows][32] fp32, xor-swizzled
-constexpr int AT_S = 0;
+constexpr int AT_MISC = AT_LN + 128 * 2 * 8;      // barriers, tmem slot, GBF constants, bias, group table
+constexpr int AT_SMEM = AT_MISC + 128 + 768 + 256 + 512 + 512;
 static_assert(AT_SMEM <= 232448, "shared memory budget");
 
 constexpr int SC = 18;        // sub_channels = 256 // 14   (models/layers.py:112)
@@ -65,13 +63,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
   if (t == 0) {
     for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
-    mbar_expect_tx(&bars[0], 32768 + 65536 + 65536);
-    bulk_g2s(smem + AT_WE, a.w_emb_img, 32768, &bars[0]);
-    bulk_g2s(smem + AT_W0, a.w0_img, 65536, &bars[0]);
-    bulk_g2s(smem + AT_W1, a.w1_img, 65536, &bars[0]);
+    mbar_expect_tx(&bars[0], 16384 + 32768 + 32768);
+    bulk_g2s(smem + AT_WE, a.w_emb_img, 16384, &bars[0]);
+    bulk_g2s(smem + AT_W0, a.w0_img, 32768, &bars[0]);
+    bulk_g2s(smem + AT_W1, a.w1_img, 32768, &bars[0]);
     if (tile0 < tile1) {
-      mbar_expect_tx(&bars[1], E_TILE_BYTES);
-      bulk_g2s(A0 + 32768, reinterpret_cast<const uint8_t*>(a.e_in) + (size_t)tile0 * a.e_tile_bytes, E_TILE_BYTES, &bars[1]);
+      mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
+      bulk_g2s(A0 + CHUNK_BYTES_A, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)tile0 * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
     }
   }
   for (int i = t; i < 192; i += AT_THREADS) gbf[i] = a.gbf[i];
@@ -89,7 +87,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
     const float* tr = a.tab + (size_t)r.mol * a.ld_tab + a.tab_off;
     const uint8_t ex = a.extra[(size_t)tile * TILE_ROWS + row];
 
-    // ---- distance features -> A0 chunk `half`
+    // ---- distance features -> A0 chunk 0, columns [32*half, 32*half+32)
     {
       float df[32];
       if (r.valid) {
@@ -99,7 +97,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) df[i] = 0.f;
       }
-      st_row32<true>(A0, row, half, df);
+      st_rowh<32>(A0, row, 0, 4 * half, df);
     }
     fence_async_smem();
     sync_tc();
@@ -107,13 +105,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
       if (tile == tile0) mbar_wait(&bars[0], 0);
       mbar_wait(&bars[1], par);
       tc_fence_after();
-      mma_tile(tmem + 256, smem_u32(A0), smem_u32(smem + AT_WE), 64, 4, false);     // e1 = edge_emb([dist | e])
+      mma_tile_h(tmem + 256, smem_u32(A0), smem_u32(smem + AT_WE), 64, 2, false);     // e1 = edge_emb([dist | e])
       umma_commit(&bars[2]);
     }
     mbar_wait(&bars[2], par);
     tc_fence_after();
+    if (t == 0 && tile + 1 < tile1) {                  // the e chunk is consumed: prefetch the next tile's
+      mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
+      bulk_g2s(A0 + CHUNK_BYTES_A, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 1) * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
+    }
 
-    // ---- en = LN(e1) * (1 + scale_msa) + shift_msa  -> A0 chunk `half`   (e tile region is scratch from here on)
+    // ---- en = LN(e1) * (1 + scale_msa) + shift_msa  -> A0 chunk 0
     {
       float x[32];
       tmem_ld32(tmem_addr(tmem, 256 + 32 * half), x);
@@ -137,14 +139,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
         x[i + 2] = r.valid ? fmaf((x[i + 2] - mean) * rstd, 1.0f + sc.z, sh.z) : 0.f;
         x[i + 3] = r.valid ? fmaf((x[i + 3] - mean) * rstd, 1.0f + sc.w, sh.w) : 0.f;
       }
-      st_row32<true>(A0, row, half, x);
+      st_rowh<32>(A0, row, 0, 4 * half, x);
     }
     fence_async_smem();
     sync_tc();
     if (t == 0) {
-      mma_tile(tmem, smem_u32(A0), smem_u32(smem + AT_W0), 256, 2, false);        // g0 pre-activation
+      mma_tile_h(tmem, smem_u32(A0), smem_u32(smem + AT_W0), 256, 1, false);        // g0 pre-activation
       umma_commit(&bars[3]);
-      mma_tile(tmem + 256, smem_u32(A0), smem_u32(smem + AT_W1), 256, 2, false);  // g1 pre-activation
+      mma_tile_h(tmem + 256, smem_u32(A0), smem_u32(smem + AT_W1), 256, 1, false);  // g1 pre-activation
       umma_commit(&bars[4]);
     }
     mbar_wait(&bars[3], par);
@@ -203,12 +205,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
     for (int h = 0; h < 8; ++h) alpha[h] = r.valid ? LG[row * 17 + 8 * half + h] * GI[r.gi * 16 + 8 * half + h] : 0.f;
     // groups whose first row lies in this warp's 32 rows are summed by this warp
     const uint32_t starts = __ballot_sync(0xffffffffu, r.valid && row == r.gs);
-    fence_async_smem();
-    __syncthreads();                                  // the scratch in the e region is dead: prefetch the next e tile
-    if (t == 0 && tile + 1 < tile1) {
-      mbar_expect_tx(&bars[1], E_TILE_BYTES);
-      bulk_g2s(A0 + 32768, reinterpret_cast<const uint8_t*>(a.e_in) + (size_t)(tile + 1) * a.e_tile_bytes, E_TILE_BYTES, &bars[1]);
-    }
 
     // ---- messages and per-group sums
     mbar_wait(&bars[4], par);
@@ -248,7 +244,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
         named_bar_sync(1 + half, 128);
       }
     }
-    fence_async_smem();        // S is overwritten by the next tile's operand rows
     sync_tc();
     par ^= 1;
   }

@@ -101,12 +101,15 @@ int jodo_attn(const jodo_attn_args* a, void* stream) {
   if (!a) return fail("jodo_attn: null args");
   if (const char* m = check_plan(a->p)) return fail(m);
   if (a->ldq % 4 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_attn: strides must be multiples of 4");
+  if (!a->e16 || !a->hnode) return fail("jodo_attn: null buffer");
   JODO_LAUNCH(jodo::launch_attn(*a, num_sms(), S(stream)), "jodo_attn");
 }
 int jodo_edge_update(const jodo_edge_update_args* a, void* stream) {
   if (!a) return fail("jodo_edge_update: null args");
   if (const char* m = check_plan(a->p)) return fail(m);
   if (a->ldp % 4 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_edge_update: strides must be multiples of 4");
+  if (!a->e32 || !a->e16 || !a->eh) return fail("jodo_edge_update: null buffer");
+  if (a->eh_col < 0 || a->eh_col + a->ce > 192) return fail("jodo_edge_update: edge-hidden slice out of range");
   JODO_LAUNCH(jodo::launch_edge_update(*a, num_sms(), S(stream)), "jodo_edge_update");
 }
 int jodo_equi(const jodo_equi_args* a, void* stream) {

@@ -225,6 +225,47 @@ __device__ __forceinline__ void mma_tile(uint32_t tmem_d, uint32_t a_saddr, uint
   }
 }
 
+// ---------------------------------------------------------------- fp16 operands (kind::f16)
+// fp16 has the same 10-bit mantissa as tf32, so an fp16 operand rounds exactly like a tf32 one but takes half the
+// shared memory and runs the tensor core at twice the rate; values beyond +-65504 saturate (cvt .satfinite).
+// fp16 operand image: same K-major SWIZZLE_128B layout, a chunk is 64 columns (128 bytes per row).
+//   [4,6) c_format=1(F32) | [7,10) a_format=0(F16) | [10,13) b_format=0 | [17,23) N>>3 | [24,29) M>>4
+__device__ __host__ constexpr uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// D[128 x N] (TMEM, fp32) (+)= A[128 x 64*nchunks] * W[N x 64*nchunks]^T, fp16 operand images in shared memory
+// (A chunks CHUNK_BYTES_A apart, W chunks N*128 bytes apart).  One thread calls this.
+__device__ __forceinline__ void mma_tile_h(uint32_t tmem_d, uint32_t a_saddr, uint32_t w_saddr, int n, int nchunks,
+                                           bool accumulate) {
+  const uint32_t idesc = umma_idesc_f16(n);
+  uint32_t acc = accumulate ? 1u : 0u;
+  for (int kc = 0; kc < nchunks; ++kc) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {   // 4 x (K=16 fp16 = 32 bytes) per 128-byte swizzle line
+      uint64_t ad = umma_desc_sw128(a_saddr + kc * CHUNK_BYTES_A + kk * 32);
+      uint64_t bd = umma_desc_sw128(w_saddr + kc * (n * 128) + kk * 32);
+      umma_f16(tmem_d, ad, bd, idesc, acc);
+      acc = 1u;
+    }
+  }
+}
+// two fp32 -> packed fp16x2 (lo in bits [0,16)), round to nearest, saturating
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // TMEM address of (lane base of this warp, column)
 __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int col) {
   return base + (((uint32_t)(threadIdx.x >> 5) & 3u) << 21) + (uint32_t)col;   // (warp%4)*32 lanes << 16

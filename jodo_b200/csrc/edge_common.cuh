@@ -70,6 +70,30 @@ __device__ __forceinline__ void st_row32(uint8_t* img, int row, int kc, const fl
   }
 }
 
+// ---- fp16 operand rows: NH consecutive groups of 8 columns (16-byte pieces) starting at piece p0 of chunk kc
+template <int N>
+__device__ __forceinline__ void st_rowh(uint8_t* img, int row, int kc, int p0, const float (&v)[N]) {
+  static_assert(N % 8 == 0, "whole 16-byte pieces");
+#pragma unroll
+  for (int p = 0; p < N / 8; ++p) {
+    uint4 o;
+    o.x = pack_h2(v[8 * p], v[8 * p + 1]);
+    o.y = pack_h2(v[8 * p + 2], v[8 * p + 3]);
+    o.z = pack_h2(v[8 * p + 4], v[8 * p + 5]);
+    o.w = pack_h2(v[8 * p + 6], v[8 * p + 7]);
+    const int pp = p0 + p;
+    *reinterpret_cast<uint4*>(img + img_piece(row, kc + (pp >> 3), pp & 7, CHUNK_BYTES_A)) = o;
+  }
+}
+// 32 consecutive fp32 columns [32*hh, 32*hh+32) of row `row` of a [128 x 64] fp32 image (2 chunks of 32 columns)
+__device__ __forceinline__ void ld_row32(const uint8_t* img, int row, int kc, float (&v)[32]) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const float4 o = *reinterpret_cast<const float4*>(img + img_piece(row, kc, p, CHUNK_BYTES_A));
+    v[4 * p] = o.x; v[4 * p + 1] = o.y; v[4 * p + 2] = o.z; v[4 * p + 3] = o.w;
+  }
+}
+
 // CondGaussianLayer (reference models/layers.py:291-295,328-334): x = d*(1+scale)+shift;
 // out = [x, exp(-0.5((x-mu_k)/sg_k)^2) / (a*sg_k)], k < 63.
 // c = {mu[64], sqrt(0.5*log2(e))/sg[64], 1/(a*sg)[64]} (packer), so that exp(-0.5 z^2) = 2^(-(w*w)), w = (x-mu)*c1.

@@ -7,203 +7,230 @@
 // The sum runs over the partners of `row`, so here the group atom g is ROW r and the partner j is COL c
 // (same stored rows as the attention pass, roles swapped; edge features are symmetric).
 // input_lin is hoisted: W[:, :D] h[g] + W[:, D:2D] h[j] come from the per-atom buffer AB, only the
-// [e | dist] part (K = 128) runs per edge.  coord_mlp.0 (256x256) is streamed in 8 K-chunks of 32 KB.
+// [e | dist] part (K = 128) runs per edge.
+//
+// fp16 operand images (same mantissa as tf32).  coord_mlp.0 (256x256, 128 KB) stays resident in shared memory; the
+// input_lin image (64 KB) is bulk-copied per tile into the region that later holds the LayerNorm-modulated operand,
+// and that copy as well as the next e tile are issued as soon as the MMA that read the region has completed, so they
+// overlap the epilogues.  256 threads: warp w = tile rows 32*(w&3)..+31 x column half (w>>2) of the 256 hidden units.
 #include "edge_common.cuh"
 
 namespace jodo {
 
 namespace {
 
-constexpr int EQ_AIN = 0;                        // 64 KB: [e | GBF(d)] (K = 128); later 2 x 32 KB coord_mlp.0 chunk ring
-constexpr int EQ_A3 = 65536;                     // 128 KB: input_lin image landing zone, then LN-modulated A (K = 256)
-constexpr int EQ_MISC = EQ_A3 + 131072;
-constexpr int EQ_SMEM = EQ_MISC + 128 + (192 + 256 + 256 + 768 + 128 * 3) * 4 + 512 + 512;
+constexpr int EQ_THREADS = 256;
+constexpr int EQ_WC0 = 0;                        // 128 KB: coord_mlp.0 image (N = 256, K = 256: 4 chunks of 32 KB)
+constexpr int EQ_X = 131072;                     // 64 KB: input_lin image (N = 256, K = 128), then LN-modulated A (K = 256)
+constexpr int EQ_U = EQ_X + 65536;               // 32 KB: [e | GBF(d)] (K = 128); chunk 1 doubles as scratch
+constexpr int EQ_MISC = EQ_U + 32768;
+constexpr int EQ_SMEM = EQ_MISC + 128 + 768;
 static_assert(EQ_SMEM <= 232448, "shared memory budget");
-constexpr int WC_CHUNK = 256 * 128;              // one K-chunk of coord_mlp.0 (N = 256) = 32 KB
+// scratch inside U chunk 1 (free once the input_lin MMA has completed)
+constexpr int EQ_SCR = EQ_U + 16384;
+constexpr int EQ_LNS = EQ_SCR;                   // [128][2] float2
+constexpr int EQ_DOT = EQ_LNS + 128 * 2 * 8;     // [128][2][4] floats
+constexpr int EQ_C3 = EQ_DOT + 128 * 2 * 16;     // [128][4] floats
+constexpr int EQ_GT = EQ_C3 + 128 * 16;          // group tables 2 x [128] ints
+static_assert(EQ_GT + 1024 <= EQ_MISC, "scratch overflows the U chunk");
 
-__global__ void __launch_bounds__(ET, 1) k_equi(EquiArgs a) {
+__global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
-  uint8_t* AIN = smem + EQ_AIN;
-  uint8_t* A3 = smem + EQ_A3;
+  uint8_t* X = smem + EQ_X;
+  uint8_t* U = smem + EQ_U;
   uint8_t* misc = smem + EQ_MISC;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // 0: e tile, 1: input_lin image, 2: MMA, 3,4: chunk landed, 5,6: chunk consumed
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // 0: coord_mlp.0 image, 1: e tile, 2: input_lin image, 3: MMA in, 4: MMA c0
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 64);
   float* gbf = reinterpret_cast<float*>(misc + 128);    // [192]
-  float* b_in = gbf + 192;                              // [256]
-  float* b_c0 = b_in + 256;                             // [256]
-  float* wc2 = b_c0 + 256;                              // [3][256]
-  float* C3 = wc2 + 768;                                // [128][3] per-row coordinate contributions
-  uint32_t* gt_meta = reinterpret_cast<uint32_t*>(C3 + 384);
+  float2* LNS = reinterpret_cast<float2*>(smem + EQ_LNS);
+  float4* DOT = reinterpret_cast<float4*>(smem + EQ_DOT);
+  float4* C3 = reinterpret_cast<float4*>(smem + EQ_C3);
+  uint32_t* gt_meta = reinterpret_cast<uint32_t*>(smem + EQ_GT);
   int* gt_node = reinterpret_cast<int*>(gt_meta + 128);
 
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int rq = warp & 3, half = warp >> 2;
+  const int row = rq * 32 + lane;
+  const int per = (a.p.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile0 = blockIdx.x * per;
+  const int tile1 = min(tile0 + per, a.p.n_tiles);
+
   if (t == 0) {
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
+    if (tile0 < tile1) {
+      mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
+      bulk_g2s(U, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)tile0 * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
+      mbar_expect_tx(&bars[2], 65536);
+      bulk_g2s(X, a.win_img, 65536, &bars[2]);
+    }
+    mbar_expect_tx(&bars[0], 131072);
+    bulk_g2s(smem + EQ_WC0, a.wc0_img, 131072, &bars[0]);
   }
-  for (int i = t; i < 192; i += ET) gbf[i] = a.gbf[i];
-  for (int i = t; i < 256; i += ET) { b_in[i] = a.b_in[i]; b_c0[i] = a.b_c0[i]; }
-  for (int i = t; i < 768; i += ET) wc2[i] = a.wc2[i];
-  if (t < 32) tmem_alloc<512>(tmem_slot);
+  for (int i = t; i < 192; i += EQ_THREADS) gbf[i] = a.gbf[i];
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
   sync_tc();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_x = tmem, tm_c = tmem + 256;
-  uint32_t par_e = 0, par_w = 0, par_m = 0;
-  uint32_t par_land[2] = {0, 0}, par_free[2] = {0, 0};          // thread 0 only
+  uint32_t par = 0;
   const float4* pos = reinterpret_cast<const float4*>(a.pos_in);
   float4* pos_out = reinterpret_cast<float4*>(a.pos_out);
+  const int cb = 128 * half;                      // first hidden column of this thread
 
-  for (int tile = blockIdx.x; tile < a.p.n_tiles; tile += gridDim.x) {
-    const RowInfo r = load_row(a.p, tile, t);
+  for (int tile = tile0; tile < tile1; ++tile) {
+    const RowInfo r = load_row(a.p, tile, row);
     const int ng = a.p.tile_ngroups[tile];
-    if (r.valid && t == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
-    if (t == 0) {
-      mbar_expect_tx(&bars[0], E_TILE_BYTES);
-      bulk_g2s(AIN, reinterpret_cast<const uint8_t*>(a.e) + (size_t)tile * a.e_tile_bytes, E_TILE_BYTES, &bars[0]);
-      mbar_expect_tx(&bars[1], 131072);
-      bulk_g2s(A3, a.win_img, 131072, &bars[1]);
-    }
     const float* tr = a.tab + (size_t)r.mol * a.ld_tab + a.tab_off;
-    const uint8_t ex = a.extra[(size_t)tile * TILE_ROWS + t];
+    const uint8_t ex = a.extra[(size_t)tile * TILE_ROWS + row];
     const float4 pg = pos[r.g], pj = pos[r.j];
     {
-      float df[64];
+      float df[32];
       if (r.valid) {
-        gbf_eval(sq_dist(pg, pj), tr[tab_gbf(D_)], tr[tab_gbf(D_) + 1], gbf, df);
+        gbf_eval_half(sq_dist(pg, pj), tr[tab_gbf(D_)], tr[tab_gbf(D_) + 1], gbf, half, df);
       } else {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) df[i] = 0.f;
+        for (int i = 0; i < 32; ++i) df[i] = 0.f;
       }
-      st_row64<true>(AIN, t, 2, df);
+      st_rowh<32>(U, row, 1, 4 * half, df);
     }
     fence_async_smem();
     sync_tc();
     if (t == 0) {
-      mbar_wait(&bars[0], par_e);
-      mbar_wait(&bars[1], par_w);
+      mbar_wait(&bars[1], par);
+      mbar_wait(&bars[2], par);
       tc_fence_after();
-      mma_tile(tm_x, smem_u32(AIN), smem_u32(A3), 256, 4, false);       // input_lin edge part
-      umma_commit(&bars[2]);
+      mma_tile_h(tm_x, smem_u32(U), smem_u32(X), 256, 2, false);       // input_lin edge part
+      umma_commit(&bars[3]);
     }
-    par_e ^= 1; par_w ^= 1;
-    mbar_wait(&bars[2], par_m);
-    par_m ^= 1;
+    mbar_wait(&bars[3], par);
     tc_fence_after();
-    if (t == 0) {      // AIN is free now: start streaming coord_mlp.0 chunks 0 and 1
-      for (int s = 0; s < 2; ++s) {
-        mbar_expect_tx(&bars[3 + s], WC_CHUNK);
-        bulk_g2s(AIN + s * WC_CHUNK, reinterpret_cast<const uint8_t*>(a.wc0_img) + (size_t)s * WC_CHUNK, WC_CHUNK, &bars[3 + s]);
-      }
+    if (t == 0 && tile + 1 < tile1) {            // U chunk 0 is consumed: prefetch the next e tile
+      mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
+      bulk_g2s(U, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 1) * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
     }
+    if (half == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
 
-    // ---- pass 1: x = acc + A[g] + B[j] + b, kept in TMEM; row statistics (shifted by the first element)
+    // ---- pass 1: x = acc + A[g] + B[j] + b over this thread's 128 hidden units, kept in TMEM; row statistics
     float mean, rstd;
     {
-      const float* ag = a.AB + (size_t)r.g * a.ldab;
-      const float* bj = a.AB + (size_t)r.j * a.ldab + D_;
-      float sh0 = 0.f, s1 = 0.f, s2 = 0.f;
+      const float* ag = a.AB + (size_t)r.g * a.ldab + cb;
+      const float* bj = a.AB + (size_t)r.j * a.ldab + D_ + cb;
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        float x[32];
-        tmem_ld32(tmem_addr(tm_x, c * 32), x);
+      for (int c = 0; c < 4; ++c) {
+        float4 u4[8], v4[8];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 u = *reinterpret_cast<const float4*>(ag + c * 32 + i);
-          const float4 v = *reinterpret_cast<const float4*>(bj + c * 32 + i);
-          x[i] += u.x + v.x + b_in[c * 32 + i];
-          x[i + 1] += u.y + v.y + b_in[c * 32 + i + 1];
-          x[i + 2] += u.z + v.z + b_in[c * 32 + i + 2];
-          x[i + 3] += u.w + v.w + b_in[c * 32 + i + 3];
+        for (int i = 0; i < 8; ++i) {
+          u4[i] = __ldg(reinterpret_cast<const float4*>(ag + c * 32) + i);
+          v4[i] = __ldg(reinterpret_cast<const float4*>(bj + c * 32) + i);
         }
-        if (c == 0) sh0 = x[0];
+        float x[32];
+        tmem_ld32(tmem_addr(tm_x, cb + c * 32), x);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { const float d = x[i] - sh0; s1 += d; s2 += d * d; }
-        tmem_st32(tmem_addr(tm_x, c * 32), x);
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b_in + cb + c * 32) + i);
+          x[4 * i] += u4[i].x + v4[i].x + b4.x;
+          x[4 * i + 1] += u4[i].y + v4[i].y + b4.y;
+          x[4 * i + 2] += u4[i].z + v4[i].z + b4.z;
+          x[4 * i + 3] += u4[i].w + v4[i].w + b4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { s1 += x[i]; s2 = fmaf(x[i], x[i], s2); }
+        tmem_st32(tmem_addr(tm_x, cb + c * 32), x);
       }
       tmem_wait_st();
-      const float m1 = s1 * (1.0f / 256.0f);
-      mean = sh0 + m1;
-      rstd = rsqrtf(fmaxf(s2 * (1.0f / 256.0f) - m1 * m1, 0.f) + 1e-6f);
+      LNS[row * 2 + half] = make_float2(s1, s2);
+      __syncthreads();
+      const float2 o = LNS[row * 2 + (half ^ 1)];
+      mean = (s1 + o.x) * (1.0f / 256.0f);
+      rstd = rsqrtf(fmaxf((s2 + o.y) * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-6f);
     }
-    // ---- pass 2: LN + modulate -> A3 (K = 256); the input_lin image there is no longer needed
+    // ---- pass 2: LN + modulate -> X (fp16, K = 256); the input_lin image there is no longer needed
     {
-      const float* shift = tr + tab_equi(D_);
+      const float* shift = tr + tab_equi(D_) + cb;
       const float* scale = shift + D_;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float x[32];
-        tmem_ld32(tmem_addr(tm_x, c * 32), x);
+        tmem_ld32(tmem_addr(tm_x, cb + c * 32), x);
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 sh = *reinterpret_cast<const float4*>(shift + c * 32 + i);
-          const float4 sc = *reinterpret_cast<const float4*>(scale + c * 32 + i);
-          x[i] = r.valid ? (x[i] - mean) * rstd * (1.0f + sc.x) + sh.x : 0.f;
-          x[i + 1] = r.valid ? (x[i + 1] - mean) * rstd * (1.0f + sc.y) + sh.y : 0.f;
-          x[i + 2] = r.valid ? (x[i + 2] - mean) * rstd * (1.0f + sc.z) + sh.z : 0.f;
-          x[i + 3] = r.valid ? (x[i + 3] - mean) * rstd * (1.0f + sc.w) + sh.w : 0.f;
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c * 32 + i));
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c * 32 + i));
+          x[i] = r.valid ? fmaf((x[i] - mean) * rstd, 1.0f + sc.x, sh.x) : 0.f;
+          x[i + 1] = r.valid ? fmaf((x[i + 1] - mean) * rstd, 1.0f + sc.y, sh.y) : 0.f;
+          x[i + 2] = r.valid ? fmaf((x[i + 2] - mean) * rstd, 1.0f + sc.z, sh.z) : 0.f;
+          x[i + 3] = r.valid ? fmaf((x[i + 3] - mean) * rstd, 1.0f + sc.w, sh.w) : 0.f;
         }
-        st_row32<true>(A3, t, c, x);
+        st_rowh<32>(X, row, 2 * half + (c >> 1), 4 * (c & 1), x);
       }
     }
     fence_async_smem();
     sync_tc();
-    if (t == 0) {      // coord_mlp.0: 8 K-chunks through a 2-deep ring in AIN
-      for (int kc = 0; kc < 8; ++kc) {
-        const int s = kc & 1;
-        mbar_wait(&bars[3 + s], par_land[s]);
-        par_land[s] ^= 1;
-        tc_fence_after();
-        mma_tile(tm_c, smem_u32(A3 + kc * CHUNK_BYTES_A), smem_u32(AIN + s * WC_CHUNK), 256, 1, kc > 0);
-        if (kc + 2 < 8) {
-          umma_commit(&bars[5 + s]);
-          mbar_wait(&bars[5 + s], par_free[s]);
-          par_free[s] ^= 1;
-          mbar_expect_tx(&bars[3 + s], WC_CHUNK);
-          bulk_g2s(AIN + s * WC_CHUNK, reinterpret_cast<const uint8_t*>(a.wc0_img) + (size_t)(kc + 2) * WC_CHUNK, WC_CHUNK,
-                   &bars[3 + s]);
-        }
-      }
-      umma_commit(&bars[2]);
+    if (t == 0) {
+      if (tile == tile0) mbar_wait(&bars[0], 0);
+      tc_fence_after();
+      mma_tile_h(tm_c, smem_u32(X), smem_u32(smem + EQ_WC0), 256, 4, false);     // coord_mlp.0
+      umma_commit(&bars[4]);
     }
-    mbar_wait(&bars[2], par_m);
-    par_m ^= 1;
+    mbar_wait(&bars[4], par);
     tc_fence_after();
+    if (t == 0 && tile + 1 < tile1) {            // X is consumed: fetch the input_lin image for the next tile
+      mbar_expect_tx(&bars[2], 65536);
+      bulk_g2s(X, a.win_img, 65536, &bars[2]);
+    }
 
-    // ---- coord_mlp.2 on CUDA cores, tanh, adjacency-weighted mean, coordinate contribution
+    // ---- SiLU, coord_mlp.2 on CUDA cores (partial dots over this thread's 128 hidden units)
     {
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float x[32];
-        tmem_ld32(tmem_addr(tm_c, c * 32), x);
+        tmem_ld32(tmem_addr(tm_c, cb + c * 32), x);
+        const float* bc = a.b_c0 + cb + c * 32;
+        const float* w = a.wc2 + cb + c * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = silu_f(x[i] + b_c0[c * 32 + i]);
-          o0 += s * wc2[c * 32 + i];
-          o1 += s * wc2[256 + c * 32 + i];
-          o2 += s * wc2[512 + c * 32 + i];
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bc + i));
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + i));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + 256 + i));
+          const float4 w2 = __ldg(reinterpret_cast<const float4*>(w + 512 + i));
+          const float s0 = silu_fast(x[i] + b4.x), s1 = silu_fast(x[i + 1] + b4.y);
+          const float s2 = silu_fast(x[i + 2] + b4.z), s3 = silu_fast(x[i + 3] + b4.w);
+          o0 = fmaf(s0, w0.x, o0); o0 = fmaf(s1, w0.y, o0); o0 = fmaf(s2, w0.z, o0); o0 = fmaf(s3, w0.w, o0);
+          o1 = fmaf(s0, w1.x, o1); o1 = fmaf(s1, w1.y, o1); o1 = fmaf(s2, w1.z, o1); o1 = fmaf(s3, w1.w, o1);
+          o2 = fmaf(s0, w2.x, o2); o2 = fmaf(s1, w2.y, o2); o2 = fmaf(s2, w2.z, o2); o2 = fmaf(s3, w2.w, o2);
         }
       }
-      const float w = (tanh_f(o0) + ((ex & 1) ? tanh_f(o1) : 0.f) + ((ex & 2) ? tanh_f(o2) : 0.f)) * (1.0f / 3.0f);
+      DOT[row * 2 + half] = make_float4(o0, o1, o2, 0.f);
+    }
+    __syncthreads();
+    if (half == 0) {     // tanh, adjacency-weighted mean, coordinate contribution of this edge
+      const float4 p = DOT[row * 2], q = DOT[row * 2 + 1];
+      const float w = (tanh_fast(p.x + q.x) + ((ex & 1) ? tanh_fast(p.y + q.y) : 0.f) + ((ex & 2) ? tanh_fast(p.z + q.z) : 0.f)) *
+                      (1.0f / 3.0f);
       const float dx = pg.x - pj.x, dy = pg.y - pj.y, dz = pg.z - pj.z;
       const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
       const float f = r.valid ? a.coord_scale * w / fmaxf(nrm, 1e-8f) : 0.f;
-      C3[t * 3 + 0] = dx * f; C3[t * 3 + 1] = dy * f; C3[t * 3 + 2] = dz * f;
+      C3[row] = make_float4(dx * f, dy * f, dz * f, 0.f);
     }
     __syncthreads();
     if (t < ng) {
       const int gs = gt_meta[t] & 255u, gl = (gt_meta[t] >> 8) & 255u;
       const int node = gt_node[t];
       float sx = 0.f, sy = 0.f, sz = 0.f;
-      for (int rr = gs; rr < gs + gl; ++rr) { sx += C3[rr * 3]; sy += C3[rr * 3 + 1]; sz += C3[rr * 3 + 2]; }
+      for (int rr = gs; rr < gs + gl; ++rr) { const float4 c = C3[rr]; sx += c.x; sy += c.y; sz += c.z; }
       const float4 p0 = pos[node];
       pos_out[node] = make_float4(p0.x + sx, p0.y + sy, p0.z + sz, 0.f);
     }
-    fence_async_smem();
+    fence_async_smem();        // the scratch is overwritten by the next tile's GBF rows
     sync_tc();
+    par ^= 1;
   }
-  if (t < 32) tmem_dealloc<512>(tmem);
+  if (tile0 >= tile1 && t == 0) mbar_wait(&bars[0], 0);   // never leave with bulk copies in flight
+  sync_tc();
+  if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace
@@ -216,7 +243,7 @@ cudaError_t launch_equi(const EquiArgs& a, int num_sms, cudaStream_t st) {
     attr = true;
   }
   const int grid = a.p.n_tiles < num_sms ? a.p.n_tiles : num_sms;
-  k_equi<<<grid, ET, EQ_SMEM, st>>>(a);
+  k_equi<<<grid, EQ_THREADS, EQ_SMEM, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -55,9 +55,10 @@ class _Workspace:
         self.n1 = f(Nn, D)
         self.n2 = f(Nn, D // 2)
         self.ap = f(Nn, meta['npred4']['N'])
-        self.eh_tile_bytes = (meta['keh'] // 32) * 128 * 128
-        self.eh = torch.zeros(nt * self.eh_tile_bytes // 4, device=dev, dtype=torch.float32)
-        self.e = torch.zeros(nt * 8192, device=dev, dtype=torch.float32)      # 32 KB per tile
+        self.eh_tile_bytes = (meta['keh'] // 64) * 128 * 128                  # fp16 image, 16 KB per 64 columns
+        self.eh = torch.zeros(nt * self.eh_tile_bytes // 2, device=dev, dtype=torch.float16)
+        self.e = torch.zeros(nt * 8192, device=dev, dtype=torch.float32)      # fp32 edge state, 32 KB per tile
+        self.e16 = torch.zeros(nt * 8192, device=dev, dtype=torch.float16)    # fp16 operand copy, 16 KB per tile
         self.extra = torch.zeros(nt * 128, device=dev, dtype=torch.uint8)
         self.flags = torch.zeros(4, device=dev, dtype=torch.int32)            # [0] dist flag, [1] nan flag
 
@@ -160,12 +161,11 @@ class _DGTBase(nn.Module):
         # ---- per edge: model-level embedding + adjacency heads
         ea = _lib.EdgeEmbedArgs(ps, _lib.dp(edge_x), _lib.dp(cond_edge_x), _lib.dp(cond_x), d.ch, d.inn, self.edge_th,
                                 self.spatial_cut_off, _lib.dp(ws.flags), _lib.dp(ws.tab), ld_tab, pk.ptr('gbf'),
-                                pk.ptr('edge_emb.img'), pk.ptr('edge_emb.b'), _lib.dp(ws.eh), ws.eh_tile_bytes,
-                                _lib.dp(ws.extra))
+                                pk.ptr('edge_emb.img'), pk.ptr('edge_emb.b'), _lib.dp(ws.e), _lib.dp(ws.e16),
+                                _lib.dp(ws.eh), ws.eh_tile_bytes, _lib.dp(ws.extra))
         _lib.call('jodo_edge_embed', ctypes.byref(ea), st)
 
-        h, ldh_view = ws.ah[:, :D], None
-        e_in_ptr, e_in_stride = _lib.dp(ws.eh), ws.eh_tile_bytes
+        h = ws.ah[:, :D]
         stride = tab_layer_stride(D)
         for l in range(d.L):
             p = f'b{l}.'
@@ -176,7 +176,7 @@ class _DGTBase(nn.Module):
             _lib.call('jodo_ln_mod', _c(D), _lib.ptr(h), _c(h.stride(0)), None, _c(0), _lib.ptr(ws.tab), _c(ld_tab),
                       _c(0), _c(off), _c(off + D), ctypes.byref(ps), _lib.ptr(ws.hn), _c(D), st)
             lin(p + 'qkv', ws.hn, ws.qkv)
-            aa = _lib.AttnArgs(ps, e_in_ptr, e_in_stride, _lib.dp(pin), _lib.dp(ws.qkv), 3 * D, _lib.dp(ws.tab), ld_tab,
+            aa = _lib.AttnArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(ws.qkv), 3 * D, _lib.dp(ws.tab), ld_tab,
                                off, _lib.dp(ws.extra), pk.ptr(p + 'gbf'), pk.ptr(p + 'emb.img'), pk.ptr(p + 'emb.b'),
                                pk.ptr(p + 'e0.img'), pk.ptr(p + 'e1.img'), _lib.dp(ws.hnode))
             _lib.call('jodo_attn', ctypes.byref(aa), st)
@@ -191,12 +191,12 @@ class _DGTBase(nn.Module):
             lin(p + 'ab', hout, ws.ab)
             lin(p + 'node_l', hout, ws.ah[:, D + l * meta['cnp']:])
             # edge path
-            ua = _lib.EdgeUpdateArgs(ps, e_in_ptr, e_in_stride, _lib.dp(ws.e), _lib.dp(ws.pbuf), 64, pk.ptr(p + 'n2e.bias'),
+            ua = _lib.EdgeUpdateArgs(ps, _lib.dp(ws.e), _lib.dp(ws.e16), _lib.dp(ws.pbuf), 64, pk.ptr(p + 'n2e.bias'),
                                      _lib.dp(ws.tab), ld_tab, off, d.r, pk.ptr(p + 'ff3.img'), pk.ptr(p + 'ff3.b'),
                                      pk.ptr(p + 'ff4.img'), pk.ptr(p + 'ff4.b'), pk.ptr(p + 'edge_l.img'),
                                      pk.ptr(p + 'edge_l.b'), _lib.dp(ws.eh), ws.eh_tile_bytes, d.ed + l * d.ce, d.ce)
             _lib.call('jodo_edge_update', ctypes.byref(ua), st)
-            qa = _lib.EquiArgs(ps, _lib.dp(ws.e), 32768, _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), 2 * D,
+            qa = _lib.EquiArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), 2 * D,
                                _lib.dp(ws.tab), ld_tab, off, _lib.dp(ws.extra), pk.ptr(p + 'gbf'), pk.ptr(p + 'win.img'),
                                pk.ptr(p + 'win.b'), pk.ptr(p + 'wc0.img'), pk.ptr(p + 'wc0.b'), pk.ptr(p + 'wc2'),
                                meta['coord_scale'][l])
@@ -206,7 +206,6 @@ class _DGTBase(nn.Module):
                 dbg.setdefault('blocks', []).append(dict(hnode=ws.hnode.clone(), h=hout.clone(), e=ws.e.clone(),
                                                          pos=pout.clone(), qkv=ws.qkv.clone(), hn=ws.hn.clone()))
             h = hout
-            e_in_ptr, e_in_stride = _lib.dp(ws.e), 32768
         # ---- heads
         lin('npred0', ws.ah, ws.n1, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)
         lin('npred2', ws.n1, ws.n2, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)

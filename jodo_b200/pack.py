@@ -40,6 +40,32 @@ def weight_image(w: torch.Tensor, nt: int | None = None, tf32: bool = True) -> t
     return torch.gather(x, 3, idx).contiguous().reshape(-1)
 
 
+def weight_image_h(w: torch.Tensor, nt: int | None = None) -> torch.Tensor:
+    """fp16 operand image of W [N, K] (N % nt == 0, K % 64 == 0): [N/nt][K/64][nt][8 slots][8 halves], returned as a
+    flat float32-typed tensor holding the fp16 bit patterns (so that it can live in the packed fp32 buffer)."""
+    n, k = w.shape
+    nt = n if nt is None else nt
+    assert n % nt == 0 and k % 64 == 0 and nt % 8 == 0, (n, k, nt)
+    h = w.to(torch.float32).clamp(-65504.0, 65504.0).to(torch.float16)
+    x = h.reshape(n // nt, nt, k // 64, 8, 8).permute(0, 2, 1, 3, 4)          # [tile, chunk, row, piece, 8]
+    rows = torch.arange(nt, device=w.device)
+    slots = torch.arange(8, device=w.device)
+    src_piece = slots[None, :] ^ (rows[:, None] & 7)
+    idx = src_piece[None, None, :, :, None].expand(n // nt, k // 64, nt, 8, 8)
+    return torch.gather(x, 3, idx).contiguous().reshape(-1).view(torch.float32)
+
+
+def image_to_matrix_h(img: torch.Tensor, rows: int, k: int) -> torch.Tensor:
+    """Inverse for ONE fp16 tile image (flat fp16 tensor [k/64][rows][8 slots][8]) -> fp32 [rows, k]."""
+    x = img.reshape(k // 64, rows, 8, 8)
+    r = torch.arange(rows, device=img.device)
+    slots = torch.arange(8, device=img.device)
+    slot_of_piece = slots[None, :] ^ (r[:, None] & 7)
+    idx = slot_of_piece[None, :, :, None].expand(k // 64, rows, 8, 8)
+    y = torch.gather(x, 2, idx)
+    return y.permute(1, 0, 2, 3).reshape(rows, k).float()
+
+
 def image_to_matrix(img: torch.Tensor, rows: int, k: int) -> torch.Tensor:
     """Inverse of the activation/edge image layout for ONE tile: [k/32][rows][8 slots][4] -> [rows, k]."""
     x = img.reshape(k // 32, rows, 8, 4)
@@ -192,18 +218,18 @@ def pack_model(sd, dims, device):
     wep[:, ed:ed + 2 * d.ch] = we[:, :2 * d.ch]
     pk.add('edge_emb.img', weight_image(wep, ed))
     pk.add('edge_emb.b', Bv('edge_emb'))
-    keh = ceil_to(ed + L * d.ce, 32)
+    keh = ceil_to(ed + L * d.ce, 64)
     assert keh == 192, keh
     pk.meta['keh'] = keh
     wh0 = z(2 * ed, keh)
     wh0[:ed, :d.edge_cat] = W('edge_exist_mlp.0')
     wh0[ed:, :d.edge_cat] = W('edge_type_mlp.0')
-    pk.add('ehead0.img', weight_image(wh0, 2 * ed))
+    pk.add('ehead0.img', weight_image_h(wh0, 2 * ed))
     pk.add('ehead0.b', torch.cat([Bv('edge_exist_mlp.0'), Bv('edge_type_mlp.0')]))
     wh2 = z(ed, 2 * ed)
     wh2[:ed // 2, :ed] = W('edge_exist_mlp.2')
     wh2[ed // 2:, ed:] = W('edge_type_mlp.2')
-    pk.add('ehead2.img', weight_image(wh2, ed))
+    pk.add('ehead2.img', weight_image_h(wh2, ed))
     pk.add('ehead2.b', torch.cat([Bv('edge_exist_mlp.2'), Bv('edge_type_mlp.2')]))
     pk.add('ehead4.w', torch.cat([W('edge_exist_mlp.4'), W('edge_type_mlp.4')], dim=0))     # [ch, 32]
     pk.add('ehead4.b', torch.cat([Bv('edge_exist_mlp.4'), Bv('edge_type_mlp.4')]))
@@ -228,22 +254,22 @@ def pack_model(sd, dims, device):
         add_lin(p + 'ab', torch.cat([wi[:, :D], wi[:, D:2 * D]], dim=0), None, 256)
         add_lin(p + 'node_l', W(f'node_{l}'), Bv(f'node_{l}'), 64, n_pad=64)
         pk.add(p + 'gbf', _gbf_consts(sd, f'{b}.dist_layer', device))
-        pk.add(p + 'emb.img', weight_image(W(f'{b}.edge_emb'), ed))                       # [64, 128]: [dist | e]
+        pk.add(p + 'emb.img', weight_image_h(W(f'{b}.edge_emb'), ed))                       # [64, 128]: [dist | e]
         pk.add(p + 'emb.b', Bv(f'{b}.edge_emb'))
-        pk.add(p + 'e0.img', weight_image(split_heads(W(f'{b}.attn_mpnn.lin_edge0'), D, d.qk), D))
-        pk.add(p + 'e1.img', weight_image(W(f'{b}.attn_mpnn.lin_edge1'), D))
+        pk.add(p + 'e0.img', weight_image_h(split_heads(W(f'{b}.attn_mpnn.lin_edge0'), D, d.qk), D))
+        pk.add(p + 'e1.img', weight_image_h(W(f'{b}.attn_mpnn.lin_edge1'), D))
         w3, w4 = W(f'{b}.ff_linear3'), W(f'{b}.ff_linear4')    # [ed r, ed], [ed, ed r]
-        pk.add(p + 'ff3.img', weight_image(w3, ed))
+        pk.add(p + 'ff3.img', weight_image_h(w3, ed * d.r))
         pk.add(p + 'ff3.b', Bv(f'{b}.ff_linear3'))
-        pk.add(p + 'ff4.img', torch.cat([weight_image(w4[:, ed * i:ed * (i + 1)].contiguous(), ed) for i in range(d.r)]))
+        pk.add(p + 'ff4.img', weight_image_h(w4, ed))
         pk.add(p + 'ff4.b', Bv(f'{b}.ff_linear4'))
-        pk.add(p + 'edge_l.img', weight_image(pad2(W(f'edge_{l}'), 16, ed), 16))
+        pk.add(p + 'edge_l.img', weight_image_h(pad2(W(f'edge_{l}'), 16, ed), 16))
         bl = z(16)
         bl[:d.ce] = Bv(f'edge_{l}')
         pk.add(p + 'edge_l.b', bl)
-        pk.add(p + 'win.img', weight_image(wi[:, 2 * D:].contiguous(), D))                # [256, 128]: [e | dist]
+        pk.add(p + 'win.img', weight_image_h(wi[:, 2 * D:].contiguous(), D))                # [256, 128]: [e | dist]
         pk.add(p + 'win.b', Bv(f'{b}.equi_update.input_lin'))
-        pk.add(p + 'wc0.img', weight_image(W(f'{b}.equi_update.coord_mlp.0'), D))
+        pk.add(p + 'wc0.img', weight_image_h(W(f'{b}.equi_update.coord_mlp.0'), D))
         pk.add(p + 'wc0.b', Bv(f'{b}.equi_update.coord_mlp.0'))
         pk.add(p + 'wc2', W(f'{b}.equi_update.coord_mlp.2'))                               # [3, 256]
         scales.append(sd[f'{b}.equi_update.coord_norm.scale'].reshape(()))

@@ -3,7 +3,7 @@ parity test to print where a mismatch starts)."""
 import torch
 
 from helpers import golden_weights, load_golden, oracle_forward
-from jodo_b200.pack import image_to_matrix
+from jodo_b200.pack import image_to_matrix, image_to_matrix_h
 
 
 def rel(a, b):
@@ -17,6 +17,14 @@ def tiles_to_dense(plan, img, k, tile_floats=None, group_first=True):
     tile_floats = (k // 32) * 128 * 32 if tile_floats is None else tile_floats
     img = img.reshape(nt, tile_floats)[:, :(k // 32) * 4096]
     rows = torch.stack([image_to_matrix(img[t], 128, k) for t in range(nt)]).reshape(nt * 128, k)
+    return plan.rows_to_dense(rows, group_first=group_first)
+
+
+def tiles_to_dense_h(plan, img, k, tile_halves, group_first=True):
+    """fp16 tile images [n_tiles][k/64][128][64] -> dense [B,N,N,k] (fp32)"""
+    nt = plan.n_tiles
+    img = img.reshape(nt, tile_halves)[:, :(k // 64) * 8192]
+    rows = torch.stack([image_to_matrix_h(img[t], 128, k) for t in range(nt)]).reshape(nt * 128, k)
     return plan.rows_to_dense(rows, group_first=group_first)
 
 
@@ -57,8 +65,8 @@ def run_case(name, device='cuda', verbose=True):
     rep.append(('h0', rel(packed_to_dense(plan, dbg['ah'][:, :D]), trace['h0'] * inp['node_mask'].double())))
     em = inp['edge_mask'].reshape(plan.B, plan.N, plan.N, 1).double()
     eh = dbg['eh']
-    rep.append(('e0', rel(tiles_to_dense(plan, eh, 64, tile_floats=model._plans[next(iter(model._plans))][1].eh_tile_bytes // 4,
-                                         group_first=False), trace['e0'] * em)))
+    rep.append(('e0', rel(tiles_to_dense_h(plan, eh, 64, model._plans[next(iter(model._plans))][1].eh_tile_bytes // 2,
+                                           group_first=False), trace['e0'] * em)))
     for l, (b, ob) in enumerate(zip(dbg['blocks'], trace['blocks'])):
         m = inp['node_mask'].double()
         rep.append((f'b{l}.hn', rel(packed_to_dense(plan, b['hn']), ob['hn'] * m)))
