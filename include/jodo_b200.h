@@ -36,8 +36,8 @@ extern "C" {
 const char* jodo_last_error_string(void);
 int jodo_abi_version(void);
 
-/* C[M,N] = epi(act_in(A[M,K]) * W^T + bias) on the tcgen05 tensor cores (tf32 operands, fp32 accumulate).
- * Wimg is the pre-swizzled weight image built by jodo_b200.pack.weight_image ([N/NT][K/32][NT][32]).
+/* C[M,N] = epi(act_in(A[M,K]) * W^T + bias) on the tcgen05 tensor cores (fp16 operands -- the mantissa of tf32, saturating at +-65504 -- fp32 accumulate).
+ * Wimg is the pre-swizzled fp16 weight image built by jodo_b200.pack.weight_image_h ([N/NT][K/64][NT][64]); K % 64 == 0.
  * Replaces every per-atom / per-molecule nn.Linear of the reference forward: time_mlp, cond_mlp, cond_lin
  * (models/mol_gnn.py:481-489, 679-684), node_emb (:556), lin_query/key/value (models/layers.py:147-149),
  * ff_linear1/2 (models/mol_gnn.py:262-264), node_i (:567), node_pred_mlp (:573) and the hoisted per-atom
@@ -136,7 +136,7 @@ typedef struct jodo_edge_head_args {                     /* edge_exist_mlp | edg
 
 
 /* per-atom / per-molecule elementwise kernels */
-int jodo_time_features(const float* noise_level, const float* w8, float* feat32, int B, void* stream);
+int jodo_time_features(const float* noise_level, const float* w8, float* feat64, int B, void* stream);  /* [B, 64] */
 int jodo_cond_in(const float* ctx, const float* w0, const float* b0, float* out, int rows, int D, void* stream);
 int jodo_gather_nodes(const float* xh, const float* cond_x, const jodo_plan* p, int inn, int kin, float* xin, float* pos4,
                       void* stream);

@@ -49,9 +49,9 @@ static int num_sms() {
 }
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
-int jodo_time_features(const float* nl, const float* w8, float* feat32, int B, void* stream) {
+int jodo_time_features(const float* nl, const float* w8, float* feat64, int B, void* stream) {
   if (B <= 0) return fail("jodo_time_features: B <= 0");
-  JODO_LAUNCH(jodo::launch_time_features(nl, w8, feat32, B, S(stream)), "jodo_time_features");
+  JODO_LAUNCH(jodo::launch_time_features(nl, w8, feat64, B, S(stream)), "jodo_time_features");
 }
 int jodo_cond_in(const float* ctx, const float* w0, const float* b0, float* out, int rows, int D, void* stream) {
   if (rows <= 0 || D <= 0) return fail("jodo_cond_in: bad sizes");

@@ -13,7 +13,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// feat[b, 0:17] = (nl, sin(nl*w*2pi) x8, cos(nl*w*2pi) x8), padded with zeros to 32 columns.
+// feat[b, 0:17] = (nl, sin(nl*w*2pi) x8, cos(nl*w*2pi) x8), padded with zeros to 64 columns.
 // LearnedSinusodialposEmb.forward, reference models/layers.py:283-288.
 __global__ void k_time_features(const float* __restrict__ nl, const float* __restrict__ w, float* __restrict__ feat, int B) {
   int b = blockIdx.x * blockDim.x / 32 + (threadIdx.x >> 5);
@@ -28,7 +28,8 @@ __global__ void k_time_features(const float* __restrict__ nl, const float* __res
     f = f * 3.14159265358979323846f;
     v = (lane <= 8) ? sinf(f) : cosf(f);
   }
-  feat[(size_t)b * 32 + lane] = v;
+  feat[(size_t)b * 64 + lane] = v;
+  feat[(size_t)b * 64 + 32 + lane] = 0.f;
 }
 
 // c1[row, d] = GELU(ctx[row] * w0[d] + b0[d]);  cond_mlp.0 + GELU, reference models/mol_gnn.py:679-681,729-730

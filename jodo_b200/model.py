@@ -32,7 +32,7 @@ class _Workspace:
         zf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
         B, Nn, nt = plan.B, plan.Nn, plan.n_tiles
         D, T = d.D, d.T
-        self.feat = f(B, 32)
+        self.feat = f(B, 64)
         self.t1 = f(B, T)
         self.temb = f(B, T)
         if d.cond_ch:
@@ -41,7 +41,7 @@ class _Workspace:
             self.ctx = f(B, T)
         self.tab = f(B, meta['ld_tab'])
         self.kin = meta['node_emb']['K']
-        self.xin = f(Nn, self.kin)
+        self.xin = f(Nn, self.kin)                          # zero-padded to the GEMM's K by jodo_gather_nodes
         self.pos = [zf(Nn, 4), zf(Nn, 4)]
         self.ah = zf(Nn, meta['ld_ah'])                    # concatenated atom hiddens (pads stay 0)
         self.h = [f(Nn, D), f(Nn, D)]

@@ -166,8 +166,8 @@ def pack_model(sd, dims, device):
     def add_lin(name, w, b, nt, n_pad=None, k_pad=None):
         n, k = w.shape
         n_pad = ceil_to(n, nt) if n_pad is None else n_pad
-        k_pad = ceil_to(k, 32) if k_pad is None else k_pad
-        pk.add(name + '.img', weight_image(pad2(w, n_pad, k_pad), nt))
+        k_pad = ceil_to(k, 64) if k_pad is None else k_pad
+        pk.add(name + '.img', weight_image_h(pad2(w, n_pad, k_pad), nt))
         bb = z(n_pad)
         if b is not None:
             bb[:n] = b
@@ -200,7 +200,7 @@ def pack_model(sd, dims, device):
     # ---- atom level
     add_lin('node_emb', W('node_emb'), Bv('node_emb'), 256)
     cnp = ceil_to(d.cn, 4)
-    k_ah = ceil_to(D + L * cnp, 32)
+    k_ah = ceil_to(D + L * cnp, 64)
     pk.meta.update(cnp=cnp, k_ah=k_ah, ld_ah=k_ah + 64)
     w0 = W('node_pred_mlp.0')
     w0p = z(D, k_ah)
