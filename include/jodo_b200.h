@@ -43,10 +43,12 @@ int jodo_abi_version(void);
  * ff_linear1/2 (models/mol_gnn.py:262-264), node_i (:567), node_pred_mlp (:573) and the hoisted per-atom
  * parts of node2edge_lin (:304-305) and input_lin (:73,79), plus the per-molecule AdaLN tables the
  * reference evaluates per edge (node_time_mlp/edge_time_mlp :291-294, equi time_mlp :78, GBF time_mlp
- * models/layers.py:330). */
-int jodo_rowlinear(const float* A, int lda, int M, int K, const float* Wimg, const float* bias, float* C, int ldc,
+ * models/layers.py:330).
+ * out_f16 != 0 (JODO_EPI_STORE only): C is an fp16 row-major matrix (ldc in elements) -- used for the per-atom
+ * operands the edge kernels gather (q | k | v, the hoisted input_lin parts, the hoisted node2edge_lin part). */
+int jodo_rowlinear(const float* A, int lda, int M, int K, const void* Wimg, const float* bias, void* C, int ldc,
                    int N, int NT, int act_in, int epi, int act_out, const float* aux, int ld_aux, const float* gate,
-                   int ld_gate, const int* row_mol, void* stream);
+                   int ld_gate, const int* row_mol, int out_f16, void* stream);
 
 
 /* ---- varlen plan and argument blocks of the edge-tile kernels ------------------------------------
@@ -88,7 +90,7 @@ typedef struct jodo_attn_args {                         /* TransMixLayer on edge
   jodo_plan p;
   const void* e16;                        /* block input edge features */
   const float* pos;                       /* [Nn] float4 */
-  const float* qkv; int ldq;              /* [Nn, 3D]: q | k | v of LN-modulated atoms (q, k in split-head layout) */
+  const void* qkv; int ldq;               /* fp16 [Nn, 3D]: q | k | v of LN-modulated atoms (q, k in split-head layout) */
   const float* tab; int ld_tab; int tab_off;   /* table base of this layer */
   const uint8_t* extra;
   const float* gbf;                       /* this layer's GBF constants */
@@ -100,7 +102,7 @@ typedef struct jodo_attn_args {                         /* TransMixLayer on edge
 typedef struct jodo_edge_update_args {                   /* edge residual + FFN + edge_l (reference models/mol_gnn.py:304-305,313-317,568) */
   jodo_plan p;
   float* e32; void* e16;                  /* in/out fp32 state (in place), out fp16 copy */
-  const float* P; int ldp;                /* [Nn, 64] node2edge_lin(hnode) without bias */
+  const void* P; int ldp;                 /* fp16 [Nn, 64] node2edge_lin(hnode) without bias */
   const float* b_n2e;                     /* [64] */
   const float* tab; int ld_tab; int tab_off;
   int r;                                  /* mlp_ratio: hidden = 64 r */
@@ -114,7 +116,7 @@ typedef struct jodo_equi_args {                         /* MultiCondEquiUpdate (
   jodo_plan p;
   const void* e16;                        /* updated edge features */
   const float* pos_in; float* pos_out;    /* [Nn] float4 */
-  const float* AB; int ldab;              /* [Nn, >=512]: input_lin[:, :D] h | input_lin[:, D:2D] h */
+  const void* AB; int ldab;               /* fp16 [Nn, >=512]: input_lin[:, :D] h | input_lin[:, D:2D] h */
   const float* tab; int ld_tab; int tab_off;
   const uint8_t* extra;
   const float* gbf;

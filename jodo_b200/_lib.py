@@ -72,7 +72,7 @@ def stream_ptr():
 
 
 def rowlinear(A, K, Wimg, bias, C, N, NT, act_in=ACT_NONE, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None,
-              row_mol=None, M=None, stream=None, tag=None):
+              row_mol=None, M=None, stream=None, tag=None, out_f16=False):
     """C[:, :N] = epi(act_in(A[:, :K]) W^T + bias); A, C, aux, gate are 2-D row-major views (stride(1)==1)."""
     M = A.shape[0] if M is None else M
     f = lib().jodo_rowlinear
@@ -80,7 +80,7 @@ def rowlinear(A, K, Wimg, bias, C, N, NT, act_in=ACT_NONE, epi=EPI_STORE, act_ou
     rc = _account(tag or 'jodo_rowlinear', lambda: f(
         ptr(A), c_int(A.stride(0)), c_int(M), c_int(K), ptr(Wimg), ptr(bias), ptr(C), c_int(C.stride(0)), c_int(N),
         c_int(NT), c_int(act_in), c_int(epi), c_int(act_out), ptr(aux), c_int(0 if aux is None else aux.stride(0)),
-        ptr(gate), c_int(0 if gate is None else gate.stride(0)), ptr(row_mol), st))
+        ptr(gate), c_int(0 if gate is None else gate.stride(0)), ptr(row_mol), c_int(1 if out_f16 else 0), st))
     check(rc, 'jodo_rowlinear')
 
 

@@ -80,12 +80,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
   uint32_t par = 0;
   const float4* pos = reinterpret_cast<const float4*>(a.pos);
 
+  // row metadata of a tile is fetched one tile ahead
+  RowInfo rn = load_row(a.p, min(tile0, a.p.n_tiles - 1), row);
+  int ngn = a.p.tile_ngroups[min(tile0, a.p.n_tiles - 1)];
+  uint8_t exn = a.extra[(size_t)min(tile0, a.p.n_tiles - 1) * TILE_ROWS + row];
   for (int tile = tile0; tile < tile1; ++tile) {
-    const RowInfo r = load_row(a.p, tile, row);
-    const int ng = a.p.tile_ngroups[tile];
+    const RowInfo r = rn;
+    const int ng = ngn;
+    const uint8_t ex = exn;
     if (half == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
     const float* tr = a.tab + (size_t)r.mol * a.ld_tab + a.tab_off;
-    const uint8_t ex = a.extra[(size_t)tile * TILE_ROWS + row];
 
     // ---- distance features -> A0 chunk 0, columns [32*half, 32*half+32)
     {
@@ -98,6 +102,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
         for (int i = 0; i < 32; ++i) df[i] = 0.f;
       }
       st_rowh<32>(A0, row, 0, 4 * half, df);
+    }
+    {
+      const int nt_ = min(tile + 1, tile1 - 1);
+      rn = load_row(a.p, nt_, row);
+      ngn = a.p.tile_ngroups[nt_];
+      exn = a.extra[(size_t)nt_ * TILE_ROWS + row];
     }
     fence_async_smem();
     sync_tc();
@@ -149,34 +159,39 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
       mma_tile_h(tmem + 256, smem_u32(A0), smem_u32(smem + AT_W1), 256, 1, false);  // g1 pre-activation
       umma_commit(&bars[4]);
     }
+    // ---- logits of this half's 7 heads: a[s] = sum_ch q[g,s,ch] k[j,s,ch] tanh(g0[s,ch]) / sqrt(16)
+    // q / k rows are fp16; the loads of a 32-column chunk are issued one chunk ahead of its use
+    const uint16_t* qkv16 = static_cast<const uint16_t*>(a.qkv);
+    const uint16_t* qrow = qkv16 + (size_t)r.g * a.ldq + 128 * half;
+    const uint16_t* krow = qkv16 + (size_t)r.j * a.ldq + D_ + 128 * half;
+    const uint16_t* vrow = qkv16 + (size_t)r.j * a.ldq + 2 * D_ + 128 * half;
+    H32 qc = ldg_h32(qrow), kc = ldg_h32(krow);
     mbar_wait(&bars[3], par);
     tc_fence_after();
-
-    // ---- logits of this half's 7 heads: a[s] = sum_ch q[g,s,ch] k[j,s,ch] tanh(g0[s,ch]) / sqrt(16)
+    H32 vc;
     {
       float lg[7];
 #pragma unroll
       for (int s = 0; s < 7; ++s) lg[s] = 0.f;
-      const float* qrow = a.qkv + (size_t)r.g * a.ldq + 128 * half;
-      const float* krow = a.qkv + (size_t)r.j * a.ldq + D_ + 128 * half;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 q4[4], k4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          q4[i] = __ldg(reinterpret_cast<const float4*>(qrow + c * 16) + i);
-          k4[i] = __ldg(reinterpret_cast<const float4*>(krow + c * 16) + i);
-        }
-        float acc[16];
-        tmem_ld16(tmem_addr(tmem, 128 * half + c * 16), acc);
+      for (int c = 0; c < 4; ++c) {
+        H32 qn, kn;
+        if (c < 3) { qn = ldg_h32(qrow + (c + 1) * 32); kn = ldg_h32(krow + (c + 1) * 32); }
+        else vc = ldg_h32(vrow);
+        float acc[32];
+        tmem_ld32(tmem_addr(tmem, 128 * half + c * 32), acc);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int col = c * 16 + 4 * i;
-          if (col < HQ) lg[col / SC] = fmaf(q4[i].x * k4[i].x, tanh_fast(acc[4 * i]), lg[col / SC]);
-          if (col + 1 < HQ) lg[(col + 1) / SC] = fmaf(q4[i].y * k4[i].y, tanh_fast(acc[4 * i + 1]), lg[(col + 1) / SC]);
-          if (col + 2 < HQ) lg[(col + 2) / SC] = fmaf(q4[i].z * k4[i].z, tanh_fast(acc[4 * i + 2]), lg[(col + 2) / SC]);
-          if (col + 3 < HQ) lg[(col + 3) / SC] = fmaf(q4[i].w * k4[i].w, tanh_fast(acc[4 * i + 3]), lg[(col + 3) / SC]);
+          float qf[8], kf[8];
+          unpack8(qc.u[i], qf);
+          unpack8(kc.u[i], kf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col = c * 32 + 8 * i + e;
+            if (col < HQ) lg[col / SC] = fmaf(qf[e] * kf[e], tanh_fast(acc[8 * i + e]), lg[col / SC]);
+          }
         }
+        if (c < 3) { qc = qn; kc = kn; }
       }
       // head order of the reference: the two adjacency heads first (1 where adjacent, -1e10 otherwise,
       // models/layers.py:170-174), then the 14 computed heads
@@ -210,25 +225,22 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
     mbar_wait(&bars[4], par);
     tc_fence_after();
     {
-      const float* vrow = a.qkv + (size_t)r.j * a.ldq + 2 * D_ + 128 * half;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float4 v4[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v4[i] = __ldg(reinterpret_cast<const float4*>(vrow + c * 32) + i);
+      for (int c = 0; c < 4; ++c) {
+        H32 vn;
+        if (c < 3) vn = ldg_h32(vrow + (c + 1) * 32);
         float acc[32];
         tmem_ld32(tmem_addr(tmem, 256 + 128 * half + c * 32), acc);
-        const float al0 = c == 0 ? alpha[0] : c == 1 ? alpha[2] : c == 2 ? alpha[4] : alpha[6];
-        const float al1 = c == 0 ? alpha[1] : c == 1 ? alpha[3] : c == 2 ? alpha[5] : alpha[7];
         float* srow = S + row * 32;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float al = i < 4 ? al0 : al1;
-          srow[(4 * i) ^ lane] = v4[i].x * tanh_fast(acc[4 * i]) * al;
-          srow[(4 * i + 1) ^ lane] = v4[i].y * tanh_fast(acc[4 * i + 1]) * al;
-          srow[(4 * i + 2) ^ lane] = v4[i].z * tanh_fast(acc[4 * i + 2]) * al;
-          srow[(4 * i + 3) ^ lane] = v4[i].w * tanh_fast(acc[4 * i + 3]) * al;
+        for (int i = 0; i < 4; ++i) {
+          float vf[8];
+          unpack8(vc.u[i], vf);
+          const float al = alpha[2 * c + (i >> 1)];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) srow[(8 * i + e) ^ lane] = vf[e] * tanh_fast(acc[8 * i + e]) * al;
         }
+        if (c < 3) vc = vn;
         named_bar_sync(1 + half, 128);
         uint32_t m = starts;
         while (m) {

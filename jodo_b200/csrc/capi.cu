@@ -22,10 +22,11 @@ extern "C" {
 const char* jodo_last_error_string(void) { return g_err; }
 int jodo_abi_version(void) { return JODO_ABI_VERSION; }
 
-int jodo_rowlinear(const float* A, int lda, int M, int K, const float* Wimg, const float* bias, float* C, int ldc,
+int jodo_rowlinear(const float* A, int lda, int M, int K, const void* Wimg, const float* bias, void* C, int ldc,
                    int N, int NT, int act_in, int epi, int act_out, const float* aux, int ld_aux, const float* gate,
-                   int ld_gate, const int* row_mol, void* stream) {
-  jodo::RowLinearArgs a{A, lda, M, K, Wimg, bias, C, ldc, N, NT, act_in, epi, act_out, aux, ld_aux, gate, ld_gate, row_mol};
+                   int ld_gate, const int* row_mol, int out_f16, void* stream) {
+  jodo::RowLinearArgs a{A, lda, M, K, static_cast<const float*>(Wimg), bias, C, ldc, N, NT, act_in, epi, act_out, aux, ld_aux,
+                        gate, ld_gate, row_mol, out_f16};
   if (const char* m = jodo::check_rowlinear(a)) return fail(m);
   cudaError_t e = jodo::launch_rowlinear(a, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? JODO_OK : cuda_fail(e, "jodo_rowlinear");
@@ -100,14 +101,14 @@ int jodo_edge_embed(const jodo_edge_embed_args* a, void* stream) {
 int jodo_attn(const jodo_attn_args* a, void* stream) {
   if (!a) return fail("jodo_attn: null args");
   if (const char* m = check_plan(a->p)) return fail(m);
-  if (a->ldq % 4 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_attn: strides must be multiples of 4");
+  if (a->ldq % 8 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_attn: strides must be multiples of 4");
   if (!a->e16 || !a->hnode) return fail("jodo_attn: null buffer");
   JODO_LAUNCH(jodo::launch_attn(*a, num_sms(), S(stream)), "jodo_attn");
 }
 int jodo_edge_update(const jodo_edge_update_args* a, void* stream) {
   if (!a) return fail("jodo_edge_update: null args");
   if (const char* m = check_plan(a->p)) return fail(m);
-  if (a->ldp % 4 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_edge_update: strides must be multiples of 4");
+  if (a->ldp % 8 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_edge_update: strides must be multiples of 4");
   if (!a->e32 || !a->e16 || !a->eh) return fail("jodo_edge_update: null buffer");
   if (a->eh_col < 0 || a->eh_col + a->ce > 192) return fail("jodo_edge_update: edge-hidden slice out of range");
   JODO_LAUNCH(jodo::launch_edge_update(*a, num_sms(), S(stream)), "jodo_edge_update");
@@ -115,7 +116,7 @@ int jodo_edge_update(const jodo_edge_update_args* a, void* stream) {
 int jodo_equi(const jodo_equi_args* a, void* stream) {
   if (!a) return fail("jodo_equi: null args");
   if (const char* m = check_plan(a->p)) return fail(m);
-  if (a->ldab % 4 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_equi: strides must be multiples of 4");
+  if (a->ldab % 8 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_equi: strides must be multiples of 4");
   JODO_LAUNCH(jodo::launch_equi(*a, num_sms(), S(stream)), "jodo_equi");
 }
 int jodo_edge_head(const jodo_edge_head_args* a, void* stream) {

@@ -1,5 +1,6 @@
 // Helpers shared by the edge-tile kernels: row metadata, operand-row I/O, GBF, LayerNorm.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -68,6 +69,23 @@ __device__ __forceinline__ void st_row32(uint8_t* img, int row, int kc, const fl
     o.w = ROUND ? to_tf32(v[4 * p + 3]) : v[4 * p + 3];
     *reinterpret_cast<float4*>(img + img_piece(row, kc, p, CHUNK_BYTES_A)) = o;
   }
+}
+
+// 8 packed fp16 (one 16-byte load of a per-atom fp16 row) -> fp32
+__device__ __forceinline__ void unpack8(const uint4 u, float (&f)[8]) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
+  const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+// 32 consecutive fp16 columns of a per-atom row = 4 x 16-byte loads
+struct H32 { uint4 u[4]; };
+__device__ __forceinline__ H32 ldg_h32(const uint16_t* p) {
+  H32 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.u[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
+  return r;
 }
 
 // ---- fp16 operand rows: NH consecutive groups of 8 columns (16-byte pieces) starting at piece p0 of chunk kc

@@ -70,10 +70,12 @@ __global__ void __launch_bounds__(EU_THREADS, 1) k_edge_update(EdgeUpdateArgs a)
   const uint32_t tm_f = tmem, tm_y = tmem + 256, tm_l = tmem + 320;
   uint32_t par_e[2] = {0, 0}, par_m = 0;
 
+  RowInfo rn = load_row(a.p, min(tile0, a.p.n_tiles - 1), row);      // row metadata is fetched one tile ahead
+  const uint16_t* p16 = static_cast<const uint16_t*>(a.P);
   for (int tile = tile0; tile < tile1; ++tile) {
     const int buf = (tile - tile0) & 1;
     uint8_t* EA = smem + EU_EA + buf * E_TILE_BYTES;
-    const RowInfo r = load_row(a.p, tile, row);
+    const RowInfo r = rn;
     if (t == 0 && tile + 1 < tile1) {          // the other ring slot was fully consumed in the previous iteration
       mbar_expect_tx(&bars[1 + (buf ^ 1)], E_TILE_BYTES);
       bulk_g2s(smem + EU_EA + (buf ^ 1) * E_TILE_BYTES, reinterpret_cast<const uint8_t*>(a.e32) + (size_t)(tile + 1) * E_TILE_BYTES,
@@ -84,14 +86,16 @@ __global__ void __launch_bounds__(EU_THREADS, 1) k_edge_update(EdgeUpdateArgs a)
     // h_edge = P[g] + P[j] + b   (own 32 columns)
     float x[32];
     {
-      const float* pg = a.P + (size_t)r.g * a.ldp + c0;
-      const float* pj = a.P + (size_t)r.j * a.ldp + c0;
+      const H32 u = ldg_h32(p16 + (size_t)r.g * a.ldp + c0);
+      const H32 v = ldg_h32(p16 + (size_t)r.j * a.ldp + c0);
+      rn = load_row(a.p, min(tile + 1, tile1 - 1), row);
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 u = __ldg(reinterpret_cast<const float4*>(pg + i));
-        const float4 v = __ldg(reinterpret_cast<const float4*>(pj + i));
-        x[i] = u.x + v.x + bn[c0 + i]; x[i + 1] = u.y + v.y + bn[c0 + i + 1];
-        x[i + 2] = u.z + v.z + bn[c0 + i + 2]; x[i + 3] = u.w + v.w + bn[c0 + i + 3];
+      for (int i = 0; i < 4; ++i) {
+        float uf[8], vf[8];
+        unpack8(u.u[i], uf);
+        unpack8(v.u[i], vf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[8 * i + e] = uf[e] + vf[e] + bn[c0 + 8 * i + e];
       }
     }
     mbar_wait(&bars[1 + buf], par_e[buf]);

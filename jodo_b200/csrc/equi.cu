@@ -78,12 +78,21 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
   float4* pos_out = reinterpret_cast<float4*>(a.pos_out);
   const int cb = 128 * half;                      // first hidden column of this thread
 
+  // row metadata of a tile is fetched one tile ahead
+  RowInfo rn = load_row(a.p, min(tile0, a.p.n_tiles - 1), row);
+  int ngn = a.p.tile_ngroups[min(tile0, a.p.n_tiles - 1)];
+  uint8_t exn = a.extra[(size_t)min(tile0, a.p.n_tiles - 1) * TILE_ROWS + row];
+  const uint16_t* ab16 = static_cast<const uint16_t*>(a.AB);
   for (int tile = tile0; tile < tile1; ++tile) {
-    const RowInfo r = load_row(a.p, tile, row);
-    const int ng = a.p.tile_ngroups[tile];
+    const RowInfo r = rn;
+    const int ng = ngn;
+    const uint8_t ex = exn;
     const float* tr = a.tab + (size_t)r.mol * a.ld_tab + a.tab_off;
-    const uint8_t ex = a.extra[(size_t)tile * TILE_ROWS + row];
     const float4 pg = pos[r.g], pj = pos[r.j];
+    // hoisted input_lin parts (fp16 rows): first 32-column chunk in flight before the MMA wait
+    const uint16_t* ag = ab16 + (size_t)r.g * a.ldab + cb;
+    const uint16_t* bj = ab16 + (size_t)r.j * a.ldab + D_ + cb;
+    H32 uc = ldg_h32(ag), vc = ldg_h32(bj);
     {
       float df[32];
       if (r.valid) {
@@ -93,6 +102,12 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
         for (int i = 0; i < 32; ++i) df[i] = 0.f;
       }
       st_rowh<32>(U, row, 1, 4 * half, df);
+    }
+    {
+      const int nt_ = min(tile + 1, tile1 - 1);
+      rn = load_row(a.p, nt_, row);
+      ngn = a.p.tile_ngroups[nt_];
+      exn = a.extra[(size_t)nt_ * TILE_ROWS + row];
     }
     fence_async_smem();
     sync_tc();
@@ -114,30 +129,29 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
     // ---- pass 1: x = acc + A[g] + B[j] + b over this thread's 128 hidden units, kept in TMEM; row statistics
     float mean, rstd;
     {
-      const float* ag = a.AB + (size_t)r.g * a.ldab + cb;
-      const float* bj = a.AB + (size_t)r.j * a.ldab + D_ + cb;
       float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float4 u4[8], v4[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          u4[i] = __ldg(reinterpret_cast<const float4*>(ag + c * 32) + i);
-          v4[i] = __ldg(reinterpret_cast<const float4*>(bj + c * 32) + i);
-        }
+      for (int c = 0; c < 4; ++c) {
+        H32 un, vn;
+        if (c < 3) { un = ldg_h32(ag + (c + 1) * 32); vn = ldg_h32(bj + (c + 1) * 32); }
         float x[32];
         tmem_ld32(tmem_addr(tm_x, cb + c * 32), x);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b_in + cb + c * 32) + i);
-          x[4 * i] += u4[i].x + v4[i].x + b4.x;
-          x[4 * i + 1] += u4[i].y + v4[i].y + b4.y;
-          x[4 * i + 2] += u4[i].z + v4[i].z + b4.z;
-          x[4 * i + 3] += u4[i].w + v4[i].w + b4.w;
+        for (int i = 0; i < 4; ++i) {
+          float uf[8], vf[8];
+          unpack8(uc.u[i], uf);
+          unpack8(vc.u[i], vf);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.b_in + cb + c * 32 + 8 * i));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.b_in + cb + c * 32 + 8 * i + 4));
+          x[8 * i] += uf[0] + vf[0] + b0.x; x[8 * i + 1] += uf[1] + vf[1] + b0.y;
+          x[8 * i + 2] += uf[2] + vf[2] + b0.z; x[8 * i + 3] += uf[3] + vf[3] + b0.w;
+          x[8 * i + 4] += uf[4] + vf[4] + b1.x; x[8 * i + 5] += uf[5] + vf[5] + b1.y;
+          x[8 * i + 6] += uf[6] + vf[6] + b1.z; x[8 * i + 7] += uf[7] + vf[7] + b1.w;
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) { s1 += x[i]; s2 = fmaf(x[i], x[i], s2); }
         tmem_st32(tmem_addr(tm_x, cb + c * 32), x);
+        if (c < 3) { uc = un; vc = vn; }
       }
       tmem_wait_st();
       LNS[row * 2 + half] = make_float2(s1, s2);

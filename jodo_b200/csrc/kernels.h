@@ -13,12 +13,13 @@ struct RowLinearArgs {
   const float* A; int lda; int M; int K;        // activations, row-major, K % 32 == 0 (zero padded)
   const float* Wimg;                            // weight image [N/NT][K/32][NT][128 B]
   const float* bias;                            // [N] or null
-  float* C; int ldc; int N; int NT;             // output, row-major
+  void* C; int ldc; int N; int NT;              // output, row-major fp32 (or fp16 when out_f16; ldc in elements)
   int act_in;                                   // applied to A on load
   int epi; int act_out;
   const float* aux; int ld_aux;                 // EPI_ADD addend / EPI_GATED_RES residual
   const float* gate; int ld_gate;               // EPI_GATED_RES: gate[row_mol[row], col]
   const int* row_mol;
+  int out_f16;                                  // EPI_STORE only: write fp16 (saturating) instead of fp32
 };
 const char* check_rowlinear(const RowLinearArgs& a);
 cudaError_t launch_rowlinear(const RowLinearArgs& a, cudaStream_t stream);

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(RL_THREADS, 2) k_rowlinear(RowLinearArgs a) {
         for (int i = 0; i < 16; ++i) { x[i] = h[i]; x[i + 16] = 0.f; }
       }
       if (live) {
+        float* C32 = static_cast<float*>(a.C);
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           if (i < ncols) {
@@ -159,7 +160,20 @@ __global__ void __launch_bounds__(RL_THREADS, 2) k_rowlinear(RowLinearArgs a) {
               const float4 g = __ldg(reinterpret_cast<const float4*>(a.gate + (size_t)mol * a.ld_gate + col));
               o.x = fmaf(g.x, o.x, y.x); o.y = fmaf(g.y, o.y, y.y); o.z = fmaf(g.z, o.z, y.z); o.w = fmaf(g.w, o.w, y.w);
             }
-            *reinterpret_cast<float4*>(a.C + (size_t)gr * a.ldc + col) = o;
+            if (!a.out_f16) *reinterpret_cast<float4*>(C32 + (size_t)gr * a.ldc + col) = o;
+            x[i] = o.x; x[i + 1] = o.y; x[i + 2] = o.z; x[i + 3] = o.w;
+          }
+        }
+        if (a.out_f16) {
+          uint16_t* C16 = static_cast<uint16_t*>(a.C) + (size_t)gr * a.ldc + n0 + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            if (i < ncols) {
+              uint4 o;
+              o.x = pack_h2(x[i], x[i + 1]); o.y = pack_h2(x[i + 2], x[i + 3]);
+              o.z = pack_h2(x[i + 4], x[i + 5]); o.w = pack_h2(x[i + 6], x[i + 7]);
+              *reinterpret_cast<uint4*>(C16 + i) = o;
+            }
           }
         }
       }
@@ -177,7 +191,8 @@ const char* check_rowlinear(const RowLinearArgs& a) {
   if (a.K <= 0 || a.K % 64) return "rowlinear: K must be a positive multiple of 64";
   if (!(a.NT == 16 || a.NT == 32 || a.NT == 64 || a.NT == 128 || a.NT == 256)) return "rowlinear: NT must be 16/32/64/128/256";
   if (a.N <= 0 || a.N % a.NT) return "rowlinear: N must be a multiple of NT";
-  if (a.lda % 4 || a.ldc % 4) return "rowlinear: lda/ldc must be multiples of 4";
+  if (a.lda % 4 || a.ldc % (a.out_f16 ? 8 : 4)) return "rowlinear: lda/ldc must be multiples of 4 (8 for fp16 output)";
+  if (a.out_f16 && a.epi != EPI_STORE) return "rowlinear: fp16 output supports EPI_STORE only";
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.C) | reinterpret_cast<uintptr_t>(a.Wimg)) & 15)
     return "rowlinear: pointers must be 16-byte aligned";
   if ((a.epi == EPI_ADD || a.epi == EPI_GATED_RES) && (!a.aux || a.ld_aux % 4)) return "rowlinear: aux missing";

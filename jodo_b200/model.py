@@ -46,12 +46,13 @@ class _Workspace:
         self.ah = zf(Nn, meta['ld_ah'])                    # concatenated atom hiddens (pads stay 0)
         self.h = [f(Nn, D), f(Nn, D)]
         self.hn = f(Nn, D)
-        self.qkv = f(Nn, 3 * D)
+        h16 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float16)
+        self.qkv = h16(Nn, 3 * D)                           # fp16 per-atom operands gathered by the edge kernels
         self.hnode = zf(Nn, D)                             # atoms without partners are never written: stay 0
-        self.pbuf = f(Nn, 64)
+        self.pbuf = h16(Nn, 64)
         self.h2 = f(Nn, D)
         self.ff = f(Nn, d.r * D)
-        self.ab = f(Nn, 2 * D)
+        self.ab = h16(Nn, 2 * D)
         self.n1 = f(Nn, D)
         self.n2 = f(Nn, D // 2)
         self.ap = f(Nn, meta['npred4']['N'])
@@ -175,20 +176,20 @@ class _DGTBase(nn.Module):
             # norm1_node + modulate, q/k/v
             _lib.call('jodo_ln_mod', _c(D), _lib.ptr(h), _c(h.stride(0)), None, _c(0), _lib.ptr(ws.tab), _c(ld_tab),
                       _c(0), _c(off), _c(off + D), ctypes.byref(ps), _lib.ptr(ws.hn), _c(D), st)
-            lin(p + 'qkv', ws.hn, ws.qkv)
+            lin(p + 'qkv', ws.hn, ws.qkv, out_f16=True)
             aa = _lib.AttnArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(ws.qkv), 3 * D, _lib.dp(ws.tab), ld_tab,
                                off, _lib.dp(ws.extra), pk.ptr(p + 'gbf'), pk.ptr(p + 'emb.img'), pk.ptr(p + 'emb.b'),
                                pk.ptr(p + 'e0.img'), pk.ptr(p + 'e1.img'), _lib.dp(ws.hnode))
             _lib.call('jodo_attn', ctypes.byref(aa), st)
             # node path: hoisted node2edge, gated residual + norm2 + FFN, hoisted input_lin parts, node_l
-            lin(p + 'n2e', ws.hnode, ws.pbuf)
+            lin(p + 'n2e', ws.hnode, ws.pbuf, out_f16=True)
             _lib.call('jodo_ln_mod', _c(D), _lib.ptr(h), _c(h.stride(0)), _lib.ptr(ws.hnode), _c(D), _lib.ptr(ws.tab),
                       _c(ld_tab), _c(off + 2 * D), _c(off + 3 * D), _c(off + 4 * D), ctypes.byref(ps), _lib.ptr(ws.h2),
                       _c(D), st)
             lin(p + 'ff1', ws.h2, ws.ff, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)
             lin(p + 'ff2', ws.ff, hout, epi=_lib.EPI_GATED_RES, aux=ws.h2, gate=ws.tab[:, off + 5 * D:],
                 row_mol=plan.node_mol)
-            lin(p + 'ab', hout, ws.ab)
+            lin(p + 'ab', hout, ws.ab, out_f16=True)
             lin(p + 'node_l', hout, ws.ah[:, D + l * meta['cnp']:])
             # edge path
             ua = _lib.EdgeUpdateArgs(ps, _lib.dp(ws.e), _lib.dp(ws.e16), _lib.dp(ws.pbuf), 64, pk.ptr(p + 'n2e.bias'),

@@ -73,9 +73,9 @@ def run_case(name, device='cuda', verbose=True):
         qk = ob['q'].shape[-1]
         hq = qk // 2                      # q / k are stored as two head halves at columns [0, qk/2) and [D/2, D/2 + qk/2)
         unsplit = lambda x: torch.cat([x[:, :hq], x[:, D // 2:D // 2 + hq]], dim=1)
-        rep.append((f'b{l}.q', rel(packed_to_dense(plan, unsplit(b['qkv'][:, :D])), ob['q'] * m)))
-        rep.append((f'b{l}.k', rel(packed_to_dense(plan, unsplit(b['qkv'][:, D:2 * D])), ob['k'] * m)))
-        rep.append((f'b{l}.v', rel(packed_to_dense(plan, b['qkv'][:, 2 * D:]), ob['v'] * m)))
+        rep.append((f'b{l}.q', rel(packed_to_dense(plan, unsplit(b['qkv'].float()[:, :D])), ob['q'] * m)))
+        rep.append((f'b{l}.k', rel(packed_to_dense(plan, unsplit(b['qkv'].float()[:, D:2 * D])), ob['k'] * m)))
+        rep.append((f'b{l}.v', rel(packed_to_dense(plan, b['qkv'].float()[:, 2 * D:]), ob['v'] * m)))
         rep.append((f'b{l}.hnode', rel(packed_to_dense(plan, b['hnode']), ob['hnode'] * m)))
         rep.append((f'b{l}.h', rel(packed_to_dense(plan, b['h']), ob['h'])))
         rep.append((f'b{l}.e', rel(tiles_to_dense(plan, b['e'], 64), ob['e'] * em)))
