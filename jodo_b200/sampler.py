@@ -58,11 +58,13 @@ def edge_noise(B, N, ch, edge_mask, generator=None):
     return z.permute(0, 2, 3, 1) * edge_mask.reshape(B, N, N, 1)
 
 
-def ancestral_coefficients(schedule, time_steps):
+def ancestral_coefficients(schedule, time_steps, s_array=None):
     """Per-step scalars of the ancestral update, evaluated in fp32 with the reference's operation
-    order (sampling.py:536-549).  Returns a CPU tensor [steps, 4]: (c_x, c_pred, sigma, noise_level)."""
+    order (sampling.py:536-549).  Returns a CPU tensor [steps, 4]: (c_x, c_pred, sigma, noise_level).
+    s_array: the "next" time of every step; default = the grid shifted by one with 0 appended
+    (sampling.py:523)."""
     t = time_steps.float().cpu()
-    s = torch.cat([t[1:], torch.zeros(1)])
+    s = torch.cat([t[1:], torch.zeros(1)]) if s_array is None else s_array.float().cpu()
     alpha_t, sigma_t = schedule.marginal_prob(t)
     alpha_s, sigma_s = schedule.marginal_prob(s)
     alpha_ts = alpha_t / alpha_s
@@ -78,10 +80,10 @@ class AncestralSampler:
     """Ancestral sampling for joint 2D & 3D generation (reference sampling.py:518-596) with
     self-conditioning ('ori' hand-off, reference utils.py:134-136)."""
 
-    def __init__(self, schedule, time_steps, generator=None, noise_fn=None):
+    def __init__(self, schedule, time_steps, generator=None, noise_fn=None, s_array=None):
         self.schedule = schedule
         self.t_array = time_steps
-        self.coef = ancestral_coefficients(schedule, time_steps)
+        self.coef = ancestral_coefficients(schedule, time_steps, s_array)
         self.generator = generator
         self.noise_fn = noise_fn          # optional (step, kind, shape...) -> tensor, for replayed noise
 

@@ -1,0 +1,21 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench lines, ncu launch list, ncu full captures of the edge kernels.
+# usage (from the repo root, under gpurun): bash tools/gpu_round.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.sw_power_cap --format=csv -lms 500 > $OUT/clocks.csv &
+SMI=$!
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+tail -5 $OUT/pytest_gpu.log
+timeout 600 python bench.py --steps 30 --warmup 5 > $OUT/bench_qm9.json 2> $OUT/bench_qm9.err; echo "bench qm9 rc=$?"
+timeout 600 python bench.py --workload geom --steps 20 --warmup 3 > $OUT/bench_geom.json 2> $OUT/bench_geom.err; echo "bench geom rc=$?"
+timeout 300 python bench.py --impl reference --steps 4 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "bench ref rc=$?"
+kill $SMI
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/launches_run.log 2>&1; echo "ncu launches rc=$?"
+for k in k_attn k_equi k_edge_update k_rowlinear; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 12 -c 2 -f -o $OUT/prof_$k \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/prof_$k.log 2>&1; echo "ncu $k rc=$?"
+done
+cat $OUT/bench_qm9.json | head -c 3000
