@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 2
+#define JODO_ABI_VERSION 3
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -49,6 +49,27 @@ int jodo_abi_version(void);
 int jodo_rowlinear(const float* A, int lda, int M, int K, const void* Wimg, const float* bias, void* C, int ldc,
                    int N, int NT, int act_in, int epi, int act_out, const float* aux, int ld_aux, const float* gate,
                    int ld_gate, const int* row_mol, int out_f16, void* stream);
+
+
+/* Persistent, TMA-fed variant of jodo_rowlinear for the per-atom GEMMs of a DGT block: the activation operand is
+ * an fp16 operand image in HBM, [ceil(M/128)][K/64][128 rows][128 bytes] (K-major SWIZZLE_128B, the layout
+ * jodo_ln_mod_img and this kernel's own image output write), so both operands are bulk-copied into shared memory
+ * and the epilogue of one 128 x NT tile overlaps the tcgen05 main loop of the next (two TMEM accumulators).
+ * Replaces the same reference nn.Linear call sites as jodo_rowlinear (models/layers.py:147-149,
+ * models/mol_gnn.py:262-264, 304-311, 567, 73-79).  Any subset of the three outputs may be requested. */
+typedef struct jodo_imglinear_args {
+  const void* Aimg; int M, K;             /* fp16 activation image; M real rows */
+  const void* Wimg; const float* bias;    /* fp16 weight image [N/NT][K/64][NT][128 B]; bias [N] or null */
+  int N, NT;
+  int epi, act_out;                       /* JODO_EPI_STORE | JODO_EPI_ACT | JODO_EPI_GATED_RES */
+  const float* aux; int ld_aux;           /* GATED_RES: residual rows */
+  const float* gate; int ld_gate;         /* GATED_RES: gate[row_mol[row], col] */
+  const int* row_mol;
+  float* C32; int ldc32;                  /* fp32 row-major output or null */
+  void* C16; int ldc16;                   /* fp16 row-major output or null (ld in elements) */
+  void* Cimg;                             /* fp16 operand image output [ceil(M/128)][N/64][128][128 B] or null */
+} jodo_imglinear_args;
+int jodo_imglinear(const jodo_imglinear_args* a, void* stream);
 
 
 /* ---- varlen plan and argument blocks of the edge-tile kernels ------------------------------------
@@ -144,6 +165,12 @@ int jodo_gather_nodes(const float* xh, const float* cond_x, const jodo_plan* p, 
                       void* stream);
 int jodo_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
                 int off_shift, int off_scale, const jodo_plan* p, float* out, int ldo, void* stream);
+/* jodo_ln_mod with fp16 operand-image outputs (D = 256): out_img = image of LN(x + gate*y)*(1+scale)+shift,
+ * out32 (optional) the same rows in fp32, y_img (optional) the image of y itself (the attention output that
+ * node2edge_lin consumes, reference models/mol_gnn.py:304-305).  Rows beyond Nn of the last tile are zeroed. */
+int jodo_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
+                    int off_shift, int off_scale, const jodo_plan* p, float* out32, int ldo, void* out_img, void* y_img,
+                    void* stream);
 int jodo_com(float* pos4, const jodo_plan* p, void* stream);
 int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, int inn,
                   float* out_dense, void* stream);

@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 2:
+        if _lib.jodo_abi_version() != 3:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -124,6 +124,24 @@ class EquiArgs(ctypes.Structure):
 class EdgeHeadArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('eh', _P), ('eh_tile_bytes', _Z), ('keh', _I), ('w0_img', _P), ('b0', _P),
                 ('w2_img', _P), ('b2', _P), ('w4', _P), ('b4', _P), ('ch', _I), ('out_dense', _P)]
+
+
+class ImgLinearArgs(ctypes.Structure):
+    _fields_ = [('Aimg', _P), ('M', _I), ('K', _I), ('Wimg', _P), ('bias', _P), ('N', _I), ('NT', _I), ('epi', _I),
+                ('act_out', _I), ('aux', _P), ('ld_aux', _I), ('gate', _P), ('ld_gate', _I), ('row_mol', _P),
+                ('C32', _P), ('ldc32', _I), ('C16', _P), ('ldc16', _I), ('Cimg', _P)]
+
+
+def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None, row_mol=None,
+              C32=None, C16=None, Cimg=None, stream=None, tag=None):
+    """Persistent TMA-fed GEMM on an fp16 activation image (include/jodo_b200.h: jodo_imglinear).
+    C32 / C16 are 2-D row-major views (stride(1) == 1), Cimg a flat fp16 image buffer."""
+    a = ImgLinearArgs(dp(Aimg), M, K, dp(Wimg), dp(bias), N, NT, epi, act_out, dp(aux),
+                      0 if aux is None else aux.stride(0), dp(gate), 0 if gate is None else gate.stride(0), dp(row_mol),
+                      dp(C32), 0 if C32 is None else C32.stride(0), dp(C16), 0 if C16 is None else C16.stride(0), dp(Cimg))
+    st = stream if stream is not None else stream_ptr()
+    f = lib().jodo_imglinear
+    check(_account(tag or 'jodo_imglinear', lambda: f(ctypes.byref(a), st)), 'jodo_imglinear')
 
 
 def dp(t):

@@ -69,6 +69,21 @@ int jodo_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const f
   JODO_LAUNCH(jodo::launch_ln_mod(D, x, ldx, y, ldy, tab, ld_tab, off_gate, off_shift, off_scale, *p, out, ldo, S(stream)),
               "jodo_ln_mod");
 }
+int jodo_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
+                    int off_shift, int off_scale, const jodo_plan* p, float* out32, int ldo, void* out_img, void* y_img,
+                    void* stream) {
+  if (!p || !x || !tab || !out_img) return fail("jodo_ln_mod_img: null pointer");
+  if ((ldx % 4) || (y && (ldy % 4)) || (out32 && (ldo % 4)) || (ld_tab % 4) || (off_gate % 4) || (off_shift % 4) || (off_scale % 4))
+    return fail("jodo_ln_mod_img: strides and offsets must be multiples of 4");
+  JODO_LAUNCH(jodo::launch_ln_mod_img(x, ldx, y, ldy, tab, ld_tab, off_gate, off_shift, off_scale, *p, out32, ldo, out_img,
+                                      y_img, S(stream)),
+              "jodo_ln_mod_img");
+}
+int jodo_imglinear(const jodo_imglinear_args* a, void* stream) {
+  if (!a) return fail("jodo_imglinear: null args");
+  if (const char* m = jodo::check_imglinear(*a)) return fail(m);
+  JODO_LAUNCH(jodo::launch_imglinear(*a, num_sms(), S(stream)), "jodo_imglinear");
+}
 int jodo_com(float* pos4, const jodo_plan* p, void* stream) { JODO_LAUNCH(jodo::launch_com(pos4, *p, S(stream)), "jodo_com"); }
 int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, int inn,
                   float* out_dense, void* stream) {

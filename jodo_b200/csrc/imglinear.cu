@@ -1,0 +1,276 @@
+// Persistent tensor-core row-linear on fp16 operand images:  C[M, N] = epi( A[M, K] * W[N, K]^T + bias ).
+//
+// This is the per-atom GEMM of every DGT block (reference models/layers.py:147-149 lin_query/key/value,
+// models/mol_gnn.py:262-264,309-311 node FFN, :304-305 hoisted node2edge_lin, :73,79 hoisted input_lin parts,
+// :567 node_i): the activations already live in HBM as fp16 operand images (written by jodo_ln_mod_img or by the
+// epilogue of the previous GEMM), so both operands reach shared memory through the TMA engine with no register
+// staging, and the kernel is a warp-specialised pipeline:
+//
+//   warp 0      producer: cp.async.bulk of the (A chunk, W chunk) pair of every K step into a ring of stages
+//   warp 1      MMA issuer: tcgen05.mma kind::f16 into one of two TMEM accumulators; tcgen05.commit frees the stage
+//   warps 2..9  epilogue: TMEM -> registers -> bias / activation / gated residual -> fp32 rows, fp16 rows and/or
+//               the fp16 operand image of the next GEMM; then the accumulator is handed back to the MMA warp
+//
+// A CTA walks work units (128-row tile, NT-column tile) with the column tile fastest, so the CTAs that share an A
+// tile run at the same time and re-read it from L2.  The epilogue of unit i overlaps the main loop of unit i+1.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace jodo {
+
+namespace {
+
+constexpr int IL_THREADS = 320;
+constexpr int IL_EPI_WARPS = 8;
+constexpr int IL_A_STAGE = TILE_ROWS * 128;          // 16 KB: [128 rows][64 fp16]
+constexpr int IL_RING_BYTES = 147456;                // 144 KB of stages (3 x 48 KB at NT = 256)
+constexpr int IL_MAX_STAGES = 6;
+constexpr int IL_STG_ROW = 144;                      // staging row: 32 fp32 + 16 bytes of padding (conflict-free both ways)
+constexpr int IL_STG_BUF = TILE_ROWS * IL_STG_ROW;   // 18 KB
+constexpr int IL_STG_BYTES = 2 * 2 * IL_STG_BUF;     // 2 column-half teams x 2 buffers
+constexpr int IL_SMEM = 1024 + IL_RING_BYTES + IL_STG_BYTES + 512;
+static_assert(IL_SMEM <= 232448, "shared memory budget");
+
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == ACT_SILU) return silu_fast(x);
+  if (act == ACT_GELU) return gelu_f(x);
+  return x;
+}
+
+// MODE < 0: every epilogue option is a run-time flag.  MODE >= 0 fixes them at compile time (the four combinations
+// a DGT block uses), which removes the predicated paths from the epilogue's dependent instruction stream:
+//   bits [0,2) epilogue | bit 2 fp32 rows | bit 3 fp16 rows | bit 4 fp16 image
+constexpr int il_mode(int epi, bool c32, bool c16, bool cimg) { return epi | (c32 ? 4 : 0) | (c16 ? 8 : 0) | (cimg ? 16 : 0); }
+
+template <int MODE>
+__global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nt = a.NT;
+  const int stage_bytes = IL_A_STAGE + nt * 128;
+  int stages = IL_RING_BYTES / stage_bytes;
+  if (stages > IL_MAX_STAGES) stages = IL_MAX_STAGES;
+  uint8_t* stg_base = smem + IL_RING_BYTES;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + IL_RING_BYTES + IL_STG_BYTES);   // operands landed
+  uint64_t* bar_empty = bar_full + IL_MAX_STAGES;                              // MMAs of the stage done
+  uint64_t* bar_tfull = bar_empty + IL_MAX_STAGES;                             // [2] accumulator complete
+  uint64_t* bar_tempty = bar_tfull + 2;                                        // [2] accumulator drained (8 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = a.K / 64;
+  const int ntn = a.N / nt;
+  const int mt = (a.M + TILE_ROWS - 1) / TILE_ROWS;
+  const int units = mt * ntn;
+
+  if (tid == 0) {
+    for (int s = 0; s < IL_MAX_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], IL_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      const uint8_t* Aimg = static_cast<const uint8_t*>(a.Aimg);
+      const uint8_t* Wimg = static_cast<const uint8_t*>(a.Wimg);
+      const uint32_t wbytes = (uint32_t)nt * 128u;
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int m = u / ntn, n = u - m * ntn;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1u;
+          mbar_wait(&bar_empty[s], ph ^ 1u);
+          uint8_t* dst = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&bar_full[s], IL_A_STAGE + wbytes);
+          bulk_g2s(dst, Aimg + ((size_t)m * nk + kc) * IL_A_STAGE, IL_A_STAGE, &bar_full[s]);
+          bulk_g2s(dst + IL_A_STAGE, Wimg + ((size_t)n * nk + kc) * wbytes, wbytes, &bar_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(nt);
+      uint32_t it = 0, ai = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++ai) {
+        const uint32_t ab = ai & 1u, aph = (ai >> 1) & 1u;
+        mbar_wait(&bar_tempty[ab], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t td = tmem + ab * 256u;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1u;
+          mbar_wait(&bar_full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sw = sa + IL_A_STAGE;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(td, umma_desc_sw128(sa + kk * 32), umma_desc_sw128(sw + kk * 32), idesc, (kc | kk) ? 1u : 0u);
+          umma_commit(&bar_empty[s]);
+        }
+        umma_commit(&bar_tfull[ab]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps = 2 column-half teams)
+    // Each team drains its half of the accumulator 32 columns at a time: TMEM -> registers (thread = row) -> padded
+    // fp32 staging rows in shared memory -> team barrier -> "row-major" pass in which 8 lanes cover the 128 bytes of
+    // one row, so that bias / residual / gate loads and every store are coalesced.
+    const int ew = warp - 2;
+    const int rq = warp & 3;                       // TMEM lane quarter this warp may read
+    const int team = ew >> 2;                      // column half
+    const int wt = ((rq - 2) & 3);                 // warp index inside the team (0..3), any bijection works
+    const int row = rq * 32 + lane;
+    const int cw = nt / 2;                         // columns per team (32, 64 or 128)
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    const int epi = MODE < 0 ? a.epi : (MODE & 3);
+    const bool has32 = MODE < 0 ? a.C32 != nullptr : (MODE & 4) != 0;
+    const bool has16 = MODE < 0 ? a.C16 != nullptr : (MODE & 8) != 0;
+    const bool hasimg = MODE < 0 ? a.Cimg != nullptr : (MODE & 16) != 0;
+    const int act = a.act_out;
+    const float* __restrict__ bias = a.bias;
+    const float* __restrict__ aux = a.aux;
+    const float* __restrict__ gate = a.gate;
+    float* __restrict__ C32 = a.C32;
+    uint16_t* __restrict__ C16 = static_cast<uint16_t*>(a.C16);
+    uint8_t* __restrict__ Cimg = static_cast<uint8_t*>(a.Cimg);
+    const int ld_aux = a.ld_aux, ld_gate = a.ld_gate, ldc32 = a.ldc32, ldc16 = a.ldc16, Mrows = a.M, nchunk_out = a.N / 64;
+    uint8_t* stg = stg_base + team * 2 * IL_STG_BUF;
+    const int r0 = wt * 4 + rsub;                  // this thread's rows in the row-major pass: r0 + 16 * it
+    uint32_t ai = 0, sb = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ai) {
+      const int m = u / ntn, n = u - m * ntn;
+      const uint32_t ab = ai & 1u, aph = (ai >> 1) & 1u;
+      const int gr0 = m * TILE_ROWS + r0;
+      int mol[8];
+      if (epi == EPI_GATED_RES) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) mol[it] = (gr0 + 16 * it) < Mrows ? __ldg(a.row_mol + gr0 + 16 * it) : 0;
+      }
+      mbar_wait(&bar_tfull[ab], aph);
+      tc_fence_after();
+      for (int c0 = team * cw; c0 < (team + 1) * cw; c0 += 32, sb ^= 1u) {
+        uint8_t* buf = stg + sb * IL_STG_BUF;
+        const int col = n * nt + c0 + c4;
+        // loads that do not depend on the accumulator go first
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + col));
+        float4 y[8], g[8];
+        if (epi == EPI_GATED_RES) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int gr = gr0 + 16 * it;
+            if (gr < Mrows) {
+              y[it] = *reinterpret_cast<const float4*>(aux + (size_t)gr * ld_aux + col);
+              g[it] = __ldg(reinterpret_cast<const float4*>(gate + (size_t)mol[it] * ld_gate + col));
+            } else {
+              y[it] = g[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+        {
+          float x[32];
+          tmem_ld32(tmem + ab * 256u + ((uint32_t)rq << 21) + (uint32_t)c0, x);
+#pragma unroll
+          for (int p = 0; p < 8; ++p)
+            *reinterpret_cast<float4*>(buf + row * IL_STG_ROW + p * 16) = make_float4(x[4 * p], x[4 * p + 1], x[4 * p + 2], x[4 * p + 3]);
+        }
+        named_bar_sync(1 + team, 128);             // staging buffer sb complete (the other buffer may still be read)
+        const uint8_t* src = buf + r0 * IL_STG_ROW + c4 * 4;
+        uint8_t* img = hasimg ? Cimg + ((size_t)m * nchunk_out + (col >> 6)) * IL_A_STAGE + ((col & 4) << 1) : nullptr;
+        const int piece = (col & 63) >> 3;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = r0 + 16 * it;
+          const int gr = gr0 + 16 * it;
+          const bool live = gr < Mrows;
+          float4 o = *reinterpret_cast<const float4*>(src + it * 16 * IL_STG_ROW);
+          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          if (epi == EPI_ACT) {
+            if (MODE >= 0 || act == ACT_SILU) {     // the compiled modes use SiLU (node FFN)
+              o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w);
+            } else {
+              o.x = act_apply(o.x, act); o.y = act_apply(o.y, act); o.z = act_apply(o.z, act); o.w = act_apply(o.w, act);
+            }
+          } else if (epi == EPI_GATED_RES) {        // out = res + gate[mol] * (acc + bias)
+            o.x = fmaf(g[it].x, o.x, y[it].x); o.y = fmaf(g[it].y, o.y, y[it].y);
+            o.z = fmaf(g[it].z, o.z, y[it].z); o.w = fmaf(g[it].w, o.w, y[it].w);
+          }
+          if (!live) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has32 && live) *reinterpret_cast<float4*>(C32 + (size_t)gr * ldc32 + col) = o;
+          const uint2 hh = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+          if (has16 && live) *reinterpret_cast<uint2*>(C16 + (size_t)gr * ldc16 + col) = hh;
+          if (hasimg) *reinterpret_cast<uint2*>(img + img_piece(r, 0, piece, IL_A_STAGE)) = hh;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&bar_tempty[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+const char* check_imglinear(const ImgLinearArgs& a) {
+  if (a.M <= 0) return "imglinear: M <= 0";
+  if (a.K <= 0 || a.K % 64) return "imglinear: K must be a positive multiple of 64";
+  if (!(a.NT == 64 || a.NT == 128 || a.NT == 256)) return "imglinear: NT must be 64/128/256";
+  if (a.N <= 0 || a.N % a.NT) return "imglinear: N must be a multiple of NT";
+  if (!a.Aimg || !a.Wimg) return "imglinear: operand image missing";
+  if ((reinterpret_cast<uintptr_t>(a.Aimg) | reinterpret_cast<uintptr_t>(a.Wimg)) & 127) return "imglinear: images must be 128-byte aligned";
+  if (!a.C32 && !a.C16 && !a.Cimg) return "imglinear: no output";
+  if (a.C32 && ((a.ldc32 % 4) || (reinterpret_cast<uintptr_t>(a.C32) & 15))) return "imglinear: fp32 output must be 16-byte aligned rows";
+  if (a.C16 && ((a.ldc16 % 8) || (reinterpret_cast<uintptr_t>(a.C16) & 15))) return "imglinear: fp16 output must be 16-byte aligned rows";
+  if (a.Cimg && ((a.N % 64) || (reinterpret_cast<uintptr_t>(a.Cimg) & 127))) return "imglinear: image output needs N % 64 == 0";
+  if (a.epi != EPI_STORE && a.epi != EPI_ACT && a.epi != EPI_GATED_RES) return "imglinear: unsupported epilogue";
+  if (a.epi == EPI_GATED_RES && (!a.aux || !a.gate || !a.row_mol || (a.ld_aux % 4) || (a.ld_gate % 4))) return "imglinear: aux/gate/row_mol missing";
+  return nullptr;
+}
+
+namespace {
+template <int MODE>
+cudaError_t launch_mode(const ImgLinearArgs& a, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_imglinear<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, IL_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_imglinear<MODE><<<grid, IL_THREADS, IL_SMEM, stream>>>(a);
+  return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_imglinear(const ImgLinearArgs& a, int num_sms, cudaStream_t stream) {
+  const int units = ((a.M + TILE_ROWS - 1) / TILE_ROWS) * (a.N / a.NT);
+  const int grid = units < num_sms ? units : num_sms;
+  const int mode = il_mode(a.epi, a.C32 != nullptr, a.C16 != nullptr, a.Cimg != nullptr);
+  const bool silu_or_none = a.epi != EPI_ACT || a.act_out == ACT_SILU;
+  if (silu_or_none) {
+    switch (mode) {
+      case il_mode(EPI_STORE, false, true, false): return launch_mode<il_mode(EPI_STORE, false, true, false)>(a, grid, stream);      // q|k|v, hoisted parts
+      case il_mode(EPI_STORE, true, false, false): return launch_mode<il_mode(EPI_STORE, true, false, false)>(a, grid, stream);      // node_i
+      case il_mode(EPI_ACT, false, false, true): return launch_mode<il_mode(EPI_ACT, false, false, true)>(a, grid, stream);          // ff_linear1
+      case il_mode(EPI_GATED_RES, true, false, true): return launch_mode<il_mode(EPI_GATED_RES, true, false, true)>(a, grid, stream);  // ff_linear2
+      default: break;
+    }
+  }
+  return launch_mode<-1>(a, grid, stream);
+}
+
+}  // namespace jodo

@@ -24,6 +24,10 @@ struct RowLinearArgs {
 const char* check_rowlinear(const RowLinearArgs& a);
 cudaError_t launch_rowlinear(const RowLinearArgs& a, cudaStream_t stream);
 
+using ImgLinearArgs = ::jodo_imglinear_args;
+const char* check_imglinear(const ImgLinearArgs& a);
+cudaError_t launch_imglinear(const ImgLinearArgs& a, int num_sms, cudaStream_t stream);
+
 // ---- per-molecule AdaLN table layout (floats from the start of a molecule's table row) -------------
 // [0,2)  model-level GBF (scale, shift); then per layer l at TAB_HEAD + l*tab_layer_stride(D):
 //   node  shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp   (6 x D)
@@ -57,6 +61,9 @@ cudaError_t launch_gather_nodes(const float* xh, const float* cond_x, const Plan
 cudaError_t launch_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab,
                           int off_gate, int off_shift, int off_scale, const Plan& p, float* out, int ldo,
                           cudaStream_t st);
+cudaError_t launch_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
+                              int off_shift, int off_scale, const Plan& p, float* out32, int ldo, void* out_img,
+                              void* y_img, cudaStream_t st);
 cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st);
 cudaError_t launch_nan_flag(const float* pos, int Nn, int* flag, cudaStream_t st);
 cudaError_t launch_node_out(const float* pos, const float* atom_pred, int ldp, const Plan& p, const int* nan_flag,

@@ -96,6 +96,70 @@ __global__ void k_ln_mod(const float* __restrict__ x, int ldx, const float* __re
   }
 }
 
+// Same math as k_ln_mod for D = 256, one warp per atom, lane owns 8 consecutive columns = one 16-byte piece of the
+// fp16 operand image [tile][4 chunks][128 rows][128 B] that the persistent GEMM (imglinear.cu) bulk-copies.
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 o;
+  o.x = pack_h2(v[0], v[1]); o.y = pack_h2(v[2], v[3]); o.z = pack_h2(v[4], v[5]); o.w = pack_h2(v[6], v[7]);
+  return o;
+}
+__global__ void k_ln_mod_img(const float* __restrict__ x, int ldx, const float* __restrict__ y, int ldy,
+                             const float* __restrict__ tab, int ld_tab, int off_gate, int off_shift, int off_scale,
+                             const int* __restrict__ node_mol, int Nn, float* __restrict__ out32, int ldo,
+                             uint8_t* __restrict__ out_img, uint8_t* __restrict__ y_img) {
+  constexpr int D = 256;
+  const int v = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);     // rows up to the end of the last tile
+  const int lane = threadIdx.x & 31;
+  const int tile = v >> 7, row = v & 127;
+  const size_t ioff = (size_t)tile * (D / 64) * CHUNK_BYTES_A + img_piece(row, lane >> 3, lane & 7, CHUNK_BYTES_A);
+  if (v >= Nn) {                                                         // padding rows of the last tile
+    *reinterpret_cast<uint4*>(out_img + ioff) = make_uint4(0u, 0u, 0u, 0u);
+    if (y_img) *reinterpret_cast<uint4*>(y_img + ioff) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const float* t = tab + (size_t)node_mol[v] * ld_tab;
+  const int c0 = 8 * lane;
+  float a[8];
+  {
+    const float4 x0 = *reinterpret_cast<const float4*>(x + (size_t)v * ldx + c0);
+    const float4 x1 = *reinterpret_cast<const float4*>(x + (size_t)v * ldx + c0 + 4);
+    a[0] = x0.x; a[1] = x0.y; a[2] = x0.z; a[3] = x0.w; a[4] = x1.x; a[5] = x1.y; a[6] = x1.z; a[7] = x1.w;
+  }
+  if (y) {
+    const float4 y0 = *reinterpret_cast<const float4*>(y + (size_t)v * ldy + c0);
+    const float4 y1 = *reinterpret_cast<const float4*>(y + (size_t)v * ldy + c0 + 4);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(t + off_gate + c0));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(t + off_gate + c0 + 4));
+    const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] += gg[i] * yy[i];
+    if (y_img) *reinterpret_cast<uint4*>(y_img + ioff) = pack8(yy);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = a[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-6f);
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(t + off_scale + c0));
+  const float4 s1 = __ldg(reinterpret_cast<const float4*>(t + off_scale + c0 + 4));
+  const float4 h0 = __ldg(reinterpret_cast<const float4*>(t + off_shift + c0));
+  const float4 h1 = __ldg(reinterpret_cast<const float4*>(t + off_shift + c0 + 4));
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = (a[i] - mean) * rstd * (1.0f + sc[i]) + sh[i];
+  if (out32) {
+    *reinterpret_cast<float4*>(out32 + (size_t)v * ldo + c0) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(out32 + (size_t)v * ldo + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+  *reinterpret_cast<uint4*>(out_img + ioff) = pack8(o);
+}
+
 // Per-molecule centre-of-mass removal of the block's coordinate update, in place on pos_new
 // (remove_mean_with_mask, reference models/utils.py:38-45; call site models/mol_gnn.py:565-566).
 // A single-atom molecule has no edges, so no kernel wrote pos_new for it: x - mean(x) = 0.
@@ -192,6 +256,14 @@ cudaError_t launch_ln_mod(int D, const float* x, int ldx, const float* y, int ld
     k_ln_mod<384><<<grid, 256, 0, st>>>(x, ldx, y, ldy, tab, ld_tab, off_gate, off_shift, off_scale, p.node_mol, p.Nn, out, ldo);
   else
     return cudaErrorInvalidValue;
+  return LAUNCH_OK();
+}
+cudaError_t launch_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
+                              int off_shift, int off_scale, const Plan& p, float* out32, int ldo, void* out_img,
+                              void* y_img, cudaStream_t st) {
+  const int rows = (p.Nn + 127) / 128 * 128;
+  k_ln_mod_img<<<rows / 8, 256, 0, st>>>(x, ldx, y, ldy, tab, ld_tab, off_gate, off_shift, off_scale, p.node_mol, p.Nn,
+                                         out32, ldo, static_cast<uint8_t*>(out_img), static_cast<uint8_t*>(y_img));
   return LAUNCH_OK();
 }
 cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st) {

@@ -45,13 +45,15 @@ class _Workspace:
         self.pos = [zf(Nn, 4), zf(Nn, 4)]
         self.ah = zf(Nn, meta['ld_ah'])                    # concatenated atom hiddens (pads stay 0)
         self.h = [f(Nn, D), f(Nn, D)]
-        self.hn = f(Nn, D)
         h16 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float16)
+        mt = (Nn + 127) // 128
+        img = lambda k: torch.zeros(mt * 128 * k, device=dev, dtype=torch.float16)    # fp16 operand image [mt][k/64][128][64]
+        self.hn_img, self.h2_img, self.hnode_img, self.hout_img = img(D), img(D), img(D), img(D)
+        self.ff_img = img(d.r * D)
         self.qkv = h16(Nn, 3 * D)                           # fp16 per-atom operands gathered by the edge kernels
         self.hnode = zf(Nn, D)                             # atoms without partners are never written: stay 0
         self.pbuf = h16(Nn, 64)
         self.h2 = f(Nn, D)
-        self.ff = f(Nn, d.r * D)
         self.ab = h16(Nn, 2 * D)
         self.n1 = f(Nn, D)
         self.n2 = f(Nn, D // 2)
@@ -140,7 +142,13 @@ class _DGTBase(nn.Module):
 
         def lin(name, A, C, M=None, **kw):
             m = meta[name]
-            _lib.rowlinear(A, m['K'], pk[name + '.img'], pk[name + '.b'], C, m['N'], m['NT'], M=M, stream=st, **kw)
+            _lib.rowlinear(A, m['K'], pk[name + '.img'], pk[name + '.b'], C, m['N'], m['NT'], M=M, stream=st,
+                           tag='jodo_rowlinear:' + name.split('.')[-1], **kw)
+
+        def ilin(name, Aimg, tag=None, **kw):
+            m = meta[name]
+            _lib.imglinear(Aimg, plan.Nn, m['K'], pk[name + '.img'], pk[name + '.b'], m['N'], m['NT'], stream=st,
+                           tag=tag or ('jodo_imglinear:' + name.split('.')[-1]), **kw)
 
         # ---- per molecule: noise-level embedding (+ context) and all AdaLN tables
         _lib.call('jodo_time_features', _lib.ptr(noise_level), _lib.ptr(pk['time.w8']), _lib.ptr(ws.feat), _c(B), st)
@@ -173,24 +181,24 @@ class _DGTBase(nn.Module):
             off = TAB_HEAD + l * stride
             pin, pout = ws.pos[l & 1], ws.pos[(l + 1) & 1]
             hout = ws.h[l & 1]
-            # norm1_node + modulate, q/k/v
-            _lib.call('jodo_ln_mod', _c(D), _lib.ptr(h), _c(h.stride(0)), None, _c(0), _lib.ptr(ws.tab), _c(ld_tab),
-                      _c(0), _c(off), _c(off + D), ctypes.byref(ps), _lib.ptr(ws.hn), _c(D), st)
-            lin(p + 'qkv', ws.hn, ws.qkv, out_f16=True)
+            # norm1_node + modulate -> fp16 operand image, q/k/v
+            _lib.call('jodo_ln_mod_img', _lib.ptr(h), _c(h.stride(0)), None, _c(0), _lib.ptr(ws.tab), _c(ld_tab),
+                      _c(0), _c(off), _c(off + D), ctypes.byref(ps), None, _c(0), _lib.ptr(ws.hn_img), None, st)
+            ilin(p + 'qkv', ws.hn_img, C16=ws.qkv)
             aa = _lib.AttnArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(ws.qkv), 3 * D, _lib.dp(ws.tab), ld_tab,
                                off, _lib.dp(ws.extra), pk.ptr(p + 'gbf'), pk.ptr(p + 'emb.img'), pk.ptr(p + 'emb.b'),
                                pk.ptr(p + 'e0.img'), pk.ptr(p + 'e1.img'), _lib.dp(ws.hnode))
             _lib.call('jodo_attn', ctypes.byref(aa), st)
-            # node path: hoisted node2edge, gated residual + norm2 + FFN, hoisted input_lin parts, node_l
-            lin(p + 'n2e', ws.hnode, ws.pbuf, out_f16=True)
-            _lib.call('jodo_ln_mod', _c(D), _lib.ptr(h), _c(h.stride(0)), _lib.ptr(ws.hnode), _c(D), _lib.ptr(ws.tab),
+            # node path: gated residual + norm2 (+ image of hnode), hoisted node2edge, FFN, hoisted input_lin parts, node_l
+            _lib.call('jodo_ln_mod_img', _lib.ptr(h), _c(h.stride(0)), _lib.ptr(ws.hnode), _c(D), _lib.ptr(ws.tab),
                       _c(ld_tab), _c(off + 2 * D), _c(off + 3 * D), _c(off + 4 * D), ctypes.byref(ps), _lib.ptr(ws.h2),
-                      _c(D), st)
-            lin(p + 'ff1', ws.h2, ws.ff, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)
-            lin(p + 'ff2', ws.ff, hout, epi=_lib.EPI_GATED_RES, aux=ws.h2, gate=ws.tab[:, off + 5 * D:],
-                row_mol=plan.node_mol)
-            lin(p + 'ab', hout, ws.ab, out_f16=True)
-            lin(p + 'node_l', hout, ws.ah[:, D + l * meta['cnp']:])
+                      _c(D), _lib.ptr(ws.h2_img), _lib.ptr(ws.hnode_img), st)
+            ilin(p + 'n2e', ws.hnode_img, C16=ws.pbuf)
+            ilin(p + 'ff1', ws.h2_img, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.ff_img)
+            ilin(p + 'ff2', ws.ff_img, epi=_lib.EPI_GATED_RES, aux=ws.h2, gate=ws.tab[:, off + 5 * D:],
+                 row_mol=plan.node_mol, C32=hout, Cimg=ws.hout_img)
+            ilin(p + 'ab', ws.hout_img, C16=ws.ab)
+            ilin(p + 'node_l', ws.hout_img, C32=ws.ah[:, D + l * meta['cnp']:])
             # edge path
             ua = _lib.EdgeUpdateArgs(ps, _lib.dp(ws.e), _lib.dp(ws.e16), _lib.dp(ws.pbuf), 64, pk.ptr(p + 'n2e.bias'),
                                      _lib.dp(ws.tab), ld_tab, off, d.r, pk.ptr(p + 'ff3.img'), pk.ptr(p + 'ff3.b'),
@@ -205,7 +213,7 @@ class _DGTBase(nn.Module):
             _lib.call('jodo_com', _lib.ptr(pout), ctypes.byref(ps), st)
             if dbg is not None:
                 dbg.setdefault('blocks', []).append(dict(hnode=ws.hnode.clone(), h=hout.clone(), e=ws.e.clone(),
-                                                         pos=pout.clone(), qkv=ws.qkv.clone(), hn=ws.hn.clone()))
+                                                         pos=pout.clone(), qkv=ws.qkv.clone(), hn_img=ws.hn_img.clone()))
             h = hout
         # ---- heads
         lin('npred0', ws.ah, ws.n1, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)

@@ -28,6 +28,12 @@ def tiles_to_dense_h(plan, img, k, tile_halves, group_first=True):
     return plan.rows_to_dense(rows, group_first=group_first)
 
 
+def act_image_to_rows(img, k):
+    """fp16 activation image [mt][k/64][128][64] -> fp32 rows [mt*128, k]"""
+    mt = img.numel() // (128 * k)
+    return torch.cat([image_to_matrix_h(img.reshape(mt, -1)[t], 128, k) for t in range(mt)])
+
+
 def packed_to_dense(plan, x):
     B, N = plan.B, plan.N
     out = torch.zeros(B * N, x.shape[1], dtype=x.dtype, device=x.device)
@@ -69,7 +75,8 @@ def run_case(name, device='cuda', verbose=True):
                                            group_first=False), trace['e0'] * em)))
     for l, (b, ob) in enumerate(zip(dbg['blocks'], trace['blocks'])):
         m = inp['node_mask'].double()
-        rep.append((f'b{l}.hn', rel(packed_to_dense(plan, b['hn']), ob['hn'] * m)))
+        hn = act_image_to_rows(b['hn_img'], D)[:plan.Nn]
+        rep.append((f'b{l}.hn', rel(packed_to_dense(plan, hn), ob['hn'] * m)))
         qk = ob['q'].shape[-1]
         hq = qk // 2                      # q / k are stored as two head halves at columns [0, qk/2) and [D/2, D/2 + qk/2)
         unsplit = lambda x: torch.cat([x[:, :hq], x[:, D // 2:D // 2 + hq]], dim=1)

@@ -1,0 +1,116 @@
+"""GPU unit tests of the persistent TMA-fed GEMM (jodo_imglinear) and of the LayerNorm/modulate kernel that writes its
+fp16 operand images (jodo_ln_mod_img), through the C ABI."""
+import ctypes
+
+import pytest
+import torch
+
+from jodo_b200 import _lib
+from jodo_b200.pack import image_to_matrix_h, weight_image_h
+from jodo_b200.plan import Plan
+
+pytestmark = pytest.mark.gpu
+
+
+def act_image(A):
+    """fp32 rows [M, K] -> fp16 operand image [ceil(M/128)][K/64][128][64] (same swizzle as the weight images)."""
+    M, K = A.shape
+    mt = (M + 127) // 128
+    Ap = torch.zeros(mt * 128, K, device=A.device)
+    Ap[:M] = A
+    return weight_image_h(Ap, 128).view(torch.float16)
+
+
+def image_rows(img, K):
+    mt = img.numel() // (128 * K)
+    return torch.cat([image_to_matrix_h(img.reshape(mt, -1)[t], 128, K) for t in range(mt)])
+
+
+def h(x):
+    return x.float().half().double()
+
+
+@pytest.mark.parametrize('M,K,N,NT', [(128, 64, 64, 64), (300, 256, 768, 256), (1000, 256, 64, 64), (45105, 256, 512, 256),
+                                     (777, 512, 256, 256), (129, 1024, 256, 128), (5000, 256, 128, 128)])
+def test_imglinear_matches_fp64(M, K, N, NT):
+    g = torch.Generator(device='cuda').manual_seed(M + K + N)
+    A = torch.randn(M, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) / K ** 0.5
+    b = torch.randn(N, device='cuda', generator=g)
+    C32 = torch.full((M, N), float('nan'), device='cuda')
+    C16 = torch.zeros(M, N, device='cuda', dtype=torch.float16)
+    Cimg = torch.zeros(((M + 127) // 128) * 128 * max(N, 64), device='cuda', dtype=torch.float16) if N % 64 == 0 else None
+    _lib.imglinear(act_image(A), M, K, weight_image_h(W, NT), b, N, NT, C32=C32, C16=C16, Cimg=Cimg)
+    torch.cuda.synchronize()
+    ref = (h(A) @ h(W).t() + b.double())
+    assert float((C32.double() - ref).abs().max()) < 2e-4
+    assert float((C16.double() - ref).abs().max()) < 1e-2
+    if Cimg is not None:
+        rows = image_rows(Cimg, N)
+        assert float((rows[:M].double() - ref).abs().max()) < 1e-2
+        assert float(rows[M:].abs().sum()) == 0.0          # padding rows of the last tile are zero
+
+
+def test_imglinear_epilogues():
+    g = torch.Generator(device='cuda').manual_seed(3)
+    M, K, N, NT = 1500, 512, 256, 256
+    A = torch.randn(M, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) / 16
+    b = torch.randn(N, device='cuda', generator=g)
+    Ai, Wi = act_image(A), weight_image_h(W, NT)
+    base = h(A) @ h(W).t() + b.double()
+    # SiLU -> image (the ff1 -> ff2 hand-off)
+    Cimg = torch.zeros(((M + 127) // 128) * 128 * N, device='cuda', dtype=torch.float16)
+    _lib.imglinear(Ai, M, K, Wi, b, N, NT, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=Cimg)
+    ref = torch.nn.functional.silu(base)
+    assert float((image_rows(Cimg, N)[:M].double() - ref).abs().max()) < 2e-2      # fp16 output + hardware tanh
+    # gated residual -> fp32 rows (strided view) + image
+    mol = torch.randint(0, 9, (M,), device='cuda', dtype=torch.int32, generator=g)
+    gate = torch.randn(9, N + 64, device='cuda', generator=g)
+    res = torch.randn(M, N, device='cuda', generator=g)
+    Cbig = torch.zeros(M, N + 32, device='cuda')
+    _lib.imglinear(Ai, M, K, Wi, b, N, NT, epi=_lib.EPI_GATED_RES, aux=res, gate=gate[:, 64:], row_mol=mol,
+                   C32=Cbig[:, 16:16 + N], Cimg=Cimg)
+    ref = res.double() + gate[:, 64:][mol.long()].double() * base
+    assert float((Cbig[:, 16:16 + N].double() - ref).abs().max()) < 5e-4
+    assert float(Cbig[:, :16].abs().max()) == 0 and float(Cbig[:, 16 + N:].abs().max()) == 0
+    assert float((image_rows(Cimg, N)[:M].double() - ref).abs().max()) < 2e-2
+
+
+def test_imglinear_rejects_bad_args():
+    A = torch.zeros(128 * 64, device='cuda', dtype=torch.float16)
+    with pytest.raises(_lib.JodoError):
+        _lib.imglinear(A, 128, 40, A, None, 64, 64, C16=A.view(128, 64))
+    with pytest.raises(_lib.JodoError):
+        _lib.imglinear(A, 128, 64, A, None, 64, 64)                     # no output
+
+
+def test_ln_mod_img_matches_torch():
+    g = torch.Generator(device='cuda').manual_seed(9)
+    n = torch.tensor([3, 17, 29, 1, 8] * 40)
+    B, N, D = len(n), int(n.max()), 256
+    mask = (torch.arange(N)[None] < n[:, None]).float().cuda()
+    plan = Plan(mask)
+    ps = _lib.plan_struct(plan)
+    Nn = plan.Nn
+    x = torch.randn(Nn, D, device='cuda', generator=g)
+    y = torch.randn(Nn, D, device='cuda', generator=g)
+    tab = torch.randn(B, 1024, device='cuda', generator=g)
+    mt = (Nn + 127) // 128
+    out32 = torch.empty(Nn, D, device='cuda')
+    oimg = torch.full((mt * 128 * D,), 7.0, device='cuda', dtype=torch.float16)
+    yimg = torch.full((mt * 128 * D,), 7.0, device='cuda', dtype=torch.float16)
+    c = ctypes.c_int
+    _lib.call('jodo_ln_mod_img', _lib.ptr(x), c(D), _lib.ptr(y), c(D), _lib.ptr(tab), c(1024), c(0), c(256), c(512),
+              ctypes.byref(ps), _lib.ptr(out32), c(D), _lib.ptr(oimg), _lib.ptr(yimg), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    t = tab[plan.node_mol.long()]
+    z = x + t[:, :256] * y
+    ref = torch.nn.functional.layer_norm(z, (D,), eps=1e-6) * (1 + t[:, 512:768]) + t[:, 256:512]
+    assert float((out32 - ref).abs().max()) < 2e-5
+    rows = image_rows(oimg, D)
+    assert float((rows[:Nn] - ref).abs().max()) < 4e-3 * float(ref.abs().max())
+    assert float(rows[Nn:].abs().sum()) == 0.0
+    yr = image_rows(yimg, D)
+    assert torch.equal(yr[:Nn], y.half().float())
+    assert float(yr[Nn:].abs().sum()) == 0.0
