@@ -67,6 +67,8 @@ typedef struct jodo_imglinear_args {
   const int* row_mol;
   float* C32; int ldc32;                  /* fp32 row-major output or null */
   void* C16; int ldc16;                   /* fp16 row-major output or null (ld in elements) */
+  int c16_piece_major;                    /* != 0: C16 is [N/8][ldc16 rows][8] -- 16-byte column pieces with the rows of one
+                                             piece contiguous, so that lanes gathering consecutive atoms read whole lines */
   void* Cimg;                             /* fp16 operand image output [ceil(M/128)][N/64][128][128 B] or null */
 } jodo_imglinear_args;
 int jodo_imglinear(const jodo_imglinear_args* a, void* stream);
@@ -137,14 +139,17 @@ typedef struct jodo_equi_args {                         /* MultiCondEquiUpdate (
   jodo_plan p;
   const void* e16;                        /* updated edge features */
   const float* pos_in; float* pos_out;    /* [Nn] float4 */
-  const void* AB; int ldab;               /* fp16 [Nn, >=512]: input_lin[:, :D] h | input_lin[:, D:2D] h */
+  const void* AB; int ldab;               /* fp16 piece-major [64][ldab rows][8]: input_lin[:, :D] h + bias | input_lin[:, D:2D] h */
   const float* tab; int ld_tab; int tab_off;
   const uint8_t* extra;
-  const float* gbf;
-  const void* win_img; const float* b_in;      /* input_lin edge part fp16 image (N=256, K=128: [e | dist]), bias [256] */
-  const void* wc0_img; const float* b_c0;      /* coord_mlp.0 fp16 image (N=256, K=256), bias [256] */
-  const float* wc2;                            /* coord_mlp.2 [3, 256] */
-  float coord_scale;                           /* CoorsNorm.scale */
+  const void* win_img;                    /* input_lin edge part fp16 image (N=256, K=128: [e | dist]) */
+  const void* wc0_img;                    /* coord_mlp.0 fp16 image (N=256, K=256), pre-scaled by 1/2 */
+  float coord_scale;                      /* CoorsNorm.scale */
+  const int* nonuni;                      /* device flag written by jodo_uniform_flag: 0 = every molecule has the same
+                                             conditioning row (fast path reads row 0 through constant memory); may be null */
+  /* per-column constants passed BY VALUE so that they reach the FMA pipe as constant-bank operands: */
+  float gbf4[256];                        /* GBF constants, {mu, c1, c2, 0} per feature column (entry 0 unused) */
+  float c0tab[1024];                      /* [256] x {coord_mlp.0 bias / 2, coord_mlp.2 weight rows 0..2} */
 } jodo_equi_args;
 
 typedef struct jodo_edge_head_args {                     /* edge_exist_mlp | edge_type_mlp (reference models/mol_gnn.py:466-479,574-578) */
@@ -171,6 +176,10 @@ int jodo_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const f
 int jodo_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
                     int off_shift, int off_scale, const jodo_plan* p, float* out32, int ldo, void* out_img, void* y_img,
                     void* stream);
+/* nonuni[0] = 1 if any row of rows[B, T] differs (bitwise) from row 0, else 0.  rows = the conditioning embedding
+ * temb (noise level [+ context], reference models/mol_gnn.py:534, 728-734): the samplers broadcast one noise level
+ * over the batch (sampling.py:549), in which case every per-molecule AdaLN row is the same row. */
+int jodo_uniform_flag(const float* rows, int B, int T, int* nonuni, void* stream);
 int jodo_com(float* pos4, const jodo_plan* p, void* stream);
 int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, int inn,
                   float* out_dense, void* stream);

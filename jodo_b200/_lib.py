@@ -42,7 +42,7 @@ def check(rc, what):
 
 # ---- launch accounting / per-call device timing (bench.py, profiling) ------------------------------
 # kernels launched per C-ABI call (everything else launches exactly one)
-KERNELS_PER_CALL = {'jodo_edge_embed': 2, 'jodo_node_out': 2}
+KERNELS_PER_CALL = {'jodo_edge_embed': 2, 'jodo_node_out': 2}     # (memsets / D2D constant uploads are not kernels)
 LAUNCHES = 0           # kernels launched through this binding since import
 TRACE = None           # set to a list to record (name, start_event, end_event) around every call
 
@@ -117,8 +117,9 @@ class EdgeUpdateArgs(ctypes.Structure):
 
 class EquiArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('e16', _P), ('pos_in', _P), ('pos_out', _P), ('AB', _P),
-                ('ldab', _I), ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P), ('gbf', _P),
-                ('win_img', _P), ('b_in', _P), ('wc0_img', _P), ('b_c0', _P), ('wc2', _P), ('coord_scale', _F)]
+                ('ldab', _I), ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P),
+                ('win_img', _P), ('wc0_img', _P), ('coord_scale', _F), ('nonuni', _P),
+                ('gbf4', _F * 256), ('c0tab', _F * 1024)]
 
 
 class EdgeHeadArgs(ctypes.Structure):
@@ -129,16 +130,19 @@ class EdgeHeadArgs(ctypes.Structure):
 class ImgLinearArgs(ctypes.Structure):
     _fields_ = [('Aimg', _P), ('M', _I), ('K', _I), ('Wimg', _P), ('bias', _P), ('N', _I), ('NT', _I), ('epi', _I),
                 ('act_out', _I), ('aux', _P), ('ld_aux', _I), ('gate', _P), ('ld_gate', _I), ('row_mol', _P),
-                ('C32', _P), ('ldc32', _I), ('C16', _P), ('ldc16', _I), ('Cimg', _P)]
+                ('C32', _P), ('ldc32', _I), ('C16', _P), ('ldc16', _I), ('c16_piece_major', _I), ('Cimg', _P)]
 
 
 def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None, row_mol=None,
               C32=None, C16=None, Cimg=None, stream=None, tag=None):
     """Persistent TMA-fed GEMM on an fp16 activation image (include/jodo_b200.h: jodo_imglinear).
-    C32 / C16 are 2-D row-major views (stride(1) == 1), Cimg a flat fp16 image buffer."""
+    C32 / C16 are 2-D row-major views (stride(1) == 1) -- or C16 a contiguous 3-D [N/8, rows, 8] tensor for the
+    piece-major layout the edge kernels gather from; Cimg a flat fp16 image buffer."""
+    pm = C16 is not None and C16.dim() == 3          # piece-major fp16 output: tensor [N/8, rows, 8]
     a = ImgLinearArgs(dp(Aimg), M, K, dp(Wimg), dp(bias), N, NT, epi, act_out, dp(aux),
                       0 if aux is None else aux.stride(0), dp(gate), 0 if gate is None else gate.stride(0), dp(row_mol),
-                      dp(C32), 0 if C32 is None else C32.stride(0), dp(C16), 0 if C16 is None else C16.stride(0), dp(Cimg))
+                      dp(C32), 0 if C32 is None else C32.stride(0), dp(C16),
+                      0 if C16 is None else (C16.shape[1] if pm else C16.stride(0)), 1 if pm else 0, dp(Cimg))
     st = stream if stream is not None else stream_ptr()
     f = lib().jodo_imglinear
     check(_account(tag or 'jodo_imglinear', lambda: f(ctypes.byref(a), st)), 'jodo_imglinear')

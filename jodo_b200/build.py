@@ -11,7 +11,7 @@ LIB = os.path.join(HERE, 'libjodo_b200.so')
 STAMP = os.path.join(HERE, '.libjodo_b200.stamp')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
-         '-Xcompiler', '-fPIC', '-Xptxas', '-v']
+         '-Xcompiler', '-fPIC', '-Xptxas', '-v'] + os.environ.get('JODO_NVCC_EXTRA', '').split()
 
 
 def _sources():

@@ -84,6 +84,10 @@ int jodo_imglinear(const jodo_imglinear_args* a, void* stream) {
   if (const char* m = jodo::check_imglinear(*a)) return fail(m);
   JODO_LAUNCH(jodo::launch_imglinear(*a, num_sms(), S(stream)), "jodo_imglinear");
 }
+int jodo_uniform_flag(const float* rows, int B, int T, int* nonuni, void* stream) {
+  if (!rows || !nonuni || B <= 0 || T <= 0) return fail("jodo_uniform_flag: bad arguments");
+  JODO_LAUNCH(jodo::launch_uniform_flag(rows, B, T, nonuni, S(stream)), "jodo_uniform_flag");
+}
 int jodo_com(float* pos4, const jodo_plan* p, void* stream) { JODO_LAUNCH(jodo::launch_com(pos4, *p, S(stream)), "jodo_com"); }
 int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, int inn,
                   float* out_dense, void* stream) {
@@ -131,7 +135,7 @@ int jodo_edge_update(const jodo_edge_update_args* a, void* stream) {
 int jodo_equi(const jodo_equi_args* a, void* stream) {
   if (!a) return fail("jodo_equi: null args");
   if (const char* m = check_plan(a->p)) return fail(m);
-  if (a->ldab % 8 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_equi: strides must be multiples of 4");
+  if (a->ldab < a->p.Nn || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_equi: bad strides");
   JODO_LAUNCH(jodo::launch_equi(*a, num_sms(), S(stream)), "jodo_equi");
 }
 int jodo_edge_head(const jodo_edge_head_args* a, void* stream) {

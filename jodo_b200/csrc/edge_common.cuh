@@ -139,6 +139,40 @@ __device__ __forceinline__ void gbf_eval_half(float d, float scale, float shift,
   }
 }
 
+// Same features from the float4 table g4[c] = {mu_k, c1_k, c2_k, 0} with k = c - 1 (entry 0 unused): columns
+// [col0, col0 + N) of the 64-wide feature row.
+template <int N>
+__device__ __forceinline__ void gbf_eval_cols(float d, float scale, float shift, const float4* __restrict__ g4, int col0,
+                                              float (&out)[N]) {
+  const float x = fmaf(d, scale, d) + shift;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float4 c = g4[col0 + i];
+    const float w = (x - c.x) * c.y;
+    out[i] = ex2_fast(-(w * w)) * c.z;
+  }
+  if (col0 == 0) out[0] = x;
+}
+// Piece-major per-atom operands: [N/8 pieces][ld rows][8 halves] -- the 16-byte piece p of atom v lives at
+// (p * ld + v) * 16 bytes, so lanes that gather consecutive atoms (the partners of one group) read whole lines.
+// 4 consecutive pieces (32 columns) of atom v:
+__device__ __forceinline__ H32 ldg_pm32(const void* base, int ld, int v, int piece0) {
+  H32 r;
+  const uint4* b = static_cast<const uint4*>(base) + (size_t)piece0 * ld + v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.u[i] = __ldg(b + (size_t)i * ld);
+  return r;
+}
+
+// 16 consecutive fp16 columns of a per-atom row = 2 x 16-byte loads
+struct H16 { uint4 u[2]; };
+__device__ __forceinline__ H16 ldg_h16(const uint16_t* p) {
+  H16 r;
+  r.u[0] = __ldg(reinterpret_cast<const uint4*>(p));
+  r.u[1] = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  return r;
+}
+
 // LayerNorm (no affine, eps 1e-6) + modulate over 64 thread-local values
 __device__ __forceinline__ void ln_mod64(float (&x)[64], const float* __restrict__ shift, const float* __restrict__ scale) {
   float s = 0.f;

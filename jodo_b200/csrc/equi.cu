@@ -6,35 +6,138 @@
 //   pos[row] += sum_col (pos[row] - pos[col]) / max(|.|, 1e-8) * coord_scale * inv.
 // The sum runs over the partners of `row`, so here the group atom g is ROW r and the partner j is COL c
 // (same stored rows as the attention pass, roles swapped; edge features are symmetric).
-// input_lin is hoisted: W[:, :D] h[g] + W[:, D:2D] h[j] come from the per-atom buffer AB, only the
+// input_lin is hoisted: W[:, :D] h[g] + b and W[:, D:2D] h[j] come from the per-atom piece-major fp16 buffer AB, only the
 // [e | dist] part (K = 128) runs per edge.
 //
-// fp16 operand images (same mantissa as tf32).  coord_mlp.0 (256x256, 128 KB) stays resident in shared memory; the
-// input_lin image (64 KB) is bulk-copied per tile into the region that later holds the LayerNorm-modulated operand,
-// and that copy as well as the next e tile are issued as soon as the MMA that read the region has completed, so they
-// overlap the epilogues.  256 threads: warp w = tile rows 32*(w&3)..+31 x column half (w>>2) of the 256 hidden units.
+// fp16 operand images (same mantissa as tf32).  coord_mlp.0 (256x256, 128 KB, pre-scaled by 1/2 for the
+// tanh form of SiLU) stays resident in shared memory; the input_lin image (64 KB) is bulk-copied per tile into the
+// region that later holds the LayerNorm-modulated operand, and that copy as well as the next e tile are issued as
+// soon as the MMA that read the region has completed, so they overlap the epilogues.
+// 512 threads: warp w = tile rows 32*(w&3)..+31 (its TMEM lane quarter) x column quarter (w>>2) of the 256 hidden
+// units, 16 columns at a time, so that four warps per scheduler cover each other's TMEM / gather latencies.
+#include <cstdio>
 #include "edge_common.cuh"
 
 namespace jodo {
 
+#ifdef JODO_PHASE_TIMING
+__device__ long long g_equi_phase[16];
+#define PHASE_MARK(i) do { if (t == 0 && blockIdx.x == 0) { long long c_ = clock64(); g_equi_phase[i] += c_ - ph_last; ph_last = c_; } } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
+
 namespace {
 
-constexpr int EQ_THREADS = 256;
+constexpr int EQ_THREADS = 512;
 constexpr int EQ_WC0 = 0;                        // 128 KB: coord_mlp.0 image (N = 256, K = 256: 4 chunks of 32 KB)
 constexpr int EQ_X = 131072;                     // 64 KB: input_lin image (N = 256, K = 128), then LN-modulated A (K = 256)
 constexpr int EQ_U = EQ_X + 65536;               // 32 KB: [e | GBF(d)] (K = 128); chunk 1 doubles as scratch
 constexpr int EQ_MISC = EQ_U + 32768;
-constexpr int EQ_SMEM = EQ_MISC + 128 + 768;
+constexpr int EQ_SMEM = EQ_MISC + 128;
 static_assert(EQ_SMEM <= 232448, "shared memory budget");
 // scratch inside U chunk 1 (free once the input_lin MMA has completed)
 constexpr int EQ_SCR = EQ_U + 16384;
-constexpr int EQ_LNS = EQ_SCR;                   // [128][2] float2
-constexpr int EQ_DOT = EQ_LNS + 128 * 2 * 8;     // [128][2][4] floats
-constexpr int EQ_C3 = EQ_DOT + 128 * 2 * 16;     // [128][4] floats
+constexpr int EQ_LNS = EQ_SCR;                   // [128][4] float2
+constexpr int EQ_DOT = EQ_LNS + 128 * 4 * 8;     // [128][4] float4
+constexpr int EQ_C3 = EQ_DOT + 128 * 4 * 16;     // [128] float4
 constexpr int EQ_GT = EQ_C3 + 128 * 16;          // group tables 2 x [128] ints
 static_assert(EQ_GT + 1024 <= EQ_MISC, "scratch overflows the U chunk");
 
-__global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
+// Uniform-conditioning fast path: when every molecule of the batch carries the same noise level (and context), the
+// AdaLN rows are identical, and row 0's (shift[256] | scale[256] | gbf scale, shift) segment is copied into constant
+// memory before the launch.  Per-column constants then reach the FMA pipe as constant-bank operands instead of one
+// 16-byte load per (thread, 4 columns) -- the L1 write-back path is what bounds these kernels (profiles/).
+__constant__ float c_eqmod[528];
+
+#define EQ_DISPATCH(F, ...)                  \
+  switch (cq) {                              \
+    case 0: F<0>(__VA_ARGS__); break;        \
+    case 1: F<1>(__VA_ARGS__); break;        \
+    case 2: F<2>(__VA_ARGS__); break;        \
+    default: F<3>(__VA_ARGS__); break;       \
+  }
+
+// distance features, columns [16 CQ, 16 CQ + 16) of the GBF chunk; constants are kernel-parameter operands
+template <int CQ>
+__device__ __forceinline__ void eq_gbf(const EquiArgs& a, float d, float scale, float shift, uint8_t* U, int row) {
+  const float x = fmaf(d, scale, d) + shift;
+  float df[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int col = 16 * CQ + i;
+    if (col == 0) {
+      df[i] = x;
+    } else {
+      const float w = (x - a.gbf4[4 * col]) * a.gbf4[4 * col + 1];
+      df[i] = ex2_fast(-(w * w)) * a.gbf4[4 * col + 2];
+    }
+  }
+  st_rowh<16>(U, row, 1, 2 * CQ, df);
+}
+
+// LN + modulate of hidden units [64 CQ, 64 CQ + 64) -> X chunk CQ
+template <int CQ, bool UNI>
+__device__ __forceinline__ void eq_pass2_t(uint32_t tm_x, uint8_t* X, int row, float mean, float rstd, const float* tr) {
+  const float nmr = -mean * rstd;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float x[16];
+    tmem_ld16(tmem_addr(tm_x, 64 * CQ + 16 * c), x);
+    if (UNI) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int col = 64 * CQ + 16 * c + i;
+        const float n = fmaf(x[i], rstd, nmr);
+        x[i] = fmaf(n, c_eqmod[256 + col], n) + c_eqmod[col];
+      }
+    } else {
+      const float* shift = tr + tab_equi(D_) + 64 * CQ + 16 * c;
+      const float* scale = shift + D_;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + i));
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + i));
+        const float n0 = fmaf(x[i], rstd, nmr), n1 = fmaf(x[i + 1], rstd, nmr), n2 = fmaf(x[i + 2], rstd, nmr), n3 = fmaf(x[i + 3], rstd, nmr);
+        x[i] = fmaf(n0, sc.x, n0) + sh.x;
+        x[i + 1] = fmaf(n1, sc.y, n1) + sh.y;
+        x[i + 2] = fmaf(n2, sc.z, n2) + sh.z;
+        x[i + 3] = fmaf(n3, sc.w, n3) + sh.w;
+      }
+    }
+    st_rowh<16>(X, row, CQ, 2 * c, x);
+  }
+}
+template <int CQ> __device__ __forceinline__ void eq_pass2_uni(uint32_t tm_x, uint8_t* X, int row, float mean, float rstd, const float* tr) {
+  eq_pass2_t<CQ, true>(tm_x, X, row, mean, rstd, tr);
+}
+template <int CQ> __device__ __forceinline__ void eq_pass2_gen(uint32_t tm_x, uint8_t* X, int row, float mean, float rstd, const float* tr) {
+  eq_pass2_t<CQ, false>(tm_x, X, row, mean, rstd, tr);
+}
+
+// SiLU (h + h tanh h with h = x/2; the image is pre-scaled by 1/2) and the partial coord_mlp.2 dots over hidden units
+// [64 CQ, 64 CQ + 64); c0tab[k] = {b_k / 2, w2[0][k], w2[1][k], w2[2][k]} as kernel-parameter operands
+template <int CQ>
+__device__ __forceinline__ void eq_silu_dot(const EquiArgs& a, uint32_t tm_c, float4* dst) {
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float x[16];
+    tmem_ld16(tmem_addr(tm_c, 64 * CQ + 16 * c), x);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = 64 * CQ + 16 * c + i;
+      const float h = x[i] + a.c0tab[4 * col];
+      const float s = fmaf(h, tanh_fast(h), h);
+      o0 = fmaf(s, a.c0tab[4 * col + 1], o0);
+      o1 = fmaf(s, a.c0tab[4 * col + 2], o1);
+      o2 = fmaf(s, a.c0tab[4 * col + 3], o2);
+    }
+  }
+  *dst = make_float4(o0, o1, o2, 0.f);
+}
+
+__global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ EquiArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
   uint8_t* X = smem + EQ_X;
@@ -42,7 +145,6 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
   uint8_t* misc = smem + EQ_MISC;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // 0: coord_mlp.0 image, 1: e tile, 2: input_lin image, 3: MMA in, 4: MMA c0
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 64);
-  float* gbf = reinterpret_cast<float*>(misc + 128);    // [192]
   float2* LNS = reinterpret_cast<float2*>(smem + EQ_LNS);
   float4* DOT = reinterpret_cast<float4*>(smem + EQ_DOT);
   float4* C3 = reinterpret_cast<float4*>(smem + EQ_C3);
@@ -50,7 +152,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
   int* gt_node = reinterpret_cast<int*>(gt_meta + 128);
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int rq = warp & 3, half = warp >> 2;
+  const int rq = warp & 3, cq = warp >> 2;
   const int row = rq * 32 + lane;
   const int per = (a.p.n_tiles + gridDim.x - 1) / gridDim.x;
   const int tile0 = blockIdx.x * per;
@@ -68,7 +170,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
     mbar_expect_tx(&bars[0], 131072);
     bulk_g2s(smem + EQ_WC0, a.wc0_img, 131072, &bars[0]);
   }
-  for (int i = t; i < 192; i += EQ_THREADS) gbf[i] = a.gbf[i];
+  const bool uni = a.nonuni != nullptr && *a.nonuni == 0;
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   sync_tc();
   const uint32_t tmem = *tmem_slot;
@@ -76,32 +178,32 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
   uint32_t par = 0;
   const float4* pos = reinterpret_cast<const float4*>(a.pos_in);
   float4* pos_out = reinterpret_cast<float4*>(a.pos_out);
-  const int cb = 128 * half;                      // first hidden column of this thread
+  const int cb = 64 * cq;                         // first hidden column of this thread
 
   // row metadata of a tile is fetched one tile ahead
   RowInfo rn = load_row(a.p, min(tile0, a.p.n_tiles - 1), row);
   int ngn = a.p.tile_ngroups[min(tile0, a.p.n_tiles - 1)];
   uint8_t exn = a.extra[(size_t)min(tile0, a.p.n_tiles - 1) * TILE_ROWS + row];
-  const uint16_t* ab16 = static_cast<const uint16_t*>(a.AB);
+#ifdef JODO_PHASE_TIMING
+  long long ph_last = clock64();
+#endif
   for (int tile = tile0; tile < tile1; ++tile) {
     const RowInfo r = rn;
     const int ng = ngn;
     const uint8_t ex = exn;
-    const float* tr = a.tab + (size_t)r.mol * a.ld_tab + a.tab_off;
+    const float* tr = a.tab + (size_t)(uni ? 0 : r.mol) * a.ld_tab + a.tab_off;
     const float4 pg = pos[r.g], pj = pos[r.j];
-    // hoisted input_lin parts (fp16 rows): first 32-column chunk in flight before the MMA wait
-    const uint16_t* ag = ab16 + (size_t)r.g * a.ldab + cb;
-    const uint16_t* bj = ab16 + (size_t)r.j * a.ldab + D_ + cb;
-    H32 uc = ldg_h32(ag), vc = ldg_h32(bj);
+    // hoisted input_lin parts (fp16 rows, bias folded into the g part): first 32 columns in flight before the MMA wait
+    H32 ua = ldg_pm32(a.AB, a.ldab, r.g, 8 * cq), ub = ldg_pm32(a.AB, a.ldab, r.j, 32 + 8 * cq);
     {
-      float df[32];
-      if (r.valid) {
-        gbf_eval_half(sq_dist(pg, pj), tr[tab_gbf(D_)], tr[tab_gbf(D_) + 1], gbf, half, df);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) df[i] = 0.f;
-      }
-      st_rowh<32>(U, row, 1, 4 * half, df);
+      const float gsc = uni ? c_eqmod[512] : tr[tab_gbf(D_)], gsh = uni ? c_eqmod[513] : tr[tab_gbf(D_) + 1];
+      const float d = sq_dist(pg, pj);
+#ifdef JODO_PHASE_TIMING
+      if (d == 123456.f) printf("x");
+      PHASE_MARK(9);
+#endif
+      EQ_DISPATCH(eq_gbf, a, d, gsc, gsh, U, row);
+      PHASE_MARK(10);
     }
     {
       const int nt_ = min(tile + 1, tile1 - 1);
@@ -109,121 +211,96 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
       ngn = a.p.tile_ngroups[nt_];
       exn = a.extra[(size_t)nt_ * TILE_ROWS + row];
     }
+    PHASE_MARK(11);
     fence_async_smem();
+    PHASE_MARK(12);
     sync_tc();
+    PHASE_MARK(0);
     if (t == 0) {
       mbar_wait(&bars[1], par);
+      PHASE_MARK(1);
       mbar_wait(&bars[2], par);
+      PHASE_MARK(2);
       tc_fence_after();
       mma_tile_h(tm_x, smem_u32(U), smem_u32(X), 256, 2, false);       // input_lin edge part
       umma_commit(&bars[3]);
     }
     mbar_wait(&bars[3], par);
+    PHASE_MARK(3);
     tc_fence_after();
     if (t == 0 && tile + 1 < tile1) {            // U chunk 0 is consumed: prefetch the next e tile
       mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
       bulk_g2s(U, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 1) * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
     }
-    if (half == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
+    if (cq == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
 
-    // ---- pass 1: x = acc + A[g] + B[j] + b over this thread's 128 hidden units, kept in TMEM; row statistics
+    // ---- pass 1: x = acc + A[g] + B[j] over this thread's 64 hidden units, kept in TMEM; row statistics
     float mean, rstd;
     {
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        H32 un, vn;
-        if (c < 3) { un = ldg_h32(ag + (c + 1) * 32); vn = ldg_h32(bj + (c + 1) * 32); }
-        float x[32];
-        tmem_ld32(tmem_addr(tm_x, cb + c * 32), x);
+      for (int h = 0; h < 2; ++h) {
+        H32 na, nb;
+        if (h == 0) { na = ldg_pm32(a.AB, a.ldab, r.g, 8 * cq + 4); nb = ldg_pm32(a.AB, a.ldab, r.j, 32 + 8 * cq + 4); }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float uf[8], vf[8];
-          unpack8(uc.u[i], uf);
-          unpack8(vc.u[i], vf);
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.b_in + cb + c * 32 + 8 * i));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.b_in + cb + c * 32 + 8 * i + 4));
-          x[8 * i] += uf[0] + vf[0] + b0.x; x[8 * i + 1] += uf[1] + vf[1] + b0.y;
-          x[8 * i + 2] += uf[2] + vf[2] + b0.z; x[8 * i + 3] += uf[3] + vf[3] + b0.w;
-          x[8 * i + 4] += uf[4] + vf[4] + b1.x; x[8 * i + 5] += uf[5] + vf[5] + b1.y;
-          x[8 * i + 6] += uf[6] + vf[6] + b1.z; x[8 * i + 7] += uf[7] + vf[7] + b1.w;
+        for (int q = 0; q < 2; ++q) {
+          float x[16];
+          tmem_ld16(tmem_addr(tm_x, cb + 32 * h + 16 * q), x);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float uf[8], vf[8];
+            unpack8(ua.u[2 * q + i], uf);
+            unpack8(ub.u[2 * q + i], vf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float v = x[8 * i + e] + (uf[e] + vf[e]);
+              x[8 * i + e] = v;
+              s1 += v;
+              s2 = fmaf(v, v, s2);
+            }
+          }
+          tmem_st16(tmem_addr(tm_x, cb + 32 * h + 16 * q), x);
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { s1 += x[i]; s2 = fmaf(x[i], x[i], s2); }
-        tmem_st32(tmem_addr(tm_x, cb + c * 32), x);
-        if (c < 3) { uc = un; vc = vn; }
+        if (h == 0) { ua = na; ub = nb; }
       }
       tmem_wait_st();
-      LNS[row * 2 + half] = make_float2(s1, s2);
+      LNS[row * 4 + cq] = make_float2(s1, s2);
       __syncthreads();
-      const float2 o = LNS[row * 2 + (half ^ 1)];
-      mean = (s1 + o.x) * (1.0f / 256.0f);
-      rstd = rsqrtf(fmaxf((s2 + o.y) * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-6f);
+      PHASE_MARK(4);
+      const float4 o01 = *reinterpret_cast<const float4*>(&LNS[row * 4]);
+      const float4 o23 = *reinterpret_cast<const float4*>(&LNS[row * 4 + 2]);
+      mean = (o01.x + o01.z + o23.x + o23.z) * (1.0f / 256.0f);
+      rstd = rsqrtf(fmaxf((o01.y + o01.w + o23.y + o23.w) * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-6f);
     }
-    // ---- pass 2: LN + modulate -> X (fp16, K = 256); the input_lin image there is no longer needed
-    {
-      const float* shift = tr + tab_equi(D_) + cb;
-      const float* scale = shift + D_;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float x[32];
-        tmem_ld32(tmem_addr(tm_x, cb + c * 32), x);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c * 32 + i));
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c * 32 + i));
-          x[i] = r.valid ? fmaf((x[i] - mean) * rstd, 1.0f + sc.x, sh.x) : 0.f;
-          x[i + 1] = r.valid ? fmaf((x[i + 1] - mean) * rstd, 1.0f + sc.y, sh.y) : 0.f;
-          x[i + 2] = r.valid ? fmaf((x[i + 2] - mean) * rstd, 1.0f + sc.z, sh.z) : 0.f;
-          x[i + 3] = r.valid ? fmaf((x[i + 3] - mean) * rstd, 1.0f + sc.w, sh.w) : 0.f;
-        }
-        st_rowh<32>(X, row, 2 * half + (c >> 1), 4 * (c & 1), x);
-      }
-    }
+    // ---- pass 2: LN + modulate -> X chunk cq (fp16, K = 256); the input_lin image there is no longer needed.
+    // Padding rows carry finite garbage; they only feed their own (discarded) output rows.
+    if (uni) { EQ_DISPATCH(eq_pass2_uni, tm_x, X, row, mean, rstd, tr); }
+    else { EQ_DISPATCH(eq_pass2_gen, tm_x, X, row, mean, rstd, tr); }
     fence_async_smem();
     sync_tc();
+    PHASE_MARK(5);
     if (t == 0) {
       if (tile == tile0) mbar_wait(&bars[0], 0);
       tc_fence_after();
-      mma_tile_h(tm_c, smem_u32(X), smem_u32(smem + EQ_WC0), 256, 4, false);     // coord_mlp.0
+      mma_tile_h(tm_c, smem_u32(X), smem_u32(smem + EQ_WC0), 256, 4, false);     // coord_mlp.0 (pre-scaled by 1/2)
       umma_commit(&bars[4]);
     }
     mbar_wait(&bars[4], par);
+    PHASE_MARK(6);
     tc_fence_after();
     if (t == 0 && tile + 1 < tile1) {            // X is consumed: fetch the input_lin image for the next tile
       mbar_expect_tx(&bars[2], 65536);
       bulk_g2s(X, a.win_img, 65536, &bars[2]);
     }
 
-    // ---- SiLU, coord_mlp.2 on CUDA cores (partial dots over this thread's 128 hidden units)
-    {
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float x[32];
-        tmem_ld32(tmem_addr(tm_c, cb + c * 32), x);
-        const float* bc = a.b_c0 + cb + c * 32;
-        const float* w = a.wc2 + cb + c * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bc + i));
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + i));
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + 256 + i));
-          const float4 w2 = __ldg(reinterpret_cast<const float4*>(w + 512 + i));
-          const float s0 = silu_fast(x[i] + b4.x), s1 = silu_fast(x[i + 1] + b4.y);
-          const float s2 = silu_fast(x[i + 2] + b4.z), s3 = silu_fast(x[i + 3] + b4.w);
-          o0 = fmaf(s0, w0.x, o0); o0 = fmaf(s1, w0.y, o0); o0 = fmaf(s2, w0.z, o0); o0 = fmaf(s3, w0.w, o0);
-          o1 = fmaf(s0, w1.x, o1); o1 = fmaf(s1, w1.y, o1); o1 = fmaf(s2, w1.z, o1); o1 = fmaf(s3, w1.w, o1);
-          o2 = fmaf(s0, w2.x, o2); o2 = fmaf(s1, w2.y, o2); o2 = fmaf(s2, w2.z, o2); o2 = fmaf(s3, w2.w, o2);
-        }
-      }
-      DOT[row * 2 + half] = make_float4(o0, o1, o2, 0.f);
-    }
+    // ---- SiLU + coord_mlp.2 partial dots on CUDA cores
+    EQ_DISPATCH(eq_silu_dot, a, tm_c, &DOT[row * 4 + cq]);
     __syncthreads();
-    if (half == 0) {     // tanh, adjacency-weighted mean, coordinate contribution of this edge
-      const float4 p = DOT[row * 2], q = DOT[row * 2 + 1];
-      const float w = (tanh_fast(p.x + q.x) + ((ex & 1) ? tanh_fast(p.y + q.y) : 0.f) + ((ex & 2) ? tanh_fast(p.z + q.z) : 0.f)) *
-                      (1.0f / 3.0f);
+    PHASE_MARK(7);
+    if (cq == 0) {       // tanh, adjacency-weighted mean, coordinate contribution of this edge
+      const float4 p0 = DOT[row * 4], p1 = DOT[row * 4 + 1], p2 = DOT[row * 4 + 2], p3 = DOT[row * 4 + 3];
+      const float d0 = (p0.x + p1.x) + (p2.x + p3.x), d1 = (p0.y + p1.y) + (p2.y + p3.y), d2 = (p0.z + p1.z) + (p2.z + p3.z);
+      const float w = (tanh_fast(d0) + ((ex & 1) ? tanh_fast(d1) : 0.f) + ((ex & 2) ? tanh_fast(d2) : 0.f)) * (1.0f / 3.0f);
       const float dx = pg.x - pj.x, dy = pg.y - pj.y, dz = pg.z - pj.z;
       const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
       const float f = r.valid ? a.coord_scale * w / fmaxf(nrm, 1e-8f) : 0.f;
@@ -240,6 +317,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
     }
     fence_async_smem();        // the scratch is overwritten by the next tile's GBF rows
     sync_tc();
+    PHASE_MARK(8);
     par ^= 1;
   }
   if (tile0 >= tile1 && t == 0) mbar_wait(&bars[0], 0);   // never leave with bulk copies in flight
@@ -249,12 +327,26 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(EquiArgs a) {
 
 }  // namespace
 
+#ifdef JODO_PHASE_TIMING
+extern "C" int jodo_debug_equi_phases(long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  if (out16) cudaMemcpyFromSymbol(out16, g_equi_phase, sizeof(long long) * 16);
+  if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_equi_phase, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
 cudaError_t launch_equi(const EquiArgs& a, int num_sms, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(k_equi, cudaFuncAttributeMaxDynamicSharedMemorySize, EQ_SMEM);
     if (e != cudaSuccess) return e;
     attr = true;
+  }
+  if (a.nonuni) {     // row 0 of the table feeds the uniform fast path (harmless when the batch is not uniform)
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_eqmod, a.tab + a.tab_off + tab_equi(D_), sizeof(float) * 528, 0,
+                                            cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return e;
   }
   const int grid = a.p.n_tiles < num_sms ? a.p.n_tiles : num_sms;
   k_equi<<<grid, EQ_THREADS, EQ_SMEM, st>>>(a);

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
     uint16_t* __restrict__ C16 = static_cast<uint16_t*>(a.C16);
     uint8_t* __restrict__ Cimg = static_cast<uint8_t*>(a.Cimg);
     const int ld_aux = a.ld_aux, ld_gate = a.ld_gate, ldc32 = a.ldc32, ldc16 = a.ldc16, Mrows = a.M, nchunk_out = a.N / 64;
+    const bool c16_pm = a.c16_piece_major != 0;
     uint8_t* stg = stg_base + team * 2 * IL_STG_BUF;
     const int r0 = wt * 4 + rsub;                  // this thread's rows in the row-major pass: r0 + 16 * it
     uint32_t ai = 0, sb = 0;
@@ -210,7 +211,10 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
           if (!live) o = make_float4(0.f, 0.f, 0.f, 0.f);
           if (has32 && live) *reinterpret_cast<float4*>(C32 + (size_t)gr * ldc32 + col) = o;
           const uint2 hh = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
-          if (has16 && live) *reinterpret_cast<uint2*>(C16 + (size_t)gr * ldc16 + col) = hh;
+          if (has16 && live) {
+            if (c16_pm) *reinterpret_cast<uint2*>(C16 + ((size_t)(col >> 3) * ldc16 + gr) * 8 + (col & 7)) = hh;
+            else *reinterpret_cast<uint2*>(C16 + (size_t)gr * ldc16 + col) = hh;
+          }
           if (hasimg) *reinterpret_cast<uint2*>(img + img_piece(r, 0, piece, IL_A_STAGE)) = hh;
         }
       }
@@ -235,7 +239,8 @@ const char* check_imglinear(const ImgLinearArgs& a) {
   if ((reinterpret_cast<uintptr_t>(a.Aimg) | reinterpret_cast<uintptr_t>(a.Wimg)) & 127) return "imglinear: images must be 128-byte aligned";
   if (!a.C32 && !a.C16 && !a.Cimg) return "imglinear: no output";
   if (a.C32 && ((a.ldc32 % 4) || (reinterpret_cast<uintptr_t>(a.C32) & 15))) return "imglinear: fp32 output must be 16-byte aligned rows";
-  if (a.C16 && ((a.ldc16 % 8) || (reinterpret_cast<uintptr_t>(a.C16) & 15))) return "imglinear: fp16 output must be 16-byte aligned rows";
+  if (a.C16 && !a.c16_piece_major && ((a.ldc16 % 8) || (reinterpret_cast<uintptr_t>(a.C16) & 15))) return "imglinear: fp16 output must be 16-byte aligned rows";
+  if (a.C16 && a.c16_piece_major && (a.ldc16 < a.M || (reinterpret_cast<uintptr_t>(a.C16) & 15))) return "imglinear: piece-major fp16 output needs ldc16 >= M rows";
   if (a.Cimg && ((a.N % 64) || (reinterpret_cast<uintptr_t>(a.Cimg) & 127))) return "imglinear: image output needs N % 64 == 0";
   if (a.epi != EPI_STORE && a.epi != EPI_ACT && a.epi != EPI_GATED_RES) return "imglinear: unsupported epilogue";
   if (a.epi == EPI_GATED_RES && (!a.aux || !a.gate || !a.row_mol || (a.ld_aux % 4) || (a.ld_gate % 4))) return "imglinear: aux/gate/row_mol missing";

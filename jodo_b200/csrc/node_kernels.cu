@@ -160,6 +160,14 @@ __global__ void k_ln_mod_img(const float* __restrict__ x, int ldx, const float* 
   *reinterpret_cast<uint4*>(out_img + ioff) = pack8(o);
 }
 
+// nonuni |= any element of rows[B, T] differs bitwise from row 0
+__global__ void k_uniform_flag(const float* __restrict__ rows, int B, int T, int* __restrict__ nonuni) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * T) return;
+  const int c = (int)(i % T);
+  if (__float_as_uint(rows[i]) != __float_as_uint(rows[c])) *nonuni = 1;
+}
+
 // Per-molecule centre-of-mass removal of the block's coordinate update, in place on pos_new
 // (remove_mean_with_mask, reference models/utils.py:38-45; call site models/mol_gnn.py:565-566).
 // A single-atom molecule has no edges, so no kernel wrote pos_new for it: x - mean(x) = 0.
@@ -264,6 +272,13 @@ cudaError_t launch_ln_mod_img(const float* x, int ldx, const float* y, int ldy, 
   const int rows = (p.Nn + 127) / 128 * 128;
   k_ln_mod_img<<<rows / 8, 256, 0, st>>>(x, ldx, y, ldy, tab, ld_tab, off_gate, off_shift, off_scale, p.node_mol, p.Nn,
                                          out32, ldo, static_cast<uint8_t*>(out_img), static_cast<uint8_t*>(y_img));
+  return LAUNCH_OK();
+}
+cudaError_t launch_uniform_flag(const float* rows, int B, int T, int* nonuni, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(nonuni, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  const long long total = (long long)B * T;
+  k_uniform_flag<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rows, B, T, nonuni);
   return LAUNCH_OK();
 }
 cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st) {

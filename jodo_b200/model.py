@@ -54,7 +54,7 @@ class _Workspace:
         self.hnode = zf(Nn, D)                             # atoms without partners are never written: stay 0
         self.pbuf = h16(Nn, 64)
         self.h2 = f(Nn, D)
-        self.ab = h16(Nn, 2 * D)
+        self.ab = h16(2 * D // 8, Nn, 8)                    # piece-major (csrc/edge_common.cuh)
         self.n1 = f(Nn, D)
         self.n2 = f(Nn, D // 2)
         self.ap = f(Nn, meta['npred4']['N'])
@@ -162,6 +162,8 @@ class _DGTBase(nn.Module):
             lin('time3', ws.t1, ws.temb, epi=_lib.EPI_ADD, aux=ws.ctx)
         else:
             lin('time3', ws.t1, ws.temb)
+        # flags[2] = 1 unless every molecule carries the same conditioning row (the samplers broadcast one noise level)
+        _lib.call('jodo_uniform_flag', _lib.ptr(ws.temb), _c(B), _c(T), ctypes.c_void_p(ws.flags.data_ptr() + 8), st)
         lin('tab', ws.temb, ws.tab, act_in=_lib.ACT_SILU)
         # ---- per atom: packed inputs, node embedding (slice 0 of the concatenated atom hiddens)
         _lib.call('jodo_gather_nodes', _lib.ptr(xh), _lib.ptr(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin),
@@ -205,10 +207,10 @@ class _DGTBase(nn.Module):
                                      pk.ptr(p + 'ff4.img'), pk.ptr(p + 'ff4.b'), pk.ptr(p + 'edge_l.img'),
                                      pk.ptr(p + 'edge_l.b'), _lib.dp(ws.eh), ws.eh_tile_bytes, d.ed + l * d.ce, d.ce)
             _lib.call('jodo_edge_update', ctypes.byref(ua), st)
-            qa = _lib.EquiArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), 2 * D,
-                               _lib.dp(ws.tab), ld_tab, off, _lib.dp(ws.extra), pk.ptr(p + 'gbf'), pk.ptr(p + 'win.img'),
-                               pk.ptr(p + 'win.b'), pk.ptr(p + 'wc0.img'), pk.ptr(p + 'wc0.b'), pk.ptr(p + 'wc2'),
-                               meta['coord_scale'][l])
+            qa = _lib.EquiArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), plan.Nn,
+                               _lib.dp(ws.tab), ld_tab, off, _lib.dp(ws.extra), pk.ptr(p + 'win.img'),
+                               pk.ptr(p + 'wc0h.img'), meta['coord_scale'][l], ws.flags.data_ptr() + 8,
+                               pk.host[p + 'gbf4'], pk.host[p + 'c0tab'])
             _lib.call('jodo_equi', ctypes.byref(qa), st)
             _lib.call('jodo_com', _lib.ptr(pout), ctypes.byref(ps), st)
             if dbg is not None:

@@ -103,6 +103,7 @@ class Packed:
         self._size = 0
         self.buf = None
         self.meta = {}
+        self.host = {}          # small per-column constant tables passed to kernels BY VALUE (ctypes float arrays)
 
     def add(self, name, t):
         t = t.detach().to(self.device, torch.float32).reshape(-1)
@@ -112,6 +113,11 @@ class Packed:
         if pad:
             self._pieces.append(torch.zeros(pad, device=self.device))
         self._size += t.numel() + pad
+
+    def add_host(self, name, t):
+        import ctypes
+        v = t.detach().float().reshape(-1).cpu().tolist()
+        self.host[name] = (ctypes.c_float * len(v))(*v)
 
     def finish(self):
         self.buf = torch.cat(self._pieces)
@@ -150,6 +156,17 @@ def _gbf_consts(sd, prefix, dev):
     out[64:64 + k] = (0.5 * 1.4426950408889634) ** 0.5 / sg
     out[128:128 + k] = 1.0 / asg
     return out
+
+
+def _gbf_table4(sd, prefix, dev):
+    """float4 {mu, sqrt(0.5 log2 e)/sg, 1/(a sg), 0} per feature COLUMN c = k + 1 (entry 0, the raw x column, is
+    unused): the layout gbf_eval_cols (csrc/edge_common.cuh) reads with one 16-byte shared-memory load per feature."""
+    c = _gbf_consts(sd, prefix, dev)
+    out = torch.zeros(64, 4, device=dev)
+    out[1:, 0] = c[0:63]
+    out[1:, 1] = c[64:127]
+    out[1:, 2] = c[128:191]
+    return out.reshape(-1)
 
 
 def pack_model(sd, dims, device):
@@ -251,7 +268,8 @@ def pack_model(sd, dims, device):
         add_lin(p + 'ff1', W(f'{b}.ff_linear1'), Bv(f'{b}.ff_linear1'), 256)
         add_lin(p + 'ff2', W(f'{b}.ff_linear2'), Bv(f'{b}.ff_linear2'), 256)
         wi = W(f'{b}.equi_update.input_lin')                   # [D, 2D + 2ed]: [h_row | h_col | e | dist]
-        add_lin(p + 'ab', torch.cat([wi[:, :D], wi[:, D:2 * D]], dim=0), None, 256)
+        add_lin(p + 'ab', torch.cat([wi[:, :D], wi[:, D:2 * D]], dim=0),
+                torch.cat([Bv(f'{b}.equi_update.input_lin'), z(D)]), 256)      # input_lin bias rides on the h[row] part
         add_lin(p + 'node_l', W(f'node_{l}'), Bv(f'node_{l}'), 64, n_pad=64)
         pk.add(p + 'gbf', _gbf_consts(sd, f'{b}.dist_layer', device))
         pk.add(p + 'emb.img', weight_image_h(W(f'{b}.edge_emb'), ed))                       # [64, 128]: [dist | e]
@@ -272,6 +290,11 @@ def pack_model(sd, dims, device):
         pk.add(p + 'wc0.img', weight_image_h(W(f'{b}.equi_update.coord_mlp.0'), D))
         pk.add(p + 'wc0.b', Bv(f'{b}.equi_update.coord_mlp.0'))
         pk.add(p + 'wc2', W(f'{b}.equi_update.coord_mlp.2'))                               # [3, 256]
+        # SiLU(x) = h + h tanh(h) with h = x / 2: the factor 1/2 is exact in fp16, so it is folded into the image and bias
+        pk.add(p + 'wc0h.img', weight_image_h(0.5 * W(f'{b}.equi_update.coord_mlp.0'), D))
+        pk.add_host(p + 'c0tab', torch.cat([0.5 * Bv(f'{b}.equi_update.coord_mlp.0')[:, None],
+                                            W(f'{b}.equi_update.coord_mlp.2').t()], dim=1).contiguous())   # [256, 4]
+        pk.add_host(p + 'gbf4', _gbf_table4(sd, f'{b}.dist_layer', device))
         scales.append(sd[f'{b}.equi_update.coord_norm.scale'].reshape(()))
     pk.meta['coord_scale'] = [float(s) for s in torch.stack(scales).cpu()]
     return pk.finish()

@@ -77,6 +77,23 @@ def test_imglinear_epilogues():
     assert float((image_rows(Cimg, N)[:M].double() - ref).abs().max()) < 2e-2
 
 
+def test_imglinear_piece_major_output():
+    """fp16 output in the piece-major layout the edge kernels gather from: [N/8][rows][8]."""
+    g = torch.Generator(device='cuda').manual_seed(11)
+    M, K, N, NT = 1000, 256, 512, 256
+    A = torch.randn(M, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) / 16
+    b = torch.randn(N, device='cuda', generator=g)
+    Cpm = torch.zeros(N // 8, M + 24, 8, device='cuda', dtype=torch.float16)
+    Crm = torch.zeros(M, N, device='cuda', dtype=torch.float16)
+    _lib.imglinear(act_image(A), M, K, weight_image_h(W, NT), b, N, NT, C16=Cpm)
+    _lib.imglinear(act_image(A), M, K, weight_image_h(W, NT), b, N, NT, C16=Crm)
+    torch.cuda.synchronize()
+    back = Cpm[:, :M].permute(1, 0, 2).reshape(M, N)
+    assert torch.equal(back, Crm)
+    assert float(Cpm[:, M:].abs().sum()) == 0.0
+
+
 def test_imglinear_rejects_bad_args():
     A = torch.zeros(128 * 64, device='cuda', dtype=torch.float16)
     with pytest.raises(_lib.JodoError):
