@@ -90,8 +90,8 @@ typedef struct jodo_plan {
 } jodo_plan;
 
 /* Edge state between kernels (per tile of 128 rows):
- *   e32  fp32 master copy, image [2 chunks][128 rows][32 cols] (32 KB per tile) -- the residual stream, read and
- *        rewritten in place by jodo_edge_update;
+ *   e32  fp32 master copy, piece-major [16 pieces of 4 columns][128 rows][16 B] (32 KB per tile) -- the residual
+ *        stream, written by jodo_edge_embed, read and rewritten in place by jodo_edge_update (row-per-thread, coalesced);
  *   e16  fp16 operand copy, image [128 rows][64 cols] (16 KB per tile) -- what the tensor-core kernels load;
  *   eh   fp16 image of the concatenated edge hiddens [keh/64 chunks][128][64]: chunk 0 = model-level embedding,
  *        then ce columns per block (edge_i projections), consumed by jodo_edge_head.
@@ -124,15 +124,20 @@ typedef struct jodo_attn_args {                         /* TransMixLayer on edge
 
 typedef struct jodo_edge_update_args {                   /* edge residual + FFN + edge_l (reference models/mol_gnn.py:304-305,313-317,568) */
   jodo_plan p;
-  float* e32; void* e16;                  /* in/out fp32 state (in place), out fp16 copy */
-  const void* P; int ldp;                 /* fp16 [Nn, 64] node2edge_lin(hnode) without bias */
-  const float* b_n2e;                     /* [64] */
+  float* e32; void* e16;                  /* in/out fp32 state (in place, piece-major tiles), out fp16 operand copy */
+  const void* P; int ldp;                 /* fp16 piece-major [8][ldp rows][8]: node2edge_lin(hnode) without bias */
   const float* tab; int ld_tab; int tab_off;
-  int r;                                  /* mlp_ratio: hidden = 64 r */
-  const void* w3_img; const float* b3;    /* fp16 image (N=64 r, K=64), bias [64 r] */
-  const void* w4_img; const float* b4;    /* fp16 image (N=64, K=64 r), bias [64] */
-  const void* wl_img; const float* bl;    /* edge_l fp16 image (N=16, K=64), bias [16] */
+  int r;                                  /* mlp_ratio (2 or 4): hidden = 64 r */
+  const void* w3_img;                     /* fp16 image (N=64 r in tiles of 128, K=64), pre-scaled by 1/2 */
+  const void* w4_img;                     /* fp16 image (N=64, K=64 r) */
+  const void* wl_img;                     /* edge_l fp16 image (N=16, K=64) */
   void* eh; size_t eh_tile_bytes; int eh_col; int ce;   /* out: columns [eh_col, eh_col+ce) of the edge-hidden image */
+  const int* nonuni;                      /* see jodo_equi_args */
+  /* per-column constants by value (constant-bank operands): */
+  float b_n2e[64];                        /* node2edge_lin bias */
+  float b3[256];                          /* ff_linear3 bias / 2 (first 64 r entries) */
+  float b4[64];                           /* ff_linear4 bias */
+  float bl[16];                           /* edge_l bias (first ce entries) */
 } jodo_edge_update_args;
 
 typedef struct jodo_equi_args {                         /* MultiCondEquiUpdate (reference models/mol_gnn.py:71-94) */

@@ -110,9 +110,9 @@ class AttnArgs(ctypes.Structure):
 
 class EdgeUpdateArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('e32', _P), ('e16', _P), ('P', _P), ('ldp', _I),
-                ('b_n2e', _P), ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('r', _I), ('w3_img', _P), ('b3', _P),
-                ('w4_img', _P), ('b4', _P), ('wl_img', _P), ('bl', _P), ('eh', _P), ('eh_tile_bytes', _Z),
-                ('eh_col', _I), ('ce', _I)]
+                ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('r', _I), ('w3_img', _P), ('w4_img', _P), ('wl_img', _P),
+                ('eh', _P), ('eh_tile_bytes', _Z), ('eh_col', _I), ('ce', _I), ('nonuni', _P),
+                ('b_n2e', _F * 64), ('b3', _F * 256), ('b4', _F * 64), ('bl', _F * 16)]
 
 
 class EquiArgs(ctypes.Structure):

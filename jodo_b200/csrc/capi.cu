@@ -127,7 +127,8 @@ int jodo_attn(const jodo_attn_args* a, void* stream) {
 int jodo_edge_update(const jodo_edge_update_args* a, void* stream) {
   if (!a) return fail("jodo_edge_update: null args");
   if (const char* m = check_plan(a->p)) return fail(m);
-  if (a->ldp % 8 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_edge_update: strides must be multiples of 4");
+  if (a->ldp < a->p.Nn || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_edge_update: bad strides");
+  if (a->r != 2 && a->r != 4) return fail("jodo_edge_update: mlp_ratio must be 2 or 4");
   if (!a->e32 || !a->e16 || !a->eh) return fail("jodo_edge_update: null buffer");
   if (a->eh_col < 0 || a->eh_col + a->ce > 192) return fail("jodo_edge_update: edge-hidden slice out of range");
   JODO_LAUNCH(jodo::launch_edge_update(*a, num_sms(), S(stream)), "jodo_edge_update");

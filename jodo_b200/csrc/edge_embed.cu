@@ -121,12 +121,11 @@ __global__ void __launch_bounds__(ET, 1) k_edge_embed(EdgeEmbedArgs a) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) { e[i] = r.valid ? h0[i] + bias[i] : 0.f; e[32 + i] = r.valid ? h1[i] + bias[32 + i] : 0.f; }
     }
-    // fp32 master copy (tile image, 2 chunks of 32 columns) + fp16 operand copies (edge state and edge-hidden chunk 0)
-    uint8_t* dst = reinterpret_cast<uint8_t*>(a.e32) + (size_t)tile * E_TILE_BYTES;
+    // fp32 master copy (piece-major tile: [16 pieces][128 rows][16 B], coalesced) + fp16 operand copies (edge state and
+    // edge-hidden chunk 0)
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a.e32) + (size_t)tile * E_TILE_BYTES) + t;
 #pragma unroll
-    for (int p = 0; p < 16; ++p)
-      *reinterpret_cast<float4*>(dst + img_piece(t, p >> 3, p & 7, CHUNK_BYTES_A)) =
-          make_float4(e[4 * p], e[4 * p + 1], e[4 * p + 2], e[4 * p + 3]);
+    for (int p = 0; p < 16; ++p) dst[p * 128] = make_float4(e[4 * p], e[4 * p + 1], e[4 * p + 2], e[4 * p + 3]);
     st_rowh<64>(reinterpret_cast<uint8_t*>(a.e16) + (size_t)tile * CHUNK_BYTES_A, t, 0, 0, e);
     st_rowh<64>(reinterpret_cast<uint8_t*>(a.eh) + (size_t)tile * a.eh_tile_bytes, t, 0, 0, e);
     sync_tc();

@@ -52,7 +52,7 @@ class _Workspace:
         self.ff_img = img(d.r * D)
         self.qkv = h16(Nn, 3 * D)                           # fp16 per-atom operands gathered by the edge kernels
         self.hnode = zf(Nn, D)                             # atoms without partners are never written: stay 0
-        self.pbuf = h16(Nn, 64)
+        self.pbuf = h16(8, Nn, 8)                           # piece-major hoisted node2edge_lin part
         self.h2 = f(Nn, D)
         self.ab = h16(2 * D // 8, Nn, 8)                    # piece-major (csrc/edge_common.cuh)
         self.n1 = f(Nn, D)
@@ -202,10 +202,11 @@ class _DGTBase(nn.Module):
             ilin(p + 'ab', ws.hout_img, C16=ws.ab)
             ilin(p + 'node_l', ws.hout_img, C32=ws.ah[:, D + l * meta['cnp']:])
             # edge path
-            ua = _lib.EdgeUpdateArgs(ps, _lib.dp(ws.e), _lib.dp(ws.e16), _lib.dp(ws.pbuf), 64, pk.ptr(p + 'n2e.bias'),
-                                     _lib.dp(ws.tab), ld_tab, off, d.r, pk.ptr(p + 'ff3.img'), pk.ptr(p + 'ff3.b'),
-                                     pk.ptr(p + 'ff4.img'), pk.ptr(p + 'ff4.b'), pk.ptr(p + 'edge_l.img'),
-                                     pk.ptr(p + 'edge_l.b'), _lib.dp(ws.eh), ws.eh_tile_bytes, d.ed + l * d.ce, d.ce)
+            ua = _lib.EdgeUpdateArgs(ps, _lib.dp(ws.e), _lib.dp(ws.e16), _lib.dp(ws.pbuf), plan.Nn,
+                                     _lib.dp(ws.tab), ld_tab, off, d.r, pk.ptr(p + 'ff3.img'), pk.ptr(p + 'ff4.img'),
+                                     pk.ptr(p + 'edge_l.img'), _lib.dp(ws.eh), ws.eh_tile_bytes, d.ed + l * d.ce, d.ce,
+                                     ws.flags.data_ptr() + 8, pk.host[p + 'n2e.bias'], pk.host[p + 'ff3.b'],
+                                     pk.host[p + 'ff4.b'], pk.host[p + 'edge_l.b'])
             _lib.call('jodo_edge_update', ctypes.byref(ua), st)
             qa = _lib.EquiArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), plan.Nn,
                                _lib.dp(ws.tab), ld_tab, off, _lib.dp(ws.extra), pk.ptr(p + 'win.img'),

@@ -264,7 +264,7 @@ def pack_model(sd, dims, device):
         wq[2 * D:], bq[2 * D:] = W(f'{b}.attn_mpnn.lin_value'), Bv(f'{b}.attn_mpnn.lin_value')
         add_lin(p + 'qkv', wq, bq, 256)
         add_lin(p + 'n2e', W(f'{b}.node2edge_lin'), None, 64)
-        pk.add(p + 'n2e.bias', Bv(f'{b}.node2edge_lin'))
+        pk.add_host(p + 'n2e.bias', Bv(f'{b}.node2edge_lin'))
         add_lin(p + 'ff1', W(f'{b}.ff_linear1'), Bv(f'{b}.ff_linear1'), 256)
         add_lin(p + 'ff2', W(f'{b}.ff_linear2'), Bv(f'{b}.ff_linear2'), 256)
         wi = W(f'{b}.equi_update.input_lin')                   # [D, 2D + 2ed]: [h_row | h_col | e | dist]
@@ -277,14 +277,17 @@ def pack_model(sd, dims, device):
         pk.add(p + 'e0.img', weight_image_h(split_heads(W(f'{b}.attn_mpnn.lin_edge0'), D, d.qk), D))
         pk.add(p + 'e1.img', weight_image_h(W(f'{b}.attn_mpnn.lin_edge1'), D))
         w3, w4 = W(f'{b}.ff_linear3'), W(f'{b}.ff_linear4')    # [ed r, ed], [ed, ed r]
-        pk.add(p + 'ff3.img', weight_image_h(w3, ed * d.r))
-        pk.add(p + 'ff3.b', Bv(f'{b}.ff_linear3'))
+        # SiLU(x) = h + h tanh(h), h = x / 2: the factor (exact in fp16) is folded into ff_linear3's image and bias
+        pk.add(p + 'ff3.img', weight_image_h(0.5 * w3, 128))                               # N tiles of 128 hidden units
+        b3 = z(256)
+        b3[:ed * d.r] = 0.5 * Bv(f'{b}.ff_linear3')
+        pk.add_host(p + 'ff3.b', b3)
         pk.add(p + 'ff4.img', weight_image_h(w4, ed))
-        pk.add(p + 'ff4.b', Bv(f'{b}.ff_linear4'))
+        pk.add_host(p + 'ff4.b', Bv(f'{b}.ff_linear4'))
         pk.add(p + 'edge_l.img', weight_image_h(pad2(W(f'edge_{l}'), 16, ed), 16))
         bl = z(16)
         bl[:d.ce] = Bv(f'edge_{l}')
-        pk.add(p + 'edge_l.b', bl)
+        pk.add_host(p + 'edge_l.b', bl)
         pk.add(p + 'win.img', weight_image_h(wi[:, 2 * D:].contiguous(), D))                # [256, 128]: [e | dist]
         pk.add(p + 'win.b', Bv(f'{b}.equi_update.input_lin'))
         pk.add(p + 'wc0.img', weight_image_h(W(f'{b}.equi_update.coord_mlp.0'), D))

@@ -85,7 +85,8 @@ def run_case(name, device='cuda', verbose=True):
         rep.append((f'b{l}.v', rel(packed_to_dense(plan, b['qkv'].float()[:, 2 * D:]), ob['v'] * m)))
         rep.append((f'b{l}.hnode', rel(packed_to_dense(plan, b['hnode']), ob['hnode'] * m)))
         rep.append((f'b{l}.h', rel(packed_to_dense(plan, b['h']), ob['h'])))
-        rep.append((f'b{l}.e', rel(tiles_to_dense(plan, b['e'], 64), ob['e'] * em)))
+        e_rows = b['e'].reshape(plan.n_tiles, 16, 128, 4).permute(0, 2, 1, 3).reshape(plan.n_tiles * 128, 64)   # piece-major tiles
+        rep.append((f'b{l}.e', rel(plan.rows_to_dense(e_rows), ob['e'] * em)))
         rep.append((f'b{l}.pos', rel(packed_to_dense(plan, b['pos'][:, :3]), ob['pos'])))
     rx, re_ = g['ref_fp64']
     rep.append(('ah', rel(packed_to_dense(plan, dbg['ah'][:, :D]), trace['ah'][..., :D] * inp['node_mask'].double())))
