@@ -113,13 +113,16 @@ typedef struct jodo_attn_args {                         /* TransMixLayer on edge
   jodo_plan p;
   const void* e16;                        /* block input edge features */
   const float* pos;                       /* [Nn] float4 */
-  const void* qkv; int ldq;               /* fp16 [Nn, 3D]: q | k | v of LN-modulated atoms (q, k in split-head layout) */
+  const void* qkv; int ldq;               /* fp16 piece-major [96][ldq rows][8]: q | k | v of LN-modulated atoms (q, k in split-head layout) */
   const float* tab; int ld_tab; int tab_off;   /* table base of this layer */
   const uint8_t* extra;
-  const float* gbf;                       /* this layer's GBF constants */
-  const void* w_emb_img; const float* b_emb;   /* block edge_emb fp16 image (N=64, K=128: [dist | e]) */
-  const void* w0_img; const void* w1_img;      /* lin_edge0 (N=256 split-head, K=64), lin_edge1 (N=256, K=64), fp16 */
+  const void* w_emb_img;                  /* block edge_emb fp16 image (N=64, K=128: [dist | e]) */
+  const void* w0_img; const void* w1_img; /* lin_edge0 (N=256 split-head, K=64), lin_edge1 (N=256, K=64), fp16 */
   float* hnode;                           /* out [Nn, 256] */
+  const int* nonuni;                      /* see jodo_equi_args */
+  /* per-column constants by value (constant-bank operands): */
+  float gbf4[256];                        /* this layer's GBF constants {mu, c1, c2, 0} per feature column */
+  float b_emb[64];                        /* block edge_emb bias */
 } jodo_attn_args;
 
 typedef struct jodo_edge_update_args {                   /* edge residual + FFN + edge_l (reference models/mol_gnn.py:304-305,313-317,568) */

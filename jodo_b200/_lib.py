@@ -104,8 +104,8 @@ class EdgeEmbedArgs(ctypes.Structure):
 
 class AttnArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('e16', _P), ('pos', _P), ('qkv', _P), ('ldq', _I),
-                ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P), ('gbf', _P), ('w_emb_img', _P),
-                ('b_emb', _P), ('w0_img', _P), ('w1_img', _P), ('hnode', _P)]
+                ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P), ('w_emb_img', _P),
+                ('w0_img', _P), ('w1_img', _P), ('hnode', _P), ('nonuni', _P), ('gbf4', _F * 256), ('b_emb', _F * 64)]
 
 
 class EdgeUpdateArgs(ctypes.Structure):

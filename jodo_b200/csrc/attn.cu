@@ -6,202 +6,217 @@
 // lin_edge1/tanh gated values, sum onto the target).
 //
 // A tile holds complete groups: group atom g = attention TARGET c, partner j = SOURCE r.
-// Per tile:  A0 = [GBF(d) | e]  --MMA1--> e1 --LN/modulate--> en  --MMA2--> g0 (TMEM 0..255)
-//                                                               --MMA3--> g1 (TMEM 256..511)
-//   (fp16 operand images, fp32 accumulation: same mantissa as tf32 at half the shared memory and twice the rate)
+// Per tile:  A0 = [GBF(d) | e]  --MMA1--> e1 --LN/modulate--> en  --MMA2--> g0 --(logits)--  --MMA3--> g1 --(messages)
+//   (fp16 operand images, fp32 accumulation; e1, g0 and g1 reuse the same 256 TMEM columns one after the other, the
+//   g1 MMA runs under the softmax)
 //   logits (k[j] . q[g] . tanh(g0)), softmax per group through shared memory,
 //   msg = v[j] * tanh(g1) * alpha, summed per group, written to hnode[g].
 //
-// 256 threads: warp w works on tile rows 32*(w&3)..+31 (its TMEM lane quarter) and on column half (w>>2) of every
+// 512 threads = two independent groups of 8 warps, each walking its own tiles (group-local named barriers, private
+// operand / staging buffers, 256 TMEM columns, its own mbarriers) and sharing the three resident weight images, so
+// that one group's tensor-core round trips, barriers and gather latencies are covered by the other group's math.
+// Inside a group warp w works on tile rows 32*(w&3)..+31 (its TMEM lane quarter) and on column half (w>>2) of every
 // row vector (32 of 64 edge features, 128 of 256 q/k/g0 columns = 7 of 14 heads, 128 of 256 value columns = 8 of 16
-// heads).  Each CTA walks a contiguous range of tiles so that the q/k/v rows of a molecule stay hot in L1/L2.
+// heads).  q | k | v rows are piece-major fp16 (edge_common.cuh) so that the partner gathers read whole lines;
+// per-column constants are kernel-parameter / constant-memory operands (uniform-conditioning fast path, see equi.cu).
 #include "edge_common.cuh"
 
 namespace jodo {
 
+__constant__ float c_atmod[130];        // row 0 of the table: edge shift_msa[64], scale_msa[64], then GBF scale, shift
+
 namespace {
 
-constexpr int AT_THREADS = 256;
-constexpr int AT_A0 = 0;                          // 32 KB fp16: chunk 0 = GBF(d) then en; chunk 1 = e (bulk-copied)
-constexpr int AT_WE = 32768;                      // 16 KB: block edge_emb image (N=64, K=128)
-constexpr int AT_W0 = AT_WE + 16384;              // 32 KB: lin_edge0 image (N=256, K=64)
+constexpr int AT_THREADS = 512;
+constexpr int AT_GROUP = 256;
+constexpr int AT_WE = 0;                          // 16 KB: block edge_emb image (N=64, K=128)
+constexpr int AT_W0 = AT_WE + 16384;              // 32 KB: lin_edge0 image (N=256 split-head, K=64)
 constexpr int AT_W1 = AT_W0 + 32768;              // 32 KB: lin_edge1 image
-constexpr int AT_S = AT_W1 + 32768;               // 32 KB: message staging, per column half [128 rows][32] fp32, xor-swizzled
-constexpr int AT_LG = AT_S + 32768;               // logits / exp values [128][17] fp32
-constexpr int AT_GI = AT_LG + 128 * 17 * 4;       // 1 / (sum + 1e-16) per (group, head)  [128][16]
-constexpr int AT_LN = AT_GI + 128 * 16 * 4;       // LayerNorm partial sums [128][2] float2
-constexpr int AT_MISC = AT_LN + 128 * 2 * 8;      // barriers, tmem slot, GBF constants, bias, group table
-constexpr int AT_SMEM = AT_MISC + 128 + 768 + 256 + 512 + 512;
+constexpr int AT_GRP = AT_W1 + 32768;             // per group:
+constexpr int G_A0 = 0;                           //   32 KB fp16: chunk 0 = GBF(d) then en; chunk 1 = e (bulk-copied)
+constexpr int G_S = 32768;                        //   16 KB: message staging, per column half [128 rows][16] fp32, xor-swizzled
+constexpr int G_LG = G_S + 16384;                 //   logits / exp values [128][17] fp32
+constexpr int G_GI = G_LG + 128 * 17 * 4;         //   1 / (sum + 1e-16) per (group, head)  [128][16]
+constexpr int G_LN = G_GI + 128 * 16 * 4;         //   LayerNorm partial sums [128][2] float2
+constexpr int G_GT = G_LN + 128 * 2 * 8;          //   group table: start | len << 8 [128], atom [128]
+constexpr int G_BYTES = ((G_GT + 1024 + 1023) / 1024) * 1024;
+constexpr int AT_MISC = AT_GRP + 2 * G_BYTES;     // barriers, tmem slot
+constexpr int AT_SMEM = AT_MISC + 128;
 static_assert(AT_SMEM <= 232448, "shared memory budget");
 
 constexpr int SC = 18;        // sub_channels = 256 // 14   (models/layers.py:112)
 constexpr int HQ = 126;       // q/k/g0 columns of one half = 7 heads x 18
 
-__global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  require_smem_alignment(smem);
-  uint8_t* A0 = smem + AT_A0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_MISC);   // 0: weights, 1: e tile, 2..4: MMA1..3
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + AT_MISC + 64);
-  float* gbf = reinterpret_cast<float*>(smem + AT_MISC + 128);
-  float* bemb = gbf + 192;
-  uint32_t* gt_meta = reinterpret_cast<uint32_t*>(bemb + 64);     // [128] group start | len << 8
-  int* gt_node = reinterpret_cast<int*>(gt_meta + 128);           // [128] group atom
-  float* LG = reinterpret_cast<float*>(smem + AT_LG);
-  float* GI = reinterpret_cast<float*>(smem + AT_GI);
-  float2* LNS = reinterpret_cast<float2*>(smem + AT_LN);
+__device__ __forceinline__ void at_group_sync(int grp) {
+  tc_fence_before();
+  named_bar_sync(1 + grp, AT_GROUP);
+  tc_fence_after();
+}
 
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int rq = warp & 3, half = warp >> 2;
-  const int row = rq * 32 + lane;
-  float* S = reinterpret_cast<float*>(smem + AT_S) + half * (128 * 32);
+struct AtCtx {
+  uint8_t* gs;                 // group-private shared memory
+  const uint8_t* WE; const uint8_t* W0; const uint8_t* W1;
+  uint64_t* bar_w; uint64_t* bar_e; uint64_t* bar_m;
+  uint32_t tm;
+  int grp, lt, row, rq, lane, tile0, tile1;
+};
 
-  const int per = (a.p.n_tiles + gridDim.x - 1) / gridDim.x;
-  const int tile0 = blockIdx.x * per;
-  const int tile1 = min(tile0 + per, a.p.n_tiles);
-
-  if (t == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
-    fence_barrier_init();
-    mbar_expect_tx(&bars[0], 16384 + 32768 + 32768);
-    bulk_g2s(smem + AT_WE, a.w_emb_img, 16384, &bars[0]);
-    bulk_g2s(smem + AT_W0, a.w0_img, 32768, &bars[0]);
-    bulk_g2s(smem + AT_W1, a.w1_img, 32768, &bars[0]);
-    if (tile0 < tile1) {
-      mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
-      bulk_g2s(A0 + CHUNK_BYTES_A, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)tile0 * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
-    }
-  }
-  for (int i = t; i < 192; i += AT_THREADS) gbf[i] = a.gbf[i];
-  if (t < 64) bemb[t] = a.b_emb[t];
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
-  sync_tc();
-  const uint32_t tmem = *tmem_slot;
-  uint32_t par = 0;
+template <int HALF, bool UNI>
+__device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c) {
+  uint8_t* A0 = c.gs + G_A0;
+  float* S = reinterpret_cast<float*>(c.gs + G_S) + HALF * (128 * 16);
+  float* LG = reinterpret_cast<float*>(c.gs + G_LG);
+  float* GI = reinterpret_cast<float*>(c.gs + G_GI);
+  float2* LNS = reinterpret_cast<float2*>(c.gs + G_LN);
+  uint32_t* gt_meta = reinterpret_cast<uint32_t*>(c.gs + G_GT);
+  int* gt_node = reinterpret_cast<int*>(gt_meta + 128);
+  const int row = c.row, lane = c.lane, lt = c.lt, rq = c.rq;
+  const uint32_t tm = c.tm;
+  const int team_bar = 3 + 2 * c.grp + HALF;
   const float4* pos = reinterpret_cast<const float4*>(a.pos);
+  uint32_t par_m = 0, par_e = 0;
 
+  if (lt == 0 && c.tile0 < c.tile1) {
+    mbar_expect_tx(c.bar_e, CHUNK_BYTES_A);
+    bulk_g2s(A0 + CHUNK_BYTES_A, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)c.tile0 * CHUNK_BYTES_A, CHUNK_BYTES_A, c.bar_e);
+  }
   // row metadata of a tile is fetched one tile ahead
-  RowInfo rn = load_row(a.p, min(tile0, a.p.n_tiles - 1), row);
-  int ngn = a.p.tile_ngroups[min(tile0, a.p.n_tiles - 1)];
-  uint8_t exn = a.extra[(size_t)min(tile0, a.p.n_tiles - 1) * TILE_ROWS + row];
-  for (int tile = tile0; tile < tile1; ++tile) {
+  const int tfirst = min(c.tile0, a.p.n_tiles - 1);
+  RowInfo rn = load_row(a.p, tfirst, row);
+  int ngn = a.p.tile_ngroups[tfirst];
+  uint8_t exn = a.extra[(size_t)tfirst * TILE_ROWS + row];
+  for (int tile = c.tile0; tile < c.tile1; tile += 2) {
     const RowInfo r = rn;
     const int ng = ngn;
     const uint8_t ex = exn;
-    if (half == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
+    if (HALF == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
     const float* tr = a.tab + (size_t)r.mol * a.ld_tab + a.tab_off;
 
-    // ---- distance features -> A0 chunk 0, columns [32*half, 32*half+32)
+    // ---- distance features -> A0 chunk 0, columns [32*HALF, 32*HALF+32)
     {
+      const float gsc = UNI ? c_atmod[128] : tr[tab_gbf(D_)], gsh = UNI ? c_atmod[129] : tr[tab_gbf(D_) + 1];
+      const float d = sq_dist(pos[r.j], pos[r.g]);
+      const float x = fmaf(d, gsc, d) + gsh;
       float df[32];
-      if (r.valid) {
-        const float d = sq_dist(pos[r.j], pos[r.g]);
-        gbf_eval_half(d, tr[tab_gbf(D_)], tr[tab_gbf(D_) + 1], gbf, half, df);
-      } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) df[i] = 0.f;
+      for (int i = 0; i < 32; ++i) {
+        const int col = 32 * HALF + i;
+        if (col == 0) {
+          df[i] = x;
+        } else {
+          const float w = (x - a.gbf4[4 * col]) * a.gbf4[4 * col + 1];
+          df[i] = ex2_fast(-(w * w)) * a.gbf4[4 * col + 2];
+        }
       }
-      st_rowh<32>(A0, row, 0, 4 * half, df);
+      st_rowh<32>(A0, row, 0, 4 * HALF, df);       // padding rows: finite garbage, masked by alpha = 0 below
     }
     {
-      const int nt_ = min(tile + 1, tile1 - 1);
+      const int nt_ = tile + 2 < c.tile1 ? tile + 2 : tile;
       rn = load_row(a.p, nt_, row);
       ngn = a.p.tile_ngroups[nt_];
       exn = a.extra[(size_t)nt_ * TILE_ROWS + row];
     }
     fence_async_smem();
-    sync_tc();
-    if (t == 0) {
-      if (tile == tile0) mbar_wait(&bars[0], 0);
-      mbar_wait(&bars[1], par);
+    at_group_sync(c.grp);
+    if (lt == 0) {
+      if (tile == c.tile0) mbar_wait(c.bar_w, 0);
+      mbar_wait(c.bar_e, par_e);
       tc_fence_after();
-      mma_tile_h(tmem + 256, smem_u32(A0), smem_u32(smem + AT_WE), 64, 2, false);     // e1 = edge_emb([dist | e])
-      umma_commit(&bars[2]);
+      mma_tile_h(tm, smem_u32(A0), smem_u32(c.WE), 64, 2, false);                   // e1 = edge_emb([dist | e])
+      umma_commit(c.bar_m);
     }
-    mbar_wait(&bars[2], par);
+    par_e ^= 1;
+    mbar_wait(c.bar_m, par_m);
+    par_m ^= 1;
     tc_fence_after();
-    if (t == 0 && tile + 1 < tile1) {                  // the e chunk is consumed: prefetch the next tile's
-      mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
-      bulk_g2s(A0 + CHUNK_BYTES_A, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 1) * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
+    if (lt == 0 && tile + 2 < c.tile1) {               // the e chunk is consumed: prefetch this group's next tile
+      mbar_expect_tx(c.bar_e, CHUNK_BYTES_A);
+      bulk_g2s(A0 + CHUNK_BYTES_A, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 2) * CHUNK_BYTES_A, CHUNK_BYTES_A, c.bar_e);
     }
 
     // ---- en = LN(e1) * (1 + scale_msa) + shift_msa  -> A0 chunk 0
     {
       float x[32];
-      tmem_ld32(tmem_addr(tmem, 256 + 32 * half), x);
+      tmem_ld32(tmem_addr(tm, 32 * HALF), x);
       float s = 0.f, q = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { x[i] += bemb[32 * half + i]; s += x[i]; q = fmaf(x[i], x[i], q); }
-      LNS[row * 2 + half] = make_float2(s, q);
-      __syncthreads();
-      const float2 o = LNS[row * 2 + (half ^ 1)];
+      for (int i = 0; i < 32; ++i) { x[i] += a.b_emb[32 * HALF + i]; s += x[i]; q = fmaf(x[i], x[i], q); }
+      LNS[row * 2 + HALF] = make_float2(s, q);
+      at_group_sync(c.grp);                              // (also: every e1 read is done before MMA2 overwrites the columns)
+      const float2 o = LNS[row * 2 + (HALF ^ 1)];
       const float mean = (s + o.x) * (1.0f / 64.0f);
       const float var = fmaxf((q + o.y) * (1.0f / 64.0f) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + 1e-6f);
-      const float* shift = tr + tab_edge(D_) + 32 * half;
-      const float* scale = shift + ED_;
+      const float nmr = -mean * rstd;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 sh = *reinterpret_cast<const float4*>(shift + i);
-        const float4 sc = *reinterpret_cast<const float4*>(scale + i);
-        x[i] = r.valid ? fmaf((x[i] - mean) * rstd, 1.0f + sc.x, sh.x) : 0.f;
-        x[i + 1] = r.valid ? fmaf((x[i + 1] - mean) * rstd, 1.0f + sc.y, sh.y) : 0.f;
-        x[i + 2] = r.valid ? fmaf((x[i + 2] - mean) * rstd, 1.0f + sc.z, sh.z) : 0.f;
-        x[i + 3] = r.valid ? fmaf((x[i + 3] - mean) * rstd, 1.0f + sc.w, sh.w) : 0.f;
+      for (int i = 0; i < 32; ++i) {
+        const int col = 32 * HALF + i;
+        const float n = fmaf(x[i], rstd, nmr);
+        const float sc = UNI ? c_atmod[64 + col] : tr[tab_edge(D_) + ED_ + col];
+        const float sh = UNI ? c_atmod[col] : tr[tab_edge(D_) + col];
+        x[i] = fmaf(n, sc, n) + sh;
       }
-      st_rowh<32>(A0, row, 0, 4 * half, x);
+      st_rowh<32>(A0, row, 0, 4 * HALF, x);
     }
     fence_async_smem();
-    sync_tc();
-    if (t == 0) {
-      mma_tile_h(tmem, smem_u32(A0), smem_u32(smem + AT_W0), 256, 1, false);        // g0 pre-activation
-      umma_commit(&bars[3]);
-      mma_tile_h(tmem + 256, smem_u32(A0), smem_u32(smem + AT_W1), 256, 1, false);  // g1 pre-activation
-      umma_commit(&bars[4]);
+    at_group_sync(c.grp);
+    if (lt == 0) {
+      mma_tile_h(tm, smem_u32(A0), smem_u32(c.W0), 256, 1, false);                  // g0 pre-activation
+      umma_commit(c.bar_m);
     }
     // ---- logits of this half's 7 heads: a[s] = sum_ch q[g,s,ch] k[j,s,ch] tanh(g0[s,ch]) / sqrt(16)
-    // q / k rows are fp16; the loads of a 32-column chunk are issued one chunk ahead of its use
-    const uint16_t* qkv16 = static_cast<const uint16_t*>(a.qkv);
-    const uint16_t* qrow = qkv16 + (size_t)r.g * a.ldq + 128 * half;
-    const uint16_t* krow = qkv16 + (size_t)r.j * a.ldq + D_ + 128 * half;
-    const uint16_t* vrow = qkv16 + (size_t)r.j * a.ldq + 2 * D_ + 128 * half;
-    H32 qc = ldg_h32(qrow), kc = ldg_h32(krow);
-    mbar_wait(&bars[3], par);
-    tc_fence_after();
-    H32 vc;
+    // q / k pieces of a 16-column chunk are loaded one chunk ahead of their use
+    H16 qc, kc;
     {
+      const uint4* qb = static_cast<const uint4*>(a.qkv) + (size_t)(16 * HALF) * a.ldq + r.g;
+      const uint4* kb = static_cast<const uint4*>(a.qkv) + (size_t)(32 + 16 * HALF) * a.ldq + r.j;
+      qc.u[0] = __ldg(qb); qc.u[1] = __ldg(qb + a.ldq);
+      kc.u[0] = __ldg(kb); kc.u[1] = __ldg(kb + a.ldq);
+      mbar_wait(c.bar_m, par_m);
+      par_m ^= 1;
+      tc_fence_after();
       float lg[7];
 #pragma unroll
       for (int s = 0; s < 7; ++s) lg[s] = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        H32 qn, kn;
-        if (c < 3) { qn = ldg_h32(qrow + (c + 1) * 32); kn = ldg_h32(krow + (c + 1) * 32); }
-        else vc = ldg_h32(vrow);
-        float acc[32];
-        tmem_ld32(tmem_addr(tmem, 128 * half + c * 32), acc);
+      for (int ch = 0; ch < 8; ++ch) {
+        H16 qn, kn;
+        if (ch < 7) {
+          qn.u[0] = __ldg(qb + (size_t)(2 * ch + 2) * a.ldq); qn.u[1] = __ldg(qb + (size_t)(2 * ch + 3) * a.ldq);
+          kn.u[0] = __ldg(kb + (size_t)(2 * ch + 2) * a.ldq); kn.u[1] = __ldg(kb + (size_t)(2 * ch + 3) * a.ldq);
+        }
+        float acc[16];
+        tmem_ld16(tmem_addr(tm, 128 * HALF + 16 * ch), acc);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           float qf[8], kf[8];
           unpack8(qc.u[i], qf);
           unpack8(kc.u[i], kf);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int col = c * 32 + 8 * i + e;
+            const int col = 16 * ch + 8 * i + e;
             if (col < HQ) lg[col / SC] = fmaf(qf[e] * kf[e], tanh_fast(acc[8 * i + e]), lg[col / SC]);
           }
         }
-        if (c < 3) { qc = qn; kc = kn; }
+        if (ch < 7) { qc = qn; kc = kn; }
       }
       // head order of the reference: the two adjacency heads first (1 where adjacent, -1e10 otherwise,
       // models/layers.py:170-174), then the 14 computed heads
-      LG[row * 17 + half] = ((ex >> half) & 1) ? 1.0f : -1e10f;
+      LG[row * 17 + HALF] = ((ex >> HALF) & 1) ? 1.0f : -1e10f;
 #pragma unroll
-      for (int s = 0; s < 7; ++s) LG[row * 17 + 2 + 7 * half + s] = lg[s] * 0.25f;
+      for (int s = 0; s < 7; ++s) LG[row * 17 + 2 + 7 * HALF + s] = lg[s] * 0.25f;
     }
-    __syncthreads();
+    at_group_sync(c.grp);                                  // logits visible; every g0 read done
+    if (lt == 0) {
+      mma_tile_h(tm, smem_u32(A0), smem_u32(c.W1), 256, 1, false);                  // g1 pre-activation, under the softmax
+      umma_commit(c.bar_m);
+    }
+    // first value chunk in flight under the softmax
+    const uint4* vb = static_cast<const uint4*>(a.qkv) + (size_t)(64 + 16 * HALF) * a.ldq + r.j;
+    H16 vc;
+    vc.u[0] = __ldg(vb); vc.u[1] = __ldg(vb + a.ldq);
     // (group, head): max, exp in place, 1 / (sum + 1e-16)      (PyG softmax, models/layers.py:178)
-    for (int it = t; it < ng * 16; it += AT_THREADS) {
+    for (int it = lt; it < ng * 16; it += AT_GROUP) {
       const int gi = it >> 4, h = it & 15;
       const int gs = gt_meta[gi] & 255u, gl = (gt_meta[gi] >> 8) & 255u;
       float m = -INFINITY;
@@ -214,35 +229,38 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
       }
       GI[gi * 16 + h] = 1.0f / (s + 1e-16f);
     }
-    __syncthreads();
+    named_bar_sync(1 + c.grp, AT_GROUP);
     float alpha[8];
 #pragma unroll
-    for (int h = 0; h < 8; ++h) alpha[h] = r.valid ? LG[row * 17 + 8 * half + h] * GI[r.gi * 16 + 8 * half + h] : 0.f;
+    for (int h = 0; h < 8; ++h) alpha[h] = r.valid ? LG[row * 17 + 8 * HALF + h] * GI[r.gi * 16 + 8 * HALF + h] : 0.f;
     // groups whose first row lies in this warp's 32 rows are summed by this warp
     const uint32_t starts = __ballot_sync(0xffffffffu, r.valid && row == r.gs);
 
-    // ---- messages and per-group sums
-    mbar_wait(&bars[4], par);
+    // ---- messages and per-group sums, 16 value columns (= one head) at a time
+    mbar_wait(c.bar_m, par_m);
+    par_m ^= 1;
     tc_fence_after();
     {
+      float* srow = S + row * 16;
+      const int sw = lane >> 1;
+#pragma unroll 1
+      for (int ch = 0; ch < 8; ++ch) {
+        H16 vn;
+        if (ch < 7) { vn.u[0] = __ldg(vb + (size_t)(2 * ch + 2) * a.ldq); vn.u[1] = __ldg(vb + (size_t)(2 * ch + 3) * a.ldq); }
+        float acc[16];
+        tmem_ld16(tmem_addr(tm, 128 * HALF + 16 * ch), acc);
+        const float al = alpha[ch];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        H32 vn;
-        if (c < 3) vn = ldg_h32(vrow + (c + 1) * 32);
-        float acc[32];
-        tmem_ld32(tmem_addr(tmem, 256 + 128 * half + c * 32), acc);
-        float* srow = S + row * 32;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           float vf[8];
           unpack8(vc.u[i], vf);
-          const float al = alpha[2 * c + (i >> 1)];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) srow[(8 * i + e) ^ lane] = vf[e] * tanh_fast(acc[8 * i + e]) * al;
+          for (int e = 0; e < 8; ++e) srow[(8 * i + e) ^ sw] = vf[e] * tanh_fast(acc[8 * i + e]) * al;
         }
-        if (c < 3) vc = vn;
-        named_bar_sync(1 + half, 128);
+        if (ch < 7) vc = vn;
+        named_bar_sync(team_bar, 128);
         uint32_t m = starts;
+        const int cc = lane & 15, sub = lane >> 4;
         while (m) {
           const int r0 = __ffs(m) - 1;
           m &= m - 1;
@@ -250,18 +268,55 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(AttnArgs a) {
           const int node = __shfl_sync(0xffffffffu, r.g, r0);
           const int R0 = rq * 32 + r0;
           float sum = 0.f;
-          for (int rr = R0; rr < R0 + gl; ++rr) sum += S[rr * 32 + (lane ^ (rr & 31))];
-          a.hnode[(size_t)node * D_ + 128 * half + c * 32 + lane] = sum;
+          for (int rr = R0 + sub; rr < R0 + gl; rr += 2) sum += S[rr * 16 + (cc ^ ((rr & 31) >> 1))];
+          sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+          if (sub == 0) a.hnode[(size_t)node * D_ + 128 * HALF + 16 * ch + cc] = sum;
         }
-        named_bar_sync(1 + half, 128);
+        named_bar_sync(team_bar, 128);
       }
     }
-    sync_tc();
-    par ^= 1;
+    tc_fence_before();                                       // g1 reads are ordered before the next tile's MMA1 by its group_sync
   }
-  if (tile0 >= tile1 && t == 0) mbar_wait(&bars[0], 0);   // never leave with bulk copies in flight
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1) k_attn(const __grid_constant__ AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  require_smem_alignment(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_MISC);   // 0: weights, 1,2: e tile of group 0,1, 3,4: MMA of group 0,1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + AT_MISC + 64);
+  const int t = threadIdx.x, warp = t >> 5;
+  const int grp = t >> 8, lt = t & 255, lw = lt >> 5;
+  const int per = (a.p.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile0 = blockIdx.x * per;
+  const int tile1 = min(tile0 + per, a.p.n_tiles);
+
+  if (t == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+    mbar_expect_tx(&bars[0], 16384 + 32768 + 32768);
+    bulk_g2s(smem + AT_WE, a.w_emb_img, 16384, &bars[0]);
+    bulk_g2s(smem + AT_W0, a.w0_img, 32768, &bars[0]);
+    bulk_g2s(smem + AT_W1, a.w1_img, 32768, &bars[0]);
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
   sync_tc();
-  if (warp == 0) tmem_dealloc<512>(tmem);
+  const bool uni = a.nonuni != nullptr && *a.nonuni == 0;
+
+  AtCtx c;
+  c.gs = smem + AT_GRP + grp * G_BYTES;
+  c.WE = smem + AT_WE; c.W0 = smem + AT_W0; c.W1 = smem + AT_W1;
+  c.bar_w = &bars[0]; c.bar_e = &bars[1 + grp]; c.bar_m = &bars[3 + grp];
+  c.tm = *tmem_slot + 256u * grp;
+  c.grp = grp; c.lt = lt; c.rq = lw & 3; c.lane = t & 31; c.row = (lw & 3) * 32 + (t & 31);
+  c.tile0 = tile0 + grp; c.tile1 = tile1;
+  if ((lw >> 2) == 0) {
+    if (uni) at_group_loop<0, true>(a, c); else at_group_loop<0, false>(a, c);
+  } else {
+    if (uni) at_group_loop<1, true>(a, c); else at_group_loop<1, false>(a, c);
+  }
+  if (t == 0) mbar_wait(&bars[0], 0);                    // never leave with bulk copies in flight
+  sync_tc();
+  if (warp == 0) tmem_dealloc<512>(*tmem_slot);
 }
 
 }  // namespace
@@ -273,7 +328,15 @@ cudaError_t launch_attn(const AttnArgs& a, int num_sms, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  const int grid = a.p.n_tiles < num_sms ? a.p.n_tiles : num_sms;
+  if (a.nonuni) {     // row 0 of the table feeds the uniform fast path: edge (shift, scale)_msa and the GBF pair
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_atmod, a.tab + a.tab_off + tab_edge(D_), sizeof(float) * 128, 0,
+                                            cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbolAsync(c_atmod, a.tab + a.tab_off + tab_gbf(D_), sizeof(float) * 2, sizeof(float) * 128,
+                                cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return e;
+  }
+  const int grid = a.p.n_tiles < 2 * num_sms ? (a.p.n_tiles + 1) / 2 : num_sms;
   k_attn<<<grid, AT_THREADS, AT_SMEM, st>>>(a);
   return cudaGetLastError();
 }

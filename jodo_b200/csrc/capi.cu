@@ -120,7 +120,7 @@ int jodo_edge_embed(const jodo_edge_embed_args* a, void* stream) {
 int jodo_attn(const jodo_attn_args* a, void* stream) {
   if (!a) return fail("jodo_attn: null args");
   if (const char* m = check_plan(a->p)) return fail(m);
-  if (a->ldq % 8 || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_attn: strides must be multiples of 4");
+  if (a->ldq < a->p.Nn || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_attn: bad strides");
   if (!a->e16 || !a->hnode) return fail("jodo_attn: null buffer");
   JODO_LAUNCH(jodo::launch_attn(*a, num_sms(), S(stream)), "jodo_attn");
 }

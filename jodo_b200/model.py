@@ -50,7 +50,7 @@ class _Workspace:
         img = lambda k: torch.zeros(mt * 128 * k, device=dev, dtype=torch.float16)    # fp16 operand image [mt][k/64][128][64]
         self.hn_img, self.h2_img, self.hnode_img, self.hout_img = img(D), img(D), img(D), img(D)
         self.ff_img = img(d.r * D)
-        self.qkv = h16(Nn, 3 * D)                           # fp16 per-atom operands gathered by the edge kernels
+        self.qkv = h16(3 * D // 8, Nn, 8)                   # fp16 per-atom operands gathered by the edge kernels (piece-major)
         self.hnode = zf(Nn, D)                             # atoms without partners are never written: stay 0
         self.pbuf = h16(8, Nn, 8)                           # piece-major hoisted node2edge_lin part
         self.h2 = f(Nn, D)
@@ -187,9 +187,9 @@ class _DGTBase(nn.Module):
             _lib.call('jodo_ln_mod_img', _lib.ptr(h), _c(h.stride(0)), None, _c(0), _lib.ptr(ws.tab), _c(ld_tab),
                       _c(0), _c(off), _c(off + D), ctypes.byref(ps), None, _c(0), _lib.ptr(ws.hn_img), None, st)
             ilin(p + 'qkv', ws.hn_img, C16=ws.qkv)
-            aa = _lib.AttnArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(ws.qkv), 3 * D, _lib.dp(ws.tab), ld_tab,
-                               off, _lib.dp(ws.extra), pk.ptr(p + 'gbf'), pk.ptr(p + 'emb.img'), pk.ptr(p + 'emb.b'),
-                               pk.ptr(p + 'e0.img'), pk.ptr(p + 'e1.img'), _lib.dp(ws.hnode))
+            aa = _lib.AttnArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(ws.qkv), plan.Nn, _lib.dp(ws.tab), ld_tab,
+                               off, _lib.dp(ws.extra), pk.ptr(p + 'emb.img'), pk.ptr(p + 'e0.img'), pk.ptr(p + 'e1.img'),
+                               _lib.dp(ws.hnode), ws.flags.data_ptr() + 8, pk.host[p + 'gbf4'], pk.host[p + 'emb.b'])
             _lib.call('jodo_attn', ctypes.byref(aa), st)
             # node path: gated residual + norm2 (+ image of hnode), hoisted node2edge, FFN, hoisted input_lin parts, node_l
             _lib.call('jodo_ln_mod_img', _lib.ptr(h), _c(h.stride(0)), _lib.ptr(ws.hnode), _c(D), _lib.ptr(ws.tab),

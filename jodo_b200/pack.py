@@ -273,7 +273,7 @@ def pack_model(sd, dims, device):
         add_lin(p + 'node_l', W(f'node_{l}'), Bv(f'node_{l}'), 64, n_pad=64)
         pk.add(p + 'gbf', _gbf_consts(sd, f'{b}.dist_layer', device))
         pk.add(p + 'emb.img', weight_image_h(W(f'{b}.edge_emb'), ed))                       # [64, 128]: [dist | e]
-        pk.add(p + 'emb.b', Bv(f'{b}.edge_emb'))
+        pk.add_host(p + 'emb.b', Bv(f'{b}.edge_emb'))
         pk.add(p + 'e0.img', weight_image_h(split_heads(W(f'{b}.attn_mpnn.lin_edge0'), D, d.qk), D))
         pk.add(p + 'e1.img', weight_image_h(W(f'{b}.attn_mpnn.lin_edge1'), D))
         w3, w4 = W(f'{b}.ff_linear3'), W(f'{b}.ff_linear4')    # [ed r, ed], [ed, ed r]

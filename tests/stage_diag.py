@@ -77,6 +77,7 @@ def run_case(name, device='cuda', verbose=True):
         m = inp['node_mask'].double()
         hn = act_image_to_rows(b['hn_img'], D)[:plan.Nn]
         rep.append((f'b{l}.hn', rel(packed_to_dense(plan, hn), ob['hn'] * m)))
+        b['qkv'] = b['qkv'].permute(1, 0, 2).reshape(b['qkv'].shape[1], -1)      # piece-major -> rows
         qk = ob['q'].shape[-1]
         hq = qk // 2                      # q / k are stored as two head halves at columns [0, qk/2) and [D/2, D/2 + qk/2)
         unsplit = lambda x: torch.cat([x[:, :hq], x[:, D // 2:D // 2 + hq]], dim=1)
