@@ -34,8 +34,9 @@ constexpr int AT_W0 = AT_WE + 16384;              // 32 KB: lin_edge0 image (N=2
 constexpr int AT_W1 = AT_W0 + 32768;              // 32 KB: lin_edge1 image
 constexpr int AT_GRP = AT_W1 + 32768;             // per group:
 constexpr int G_A0 = 0;                           //   32 KB fp16: chunk 0 = GBF(d) then en; chunk 1 = e (bulk-copied)
-constexpr int G_S = 32768;                        //   16 KB: message staging, per column half [128 rows][16] fp32, xor-swizzled
-constexpr int G_LG = G_S + 16384;                 //   logits / exp values [128][17] fp32
+constexpr int S_ROW = 20;                         //   staging row: 16 fp32 + 16 bytes of padding (conflict-free STS.128 / LDS.128)
+constexpr int G_S = 32768;                        //   20 KB: message staging, per column half [128 rows][20] fp32
+constexpr int G_LG = G_S + 2 * 128 * S_ROW * 4;                 //   logits / exp values [128][17] fp32
 constexpr int G_GI = G_LG + 128 * 17 * 4;         //   1 / (sum + 1e-16) per (group, head)  [128][16]
 constexpr int G_LN = G_GI + 128 * 16 * 4;         //   LayerNorm partial sums [128][2] float2
 constexpr int G_GT = G_LN + 128 * 2 * 8;          //   group table: start | len << 8 [128], atom [128]
@@ -64,7 +65,7 @@ struct AtCtx {
 template <int HALF, bool UNI>
 __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c) {
   uint8_t* A0 = c.gs + G_A0;
-  float* S = reinterpret_cast<float*>(c.gs + G_S) + HALF * (128 * 16);
+  float* S = reinterpret_cast<float*>(c.gs + G_S) + HALF * (128 * S_ROW);
   float* LG = reinterpret_cast<float*>(c.gs + G_LG);
   float* GI = reinterpret_cast<float*>(c.gs + G_GI);
   float2* LNS = reinterpret_cast<float2*>(c.gs + G_LN);
@@ -241,8 +242,8 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
     par_m ^= 1;
     tc_fence_after();
     {
-      float* srow = S + row * 16;
-      const int sw = lane >> 1;
+      float* srow = S + row * S_ROW;
+      const int rs = lane & 7, c4 = lane >> 3;        // row-sum pass: lane = (row subset, 4-column piece)
 #pragma unroll 1
       for (int ch = 0; ch < 8; ++ch) {
         H16 vn;
@@ -255,22 +256,33 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
           float vf[8];
           unpack8(vc.u[i], vf);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) srow[(8 * i + e) ^ sw] = vf[e] * tanh_fast(acc[8 * i + e]) * al;
+          for (int e = 0; e < 8; ++e) acc[8 * i + e] = (vf[e] * al) * tanh_fast(acc[8 * i + e]);
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<float4*>(srow + 4 * k) = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
         if (ch < 7) vc = vn;
         named_bar_sync(team_bar, 128);
         uint32_t m = starts;
-        const int cc = lane & 15, sub = lane >> 4;
         while (m) {
           const int r0 = __ffs(m) - 1;
           m &= m - 1;
           const int gl = __shfl_sync(0xffffffffu, r.gl, r0);
           const int node = __shfl_sync(0xffffffffu, r.g, r0);
-          const int R0 = rq * 32 + r0;
-          float sum = 0.f;
-          for (int rr = R0 + sub; rr < R0 + gl; rr += 2) sum += S[rr * 16 + (cc ^ ((rr & 31) >> 1))];
-          sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-          if (sub == 0) a.hnode[(size_t)node * D_ + 128 * HALF + 16 * ch + cc] = sum;
+          const float* sp = S + (rq * 32 + r0 + rs) * S_ROW + 4 * c4;
+          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = rs; k < gl; k += 8, sp += 8 * S_ROW) {
+            const float4 v = *reinterpret_cast<const float4*>(sp);
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+          }
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
+            sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+          }
+          if (rs == 0) *reinterpret_cast<float4*>(a.hnode + (size_t)node * D_ + 128 * HALF + 16 * ch + 4 * c4) = sum;
         }
         named_bar_sync(team_bar, 128);
       }
