@@ -12,9 +12,9 @@ timeout 600 python bench.py --steps 30 --warmup 5 > $OUT/bench_qm9.json 2> $OUT/
 timeout 600 python bench.py --workload geom --steps 20 --warmup 3 > $OUT/bench_geom.json 2> $OUT/bench_geom.err; echo "bench geom rc=$?"
 timeout 300 python bench.py --impl reference --steps 4 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "bench ref rc=$?"
 kill $SMI
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches.csv \
+JODO_CUDA_PROFILER=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/launches_run.log 2>&1; echo "ncu launches rc=$?"
-for k in k_attn k_equi k_edge_update k_rowlinear; do
+for k in k_attn k_equi k_edge_update k_imglinear; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 12 -c 2 -f -o $OUT/prof_$k \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/prof_$k.log 2>&1; echo "ncu $k rc=$?"
 done
