@@ -33,12 +33,13 @@ constexpr int AT_WE = 0;                          // 16 KB: block edge_emb image
 constexpr int AT_W0 = AT_WE + 16384;              // 32 KB: lin_edge0 image (N=256 split-head, K=64)
 constexpr int AT_W1 = AT_W0 + 32768;              // 32 KB: lin_edge1 image
 constexpr int AT_GRP = AT_W1 + 32768;             // per group:
-constexpr int G_A0 = 0;                           //   32 KB fp16: chunk 0 = GBF(d) then en; chunk 1 = e (bulk-copied)
-constexpr int S_ROW = 20;                         //   staging row: 16 fp32 + 16 bytes of padding (conflict-free STS.128 / LDS.128)
-constexpr int G_S = 32768;                        //   20 KB: message staging, per column half [128 rows][20] fp32
-constexpr int G_LG = G_S + 2 * 128 * S_ROW * 4;                 //   logits / exp values [128][17] fp32
-constexpr int G_GI = G_LG + 128 * 17 * 4;         //   1 / (sum + 1e-16) per (group, head)  [128][16]
-constexpr int G_LN = G_GI + 128 * 16 * 4;         //   LayerNorm partial sums [128][2] float2
+constexpr int G_A0 = 0;                           //   32 KB fp16: chunk 0 = GBF(d), then en, then message image of half 0;
+                                                  //                chunk 1 = e (bulk-copied one tile ahead)
+constexpr int G_MIB = 32768;                      //   17 KB: logits / exp values [128][17] fp32 + 1/(sum + 1e-16) [128][16] during
+constexpr int G_LG = G_MIB;                       //          the softmax, then the message image of half 1 (16 KB)
+constexpr int G_GI = G_LG + 128 * 17 * 4;
+constexpr int G_IND = G_MIB + 17408;              //   16 KB: row -> group indicator, fp16 K-major image [64 slots][128 rows]
+constexpr int G_LN = G_IND + 16384;               //   LayerNorm partial sums [128][2] float2
 constexpr int G_GT = G_LN + 128 * 2 * 8;          //   group table: start | len << 8 [128], atom [128]
 constexpr int G_BYTES = ((G_GT + 1024 + 1023) / 1024) * 1024;
 constexpr int AT_MISC = AT_GRP + 2 * G_BYTES;     // barriers, tmem slot
@@ -47,6 +48,14 @@ static_assert(AT_SMEM <= 232448, "shared memory budget");
 
 constexpr int SC = 18;        // sub_channels = 256 // 14   (models/layers.py:112)
 constexpr int HQ = 126;       // q/k/g0 columns of one half = 7 heads x 18
+
+// Shared-memory descriptor of an MN-major SWIZZLE_128B operand (cute/arch/mma_sm100_desc.hpp, make_umma_desc<Major::MN>):
+// 64 consecutive MN elements (128 B) per K row, 8-row swizzle atoms of 1024 B (SBO), MN blocks of 64 `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor with an MN-major A operand (bit 15), M = 128
+__device__ __host__ constexpr uint32_t umma_idesc_f16_amn(int n) { return umma_idesc_f16(n) | (1u << 15); }
 
 __device__ __forceinline__ void at_group_sync(int grp) {
   tc_fence_before();
@@ -65,7 +74,8 @@ struct AtCtx {
 template <int HALF, bool UNI>
 __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c) {
   uint8_t* A0 = c.gs + G_A0;
-  float* S = reinterpret_cast<float*>(c.gs + G_S) + HALF * (128 * S_ROW);
+  uint8_t* MI = HALF == 0 ? A0 : c.gs + G_MIB;       // this half's 64-column message image (MN-major A operand chunk)
+  uint8_t* IND = c.gs + G_IND;
   float* LG = reinterpret_cast<float*>(c.gs + G_LG);
   float* GI = reinterpret_cast<float*>(c.gs + G_GI);
   float2* LNS = reinterpret_cast<float2*>(c.gs + G_LN);
@@ -73,7 +83,7 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
   int* gt_node = reinterpret_cast<int*>(gt_meta + 128);
   const int row = c.row, lane = c.lane, lt = c.lt, rq = c.rq;
   const uint32_t tm = c.tm;
-  const int team_bar = 3 + 2 * c.grp + HALF;
+  uint32_t ind_prev = 0xFFFFFFFFu;                  // byte offset of this row's 1.0 in the indicator image
   const float4* pos = reinterpret_cast<const float4*>(a.pos);
   uint32_t par_m = 0, par_e = 0;
 
@@ -130,6 +140,16 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
     mbar_wait(c.bar_m, par_m);
     par_m ^= 1;
     tc_fence_after();
+    // row -> group indicator for the aggregation MMA: B[slot][row] = 1 (K-major image, two chunks of 64 rows)
+    if (HALF == 0) {
+      if (ind_prev != 0xFFFFFFFFu) *reinterpret_cast<uint16_t*>(IND + ind_prev) = 0;
+      if (r.valid) {
+        ind_prev = (uint32_t)(row >> 6) * 8192u + (uint32_t)r.gi * 128u + (((uint32_t)((row & 63) >> 3) ^ ((uint32_t)r.gi & 7u)) << 4) + ((uint32_t)(row & 7) << 1);
+        *reinterpret_cast<uint16_t*>(IND + ind_prev) = 0x3C00;      // fp16 1.0
+      } else {
+        ind_prev = 0xFFFFFFFFu;
+      }
+    }
     if (lt == 0 && tile + 2 < c.tile1) {               // the e chunk is consumed: prefetch this group's next tile
       mbar_expect_tx(c.bar_e, CHUNK_BYTES_A);
       bulk_g2s(A0 + CHUNK_BYTES_A, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 2) * CHUNK_BYTES_A, CHUNK_BYTES_A, c.bar_e);
@@ -234,23 +254,24 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
     float alpha[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) alpha[h] = r.valid ? LG[row * 17 + 8 * HALF + h] * GI[r.gi * 16 + 8 * HALF + h] : 0.f;
-    // groups whose first row lies in this warp's 32 rows are summed by this warp
-    const uint32_t starts = __ballot_sync(0xffffffffu, r.valid && row == r.gs);
+    named_bar_sync(1 + c.grp, AT_GROUP);                 // the logits buffer becomes the message image of half 1
 
-    // ---- messages and per-group sums, 16 value columns (= one head) at a time
+    // ---- messages -> fp16 image; group sums on the tensor core:  D^T[col][slot] = sum_row msg[row][col] * ind[row][slot]
+    // (A = message image, MN-major: M = 128 value columns of this pass, K = 128 rows; B = indicator, N = 64 slots).
+    // Two passes of 64 columns per half; D^T(p) lands in TMEM columns [64p, 64p+64), whose g1 values are consumed by then.
     mbar_wait(c.bar_m, par_m);
     par_m ^= 1;
     tc_fence_after();
-    {
-      float* srow = S + row * S_ROW;
-      const int rs = lane & 7, c4 = lane >> 3;        // row-sum pass: lane = (row subset, 4-column piece)
 #pragma unroll 1
-      for (int ch = 0; ch < 8; ++ch) {
+    for (int p = 0; p < 2; ++p) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int ch = 4 * p + cc;                      // value head of this half = 16 columns
         H16 vn;
         if (ch < 7) { vn.u[0] = __ldg(vb + (size_t)(2 * ch + 2) * a.ldq); vn.u[1] = __ldg(vb + (size_t)(2 * ch + 3) * a.ldq); }
         float acc[16];
         tmem_ld16(tmem_addr(tm, 128 * HALF + 16 * ch), acc);
-        const float al = alpha[ch];
+        const float al = p == 0 ? alpha[cc] : alpha[4 + cc];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           float vf[8];
@@ -258,33 +279,30 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[8 * i + e] = (vf[e] * al) * tanh_fast(acc[8 * i + e]);
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          *reinterpret_cast<float4*>(srow + 4 * k) = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+        st_rowh<16>(MI, row, 0, 2 * cc, acc);
         if (ch < 7) vc = vn;
-        named_bar_sync(team_bar, 128);
-        uint32_t m = starts;
-        while (m) {
-          const int r0 = __ffs(m) - 1;
-          m &= m - 1;
-          const int gl = __shfl_sync(0xffffffffu, r.gl, r0);
-          const int node = __shfl_sync(0xffffffffu, r.g, r0);
-          const float* sp = S + (rq * 32 + r0 + rs) * S_ROW + 4 * c4;
-          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int k = rs; k < gl; k += 8, sp += 8 * S_ROW) {
-            const float4 v = *reinterpret_cast<const float4*>(sp);
-            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-          }
+      }
+      fence_async_smem();
+      at_group_sync(c.grp);
+      if (lt == 0) {
+        const uint32_t idesc = umma_idesc_f16_amn(64);
+        const uint32_t sa = smem_u32(A0), lbo = (uint32_t)G_MIB, sb = smem_u32(IND);
 #pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
-            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
-            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
-            sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
-          }
-          if (rs == 0) *reinterpret_cast<float4*>(a.hnode + (size_t)node * D_ + 128 * HALF + 16 * ch + 4 * c4) = sum;
-        }
-        named_bar_sync(team_bar, 128);
+        for (int k = 0; k < 8; ++k)                     // 16 rows per step
+          umma_f16(tm + 64 * p, umma_desc_sw128_mn(sa + k * 2048, lbo), umma_desc_sw128(sb + (k >> 2) * 8192 + (k & 3) * 32), idesc, k ? 1u : 0u);
+        umma_commit(c.bar_m);
+      }
+      mbar_wait(c.bar_m, par_m);
+      par_m ^= 1;
+      tc_fence_after();
+      // D^T lanes = value columns (lanes 0..63: half 0, 64..127: half 1); this warp drains slots [32 HALF, 32 HALF + 32)
+      if (32 * HALF < ng) {
+        float dsum[32];
+        tmem_ld32(tmem_addr(tm, 64 * p + 32 * HALF), dsum);
+        float* dst = a.hnode + 128 * (rq >> 1) + 64 * p + 32 * (rq & 1) + lane;
+#pragma unroll
+        for (int sl = 0; sl < 32; ++sl)
+          if (32 * HALF + sl < ng) dst[(size_t)gt_node[32 * HALF + sl] * D_] = dsum[sl];
       }
     }
     tc_fence_before();                                       // g1 reads are ordered before the next tile's MMA1 by its group_sync
@@ -311,6 +329,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(const __grid_constant__ 
     bulk_g2s(smem + AT_W1, a.w1_img, 32768, &bars[0]);
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
+  for (int i = lt; i < 16384 / 16; i += AT_GROUP)       // indicator images start empty
+    reinterpret_cast<uint4*>(smem + AT_GRP + grp * G_BYTES + G_IND)[i] = make_uint4(0u, 0u, 0u, 0u);
   sync_tc();
   const bool uni = a.nonuni != nullptr && *a.nonuni == 0;
 

@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 TILE = 128
+MAX_GROUPS = 64          # groups per tile (the attention kernel's group-sum MMA has 64 output slots)
 
 
 class Plan:
@@ -55,7 +56,7 @@ class Plan:
                 continue
             s = int(mol_start[b])
             for v in range(s, s + int(n[b])):
-                if fill + gl > TILE:
+                if fill + gl > TILE or ng == MAX_GROUPS:
                     ngroups.append(ng)
                     tile, fill, ng = tile + 1, 0, 0
                 g_tile[v], g_start[v], g_idx[v] = tile, fill, ng
