@@ -87,6 +87,7 @@ typedef struct jodo_plan {
   const int* row_j;                      /* [n_tiles*128] the partner atom */
   const uint32_t* row_meta;              /* group start row (8b) | group length (8b) << 8 | group index in tile (8b) << 16 */
   const int* tile_ngroups;               /* [n_tiles] */
+  const int* row_mol;                    /* [n_tiles*128] molecule of the row's group atom (0 on padding rows) */
 } jodo_plan;
 
 /* Edge state between kernels (per tile of 128 rows):

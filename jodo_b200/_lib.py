@@ -93,7 +93,7 @@ _Z = ctypes.c_size_t
 
 class PlanStruct(ctypes.Structure):
     _fields_ = [('B', _I), ('Nn', _I), ('n_tiles', _I), ('N', _I), ('node_mol', _P), ('node_dense', _P),
-                ('mol_start', _P), ('row_g', _P), ('row_j', _P), ('row_meta', _P), ('tile_ngroups', _P)]
+                ('mol_start', _P), ('row_g', _P), ('row_j', _P), ('row_meta', _P), ('tile_ngroups', _P), ('row_mol', _P)]
 
 
 class EdgeEmbedArgs(ctypes.Structure):
@@ -155,7 +155,8 @@ def dp(t):
 
 def plan_struct(plan):
     return PlanStruct(plan.B, plan.Nn, plan.n_tiles, plan.N, dp(plan.node_mol), dp(plan.node_dense),
-                      dp(plan.mol_start), dp(plan.row_g), dp(plan.row_j), dp(plan.row_meta), dp(plan.tile_ngroups))
+                      dp(plan.mol_start), dp(plan.row_g), dp(plan.row_j), dp(plan.row_meta), dp(plan.tile_ngroups),
+                      dp(plan.row_mol))
 
 
 def call(name, *args):

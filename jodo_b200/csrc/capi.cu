@@ -103,7 +103,7 @@ int jodo_sym_edges(const float* tmp, float* out, int B, int N, int ch, void* str
 
 static const char* check_plan(const jodo_plan& p) {
   if (p.B <= 0 || p.Nn <= 0 || p.n_tiles <= 0 || p.N <= 0) return "plan: empty";
-  if (!p.node_mol || !p.node_dense || !p.mol_start || !p.row_g || !p.row_j || !p.row_meta || !p.tile_ngroups)
+  if (!p.node_mol || !p.node_dense || !p.mol_start || !p.row_g || !p.row_j || !p.row_meta || !p.tile_ngroups || !p.row_mol)
     return "plan: null pointer";
   return nullptr;
 }

@@ -27,7 +27,7 @@ __device__ __forceinline__ RowInfo load_row(const Plan& p, int tile, int t) {
   r.j = r.valid ? p.row_j[R] : 0;
   const uint32_t m = p.row_meta[R];
   r.gs = m & 255u; r.gl = (m >> 8) & 255u; r.gi = (m >> 16) & 255u;
-  r.mol = p.node_mol[r.g];
+  r.mol = p.row_mol[R];
   return r;
 }
 

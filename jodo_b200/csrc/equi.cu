@@ -6,7 +6,8 @@
 //   pos[row] += sum_col (pos[row] - pos[col]) / max(|.|, 1e-8) * coord_scale * inv.
 // The sum runs over the partners of `row`, so here the group atom g is ROW r and the partner j is COL c
 // (same stored rows as the attention pass, roles swapped; edge features are symmetric).
-// input_lin is hoisted: W[:, :D] h[g] + b and W[:, D:2D] h[j] come from the per-atom piece-major fp16 buffer AB, only the
+// input_lin is hoisted: W[:, :D] h[g] + b and W[:, D:2D] h[j] come from the per-atom piece-major fp16 buffer AB (pre-added
+// as half2 under the input_lin MMA), only the
 // [e | dist] part (K = 128) runs per edge.
 //
 // fp16 operand images (same mantissa as tf32).  coord_mlp.0 (256x256, 128 KB, pre-scaled by 1/2 for the
@@ -60,7 +61,7 @@ __constant__ float c_eqmod[528];
 
 // distance features, columns [16 CQ, 16 CQ + 16) of the GBF chunk; constants are kernel-parameter operands
 template <int CQ>
-__device__ __forceinline__ void eq_gbf(const EquiArgs& a, float d, float scale, float shift, uint8_t* U, int row) {
+__device__ __forceinline__ void eq_gbf(const EquiArgs& a, float d, float scale, float shift, uint4 (&out)[2]) {
   const float x = fmaf(d, scale, d) + shift;
   float df[16];
 #pragma unroll
@@ -73,7 +74,11 @@ __device__ __forceinline__ void eq_gbf(const EquiArgs& a, float d, float scale, 
       df[i] = ex2_fast(-(w * w)) * a.gbf4[4 * col + 2];
     }
   }
-  st_rowh<16>(U, row, 1, 2 * CQ, df);
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    out[p].x = pack_h2(df[8 * p], df[8 * p + 1]); out[p].y = pack_h2(df[8 * p + 2], df[8 * p + 3]);
+    out[p].z = pack_h2(df[8 * p + 4], df[8 * p + 5]); out[p].w = pack_h2(df[8 * p + 6], df[8 * p + 7]);
+  }
 }
 
 // LN + modulate of hidden units [64 CQ, 64 CQ + 64) -> X chunk CQ
@@ -180,40 +185,35 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   float4* pos_out = reinterpret_cast<float4*>(a.pos_out);
   const int cb = 64 * cq;                         // first hidden column of this thread
 
-  // row metadata of a tile is fetched one tile ahead
-  RowInfo rn = load_row(a.p, min(tile0, a.p.n_tiles - 1), row);
-  int ngn = a.p.tile_ngroups[min(tile0, a.p.n_tiles - 1)];
-  uint8_t exn = a.extra[(size_t)min(tile0, a.p.n_tiles - 1) * TILE_ROWS + row];
+  // Software pipeline across tiles: the row metadata, positions and distance features of tile i+1 are produced while
+  // the coord_mlp.0 MMA of tile i runs; the hoisted per-atom parts of tile i are gathered and pre-added (half2) while
+  // its input_lin MMA runs.
+  const int tfirst = min(tile0, a.p.n_tiles - 1);
+  RowInfo r = load_row(a.p, tfirst, row);
+  int ng = a.p.tile_ngroups[tfirst];
+  uint8_t ex = a.extra[(size_t)tfirst * TILE_ROWS + row];
+  float4 pg = pos[r.g], pj = pos[r.j];
+  uint4 dfh[2];
+  {
+    const float* tr0 = a.tab + (size_t)(uni ? 0 : r.mol) * a.ld_tab + a.tab_off;
+    const float gsc = uni ? c_eqmod[512] : tr0[tab_gbf(D_)], gsh = uni ? c_eqmod[513] : tr0[tab_gbf(D_) + 1];
+    EQ_DISPATCH(eq_gbf, a, sq_dist(pg, pj), gsc, gsh, dfh);
+  }
 #ifdef JODO_PHASE_TIMING
   long long ph_last = clock64();
 #endif
   for (int tile = tile0; tile < tile1; ++tile) {
-    const RowInfo r = rn;
-    const int ng = ngn;
-    const uint8_t ex = exn;
     const float* tr = a.tab + (size_t)(uni ? 0 : r.mol) * a.ld_tab + a.tab_off;
-    const float4 pg = pos[r.g], pj = pos[r.j];
-    // hoisted input_lin parts (fp16 rows, bias folded into the g part): first 32 columns in flight before the MMA wait
-    H32 ua = ldg_pm32(a.AB, a.ldab, r.g, 8 * cq), ub = ldg_pm32(a.AB, a.ldab, r.j, 32 + 8 * cq);
-    {
-      const float gsc = uni ? c_eqmod[512] : tr[tab_gbf(D_)], gsh = uni ? c_eqmod[513] : tr[tab_gbf(D_) + 1];
-      const float d = sq_dist(pg, pj);
-#ifdef JODO_PHASE_TIMING
-      if (d == 123456.f) printf("x");
-      PHASE_MARK(9);
-#endif
-      EQ_DISPATCH(eq_gbf, a, d, gsc, gsh, U, row);
-      PHASE_MARK(10);
-    }
-    {
-      const int nt_ = min(tile + 1, tile1 - 1);
-      rn = load_row(a.p, nt_, row);
-      ngn = a.p.tile_ngroups[nt_];
-      exn = a.extra[(size_t)nt_ * TILE_ROWS + row];
-    }
-    PHASE_MARK(11);
+    // distance features of this tile (computed one tile ahead) -> U chunk 1
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+      *reinterpret_cast<uint4*>(U + img_piece(row, 1, 2 * cq + p, CHUNK_BYTES_A)) = dfh[p];
+    // row metadata of the next tile
+    const int nt_ = min(tile + 1, tile1 - 1);
+    const RowInfo rn = load_row(a.p, nt_, row);
+    const int ngn = a.p.tile_ngroups[nt_];
+    const uint8_t exn = a.extra[(size_t)nt_ * TILE_ROWS + row];
     fence_async_smem();
-    PHASE_MARK(12);
     sync_tc();
     PHASE_MARK(0);
     if (t == 0) {
@@ -225,6 +225,26 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       mma_tile_h(tm_x, smem_u32(U), smem_u32(X), 256, 2, false);       // input_lin edge part
       umma_commit(&bars[3]);
     }
+    // under the MMA: hoisted input_lin parts (piece-major fp16 rows, bias folded into the g part), pre-added as half2
+    uint4 ab[8];
+    {
+      const uint4* pa = static_cast<const uint4*>(a.AB) + (size_t)(8 * cq) * a.ldab + r.g;
+      const uint4* pb = static_cast<const uint4*>(a.AB) + (size_t)(32 + 8 * cq) * a.ldab + r.j;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 ua[4], ub[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ua[i] = __ldg(pa + (size_t)(4 * h + i) * a.ldab); ub[i] = __ldg(pb + (size_t)(4 * h + i) * a.ldab); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half2* x2 = reinterpret_cast<__half2*>(&ua[i]);
+          const __half2* y2 = reinterpret_cast<const __half2*>(&ub[i]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) x2[k] = __hadd2(x2[k], y2[k]);
+          ab[4 * h + i] = ua[i];
+        }
+      }
+    }
     mbar_wait(&bars[3], par);
     PHASE_MARK(3);
     tc_fence_after();
@@ -234,34 +254,27 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
     }
     if (cq == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
 
-    // ---- pass 1: x = acc + A[g] + B[j] over this thread's 64 hidden units, kept in TMEM; row statistics
+    // ---- pass 1: x = acc + (A[g] + B[j]) over this thread's 64 hidden units, kept in TMEM; row statistics
     float mean, rstd;
     {
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        H32 na, nb;
-        if (h == 0) { na = ldg_pm32(a.AB, a.ldab, r.g, 8 * cq + 4); nb = ldg_pm32(a.AB, a.ldab, r.j, 32 + 8 * cq + 4); }
+      for (int q = 0; q < 4; ++q) {
+        float x[16];
+        tmem_ld16(tmem_addr(tm_x, cb + 16 * q), x);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float x[16];
-          tmem_ld16(tmem_addr(tm_x, cb + 32 * h + 16 * q), x);
+        for (int i = 0; i < 2; ++i) {
+          float uf[8];
+          unpack8(ab[2 * q + i], uf);
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            float uf[8], vf[8];
-            unpack8(ua.u[2 * q + i], uf);
-            unpack8(ub.u[2 * q + i], vf);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float v = x[8 * i + e] + (uf[e] + vf[e]);
-              x[8 * i + e] = v;
-              s1 += v;
-              s2 = fmaf(v, v, s2);
-            }
+          for (int e = 0; e < 8; ++e) {
+            const float v = x[8 * i + e] + uf[e];
+            x[8 * i + e] = v;
+            s1 += v;
+            s2 = fmaf(v, v, s2);
           }
-          tmem_st16(tmem_addr(tm_x, cb + 32 * h + 16 * q), x);
         }
-        if (h == 0) { ua = na; ub = nb; }
+        tmem_st16(tmem_addr(tm_x, cb + 16 * q), x);
       }
       tmem_wait_st();
       LNS[row * 4 + cq] = make_float2(s1, s2);
@@ -272,6 +285,8 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       mean = (o01.x + o01.z + o23.x + o23.z) * (1.0f / 256.0f);
       rstd = rsqrtf(fmaxf((o01.y + o01.w + o23.y + o23.w) * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-6f);
     }
+    // positions of the next tile's rows: in flight during pass 2
+    const float4 pgn = pos[rn.g], pjn = pos[rn.j];
     // ---- pass 2: LN + modulate -> X chunk cq (fp16, K = 256); the input_lin image there is no longer needed.
     // Padding rows carry finite garbage; they only feed their own (discarded) output rows.
     if (uni) { EQ_DISPATCH(eq_pass2_uni, tm_x, X, row, mean, rstd, tr); }
@@ -284,6 +299,12 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       tc_fence_after();
       mma_tile_h(tm_c, smem_u32(X), smem_u32(smem + EQ_WC0), 256, 4, false);     // coord_mlp.0 (pre-scaled by 1/2)
       umma_commit(&bars[4]);
+    }
+    // under the MMA: distance features of the next tile
+    {
+      const float* trn = a.tab + (size_t)(uni ? 0 : rn.mol) * a.ld_tab + a.tab_off;
+      const float gsc = uni ? c_eqmod[512] : trn[tab_gbf(D_)], gsh = uni ? c_eqmod[513] : trn[tab_gbf(D_) + 1];
+      EQ_DISPATCH(eq_gbf, a, sq_dist(pgn, pjn), gsc, gsh, dfh);
     }
     mbar_wait(&bars[4], par);
     PHASE_MARK(6);
@@ -319,6 +340,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
     sync_tc();
     PHASE_MARK(8);
     par ^= 1;
+    r = rn; ng = ngn; ex = exn; pg = pgn; pj = pjn;
   }
   if (tile0 >= tile1 && t == 0) mbar_wait(&bars[0], 0);   // never leave with bulk copies in flight
   sync_tc();

@@ -68,6 +68,7 @@ class Plan:
         row_g = np.full(R, -1, dtype=np.int32)
         row_j = np.full(R, -1, dtype=np.int32)
         row_meta = np.zeros(R, dtype=np.uint32)
+        row_mol = np.zeros(R, dtype=np.int32)
         has = gl_node > 0
         v_ids = np.nonzero(has)[0]
         gl_v = gl_node[v_ids]
@@ -85,6 +86,7 @@ class Plan:
             row_g[rows] = v
             row_j[rows] = j
             row_meta[rows] = (g_start[v] | (gl_node[v] << 8) | (g_idx[v] << 16)).astype(np.uint32)
+            row_mol[rows] = node_mol[v]
         self.utilization = tot / float(R)
         dev = device if device is not None else node_mask.device
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -95,6 +97,7 @@ class Plan:
         self.row_j = t(row_j)
         self.row_meta = t(row_meta.view(np.int32))
         self.tile_ngroups = t(np.asarray(ngroups, dtype=np.int32))
+        self.row_mol = t(row_mol)
         self.device = dev
 
     # ---- helpers used by tests (pure index bookkeeping) -------------------------------------------
