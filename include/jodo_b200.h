@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 3
+#define JODO_ABI_VERSION 4
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -48,7 +48,10 @@ int jodo_abi_version(void);
  * operands the edge kernels gather (q | k | v, the hoisted input_lin parts, the hoisted node2edge_lin part). */
 int jodo_rowlinear(const float* A, int lda, int M, int K, const void* Wimg, const float* bias, void* C, int ldc,
                    int N, int NT, int act_in, int epi, int act_out, const float* aux, int ld_aux, const float* gate,
-                   int ld_gate, const int* row_mol, int out_f16, void* stream);
+                   int ld_gate, const int* row_mol, int out_f16, const int* only_row0_if_zero, void* stream);
+/* only_row0_if_zero (may be null): device flag of jodo_uniform_flag; when it reads 0 only the first 128-row tile is
+ * computed -- used for the per-molecule AdaLN table, whose rows are all equal to row 0 under uniform conditioning
+ * (every consumer then reads row 0). */
 
 
 /* Persistent, TMA-fed variant of jodo_rowlinear for the per-atom GEMMs of a DGT block: the activation operand is
@@ -65,6 +68,7 @@ typedef struct jodo_imglinear_args {
   const float* aux; int ld_aux;           /* GATED_RES: residual rows */
   const float* gate; int ld_gate;         /* GATED_RES: gate[row_mol[row], col] */
   const int* row_mol;
+  const int* nonuni;                      /* device flag of jodo_uniform_flag or null: 0 = read gate row 0 for every row */
   float* C32; int ldc32;                  /* fp32 row-major output or null */
   void* C16; int ldc16;                   /* fp16 row-major output or null (ld in elements) */
   int c16_piece_major;                    /* != 0: C16 is [N/8][ldc16 rows][8] -- 16-byte column pieces with the rows of one
@@ -108,6 +112,7 @@ typedef struct jodo_edge_embed_args {                    /* model-level edge emb
   float* e32; void* e16;                  /* out: edge state */
   void* eh; size_t eh_tile_bytes;         /* out: chunk 0 of the edge-hidden image */
   uint8_t* extra;                         /* out: [R] bit0 = 2-D adjacency head, bit1 = spatial adjacency head */
+  const int* nonuni;                      /* device flag of jodo_uniform_flag or null: 0 = read table row 0 */
 } jodo_edge_embed_args;
 
 typedef struct jodo_attn_args {                         /* TransMixLayer on edge tiles (reference models/layers.py:131-186) */
@@ -184,7 +189,7 @@ int jodo_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const f
  * node2edge_lin consumes, reference models/mol_gnn.py:304-305).  Rows beyond Nn of the last tile are zeroed. */
 int jodo_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
                     int off_shift, int off_scale, const jodo_plan* p, float* out32, int ldo, void* out_img, void* y_img,
-                    void* stream);
+                    const int* nonuni, void* stream);
 /* nonuni[0] = 1 if any row of rows[B, T] differs (bitwise) from row 0, else 0.  rows = the conditioning embedding
  * temb (noise level [+ context], reference models/mol_gnn.py:534, 728-734): the samplers broadcast one noise level
  * over the batch (sampling.py:549), in which case every per-molecule AdaLN row is the same row. */

@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 3:
+        if _lib.jodo_abi_version() != 4:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -72,7 +72,7 @@ def stream_ptr():
 
 
 def rowlinear(A, K, Wimg, bias, C, N, NT, act_in=ACT_NONE, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None,
-              row_mol=None, M=None, stream=None, tag=None, out_f16=False):
+              row_mol=None, M=None, stream=None, tag=None, out_f16=False, only_row0_if_zero=None):
     """C[:, :N] = epi(act_in(A[:, :K]) W^T + bias); A, C, aux, gate are 2-D row-major views (stride(1)==1)."""
     M = A.shape[0] if M is None else M
     f = lib().jodo_rowlinear
@@ -80,7 +80,8 @@ def rowlinear(A, K, Wimg, bias, C, N, NT, act_in=ACT_NONE, epi=EPI_STORE, act_ou
     rc = _account(tag or 'jodo_rowlinear', lambda: f(
         ptr(A), c_int(A.stride(0)), c_int(M), c_int(K), ptr(Wimg), ptr(bias), ptr(C), c_int(C.stride(0)), c_int(N),
         c_int(NT), c_int(act_in), c_int(epi), c_int(act_out), ptr(aux), c_int(0 if aux is None else aux.stride(0)),
-        ptr(gate), c_int(0 if gate is None else gate.stride(0)), ptr(row_mol), c_int(1 if out_f16 else 0), st))
+        ptr(gate), c_int(0 if gate is None else gate.stride(0)), ptr(row_mol), c_int(1 if out_f16 else 0),
+        ctypes.c_void_p(only_row0_if_zero), st))
     check(rc, 'jodo_rowlinear')
 
 
@@ -99,7 +100,8 @@ class PlanStruct(ctypes.Structure):
 class EdgeEmbedArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('edge_x', _P), ('cond_edge_x', _P), ('cond_x', _P), ('ch', _I), ('inn', _I),
                 ('edge_th', _F), ('spatial_cut', _F), ('dist_flag', _P), ('tab', _P), ('ld_tab', _I), ('gbf', _P),
-                ('w_img', _P), ('bias', _P), ('e32', _P), ('e16', _P), ('eh', _P), ('eh_tile_bytes', _Z), ('extra', _P)]
+                ('w_img', _P), ('bias', _P), ('e32', _P), ('e16', _P), ('eh', _P), ('eh_tile_bytes', _Z), ('extra', _P),
+                ('nonuni', _P)]
 
 
 class AttnArgs(ctypes.Structure):
@@ -129,18 +131,18 @@ class EdgeHeadArgs(ctypes.Structure):
 
 class ImgLinearArgs(ctypes.Structure):
     _fields_ = [('Aimg', _P), ('M', _I), ('K', _I), ('Wimg', _P), ('bias', _P), ('N', _I), ('NT', _I), ('epi', _I),
-                ('act_out', _I), ('aux', _P), ('ld_aux', _I), ('gate', _P), ('ld_gate', _I), ('row_mol', _P),
+                ('act_out', _I), ('aux', _P), ('ld_aux', _I), ('gate', _P), ('ld_gate', _I), ('row_mol', _P), ('nonuni', _P),
                 ('C32', _P), ('ldc32', _I), ('C16', _P), ('ldc16', _I), ('c16_piece_major', _I), ('Cimg', _P)]
 
 
 def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None, row_mol=None,
-              C32=None, C16=None, Cimg=None, stream=None, tag=None):
+              C32=None, C16=None, Cimg=None, stream=None, tag=None, nonuni=0):
     """Persistent TMA-fed GEMM on an fp16 activation image (include/jodo_b200.h: jodo_imglinear).
     C32 / C16 are 2-D row-major views (stride(1) == 1) -- or C16 a contiguous 3-D [N/8, rows, 8] tensor for the
     piece-major layout the edge kernels gather from; Cimg a flat fp16 image buffer."""
     pm = C16 is not None and C16.dim() == 3          # piece-major fp16 output: tensor [N/8, rows, 8]
     a = ImgLinearArgs(dp(Aimg), M, K, dp(Wimg), dp(bias), N, NT, epi, act_out, dp(aux),
-                      0 if aux is None else aux.stride(0), dp(gate), 0 if gate is None else gate.stride(0), dp(row_mol),
+                      0 if aux is None else aux.stride(0), dp(gate), 0 if gate is None else gate.stride(0), dp(row_mol), nonuni,
                       dp(C32), 0 if C32 is None else C32.stride(0), dp(C16),
                       0 if C16 is None else (C16.shape[1] if pm else C16.stride(0)), 1 if pm else 0, dp(Cimg))
     st = stream if stream is not None else stream_ptr()

@@ -24,9 +24,9 @@ int jodo_abi_version(void) { return JODO_ABI_VERSION; }
 
 int jodo_rowlinear(const float* A, int lda, int M, int K, const void* Wimg, const float* bias, void* C, int ldc,
                    int N, int NT, int act_in, int epi, int act_out, const float* aux, int ld_aux, const float* gate,
-                   int ld_gate, const int* row_mol, int out_f16, void* stream) {
+                   int ld_gate, const int* row_mol, int out_f16, const int* only_row0_if_zero, void* stream) {
   jodo::RowLinearArgs a{A, lda, M, K, static_cast<const float*>(Wimg), bias, C, ldc, N, NT, act_in, epi, act_out, aux, ld_aux,
-                        gate, ld_gate, row_mol, out_f16};
+                        gate, ld_gate, row_mol, out_f16, only_row0_if_zero};
   if (const char* m = jodo::check_rowlinear(a)) return fail(m);
   cudaError_t e = jodo::launch_rowlinear(a, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? JODO_OK : cuda_fail(e, "jodo_rowlinear");
@@ -71,12 +71,12 @@ int jodo_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const f
 }
 int jodo_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
                     int off_shift, int off_scale, const jodo_plan* p, float* out32, int ldo, void* out_img, void* y_img,
-                    void* stream) {
+                    const int* nonuni, void* stream) {
   if (!p || !x || !tab || !out_img) return fail("jodo_ln_mod_img: null pointer");
   if ((ldx % 4) || (y && (ldy % 4)) || (out32 && (ldo % 4)) || (ld_tab % 4) || (off_gate % 4) || (off_shift % 4) || (off_scale % 4))
     return fail("jodo_ln_mod_img: strides and offsets must be multiples of 4");
   JODO_LAUNCH(jodo::launch_ln_mod_img(x, ldx, y, ldy, tab, ld_tab, off_gate, off_shift, off_scale, *p, out32, ldo, out_img,
-                                      y_img, S(stream)),
+                                      y_img, nonuni, S(stream)),
               "jodo_ln_mod_img");
 }
 int jodo_imglinear(const jodo_imglinear_args* a, void* stream) {

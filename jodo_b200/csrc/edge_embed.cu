@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(ET, 1) k_edge_embed(EdgeEmbedArgs a) {
   sync_tc();
   const uint32_t tmem = *tmem_slot;
   const int use_gbf = a.cond_x ? *a.dist_flag : 0;
+  const bool uni = a.nonuni != nullptr && *a.nonuni == 0;
   const int N = a.p.N, w = 3 + a.inn, ch = a.ch;
   uint32_t par_m = 0;
   bool w_ready = false;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(ET, 1) k_edge_embed(EdgeEmbedArgs a) {
     }
     float v[64];
     if (use_gbf && r.valid) {
-      const float* tr = a.tab + (size_t)r.mol * a.ld_tab;
+      const float* tr = a.tab + (size_t)(uni ? 0 : r.mol) * a.ld_tab;
       gbf_eval(d0, tr[0], tr[1], gbf, v);
     } else {
 #pragma unroll

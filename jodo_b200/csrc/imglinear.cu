@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
     uint8_t* __restrict__ Cimg = static_cast<uint8_t*>(a.Cimg);
     const int ld_aux = a.ld_aux, ld_gate = a.ld_gate, ldc32 = a.ldc32, ldc16 = a.ldc16, Mrows = a.M, nchunk_out = a.N / 64;
     const bool c16_pm = a.c16_piece_major != 0;
+    const bool gate_row0 = a.nonuni != nullptr && *a.nonuni == 0;       // uniform conditioning: every molecule's gate row is row 0
     uint8_t* stg = stg_base + team * 2 * IL_STG_BUF;
     const int r0 = wt * 4 + rsub;                  // this thread's rows in the row-major pass: r0 + 16 * it
     uint32_t ai = 0, sb = 0;
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
       int mol[8];
       if (epi == EPI_GATED_RES) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) mol[it] = (gr0 + 16 * it) < Mrows ? __ldg(a.row_mol + gr0 + 16 * it) : 0;
+        for (int it = 0; it < 8; ++it) mol[it] = (!gate_row0 && (gr0 + 16 * it) < Mrows) ? __ldg(a.row_mol + gr0 + 16 * it) : 0;
       }
       mbar_wait(&bar_tfull[ab], aph);
       tc_fence_after();

@@ -20,6 +20,7 @@ struct RowLinearArgs {
   const float* gate; int ld_gate;               // EPI_GATED_RES: gate[row_mol[row], col]
   const int* row_mol;
   int out_f16;                                  // EPI_STORE only: write fp16 (saturating) instead of fp32
+  const int* only_row0_if_zero;                 // device flag: 0 = compute the first row tile only
 };
 const char* check_rowlinear(const RowLinearArgs& a);
 cudaError_t launch_rowlinear(const RowLinearArgs& a, cudaStream_t stream);
@@ -63,7 +64,7 @@ cudaError_t launch_ln_mod(int D, const float* x, int ldx, const float* y, int ld
                           cudaStream_t st);
 cudaError_t launch_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
                               int off_shift, int off_scale, const Plan& p, float* out32, int ldo, void* out_img,
-                              void* y_img, cudaStream_t st);
+                              void* y_img, const int* nonuni, cudaStream_t st);
 cudaError_t launch_uniform_flag(const float* rows, int B, int T, int* nonuni, cudaStream_t st);
 cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st);
 cudaError_t launch_nan_flag(const float* pos, int Nn, int* flag, cudaStream_t st);

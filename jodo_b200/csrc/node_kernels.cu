@@ -106,7 +106,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 __global__ void k_ln_mod_img(const float* __restrict__ x, int ldx, const float* __restrict__ y, int ldy,
                              const float* __restrict__ tab, int ld_tab, int off_gate, int off_shift, int off_scale,
                              const int* __restrict__ node_mol, int Nn, float* __restrict__ out32, int ldo,
-                             uint8_t* __restrict__ out_img, uint8_t* __restrict__ y_img) {
+                             uint8_t* __restrict__ out_img, uint8_t* __restrict__ y_img, const int* __restrict__ nonuni) {
   constexpr int D = 256;
   const int v = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);     // rows up to the end of the last tile
   const int lane = threadIdx.x & 31;
@@ -117,7 +117,7 @@ __global__ void k_ln_mod_img(const float* __restrict__ x, int ldx, const float* 
     if (y_img) *reinterpret_cast<uint4*>(y_img + ioff) = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
-  const float* t = tab + (size_t)node_mol[v] * ld_tab;
+  const float* t = tab + (size_t)((nonuni && *nonuni == 0) ? 0 : node_mol[v]) * ld_tab;     // uniform conditioning: row 0
   const int c0 = 8 * lane;
   float a[8];
   {
@@ -268,10 +268,10 @@ cudaError_t launch_ln_mod(int D, const float* x, int ldx, const float* y, int ld
 }
 cudaError_t launch_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
                               int off_shift, int off_scale, const Plan& p, float* out32, int ldo, void* out_img,
-                              void* y_img, cudaStream_t st) {
+                              void* y_img, const int* nonuni, cudaStream_t st) {
   const int rows = (p.Nn + 127) / 128 * 128;
   k_ln_mod_img<<<rows / 8, 256, 0, st>>>(x, ldx, y, ldy, tab, ld_tab, off_gate, off_shift, off_scale, p.node_mol, p.Nn,
-                                         out32, ldo, static_cast<uint8_t*>(out_img), static_cast<uint8_t*>(y_img));
+                                         out32, ldo, static_cast<uint8_t*>(out_img), static_cast<uint8_t*>(y_img), nonuni);
   return LAUNCH_OK();
 }
 cudaError_t launch_uniform_flag(const float* rows, int B, int T, int* nonuni, cudaStream_t st) {

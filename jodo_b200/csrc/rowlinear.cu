@@ -35,6 +35,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 __global__ void __launch_bounds__(RL_THREADS, 2) k_rowlinear(RowLinearArgs a) {
+  if (a.only_row0_if_zero && blockIdx.x > 0 && *a.only_row0_if_zero == 0) return;   // uniform conditioning: row 0 is every row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_buf = smem;                                   // RL_STAGES x 16 KB

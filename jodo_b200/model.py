@@ -164,7 +164,8 @@ class _DGTBase(nn.Module):
             lin('time3', ws.t1, ws.temb)
         # flags[2] = 1 unless every molecule carries the same conditioning row (the samplers broadcast one noise level)
         _lib.call('jodo_uniform_flag', _lib.ptr(ws.temb), _c(B), _c(T), ctypes.c_void_p(ws.flags.data_ptr() + 8), st)
-        lin('tab', ws.temb, ws.tab, act_in=_lib.ACT_SILU)
+        nonuni = ws.flags.data_ptr() + 8
+        lin('tab', ws.temb, ws.tab, act_in=_lib.ACT_SILU, only_row0_if_zero=nonuni)
         # ---- per atom: packed inputs, node embedding (slice 0 of the concatenated atom hiddens)
         _lib.call('jodo_gather_nodes', _lib.ptr(xh), _lib.ptr(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin),
                   _lib.ptr(ws.xin), _lib.ptr(ws.pos[0]), st)
@@ -173,7 +174,7 @@ class _DGTBase(nn.Module):
         ea = _lib.EdgeEmbedArgs(ps, _lib.dp(edge_x), _lib.dp(cond_edge_x), _lib.dp(cond_x), d.ch, d.inn, self.edge_th,
                                 self.spatial_cut_off, _lib.dp(ws.flags), _lib.dp(ws.tab), ld_tab, pk.ptr('gbf'),
                                 pk.ptr('edge_emb.img'), pk.ptr('edge_emb.b'), _lib.dp(ws.e), _lib.dp(ws.e16),
-                                _lib.dp(ws.eh), ws.eh_tile_bytes, _lib.dp(ws.extra))
+                                _lib.dp(ws.eh), ws.eh_tile_bytes, _lib.dp(ws.extra), ws.flags.data_ptr() + 8)
         _lib.call('jodo_edge_embed', ctypes.byref(ea), st)
 
         h = ws.ah[:, :D]
@@ -185,7 +186,8 @@ class _DGTBase(nn.Module):
             hout = ws.h[l & 1]
             # norm1_node + modulate -> fp16 operand image, q/k/v
             _lib.call('jodo_ln_mod_img', _lib.ptr(h), _c(h.stride(0)), None, _c(0), _lib.ptr(ws.tab), _c(ld_tab),
-                      _c(0), _c(off), _c(off + D), ctypes.byref(ps), None, _c(0), _lib.ptr(ws.hn_img), None, st)
+                      _c(0), _c(off), _c(off + D), ctypes.byref(ps), None, _c(0), _lib.ptr(ws.hn_img), None,
+                      ctypes.c_void_p(nonuni), st)
             ilin(p + 'qkv', ws.hn_img, C16=ws.qkv)
             aa = _lib.AttnArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(ws.qkv), plan.Nn, _lib.dp(ws.tab), ld_tab,
                                off, _lib.dp(ws.extra), pk.ptr(p + 'emb.img'), pk.ptr(p + 'e0.img'), pk.ptr(p + 'e1.img'),
@@ -194,11 +196,11 @@ class _DGTBase(nn.Module):
             # node path: gated residual + norm2 (+ image of hnode), hoisted node2edge, FFN, hoisted input_lin parts, node_l
             _lib.call('jodo_ln_mod_img', _lib.ptr(h), _c(h.stride(0)), _lib.ptr(ws.hnode), _c(D), _lib.ptr(ws.tab),
                       _c(ld_tab), _c(off + 2 * D), _c(off + 3 * D), _c(off + 4 * D), ctypes.byref(ps), _lib.ptr(ws.h2),
-                      _c(D), _lib.ptr(ws.h2_img), _lib.ptr(ws.hnode_img), st)
+                      _c(D), _lib.ptr(ws.h2_img), _lib.ptr(ws.hnode_img), ctypes.c_void_p(nonuni), st)
             ilin(p + 'n2e', ws.hnode_img, C16=ws.pbuf)
             ilin(p + 'ff1', ws.h2_img, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.ff_img)
             ilin(p + 'ff2', ws.ff_img, epi=_lib.EPI_GATED_RES, aux=ws.h2, gate=ws.tab[:, off + 5 * D:],
-                 row_mol=plan.node_mol, C32=hout, Cimg=ws.hout_img)
+                 row_mol=plan.node_mol, C32=hout, Cimg=ws.hout_img, nonuni=nonuni)
             ilin(p + 'ab', ws.hout_img, C16=ws.ab)
             ilin(p + 'node_l', ws.hout_img, C32=ws.ah[:, D + l * meta['cnp']:])
             # edge path

@@ -119,7 +119,7 @@ def test_ln_mod_img_matches_torch():
     yimg = torch.full((mt * 128 * D,), 7.0, device='cuda', dtype=torch.float16)
     c = ctypes.c_int
     _lib.call('jodo_ln_mod_img', _lib.ptr(x), c(D), _lib.ptr(y), c(D), _lib.ptr(tab), c(1024), c(0), c(256), c(512),
-              ctypes.byref(ps), _lib.ptr(out32), c(D), _lib.ptr(oimg), _lib.ptr(yimg), _lib.stream_ptr())
+              ctypes.byref(ps), _lib.ptr(out32), c(D), _lib.ptr(oimg), _lib.ptr(yimg), None, _lib.stream_ptr())
     torch.cuda.synchronize()
     t = tab[plan.node_mol.long()]
     z = x + t[:, :256] * y
