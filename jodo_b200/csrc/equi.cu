@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   uint8_t* X = smem + EQ_X;
   uint8_t* U = smem + EQ_U;
   uint8_t* misc = smem + EQ_MISC;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // 0: coord_mlp.0 image, 1: e tile, 2: input_lin image, 3: MMA in, 4: MMA c0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // 0: coord_mlp.0 image, 1: e tile, 2: input_lin image, 3/5: MMA in (N halves), 4/6: MMA c0 (N halves)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 64);
   float2* LNS = reinterpret_cast<float2*>(smem + EQ_LNS);
   float4* DOT = reinterpret_cast<float4*>(smem + EQ_DOT);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   const int tile1 = min(tile0 + per, a.p.n_tiles);
 
   if (t == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
     if (tile0 < tile1) {
       mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
@@ -222,8 +222,17 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       mbar_wait(&bars[2], par);
       PHASE_MARK(2);
       tc_fence_after();
-      mma_tile_h(tm_x, smem_u32(U), smem_u32(X), 256, 2, false);       // input_lin edge part
-      umma_commit(&bars[3]);
+      // input_lin edge part, hidden units [0,128) then [128,256): the column quarters 0,1 start on the first half
+      // while the tensor core works on the second
+      const uint32_t idesc = umma_idesc_f16(128);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16(tm_x + 128 * hf, umma_desc_sw128(smem_u32(U) + (k >> 2) * CHUNK_BYTES_A + (k & 3) * 32),
+                   umma_desc_sw128(smem_u32(X) + (k >> 2) * 32768 + hf * 16384 + (k & 3) * 32), idesc, k ? 1u : 0u);
+        umma_commit(&bars[hf ? 5 : 3]);
+      }
     }
     // under the MMA: hoisted input_lin parts (piece-major fp16 rows, bias folded into the g part), pre-added as half2
     uint4 ab[8];
@@ -245,14 +254,9 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
         }
       }
     }
-    mbar_wait(&bars[3], par);
+    mbar_wait(&bars[cq < 2 ? 3 : 5], par);
     PHASE_MARK(3);
     tc_fence_after();
-    if (t == 0 && tile + 1 < tile1) {            // U chunk 0 is consumed: prefetch the next e tile
-      mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
-      bulk_g2s(U, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 1) * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
-    }
-    if (cq == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
 
     // ---- pass 1: x = acc + (A[g] + B[j]) over this thread's 64 hidden units, kept in TMEM; row statistics
     float mean, rstd;
@@ -277,6 +281,12 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
         tmem_st16(tmem_addr(tm_x, cb + 16 * q), x);
       }
       tmem_wait_st();
+      if (cq < 2) mbar_wait(&bars[5], par);      // the scratch aliases the GBF chunk: the whole input_lin MMA must be done
+      if (t == 0 && tile + 1 < tile1) {          // U chunk 0 is consumed: prefetch the next e tile
+        mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
+        bulk_g2s(U, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 1) * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
+      }
+      if (cq == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
       LNS[row * 4 + cq] = make_float2(s1, s2);
       __syncthreads();
       PHASE_MARK(4);
@@ -297,8 +307,15 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
     if (t == 0) {
       if (tile == tile0) mbar_wait(&bars[0], 0);
       tc_fence_after();
-      mma_tile_h(tm_c, smem_u32(X), smem_u32(smem + EQ_WC0), 256, 4, false);     // coord_mlp.0 (pre-scaled by 1/2)
-      umma_commit(&bars[4]);
+      const uint32_t idesc = umma_idesc_f16(128);                                // coord_mlp.0 (pre-scaled by 1/2), N halves
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          umma_f16(tm_c + 128 * hf, umma_desc_sw128(smem_u32(X) + (k >> 2) * CHUNK_BYTES_A + (k & 3) * 32),
+                   umma_desc_sw128(smem_u32(smem + EQ_WC0) + (k >> 2) * 32768 + hf * 16384 + (k & 3) * 32), idesc, k ? 1u : 0u);
+        umma_commit(&bars[hf ? 6 : 4]);
+      }
     }
     // under the MMA: distance features of the next tile
     {
@@ -306,16 +323,19 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       const float gsc = uni ? c_eqmod[512] : trn[tab_gbf(D_)], gsh = uni ? c_eqmod[513] : trn[tab_gbf(D_) + 1];
       EQ_DISPATCH(eq_gbf, a, sq_dist(pgn, pjn), gsc, gsh, dfh);
     }
-    mbar_wait(&bars[4], par);
+    mbar_wait(&bars[cq < 2 ? 4 : 6], par);
     PHASE_MARK(6);
     tc_fence_after();
-    if (t == 0 && tile + 1 < tile1) {            // X is consumed: fetch the input_lin image for the next tile
-      mbar_expect_tx(&bars[2], 65536);
-      bulk_g2s(X, a.win_img, 65536, &bars[2]);
-    }
 
     // ---- SiLU + coord_mlp.2 partial dots on CUDA cores
     EQ_DISPATCH(eq_silu_dot, a, tm_c, &DOT[row * 4 + cq]);
+    if (t == 0) {                                // X is consumed once both halves are done: fetch the input_lin image for the next tile
+      mbar_wait(&bars[6], par);
+      if (tile + 1 < tile1) {
+        mbar_expect_tx(&bars[2], 65536);
+        bulk_g2s(X, a.win_img, 65536, &bars[2]);
+      }
+    }
     __syncthreads();
     PHASE_MARK(7);
     if (cq == 0) {       // tanh, adjacency-weighted mean, coordinate contribution of this edge
