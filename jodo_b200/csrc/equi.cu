@@ -84,31 +84,17 @@ __device__ __forceinline__ void eq_gbf(const EquiArgs& a, float d, float scale, 
 // LN + modulate of hidden units [64 CQ, 64 CQ + 64) -> X chunk CQ
 template <int CQ, bool UNI>
 __device__ __forceinline__ void eq_pass2_t(uint32_t tm_x, uint8_t* X, int row, float mean, float rstd, const float* tr) {
+  static_assert(UNI, "the general path is eq_pass2_gen");
   const float nmr = -mean * rstd;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     float x[16];
     tmem_ld16(tmem_addr(tm_x, 64 * CQ + 16 * c), x);
-    if (UNI) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int col = 64 * CQ + 16 * c + i;
-        const float n = fmaf(x[i], rstd, nmr);
-        x[i] = fmaf(n, c_eqmod[256 + col], n) + c_eqmod[col];
-      }
-    } else {
-      const float* shift = tr + tab_equi(D_) + 64 * CQ + 16 * c;
-      const float* scale = shift + D_;
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + i));
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + i));
-        const float n0 = fmaf(x[i], rstd, nmr), n1 = fmaf(x[i + 1], rstd, nmr), n2 = fmaf(x[i + 2], rstd, nmr), n3 = fmaf(x[i + 3], rstd, nmr);
-        x[i] = fmaf(n0, sc.x, n0) + sh.x;
-        x[i + 1] = fmaf(n1, sc.y, n1) + sh.y;
-        x[i + 2] = fmaf(n2, sc.z, n2) + sh.z;
-        x[i + 3] = fmaf(n3, sc.w, n3) + sh.w;
-      }
+    for (int i = 0; i < 16; ++i) {
+      const int col = 64 * CQ + 16 * c + i;
+      const float n = fmaf(x[i], rstd, nmr);
+      x[i] = fmaf(n, c_eqmod[256 + col], n) + c_eqmod[col];
     }
     st_rowh<16>(X, row, CQ, 2 * c, x);
   }
@@ -116,8 +102,27 @@ __device__ __forceinline__ void eq_pass2_t(uint32_t tm_x, uint8_t* X, int row, f
 template <int CQ> __device__ __forceinline__ void eq_pass2_uni(uint32_t tm_x, uint8_t* X, int row, float mean, float rstd, const float* tr) {
   eq_pass2_t<CQ, true>(tm_x, X, row, mean, rstd, tr);
 }
-template <int CQ> __device__ __forceinline__ void eq_pass2_gen(uint32_t tm_x, uint8_t* X, int row, float mean, float rstd, const float* tr) {
-  eq_pass2_t<CQ, false>(tm_x, X, row, mean, rstd, tr);
+// general path (per-molecule rows through loads): one code copy for all column quarters (instruction-cache footprint)
+__device__ __noinline__ void eq_pass2_gen(uint32_t tm_x, uint8_t* X, int row, int cq, float mean, float rstd, const float* tr) {
+  const float nmr = -mean * rstd;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    float x[16];
+    tmem_ld16(tmem_addr(tm_x, 64 * cq + 16 * c), x);
+    const float* shift = tr + tab_equi(D_) + 64 * cq + 16 * c;
+    const float* scale = shift + D_;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + i));
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + i));
+      const float n0 = fmaf(x[i], rstd, nmr), n1 = fmaf(x[i + 1], rstd, nmr), n2 = fmaf(x[i + 2], rstd, nmr), n3 = fmaf(x[i + 3], rstd, nmr);
+      x[i] = fmaf(n0, sc.x, n0) + sh.x;
+      x[i + 1] = fmaf(n1, sc.y, n1) + sh.y;
+      x[i + 2] = fmaf(n2, sc.z, n2) + sh.z;
+      x[i + 3] = fmaf(n3, sc.w, n3) + sh.w;
+    }
+    st_rowh<16>(X, row, cq, 2 * c, x);
+  }
 }
 
 // SiLU (h + h tanh h with h = x/2; the image is pre-scaled by 1/2) and the partial coord_mlp.2 dots over hidden units
@@ -194,15 +199,16 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   uint8_t ex = a.extra[(size_t)tfirst * TILE_ROWS + row];
   float4 pg = pos[r.g], pj = pos[r.j];
   uint4 dfh[2];
-  {
-    const float* tr0 = a.tab + (size_t)(uni ? 0 : r.mol) * a.ld_tab + a.tab_off;
-    const float gsc = uni ? c_eqmod[512] : tr0[tab_gbf(D_)], gsh = uni ? c_eqmod[513] : tr0[tab_gbf(D_) + 1];
-    EQ_DISPATCH(eq_gbf, a, sq_dist(pg, pj), gsc, gsh, dfh);
-  }
+  RowInfo rn = r;
+  int ngn = ng;
+  uint8_t exn = ex;
+  float4 pgn = pg, pjn = pj;
 #ifdef JODO_PHASE_TIMING
   long long ph_last = clock64();
 #endif
-  for (int tile = tile0; tile < tile1; ++tile) {
+  // tile0 - 1 is a pipeline fill step: it only produces the distance features of tile0
+  for (int tile = tile0 - 1; tile < tile1; ++tile) {
+    if (tile >= tile0) {
     const float* tr = a.tab + (size_t)(uni ? 0 : r.mol) * a.ld_tab + a.tab_off;
     // distance features of this tile (computed one tile ahead) -> U chunk 1
 #pragma unroll
@@ -210,9 +216,9 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       *reinterpret_cast<uint4*>(U + img_piece(row, 1, 2 * cq + p, CHUNK_BYTES_A)) = dfh[p];
     // row metadata of the next tile
     const int nt_ = min(tile + 1, tile1 - 1);
-    const RowInfo rn = load_row(a.p, nt_, row);
-    const int ngn = a.p.tile_ngroups[nt_];
-    const uint8_t exn = a.extra[(size_t)nt_ * TILE_ROWS + row];
+    rn = load_row(a.p, nt_, row);
+    ngn = a.p.tile_ngroups[nt_];
+    exn = a.extra[(size_t)nt_ * TILE_ROWS + row];
     fence_async_smem();
     sync_tc();
     PHASE_MARK(0);
@@ -296,11 +302,11 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       rstd = rsqrtf(fmaxf((o01.y + o01.w + o23.y + o23.w) * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-6f);
     }
     // positions of the next tile's rows: in flight during pass 2
-    const float4 pgn = pos[rn.g], pjn = pos[rn.j];
+    pgn = pos[rn.g]; pjn = pos[rn.j];
     // ---- pass 2: LN + modulate -> X chunk cq (fp16, K = 256); the input_lin image there is no longer needed.
     // Padding rows carry finite garbage; they only feed their own (discarded) output rows.
     if (uni) { EQ_DISPATCH(eq_pass2_uni, tm_x, X, row, mean, rstd, tr); }
-    else { EQ_DISPATCH(eq_pass2_gen, tm_x, X, row, mean, rstd, tr); }
+    else eq_pass2_gen(tm_x, X, row, cq, mean, rstd, tr);
     fence_async_smem();
     sync_tc();
     PHASE_MARK(5);
@@ -317,12 +323,14 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
         umma_commit(&bars[hf ? 6 : 4]);
       }
     }
+    }   // tile >= tile0
     // under the MMA: distance features of the next tile
     {
       const float* trn = a.tab + (size_t)(uni ? 0 : rn.mol) * a.ld_tab + a.tab_off;
       const float gsc = uni ? c_eqmod[512] : trn[tab_gbf(D_)], gsh = uni ? c_eqmod[513] : trn[tab_gbf(D_) + 1];
       EQ_DISPATCH(eq_gbf, a, sq_dist(pgn, pjn), gsc, gsh, dfh);
     }
+    if (tile >= tile0) {
     mbar_wait(&bars[cq < 2 ? 4 : 6], par);
     PHASE_MARK(6);
     tc_fence_after();
@@ -360,6 +368,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
     sync_tc();
     PHASE_MARK(8);
     par ^= 1;
+    }   // tile >= tile0
     r = rn; ng = ngn; ex = exn; pg = pgn; pj = pjn;
   }
   if (tile0 >= tile1 && t == 0) mbar_wait(&bars[0], 0);   // never leave with bulk copies in flight
