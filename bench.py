@@ -36,8 +36,10 @@ WORKLOADS = {
     # name -> (config factory name, per-GPU batch, max n, description)
     'qm9': ('qm9_uncond', 2500, None, 'QM9 uncond 1000-step ancestral sampling, batch 2500, N<=29'),
     'geom': ('geom_l8', 512, 80, 'GEOM-Drugs uncond medium (n_layers=8, nf=256), batch 512, N<=80'),
+    'qm9_cond': ('qm9_cond', 2500, None, 'QM9 conditional single-property, 50-step DPM-Solver++ (singlestep, order 2), '
+                 'batch 2500; a step = one model evaluation'),
 }
-CPU_SAMPLE = {'qm9': 64, 'geom': 4}
+CPU_SAMPLE = {'qm9': 64, 'geom': 4, 'qm9_cond': 64}
 
 
 def parse():
@@ -123,6 +125,20 @@ def cpu_step_rate(cfg, wl, n_steps, threads):
     def model(t, xh, node_mask, edge_mask, **kw):
         return dgt_forward(sd, cfg, t, xh, node_mask, edge_mask, **kw)
 
+    if wl == 'qm9_cond':
+        ctx = torch.randn(bs, 1, generator=torch.Generator().manual_seed(2))
+        sol = S.DPMSolverSinglestep(S.CosineVP(), 50, order=2, generator=torch.Generator().manual_seed(1))
+        grid = sol.outer_grid('cpu')
+        x, ex = b['xh'], b['edge_x']
+        n_outer = max(1, n_steps // 2)
+        with torch.no_grad():
+            x, ex = sol.outer_step(model, 0, grid, x, b['node_mask'], b['edge_mask'], ex, ctx)                  # warm-up
+            t0 = time.perf_counter()
+            for i in range(n_outer):
+                x, ex = sol.outer_step(model, 1 + i, grid, x, b['node_mask'], b['edge_mask'], ex, ctx)
+            dt = time.perf_counter() - t0
+        return bs * 2 * n_outer / dt, (f'{bs} molecules (same histogram, seed 42) x {2 * n_outer} model evaluations of the '
+                                       f'DPM-Solver chain, oracle port fp32')
     smp = S.AncestralSampler(S.CosineVP(), torch.linspace(0.9946, 1e-3, 1000), generator=torch.Generator().manual_seed(1))
     x, ex, cx, cex = b['xh'], b['edge_x'], None, None
     with torch.no_grad():
@@ -186,7 +202,17 @@ def run_b200(args):
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     smp = S.AncestralSampler(S.CosineVP(), grid, generator=gen)
     K, W = args.steps, args.warmup
-    if W + K > len(grid):
+    dpm = args.workload == 'qm9_cond'
+    if dpm:
+        # a step = one model evaluation; the solver advances in outer steps of two evaluations (order 2)
+        if K % 2 or W % 2:
+            K, W = K + (K % 2), W + (W % 2)
+        if W + K > 50:
+            raise SystemExit('qm9_cond: warmup + steps must not exceed the 50 model evaluations of the chain')
+        sol = S.DPMSolverSinglestep(S.CosineVP(), 50, order=2, generator=gen)
+        ogrid = sol.outer_grid(dev)
+        context = torch.randn(batch, 1, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
+    elif W + K > len(grid):
         raise SystemExit('warmup + steps must not exceed the 1000-step grid')
 
     def barrier():
@@ -198,6 +224,12 @@ def run_b200(args):
     state = dict(x=b['xh'].to(dev), ex=b['edge_x'].to(dev), cx=None, cex=None)
 
     def step(i):
+        if dpm:
+            if i % 2:
+                return                                   # odd evaluation indices belong to the outer step of i - 1
+            x, ex = sol.outer_step(model, i // 2, ogrid, state['x'], node_mask, edge_mask, state['ex'], context)
+            state.update(x=x, ex=ex, cx=sol.cond_x, cex=sol.cond_edge_x, xm=x, em=ex)
+            return
         x, ex, xm, em, cx, cex = smp.step(model, i, state['x'], state['ex'], node_mask, edge_mask, state['cx'], state['cex'])
         state.update(x=x, ex=ex, cx=cx, cex=cex, xm=xm, em=em)
 
@@ -239,7 +271,12 @@ def run_b200(args):
 
         def e2e_step(i):
             dv = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            x, ex, _, _, cx, cex = smp.step(model, i, dv['x'], dv['ex'], node_mask, edge_mask, dv['cx'], dv['cex'])
+            if dpm:
+                sol.cond_x, sol.cond_edge_x = dv['cx'], dv['cex']
+                x, ex = sol.outer_step(model, (i // 2) % 24, ogrid, dv['x'], node_mask, edge_mask, dv['ex'], context)
+                cx, cex = sol.cond_x, sol.cond_edge_x
+            else:
+                x, ex, _, _, cx, cex = smp.step(model, i, dv['x'], dv['ex'], node_mask, edge_mask, dv['cx'], dv['cex'])
             outh['x'].copy_(x, non_blocking=True)
             outh['ex'].copy_(ex, non_blocking=True)
             outh['cx'].copy_(cx, non_blocking=True)
@@ -260,14 +297,15 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {'value': batch * world * ke / float(dt), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-               'd2h_bytes_per_step': d2h, 'steps': ke}
+        evals = 2 if dpm else 1                         # model evaluations per e2e_step
+        e2e = {'value': batch * world * ke * evals / float(dt), 'unit': UNIT, 'h2d_bytes_per_step': h2d // evals,
+               'd2h_bytes_per_step': d2h // evals, 'steps': ke * evals}
 
     # ---- per-kernel device times (CUDA events around every C-ABI call, outside the timed region) -------
     _lib.TRACE = []
     reps = 3
     for i in range(reps):
-        step(W + K - 1)
+        step(W + K - (2 if dpm else 1))
     torch.cuda.synchronize()
     per = {}
     for name, a, z in _lib.TRACE:
@@ -282,7 +320,7 @@ def run_b200(args):
     kernels = {}
     for name, (t, c) in sorted(per.items(), key=lambda kv: -kv[1][0]):
         avg_ms = t / c
-        ent = {'launches_per_step': c // reps, 'avg_ms': round(avg_ms, 4), 'share': round(t / total_traced, 4)}
+        ent = {'launches_per_step': c // reps // (2 if dpm else 1), 'avg_ms': round(avg_ms, 4), 'share': round(t / total_traced, 4)}
         if name in kf:
             ent['tflops'] = round(kf[name] * tot['edges'] / (avg_ms * 1e-3) / 1e12, 2)
             ent['gbs'] = round(kb[name] * tot['edges'] / (avg_ms * 1e-3) / 1e9, 1)

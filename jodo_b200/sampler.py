@@ -8,6 +8,9 @@ drive the denoiser exactly the way ``sampling_fn`` does without the reference tr
 * ``AncestralSampler``    - reference sampling.py:518-596 (pred_edge=True, self_cond=True, model_pred_data=True)
 * ``node_noise/edge_noise`` - reference models/utils.py:67-99 (same torch.randn call order, so on one
   device with one seed the stream is the one the reference would draw)
+* ``DPMSolverSinglestep`` - reference mix_dpm_solver.py:16-59,93-150,285-335 (DPM-Solver++ 'singlestep_fixed',
+  order 1 or 2, atom / bond features by the solver update, positions by the ancestral update; the driver of
+  conditional QM9 sampling, BASELINE config 5)
 * ``shard_molecules`` / ``gather_samples`` - one process per GPU, molecules dealt so that sum n(n-1) is
   balanced, no collective inside the loop, one all_gather of the final samples
 """
@@ -33,6 +36,25 @@ class CosineVP:
     def marginal_prob(self, t):
         lm = self.marginal_log_mean_coeff(t)
         return torch.exp(lm), torch.sqrt(1. - torch.exp(2. * lm))
+
+    def marginal_std(self, t):
+        return torch.sqrt(1. - torch.exp(2. * self.marginal_log_mean_coeff(t)))
+
+    def marginal_lambda(self, t):
+        """half log-SNR (reference diffusion/noise_schedule.py:93-99)"""
+        lm = self.marginal_log_mean_coeff(t)
+        return lm - 0.5 * torch.log(1. - torch.exp(2. * lm))
+
+    def inverse_lambda(self, lamb):
+        """reference diffusion/noise_schedule.py:113-117 (cosine branch)"""
+        log_alpha = -0.5 * torch.logaddexp(-2. * lamb, torch.zeros((1,)).to(lamb))
+        return torch.arccos(torch.exp(log_alpha + self.cosine_log_alpha_0)) * 2. * (1. + self.cosine_s) / math.pi - self.cosine_s
+
+    def get_noise_level(self, t):
+        """reference diffusion/noise_schedule.py:119-122"""
+        alpha_t = torch.exp(self.marginal_log_mean_coeff(t))
+        sigma_t = self.marginal_std(t)
+        return torch.log(alpha_t ** 2 / sigma_t ** 2)
 
 
 def remove_mean_with_mask(x, node_mask):
@@ -119,6 +141,114 @@ class AncestralSampler:
             x, edge_x, x_mean, edge_mean, cond_x, cond_edge_x = self.step(
                 model, i, x, edge_x, node_mask, edge_mask, cond_x, cond_edge_x, context)
         return x_mean, edge_mean
+
+
+def position_noise(B, N, node_mask, generator=None):
+    """sample_center_gravity_zero_gaussian_with_mask, reference models/utils.py:67-74"""
+    z = torch.randn((B, N, 3), device=node_mask.device, generator=generator) * node_mask
+    return remove_mean_with_mask(z, node_mask)
+
+
+class DPMSolverSinglestep:
+    """DPM-Solver++ 'singlestep_fixed' of order 1 or 2 for joint 2D & 3D generation (reference mix_dpm_solver.py):
+    features and bonds follow the exponential-integrator update, positions the ancestral update (:44-59), the model
+    is self-conditioned on its previous prediction (:285-291).  One model evaluation per order per outer step."""
+
+    def __init__(self, schedule, steps, order=2, generator=None, noise_fn=None):
+        assert order in (1, 2), 'orders 1 and 2 (BASELINE config 5 uses dpm_solver_order = 2)'
+        self.ns, self.steps, self.order = schedule, steps, order
+        self.generator, self.noise_fn = generator, noise_fn
+        self.cond_x = self.cond_edge_x = None
+        self.n_noise = 0
+        self.n_evals = 0
+
+    # -- pieces ---------------------------------------------------------------------------------------
+    def _model(self, model, x, node_mask, edge_mask, edge_x, context, t):
+        bs = x.shape[0]
+        vec_t = torch.ones(bs, device=x.device) * t
+        nl = torch.ones(bs, device=x.device) * self.ns.get_noise_level(t)
+        pred, edge_pred = model(vec_t, x, node_mask, edge_mask, edge_x=edge_x, noise_level=nl, cond_x=self.cond_x,
+                                cond_edge_x=self.cond_edge_x, context=context)
+        self.cond_x, self.cond_edge_x = pred, edge_pred
+        self.n_evals += 1
+        return pred, edge_pred
+
+    def _position_update(self, pos, pos_pred, node_mask, t_start, t_end, last_step=False):
+        """mix_dpm_solver.py:44-59"""
+        alpha_t, sigma_t = self.ns.marginal_prob(t_start)
+        alpha_s, sigma_s = self.ns.marginal_prob(t_end)
+        alpha_ts = alpha_t / alpha_s
+        sigma2_ts = sigma_t ** 2 - alpha_ts ** 2 * sigma_s ** 2
+        sigma = torch.sqrt(sigma2_ts) * sigma_s / sigma_t
+        out = (alpha_ts * sigma_s ** 2 / sigma_t ** 2) * pos + (alpha_s * sigma2_ts / sigma_t ** 2) * pos_pred
+        if not last_step:
+            if self.noise_fn is not None:
+                z = self.noise_fn(self.n_noise)
+            else:
+                z = position_noise(pos.shape[0], pos.shape[1], node_mask, self.generator)
+            self.n_noise += 1
+            out = out + sigma * z
+        return out
+
+    def _first_update(self, model, x, node_mask, edge_mask, edge_x, context, t_start, t_end, last_step):
+        """mix_dpm_solver.py:61-91"""
+        ns = self.ns
+        h = ns.marginal_lambda(t_end) - ns.marginal_lambda(t_start)
+        sigma_start, sigma_end = ns.marginal_std(t_start), ns.marginal_std(t_end)
+        alpha_end = torch.exp(ns.marginal_log_mean_coeff(t_end))
+        phi_1 = torch.expm1(-h)
+        pred, edge_pred = self._model(model, x, node_mask, edge_mask, edge_x, context, t_start)
+        atom_end = sigma_end / sigma_start * x[..., 3:] - alpha_end * phi_1 * pred[..., 3:]
+        edge_end = sigma_end / sigma_start * edge_x - alpha_end * phi_1 * edge_pred
+        pos_end = self._position_update(x[..., :3], pred[..., :3], node_mask, t_start, t_end, last_step)
+        return torch.cat([pos_end, atom_end], dim=-1), edge_end
+
+    def _second_update(self, model, x, node_mask, edge_mask, edge_x, context, t_start, t_end, last_step, r1):
+        """mix_dpm_solver.py:94-150"""
+        ns = self.ns
+        lambda_start, lambda_end = ns.marginal_lambda(t_start), ns.marginal_lambda(t_end)
+        h = lambda_end - lambda_start
+        s1 = ns.inverse_lambda(lambda_start + r1 * h)
+        sigma_start, sigma_s1, sigma_end = ns.marginal_std(t_start), ns.marginal_std(s1), ns.marginal_std(t_end)
+        alpha_s1, alpha_end = torch.exp(ns.marginal_log_mean_coeff(s1)), torch.exp(ns.marginal_log_mean_coeff(t_end))
+        phi_11, phi_1 = torch.expm1(-r1 * h), torch.expm1(-h)
+        pos_start, atom_start = x[..., :3], x[..., 3:]
+        pred, edge_pred = self._model(model, x, node_mask, edge_mask, edge_x, context, t_start)
+        atom_s1 = (sigma_s1 / sigma_start) * atom_start - (alpha_s1 * phi_11) * pred[..., 3:]
+        edge_s1 = (sigma_s1 / sigma_start) * edge_x - (alpha_s1 * phi_11) * edge_pred
+        pos_s1 = self._position_update(pos_start, pred[..., :3], node_mask, t_start, s1)
+        pred1, edge_pred1 = self._model(model, torch.cat([pos_s1, atom_s1], dim=-1), node_mask, edge_mask, edge_s1, context, s1)
+        atom_end = ((sigma_end / sigma_start) * atom_start - (alpha_end * phi_1) * pred[..., 3:]
+                    - (0.5 / r1) * (alpha_end * phi_1) * (pred1[..., 3:] - pred[..., 3:]))
+        edge_end = ((sigma_end / sigma_start) * edge_x - (alpha_end * phi_1) * edge_pred
+                    - (0.5 / r1) * (alpha_end * phi_1) * (edge_pred1 - edge_pred))
+        pos_end = self._position_update(pos_s1, pred1[..., :3], node_mask, s1, t_end, last_step)
+        return torch.cat([pos_end, atom_end], dim=-1), edge_end
+
+    # -- driver ---------------------------------------------------------------------------------------
+    def outer_grid(self, device):
+        K = self.steps // self.order
+        return torch.linspace(self.ns.T, 1. / self.ns.total_N, K + 1).to(device)
+
+    def outer_step(self, model, step, grid, x, node_mask, edge_mask, edge_x, context=None):
+        """One outer step (= `order` model evaluations), mix_dpm_solver.py:322-334."""
+        t_start, t_end = grid[step], grid[step + 1]
+        last = step == len(grid) - 2
+        if self.order == 1:
+            return self._first_update(model, x, node_mask, edge_mask, edge_x, context, t_start, t_end, last)
+        inner = torch.linspace(t_start.item(), t_end.item(), self.order + 1).to(x.device)
+        lam = self.ns.marginal_lambda(inner)
+        r1 = (lam[1] - lam[0]) / (lam[-1] - lam[0])
+        return self._second_update(model, x, node_mask, edge_mask, edge_x, context, t_start, t_end, last, r1)
+
+    @torch.no_grad()
+    def sampling(self, model, x, node_mask, edge_mask, edge_x, context=None):
+        self.cond_x = self.cond_edge_x = None
+        self.n_noise = self.n_evals = 0
+        grid = self.outer_grid(x.device)
+        for step in range(len(grid) - 1):
+            x, edge_x = self.outer_step(model, step, grid, x, node_mask, edge_mask, edge_x, context)
+        return x, edge_x
 
 
 # ---- multi-GPU: shard independent molecules, gather final samples --------------------------------

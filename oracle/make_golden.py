@@ -153,6 +153,41 @@ def run_sampler_case(ref):
     print('qm9_ancestral_chain:', tuple(x.shape), tuple(ex.shape), float(x.abs().max()))
 
 
+def run_dpm_case(ref):
+    """3 outer steps (6 model evaluations) of the reference DPM_Solver_hybrid ('singlestep_fixed', order 2,
+    mix_dpm_solver.py:285-335) on the conditional QM9 model with a context, recording every position-noise draw."""
+    ours = configs.qm9_cond()
+    rcfg = ref_loader.load_config('vpsde_qm9_cond_jodo')
+    rcfg.sampling.steps = 6
+    rcfg.sampling.dpm_solver_order = 2
+    rcfg.sampling.dpm_solver_method = 'singlestep_fixed'
+    model = ref.model_utils._MODELS[rcfg.model.name](rcfg)
+    model.load_state_dict(synth_state_dict(param_spec(ours), seed=3, perturb=True), strict=True)
+    model.eval()
+    ns = ref.noise_schedule.NoiseScheduleVP(rcfg.sde.schedule, continuous_beta_0=rcfg.sde.continuous_beta_0,
+                                            continuous_beta_1=rcfg.sde.continuous_beta_1)
+    solver = ref.mix_dpm_solver.DPM_Solver_hybrid(ns, rcfg)
+    batch = synth.make_batch(ours, 3, seed=21, n_nodes=[6, 11, 4], context=True)
+    rec = []
+    orig = ref.mix_dpm_solver.sample_center_gravity_zero_gaussian_with_mask
+
+    def rec_fn(*a, **k):
+        v = orig(*a, **k)
+        rec.append(v.clone())
+        return v
+
+    ref.mix_dpm_solver.sample_center_gravity_zero_gaussian_with_mask = rec_fn
+    torch.manual_seed(77)
+    try:
+        x, ex = solver.sampling(model, batch['xh'], batch['node_mask'], batch['edge_mask'], batch['edge_x'], batch['context'])
+    finally:
+        ref.mix_dpm_solver.sample_center_gravity_zero_gaussian_with_mask = orig
+    out = dict(case='qm9_cond_dpm_chain', config='qm9_cond', weights=dict(seed=3, perturb=True), inputs=batch,
+               steps=6, order=2, noise_pos=rec, x=x, edge_x=ex)
+    torch.save(out, os.path.join(GOLD, 'qm9_cond_dpm_chain.pt'))
+    print('qm9_cond_dpm_chain:', tuple(x.shape), tuple(ex.shape), len(rec), 'noise draws', float(x.abs().max()))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -163,6 +198,8 @@ def main():
             run_case(ref, name)
     if not only or 'chain' in only:
         run_sampler_case(ref)
+    if not only or 'dpm' in only:
+        run_dpm_case(ref)
 
 
 if __name__ == '__main__':

@@ -144,3 +144,58 @@ def test_cuda_chain_free_running():
     assert float((xm * (1 - nm)).abs().max()) == 0.0
     assert float((em - em.permute(0, 2, 1, 3)).abs().max()) == 0.0
     assert float(xm[..., :3].sum(1).abs().max()) < 1e-4
+
+
+# ---- DPM-Solver++ singlestep, order 2: the driver of conditional QM9 sampling (BASELINE config 5) ---------------------
+def test_oracle_dpm_solver_replays_reference_chain():
+    from oracle import sampler_ref as R
+    g, cfg = load_golden('qm9_cond_dpm_chain')
+    model = _oracle_model(golden_weights(g, cfg), cfg, torch.float32)
+    b = g['inputs']
+    with torch.no_grad():
+        x, e = R.dpm_singlestep2_chain(model, b['xh'], b['edge_x'], b['node_mask'], b['edge_mask'], b['context'], g['steps'],
+                                       g['noise_pos'])
+    assert float((x - g['x']).abs().max()) < 5e-4 * float(g['x'].abs().max())
+    assert float((e - g['edge_x']).abs().max()) < 5e-4 * float(g['edge_x'].abs().max())
+
+
+def test_product_dpm_solver_replays_reference_chain():
+    g, cfg = load_golden('qm9_cond_dpm_chain')
+    model = _oracle_model(golden_weights(g, cfg), cfg, torch.float32)
+    b = g['inputs']
+    sol = S.DPMSolverSinglestep(S.CosineVP(), g['steps'], order=g['order'], noise_fn=lambda i: g['noise_pos'][i])
+    x, e = sol.sampling(model, b['xh'], b['node_mask'], b['edge_mask'], b['edge_x'], b['context'])
+    assert sol.n_evals == g['steps'] and sol.n_noise == len(g['noise_pos'])
+    assert float((x - g['x']).abs().max()) < 5e-4 * float(g['x'].abs().max())
+    assert float((e - g['edge_x']).abs().max()) < 5e-4 * float(g['edge_x'].abs().max())
+    assert float(x[..., :3].sum(1).abs().max()) < 1e-4                  # assert_mean_zero_with_mask, mix_dpm_solver.py:374
+
+
+def test_position_noise_matches_reference_draws():
+    g, cfg = load_golden('qm9_cond_dpm_chain')
+    b = g['inputs']
+    gen = torch.Generator().manual_seed(77)
+    for z in g['noise_pos']:
+        assert torch.equal(S.position_noise(b['xh'].shape[0], b['xh'].shape[1], b['node_mask'], gen), z)
+
+
+@pytest.mark.gpu
+def test_cuda_dpm_solver_chain():
+    """Conditional model (context path) under the product DPM-Solver with replayed noise, free-running for 6 model
+    evaluations: loose tolerance for the same reason as the ancestral chain, exact invariants."""
+    from jodo_b200.model import MODELS
+    g, cfg = load_golden('qm9_cond_dpm_chain')
+    model = MODELS[cfg.model.name](cfg)
+    model.load_state_dict(golden_weights(g, cfg), strict=True)
+    model = model.cuda().eval()
+    b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in g['inputs'].items()}
+    sol = S.DPMSolverSinglestep(S.CosineVP(), g['steps'], order=g['order'], noise_fn=lambda i: g['noise_pos'][i].cuda())
+    x, e = sol.sampling(model, b['xh'], b['node_mask'], b['edge_mask'], b['edge_x'], b['context'])
+    x, e = x.cpu(), e.cpu()
+    assert sol.n_evals == 6
+    assert float((x - g['x']).abs().max()) < 5e-2 * float(g['x'].abs().max())
+    assert float((e - g['edge_x']).abs().max()) < 1e-1 * float(g['edge_x'].abs().max())
+    nm = g['inputs']['node_mask']
+    assert float((x * (1 - nm)).abs().max()) == 0.0
+    assert float((e - e.permute(0, 2, 1, 3)).abs().max()) == 0.0
+    assert float(x[..., :3].sum(1).abs().max()) < 1e-4
