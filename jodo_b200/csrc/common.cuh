@@ -54,7 +54,7 @@ __device__ __forceinline__ float rcp_fast(float x) {
   return y;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+  asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float tanh_f(float x) {         // accurate to ~1e-6 abs (2 MUFU)

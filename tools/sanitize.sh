@@ -1,0 +1,8 @@
+#!/bin/bash
+# compute-sanitizer over one small denoiser call (smoke): memcheck, racecheck (shared-memory hazards), synccheck.
+OUT=gpurun_out/sanitize
+mkdir -p $OUT
+for tool in memcheck racecheck synccheck; do
+  timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/$tool.log 2>&1
+  echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke:" $OUT/$tool.log | tail -3
+done
