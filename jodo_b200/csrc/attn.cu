@@ -169,12 +169,14 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
       const float var = fmaxf((q + o.y) * (1.0f / 64.0f) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + 1e-6f);
       const float nmr = -mean * rstd;
+      float scv[32], shv[32];                              // general path: this molecule's row, 16-byte loads
+      if (!UNI) { ldg_row<32>(tr + tab_edge(D_) + ED_ + 32 * HALF, scv); ldg_row<32>(tr + tab_edge(D_) + 32 * HALF, shv); }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int col = 32 * HALF + i;
         const float n = fmaf(x[i], rstd, nmr);
-        const float sc = UNI ? c_atmod[64 + col] : tr[tab_edge(D_) + ED_ + col];
-        const float sh = UNI ? c_atmod[col] : tr[tab_edge(D_) + col];
+        const float sc = UNI ? c_atmod[64 + col] : scv[i];
+        const float sh = UNI ? c_atmod[col] : shv[i];
         x[i] = fmaf(n, sc, n) + sh;
       }
       st_rowh<32>(A0, row, 0, 4 * HALF, x);

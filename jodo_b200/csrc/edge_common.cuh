@@ -173,6 +173,17 @@ __device__ __forceinline__ H16 ldg_h16(const uint16_t* p) {
   return r;
 }
 
+// N consecutive floats of a per-molecule table row (16-byte aligned) through 16-byte loads
+template <int N>
+__device__ __forceinline__ void ldg_row(const float* __restrict__ p, float (&v)[N]) {
+  static_assert(N % 4 == 0, "whole float4s");
+#pragma unroll
+  for (int k = 0; k < N / 4; ++k) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p) + k);
+    v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+  }
+}
+
 // LayerNorm (no affine, eps 1e-6) + modulate over 64 thread-local values
 __device__ __forceinline__ void ln_mod64(float (&x)[64], const float* __restrict__ shift, const float* __restrict__ scale) {
   float s = 0.f;

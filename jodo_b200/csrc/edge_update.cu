@@ -75,6 +75,8 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
     // ---- e2 = LN(e + gate_msa * (P[g] + P[j] + b)) * (1 + scale_mlp) + shift_mlp
     float e2[32];
     {
+      float gv[32];                                  // general path: this molecule's row, 16-byte loads
+      if (!UNI) ldg_row<32>(tr + 2 * ED_ + C0, gv);
       float s = 0.f, q = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -85,7 +87,7 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int col = C0 + 8 * i + k;
-          const float g = UNI ? c_eumod[2 * ED_ + col] : tr[2 * ED_ + col];
+          const float g = UNI ? c_eumod[2 * ED_ + col] : gv[8 * i + k];
           const float v = fmaf(g, (uf[k] + vf[k]) + a.b_n2e[col], ee[k]);
           e2[8 * i + k] = v;
           s += v;
@@ -99,12 +101,14 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
       const float mean = (s + o.x) * (1.0f / 64.0f);
       const float rstd = rsqrtf(fmaxf((q + o.y) * (1.0f / 64.0f) - mean * mean, 0.f) + 1e-6f);
       const float nmr = -mean * rstd;
+      float scv[32], shv[32];
+      if (!UNI) { ldg_row<32>(tr + 4 * ED_ + C0, scv); ldg_row<32>(tr + 3 * ED_ + C0, shv); }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int col = C0 + i;
         const float n = fmaf(e2[i], rstd, nmr);
-        const float sc = UNI ? c_eumod[4 * ED_ + col] : tr[4 * ED_ + col];
-        const float sh = UNI ? c_eumod[3 * ED_ + col] : tr[3 * ED_ + col];
+        const float sc = UNI ? c_eumod[4 * ED_ + col] : scv[i];
+        const float sh = UNI ? c_eumod[3 * ED_ + col] : shv[i];
         e2[i] = fmaf(n, sc, n) + sh;               // padding rows carry finite garbage until the final select
       }
       st_rowh<32>(c.A, row, 0, 4 * HALF, e2);
@@ -148,10 +152,12 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
     {
       float y[32];
       tmem_ld32(tmem_addr(c.tm_y, C0), y);
+      float gv[32];
+      if (!UNI) ldg_row<32>(tr + 5 * ED_ + C0, gv);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int col = C0 + i;
-        const float g = UNI ? c_eumod[5 * ED_ + col] : tr[5 * ED_ + col];
+        const float g = UNI ? c_eumod[5 * ED_ + col] : gv[i];
         e2[i] = r.valid ? fmaf(g, y[i] + a.b4[col], e2[i]) : 0.f;
       }
       float4* dst = reinterpret_cast<float4*>(e32 + (size_t)tile * E_TILE_BYTES) + (8 * HALF) * 128 + row;
