@@ -266,7 +266,7 @@ def pack_model(sd, dims, device):
         add_lin(p + 'n2e', W(f'{b}.node2edge_lin'), None, 64)
         pk.add_host(p + 'n2e.bias', Bv(f'{b}.node2edge_lin'))
         add_lin(p + 'ff1', W(f'{b}.ff_linear1'), Bv(f'{b}.ff_linear1'), 256)
-        add_lin(p + 'ff2', W(f'{b}.ff_linear2'), Bv(f'{b}.ff_linear2'), 256)
+        add_lin(p + 'ff2', W(f'{b}.ff_linear2'), Bv(f'{b}.ff_linear2'), 128)     # K = r D is deep: narrower tiles balance the SMs
         wi = W(f'{b}.equi_update.input_lin')                   # [D, 2D + 2ed]: [h_row | h_col | e | dist]
         add_lin(p + 'ab', torch.cat([wi[:, :D], wi[:, D:2 * D]], dim=0),
                 torch.cat([Bv(f'{b}.equi_update.input_lin'), z(D)]), 256)      # input_lin bias rides on the h[row] part

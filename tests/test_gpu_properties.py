@@ -1,0 +1,135 @@
+"""GPU property tests at the full BASELINE sizes (QM9 B=2500, GEOM-Drugs B=512), where the oracle is too slow to be the
+checker: size-independent properties of the denoiser that the reference has by construction --
+* molecules are independent: permuting the batch permutes the outputs, and the padding width N does not matter;
+* E(3): rotating / reflecting and translating the input positions (and the self-conditioning positions) rotates the
+  predicted positions and leaves atom and bond logits unchanged (translations are removed by the CoM projection,
+  reference models/mol_gnn.py:565-566, 592);
+* the structural invariants of tests/test_gpu_parity.py (masked entries exactly zero, exact symmetry, CoM).
+Plus the edge cases of the varlen layout: single-atom molecules, two-atom molecules, a batch of one, the largest
+supported molecule, checked against the oracle."""
+import pytest
+import torch
+
+from jodo_b200 import configs, synth
+from jodo_b200.model import MODELS
+from jodo_b200.params import param_spec, synth_state_dict
+
+pytestmark = pytest.mark.gpu
+TOL = 5e-3
+
+
+def _model(cfg_name, seed=5):
+    cfg = configs.NAMED[cfg_name]()
+    m = MODELS[cfg.model.name](cfg)
+    m.load_state_dict(synth_state_dict(param_spec(cfg), seed=seed, perturb=True), strict=True)
+    return cfg, m.cuda().eval()
+
+
+def _call(model, b, noise_level=None, **over):
+    d = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+    d.update(over)
+    nl = d['noise_level'] if noise_level is None else noise_level
+    return model(d['t'], d['xh'], d['node_mask'], d['edge_mask'], context=d.get('context'), edge_x=d['edge_x'],
+                 noise_level=nl, cond_x=d['cond_x'], cond_edge_x=d['cond_edge_x'])
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-20))
+
+
+@pytest.mark.parametrize('cfg_name,B,max_n', [('qm9_uncond', 2500, None), ('geom_l8', 512, 80)])
+def test_full_size_invariants_and_independence(cfg_name, B, max_n):
+    cfg, model = _model(cfg_name)
+    b = synth.make_batch(cfg, B, seed=3, max_n=max_n, self_cond=True)
+    x, e = _call(model, b)
+    nm = b['node_mask'].cuda()
+    N = nm.shape[1]
+    em = b['edge_mask'].cuda().reshape(B, N, N, 1)
+    assert torch.isfinite(x).all() and torch.isfinite(e).all()
+    assert float((x * (1 - nm)).abs().max()) == 0.0
+    assert float((e * (1 - em)).abs().max()) == 0.0
+    assert float((e - e.permute(0, 2, 1, 3)).abs().max()) == 0.0
+    assert float(x[..., :3].sum(1).abs().max()) < 1e-3
+    # batch permutation: outputs permute (different tiles, same per-molecule arithmetic up to fp32 summation order)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+    bp = {k: (v[perm] if torch.is_tensor(v) and v.shape[0] == B else v) for k, v in b.items()}
+    bp['edge_mask'] = b['edge_mask'].reshape(B, N * N, 1)[perm].reshape(B * N * N, 1)
+    xp, ep = _call(model, bp)
+    assert _rel(xp, x[perm.cuda()]) < 1e-4 and _rel(ep, e[perm.cuda()]) < 1e-4
+    # padding width: the first 64 molecules alone, padded to their own maximum
+    idx = torch.arange(64)
+    n = b['n_nodes'][idx]
+    Ns = int(n.max())
+    nm_s, em_s = synth.make_masks(n, Ns)
+    sub = dict(t=b['t'][idx], xh=b['xh'][idx][:, :Ns], node_mask=nm_s, edge_mask=em_s, edge_x=b['edge_x'][idx][:, :Ns, :Ns],
+               noise_level=b['noise_level'][idx], cond_x=b['cond_x'][idx][:, :Ns], cond_edge_x=b['cond_edge_x'][idx][:, :Ns, :Ns],
+               context=None)
+    xs, es = _call(model, sub)
+    assert _rel(xs, x[:64, :Ns]) < 1e-4 and _rel(es, e[:64, :Ns, :Ns]) < 1e-4
+
+
+@pytest.mark.parametrize('cfg_name,B,max_n', [('qm9_uncond', 2500, None), ('geom_l8', 512, 80)])
+def test_full_size_e3_equivariance(cfg_name, B, max_n):
+    cfg, model = _model(cfg_name)
+    b = synth.make_batch(cfg, B, seed=4, max_n=max_n, self_cond=True)
+    x, e = _call(model, b)
+    g = torch.Generator().manual_seed(9)
+    Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+    Q = Q * torch.tensor([1.0, 1.0, -1.0], dtype=torch.float64)       # include a reflection
+    Q = Q.float()
+    shift = torch.tensor([0.3, -1.1, 0.7])
+    nm = b['node_mask']
+
+    def move(v):
+        out = v.clone()
+        out[..., :3] = (v[..., :3] @ Q.t() + shift) * nm
+        return out
+
+    xr, er = _call(model, b, xh=move(b['xh']).cuda(), cond_x=move(b['cond_x']).cuda())
+    want = x.clone()
+    want[..., :3] = x[..., :3] @ Q.t().cuda()
+    # the rotated problem rounds differently in the fp16 operands: tolerance of one forward
+    assert _rel(xr[..., :3], want[..., :3]) < TOL
+    assert _rel(xr[..., 3:], x[..., 3:]) < TOL
+    assert _rel(er, e) < TOL
+
+
+def _oracle(cfg, sd, b):
+    from oracle.dgt_dense import dgt_forward
+    c = lambda v: None if v is None else v.double()
+    sd = {k: v.double() for k, v in sd.items()}
+    return dgt_forward(sd, cfg, c(b['t']), c(b['xh']), c(b['node_mask']), c(b['edge_mask']), context=c(b.get('context')),
+                       edge_x=c(b['edge_x']), noise_level=c(b['noise_level']), cond_x=c(b['cond_x']), cond_edge_x=c(b['cond_edge_x']))
+
+
+@pytest.mark.parametrize('n_nodes', [[1, 5, 1, 3], [2, 2, 7], [9], [1], [29, 1, 2, 29, 3]])
+def test_edge_cases_against_oracle(n_nodes):
+    """single-atom molecules (no edges: the denoiser sees only the atom's own features), two-atom molecules (groups of
+    one row), batches of one."""
+    cfg = configs.NAMED['qm9_uncond']()
+    sd = synth_state_dict(param_spec(cfg), seed=2, perturb=True)
+    model = MODELS[cfg.model.name](cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    b = synth.make_batch(cfg, len(n_nodes), seed=8, n_nodes=n_nodes, self_cond=True)
+    x, e = _call(model, b)
+    ox, oe = _oracle(cfg, sd, b)
+    assert _rel(x.cpu().double(), ox) < TOL
+    if float(oe.abs().max()) > 0:
+        assert _rel(e.cpu().double(), oe) < TOL
+    else:
+        assert float(e.abs().max()) == 0.0
+    assert float((x.cpu() * (1 - b['node_mask'])).abs().max()) == 0.0
+
+
+def test_largest_supported_molecule_and_rejection():
+    """One group must fit a 128-row tile: 129 atoms is the largest molecule; beyond that the plan refuses loudly
+    (GEOM-Drugs goes up to 181 atoms; BASELINE quotes N <= 80)."""
+    cfg, model = _model('geom_l8')
+    b = synth.make_batch(cfg, 2, seed=6, n_nodes=[129, 40], self_cond=True)
+    x, e = _call(model, b)
+    assert torch.isfinite(x).all() and torch.isfinite(e).all()
+    assert float((e - e.permute(0, 2, 1, 3)).abs().max()) == 0.0
+    big = synth.make_batch(cfg, 1, seed=6, n_nodes=[130])
+    with pytest.raises(ValueError):
+        _call(model, big)

@@ -17,6 +17,10 @@ shapes = {  # name: (K, N, NT, outputs)
     'n2e': (256, 64, 64, ('C16',)),
     'ff1': (256, 512, 256, ('Cimg',)),
     'ff2': (512, 256, 256, ('C32', 'Cimg', 'gated')),
+    'ff2_nt128': (512, 256, 128, ('C32', 'Cimg', 'gated')),
+    'qkv_nt128': (256, 768, 128, ('C16',)),
+    'ff1_nt128': (256, 512, 128, ('Cimg',)),
+    'ab_nt128': (256, 512, 128, ('C16',)),
     'ab': (256, 512, 256, ('C16',)),
     'node_l': (256, 64, 64, ('C32',)),
 }
