@@ -36,10 +36,11 @@ WORKLOADS = {
     # name -> (config factory name, per-GPU batch, max n, description)
     'qm9': ('qm9_uncond', 2500, None, 'QM9 uncond 1000-step ancestral sampling, batch 2500, N<=29'),
     'geom': ('geom_l8', 512, 80, 'GEOM-Drugs uncond medium (n_layers=8, nf=256), batch 512, N<=80'),
+    'geom_l10': ('geom_l10', 512, 80, 'GEOM-Drugs uncond medium with the reference default n_layers=10 (nf=256), batch 512, N<=80'),
     'qm9_cond': ('qm9_cond', 2500, None, 'QM9 conditional single-property, 50-step DPM-Solver++ (singlestep, order 2), '
                  'batch 2500; a step = one model evaluation'),
 }
-CPU_SAMPLE = {'qm9': 64, 'geom': 4, 'qm9_cond': 64}
+CPU_SAMPLE = {'qm9': 64, 'geom': 4, 'geom_l10': 4, 'qm9_cond': 64}
 
 
 def parse():
