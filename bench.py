@@ -40,7 +40,7 @@ WORKLOADS = {
     'qm9_cond': ('qm9_cond', 2500, None, 'QM9 conditional single-property, 50-step DPM-Solver++ (singlestep, order 2), '
                  'batch 2500; a step = one model evaluation'),
 }
-CPU_SAMPLE = {'qm9': 64, 'geom': 4, 'geom_l10': 4, 'qm9_cond': 64}
+CPU_SAMPLE = {'qm9': 64, 'geom': 16, 'geom_l10': 16, 'qm9_cond': 64}
 
 
 def parse():
