@@ -34,16 +34,16 @@ constexpr int EQ_THREADS = 512;
 constexpr int EQ_WC0 = 0;                        // 128 KB: coord_mlp.0 image (N = 256, K = 256: 4 chunks of 32 KB)
 constexpr int EQ_X = 131072;                     // 64 KB: input_lin image (N = 256, K = 128), then LN-modulated A (K = 256)
 constexpr int EQ_U = EQ_X + 65536;               // 32 KB: [e | GBF(d)] (K = 128); chunk 1 doubles as scratch
-constexpr int EQ_MISC = EQ_U + 32768;
-constexpr int EQ_SMEM = EQ_MISC + 128;
+constexpr int EQ_MISC = EQ_U + 32768;            // barriers + tmem slot (128 B), then C3 [128] float4 and the group table
+constexpr int EQ_C3 = EQ_MISC + 128;             // per-row coordinate contribution (dedicated: read across the tile end)
+constexpr int EQ_GT = EQ_C3 + 128 * 16;          // group table: start | len << 8 [64], atom [64] (<= 64 groups per tile)
+constexpr int EQ_SMEM = EQ_GT + 512;
 static_assert(EQ_SMEM <= 232448, "shared memory budget");
 // scratch inside U chunk 1 (free once the input_lin MMA has completed)
 constexpr int EQ_SCR = EQ_U + 16384;
 constexpr int EQ_LNS = EQ_SCR;                   // [128][4] float2
 constexpr int EQ_DOT = EQ_LNS + 128 * 4 * 8;     // [128][4] float4
-constexpr int EQ_C3 = EQ_DOT + 128 * 4 * 16;     // [128] float4
-constexpr int EQ_GT = EQ_C3 + 128 * 16;          // group tables 2 x [128] ints
-static_assert(EQ_GT + 1024 <= EQ_MISC, "scratch overflows the U chunk");
+static_assert(EQ_DOT + 128 * 4 * 16 <= EQ_MISC, "scratch overflows the U chunk");
 
 // Uniform-conditioning fast path: when every molecule of the batch carries the same noise level (and context), the
 // AdaLN rows are identical, and row 0's (shift[256] | scale[256] | gbf scale, shift) segment is copied into constant
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   float4* DOT = reinterpret_cast<float4*>(smem + EQ_DOT);
   float4* C3 = reinterpret_cast<float4*>(smem + EQ_C3);
   uint32_t* gt_meta = reinterpret_cast<uint32_t*>(smem + EQ_GT);
-  int* gt_node = reinterpret_cast<int*>(gt_meta + 128);
+  int* gt_node = reinterpret_cast<int*>(gt_meta + 64);
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int rq = warp & 3, cq = warp >> 2;
@@ -356,16 +356,25 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       C3[row] = make_float4(dx * f, dy * f, dz * f, 0.f);
     }
     __syncthreads();
-    if (t < ng) {
-      const int gs = gt_meta[t] & 255u, gl = (gt_meta[t] >> 8) & 255u;
-      const int node = gt_node[t];
+    // per-atom sums of the coordinate contributions: one warp per group, lanes over its rows, shuffle tree
+    for (int gi = warp; gi < ng; gi += EQ_THREADS / 32) {
+      const int gs = gt_meta[gi] & 255u, gl = (gt_meta[gi] >> 8) & 255u;
       float sx = 0.f, sy = 0.f, sz = 0.f;
-      for (int rr = gs; rr < gs + gl; ++rr) { const float4 c = C3[rr]; sx += c.x; sy += c.y; sz += c.z; }
-      const float4 p0 = pos[node];
-      pos_out[node] = make_float4(p0.x + sx, p0.y + sy, p0.z + sz, 0.f);
+      for (int k = lane; k < gl; k += 32) { const float4 c = C3[gs + k]; sx += c.x; sy += c.y; sz += c.z; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+      }
+      if (lane == 0) {
+        const int node = gt_node[gi];
+        const float4 p0 = pos[node];
+        pos_out[node] = make_float4(p0.x + sx, p0.y + sy, p0.z + sz, 0.f);
+      }
     }
-    fence_async_smem();        // the scratch is overwritten by the next tile's GBF rows
-    sync_tc();
+    // no barrier here: C3 and the group table are dedicated buffers that are rewritten only after the next tile's
+    // barriers; the scratch inside the GBF chunk (LNS, DOT) was last read before the barrier above
     PHASE_MARK(8);
     par ^= 1;
     }   // tile >= tile0
