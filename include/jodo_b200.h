@@ -199,6 +199,14 @@ int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo
                   float* out_dense, void* stream);
 int jodo_sym_edges(const float* tmp, float* out, int B, int N, int ch, void* stream);
 
+/* Fused posterior-mean update + noise of one ancestral reverse step (reference sampling.py:569-589 with the noise
+ * construction of models/utils.py:67-99): dense [B,N,F] / [B,N,N,ch] tensors, raw standard-normal draws supplied by
+ * the caller ([B,N,3], [B,N,F-3], [B,ch,N,N]); writes x_new, x_mean, e_new, e_mean. */
+int jodo_ancestral_update(const float* x, const float* pred, const float* raw_pos, const float* raw_feat,
+                          const float* node_mask, const float* edge_x, const float* edge_pred, const float* raw_edge,
+                          const float* edge_mask, int B, int N, int F, int ch, float c_x, float c_pred, float sigma,
+                          float* x_new, float* x_mean, float* e_new, float* e_mean, void* stream);
+
 /* edge-tile kernels (tcgen05 + TMEM + bulk-copied operand images); see the structs above */
 int jodo_edge_embed(const jodo_edge_embed_args* a, void* stream);
 int jodo_attn(const jodo_attn_args* a, void* stream);

@@ -102,7 +102,8 @@ class AncestralSampler:
     """Ancestral sampling for joint 2D & 3D generation (reference sampling.py:518-596) with
     self-conditioning ('ori' hand-off, reference utils.py:134-136)."""
 
-    def __init__(self, schedule, time_steps, generator=None, noise_fn=None, s_array=None):
+    def __init__(self, schedule, time_steps, generator=None, noise_fn=None, s_array=None, fused=True):
+        self.fused = fused                # CUDA tensors: fused update kernel (same random stream as the torch ops)
         self.schedule = schedule
         self.t_array = time_steps
         self.coef = ancestral_coefficients(schedule, time_steps, s_array)
@@ -119,6 +120,8 @@ class AncestralSampler:
         noise_level = torch.full((bs,), nl, device=x.device)
         pred, edge_pred = model(vec_t, x, node_mask, edge_mask, edge_x=edge_x, noise_level=noise_level,
                                 cond_x=cond_x, cond_edge_x=cond_edge_x, context=context)
+        if x.is_cuda and self.noise_fn is None and self.fused:
+            return self._fused_update(x, edge_x, pred, edge_pred, node_mask, edge_mask, c_x, c_pred, sigma)
         x_mean = c_x * x + c_pred * pred
         if self.noise_fn is not None:
             zn, ze = self.noise_fn(i, 'node'), self.noise_fn(i, 'edge')
@@ -131,6 +134,29 @@ class AncestralSampler:
             ze = edge_noise(bs, N, edge_x.shape[-1], edge_mask, self.generator)
         edge_new = edge_mean + sigma * ze
         return x_new, edge_new, x_mean, edge_mean, pred, edge_pred
+
+    def _fused_update(self, x, edge_x, pred, edge_pred, node_mask, edge_mask, c_x, c_pred, sigma):
+        """Posterior mean + noise in two launches of libjodo_b200 (jodo_ancestral_update) instead of ~30 torch
+        kernels; the raw normal draws are the same torch.randn calls, in the same order, as node_noise / edge_noise."""
+        import ctypes
+        from . import _lib
+        bs, N, F_ = x.shape
+        ch = edge_x.shape[-1]
+        dev = x.device
+        raw_pos = torch.randn((bs, N, 3), device=dev, generator=self.generator)
+        raw_feat = torch.randn((bs, N, F_ - 3), device=dev, generator=self.generator)
+        raw_edge = torch.randn((bs, ch, N, N), device=dev, generator=self.generator)
+        c32 = lambda t: t.contiguous().float()
+        x, edge_x, pred, edge_pred = c32(x), c32(edge_x), c32(pred), c32(edge_pred)
+        nm, em = c32(node_mask), c32(edge_mask)
+        x_new, x_mean = torch.empty_like(x), torch.empty_like(x)
+        e_new, e_mean = torch.empty_like(edge_x), torch.empty_like(edge_x)
+        f = ctypes.c_float
+        _lib.call('jodo_ancestral_update', _lib.ptr(x), _lib.ptr(pred), _lib.ptr(raw_pos), _lib.ptr(raw_feat), _lib.ptr(nm),
+                  _lib.ptr(edge_x), _lib.ptr(edge_pred), _lib.ptr(raw_edge), _lib.ptr(em), ctypes.c_int(bs), ctypes.c_int(N),
+                  ctypes.c_int(F_), ctypes.c_int(ch), f(c_x), f(c_pred), f(sigma), _lib.ptr(x_new), _lib.ptr(x_mean),
+                  _lib.ptr(e_new), _lib.ptr(e_mean), _lib.stream_ptr())
+        return x_new, e_new, x_mean, e_mean, pred, edge_pred
 
     @torch.no_grad()
     def sampling(self, model, z_T, node_mask, edge_mask, edge_z_T, context=None):
