@@ -158,12 +158,13 @@ typedef struct jodo_equi_args {                         /* MultiCondEquiUpdate (
   const uint8_t* extra;
   const void* win_img;                    /* input_lin edge part fp16 image (N=256, K=128: [e | dist]) */
   const void* wc0_img;                    /* coord_mlp.0 fp16 image (N=256, K=256), pre-scaled by 1/2 */
+  const void* w2_img;                     /* coord_mlp.2 fp16 image (N=16: rows 0..2 real, K=256) */
   float coord_scale;                      /* CoorsNorm.scale */
   const int* nonuni;                      /* device flag written by jodo_uniform_flag: 0 = every molecule has the same
                                              conditioning row (fast path reads row 0 through constant memory); may be null */
   /* per-column constants passed BY VALUE so that they reach the FMA pipe as constant-bank operands: */
   float gbf4[256];                        /* GBF constants, {mu, c1, c2, 0} per feature column (entry 0 unused) */
-  float c0tab[1024];                      /* [256] x {coord_mlp.0 bias / 2, coord_mlp.2 weight rows 0..2} */
+  float b0h[256];                         /* coord_mlp.0 bias / 2 */
 } jodo_equi_args;
 
 typedef struct jodo_edge_head_args {                     /* edge_exist_mlp | edge_type_mlp (reference models/mol_gnn.py:466-479,574-578) */

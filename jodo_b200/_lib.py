@@ -120,8 +120,8 @@ class EdgeUpdateArgs(ctypes.Structure):
 class EquiArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('e16', _P), ('pos_in', _P), ('pos_out', _P), ('AB', _P),
                 ('ldab', _I), ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P),
-                ('win_img', _P), ('wc0_img', _P), ('coord_scale', _F), ('nonuni', _P),
-                ('gbf4', _F * 256), ('c0tab', _F * 1024)]
+                ('win_img', _P), ('wc0_img', _P), ('w2_img', _P), ('coord_scale', _F), ('nonuni', _P),
+                ('gbf4', _F * 256), ('b0h', _F * 256)]
 
 
 class EdgeHeadArgs(ctypes.Structure):

@@ -42,8 +42,8 @@ static_assert(EQ_SMEM <= 232448, "shared memory budget");
 // scratch inside U chunk 1 (free once the input_lin MMA has completed)
 constexpr int EQ_SCR = EQ_U + 16384;
 constexpr int EQ_LNS = EQ_SCR;                   // [128][4] float2
-constexpr int EQ_DOT = EQ_LNS + 128 * 4 * 8;     // [128][4] float4
-static_assert(EQ_DOT + 128 * 4 * 16 <= EQ_MISC, "scratch overflows the U chunk");
+constexpr int EQ_W2 = EQ_LNS + 128 * 4 * 8;      // 8 KB: coord_mlp.2 image (N = 16, K = 256), bulk-copied per tile
+static_assert(EQ_W2 % 1024 == 0 && EQ_W2 + 8192 <= EQ_MISC, "scratch overflows the U chunk");
 
 // Uniform-conditioning fast path: when every molecule of the batch carries the same noise level (and context), the
 // AdaLN rows are identical, and row 0's (shift[256] | scale[256] | gbf scale, shift) segment is copied into constant
@@ -125,26 +125,24 @@ __device__ __noinline__ void eq_pass2_gen(uint32_t tm_x, uint8_t* X, int row, in
   }
 }
 
-// SiLU (h + h tanh h with h = x/2; the image is pre-scaled by 1/2) and the partial coord_mlp.2 dots over hidden units
-// [64 CQ, 64 CQ + 64); c0tab[k] = {b_k / 2, w2[0][k], w2[1][k], w2[2][k]} as kernel-parameter operands
+// SiLU (h + h tanh h with h = x/2; the image is pre-scaled by 1/2) of hidden units [64 CQ, 64 CQ + 64), written back to
+// tensor memory as packed fp16 pairs: the A operand of the coord_mlp.2 MMA (lane = row, column = two K elements).
+// b0h[k] = coord_mlp.0 bias / 2 as kernel-parameter operands.
 template <int CQ>
-__device__ __forceinline__ void eq_silu_dot(const EquiArgs& a, uint32_t tm_c, float4* dst) {
-  float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+__device__ __forceinline__ void eq_silu_tm(const EquiArgs& a, uint32_t tm_c, uint32_t tm_s) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     float x[16];
     tmem_ld16(tmem_addr(tm_c, 64 * CQ + 16 * c), x);
+    uint32_t pk[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int col = 64 * CQ + 16 * c + i;
-      const float h = x[i] + a.c0tab[4 * col];
-      const float s = fmaf(h, tanh_fast(h), h);
-      o0 = fmaf(s, a.c0tab[4 * col + 1], o0);
-      o1 = fmaf(s, a.c0tab[4 * col + 2], o1);
-      o2 = fmaf(s, a.c0tab[4 * col + 3], o2);
+    for (int i = 0; i < 16; i += 2) {
+      const float h0 = x[i] + a.b0h[64 * CQ + 16 * c + i], h1 = x[i + 1] + a.b0h[64 * CQ + 16 * c + i + 1];
+      pk[i >> 1] = pack_h2(fmaf(h0, tanh_fast(h0), h0), fmaf(h1, tanh_fast(h1), h1));
     }
+    tmem_st8(tmem_addr(tm_s, 32 * CQ + 8 * c), pk);
   }
-  *dst = make_float4(o0, o1, o2, 0.f);
+  tmem_wait_st();
 }
 
 __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ EquiArgs a) {
@@ -154,9 +152,8 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   uint8_t* U = smem + EQ_U;
   uint8_t* misc = smem + EQ_MISC;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // 0: coord_mlp.0 image, 1: e tile, 2: input_lin image, 3/5: MMA in (N halves), 4/6: MMA c0 (N halves)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 96);    // bars: ... 7: MMA coord_mlp.2, 8: its weight image
   float2* LNS = reinterpret_cast<float2*>(smem + EQ_LNS);
-  float4* DOT = reinterpret_cast<float4*>(smem + EQ_DOT);
   float4* C3 = reinterpret_cast<float4*>(smem + EQ_C3);
   uint32_t* gt_meta = reinterpret_cast<uint32_t*>(smem + EQ_GT);
   int* gt_node = reinterpret_cast<int*>(gt_meta + 64);
@@ -169,7 +166,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   const int tile1 = min(tile0 + per, a.p.n_tiles);
 
   if (t == 0) {
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
     if (tile0 < tile1) {
       mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
@@ -288,9 +285,13 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       }
       tmem_wait_st();
       if (cq < 2) mbar_wait(&bars[5], par);      // the scratch aliases the GBF chunk: the whole input_lin MMA must be done
-      if (t == 0 && tile + 1 < tile1) {          // U chunk 0 is consumed: prefetch the next e tile
-        mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
-        bulk_g2s(U, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 1) * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
+      if (t == 0) {
+        if (tile + 1 < tile1) {                  // U chunk 0 is consumed: prefetch the next e tile
+          mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
+          bulk_g2s(U, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 1) * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
+        }
+        mbar_expect_tx(&bars[8], 8192);          // the GBF chunk is consumed too: its tail takes the coord_mlp.2 image
+        bulk_g2s(smem + EQ_W2, a.w2_img, 8192, &bars[8]);
       }
       if (cq == 0 && r.valid && row == r.gs) { gt_meta[r.gi] = (uint32_t)r.gs | ((uint32_t)r.gl << 8); gt_node[r.gi] = r.g; }
       LNS[row * 4 + cq] = make_float2(s1, s2);
@@ -335,8 +336,8 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
     PHASE_MARK(6);
     tc_fence_after();
 
-    // ---- SiLU + coord_mlp.2 partial dots on CUDA cores
-    EQ_DISPATCH(eq_silu_dot, a, tm_c, &DOT[row * 4 + cq]);
+    // ---- SiLU -> fp16 A operand in tensor memory (the columns of x, dead since pass 2); coord_mlp.2 on the tensor core
+    EQ_DISPATCH(eq_silu_tm, a, tm_c, tm_x);
     if (t == 0) {                                // X is consumed once both halves are done: fetch the input_lin image for the next tile
       mbar_wait(&bars[6], par);
       if (tile + 1 < tile1) {
@@ -344,17 +345,29 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
         bulk_g2s(X, a.win_img, 65536, &bars[2]);
       }
     }
-    __syncthreads();
+    sync_tc();
     PHASE_MARK(7);
+    if (t == 0) {
+      mbar_wait(&bars[8], par);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_f16(16);
+#pragma unroll
+      for (int k = 0; k < 16; ++k)               // K = 16 per step = 8 columns of packed pairs
+        umma_f16_ts(tm_x + 128, tm_x + 8 * k, umma_desc_sw128(smem_u32(smem + EQ_W2) + (k >> 2) * 2048 + (k & 3) * 32), idesc, k ? 1u : 0u);
+      umma_commit(&bars[7]);
+    }
     if (cq == 0) {       // tanh, adjacency-weighted mean, coordinate contribution of this edge
-      const float4 p0 = DOT[row * 4], p1 = DOT[row * 4 + 1], p2 = DOT[row * 4 + 2], p3 = DOT[row * 4 + 3];
-      const float d0 = (p0.x + p1.x) + (p2.x + p3.x), d1 = (p0.y + p1.y) + (p2.y + p3.y), d2 = (p0.z + p1.z) + (p2.z + p3.z);
-      const float w = (tanh_fast(d0) + ((ex & 1) ? tanh_fast(d1) : 0.f) + ((ex & 2) ? tanh_fast(d2) : 0.f)) * (1.0f / 3.0f);
+      mbar_wait(&bars[7], par);
+      tc_fence_after();
+      float dd[16];
+      tmem_ld16(tmem_addr(tm_x, 128), dd);
+      const float w = (tanh_fast(dd[0]) + ((ex & 1) ? tanh_fast(dd[1]) : 0.f) + ((ex & 2) ? tanh_fast(dd[2]) : 0.f)) * (1.0f / 3.0f);
       const float dx = pg.x - pj.x, dy = pg.y - pj.y, dz = pg.z - pj.z;
       const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
       const float f = r.valid ? a.coord_scale * w / fmaxf(nrm, 1e-8f) : 0.f;
       C3[row] = make_float4(dx * f, dy * f, dz * f, 0.f);
     }
+    tc_fence_before();
     __syncthreads();
     // per-atom sums of the coordinate contributions: one warp per group, lanes over its rows, shuffle tree
     for (int gi = warp; gi < ng; gi += EQ_THREADS / 32) {
@@ -374,7 +387,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       }
     }
     // no barrier here: C3 and the group table are dedicated buffers that are rewritten only after the next tile's
-    // barriers; the scratch inside the GBF chunk (LNS, DOT) was last read before the barrier above
+    // barriers; the scratch inside the GBF chunk (LNS, coord_mlp.2 image) was last read before the barrier above
     PHASE_MARK(8);
     par ^= 1;
     }   // tile >= tile0

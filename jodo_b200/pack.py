@@ -295,8 +295,8 @@ def pack_model(sd, dims, device):
         pk.add(p + 'wc2', W(f'{b}.equi_update.coord_mlp.2'))                               # [3, 256]
         # SiLU(x) = h + h tanh(h) with h = x / 2: the factor 1/2 is exact in fp16, so it is folded into the image and bias
         pk.add(p + 'wc0h.img', weight_image_h(0.5 * W(f'{b}.equi_update.coord_mlp.0'), D))
-        pk.add_host(p + 'c0tab', torch.cat([0.5 * Bv(f'{b}.equi_update.coord_mlp.0')[:, None],
-                                            W(f'{b}.equi_update.coord_mlp.2').t()], dim=1).contiguous())   # [256, 4]
+        pk.add_host(p + 'b0h', 0.5 * Bv(f'{b}.equi_update.coord_mlp.0'))
+        pk.add(p + 'w2.img', weight_image_h(pad2(W(f'{b}.equi_update.coord_mlp.2'), 16, D), 16))          # N = 16 (3 real)
         pk.add_host(p + 'gbf4', _gbf_table4(sd, f'{b}.dist_layer', device))
         scales.append(sd[f'{b}.equi_update.coord_norm.scale'].reshape(()))
     pk.meta['coord_scale'] = [float(s) for s in torch.stack(scales).cpu()]

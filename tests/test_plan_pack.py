@@ -112,7 +112,8 @@ def test_pack_model_cpu(name):
     assert pk.meta['ld_tab'] % 256 == 0 and pk.meta['keh'] == 192
     for l in range(d.L):
         p = f'b{l}.'
-        assert len(pk.host[p + 'c0tab']) == 1024 and len(pk.host[p + 'gbf4']) == 256
+        assert len(pk.host[p + 'b0h']) == 256 and len(pk.host[p + 'gbf4']) == 256
+        assert pk[p + 'w2.img'].numel() * 4 == 16 * 256 * 2
         assert len(pk.host[p + 'ff3.b']) == 256 and len(pk.host[p + 'emb.b']) == 64
         assert pk[p + 'wc0h.img'].numel() * 4 == 256 * 256 * 2
         assert pk[p + 'ff3.img'].numel() * 4 == 64 * d.r * 64 * 2
