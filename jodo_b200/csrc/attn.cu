@@ -238,19 +238,58 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
     const uint4* vb = static_cast<const uint4*>(a.qkv) + (size_t)(64 + 16 * HALF) * a.ldq + r.j;
     H16 vc;
     vc.u[0] = __ldg(vb); vc.u[1] = __ldg(vb + a.ldq);
-    // (group, head): max, exp in place, 1 / (sum + 1e-16)      (PyG softmax, models/layers.py:178)
-    for (int it = lt; it < ng * 16; it += AT_GROUP) {
-      const int gi = it >> 4, h = it & 15;
-      const int gs = gt_meta[gi] & 255u, gl = (gt_meta[gi] >> 8) & 255u;
-      float m = -INFINITY;
-      for (int rr = gs; rr < gs + gl; ++rr) m = fmaxf(m, LG[rr * 17 + h]);
-      float s = 0.f;
-      for (int rr = gs; rr < gs + gl; ++rr) {
-        const float e = ex2_fast((LG[rr * 17 + h] - m) * 1.4426950408889634f);
-        LG[rr * 17 + h] = e;
-        s += e;
+    // (group, head): max, exp in place, 1 / (sum + 1e-16)      (PyG softmax, models/layers.py:178).
+    // Four lanes share one (group, head) and interleave its rows; ng * 64 is a whole number of warps.
+    // Long groups (>= 32 rows) sum in four interleaved partial sums combined as (s0 + s1) + (s2 + s3), short ones
+    // sequentially: the arithmetic depends on the group alone.  The work distribution depends on the tile: with few
+    // groups (<= 4: GEOM-sized molecules) four lanes share a (group, head) and take one partial sum each, otherwise
+    // one lane does it all  [same-box A/B: 8 % either way].
+    if (ng <= 4) {
+      for (int it = lt; it < ng * 64; it += AT_GROUP) {
+        const int sub = it & 3, gi = it >> 6, h = (it >> 2) & 15;
+        const int gs = gt_meta[gi] & 255u, gl = (gt_meta[gi] >> 8) & 255u;
+        const bool wide = gl >= 32;
+        const int r0 = gs + (wide ? sub : (sub == 0 ? 0 : gl)), st = wide ? 4 : 1;
+        float m = -INFINITY;
+        for (int rr = r0; rr < gs + gl; rr += st) m = fmaxf(m, LG[rr * 17 + h]);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        float sm = 0.f;
+        for (int rr = r0; rr < gs + gl; rr += st) {
+          const float e = ex2_fast((LG[rr * 17 + h] - m) * 1.4426950408889634f);
+          LG[rr * 17 + h] = e;
+          sm += e;
+        }
+        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+        if (sub == 0) GI[gi * 16 + h] = 1.0f / (sm + 1e-16f);
       }
-      GI[gi * 16 + h] = 1.0f / (s + 1e-16f);
+    } else {
+      for (int it = lt; it < ng * 16; it += AT_GROUP) {
+        const int gi = it >> 4, h = it & 15;
+        const int gs = gt_meta[gi] & 255u, gl = (gt_meta[gi] >> 8) & 255u;
+        float m = -INFINITY;
+        for (int rr = gs; rr < gs + gl; ++rr) m = fmaxf(m, LG[rr * 17 + h]);
+        float sm;
+        if (gl >= 32) {
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int rr = gs; rr < gs + gl; ++rr) {
+            const float e = ex2_fast((LG[rr * 17 + h] - m) * 1.4426950408889634f);
+            LG[rr * 17 + h] = e;
+            const int k = (rr - gs) & 3;
+            s4[0] += k == 0 ? e : 0.f; s4[1] += k == 1 ? e : 0.f; s4[2] += k == 2 ? e : 0.f; s4[3] += k == 3 ? e : 0.f;
+          }
+          sm = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        } else {
+          sm = 0.f;
+          for (int rr = gs; rr < gs + gl; ++rr) {
+            const float e = ex2_fast((LG[rr * 17 + h] - m) * 1.4426950408889634f);
+            LG[rr * 17 + h] = e;
+            sm += e;
+          }
+        }
+        GI[gi * 16 + h] = 1.0f / (sm + 1e-16f);
+      }
     }
     named_bar_sync(1 + c.grp, AT_GROUP);
     float alpha[8];
