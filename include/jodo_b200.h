@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 4
+#define JODO_ABI_VERSION 5
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -69,6 +69,8 @@ typedef struct jodo_imglinear_args {
   const float* gate; int ld_gate;         /* GATED_RES: gate[row_mol[row], col] */
   const int* row_mol;
   const int* nonuni;                      /* device flag of jodo_uniform_flag or null: 0 = read gate row 0 for every row */
+  const int* skip_if_zero;                /* device flag or null: when it reads 0 the launch does nothing (the per-molecule
+                                             AdaLN table under uniform conditioning: row 0 comes from jodo_rowlinear) */
   float* C32; int ldc32;                  /* fp32 row-major output or null */
   void* C16; int ldc16;                   /* fp16 row-major output or null (ld in elements) */
   int c16_piece_major;                    /* != 0: C16 is [N/8][ldc16 rows][8] -- 16-byte column pieces with the rows of one
@@ -191,6 +193,8 @@ int jodo_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const f
 int jodo_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
                     int off_shift, int off_scale, const jodo_plan* p, float* out32, int ldo, void* out_img, void* y_img,
                     const int* nonuni, void* stream);
+/* fp16 operand image of act(rows[M, K]) (row-major fp32, ld in elements, K % 64 == 0) for jodo_imglinear */
+int jodo_act_image(const float* rows, int ld, int M, int K, int act, void* img, void* stream);
 /* nonuni[0] = 1 if any row of rows[B, T] differs (bitwise) from row 0, else 0.  rows = the conditioning embedding
  * temb (noise level [+ context], reference models/mol_gnn.py:534, 728-734): the samplers broadcast one noise level
  * over the batch (sampling.py:549), in which case every per-molecule AdaLN row is the same row. */

@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 4:
+        if _lib.jodo_abi_version() != 5:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -132,18 +132,18 @@ class EdgeHeadArgs(ctypes.Structure):
 class ImgLinearArgs(ctypes.Structure):
     _fields_ = [('Aimg', _P), ('M', _I), ('K', _I), ('Wimg', _P), ('bias', _P), ('N', _I), ('NT', _I), ('epi', _I),
                 ('act_out', _I), ('aux', _P), ('ld_aux', _I), ('gate', _P), ('ld_gate', _I), ('row_mol', _P), ('nonuni', _P),
-                ('C32', _P), ('ldc32', _I), ('C16', _P), ('ldc16', _I), ('c16_piece_major', _I), ('Cimg', _P)]
+                ('skip_if_zero', _P), ('C32', _P), ('ldc32', _I), ('C16', _P), ('ldc16', _I), ('c16_piece_major', _I), ('Cimg', _P)]
 
 
 def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None, row_mol=None,
-              C32=None, C16=None, Cimg=None, stream=None, tag=None, nonuni=0):
+              C32=None, C16=None, Cimg=None, stream=None, tag=None, nonuni=0, skip_if_zero=0):
     """Persistent TMA-fed GEMM on an fp16 activation image (include/jodo_b200.h: jodo_imglinear).
     C32 / C16 are 2-D row-major views (stride(1) == 1) -- or C16 a contiguous 3-D [N/8, rows, 8] tensor for the
     piece-major layout the edge kernels gather from; Cimg a flat fp16 image buffer."""
     pm = C16 is not None and C16.dim() == 3          # piece-major fp16 output: tensor [N/8, rows, 8]
     a = ImgLinearArgs(dp(Aimg), M, K, dp(Wimg), dp(bias), N, NT, epi, act_out, dp(aux),
                       0 if aux is None else aux.stride(0), dp(gate), 0 if gate is None else gate.stride(0), dp(row_mol), nonuni,
-                      dp(C32), 0 if C32 is None else C32.stride(0), dp(C16),
+                      skip_if_zero, dp(C32), 0 if C32 is None else C32.stride(0), dp(C16),
                       0 if C16 is None else (C16.shape[1] if pm else C16.stride(0)), 1 if pm else 0, dp(Cimg))
     st = stream if stream is not None else stream_ptr()
     f = lib().jodo_imglinear

@@ -84,6 +84,10 @@ int jodo_imglinear(const jodo_imglinear_args* a, void* stream) {
   if (const char* m = jodo::check_imglinear(*a)) return fail(m);
   JODO_LAUNCH(jodo::launch_imglinear(*a, num_sms(), S(stream)), "jodo_imglinear");
 }
+int jodo_act_image(const float* rows, int ld, int M, int K, int act, void* img, void* stream) {
+  if (!rows || !img || M <= 0 || K <= 0 || (K % 64) || (ld % 4)) return fail("jodo_act_image: bad arguments");
+  JODO_LAUNCH(jodo::launch_act_image(rows, ld, M, K, act, img, S(stream)), "jodo_act_image");
+}
 int jodo_uniform_flag(const float* rows, int B, int T, int* nonuni, void* stream) {
   if (!rows || !nonuni || B <= 0 || T <= 0) return fail("jodo_uniform_flag: bad arguments");
   JODO_LAUNCH(jodo::launch_uniform_flag(rows, B, T, nonuni, S(stream)), "jodo_uniform_flag");

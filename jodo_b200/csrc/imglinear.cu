@@ -47,6 +47,7 @@ constexpr int il_mode(int epi, bool c32, bool c16, bool cimg) { return epi | (c3
 
 template <int MODE>
 __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
+  if (a.skip_if_zero && *a.skip_if_zero == 0) return;     // uniform conditioning: nothing to do (warp-uniform, before any setup)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nt = a.NT;

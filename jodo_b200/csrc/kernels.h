@@ -65,6 +65,7 @@ cudaError_t launch_ln_mod(int D, const float* x, int ldx, const float* y, int ld
 cudaError_t launch_ln_mod_img(const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
                               int off_shift, int off_scale, const Plan& p, float* out32, int ldo, void* out_img,
                               void* y_img, const int* nonuni, cudaStream_t st);
+cudaError_t launch_act_image(const float* rows, int ld, int M, int K, int act, void* img, cudaStream_t st);
 cudaError_t launch_uniform_flag(const float* rows, int B, int T, int* nonuni, cudaStream_t st);
 cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st);
 cudaError_t launch_nan_flag(const float* pos, int Nn, int* flag, cudaStream_t st);

@@ -160,6 +160,29 @@ __global__ void k_ln_mod_img(const float* __restrict__ x, int ldx, const float* 
   *reinterpret_cast<uint4*>(out_img + ioff) = pack8(o);
 }
 
+// fp16 operand image of act(rows[M, K]) (K % 64 == 0): [ceil(M/128)][K/64][128 rows][128 B]; padding rows are zero.
+// One thread per 16-byte piece.
+__global__ void k_act_image(const float* __restrict__ rows, int ld, int M, int K, int act, uint8_t* __restrict__ img) {
+  const int pieces_per_row = K / 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)((M + 127) / 128 * 128) * pieces_per_row;
+  if (i >= total) return;
+  const int r = (int)(i / pieces_per_row), p = (int)(i - (long long)r * pieces_per_row);
+  float v[8];
+  if (r < M) {
+    const float4 a = *reinterpret_cast<const float4*>(rows + (size_t)r * ld + 8 * p);
+    const float4 b = *reinterpret_cast<const float4*>(rows + (size_t)r * ld + 8 * p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = act == ACT_SILU ? silu_f(v[k]) : (act == ACT_GELU ? gelu_f(v[k]) : v[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+  }
+  const int tile = r >> 7, row = r & 127;
+  *reinterpret_cast<uint4*>(img + (size_t)tile * (K / 64) * CHUNK_BYTES_A + img_piece(row, p >> 3, p & 7, CHUNK_BYTES_A)) = pack8(v);
+}
+
 // nonuni |= any element of rows[B, T] differs bitwise from row 0
 __global__ void k_uniform_flag(const float* __restrict__ rows, int B, int T, int* __restrict__ nonuni) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,6 +295,11 @@ cudaError_t launch_ln_mod_img(const float* x, int ldx, const float* y, int ldy, 
   const int rows = (p.Nn + 127) / 128 * 128;
   k_ln_mod_img<<<rows / 8, 256, 0, st>>>(x, ldx, y, ldy, tab, ld_tab, off_gate, off_shift, off_scale, p.node_mol, p.Nn,
                                          out32, ldo, static_cast<uint8_t*>(out_img), static_cast<uint8_t*>(y_img), nonuni);
+  return LAUNCH_OK();
+}
+cudaError_t launch_act_image(const float* rows, int ld, int M, int K, int act, void* img, cudaStream_t st) {
+  const long long total = (long long)((M + 127) / 128 * 128) * (K / 8);
+  k_act_image<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rows, ld, M, K, act, static_cast<uint8_t*>(img));
   return LAUNCH_OK();
 }
 cudaError_t launch_uniform_flag(const float* rows, int B, int T, int* nonuni, cudaStream_t st) {

@@ -40,6 +40,7 @@ class _Workspace:
             self.c2 = f(B * d.cond_ch, D)
             self.ctx = f(B, T)
         self.tab = f(B, meta['ld_tab'])
+        self.temb_img = torch.zeros(((B + 127) // 128) * 128 * T, device=dev, dtype=torch.float16)
         self.kin = meta['node_emb']['K']
         self.xin = f(Nn, self.kin)                          # zero-padded to the GEMM's K by jodo_gather_nodes
         self.pos = [zf(Nn, 4), zf(Nn, 4)]
@@ -73,6 +74,8 @@ class _DGTBase(nn.Module):
         self.dims = dims_from_config(config)
         if self.dims.D != 256:
             raise NotImplementedError(f'jodo_b200 kernels are built for model.nf = 256 (got {self.dims.D})')
+        if self.dims.r not in (2, 4):
+            raise NotImplementedError(f'jodo_b200 edge kernels are built for model.mlp_ratio 2 or 4 (got {self.dims.r})')
         if self.dims.ce % 4 or self.dims.ce > 16:
             raise NotImplementedError('unsupported n_layers (edge hidden slice must be a multiple of 4 <= 16)')
         self.edge_th = float(config.model.edge_quan_th)
@@ -165,7 +168,14 @@ class _DGTBase(nn.Module):
         # flags[2] = 1 unless every molecule carries the same conditioning row (the samplers broadcast one noise level)
         _lib.call('jodo_uniform_flag', _lib.ptr(ws.temb), _c(B), _c(T), ctypes.c_void_p(ws.flags.data_ptr() + 8), st)
         nonuni = ws.flags.data_ptr() + 8
-        lin('tab', ws.temb, ws.tab, act_in=_lib.ACT_SILU, only_row0_if_zero=nonuni)
+        # all AdaLN rows: the first 128 molecules always (register-staged GEMM: row 0 serves the uniform fast path),
+        # every molecule through the persistent GEMM only when the conditioning is not uniform (device-side skip)
+        lin('tab', ws.temb, ws.tab, M=min(B, 128), act_in=_lib.ACT_SILU)
+        if B > 128:
+            _lib.call('jodo_act_image', _lib.ptr(ws.temb), _c(T), _c(B), _c(T), _c(_lib.ACT_SILU), _lib.ptr(ws.temb_img), st)
+            m = meta['tab']
+            _lib.imglinear(ws.temb_img, B, m['K'], pk['tab.img'], pk['tab.b'], m['N'], m['NT'], C32=ws.tab, stream=st,
+                           tag='jodo_imglinear:tab', skip_if_zero=nonuni)
         # ---- per atom: packed inputs, node embedding (slice 0 of the concatenated atom hiddens)
         _lib.call('jodo_gather_nodes', _lib.ptr(xh), _lib.ptr(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin),
                   _lib.ptr(ws.xin), _lib.ptr(ws.pos[0]), st)
