@@ -12,69 +12,74 @@ namespace jodo {
 namespace {
 
 constexpr int EH_KEH = 192;                       // concatenated width (64 + ce*L padded to a multiple of 64)
-constexpr int EH_IN = 0;                          // 48 KB: tile image (3 chunks of 64 columns)
-constexpr int EH_A2 = 3 * CHUNK_BYTES_A;          // 32 KB: SiLU(layer 0) (K = 128)
-constexpr int EH_W0 = EH_A2 + 2 * CHUNK_BYTES_A;  // 48 KB: layer-0 image, N=128, K=192
-constexpr int EH_W2 = EH_W0 + 3 * 128 * 128;      // 16 KB: layer-2 image, N=64, K=128
-constexpr int EH_MISC = EH_W2 + 2 * 64 * 128;
+constexpr int EH_THREADS = 256;                   // two independent groups of 4 warps, each walking its own tiles
+constexpr int EH_W0 = 0;                          // 48 KB: layer-0 image, N=128, K=192 (shared)
+constexpr int EH_W2 = EH_W0 + 3 * 128 * 128;      // 16 KB: layer-2 image, N=64, K=128 (shared)
+constexpr int EH_GRP = EH_W2 + 2 * 64 * 128;      // per group: 48 KB tile image (3 chunks of 64 columns) + 32 KB SiLU(layer 0)
+constexpr int EH_GBYTES = 5 * CHUNK_BYTES_A;
+constexpr int EH_MISC = EH_GRP + 2 * EH_GBYTES;
 constexpr int EH_SMEM = EH_MISC + 128 + (128 + 64 + 8 * 32 + 8) * 4;
 static_assert(EH_SMEM <= 232448, "shared memory budget");
 
-__global__ void __launch_bounds__(ET, 1) k_edge_head(EdgeHeadArgs a) {
+__global__ void __launch_bounds__(EH_THREADS, 1) k_edge_head(EdgeHeadArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
-  uint8_t* IN = smem + EH_IN;
-  uint8_t* A2 = smem + EH_A2;
+  const int grp = threadIdx.x >> 7;
+  uint8_t* IN = smem + EH_GRP + grp * EH_GBYTES;
+  uint8_t* A2 = IN + 3 * CHUNK_BYTES_A;
   uint8_t* misc = smem + EH_MISC;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // 0: weights, 1: tile, 2: MMA
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);   // 0: weights, 1,2: tile of group 0,1, 3,4: MMA of group 0,1
+  uint64_t* bar_t = &bars[1 + grp];
+  uint64_t* bar_m = &bars[3 + grp];
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 64);
   float* b0 = reinterpret_cast<float*>(misc + 128);     // [128]
   float* b2 = b0 + 128;                                 // [64]
   float* w4 = b2 + 64;                                  // [ch][32]
   float* b4 = w4 + 8 * 32;                              // [ch]
 
-  const int t = threadIdx.x;
+  const int t = threadIdx.x & 127;                     // thread inside the group = tile row
   const int ch = a.ch;
   const int per = (a.p.n_tiles + gridDim.x - 1) / gridDim.x;
-  const int tile0 = blockIdx.x * per;
-  const int tile1 = min(tile0 + per, a.p.n_tiles);
-  if (t == 0) {
-    for (int i = 0; i < 3; ++i) mbar_init(&bars[i], 1);
+  const int tile0 = blockIdx.x * per + grp;
+  const int tile1 = min(blockIdx.x * per + per, a.p.n_tiles);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
     mbar_expect_tx(&bars[0], 3 * 128 * 128 + 2 * 64 * 128);
     bulk_g2s(smem + EH_W0, a.w0_img, 3 * 128 * 128, &bars[0]);
     bulk_g2s(smem + EH_W2, a.w2_img, 2 * 64 * 128, &bars[0]);
-    if (tile0 < tile1) {
-      mbar_expect_tx(&bars[1], 3 * CHUNK_BYTES_A);
-      bulk_g2s(IN, reinterpret_cast<const uint8_t*>(a.eh) + (size_t)tile0 * a.eh_tile_bytes, 3 * CHUNK_BYTES_A, &bars[1]);
-    }
   }
-  b0[t] = a.b0[t];
-  if (t < 64) b2[t] = a.b2[t];
-  for (int i = t; i < ch * 32; i += ET) w4[i] = a.w4[i];
-  if (t < ch) b4[t] = a.b4[t];
-  if (t < 32) tmem_alloc<256>(tmem_slot);
+  if (threadIdx.x < 128) b0[threadIdx.x] = a.b0[threadIdx.x];
+  if (threadIdx.x < 64) b2[threadIdx.x] = a.b2[threadIdx.x];
+  for (int i = threadIdx.x; i < ch * 32; i += EH_THREADS) w4[i] = a.w4[i];
+  if (threadIdx.x < ch) b4[threadIdx.x] = a.b4[threadIdx.x];
+  if (threadIdx.x < 32) tmem_alloc<512>(tmem_slot);
   sync_tc();
-  const uint32_t tmem = *tmem_slot;
+  if (t == 0 && tile0 < tile1) {
+    mbar_expect_tx(bar_t, 3 * CHUNK_BYTES_A);
+    bulk_g2s(IN, reinterpret_cast<const uint8_t*>(a.eh) + (size_t)tile0 * a.eh_tile_bytes, 3 * CHUNK_BYTES_A, bar_t);
+  }
+  const uint32_t tmem = *tmem_slot + 256u * grp;
   uint32_t par_t = 0, par_m = 0;
   const int N = a.p.N;
+  auto group_sync = [&]() { tc_fence_before(); named_bar_sync(1 + grp, 128); tc_fence_after(); };
 
-  for (int tile = tile0; tile < tile1; ++tile) {
+  for (int tile = tile0; tile < tile1; tile += 2) {
     const RowInfo r = load_row(a.p, tile, t);
     if (t == 0) {
       if (tile == tile0) mbar_wait(&bars[0], 0);
-      mbar_wait(&bars[1], par_t);
+      mbar_wait(bar_t, par_t);
       tc_fence_after();
       mma_tile_h(tmem, smem_u32(IN), smem_u32(smem + EH_W0), 128, 3, false);
-      umma_commit(&bars[2]);
+      umma_commit(bar_m);
     }
     par_t ^= 1;
-    mbar_wait(&bars[2], par_m);
+    mbar_wait(bar_m, par_m);
     par_m ^= 1;
     tc_fence_after();
-    if (t == 0 && tile + 1 < tile1) {      // the tile region is free: fetch the next one
-      mbar_expect_tx(&bars[1], 3 * CHUNK_BYTES_A);
-      bulk_g2s(IN, reinterpret_cast<const uint8_t*>(a.eh) + (size_t)(tile + 1) * a.eh_tile_bytes, 3 * CHUNK_BYTES_A, &bars[1]);
+    if (t == 0 && tile + 2 < tile1) {      // the tile region is free: fetch this group's next one
+      mbar_expect_tx(bar_t, 3 * CHUNK_BYTES_A);
+      bulk_g2s(IN, reinterpret_cast<const uint8_t*>(a.eh) + (size_t)(tile + 2) * a.eh_tile_bytes, 3 * CHUNK_BYTES_A, bar_t);
     }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
@@ -85,12 +90,12 @@ __global__ void __launch_bounds__(ET, 1) k_edge_head(EdgeHeadArgs a) {
       st_rowh<32>(A2, t, c >> 1, 4 * (c & 1), x);
     }
     fence_async_smem();
-    sync_tc();
+    group_sync();
     if (t == 0) {
       mma_tile_h(tmem + 128, smem_u32(A2), smem_u32(smem + EH_W2), 64, 2, false);
-      umma_commit(&bars[2]);
+      umma_commit(bar_m);
     }
-    mbar_wait(&bars[2], par_m);
+    mbar_wait(bar_m, par_m);
     par_m ^= 1;
     tc_fence_after();
     {
@@ -116,11 +121,11 @@ __global__ void __launch_bounds__(ET, 1) k_edge_head(EdgeHeadArgs a) {
         for (int k = 0; k < 8; ++k) if (k < ch) dst[k] = o[k] + b4[k];
       }
     }
-    sync_tc();
+    group_sync();
   }
-  if (tile0 >= tile1 && t == 0) mbar_wait(&bars[0], 0);
+  if (threadIdx.x == 0) mbar_wait(&bars[0], 0);          // never leave with the weight copies in flight
   sync_tc();
-  if (t < 32) tmem_dealloc<256>(tmem);
+  if (threadIdx.x < 32) tmem_dealloc<512>(*tmem_slot);
 }
 
 }  // namespace
@@ -133,8 +138,8 @@ cudaError_t launch_edge_head(const EdgeHeadArgs& a, int num_sms, cudaStream_t st
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  const int grid = a.p.n_tiles < num_sms ? a.p.n_tiles : num_sms;
-  k_edge_head<<<grid, ET, EH_SMEM, st>>>(a);
+  const int grid = a.p.n_tiles < 2 * num_sms ? (a.p.n_tiles + 1) / 2 : num_sms;
+  k_edge_head<<<grid, EH_THREADS, EH_SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
