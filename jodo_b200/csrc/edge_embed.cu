@@ -23,7 +23,8 @@ __global__ void k_dist_flag(Plan p, const float* __restrict__ cond_x, int w, int
 
 constexpr int EE_A = 0;                       // A operand: 3 chunks (K = 96) = 48 KB
 constexpr int EE_W = 3 * CHUNK_BYTES_A;       // weight image: 3 chunks x 64 rows x 128 B = 24 KB
-constexpr int EE_MISC = EE_W + 3 * 64 * 128;
+constexpr int EE_OUT = EE_W + 3 * 64 * 128;   // 16 KB: fp16 operand image of the embedded tile, bulk-stored to e16 and eh
+constexpr int EE_MISC = EE_OUT + CHUNK_BYTES_A;
 constexpr int EE_SMEM = EE_MISC + 64 + 64 + 768 + 256;
 
 __global__ void __launch_bounds__(ET, 1) k_edge_embed(EdgeEmbedArgs a) {
@@ -127,10 +128,22 @@ __global__ void __launch_bounds__(ET, 1) k_edge_embed(EdgeEmbedArgs a) {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a.e32) + (size_t)tile * E_TILE_BYTES) + t;
 #pragma unroll
     for (int p = 0; p < 16; ++p) dst[p * 128] = make_float4(e[4 * p], e[4 * p + 1], e[4 * p + 2], e[4 * p + 3]);
-    st_rowh<64>(reinterpret_cast<uint8_t*>(a.e16) + (size_t)tile * CHUNK_BYTES_A, t, 0, 0, e);
-    st_rowh<64>(reinterpret_cast<uint8_t*>(a.eh) + (size_t)tile * a.eh_tile_bytes, t, 0, 0, e);
+    // fp16 copies through shared memory: one image, two bulk stores (row-per-thread global stores touch 32 lines each)
+    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // previous tile's stores have read OUT
+    __syncthreads();
+    st_rowh<64>(smem + EE_OUT, t, 0, 0, e);
+    fence_async_smem();
     sync_tc();
+    if (t == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint8_t*>(a.e16) + (size_t)tile * CHUNK_BYTES_A),
+                   "r"(smem_u32(smem + EE_OUT)), "r"((uint32_t)CHUNK_BYTES_A) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint8_t*>(a.eh) + (size_t)tile * a.eh_tile_bytes),
+                   "r"(smem_u32(smem + EE_OUT)), "r"((uint32_t)CHUNK_BYTES_A) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
   }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncthreads();
   if (t < 32) tmem_dealloc<64>(tmem);
 }
 
