@@ -188,6 +188,27 @@ def run_dpm_case(ref):
     print('qm9_cond_dpm_chain:', tuple(x.shape), tuple(ex.shape), len(rec), 'noise draws', float(x.abs().max()))
 
 
+def run_postprocess_case(ref):
+    """post_process + mol_process of the reference (sampling.py:12-97) on a QM9-shaped and a GEOM-shaped final state."""
+    import importlib
+    out = {}
+    for cfg_name, fname in (('qm9_uncond', 'vpsde_qm9_uncond_jodo'), ('geom_l8', 'vpsde_geom_uncond_jodo')):
+        ours = configs.NAMED[cfg_name]()
+        rcfg = ref_loader.load_config(fname)
+        b = synth.make_batch(ours, 6, seed=31, max_n=40)
+        xh = b['xh'] * 0.8
+        ex = b['edge_x'] * 0.9
+        inv = ref.utils.get_data_inverse_scaler(rcfg)
+        pos, one_hot, fc, edge = ref.sampling.post_process(xh.clone(), rcfg.data.atom_types, rcfg.model.include_fc_charge,
+                                                           b['node_mask'], inv, ex.clone(), b['edge_mask'],
+                                                           rcfg.data.compress_edge)
+        mols = ref.sampling.mol_process(one_hot, pos, fc, b['n_nodes'], edge)
+        out[cfg_name] = dict(xh=xh, edge_x=ex, node_mask=b['node_mask'], edge_mask=b['edge_mask'], n_nodes=b['n_nodes'],
+                             pos=pos, one_hot=one_hot, fc=fc, edge=edge, mols=mols)
+    torch.save(out, os.path.join(GOLD, 'postprocess.pt'))
+    print('postprocess:', {k: tuple(v['edge'].shape) for k, v in out.items()})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -200,6 +221,8 @@ def main():
         run_sampler_case(ref)
     if not only or 'dpm' in only:
         run_dpm_case(ref)
+    if not only or 'post' in only:
+        run_postprocess_case(ref)
 
 
 if __name__ == '__main__':
