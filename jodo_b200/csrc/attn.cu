@@ -107,7 +107,7 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
     {
       const float gsc = UNI ? c_atmod[128] : tr[tab_gbf(D_)], gsh = UNI ? c_atmod[129] : tr[tab_gbf(D_) + 1];
       const float d = sq_dist(pos[r.j], pos[r.g]);
-      const float x = fmaf(d, gsc, d) + gsh;
+      const float x = fmaf(d, gsc, gsh);                  // the table stores 1 + scale
       float df[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -177,7 +177,7 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
         const float n = fmaf(x[i], rstd, nmr);
         const float sc = UNI ? c_atmod[64 + col] : scv[i];
         const float sh = UNI ? c_atmod[col] : shv[i];
-        x[i] = fmaf(n, sc, n) + sh;
+        x[i] = fmaf(n, sc, sh);
       }
       st_rowh<32>(A0, row, 0, 4 * HALF, x);
     }

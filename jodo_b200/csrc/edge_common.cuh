@@ -120,7 +120,7 @@ __device__ __forceinline__ float gbf_one(float x, const float* __restrict__ c, i
   return ex2_fast(-(w * w)) * c[128 + k];
 }
 __device__ __forceinline__ void gbf_eval(float d, float scale, float shift, const float* __restrict__ c, float (&out)[64]) {
-  const float x = fmaf(d, scale, d) + shift;
+  const float x = fmaf(d, scale, shift);               // `scale` is the table's 1 + scale
   out[0] = x;
 #pragma unroll
   for (int k = 0; k < 63; ++k) out[1 + k] = gbf_one(x, c, k);
@@ -128,7 +128,7 @@ __device__ __forceinline__ void gbf_eval(float d, float scale, float shift, cons
 // columns [32*half, 32*half + 32) of the same feature row (two threads share one edge row)
 __device__ __forceinline__ void gbf_eval_half(float d, float scale, float shift, const float* __restrict__ c, int half,
                                               float (&out)[32]) {
-  const float x = fmaf(d, scale, d) + shift;
+  const float x = fmaf(d, scale, shift);               // `scale` is the table's 1 + scale
   if (half == 0) {
     out[0] = x;
 #pragma unroll
@@ -144,7 +144,7 @@ __device__ __forceinline__ void gbf_eval_half(float d, float scale, float shift,
 template <int N>
 __device__ __forceinline__ void gbf_eval_cols(float d, float scale, float shift, const float4* __restrict__ g4, int col0,
                                               float (&out)[N]) {
-  const float x = fmaf(d, scale, d) + shift;
+  const float x = fmaf(d, scale, shift);               // `scale` is the table's 1 + scale
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const float4 c = g4[col0 + i];
@@ -198,10 +198,10 @@ __device__ __forceinline__ void ln_mod64(float (&x)[64], const float* __restrict
   for (int i = 0; i < 64; i += 4) {
     const float4 sh = *reinterpret_cast<const float4*>(shift + i);
     const float4 sc = *reinterpret_cast<const float4*>(scale + i);
-    x[i] = (x[i] - mean) * rstd * (1.0f + sc.x) + sh.x;
-    x[i + 1] = (x[i + 1] - mean) * rstd * (1.0f + sc.y) + sh.y;
-    x[i + 2] = (x[i + 2] - mean) * rstd * (1.0f + sc.z) + sh.z;
-    x[i + 3] = (x[i + 3] - mean) * rstd * (1.0f + sc.w) + sh.w;
+    x[i] = (x[i] - mean) * rstd * sc.x + sh.x;
+    x[i + 1] = (x[i + 1] - mean) * rstd * sc.y + sh.y;
+    x[i + 2] = (x[i + 2] - mean) * rstd * sc.z + sh.z;
+    x[i + 3] = (x[i + 3] - mean) * rstd * sc.w + sh.w;
   }
 }
 

@@ -109,7 +109,7 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
         const float n = fmaf(e2[i], rstd, nmr);
         const float sc = UNI ? c_eumod[4 * ED_ + col] : scv[i];
         const float sh = UNI ? c_eumod[3 * ED_ + col] : shv[i];
-        e2[i] = fmaf(n, sc, n) + sh;               // padding rows carry finite garbage until the final select
+        e2[i] = fmaf(n, sc, sh);               // padding rows carry finite garbage until the final select
       }
       st_rowh<32>(c.A, row, 0, 4 * HALF, e2);
     }

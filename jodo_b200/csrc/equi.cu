@@ -62,7 +62,7 @@ __constant__ float c_eqmod[528];
 // distance features, columns [16 CQ, 16 CQ + 16) of the GBF chunk; constants are kernel-parameter operands
 template <int CQ>
 __device__ __forceinline__ void eq_gbf(const EquiArgs& a, float d, float scale, float shift, uint4 (&out)[2]) {
-  const float x = fmaf(d, scale, d) + shift;
+  const float x = fmaf(d, scale, shift);               // the table stores 1 + scale
   float df[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -94,7 +94,7 @@ __device__ __forceinline__ void eq_pass2_t(uint32_t tm_x, uint8_t* X, int row, f
     for (int i = 0; i < 16; ++i) {
       const int col = 64 * CQ + 16 * c + i;
       const float n = fmaf(x[i], rstd, nmr);
-      x[i] = fmaf(n, c_eqmod[256 + col], n) + c_eqmod[col];
+      x[i] = fmaf(n, c_eqmod[256 + col], c_eqmod[col]);
     }
     st_rowh<16>(X, row, CQ, 2 * c, x);
   }
@@ -116,10 +116,10 @@ __device__ __noinline__ void eq_pass2_gen(uint32_t tm_x, uint8_t* X, int row, in
       const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + i));
       const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + i));
       const float n0 = fmaf(x[i], rstd, nmr), n1 = fmaf(x[i + 1], rstd, nmr), n2 = fmaf(x[i + 2], rstd, nmr), n3 = fmaf(x[i + 3], rstd, nmr);
-      x[i] = fmaf(n0, sc.x, n0) + sh.x;
-      x[i + 1] = fmaf(n1, sc.y, n1) + sh.y;
-      x[i + 2] = fmaf(n2, sc.z, n2) + sh.z;
-      x[i + 3] = fmaf(n3, sc.w, n3) + sh.w;
+      x[i] = fmaf(n0, sc.x, sh.x);
+      x[i + 1] = fmaf(n1, sc.y, sh.y);
+      x[i + 2] = fmaf(n2, sc.z, sh.z);
+      x[i + 3] = fmaf(n3, sc.w, sh.w);
     }
     st_rowh<16>(X, row, cq, 2 * c, x);
   }

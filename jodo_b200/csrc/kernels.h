@@ -30,6 +30,7 @@ const char* check_imglinear(const ImgLinearArgs& a);
 cudaError_t launch_imglinear(const ImgLinearArgs& a, int num_sms, cudaStream_t stream);
 
 // ---- per-molecule AdaLN table layout (floats from the start of a molecule's table row) -------------
+// Every `scale` entry holds 1 + scale (the packer adds 1 to the bias of those columns), so modulation is one FMA.
 // [0,2)  model-level GBF (scale, shift); then per layer l at TAB_HEAD + l*tab_layer_stride(D):
 //   node  shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp   (6 x D)
 //   edge  shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp   (6 x ed)

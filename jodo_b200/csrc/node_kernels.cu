@@ -92,7 +92,7 @@ __global__ void k_ln_mod(const float* __restrict__ x, int ldx, const float* __re
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     int c = lane + 32 * i;
-    out[(size_t)v * ldo + c] = (a[i] - mean) * rstd * (1.0f + t[off_scale + c]) + t[off_shift + c];
+    out[(size_t)v * ldo + c] = (a[i] - mean) * rstd * t[off_scale + c] + t[off_shift + c];
   }
 }
 
@@ -152,7 +152,7 @@ __global__ void k_ln_mod_img(const float* __restrict__ x, int ldx, const float* 
   const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
   float o[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = (a[i] - mean) * rstd * (1.0f + sc[i]) + sh[i];
+  for (int i = 0; i < 8; ++i) o[i] = (a[i] - mean) * rstd * sc[i] + sh[i];            // the table stores 1 + scale
   if (out32) {
     *reinterpret_cast<float4*>(out32 + (size_t)v * ldo + c0) = make_float4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<float4*>(out32 + (size_t)v * ldo + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);

@@ -123,7 +123,7 @@ def test_ln_mod_img_matches_torch():
     torch.cuda.synchronize()
     t = tab[plan.node_mol.long()]
     z = x + t[:, :256] * y
-    ref = torch.nn.functional.layer_norm(z, (D,), eps=1e-6) * (1 + t[:, 512:768]) + t[:, 256:512]
+    ref = torch.nn.functional.layer_norm(z, (D,), eps=1e-6) * t[:, 512:768] + t[:, 256:512]      # the table holds 1 + scale
     assert float((out32 - ref).abs().max()) < 2e-5
     rows = image_rows(oimg, D)
     assert float((rows[:Nn] - ref).abs().max()) < 4e-3 * float(ref.abs().max())
