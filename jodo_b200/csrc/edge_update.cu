@@ -27,7 +27,10 @@ constexpr int EU_GROUP = 256;
 __host__ __device__ constexpr int eu_w3() { return 0; }
 __host__ __device__ constexpr int eu_w4(int r) { return r * 8192; }
 __host__ __device__ constexpr int eu_wl(int r) { return 2 * r * 8192; }
-__host__ __device__ constexpr int eu_grp(int r, int g) { return 2 * r * 8192 + 2048 + g * 49152; }
+// r = 2: each group also owns a 32 KB buffer into which its next fp32 edge tile is bulk-copied one tile ahead
+// (r = 4 has no room for it and loads the rows directly)
+__host__ __device__ constexpr int eu_gbytes(int r) { return r == 2 ? 49152 + 32768 : 49152; }
+__host__ __device__ constexpr int eu_grp(int r, int g) { return 2 * r * 8192 + 2048 + g * eu_gbytes(r); }
 __host__ __device__ constexpr int eu_misc(int r) { return eu_grp(r, 2); }
 __host__ __device__ constexpr int eu_smem(int r) { return eu_misc(r) + 128 + 2 * 128 * 2 * 8; }
 
@@ -46,7 +49,7 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 
 struct GroupCtx {
   uint8_t* A; uint8_t* A2; const uint8_t* W3; const uint8_t* W4; const uint8_t* WL;
-  uint64_t* bar_w; uint64_t* bar_m; float2* LNS;
+  uint64_t* bar_w; uint64_t* bar_m; uint64_t* bar_e; float2* LNS; uint8_t* EA;
   uint32_t tm_f, tm_y, tm_l;
   int grp, lt, row, tile0, tile1;
 };
@@ -56,14 +59,24 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
   constexpr int C0 = 32 * HALF;
   constexpr int NCH = R / 2;                      // hidden chunks of 128 units
   const int row = c.row, lt = c.lt;
-  uint32_t par_m = 0;
+  uint32_t par_m = 0, par_e = 0;
   uint8_t* e32 = reinterpret_cast<uint8_t*>(a.e32);
+  if (R == 2 && lt == 0 && c.tile0 < c.tile1) {
+    mbar_expect_tx(c.bar_e, E_TILE_BYTES);
+    bulk_g2s(c.EA, e32 + (size_t)c.tile0 * E_TILE_BYTES, E_TILE_BYTES, c.bar_e);
+  }
   RowInfo rn = load_row(a.p, min(c.tile0, a.p.n_tiles - 1), row);      // row metadata is fetched one tile ahead
   for (int tile = c.tile0; tile < c.tile1; tile += 2) {
     const RowInfo r = rn;
     // ---- loads of this tile: fp32 e (own 32 columns, piece-major tile), P[g], P[j] (piece-major fp16)
     float4 ev[8];
-    {
+    if (R == 2) {                                  // staged tile: [16 pieces][128 rows][16 B], conflict-free row reads
+      mbar_wait(c.bar_e, par_e);
+      par_e ^= 1;
+      const float4* src = reinterpret_cast<const float4*>(c.EA) + (8 * HALF) * 128 + row;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) ev[p] = src[p * 128];
+    } else {
       const float4* src = reinterpret_cast<const float4*>(e32 + (size_t)tile * E_TILE_BYTES) + (8 * HALF) * 128 + row;
 #pragma unroll
       for (int p = 0; p < 8; ++p) ev[p] = src[p * 128];
@@ -97,6 +110,10 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
       c.LNS[row * 2 + HALF] = make_float2(s, q);
       if (lt == 0) bulk_wait_read();               // the previous tile's bulk store has finished reading A
       named_bar_sync(1 + c.grp, EU_GROUP);
+      if (R == 2 && lt == 0 && tile + 2 < c.tile1) {   // the staged tile is consumed: fetch this group's next one
+        mbar_expect_tx(c.bar_e, E_TILE_BYTES);
+        bulk_g2s(c.EA, e32 + (size_t)(tile + 2) * E_TILE_BYTES, E_TILE_BYTES, c.bar_e);
+      }
       const float2 o = c.LNS[row * 2 + (HALF ^ 1)];
       const float mean = (s + o.x) * (1.0f / 64.0f);
       const float rstd = rsqrtf(fmaxf((q + o.y) * (1.0f / 64.0f) - mean * mean, 0.f) + 1e-6f);
@@ -212,7 +229,7 @@ __global__ void __launch_bounds__(EU_THREADS, 1) k_edge_update(const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
   uint8_t* misc = smem + eu_misc(R);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);     // 0: weights, 1,2: MMA of group 0,1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);     // 0: weights, 1,2: MMA of group 0,1, 3,4: staged e tile of group 0,1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 64);
   const int t = threadIdx.x, warp = t >> 5;
   const int grp = t >> 8, lt = t & 255, lw = lt >> 5;
@@ -221,7 +238,7 @@ __global__ void __launch_bounds__(EU_THREADS, 1) k_edge_update(const __grid_cons
   const int tile1 = min(tile0 + per, a.p.n_tiles);
 
   if (t == 0) {
-    for (int i = 0; i < 3; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
     mbar_expect_tx(&bars[0], 2 * R * 8192 + 2048);
     bulk_g2s(smem + eu_w3(), a.w3_img, R * 8192, &bars[0]);
@@ -237,7 +254,8 @@ __global__ void __launch_bounds__(EU_THREADS, 1) k_edge_update(const __grid_cons
   c.A = smem + eu_grp(R, grp);
   c.A2 = c.A + 16384;
   c.W3 = smem + eu_w3(); c.W4 = smem + eu_w4(R); c.WL = smem + eu_wl(R);
-  c.bar_w = &bars[0]; c.bar_m = &bars[1 + grp];
+  c.bar_w = &bars[0]; c.bar_m = &bars[1 + grp]; c.bar_e = &bars[3 + grp];
+  c.EA = c.A + 49152;
   c.LNS = reinterpret_cast<float2*>(misc + 128) + grp * 256;
   c.tm_f = tmem; c.tm_y = tmem + 128; c.tm_l = tmem + 192;
   c.grp = grp; c.lt = lt; c.row = (lw & 3) * 32 + (t & 31);
