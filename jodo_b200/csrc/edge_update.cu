@@ -27,12 +27,11 @@ constexpr int EU_GROUP = 256;
 __host__ __device__ constexpr int eu_w3() { return 0; }
 __host__ __device__ constexpr int eu_w4(int r) { return r * 8192; }
 __host__ __device__ constexpr int eu_wl(int r) { return 2 * r * 8192; }
-// r = 2: each group also owns a 32 KB buffer into which its next fp32 edge tile is bulk-copied one tile ahead
-// (r = 4 has no room for it and loads the rows directly)
-__host__ __device__ constexpr int eu_gbytes(int r) { return r == 2 ? 49152 + 32768 : 49152; }
+// each group also owns a 32 KB buffer into which its next fp32 edge tile is bulk-copied one tile ahead
+__host__ __device__ constexpr int eu_gbytes(int r) { return 49152 + 32768; }
 __host__ __device__ constexpr int eu_grp(int r, int g) { return 2 * r * 8192 + 2048 + g * eu_gbytes(r); }
 __host__ __device__ constexpr int eu_misc(int r) { return eu_grp(r, 2); }
-__host__ __device__ constexpr int eu_smem(int r) { return eu_misc(r) + 128 + 2 * 128 * 2 * 8; }
+__host__ __device__ constexpr int eu_smem(int r) { return eu_misc(r) + 128; }     // r = 4: 226 KB + 128 B
 
 __device__ __forceinline__ void group_sync(int grp) {        // group-local barrier that also orders tcgen05 traffic
   tc_fence_before();
@@ -61,7 +60,7 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
   const int row = c.row, lt = c.lt;
   uint32_t par_m = 0, par_e = 0;
   uint8_t* e32 = reinterpret_cast<uint8_t*>(a.e32);
-  if (R == 2 && lt == 0 && c.tile0 < c.tile1) {
+  if (lt == 0 && c.tile0 < c.tile1) {
     mbar_expect_tx(c.bar_e, E_TILE_BYTES);
     bulk_g2s(c.EA, e32 + (size_t)c.tile0 * E_TILE_BYTES, E_TILE_BYTES, c.bar_e);
   }
@@ -70,14 +69,10 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
     const RowInfo r = rn;
     // ---- loads of this tile: fp32 e (own 32 columns, piece-major tile), P[g], P[j] (piece-major fp16)
     float4 ev[8];
-    if (R == 2) {                                  // staged tile: [16 pieces][128 rows][16 B], conflict-free row reads
+    {                                              // staged tile: [16 pieces][128 rows][16 B], conflict-free row reads
       mbar_wait(c.bar_e, par_e);
       par_e ^= 1;
       const float4* src = reinterpret_cast<const float4*>(c.EA) + (8 * HALF) * 128 + row;
-#pragma unroll
-      for (int p = 0; p < 8; ++p) ev[p] = src[p * 128];
-    } else {
-      const float4* src = reinterpret_cast<const float4*>(e32 + (size_t)tile * E_TILE_BYTES) + (8 * HALF) * 128 + row;
 #pragma unroll
       for (int p = 0; p < 8; ++p) ev[p] = src[p * 128];
     }
@@ -110,7 +105,7 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
       c.LNS[row * 2 + HALF] = make_float2(s, q);
       if (lt == 0) bulk_wait_read();               // the previous tile's bulk store has finished reading A
       named_bar_sync(1 + c.grp, EU_GROUP);
-      if (R == 2 && lt == 0 && tile + 2 < c.tile1) {   // the staged tile is consumed: fetch this group's next one
+      if (lt == 0 && tile + 2 < c.tile1) {       // the staged tile is consumed: fetch this group's next one
         mbar_expect_tx(c.bar_e, E_TILE_BYTES);
         bulk_g2s(c.EA, e32 + (size_t)(tile + 2) * E_TILE_BYTES, E_TILE_BYTES, c.bar_e);
       }
@@ -256,7 +251,7 @@ __global__ void __launch_bounds__(EU_THREADS, 1) k_edge_update(const __grid_cons
   c.W3 = smem + eu_w3(); c.W4 = smem + eu_w4(R); c.WL = smem + eu_wl(R);
   c.bar_w = &bars[0]; c.bar_m = &bars[1 + grp]; c.bar_e = &bars[3 + grp];
   c.EA = c.A + 49152;
-  c.LNS = reinterpret_cast<float2*>(misc + 128) + grp * 256;
+  c.LNS = reinterpret_cast<float2*>(c.A2);           // LayerNorm partial sums live in A2, which is rewritten only later (SiLU)
   c.tm_f = tmem; c.tm_y = tmem + 128; c.tm_l = tmem + 192;
   c.grp = grp; c.lt = lt; c.row = (lw & 3) * 32 + (t & 31);
   c.tile0 = tile0 + grp; c.tile1 = tile1;
