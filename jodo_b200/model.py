@@ -22,6 +22,30 @@ from .params import build_param_tree, check_supported, dims_from_config, param_s
 from .plan import Plan
 
 _c = ctypes.c_int
+_WEIGHT_EPOCH = [0]
+
+
+def invalidate_packed_weights():
+    """Make every jodo_b200 module re-derive its packed weight images at its next call."""
+    _WEIGHT_EPOCH[0] += 1
+
+
+def watch_data_writers(cls, names=('copy_to', 'restore')):
+    """Wrap methods that write parameters through ``.data`` (reference models/ema.py:44-55, 66-77:
+    ``ExponentialMovingAverage.copy_to`` / ``restore``) so that the packed images are invalidated after each call."""
+    for name in names:
+        fn = getattr(cls, name)
+        if getattr(fn, '_jodo_watched', False):
+            continue
+
+        def wrapped(*a, __fn=fn, **k):
+            try:
+                return __fn(*a, **k)
+            finally:
+                invalidate_packed_weights()
+        wrapped._jodo_watched = True
+        wrapped.__name__, wrapped.__doc__ = getattr(fn, '__name__', name), fn.__doc__
+        setattr(cls, name, wrapped)
 
 
 class _Workspace:
@@ -90,13 +114,44 @@ class _DGTBase(nn.Module):
         self.debug = None          # set to a dict to capture intermediates (tests)
 
     # ---- caches -------------------------------------------------------------------------------------
+    def refresh_weights(self):
+        """Drop the packed weight images; the next call re-derives them from the parameters."""
+        self._packed = None
+        self._fp_pending = None
+
+    @staticmethod
+    def _fingerprint(params):
+        return torch.stack(torch._foreach_norm(params))          # one 2-norm per parameter tensor, on the device
+
     def _weights(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Packed fp16 operand images of the parameters.  They are re-derived when a parameter is replaced or written
+        in place through the tensor itself (optimizer steps, ``load_state_dict``, ``p.copy_``: ``_version`` changes) or
+        after ``refresh_weights()`` / ``invalidate_packed_weights()``.  Writes through ``p.data`` (the reference's
+        ``ExponentialMovingAverage.copy_to`` / ``restore``, models/ema.py:55, 77) bypass the version counter;
+        wrap those with ``watch_data_writers``.  As a backstop every call enqueues a fingerprint of the parameters
+        (no host sync); a later call that finds it different from the one taken at pack time raises."""
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params) + (_WEIGHT_EPOCH[0],)
+        pend = getattr(self, '_fp_pending', None)
+        if pend is not None and pend.query():
+            self._fp_pending = None
+            if self._packed is not None and key == self._packed_key and not torch.equal(self._fp_host, self._packed_fp):
+                self._packed = None
+                raise _lib.JodoError('parameters were modified through .data after the weight images were packed, so '
+                                     'earlier calls used stale weights; call model.refresh_weights() after such writes '
+                                     '(or wrap the writer with jodo_b200.model.watch_data_writers)')
         if self._packed is None or key != self._packed_key:
             sd = {k: v for k, v in self.state_dict().items()}
-            dev = next(self.parameters()).device
+            dev = params[0].device
             self._packed = pack_model(sd, self.dims, dev)
             self._packed_key = key
+            self._packed_fp = self._fingerprint(params).cpu()
+            self._fp_host = torch.empty_like(self._packed_fp).pin_memory()
+            self._fp_pending = None
+        elif self._fp_pending is None:
+            self._fp_host.copy_(self._fingerprint(params), non_blocking=True)
+            self._fp_pending = torch.cuda.Event()
+            self._fp_pending.record()
         return self._packed
 
     def _plan(self, node_mask, edge_mask):
@@ -113,7 +168,8 @@ class _DGTBase(nn.Module):
             ws = _Workspace(plan, self.dims, self._weights().meta, node_mask.device)
             if len(self._plans) > 4:
                 self._plans.clear()
-            hit = self._plans[key] = (plan, ws, _lib.plan_struct(plan))
+            # the masks are kept alive with the entry so that the allocator cannot hand their addresses to new masks
+            hit = self._plans[key] = (plan, ws, _lib.plan_struct(plan), node_mask, edge_mask)
         return hit
 
     # ---- forward ------------------------------------------------------------------------------------
@@ -132,7 +188,7 @@ class _DGTBase(nn.Module):
             raise ValueError('cond_DGT_concat needs a context')
         pk = self._weights()
         meta = pk.meta
-        plan, ws, ps = self._plan(node_mask, edge_mask)
+        plan, ws, ps = self._plan(node_mask, edge_mask)[:3]
         B, N = plan.B, plan.N
         st = _lib.stream_ptr()
         L = _lib.lib()
