@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 5
+#define JODO_ABI_VERSION 6
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -218,6 +218,56 @@ int jodo_attn(const jodo_attn_args* a, void* stream);
 int jodo_edge_update(const jodo_edge_update_args* a, void* stream);
 int jodo_equi(const jodo_equi_args* a, void* stream);
 int jodo_edge_head(const jodo_edge_head_args* a, void* stream);
+
+/* ---- wide path: row kernels between the GEMMs for hidden sizes the fused edge-tile kernels above are not built
+ * for (model.nf = 384, reference README.md:156,168).  Every linear layer runs through jodo_imglinear; these kernels do
+ * the row-local work on the plan's edge rows (R = n_tiles * 128) or on packed atoms.  Operand images are the fp16
+ * K-major SWIZZLE_128B images jodo_imglinear reads: [rows / 128][K / 64][128 rows][128 B]. */
+typedef struct jodo_wide_embed_args {                   /* model-level edge inputs (reference models/mol_gnn.py:517-557) */
+  jodo_plan p;
+  const float* edge_x; const float* cond_edge_x; const float* cond_x;   /* dense inputs; cond_* null on the first call */
+  int ch, inn, ed; float edge_th, spatial_cut;
+  int* dist_flag;                         /* device int (out): any cond distance != 0 (models/mol_gnn.py:544) */
+  const float* tab; int ld_tab;           /* per-molecule tables (model-level GBF 1 + scale, shift at [0], [1]) */
+  const float* gbf; int ld_gbf;           /* GBF constants {mu, c1, c2} x ld_gbf */
+  void* img; int K;                       /* out: image [dist0 (ed) | edge_x (ch) | cond_edge_x (ch) | 0], K columns */
+  uint8_t* extra;                         /* out: [R] bit0 = 2-D adjacency head, bit1 = spatial adjacency head */
+} jodo_wide_embed_args;
+
+typedef struct jodo_wide_ln_args {                      /* LayerNorm(eps 1e-6) + modulation of a = x + gate (y[yi] + y2[y2i] + ybias) */
+  int M, W, Kimg;                         /* rows; real columns (W % 8 == 0, <= 512); image columns (>= W, % 64 == 0) */
+  const float* x; int ldx;
+  const float* y; int ldy; const int* yi; /* optional addend rows (gathered through yi when given) */
+  const float* y2; int ldy2; const int* y2i;
+  const float* ybias;                     /* optional [W] */
+  const float* tab; int ld_tab; const int* row_mol;       /* per-molecule table row of every row */
+  int off_gate, off_shift, off_scale;     /* table columns; off_gate < 0: the addend enters with weight 1; scale holds 1 + scale */
+  const int* valid;                       /* optional: rows with valid[row] < 0 are padding (zero outputs) */
+  float* out32; int ldo;                  /* optional modulated fp32 rows (columns [W, min(Kimg, ldo)) are zeroed) */
+  void* out_img; void* y_img;             /* fp16 images of the result / of y (either may be null) */
+} jodo_wide_ln_args;
+
+typedef struct jodo_wide_attn_args {                    /* TransMixLayer message + aggregation (reference models/layers.py:157-186) */
+  int Nn, D, H, X, sc;                    /* atoms, hidden, heads, extra (adjacency) heads, channels per learned q/k head */
+  const int* grp_row0; const int* grp_len; const int* row_j;   /* first edge row / partner count of every atom; partner per row */
+  const uint16_t* qkv; int ldq, k_off, v_off;                  /* fp16 rows per atom: q at 0, k at k_off, v at v_off */
+  const uint16_t* G; int ldg, g1_off;                          /* fp16 rows per edge: tanh(lin_edge0) at 0, tanh(lin_edge1) at g1_off */
+  const uint8_t* extra;
+  float* hnode;                           /* out [Nn, D] */
+} jodo_wide_attn_args;
+
+int jodo_wide_embed_in(const jodo_wide_embed_args* a, void* stream);
+int jodo_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1, void* img2, int K2,
+                  int col2, void* stream);                      /* fp32 rows -> fp16 columns [col, col + W) of one or two images */
+int jodo_wide_dist(const jodo_plan* p, const float* pos4, const float* tab, int ld_tab, int off_gbf, const float* gbf,
+                   int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, void* stream);   /* mol_gnn.py:284-286 */
+int jodo_wide_ln(const jodo_wide_ln_args* a, void* stream);
+int jodo_wide_attn(const jodo_wide_attn_args* a, void* stream);
+int jodo_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
+                       const uint8_t* extra, int X, float coord_scale, const float* pos_in4, float* pos_out4, int Nn,
+                       void* stream);                           /* mol_gnn.py:82-92 */
+int jodo_wide_head_out(const jodo_plan* p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,
+                       float* out_dense, void* stream);         /* mol_gnn.py:574-578 */
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ _lib = None
 c_fp = ctypes.c_void_p
 c_int = ctypes.c_int
 
-ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
 EPI_STORE, EPI_ACT, EPI_ADD, EPI_GATED_RES = 0, 1, 2, 3
 
 
@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 5:
+        if _lib.jodo_abi_version() != 6:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -42,7 +42,7 @@ def check(rc, what):
 
 # ---- launch accounting / per-call device timing (bench.py, profiling) ------------------------------
 # kernels launched per C-ABI call (everything else launches exactly one)
-KERNELS_PER_CALL = {'jodo_edge_embed': 2, 'jodo_node_out': 2, 'jodo_ancestral_update': 2}     # (memsets / D2D constant uploads are not kernels)
+KERNELS_PER_CALL = {'jodo_edge_embed': 2, 'jodo_wide_embed_in': 2, 'jodo_node_out': 2, 'jodo_ancestral_update': 2}     # (memsets / D2D constant uploads are not kernels)
 LAUNCHES = 0           # kernels launched through this binding since import
 TRACE = None           # set to a list to record (name, start_event, end_event) around every call
 
@@ -133,6 +133,25 @@ class ImgLinearArgs(ctypes.Structure):
     _fields_ = [('Aimg', _P), ('M', _I), ('K', _I), ('Wimg', _P), ('bias', _P), ('N', _I), ('NT', _I), ('epi', _I),
                 ('act_out', _I), ('aux', _P), ('ld_aux', _I), ('gate', _P), ('ld_gate', _I), ('row_mol', _P), ('nonuni', _P),
                 ('skip_if_zero', _P), ('C32', _P), ('ldc32', _I), ('C16', _P), ('ldc16', _I), ('c16_piece_major', _I), ('Cimg', _P)]
+
+
+class WideEmbedArgs(ctypes.Structure):
+    _fields_ = [('p', PlanStruct), ('edge_x', _P), ('cond_edge_x', _P), ('cond_x', _P), ('ch', _I), ('inn', _I), ('ed', _I),
+                ('edge_th', _F), ('spatial_cut', _F), ('dist_flag', _P), ('tab', _P), ('ld_tab', _I), ('gbf', _P),
+                ('ld_gbf', _I), ('img', _P), ('K', _I), ('extra', _P)]
+
+
+class WideLnArgs(ctypes.Structure):
+    _fields_ = [('M', _I), ('W', _I), ('Kimg', _I), ('x', _P), ('ldx', _I), ('y', _P), ('ldy', _I), ('yi', _P),
+                ('y2', _P), ('ldy2', _I), ('y2i', _P), ('ybias', _P), ('tab', _P), ('ld_tab', _I), ('row_mol', _P),
+                ('off_gate', _I), ('off_shift', _I), ('off_scale', _I), ('valid', _P), ('out32', _P), ('ldo', _I),
+                ('out_img', _P), ('y_img', _P)]
+
+
+class WideAttnArgs(ctypes.Structure):
+    _fields_ = [('Nn', _I), ('D', _I), ('H', _I), ('X', _I), ('sc', _I), ('grp_row0', _P), ('grp_len', _P), ('row_j', _P),
+                ('qkv', _P), ('ldq', _I), ('k_off', _I), ('v_off', _I), ('G', _P), ('ldg', _I), ('g1_off', _I),
+                ('extra', _P), ('hnode', _P)]
 
 
 def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None, row_mol=None,

@@ -162,4 +162,64 @@ int jodo_edge_head(const jodo_edge_head_args* a, void* stream) {
   JODO_LAUNCH(jodo::launch_edge_head(*a, num_sms(), S(stream)), "jodo_edge_head");
 }
 
+// ---- wide path (nf = 384)
+static bool img_ok(const void* img, int K, int col, int W) {
+  return img && !(reinterpret_cast<uintptr_t>(img) & 127) && K > 0 && K % 64 == 0 && col >= 0 && col % 8 == 0 && W % 8 == 0 && col + W <= K;
+}
+int jodo_wide_embed_in(const jodo_wide_embed_args* a, void* stream) {
+  if (!a) return fail("jodo_wide_embed_in: null args");
+  if (const char* m = check_plan(a->p)) return fail(m);
+  if (a->ch < 1 || a->ed <= 0 || a->ed % 8 || a->ed + 2 * a->ch > a->K) return fail("jodo_wide_embed_in: bad sizes");
+  if (!img_ok(a->img, a->K, 0, a->K) || !a->edge_x || !a->extra || !a->dist_flag || !a->tab || !a->gbf) return fail("jodo_wide_embed_in: bad buffers");
+  if ((a->cond_x == nullptr) != (a->cond_edge_x == nullptr)) return fail("jodo_wide_embed_in: cond_x / cond_edge_x must come together");
+  JODO_LAUNCH(jodo::launch_wide_embed_in(*a, S(stream)), "jodo_wide_embed_in");
+}
+int jodo_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1, void* img2, int K2,
+                  int col2, void* stream) {
+  if (!src || M <= 0 || W <= 0 || (ld % 4) || ld < W) return fail("jodo_wide_put: bad source");
+  if (!img_ok(img1, K1, col1, W) || (img2 && !img_ok(img2, K2, col2, W))) return fail("jodo_wide_put: bad image");
+  JODO_LAUNCH(jodo::launch_wide_put(src, ld, M, W, valid, img1, K1, col1, img2, K2, col2, S(stream)), "jodo_wide_put");
+}
+int jodo_wide_dist(const jodo_plan* p, const float* pos4, const float* tab, int ld_tab, int off_gbf, const float* gbf,
+                   int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, void* stream) {
+  if (!p) return fail("jodo_wide_dist: null plan");
+  if (const char* m = check_plan(*p)) return fail(m);
+  if (!pos4 || !tab || !gbf || ed <= 0 || ld_gbf < ed - 1) return fail("jodo_wide_dist: bad arguments");
+  if (!img_ok(img1, K1, col1, ed) || !img_ok(img2, K2, col2, ed)) return fail("jodo_wide_dist: bad image");
+  JODO_LAUNCH(jodo::launch_wide_dist(*p, pos4, tab, ld_tab, off_gbf, gbf, ld_gbf, ed, img1, K1, col1, img2, K2, col2, S(stream)),
+              "jodo_wide_dist");
+}
+int jodo_wide_ln(const jodo_wide_ln_args* a, void* stream) {
+  if (!a) return fail("jodo_wide_ln: null args");
+  if (a->M <= 0 || a->W <= 0 || a->W % 8 || a->W > 512 || a->Kimg < a->W || a->Kimg % 64 || a->Kimg > 512) return fail("jodo_wide_ln: bad sizes");
+  if (!a->x || !a->tab || !a->row_mol || (a->ldx % 4) || (a->ld_tab % 4) || (a->off_shift % 4) || (a->off_scale % 4)) return fail("jodo_wide_ln: bad inputs");
+  if (a->y && (a->ldy % 4)) return fail("jodo_wide_ln: bad addend stride");
+  if (a->y2 && (!a->y || (a->ldy2 % 4))) return fail("jodo_wide_ln: y2 needs y");
+  if (!a->out_img && !a->out32) return fail("jodo_wide_ln: no output");
+  if (a->out32 && (a->ldo % 4)) return fail("jodo_wide_ln: bad output stride");
+  JODO_LAUNCH(jodo::launch_wide_ln(*a, S(stream)), "jodo_wide_ln");
+}
+int jodo_wide_attn(const jodo_wide_attn_args* a, void* stream) {
+  if (!a) return fail("jodo_wide_attn: null args");
+  if (a->Nn <= 0 || a->D <= 0 || a->H <= 0 || a->H > 32 || a->X < 0 || a->X >= a->H || a->X > 8 || a->D % a->H || a->sc <= 0)
+    return fail("jodo_wide_attn: bad sizes");
+  if (!a->grp_row0 || !a->grp_len || !a->row_j || !a->qkv || !a->G || !a->extra || !a->hnode) return fail("jodo_wide_attn: null buffer");
+  JODO_LAUNCH(jodo::launch_wide_attn(*a, S(stream)), "jodo_wide_attn");
+}
+int jodo_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
+                       const uint8_t* extra, int X, float coord_scale, const float* pos_in4, float* pos_out4, int Nn,
+                       void* stream) {
+  if (!grp_row0 || !grp_len || !row_j || !c3 || !extra || !pos_in4 || !pos_out4 || Nn <= 0 || X < 0 || X > 8 || ldc < 1 + X)
+    return fail("jodo_wide_equi_out: bad arguments");
+  JODO_LAUNCH(jodo::launch_wide_equi_out(grp_row0, grp_len, row_j, c3, ldc, extra, X, coord_scale, pos_in4, pos_out4, Nn, S(stream)),
+              "jodo_wide_equi_out");
+}
+int jodo_wide_head_out(const jodo_plan* p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,
+                       float* out_dense, void* stream) {
+  if (!p) return fail("jodo_wide_head_out: null plan");
+  if (const char* m = check_plan(*p)) return fail(m);
+  if (!x || !w4 || !b4 || !out_dense || hw <= 0 || ch < 1 || ldx < 2 * hw) return fail("jodo_wide_head_out: bad arguments");
+  JODO_LAUNCH(jodo::launch_wide_head_out(*p, x, ldx, hw, w4, b4, ch, out_dense, S(stream)), "jodo_wide_head_out");
+}
+
 }  // extern "C"

@@ -37,6 +37,7 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
 __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == ACT_SILU) return silu_fast(x);
   if (act == ACT_GELU) return gelu_f(x);
+  if (act == ACT_TANH) return tanh_fast(x);
   return x;
 }
 

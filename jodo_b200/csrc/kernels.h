@@ -6,7 +6,7 @@
 
 namespace jodo {
 
-enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2 };
+enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_TANH = 3 };
 enum { EPI_STORE = 0, EPI_ACT = 1, EPI_ADD = 2, EPI_GATED_RES = 3 };
 
 struct RowLinearArgs {
@@ -95,5 +95,22 @@ cudaError_t launch_equi(const EquiArgs& a, int num_sms, cudaStream_t st);
 
 using EdgeHeadArgs = ::jodo_edge_head_args;
 cudaError_t launch_edge_head(const EdgeHeadArgs& a, int num_sms, cudaStream_t st);
+
+// ---- wide path (wide.cu): row kernels between the GEMMs for nf = 384
+using WideEmbedArgs = ::jodo_wide_embed_args;
+using WideLnArgs = ::jodo_wide_ln_args;
+using WideAttnArgs = ::jodo_wide_attn_args;
+cudaError_t launch_wide_embed_in(const WideEmbedArgs& a, cudaStream_t st);
+cudaError_t launch_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1,
+                            void* img2, int K2, int col2, cudaStream_t st);
+cudaError_t launch_wide_dist(const Plan& p, const float* pos, const float* tab, int ld_tab, int off_gbf, const float* gbf,
+                             int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, cudaStream_t st);
+cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st);
+cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st);
+cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
+                                 const uint8_t* extra, int X, float coord_scale, const float* pos_in, float* pos_out, int Nn,
+                                 cudaStream_t st);
+cudaError_t launch_wide_head_out(const Plan& p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,
+                                 float* out_dense, cudaStream_t st);
 
 }  // namespace jodo

@@ -1,0 +1,416 @@
+// Wide path: the DGT edge stages for hidden sizes the fused edge-tile kernels are not built for (model.nf = 384,
+// the reference's "large" GEOM-Drugs configuration, README.md:156,168).  At nf = 384 one block's edge weights
+// (lin_edge0/1, input_lin, coord_mlp.0: 96x378, 96x384, 192x384, 384x384 fp16) no longer fit the shared memory of one
+// SM next to a tile, so this path keeps every linear layer on the persistent tcgen05 GEMM (jodo_imglinear, fp16
+// operand images streamed by TMA) and runs the row-local work between two GEMMs -- GBF features, LayerNorm +
+// modulation, the per-target softmax and message sum, the coordinate sum -- as the row kernels below.  Rows are the
+// plan's edge rows (tiles of 128, a group = all partners of one atom, contiguous), per-edge intermediates live in HBM.
+// Every size is a run-time argument.
+//
+// Reference lines restated: models/mol_gnn.py:270-322 (EquivariantMixBlock), :71-94 (MultiCondEquiUpdate),
+// models/layers.py:131-186 (TransMixLayer), :291-295,328-334 (CondGaussianLayer), models/mol_gnn.py:517-557, 571-579.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace jodo {
+namespace {
+
+constexpr int WCHUNK = 128 * 128;      // bytes of one image chunk: [128 rows][64 fp16]
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// address of the 16-byte piece holding columns [col8, col8 + 8) of `row` in an image with K columns
+__device__ __forceinline__ uint4* wimg(void* img, int row, int col8, int K) {
+  const int tile = row >> 7, r = row & 127, chunk = col8 >> 6, piece = (col8 & 63) >> 3;
+  return reinterpret_cast<uint4*>(static_cast<uint8_t*>(img) + ((size_t)tile * (K >> 6) + chunk) * WCHUNK +
+                                  (size_t)r * 128 + ((piece ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ uint4 wpack8(const float* v) {
+  uint4 o;
+  o.x = pack_h2(v[0], v[1]); o.y = pack_h2(v[2], v[3]); o.z = pack_h2(v[4], v[5]); o.w = pack_h2(v[6], v[7]);
+  return o;
+}
+__device__ __forceinline__ void wload8(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ float h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+
+// CondGaussianLayer features of one squared distance, columns [c0, c0 + 8): column 0 is x = d (1 + scale) + shift,
+// column k + 1 is exp(-0.5 ((x - mu_k) / sg_k)^2) / (a sg_k) = 2^(-((x - mu_k) c1_k)^2) c2_k  (gbf = {mu, c1, c2} x ldg)
+__device__ __forceinline__ void wgbf8(float x, const float* __restrict__ gbf, int ldg, int c0, int ed, float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    if (c == 0) v[i] = x;
+    else if (c < ed) {
+      const float u = (x - __ldg(gbf + c - 1)) * __ldg(gbf + ldg + c - 1);
+      v[i] = exp2f(-u * u) * __ldg(gbf + 2 * ldg + c - 1);
+    } else v[i] = 0.f;
+  }
+}
+
+// ---- any squared cond distance over real ordered pairs != 0 (batch-global branch, models/mol_gnn.py:544)
+__global__ void k_wide_dist_flag(Plan p, const float* __restrict__ cond_x, int w, int* __restrict__ flag) {
+  const int R = blockIdx.x * blockDim.x + threadIdx.x;
+  if (R >= p.n_tiles * 128) return;
+  const int g = p.row_g[R];
+  if (g < 0) return;
+  const float* a = cond_x + (size_t)p.node_dense[g] * w;
+  const float* b = cond_x + (size_t)p.node_dense[p.row_j[R]] * w;
+  const float dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
+  if (dx * dx + dy * dy + dz * dz != 0.0f) atomicOr(flag, 1);
+}
+
+// ---- model-level edge inputs (models/mol_gnn.py:517-557): image [dist0 (ed) | edge_x (ch) | cond_edge_x (ch) | 0]
+// with K columns, and the two adjacency-head bits per row.  One warp per row.
+__global__ void k_wide_embed_in(WideEmbedArgs a) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= a.p.n_tiles * 128) return;
+  const int g = a.p.row_g[row];
+  const int np = a.K >> 3;
+  if (g < 0) {
+    for (int p = lane; p < np; p += 32) *wimg(a.img, row, 8 * p, a.K) = make_uint4(0u, 0u, 0u, 0u);
+    if (lane == 0) a.extra[row] = 0;
+    return;
+  }
+  const int j = a.p.row_j[row], N = a.p.N, w = 3 + a.inn, ch = a.ch, ed = a.ed;
+  const int dg = a.p.node_dense[g], dj = a.p.node_dense[j];
+  const int b = dg / N, ig = dg - b * N, ij = dj - b * N;
+  const size_t eoff = (((size_t)b * N + ij) * N + ig) * ch;                 // edge_x[b, r = j, c = g]
+  float d0 = 0.f;
+  if (a.cond_x) {
+    const float* cg = a.cond_x + (size_t)dg * w;
+    const float* cj = a.cond_x + (size_t)dj * w;
+    const float dx = cj[0] - cg[0], dy = cj[1] - cg[1], dz = cj[2] - cg[2];
+    d0 = dx * dx + dy * dy + dz * dz;
+  }
+  const bool use_gbf = a.cond_x && *a.dist_flag;
+  const float* tr = a.tab + (size_t)a.p.row_mol[row] * a.ld_tab;
+  const float x = d0 * tr[0] + tr[1];                                        // the table stores 1 + scale
+  for (int p = lane; p < np; p += 32) {
+    float v[8];
+    const int c0 = 8 * p;
+    if (c0 < ed) {
+      if (use_gbf) wgbf8(x, a.gbf, a.ld_gbf, c0, ed, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = c0 + i - ed;
+        v[i] = k < ch ? a.edge_x[eoff + k] : ((k < 2 * ch && a.cond_edge_x) ? a.cond_edge_x[eoff + k - ch] : 0.f);
+      }
+    }
+    *wimg(a.img, row, c0, a.K) = wpack8(v);
+  }
+  if (lane == 0) {
+    // adjacency heads: cond_adj_2d (models/mol_gnn.py:520-525), cond_adj_spatial (models/utils.py:111-119)
+    const bool a2d = a.cond_edge_x ? (a.cond_edge_x[eoff] >= a.edge_th) : true;
+    const bool asp = d0 <= a.spatial_cut;
+    a.extra[row] = (uint8_t)((a2d ? 1 : 0) | (asp ? 2 : 0));
+  }
+}
+
+// ---- fp32 rows -> fp16 pieces at a column offset of up to two images (the edge part of the next block's
+// [dist | e] operand and of this block's [e | dist] operand).  One warp per row, W % 8 == 0.
+__global__ void k_wide_put(const float* __restrict__ src, int ld, int M, int W, const int* __restrict__ valid,
+                           void* img1, int K1, int col1, void* img2, int K2, int col2) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const bool live = !valid || valid[row] >= 0;
+  for (int p = lane; p < (W >> 3); p += 32) {
+    float v[8];
+    if (live) wload8(src + (size_t)row * ld + 8 * p, v);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+    const uint4 o = wpack8(v);
+    if (img1) *wimg(img1, row, col1 + 8 * p, K1) = o;
+    if (img2) *wimg(img2, row, col2 + 8 * p, K2) = o;
+  }
+}
+
+// ---- per-block distance features (models/mol_gnn.py:284-286): written as columns [col1, col1 + ed) of the
+// [dist | e] operand and [col2, col2 + ed) of the [e | dist] operand.  One warp per row.
+__global__ void k_wide_dist(Plan p, const float4* __restrict__ pos, const float* __restrict__ tab, int ld_tab,
+                            int off_gbf, const float* __restrict__ gbf, int ld_gbf, int ed, void* img1, int K1, int col1,
+                            void* img2, int K2, int col2) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= p.n_tiles * 128) return;
+  const int g = p.row_g[row];
+  float x = 0.f;
+  if (g >= 0) {
+    const float4 a = pos[g], b = pos[p.row_j[row]];
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    const float* tr = tab + (size_t)p.row_mol[row] * ld_tab + off_gbf;
+    x = (dx * dx + dy * dy + dz * dz) * tr[0] + tr[1];
+  }
+  for (int q = lane; q < (ed >> 3); q += 32) {
+    float v[8];
+    if (g >= 0) wgbf8(x, gbf, ld_gbf, 8 * q, ed, v);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+    const uint4 o = wpack8(v);
+    *wimg(img1, row, col1 + 8 * q, K1) = o;
+    *wimg(img2, row, col2 + 8 * q, K2) = o;
+  }
+}
+
+// ---- LayerNorm (eps 1e-6, no affine) + modulation of  a = x + gate * (y[yi] + y2[y2i] + ybias), one warp per row,
+// W <= 512 columns.  Serves norm1/norm2 of atoms and edges (models/mol_gnn.py:296-297, 307-308, 313-314) and the
+// input_lin LayerNorm of the coordinate update (:73-79, with the hoisted per-atom parts as y, y2).
+__global__ void k_wide_ln(WideLnArgs a) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int rows_pad = (a.M + 127) / 128 * 128;
+  if (row >= rows_pad) return;
+  const int npw = a.W >> 3, npk = a.Kimg >> 3;
+  const bool live = row < a.M && (!a.valid || a.valid[row] >= 0);
+  if (!live) {
+    for (int p = lane; p < npk; p += 32) {
+      if (a.out_img) *wimg(a.out_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
+      if (a.y_img) *wimg(a.y_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
+      if (a.out32 && row < a.M && 8 * p < a.ldo) {
+        *reinterpret_cast<float4*>(a.out32 + (size_t)row * a.ldo + 8 * p) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a.out32 + (size_t)row * a.ldo + 8 * p + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    return;
+  }
+  const float* t = a.tab + (size_t)a.row_mol[row] * a.ld_tab;
+  const int iy = a.y ? (a.yi ? a.yi[row] : row) : 0;
+  const int iy2 = a.y2 ? (a.y2i ? a.y2i[row] : row) : 0;
+  float v[2][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int p = lane + 32 * k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
+    if (p < npw) {
+      wload8(a.x + (size_t)row * a.ldx + 8 * p, v[k]);
+      if (a.y) {
+        float y[8];
+        wload8(a.y + (size_t)iy * a.ldy + 8 * p, y);
+        if (a.y_img) *wimg(a.y_img, row, 8 * p, a.Kimg) = wpack8(y);
+        if (a.y2) {
+          float y2[8];
+          wload8(a.y2 + (size_t)iy2 * a.ldy2 + 8 * p, y2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] += y2[i];
+        }
+        if (a.ybias) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] += __ldg(a.ybias + 8 * p + i);
+        }
+        if (a.off_gate >= 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[k][i] = fmaf(__ldg(t + a.off_gate + 8 * p + i), y[i], v[k][i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[k][i] += y[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[k][i];
+    } else if (p < npk && a.y_img) {
+      *wimg(a.y_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  const float mean = wsum(s) / (float)a.W;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (lane + 32 * k < npw) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; q += d * d; }
+    }
+  const float rstd = rsqrtf(wsum(q) / (float)a.W + 1e-6f);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int p = lane + 32 * k;
+    if (p >= npk) continue;
+    float o[8];
+    if (p < npw) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)             // the table stores 1 + scale
+        o[i] = fmaf((v[k][i] - mean) * rstd, __ldg(t + a.off_scale + 8 * p + i), __ldg(t + a.off_shift + 8 * p + i));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    }
+    if (a.out32 && 8 * p < a.ldo) {
+      *reinterpret_cast<float4*>(a.out32 + (size_t)row * a.ldo + 8 * p) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(a.out32 + (size_t)row * a.ldo + 8 * p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    if (a.out_img) *wimg(a.out_img, row, 8 * p, a.Kimg) = wpack8(o);
+  }
+}
+
+// ---- TransMixLayer.message + aggregation (models/layers.py:157-186) for one target atom per CTA.
+// logits over the sources of the atom's group: extra heads first (adjacency bit ? 1 : -1e10), then
+// a[s] = sum_ch q[c,s,ch] k[r,s,ch] g0[s,ch] / sqrt(C); PyG softmax exp(a - max) / (sum + 1e-16); message
+// v[r] * g1 * alpha summed over the sources.  g0 | g1 = tanh(lin_edge0 | lin_edge1) come from one GEMM.
+constexpr int WA_THREADS = 128;
+__global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
+  extern __shared__ float wsm[];
+  const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gl = a.grp_len[g], row0 = a.grp_row0[g];
+  const int D = a.D, H = a.H, X = a.X, S = H - X, sc = a.sc, qk = S * sc, C = D / H;
+  const int qkp = (qk + 31) & ~31;
+  float* qs = wsm;                          // [qkp] q of the target, pre-scaled
+  float* prod = qs + qkp;                   // [4 warps][qkp]
+  float* lg = prod + 4 * qkp;               // [128][H] logits -> alpha
+  int* js = reinterpret_cast<int*>(lg + 128 * H);   // [128] source atoms
+  if (gl <= 0) {
+    for (int c = tid; c < D; c += WA_THREADS) a.hnode[(size_t)g * D + c] = 0.f;
+    return;
+  }
+  const float inv = rsqrtf((float)C);
+  const uint16_t* qrow = a.qkv + (size_t)g * a.ldq;
+  for (int c = tid; c < qk; c += WA_THREADS) qs[c] = h2f(qrow[c]) * inv;
+  for (int i = tid; i < gl; i += WA_THREADS) js[i] = a.row_j[row0 + i];
+  __syncthreads();
+  for (int i = warp; i < gl; i += 4) {
+    const uint16_t* krow = a.qkv + (size_t)js[i] * a.ldq + a.k_off;
+    const uint16_t* grow = a.G + (size_t)(row0 + i) * a.ldg;
+    float* pr = prod + warp * qkp;
+    for (int c = lane; c < qk; c += 32) pr[c] = qs[c] * h2f(krow[c]) * h2f(grow[c]);
+    __syncwarp();
+    if (lane < S) {
+      float s = 0.f;
+      for (int k = 0; k < sc; ++k) s += pr[lane * sc + k];
+      lg[i * H + X + lane] = s;
+    } else if (lane - S < X) {
+      const int x = lane - S;
+      lg[i * H + x] = ((a.extra[row0 + i] >> x) & 1) ? 1.0f : -1e10f;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (tid < H) {
+    float m = -INFINITY;
+    for (int i = 0; i < gl; ++i) m = fmaxf(m, lg[i * H + tid]);
+    float s = 0.f;
+    for (int i = 0; i < gl; ++i) { const float e = expf(lg[i * H + tid] - m); lg[i * H + tid] = e; s += e; }
+    const float rs = 1.0f / (s + 1e-16f);
+    for (int i = 0; i < gl; ++i) lg[i * H + tid] *= rs;
+  }
+  __syncthreads();
+  for (int c = tid; c < D; c += WA_THREADS) {
+    const int h = c / C;
+    float acc = 0.f;
+    for (int i = 0; i < gl; ++i) {
+      const float vv = h2f(a.qkv[(size_t)js[i] * a.ldq + a.v_off + c]);
+      const float g1 = h2f(a.G[(size_t)(row0 + i) * a.ldg + a.g1_off + c]);
+      acc = fmaf(vv * g1, lg[i * H + h], acc);
+    }
+    a.hnode[(size_t)g * D + c] = acc;
+  }
+}
+
+// ---- coordinate update tail (models/mol_gnn.py:82-92): inv = mean([1, extra] * tanh(coord_mlp.2 output)),
+// pos_r += sum_c (pos_r - pos_c) / max(|.|, 1e-8) * scale * inv.  One thread per atom.
+__global__ void k_wide_equi_out(const int* __restrict__ grp_row0, const int* __restrict__ grp_len,
+                                const int* __restrict__ row_j, const float* __restrict__ c3, int ldc,
+                                const uint8_t* __restrict__ extra, int X, float coord_scale,
+                                const float4* __restrict__ pos_in, float4* __restrict__ pos_out, int Nn) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Nn) return;
+  const float4 p = pos_in[g];
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  const int r0 = grp_row0[g], gl = grp_len[g];
+  for (int i = 0; i < gl; ++i) {
+    const int R = r0 + i;
+    const float4 q = pos_in[row_j[R]];
+    const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+    const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
+    const float* c = c3 + (size_t)R * ldc;
+    const uint8_t bits = extra[R];
+    float inv = tanhf(c[0]);
+    for (int x = 0; x < X; ++x) inv += ((bits >> x) & 1) ? tanhf(c[1 + x]) : 0.f;
+    const float f = coord_scale * inv / ((float)(1 + X) * nrm);
+    sx = fmaf(dx, f, sx); sy = fmaf(dy, f, sy); sz = fmaf(dz, f, sz);
+  }
+  pos_out[g] = make_float4(p.x + sx, p.y + sy, p.z + sz, 0.f);
+}
+
+// ---- last layer of edge_exist_mlp / edge_type_mlp (models/mol_gnn.py:574-578) + scatter to the dense grid.
+// x[row] = [SiLU hidden of exist (hw) | SiLU hidden of type (hw)]; w4 [ch][hw]: row 0 reads the first half.
+__global__ void k_wide_head_out(Plan p, const float* __restrict__ x, int ldx, int hw, const float* __restrict__ w4,
+                                const float* __restrict__ b4, int ch, float* __restrict__ out_dense) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= p.n_tiles * 128) return;
+  const int g = p.row_g[row];
+  if (g < 0) return;
+  const int N = p.N;
+  const int dg = p.node_dense[g], dj = p.node_dense[p.row_j[row]];
+  const int b = dg / N, ig = dg - b * N, ij = dj - b * N;
+  float* dst = out_dense + (((size_t)b * N + ij) * N + ig) * ch;            // row (g, j) is the edge r = j -> c = g
+  const float* xr = x + (size_t)row * ldx;
+  for (int k = 0; k < ch; ++k) {
+    const float* xs = xr + (k == 0 ? 0 : hw);
+    float o = b4[k];
+    for (int i = 0; i < hw; ++i) o = fmaf(xs[i], w4[k * hw + i], o);
+    dst[k] = o;
+  }
+}
+
+}  // namespace
+
+#define WIDE_OK() cudaGetLastError()
+
+cudaError_t launch_wide_embed_in(const WideEmbedArgs& a, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(a.dist_flag, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  const int R = a.p.n_tiles * 128;
+  if (a.cond_x) k_wide_dist_flag<<<(R + 255) / 256, 256, 0, st>>>(a.p, a.cond_x, 3 + a.inn, a.dist_flag);
+  k_wide_embed_in<<<R / 8, 256, 0, st>>>(a);
+  return WIDE_OK();
+}
+cudaError_t launch_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1,
+                            void* img2, int K2, int col2, cudaStream_t st) {
+  k_wide_put<<<(M + 7) / 8, 256, 0, st>>>(src, ld, M, W, valid, img1, K1, col1, img2, K2, col2);
+  return WIDE_OK();
+}
+cudaError_t launch_wide_dist(const Plan& p, const float* pos, const float* tab, int ld_tab, int off_gbf, const float* gbf,
+                             int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, cudaStream_t st) {
+  k_wide_dist<<<p.n_tiles * 128 / 8, 256, 0, st>>>(p, reinterpret_cast<const float4*>(pos), tab, ld_tab, off_gbf, gbf,
+                                                   ld_gbf, ed, img1, K1, col1, img2, K2, col2);
+  return WIDE_OK();
+}
+cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st) {
+  const int rows_pad = (a.M + 127) / 128 * 128;
+  k_wide_ln<<<rows_pad / 8, 256, 0, st>>>(a);
+  return WIDE_OK();
+}
+cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st) {
+  const int S = a.H - a.X, qkp = (S * a.sc + 31) & ~31;
+  const size_t smem = (size_t)(5 * qkp + 128 * a.H) * sizeof(float) + 128 * sizeof(int);
+  k_wide_attn<<<a.Nn, WA_THREADS, smem, st>>>(a);
+  return WIDE_OK();
+}
+cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
+                                 const uint8_t* extra, int X, float coord_scale, const float* pos_in, float* pos_out, int Nn,
+                                 cudaStream_t st) {
+  k_wide_equi_out<<<(Nn + 127) / 128, 128, 0, st>>>(grp_row0, grp_len, row_j, c3, ldc, extra, X, coord_scale,
+                                                    reinterpret_cast<const float4*>(pos_in), reinterpret_cast<float4*>(pos_out), Nn);
+  return WIDE_OK();
+}
+cudaError_t launch_wide_head_out(const Plan& p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,
+                                 float* out_dense, cudaStream_t st) {
+  const int R = p.n_tiles * 128;
+  k_wide_head_out<<<(R + 127) / 128, 128, 0, st>>>(p, x, ldx, hw, w4, b4, ch, out_dense);
+  return WIDE_OK();
+}
+
+}  // namespace jodo

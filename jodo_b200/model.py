@@ -16,7 +16,7 @@ import ctypes
 import torch
 from torch import nn
 
-from . import _lib
+from . import _lib, wide
 from .pack import TAB_HEAD, pack_model, tab_layer_stride
 from .params import build_param_tree, check_supported, dims_from_config, param_spec, synth_state_dict
 from .plan import Plan
@@ -96,12 +96,16 @@ class _DGTBase(nn.Module):
         super().__init__()
         check_supported(config)
         self.dims = dims_from_config(config)
-        if self.dims.D != 256:
-            raise NotImplementedError(f'jodo_b200 kernels are built for model.nf = 256 (got {self.dims.D})')
-        if self.dims.r not in (2, 4):
-            raise NotImplementedError(f'jodo_b200 edge kernels are built for model.mlp_ratio 2 or 4 (got {self.dims.r})')
-        if self.dims.ce % 4 or self.dims.ce > 16:
-            raise NotImplementedError('unsupported n_layers (edge hidden slice must be a multiple of 4 <= 16)')
+        self.wide = self.dims.D != 256      # nf = 256: fused edge-tile kernels; other sizes: GEMM + row-kernel path (wide.py)
+        if self.wide:
+            why = wide.supported(self.dims)
+            if why:
+                raise NotImplementedError('jodo_b200: ' + why)
+        else:
+            if self.dims.r not in (2, 4):
+                raise NotImplementedError(f'jodo_b200 edge kernels are built for model.mlp_ratio 2 or 4 (got {self.dims.r})')
+            if self.dims.ce % 4 or self.dims.ce > 16:
+                raise NotImplementedError('unsupported n_layers (edge hidden slice must be a multiple of 4 <= 16)')
         self.edge_th = float(config.model.edge_quan_th)
         self.spatial_cut_off = float(config.model.spatial_cut_off)
         self.n_layers = self.dims.L
@@ -165,7 +169,7 @@ class _DGTBase(nn.Module):
             if not torch.equal((edge_mask.reshape(B, N, N) > 0).float(), want):
                 raise ValueError('edge_mask must be node_mask x node_mask without the diagonal '
                                  '(reference sampling.py:197-199)')
-            ws = _Workspace(plan, self.dims, self._weights().meta, node_mask.device)
+            ws = (wide.WideWorkspace if self.wide else _Workspace)(plan, self.dims, self._weights().meta, node_mask.device)
             if len(self._plans) > 4:
                 self._plans.clear()
             # the masks are kept alive with the entry so that the allocator cannot hand their addresses to new masks
@@ -197,6 +201,8 @@ class _DGTBase(nn.Module):
         xh, edge_x, noise_level = c32(xh), c32(edge_x), c32(noise_level)
         if cond_x is not None:
             cond_x, cond_edge_x = c32(cond_x), c32(cond_edge_x)
+        if self.wide:
+            return wide.forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_edge_x, context)
         D, T, ld_tab = d.D, d.T, meta['ld_tab']
 
         def lin(name, A, C, M=None, **kw):

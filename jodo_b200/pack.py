@@ -173,7 +173,8 @@ def pack_model(sd, dims, device):
     """sd: name -> tensor (reference names, no 'module.' prefix); dims: jodo_b200.params.Dims."""
     d = dims
     D, ed, T, L = d.D, d.ed, d.T, d.L
-    assert D == 256 and ed == 64, 'edge kernels are built for nf = 256'
+    fused = D == 256                       # fused edge-tile kernels; other sizes take the wide path (jodo_b200/wide.py)
+    ntb = 256 if D % 256 == 0 else 128     # N tile of the wide per-molecule / per-atom GEMMs
     sd = {k: v.detach().to(device, torch.float32) for k, v in sd.items()}
     pk = Packed(device)
     W = lambda n: sd[n + '.weight']
@@ -193,13 +194,13 @@ def pack_model(sd, dims, device):
 
     # ---- molecule level
     pk.add('time.w8', sd['time_mlp.0.weights'])
-    add_lin('time1', W('time_mlp.1'), Bv('time_mlp.1'), 256)
-    add_lin('time3', W('time_mlp.3'), Bv('time_mlp.3'), 256)
+    add_lin('time1', W('time_mlp.1'), Bv('time_mlp.1'), ntb)
+    add_lin('time3', W('time_mlp.3'), Bv('time_mlp.3'), ntb)
     if d.cond_ch:
         pk.add('cond0.w', W('cond_mlp.0').reshape(-1))
         pk.add('cond0.b', Bv('cond_mlp.0'))
-        add_lin('cond2', W('cond_mlp.2'), Bv('cond_mlp.2'), 256)
-        add_lin('condlin', W('cond_lin'), Bv('cond_lin'), 256)
+        add_lin('cond2', W('cond_mlp.2'), Bv('cond_mlp.2'), ntb)
+        add_lin('condlin', W('cond_lin'), Bv('cond_lin'), ntb)
     # per-molecule tables: one GEMM  [B, T] x [T, ld_tab]
     stride = tab_layer_stride(D)
     ld_tab = ceil_to(TAB_HEAD + L * stride, 256)
@@ -218,21 +219,25 @@ def pack_model(sd, dims, device):
             for s0, s1 in scales:                             # chunk order: shift, scale, gate (AdaLN); scale, shift (GBF)
                 bt[o + s0:o + s1] += 1.0
             o += n
-    add_lin('tab', wt, bt, 256)
+    add_lin('tab', wt, bt, 256)                              # ld_tab is a multiple of 256
     pk.meta['ld_tab'] = ld_tab
     # ---- atom level
-    add_lin('node_emb', W('node_emb'), Bv('node_emb'), 256)
+    add_lin('node_emb', W('node_emb'), Bv('node_emb'), ntb)
     cnp = ceil_to(d.cn, 4)
     k_ah = ceil_to(D + L * cnp, 64)
-    pk.meta.update(cnp=cnp, k_ah=k_ah, ld_ah=k_ah + 64)
+    pk.meta.update(cnp=cnp, k_ah=k_ah, ld_ah=k_ah + (64 if fused else 128))    # room for the last node_i GEMM's padded N tile
     w0 = W('node_pred_mlp.0')
     w0p = z(D, k_ah)
     w0p[:, :D] = w0[:, :D]
     for l in range(L):
         w0p[:, D + l * cnp:D + l * cnp + d.cn] = w0[:, D + l * d.cn:D + (l + 1) * d.cn]
-    add_lin('npred0', w0p, Bv('node_pred_mlp.0'), 256)
-    add_lin('npred2', W('node_pred_mlp.2'), Bv('node_pred_mlp.2'), 128)
+    add_lin('npred0', w0p, Bv('node_pred_mlp.0'), ntb)
+    add_lin('npred2', W('node_pred_mlp.2'), Bv('node_pred_mlp.2'), 128 if (D // 2) % 128 == 0 else 64)
     add_lin('npred4', W('node_pred_mlp.4'), Bv('node_pred_mlp.4'), 16)
+    if not fused:
+        from .wide import pack_wide
+        pack_wide(pk, sd, d, add_lin)
+        return pk.finish()
     # ---- edge level (model)
     pk.add('gbf', _gbf_consts(sd, 'dist_layer', device))
     we = W('edge_emb')                                         # [ed, 2ch + ed]: [edge_x | cond_edge_x | dist]

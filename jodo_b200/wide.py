@@ -1,0 +1,310 @@
+"""Wide path of the DGT denoiser: hidden sizes the fused edge-tile kernels are not built for
+(``model.nf = 384``, the reference's "large" GEOM-Drugs model, reference README.md:156,168).
+
+Same boundary and the same plan / packed-atom layout as the fused path (jodo_b200/model.py), but the
+per-edge work is a sequence of persistent tcgen05 GEMMs (``jodo_imglinear``) over the plan's edge rows
+with the row kernels of csrc/wide.cu between them; per-edge intermediates live in HBM.  Reference lines:
+models/mol_gnn.py:491-594 (forward), :270-322 (block), :71-94 (coordinate update),
+models/layers.py:131-186 (attention).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from .pack import TAB_HEAD, ceil_to, pad2, tab_layer_stride
+
+_c = ctypes.c_int
+EDP = 128            # row stride (floats) of the per-edge fp32 buffers and K of the per-edge images (ed <= 128)
+
+
+def supported(d) -> str | None:
+    """None when the wide path covers these sizes, else the reason."""
+    if d.D % 128 or d.D > 512:
+        return f'model.nf must be a multiple of 128 up to 512 (got {d.D})'
+    if d.ed % 8 or d.ed > EDP:
+        return f'edge width nf/4 must be a multiple of 8 up to {EDP} (got {d.ed})'
+    if d.H > 32 or d.D % d.H:
+        return f'n_heads must divide nf and be at most 32 (got {d.H})'
+    if 2 * d.ch + d.ed > EDP:
+        return f'edge_ch too large for the embedding image (got {d.ch})'
+    return None
+
+
+def _gbf_consts(sd, prefix, dev):
+    """{mu, sqrt(0.5 log2 e) / sg, 1 / (a sg)} x EDP (reference models/layers.py:291-295, 332-333):
+    exp(-0.5 ((x - mu) / sg)^2) / (a sg) = 2^(-((x - mu) c1)^2) c2."""
+    mu = sd[prefix + '.means.weight'].float().view(-1)
+    sg = sd[prefix + '.stds.weight'].float().view(-1).abs() + 1e-5
+    a = (2 * 3.14159) ** 0.5
+    out = torch.zeros(3, EDP, device=dev)
+    k = mu.numel()
+    out[0, :k] = mu
+    out[1, :k] = (0.5 * 1.4426950408889634) ** 0.5 / sg
+    out[2, :k] = 1.0 / (a * sg)
+    return out.reshape(-1)
+
+
+def pack_wide(pk, sd, d, add_lin):
+    """Edge-level and per-block weights of the wide path (the molecule / atom level pieces are packed by
+    pack.pack_model).  Every GEMM runs with 128-column tiles; N and K are zero padded."""
+    D, ed, L, r = d.D, d.ed, d.L, d.r
+    dev = pk.device
+    W = lambda n: sd[n + '.weight']
+    Bv = lambda n: sd[n + '.bias']
+    z = lambda *s: torch.zeros(*s, device=dev)
+    qkp = ceil_to(d.qk, 128)
+    pk.meta.update(qkp=qkp, wide=True)
+    # ---- model level: edge_emb on [dist0 (ed) | edge_x (ch) | cond_edge_x (ch)]
+    pk.add('gbf', _gbf_consts(sd, 'dist_layer', dev))
+    we = W('edge_emb')                                         # [ed, 2ch + ed]: [edge_x | cond_edge_x | dist]
+    wep = z(ed, EDP)
+    wep[:, :ed] = we[:, 2 * d.ch:]
+    wep[:, ed:ed + 2 * d.ch] = we[:, :2 * d.ch]
+    add_lin('edge_emb', wep, Bv('edge_emb'), 128)
+    # ---- edge heads: layer 0 of edge_exist_mlp | edge_type_mlp is linear in the concatenated edge hiddens
+    # cat[e0, edge_0(e_1), ..] (reference models/mol_gnn.py:567-574), so the edge_i projections are folded into it and
+    # the heads' first hidden state H is accumulated block by block:  H = W0[:, :ed] e0 + sum_l (W0[:, s_l] We_l) e_l + b.
+    w0 = torch.cat([W('edge_exist_mlp.0'), W('edge_type_mlp.0')], dim=0)            # [2ed, ed + L ce]
+    b0 = torch.cat([Bv('edge_exist_mlp.0'), Bv('edge_type_mlp.0')]).clone()
+    hp = ceil_to(2 * ed, 128)
+    wh = z(2 * ed, 2 * ed)
+    wh[:, ed:] = w0[:, :ed]                                   # operand [dist | e] of block 0: the e columns
+    for l in range(L):
+        sl = w0[:, ed + l * d.ce:ed + (l + 1) * d.ce]
+        b0 += sl @ Bv(f'edge_{l}')
+        wf = z(2 * ed, 2 * ed)
+        wf[:, :ed] = sl @ W(f'edge_{l}')                      # operand [e | dist]: the e columns
+        add_lin(f'b{l}.hfold', wf, None, 128, n_pad=hp)
+    add_lin('h0', wh, b0, 128, n_pad=hp)
+    w2 = z(ed, hp)
+    w2[:ed // 2, :ed] = W('edge_exist_mlp.2')
+    w2[ed // 2:, ed:2 * ed] = W('edge_type_mlp.2')
+    add_lin('ehead2', w2, torch.cat([Bv('edge_exist_mlp.2'), Bv('edge_type_mlp.2')]), 128)
+    pk.add('ehead4.w', torch.cat([W('edge_exist_mlp.4'), W('edge_type_mlp.4')], dim=0))     # [ch, ed / 2]
+    pk.add('ehead4.b', torch.cat([Bv('edge_exist_mlp.4'), Bv('edge_type_mlp.4')]))
+    pk.add('ones', torch.ones(hp, device=dev))
+    pk.meta['hp'] = hp
+    # ---- blocks
+    scales = []
+    f3p = ceil_to(ed * r, 128)
+    pk.meta['f3p'] = f3p
+    for l in range(L):
+        b = f'e_block_{l}'
+        p = f'b{l}.'
+        wq, bq = z(2 * qkp + D, D), z(2 * qkp + D)
+        wq[:d.qk], bq[:d.qk] = W(f'{b}.attn_mpnn.lin_query'), Bv(f'{b}.attn_mpnn.lin_query')
+        wq[qkp:qkp + d.qk], bq[qkp:qkp + d.qk] = W(f'{b}.attn_mpnn.lin_key'), Bv(f'{b}.attn_mpnn.lin_key')
+        wq[2 * qkp:], bq[2 * qkp:] = W(f'{b}.attn_mpnn.lin_value'), Bv(f'{b}.attn_mpnn.lin_value')
+        add_lin(p + 'qkv', wq, bq, 128)
+        add_lin(p + 'n2e', W(f'{b}.node2edge_lin'), None, 128)
+        nb = z(EDP)
+        nb[:ed] = Bv(f'{b}.node2edge_lin')
+        pk.add(p + 'n2e.bias', nb)
+        add_lin(p + 'ff1', W(f'{b}.ff_linear1'), Bv(f'{b}.ff_linear1'), 128)
+        add_lin(p + 'ff2', W(f'{b}.ff_linear2'), Bv(f'{b}.ff_linear2'), 128)
+        wi = W(f'{b}.equi_update.input_lin')                   # [D, 2D + 2ed]: [h_row | h_col | e | dist]
+        add_lin(p + 'ab', torch.cat([wi[:, :D], wi[:, D:2 * D]], dim=0),
+                torch.cat([Bv(f'{b}.equi_update.input_lin'), z(D)]), 128)      # input_lin bias rides on the h[row] part
+        add_lin(p + 'node_l', W(f'node_{l}'), Bv(f'node_{l}'), 128)
+        pk.add(p + 'gbf', _gbf_consts(sd, f'{b}.dist_layer', dev))
+        add_lin(p + 'emb', W(f'{b}.edge_emb'), Bv(f'{b}.edge_emb'), 128)                    # K = 2ed: [dist | e]
+        wg = z(qkp + D, EDP)
+        wg[:d.qk, :ed] = W(f'{b}.attn_mpnn.lin_edge0')
+        wg[qkp:, :ed] = W(f'{b}.attn_mpnn.lin_edge1')
+        add_lin(p + 'g01', wg, None, 128)
+        add_lin(p + 'ff3', pad2(W(f'{b}.ff_linear3'), f3p, EDP), Bv(f'{b}.ff_linear3'), 128, n_pad=f3p)
+        add_lin(p + 'ff4', pad2(W(f'{b}.ff_linear4'), ed, f3p), Bv(f'{b}.ff_linear4'), 128)
+        add_lin(p + 'equi_in', wi[:, 2 * D:].contiguous(), None, 128)                       # K = 2ed: [e | dist]
+        add_lin(p + 'c0', W(f'{b}.equi_update.coord_mlp.0'), Bv(f'{b}.equi_update.coord_mlp.0'), 128)
+        add_lin(p + 'c2', W(f'{b}.equi_update.coord_mlp.2'), None, 64)                      # N = 64 (1 + X real)
+        scales.append(sd[f'{b}.equi_update.coord_norm.scale'].reshape(()))
+    pk.meta['coord_scale'] = [float(s) for s in torch.stack(scales).cpu()]
+
+
+class WideWorkspace:
+    """Device buffers of the wide path for one plan."""
+
+    def __init__(self, plan, d, meta, dev):
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        zf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        B, Nn, nt = plan.B, plan.Nn, plan.n_tiles
+        D, T, R = d.D, d.T, plan.n_tiles * 128
+        self.R = R
+        self.feat, self.t1, self.temb = f(B, 64), f(B, T), f(B, T)
+        if d.cond_ch:
+            self.c1, self.c2, self.ctx = f(B * d.cond_ch, D), f(B * d.cond_ch, D), f(B, T)
+        self.tab = f(B, meta['ld_tab'])
+        bt = (B + 127) // 128 * 128
+        self.temb_img = torch.zeros(bt * T, device=dev, dtype=torch.float16)
+        self.kin = meta['node_emb']['K']
+        self.xin = f(Nn, self.kin)
+        self.pos = [zf(Nn, 4), zf(Nn, 4)]
+        self.ah = zf(Nn, meta['ld_ah'])
+        self.h = [f(Nn, D), f(Nn, D)]
+        mt = (Nn + 127) // 128
+        nimg = lambda k: torch.zeros(mt * 128 * k, device=dev, dtype=torch.float16)
+        eimg = lambda k: torch.zeros(R * k, device=dev, dtype=torch.float16)
+        self.hn_img, self.h2_img, self.hnode_img, self.hout_img = nimg(D), nimg(D), nimg(D), nimg(D)
+        self.ff_img = nimg(d.r * D)
+        self.ldq = 2 * meta['qkp'] + D
+        self.qkv = torch.zeros(Nn, self.ldq, device=dev, dtype=torch.float16)
+        self.hnode, self.h2 = zf(Nn, D), f(Nn, D)
+        self.P = zf(Nn, EDP)
+        self.AB = f(Nn, 2 * D)
+        self.n1, self.n2, self.ap = f(Nn, D), f(Nn, meta['npred2']['N']), f(Nn, meta['npred4']['N'])
+        # per edge row
+        self.A0, self.A1, self.A4 = eimg(EDP), eimg(2 * d.ed), eimg(2 * d.ed)
+        self.e32, self.e1, self.e2 = zf(R, EDP), zf(R, EDP), zf(R, EDP)
+        self.en_img, self.e2_img = eimg(EDP), eimg(EDP)
+        self.ldg = meta['qkp'] + D
+        self.G = torch.zeros(R, self.ldg, device=dev, dtype=torch.float16)
+        self.f3_img = eimg(meta['f3p'])
+        self.H = zf(R, meta['hp'])
+        self.H_img = eimg(meta['hp'])
+        self.X2 = zf(R, EDP)
+        self.U = zf(R, D)
+        self.u_img, self.c0_img = eimg(D), eimg(D)
+        self.c3 = zf(R, 64)
+        self.extra = torch.zeros(R, device=dev, dtype=torch.uint8)
+        self.flags = torch.zeros(4, device=dev, dtype=torch.int32)            # [0] dist flag, [1] nan flag
+        self.ones = torch.ones(1, meta['hp'], device=dev).expand(B, meta['hp'])      # gate rows of the H accumulation
+        # first edge row / partner count of every packed atom (groups are contiguous rows of one tile)
+        rows = torch.arange(R, device=dev, dtype=torch.int32)
+        ok = plan.row_g >= 0
+        first = (rows & ~127) + (plan.row_meta & 255)
+        self.grp_row0 = torch.zeros(Nn, device=dev, dtype=torch.int32)
+        self.grp_len = torch.zeros(Nn, device=dev, dtype=torch.int32)
+        self.grp_row0[plan.row_g[ok].long()] = first[ok]
+        self.grp_len[plan.row_g[ok].long()] = ((plan.row_meta[ok] >> 8) & 255)
+
+
+def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_edge_x, context):
+    """The wide-path launch sequence of one denoiser evaluation (called by model._DGTBase.forward)."""
+    d, meta = self.dims, pk.meta
+    B, N, Nn, R = plan.B, plan.N, plan.Nn, ws.R
+    D, T, ed, ld_tab = d.D, d.T, d.ed, meta['ld_tab']
+    st = _lib.stream_ptr()
+    P, dp = _lib.ptr, _lib.dp
+    dbg = self.debug
+
+    def lin(name, A, C, M=None, **kw):
+        m = meta[name]
+        _lib.rowlinear(A, m['K'], pk[name + '.img'], pk[name + '.b'], C, m['N'], m['NT'], M=M, stream=st,
+                       tag='jodo_rowlinear:' + name.split('.')[-1], **kw)
+
+    def ilin(name, Aimg, M, bias=True, **kw):
+        m = meta[name]
+        _lib.imglinear(Aimg, M, m['K'], pk[name + '.img'], pk[name + '.b'] if bias else None, m['N'], m['NT'], stream=st,
+                       tag='jodo_imglinear:' + name.split('.')[-1], **kw)
+
+    def ln(M, W, K, x, tab_off, row_mol, out_img=None, out32=None, y=None, yi=None, y2=None, y2i=None, ybias=None,
+           gate=-1, valid=None, y_img=None):
+        shift, scale = tab_off
+        a = _lib.WideLnArgs(M, W, K, dp(x), x.stride(0), dp(y), 0 if y is None else y.stride(0), dp(yi),
+                            dp(y2), 0 if y2 is None else y2.stride(0), dp(y2i), dp(ybias), dp(ws.tab), ld_tab, dp(row_mol),
+                            gate, shift, scale, dp(valid), dp(out32), 0 if out32 is None else out32.stride(0),
+                            dp(out_img), dp(y_img))
+        _lib.call('jodo_wide_ln', ctypes.byref(a), st)
+
+    # ---- per molecule: noise-level embedding (+ context) and all AdaLN tables
+    _lib.call('jodo_time_features', P(noise_level), P(pk['time.w8']), P(ws.feat), _c(B), st)
+    lin('time1', ws.feat, ws.t1, epi=_lib.EPI_ACT, act_out=_lib.ACT_GELU)
+    if d.cond_ch:
+        ctx = context.contiguous().float().reshape(B * d.cond_ch)
+        _lib.call('jodo_cond_in', P(ctx), P(pk['cond0.w']), P(pk['cond0.b']), P(ws.c1), _c(B * d.cond_ch), _c(D), st)
+        lin('cond2', ws.c1, ws.c2)
+        lin('condlin', ws.c2.view(B, d.cond_ch * D), ws.ctx)
+        lin('time3', ws.t1, ws.temb, epi=_lib.EPI_ADD, aux=ws.ctx)
+    else:
+        lin('time3', ws.t1, ws.temb)
+    _lib.call('jodo_act_image', P(ws.temb), _c(T), _c(B), _c(T), _c(_lib.ACT_SILU), P(ws.temb_img), st)
+    ilin('tab', ws.temb_img, B, C32=ws.tab)
+    # ---- per atom
+    _lib.call('jodo_gather_nodes', P(xh), P(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin), P(ws.xin), P(ws.pos[0]), st)
+    lin('node_emb', ws.xin, ws.ah[:, :D])
+    # ---- per edge: model-level embedding, adjacency heads
+    ea = _lib.WideEmbedArgs(ps, dp(edge_x), dp(cond_edge_x), dp(cond_x), d.ch, d.inn, ed, self.edge_th,
+                            self.spatial_cut_off, dp(ws.flags), dp(ws.tab), ld_tab, pk.ptr('gbf'), EDP, dp(ws.A0), EDP,
+                            dp(ws.extra))
+    _lib.call('jodo_wide_embed_in', ctypes.byref(ea), st)
+    ilin('edge_emb', ws.A0, R, C32=ws.e32)
+    K2 = 2 * ed
+    _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.A1), _c(K2), _c(ed), None, _c(0),
+              _c(0), st)
+
+    h = ws.ah[:, :D]
+    stride = tab_layer_stride(D)
+    for l in range(d.L):
+        p = f'b{l}.'
+        o = TAB_HEAD + l * stride
+        oe, oq, og = o + 6 * D, o + 6 * D + 6 * ed, o + 6 * D + 6 * ed + 2 * D
+        pin, pout = ws.pos[l & 1], ws.pos[(l + 1) & 1]
+        hout = ws.h[l & 1]
+        # distance features into the [dist | e] and [e | dist] operands; block edge_emb; norm1_edge; g0 | g1
+        _lib.call('jodo_wide_dist', ctypes.byref(ps), P(pin), P(ws.tab), _c(ld_tab), _c(og), P(pk[p + 'gbf']), _c(EDP),
+                  _c(ed), P(ws.A1), _c(K2), _c(0), P(ws.A4), _c(K2), _c(ed), st)
+        if l == 0:
+            ilin('h0', ws.A1, R, C32=ws.H)
+        ilin(p + 'emb', ws.A1, R, C32=ws.e1)
+        ln(R, ed, EDP, ws.e1, (oe, oe + ed), plan.row_mol, out_img=ws.en_img, valid=plan.row_g)
+        ilin(p + 'g01', ws.en_img, R, bias=False, epi=_lib.EPI_ACT, act_out=_lib.ACT_TANH, C16=ws.G)
+        # attention
+        ln(Nn, D, D, h, (o, o + D), plan.node_mol, out_img=ws.hn_img)
+        ilin(p + 'qkv', ws.hn_img, Nn, C16=ws.qkv)
+        aa = _lib.WideAttnArgs(Nn, D, d.H, d.X, d.sc, dp(ws.grp_row0), dp(ws.grp_len), dp(plan.row_j), dp(ws.qkv), ws.ldq,
+                               meta['qkp'], 2 * meta['qkp'], dp(ws.G), ws.ldg, meta['qkp'], dp(ws.extra), dp(ws.hnode))
+        _lib.call('jodo_wide_attn', ctypes.byref(aa), st)
+        # node path
+        ln(Nn, D, D, h, (o + 3 * D, o + 4 * D), plan.node_mol, out_img=ws.h2_img, out32=ws.h2, y=ws.hnode, gate=o + 2 * D,
+           y_img=ws.hnode_img)
+        ilin(p + 'n2e', ws.hnode_img, Nn, bias=False, C32=ws.P)
+        ilin(p + 'ff1', ws.h2_img, Nn, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.ff_img)
+        ilin(p + 'ff2', ws.ff_img, Nn, epi=_lib.EPI_GATED_RES, aux=ws.h2, gate=ws.tab[:, o + 5 * D:], row_mol=plan.node_mol,
+             C32=hout, Cimg=ws.hout_img)
+        ilin(p + 'ab', ws.hout_img, Nn, C32=ws.AB)
+        ilin(p + 'node_l', ws.hout_img, Nn, C32=ws.ah[:, D + l * meta['cnp']:])
+        # edge path: e2 = norm2(e + gate * node2edge(hnode[r] + hnode[c])), e_out = e2 + gate * FFN(e2)
+        ln(R, ed, EDP, ws.e32, (oe + 3 * ed, oe + 4 * ed), plan.row_mol, out_img=ws.e2_img, out32=ws.e2, y=ws.P,
+           yi=plan.row_g, y2=ws.P, y2i=plan.row_j, ybias=pk[p + 'n2e.bias'], gate=oe + 2 * ed, valid=plan.row_g)
+        ilin(p + 'ff3', ws.e2_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.f3_img)
+        ilin(p + 'ff4', ws.f3_img, R, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.row_mol,
+             C32=ws.e32)
+        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.A4), _c(K2), _c(0), P(ws.A1),
+                  _c(K2), _c(ed), st)
+        ilin(p + 'hfold', ws.A4, R, bias=False, epi=_lib.EPI_GATED_RES, aux=ws.H, gate=ws.ones, row_mol=plan.row_mol,
+             C32=ws.H)
+        # coordinate update
+        ilin(p + 'equi_in', ws.A4, R, bias=False, C32=ws.U)
+        ln(R, D, D, ws.U, (oq, oq + D), plan.row_mol, out_img=ws.u_img, y=ws.AB, yi=plan.row_g, y2=ws.AB[:, D:],
+           y2i=plan.row_j, valid=plan.row_g)
+        ilin(p + 'c0', ws.u_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.c0_img)
+        ilin(p + 'c2', ws.c0_img, R, bias=False, C32=ws.c3)
+        _lib.call('jodo_wide_equi_out', P(ws.grp_row0), P(ws.grp_len), P(plan.row_j), P(ws.c3), _c(64), P(ws.extra),
+                  _c(d.X), ctypes.c_float(meta['coord_scale'][l]), P(pin), P(pout), _c(Nn), st)
+        _lib.call('jodo_com', P(pout), ctypes.byref(ps), st)
+        if dbg is not None:
+            dbg.setdefault('blocks', []).append(dict(hnode=ws.hnode.clone(), h=hout.clone(), e=ws.e32.clone(),
+                                                     pos=pout.clone(), e1=ws.e1.clone(), e2=ws.e2.clone()))
+        h = hout
+    # ---- heads
+    lin('npred0', ws.ah, ws.n1, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)
+    lin('npred2', ws.n1, ws.n2, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)
+    lin('npred4', ws.n2, ws.ap)
+    out_x = torch.zeros(B, N, 3 + d.inn, device=xh.device, dtype=torch.float32)
+    _lib.call('jodo_node_out', P(ws.pos[d.L & 1]), P(ws.ap), _c(ws.ap.stride(0)), ctypes.byref(ps),
+              ctypes.c_void_p(ws.flags.data_ptr() + 4), _c(d.inn), P(out_x), st)
+    hp = meta['hp']
+    _lib.call('jodo_act_image', P(ws.H), _c(hp), _c(R), _c(hp), _c(_lib.ACT_SILU), P(ws.H_img), st)
+    ilin('ehead2', ws.H_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, C32=ws.X2)
+    tmp = torch.zeros(B, N, N, d.ch, device=xh.device, dtype=torch.float32)
+    _lib.call('jodo_wide_head_out', ctypes.byref(ps), P(ws.X2), _c(EDP), _c(ed // 2), P(pk['ehead4.w']), P(pk['ehead4.b']),
+              _c(d.ch), P(tmp), st)
+    out_e = torch.empty_like(tmp)
+    _lib.call('jodo_sym_edges', P(tmp), P(out_e), _c(B), _c(N), _c(d.ch), st)
+    if dbg is not None:
+        dbg.update(tab=ws.tab.clone(), temb=ws.temb.clone(), ah=ws.ah.clone(), H=ws.H.clone(), extra=ws.extra.clone(),
+                   plan=plan, flags=ws.flags.clone())
+    return out_x, out_e

@@ -41,6 +41,28 @@ def packed_to_dense(plan, x):
     return out.reshape(B, N, -1)
 
 
+def _fused_stages(model, dbg, trace, plan, inp, em, rep, D):
+    eh = dbg['eh']
+    rep.append(('e0', rel(tiles_to_dense_h(plan, eh, 64, model._plans[next(iter(model._plans))][1].eh_tile_bytes // 2,
+                                           group_first=False), trace['e0'] * em)))
+    for l, (b, ob) in enumerate(zip(dbg['blocks'], trace['blocks'])):
+        m = inp['node_mask'].double()
+        hn = act_image_to_rows(b['hn_img'], D)[:plan.Nn]
+        rep.append((f'b{l}.hn', rel(packed_to_dense(plan, hn), ob['hn'] * m)))
+        b['qkv'] = b['qkv'].permute(1, 0, 2).reshape(b['qkv'].shape[1], -1)      # piece-major -> rows
+        qk = ob['q'].shape[-1]
+        hq = qk // 2                      # q / k are stored as two head halves at columns [0, qk/2) and [D/2, D/2 + qk/2)
+        unsplit = lambda x: torch.cat([x[:, :hq], x[:, D // 2:D // 2 + hq]], dim=1)
+        rep.append((f'b{l}.q', rel(packed_to_dense(plan, unsplit(b['qkv'].float()[:, :D])), ob['q'] * m)))
+        rep.append((f'b{l}.k', rel(packed_to_dense(plan, unsplit(b['qkv'].float()[:, D:2 * D])), ob['k'] * m)))
+        rep.append((f'b{l}.v', rel(packed_to_dense(plan, b['qkv'].float()[:, 2 * D:]), ob['v'] * m)))
+        rep.append((f'b{l}.hnode', rel(packed_to_dense(plan, b['hnode']), ob['hnode'] * m)))
+        rep.append((f'b{l}.h', rel(packed_to_dense(plan, b['h']), ob['h'])))
+        e_rows = b['e'].reshape(plan.n_tiles, 16, 128, 4).permute(0, 2, 1, 3).reshape(plan.n_tiles * 128, 64)   # piece-major tiles
+        rep.append((f'b{l}.e', rel(plan.rows_to_dense(e_rows), ob['e'] * em)))
+        rep.append((f'b{l}.pos', rel(packed_to_dense(plan, b['pos'][:, :3]), ob['pos'])))
+
+
 def run_case(name, device='cuda', verbose=True):
     from jodo_b200.model import MODELS
     g, cfg = load_golden(name)
@@ -70,25 +92,17 @@ def run_case(name, device='cuda', verbose=True):
     rep.append(('temb', rel(dbg['temb'], trace['temb'])))
     rep.append(('h0', rel(packed_to_dense(plan, dbg['ah'][:, :D]), trace['h0'] * inp['node_mask'].double())))
     em = inp['edge_mask'].reshape(plan.B, plan.N, plan.N, 1).double()
-    eh = dbg['eh']
-    rep.append(('e0', rel(tiles_to_dense_h(plan, eh, 64, model._plans[next(iter(model._plans))][1].eh_tile_bytes // 2,
-                                           group_first=False), trace['e0'] * em)))
-    for l, (b, ob) in enumerate(zip(dbg['blocks'], trace['blocks'])):
+    if model.wide:
+        ed = model.dims.ed
         m = inp['node_mask'].double()
-        hn = act_image_to_rows(b['hn_img'], D)[:plan.Nn]
-        rep.append((f'b{l}.hn', rel(packed_to_dense(plan, hn), ob['hn'] * m)))
-        b['qkv'] = b['qkv'].permute(1, 0, 2).reshape(b['qkv'].shape[1], -1)      # piece-major -> rows
-        qk = ob['q'].shape[-1]
-        hq = qk // 2                      # q / k are stored as two head halves at columns [0, qk/2) and [D/2, D/2 + qk/2)
-        unsplit = lambda x: torch.cat([x[:, :hq], x[:, D // 2:D // 2 + hq]], dim=1)
-        rep.append((f'b{l}.q', rel(packed_to_dense(plan, unsplit(b['qkv'].float()[:, :D])), ob['q'] * m)))
-        rep.append((f'b{l}.k', rel(packed_to_dense(plan, unsplit(b['qkv'].float()[:, D:2 * D])), ob['k'] * m)))
-        rep.append((f'b{l}.v', rel(packed_to_dense(plan, b['qkv'].float()[:, 2 * D:]), ob['v'] * m)))
-        rep.append((f'b{l}.hnode', rel(packed_to_dense(plan, b['hnode']), ob['hnode'] * m)))
-        rep.append((f'b{l}.h', rel(packed_to_dense(plan, b['h']), ob['h'])))
-        e_rows = b['e'].reshape(plan.n_tiles, 16, 128, 4).permute(0, 2, 1, 3).reshape(plan.n_tiles * 128, 64)   # piece-major tiles
-        rep.append((f'b{l}.e', rel(plan.rows_to_dense(e_rows), ob['e'] * em)))
-        rep.append((f'b{l}.pos', rel(packed_to_dense(plan, b['pos'][:, :3]), ob['pos'])))
+        for l, (b, ob) in enumerate(zip(dbg['blocks'], trace['blocks'])):
+            rep.append((f'b{l}.e1', rel(plan.rows_to_dense(b['e1'][:, :ed], group_first=False), ob['e1'] * em)))
+            rep.append((f'b{l}.hnode', rel(packed_to_dense(plan, b['hnode']), ob['hnode'] * m)))
+            rep.append((f'b{l}.h', rel(packed_to_dense(plan, b['h']), ob['h'])))
+            rep.append((f'b{l}.e', rel(plan.rows_to_dense(b['e'][:, :ed]), ob['e'] * em)))
+            rep.append((f'b{l}.pos', rel(packed_to_dense(plan, b['pos'][:, :3]), ob['pos'])))
+    else:
+        _fused_stages(model, dbg, trace, plan, inp, em, rep, D)
     rx, re_ = g['ref_fp64']
     rep.append(('ah', rel(packed_to_dense(plan, dbg['ah'][:, :D]), trace['ah'][..., :D] * inp['node_mask'].double())))
     rep.append(('out.pos', rel(x[..., :3], rx[..., :3])))

@@ -57,7 +57,9 @@ def _struct_fields(name):
 @pytest.mark.parametrize('cname,pytype', [('jodo_plan', 'PlanStruct'), ('jodo_edge_embed_args', 'EdgeEmbedArgs'),
                                           ('jodo_attn_args', 'AttnArgs'), ('jodo_edge_update_args', 'EdgeUpdateArgs'),
                                           ('jodo_equi_args', 'EquiArgs'), ('jodo_edge_head_args', 'EdgeHeadArgs'),
-                                          ('jodo_imglinear_args', 'ImgLinearArgs')])
+                                          ('jodo_imglinear_args', 'ImgLinearArgs'),
+                                          ('jodo_wide_embed_args', 'WideEmbedArgs'), ('jodo_wide_ln_args', 'WideLnArgs'),
+                                          ('jodo_wide_attn_args', 'WideAttnArgs')])
 def test_ctypes_structs_mirror_header(cname, pytype):
     assert [f[0] for f in getattr(_lib, pytype)._fields_] == _struct_fields(cname)
 

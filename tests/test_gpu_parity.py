@@ -14,7 +14,8 @@ from stage_diag import run_case
 pytestmark = pytest.mark.gpu
 
 TOL = 5e-3
-CASES = ['qm9_first', 'qm9_first_default_init', 'qm9_selfcond', 'qm9_cond_ctx', 'geom_l8', 'geom_l10_first']
+CASES = ['qm9_first', 'qm9_first_default_init', 'qm9_selfcond', 'qm9_cond_ctx', 'geom_l8', 'geom_l10_first',
+         'geom_large']          # nf = 384: the wide path (jodo_b200/wide.py)
 
 
 @pytest.mark.parametrize('name', CASES)
