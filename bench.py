@@ -37,10 +37,12 @@ WORKLOADS = {
     'qm9': ('qm9_uncond', 2500, None, 'QM9 uncond 1000-step ancestral sampling, batch 2500, N<=29'),
     'geom': ('geom_l8', 512, 80, 'GEOM-Drugs uncond medium (n_layers=8, nf=256), batch 512, N<=80'),
     'geom_l10': ('geom_l10', 512, 80, 'GEOM-Drugs uncond medium with the reference default n_layers=10 (nf=256), batch 512, N<=80'),
+    'geom_large': ('geom_large', 512, 80, 'GEOM-Drugs uncond large (nf=384, n_layers=10), batch 512 per GPU, N<=80 '
+                   '(BASELINE configs[3]: batch 4096 over 8 GPUs)'),
     'qm9_cond': ('qm9_cond', 2500, None, 'QM9 conditional single-property, 50-step DPM-Solver++ (singlestep, order 2), '
                  'batch 2500; a step = one model evaluation'),
 }
-CPU_SAMPLE = {'qm9': 64, 'geom': 16, 'geom_l10': 16, 'qm9_cond': 64}
+CPU_SAMPLE = {'qm9': 64, 'geom': 16, 'geom_l10': 16, 'geom_large': 8, 'qm9_cond': 64}
 
 
 def parse():

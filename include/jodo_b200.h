@@ -245,6 +245,7 @@ typedef struct jodo_wide_ln_args {                      /* LayerNorm(eps 1e-6) +
   const int* valid;                       /* optional: rows with valid[row] < 0 are padding (zero outputs) */
   float* out32; int ldo;                  /* optional modulated fp32 rows (columns [W, min(Kimg, ldo)) are zeroed) */
   void* out_img; void* y_img;             /* fp16 images of the result / of y (either may be null) */
+  int x_f16, y_f16;                       /* != 0: x / (y and y2) are fp16 rows (strides in elements, % 8 == 0) */
 } jodo_wide_ln_args;
 
 typedef struct jodo_wide_attn_args {                    /* TransMixLayer message + aggregation (reference models/layers.py:157-186) */

@@ -49,7 +49,7 @@ TRACE = None           # set to a list to record (name, start_event, end_event) 
 
 def _account(name, fn):
     global LAUNCHES
-    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
+    LAUNCHES += KERNELS_PER_CALL.get(name.split(':')[0], 1)
     if TRACE is None:
         return fn()
     import torch
@@ -145,7 +145,7 @@ class WideLnArgs(ctypes.Structure):
     _fields_ = [('M', _I), ('W', _I), ('Kimg', _I), ('x', _P), ('ldx', _I), ('y', _P), ('ldy', _I), ('yi', _P),
                 ('y2', _P), ('ldy2', _I), ('y2i', _P), ('ybias', _P), ('tab', _P), ('ld_tab', _I), ('row_mol', _P),
                 ('off_gate', _I), ('off_shift', _I), ('off_scale', _I), ('valid', _P), ('out32', _P), ('ldo', _I),
-                ('out_img', _P), ('y_img', _P)]
+                ('out_img', _P), ('y_img', _P), ('x_f16', _I), ('y_f16', _I)]
 
 
 class WideAttnArgs(ctypes.Structure):
@@ -180,6 +180,6 @@ def plan_struct(plan):
                       dp(plan.row_mol))
 
 
-def call(name, *args):
+def call(name, *args, tag=None):
     f = getattr(lib(), name)
-    check(_account(name, lambda: f(*args)), name)
+    check(_account(tag or name, lambda: f(*args)), name)

@@ -184,7 +184,7 @@ int jodo_wide_dist(const jodo_plan* p, const float* pos4, const float* tab, int 
                    int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, void* stream) {
   if (!p) return fail("jodo_wide_dist: null plan");
   if (const char* m = check_plan(*p)) return fail(m);
-  if (!pos4 || !tab || !gbf || ed <= 0 || ld_gbf < ed - 1) return fail("jodo_wide_dist: bad arguments");
+  if (!pos4 || !tab || !gbf || ed <= 0 || ed % 8 || ld_gbf < ed || ld_gbf % 4) return fail("jodo_wide_dist: bad arguments");
   if (!img_ok(img1, K1, col1, ed) || !img_ok(img2, K2, col2, ed)) return fail("jodo_wide_dist: bad image");
   JODO_LAUNCH(jodo::launch_wide_dist(*p, pos4, tab, ld_tab, off_gbf, gbf, ld_gbf, ed, img1, K1, col1, img2, K2, col2, S(stream)),
               "jodo_wide_dist");
@@ -192,6 +192,7 @@ int jodo_wide_dist(const jodo_plan* p, const float* pos4, const float* tab, int 
 int jodo_wide_ln(const jodo_wide_ln_args* a, void* stream) {
   if (!a) return fail("jodo_wide_ln: null args");
   if (a->M <= 0 || a->W <= 0 || a->W % 8 || a->W > 512 || a->Kimg < a->W || a->Kimg % 64 || a->Kimg > 512) return fail("jodo_wide_ln: bad sizes");
+  if ((a->x_f16 && (a->ldx % 8)) || (a->y_f16 && a->y && ((a->ldy % 8) || (a->y2 && (a->ldy2 % 8))))) return fail("jodo_wide_ln: fp16 rows need strides % 8 == 0");
   if (!a->x || !a->tab || !a->row_mol || (a->ldx % 4) || (a->ld_tab % 4) || (a->off_shift % 4) || (a->off_scale % 4)) return fail("jodo_wide_ln: bad inputs");
   if (a->y && (a->ldy % 4)) return fail("jodo_wide_ln: bad addend stride");
   if (a->y2 && (!a->y || (a->ldy2 % 4))) return fail("jodo_wide_ln: y2 needs y");
@@ -201,8 +202,9 @@ int jodo_wide_ln(const jodo_wide_ln_args* a, void* stream) {
 }
 int jodo_wide_attn(const jodo_wide_attn_args* a, void* stream) {
   if (!a) return fail("jodo_wide_attn: null args");
-  if (a->Nn <= 0 || a->D <= 0 || a->H <= 0 || a->H > 32 || a->X < 0 || a->X >= a->H || a->X > 8 || a->D % a->H || a->sc <= 0)
-    return fail("jodo_wide_attn: bad sizes");
+  if (a->Nn <= 0 || a->D <= 0 || a->H <= 0 || a->H > 32 || a->X < 0 || a->X >= a->H || a->X > 8 || a->D % a->H || a->sc <= 0 ||
+      (a->D / a->H) % 4 || (((a->H - a->X) * a->sc) & 1) || (a->ldq % 4) || (a->ldg % 4) || (a->k_off % 2) || (a->v_off % 4) || (a->g1_off % 4))
+    return fail("jodo_wide_attn: bad sizes (needs D / H % 4 == 0, an even q/k width, 8-byte aligned row parts)");
   if (!a->grp_row0 || !a->grp_len || !a->row_j || !a->qkv || !a->G || !a->extra || !a->hnode) return fail("jodo_wide_attn: null buffer");
   JODO_LAUNCH(jodo::launch_wide_attn(*a, S(stream)), "jodo_wide_attn");
 }

@@ -46,7 +46,7 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 //   bits [0,2) epilogue | bit 2 fp32 rows | bit 3 fp16 rows | bit 4 fp16 image
 constexpr int il_mode(int epi, bool c32, bool c16, bool cimg) { return epi | (c32 ? 4 : 0) | (c16 ? 8 : 0) | (cimg ? 16 : 0); }
 
-template <int MODE>
+template <int MODE, int ACT = ACT_SILU>
 __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
   if (a.skip_if_zero && *a.skip_if_zero == 0) return;     // uniform conditioning: nothing to do (warp-uniform, before any setup)
   extern __shared__ uint8_t smem_raw[];
@@ -202,7 +202,9 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
           float4 o = *reinterpret_cast<const float4*>(src + it * 16 * IL_STG_ROW);
           o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           if (epi == EPI_ACT) {
-            if (MODE >= 0 || act == ACT_SILU) {     // the compiled modes use SiLU (node FFN)
+            if (MODE >= 0 && ACT == ACT_TANH) {     // compiled: tanh (lin_edge0 | lin_edge1 of the wide path)
+              o.x = tanh_fast(o.x); o.y = tanh_fast(o.y); o.z = tanh_fast(o.z); o.w = tanh_fast(o.w);
+            } else if (MODE >= 0 || act == ACT_SILU) {     // the other compiled modes use SiLU (FFNs)
               o.x = silu_fast(o.x); o.y = silu_fast(o.y); o.z = silu_fast(o.z); o.w = silu_fast(o.w);
             } else {
               o.x = act_apply(o.x, act); o.y = act_apply(o.y, act); o.z = act_apply(o.z, act); o.w = act_apply(o.w, act);
@@ -251,15 +253,15 @@ const char* check_imglinear(const ImgLinearArgs& a) {
 }
 
 namespace {
-template <int MODE>
+template <int MODE, int ACT = ACT_SILU>
 cudaError_t launch_mode(const ImgLinearArgs& a, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_imglinear<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, IL_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_imglinear<MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, IL_SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_imglinear<MODE><<<grid, IL_THREADS, IL_SMEM, stream>>>(a);
+  k_imglinear<MODE, ACT><<<grid, IL_THREADS, IL_SMEM, stream>>>(a);
   return cudaGetLastError();
 }
 }  // namespace
@@ -275,8 +277,11 @@ cudaError_t launch_imglinear(const ImgLinearArgs& a, int num_sms, cudaStream_t s
       case il_mode(EPI_STORE, true, false, false): return launch_mode<il_mode(EPI_STORE, true, false, false)>(a, grid, stream);      // node_i
       case il_mode(EPI_ACT, false, false, true): return launch_mode<il_mode(EPI_ACT, false, false, true)>(a, grid, stream);          // ff_linear1
       case il_mode(EPI_GATED_RES, true, false, true): return launch_mode<il_mode(EPI_GATED_RES, true, false, true)>(a, grid, stream);  // ff_linear2
+      case il_mode(EPI_GATED_RES, true, false, false): return launch_mode<il_mode(EPI_GATED_RES, true, false, false)>(a, grid, stream);  // wide: ff_linear4, head accumulation
       default: break;
     }
+  } else if (a.act_out == ACT_TANH && mode == il_mode(EPI_ACT, false, true, false)) {
+    return launch_mode<il_mode(EPI_ACT, false, true, false), ACT_TANH>(a, grid, stream);                                            // wide: tanh(lin_edge0 | lin_edge1)
   }
   return launch_mode<-1>(a, grid, stream);
 }

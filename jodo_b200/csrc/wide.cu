@@ -38,19 +38,37 @@ __device__ __forceinline__ void wload8(const float* p, float* v) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
+__device__ __forceinline__ void wload8h(const void* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+// 8 columns of row `r` of an fp32 or fp16 row-major matrix (ld in elements)
+__device__ __forceinline__ void wload8x(const float* base, bool f16, size_t r, int ld, int c, float* v) {
+  if (f16) wload8h(reinterpret_cast<const uint16_t*>(base) + r * ld + c, v);
+  else wload8(base + r * ld + c, v);
+}
 __device__ __forceinline__ float h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 
+// 8 consecutive floats through the read-only path (16-byte aligned)
+__device__ __forceinline__ void wldg8(const float* __restrict__ p, float* v) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
 // CondGaussianLayer features of one squared distance, columns [c0, c0 + 8): column 0 is x = d (1 + scale) + shift,
-// column k + 1 is exp(-0.5 ((x - mu_k) / sg_k)^2) / (a sg_k) = 2^(-((x - mu_k) c1_k)^2) c2_k  (gbf = {mu, c1, c2} x ldg)
+// column c >= 1 is exp(-0.5 ((x - mu) / sg)^2) / (a sg) = 2^(-((x - mu) c1)^2) c2 of Gaussian c - 1.  The constant
+// tables gbf = {mu, c1, c2} x ldg are indexed by COLUMN (entry 0 unused), so that a piece reads them as float4s.
 __device__ __forceinline__ void wgbf8(float x, const float* __restrict__ gbf, int ldg, int c0, int ed, float* v) {
+  float mu[8], c1[8], c2[8];
+  wldg8(gbf + c0, mu);
+  wldg8(gbf + ldg + c0, c1);
+  wldg8(gbf + 2 * ldg + c0, c2);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = c0 + i;
-    if (c == 0) v[i] = x;
-    else if (c < ed) {
-      const float u = (x - __ldg(gbf + c - 1)) * __ldg(gbf + ldg + c - 1);
-      v[i] = exp2f(-u * u) * __ldg(gbf + 2 * ldg + c - 1);
-    } else v[i] = 0.f;
+    const float u = (x - mu[i]) * c1[i];
+    v[i] = c == 0 ? x : (c < ed ? exp2f(-u * u) * c2[i] : 0.f);
   }
 }
 
@@ -197,24 +215,28 @@ __global__ void k_wide_ln(WideLnArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
     if (p < npw) {
-      wload8(a.x + (size_t)row * a.ldx + 8 * p, v[k]);
+      wload8x(a.x, a.x_f16 != 0, row, a.ldx, 8 * p, v[k]);
       if (a.y) {
         float y[8];
-        wload8(a.y + (size_t)iy * a.ldy + 8 * p, y);
+        wload8x(a.y, a.y_f16 != 0, iy, a.ldy, 8 * p, y);
         if (a.y_img) *wimg(a.y_img, row, 8 * p, a.Kimg) = wpack8(y);
         if (a.y2) {
           float y2[8];
-          wload8(a.y2 + (size_t)iy2 * a.ldy2 + 8 * p, y2);
+          wload8x(a.y2, a.y_f16 != 0, iy2, a.ldy2, 8 * p, y2);
 #pragma unroll
           for (int i = 0; i < 8; ++i) y[i] += y2[i];
         }
         if (a.ybias) {
+          float yb[8];
+          wldg8(a.ybias + 8 * p, yb);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] += __ldg(a.ybias + 8 * p + i);
+          for (int i = 0; i < 8; ++i) y[i] += yb[i];
         }
         if (a.off_gate >= 0) {
+          float gt[8];
+          wldg8(t + a.off_gate + 8 * p, gt);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[k][i] = fmaf(__ldg(t + a.off_gate + 8 * p + i), y[i], v[k][i]);
+          for (int i = 0; i < 8; ++i) v[k][i] = fmaf(gt[i], y[i], v[k][i]);
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[k][i] += y[i];
@@ -241,9 +263,11 @@ __global__ void k_wide_ln(WideLnArgs a) {
     if (p >= npk) continue;
     float o[8];
     if (p < npw) {
+      float sc[8], sh[8];
+      wldg8(t + a.off_scale + 8 * p, sc);     // the table stores 1 + scale
+      wldg8(t + a.off_shift + 8 * p, sh);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)             // the table stores 1 + scale
-        o[i] = fmaf((v[k][i] - mean) * rstd, __ldg(t + a.off_scale + 8 * p + i), __ldg(t + a.off_shift + 8 * p + i));
+      for (int i = 0; i < 8; ++i) o[i] = fmaf((v[k][i] - mean) * rstd, sc[i], sh[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -281,10 +305,14 @@ __global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
   for (int i = tid; i < gl; i += WA_THREADS) js[i] = a.row_j[row0 + i];
   __syncthreads();
   for (int i = warp; i < gl; i += 4) {
-    const uint16_t* krow = a.qkv + (size_t)js[i] * a.ldq + a.k_off;
-    const uint16_t* grow = a.G + (size_t)(row0 + i) * a.ldg;
+    const __half2* krow = reinterpret_cast<const __half2*>(a.qkv + (size_t)js[i] * a.ldq + a.k_off);
+    const __half2* grow = reinterpret_cast<const __half2*>(a.G + (size_t)(row0 + i) * a.ldg);
     float* pr = prod + warp * qkp;
-    for (int c = lane; c < qk; c += 32) pr[c] = qs[c] * h2f(krow[c]) * h2f(grow[c]);
+    for (int c = lane; c < (qk >> 1); c += 32) {                  // qk is even
+      const float2 kk = __half22float2(krow[c]), gg = __half22float2(grow[c]);
+      pr[2 * c] = qs[2 * c] * kk.x * gg.x;
+      pr[2 * c + 1] = qs[2 * c + 1] * kk.y * gg.y;
+    }
     __syncwarp();
     if (lane < S) {
       float s = 0.f;
@@ -306,15 +334,19 @@ __global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
     for (int i = 0; i < gl; ++i) lg[i * H + tid] *= rs;
   }
   __syncthreads();
-  for (int c = tid; c < D; c += WA_THREADS) {
+  for (int c = 4 * tid; c < D; c += 4 * WA_THREADS) {             // 4 columns of one head per thread (C % 4 == 0)
     const int h = c / C;
-    float acc = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < gl; ++i) {
-      const float vv = h2f(a.qkv[(size_t)js[i] * a.ldq + a.v_off + c]);
-      const float g1 = h2f(a.G[(size_t)(row0 + i) * a.ldg + a.g1_off + c]);
-      acc = fmaf(vv * g1, lg[i * H + h], acc);
+      const uint2 vu = *reinterpret_cast<const uint2*>(a.qkv + (size_t)js[i] * a.ldq + a.v_off + c);
+      const uint2 gu = *reinterpret_cast<const uint2*>(a.G + (size_t)(row0 + i) * a.ldg + a.g1_off + c);
+      const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vu.x)), v1 = __half22float2(*reinterpret_cast<const __half2*>(&vu.y));
+      const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&gu.x)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&gu.y));
+      const float al = lg[i * H + h];
+      acc[0] = fmaf(v0.x * g0.x, al, acc[0]); acc[1] = fmaf(v0.y * g0.y, al, acc[1]);
+      acc[2] = fmaf(v1.x * g1.x, al, acc[2]); acc[3] = fmaf(v1.y * g1.y, al, acc[3]);
     }
-    a.hnode[(size_t)g * D + c] = acc;
+    *reinterpret_cast<float4*>(a.hnode + (size_t)g * D + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 

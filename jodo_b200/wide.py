@@ -26,8 +26,8 @@ def supported(d) -> str | None:
         return f'model.nf must be a multiple of 128 up to 512 (got {d.D})'
     if d.ed % 8 or d.ed > EDP:
         return f'edge width nf/4 must be a multiple of 8 up to {EDP} (got {d.ed})'
-    if d.H > 32 or d.D % d.H:
-        return f'n_heads must divide nf and be at most 32 (got {d.H})'
+    if d.H > 32 or d.D % d.H or (d.D // d.H) % 4 or d.qk % 2:
+        return f'n_heads must divide nf into head widths that are multiples of 4, at most 32 heads (got {d.H})'
     if 2 * d.ch + d.ed > EDP:
         return f'edge_ch too large for the embedding image (got {d.ch})'
     return None
@@ -35,15 +35,16 @@ def supported(d) -> str | None:
 
 def _gbf_consts(sd, prefix, dev):
     """{mu, sqrt(0.5 log2 e) / sg, 1 / (a sg)} x EDP (reference models/layers.py:291-295, 332-333):
-    exp(-0.5 ((x - mu) / sg)^2) / (a sg) = 2^(-((x - mu) c1)^2) c2."""
+    exp(-0.5 ((x - mu) / sg)^2) / (a sg) = 2^(-((x - mu) c1)^2) c2.  Indexed by feature COLUMN: Gaussian k sits at
+    entry k + 1 (column 0 of the features is the raw x)."""
     mu = sd[prefix + '.means.weight'].float().view(-1)
     sg = sd[prefix + '.stds.weight'].float().view(-1).abs() + 1e-5
     a = (2 * 3.14159) ** 0.5
     out = torch.zeros(3, EDP, device=dev)
     k = mu.numel()
-    out[0, :k] = mu
-    out[1, :k] = (0.5 * 1.4426950408889634) ** 0.5 / sg
-    out[2, :k] = 1.0 / (a * sg)
+    out[0, 1:k + 1] = mu
+    out[1, 1:k + 1] = (0.5 * 1.4426950408889634) ** 0.5 / sg
+    out[2, 1:k + 1] = 1.0 / (a * sg)
     return out.reshape(-1)
 
 
@@ -153,7 +154,7 @@ class WideWorkspace:
         self.qkv = torch.zeros(Nn, self.ldq, device=dev, dtype=torch.float16)
         self.hnode, self.h2 = zf(Nn, D), f(Nn, D)
         self.P = zf(Nn, EDP)
-        self.AB = f(Nn, 2 * D)
+        self.AB = torch.zeros(Nn, 2 * D, device=dev, dtype=torch.float16)    # hoisted input_lin parts, gathered per edge
         self.n1, self.n2, self.ap = f(Nn, D), f(Nn, meta['npred2']['N']), f(Nn, meta['npred4']['N'])
         # per edge row
         self.A0, self.A1, self.A4 = eimg(EDP), eimg(2 * d.ed), eimg(2 * d.ed)
@@ -165,7 +166,7 @@ class WideWorkspace:
         self.H = zf(R, meta['hp'])
         self.H_img = eimg(meta['hp'])
         self.X2 = zf(R, EDP)
-        self.U = zf(R, D)
+        self.U = torch.zeros(R, D, device=dev, dtype=torch.float16)          # input_lin edge part (pre-LayerNorm)
         self.u_img, self.c0_img = eimg(D), eimg(D)
         self.c3 = zf(R, 64)
         self.extra = torch.zeros(R, device=dev, dtype=torch.uint8)
@@ -201,13 +202,14 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
                        tag='jodo_imglinear:' + name.split('.')[-1], **kw)
 
     def ln(M, W, K, x, tab_off, row_mol, out_img=None, out32=None, y=None, yi=None, y2=None, y2i=None, ybias=None,
-           gate=-1, valid=None, y_img=None):
+           gate=-1, valid=None, y_img=None, tag=''):
         shift, scale = tab_off
         a = _lib.WideLnArgs(M, W, K, dp(x), x.stride(0), dp(y), 0 if y is None else y.stride(0), dp(yi),
                             dp(y2), 0 if y2 is None else y2.stride(0), dp(y2i), dp(ybias), dp(ws.tab), ld_tab, dp(row_mol),
                             gate, shift, scale, dp(valid), dp(out32), 0 if out32 is None else out32.stride(0),
-                            dp(out_img), dp(y_img))
-        _lib.call('jodo_wide_ln', ctypes.byref(a), st)
+                            dp(out_img), dp(y_img), int(x.dtype == torch.float16),
+                            int(y is not None and y.dtype == torch.float16))
+        _lib.call('jodo_wide_ln', ctypes.byref(a), st, tag='jodo_wide_ln:' + tag)
 
     # ---- per molecule: noise-level embedding (+ context) and all AdaLN tables
     _lib.call('jodo_time_features', P(noise_level), P(pk['time.w8']), P(ws.feat), _c(B), st)
@@ -249,26 +251,26 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         if l == 0:
             ilin('h0', ws.A1, R, C32=ws.H)
         ilin(p + 'emb', ws.A1, R, C32=ws.e1)
-        ln(R, ed, EDP, ws.e1, (oe, oe + ed), plan.row_mol, out_img=ws.en_img, valid=plan.row_g)
+        ln(R, ed, EDP, ws.e1, (oe, oe + ed), plan.row_mol, out_img=ws.en_img, valid=plan.row_g, tag='e1')
         ilin(p + 'g01', ws.en_img, R, bias=False, epi=_lib.EPI_ACT, act_out=_lib.ACT_TANH, C16=ws.G)
         # attention
-        ln(Nn, D, D, h, (o, o + D), plan.node_mol, out_img=ws.hn_img)
+        ln(Nn, D, D, h, (o, o + D), plan.node_mol, out_img=ws.hn_img, tag='h1')
         ilin(p + 'qkv', ws.hn_img, Nn, C16=ws.qkv)
         aa = _lib.WideAttnArgs(Nn, D, d.H, d.X, d.sc, dp(ws.grp_row0), dp(ws.grp_len), dp(plan.row_j), dp(ws.qkv), ws.ldq,
                                meta['qkp'], 2 * meta['qkp'], dp(ws.G), ws.ldg, meta['qkp'], dp(ws.extra), dp(ws.hnode))
         _lib.call('jodo_wide_attn', ctypes.byref(aa), st)
         # node path
         ln(Nn, D, D, h, (o + 3 * D, o + 4 * D), plan.node_mol, out_img=ws.h2_img, out32=ws.h2, y=ws.hnode, gate=o + 2 * D,
-           y_img=ws.hnode_img)
+           y_img=ws.hnode_img, tag='h2')
         ilin(p + 'n2e', ws.hnode_img, Nn, bias=False, C32=ws.P)
         ilin(p + 'ff1', ws.h2_img, Nn, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.ff_img)
         ilin(p + 'ff2', ws.ff_img, Nn, epi=_lib.EPI_GATED_RES, aux=ws.h2, gate=ws.tab[:, o + 5 * D:], row_mol=plan.node_mol,
              C32=hout, Cimg=ws.hout_img)
-        ilin(p + 'ab', ws.hout_img, Nn, C32=ws.AB)
+        ilin(p + 'ab', ws.hout_img, Nn, C16=ws.AB)
         ilin(p + 'node_l', ws.hout_img, Nn, C32=ws.ah[:, D + l * meta['cnp']:])
         # edge path: e2 = norm2(e + gate * node2edge(hnode[r] + hnode[c])), e_out = e2 + gate * FFN(e2)
         ln(R, ed, EDP, ws.e32, (oe + 3 * ed, oe + 4 * ed), plan.row_mol, out_img=ws.e2_img, out32=ws.e2, y=ws.P,
-           yi=plan.row_g, y2=ws.P, y2i=plan.row_j, ybias=pk[p + 'n2e.bias'], gate=oe + 2 * ed, valid=plan.row_g)
+           yi=plan.row_g, y2=ws.P, y2i=plan.row_j, ybias=pk[p + 'n2e.bias'], gate=oe + 2 * ed, valid=plan.row_g, tag='e2')
         ilin(p + 'ff3', ws.e2_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.f3_img)
         ilin(p + 'ff4', ws.f3_img, R, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.row_mol,
              C32=ws.e32)
@@ -277,9 +279,9 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         ilin(p + 'hfold', ws.A4, R, bias=False, epi=_lib.EPI_GATED_RES, aux=ws.H, gate=ws.ones, row_mol=plan.row_mol,
              C32=ws.H)
         # coordinate update
-        ilin(p + 'equi_in', ws.A4, R, bias=False, C32=ws.U)
+        ilin(p + 'equi_in', ws.A4, R, bias=False, C16=ws.U)
         ln(R, D, D, ws.U, (oq, oq + D), plan.row_mol, out_img=ws.u_img, y=ws.AB, yi=plan.row_g, y2=ws.AB[:, D:],
-           y2i=plan.row_j, valid=plan.row_g)
+           y2i=plan.row_j, valid=plan.row_g, tag='equi')
         ilin(p + 'c0', ws.u_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.c0_img)
         ilin(p + 'c2', ws.c0_img, R, bias=False, C32=ws.c3)
         _lib.call('jodo_wide_equi_out', P(ws.grp_row0), P(ws.grp_len), P(plan.row_j), P(ws.c3), _c(64), P(ws.extra),

@@ -37,7 +37,7 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-20))
 
 
-@pytest.mark.parametrize('cfg_name,B,max_n', [('qm9_uncond', 2500, None), ('geom_l8', 512, 80)])
+@pytest.mark.parametrize('cfg_name,B,max_n', [('qm9_uncond', 2500, None), ('geom_l8', 512, 80), ('geom_large', 512, 80)])
 def test_full_size_invariants_and_independence(cfg_name, B, max_n):
     cfg, model = _model(cfg_name)
     b = synth.make_batch(cfg, B, seed=3, max_n=max_n, self_cond=True)
@@ -68,7 +68,7 @@ def test_full_size_invariants_and_independence(cfg_name, B, max_n):
     assert _rel(xs, x[:64, :Ns]) < 1e-4 and _rel(es, e[:64, :Ns, :Ns]) < 1e-4
 
 
-@pytest.mark.parametrize('cfg_name,B,max_n', [('qm9_uncond', 2500, None), ('geom_l8', 512, 80)])
+@pytest.mark.parametrize('cfg_name,B,max_n', [('qm9_uncond', 2500, None), ('geom_l8', 512, 80), ('geom_large', 256, 80)])
 def test_full_size_e3_equivariance(cfg_name, B, max_n):
     cfg, model = _model(cfg_name)
     b = synth.make_batch(cfg, B, seed=4, max_n=max_n, self_cond=True)
@@ -102,11 +102,13 @@ def _oracle(cfg, sd, b):
                        edge_x=c(b['edge_x']), noise_level=c(b['noise_level']), cond_x=c(b['cond_x']), cond_edge_x=c(b['cond_edge_x']))
 
 
-@pytest.mark.parametrize('n_nodes', [[1, 5, 1, 3], [2, 2, 7], [9], [1], [29, 1, 2, 29, 3]])
-def test_edge_cases_against_oracle(n_nodes):
+@pytest.mark.parametrize('cfg_name,n_nodes', [('qm9_uncond', [1, 5, 1, 3]), ('qm9_uncond', [2, 2, 7]), ('qm9_uncond', [9]),
+                                              ('qm9_uncond', [1]), ('qm9_uncond', [29, 1, 2, 29, 3]),
+                                              ('geom_large', [1, 5, 1, 3]), ('geom_large', [2, 30, 1]), ('geom_large', [1])])
+def test_edge_cases_against_oracle(cfg_name, n_nodes):
     """single-atom molecules (no edges: the denoiser sees only the atom's own features), two-atom molecules (groups of
-    one row), batches of one."""
-    cfg = configs.NAMED['qm9_uncond']()
+    one row), batches of one; on the fused path (nf = 256) and on the wide path (nf = 384)."""
+    cfg = configs.NAMED[cfg_name]()
     sd = synth_state_dict(param_spec(cfg), seed=2, perturb=True)
     model = MODELS[cfg.model.name](cfg)
     model.load_state_dict(sd, strict=True)
