@@ -259,7 +259,7 @@ typedef struct jodo_wide_attn_args {                    /* TransMixLayer message
 
 int jodo_wide_embed_in(const jodo_wide_embed_args* a, void* stream);
 int jodo_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1, void* img2, int K2,
-                  int col2, void* stream);                      /* fp32 rows -> fp16 columns [col, col + W) of one or two images */
+                  int col2, void* img3, int K3, int col3, void* stream);   /* fp32 rows -> fp16 columns [col, col + W) of up to three images */
 int jodo_wide_dist(const jodo_plan* p, const float* pos4, const float* tab, int ld_tab, int off_gbf, const float* gbf,
                    int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, void* stream);   /* mol_gnn.py:284-286 */
 int jodo_wide_ln(const jodo_wide_ln_args* a, void* stream);

@@ -175,10 +175,10 @@ int jodo_wide_embed_in(const jodo_wide_embed_args* a, void* stream) {
   JODO_LAUNCH(jodo::launch_wide_embed_in(*a, S(stream)), "jodo_wide_embed_in");
 }
 int jodo_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1, void* img2, int K2,
-                  int col2, void* stream) {
+                  int col2, void* img3, int K3, int col3, void* stream) {
   if (!src || M <= 0 || W <= 0 || (ld % 4) || ld < W) return fail("jodo_wide_put: bad source");
-  if (!img_ok(img1, K1, col1, W) || (img2 && !img_ok(img2, K2, col2, W))) return fail("jodo_wide_put: bad image");
-  JODO_LAUNCH(jodo::launch_wide_put(src, ld, M, W, valid, img1, K1, col1, img2, K2, col2, S(stream)), "jodo_wide_put");
+  if (!img_ok(img1, K1, col1, W) || (img2 && !img_ok(img2, K2, col2, W)) || (img3 && !img_ok(img3, K3, col3, W))) return fail("jodo_wide_put: bad image");
+  JODO_LAUNCH(jodo::launch_wide_put(src, ld, M, W, valid, img1, K1, col1, img2, K2, col2, img3, K3, col3, S(stream)), "jodo_wide_put");
 }
 int jodo_wide_dist(const jodo_plan* p, const float* pos4, const float* tab, int ld_tab, int off_gbf, const float* gbf,
                    int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, void* stream) {

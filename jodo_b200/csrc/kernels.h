@@ -102,7 +102,7 @@ using WideLnArgs = ::jodo_wide_ln_args;
 using WideAttnArgs = ::jodo_wide_attn_args;
 cudaError_t launch_wide_embed_in(const WideEmbedArgs& a, cudaStream_t st);
 cudaError_t launch_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1,
-                            void* img2, int K2, int col2, cudaStream_t st);
+                            void* img2, int K2, int col2, void* img3, int K3, int col3, cudaStream_t st);
 cudaError_t launch_wide_dist(const Plan& p, const float* pos, const float* tab, int ld_tab, int off_gbf, const float* gbf,
                              int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, cudaStream_t st);
 cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st);

@@ -136,10 +136,10 @@ __global__ void k_wide_embed_in(WideEmbedArgs a) {
   }
 }
 
-// ---- fp32 rows -> fp16 pieces at a column offset of up to two images (the edge part of the next block's
-// [dist | e] operand and of this block's [e | dist] operand).  One warp per row, W % 8 == 0.
+// ---- fp32 rows -> fp16 pieces at a column offset of up to three images (the edge part of the next block's
+// [dist | e] operand, of this block's [e | dist] operand, and this block's slot of the edge heads' operand).  One warp per row, W % 8 == 0.
 __global__ void k_wide_put(const float* __restrict__ src, int ld, int M, int W, const int* __restrict__ valid,
-                           void* img1, int K1, int col1, void* img2, int K2, int col2) {
+                           void* img1, int K1, int col1, void* img2, int K2, int col2, void* img3, int K3, int col3) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
   const bool live = !valid || valid[row] >= 0;
@@ -153,6 +153,7 @@ __global__ void k_wide_put(const float* __restrict__ src, int ld, int M, int W, 
     const uint4 o = wpack8(v);
     if (img1) *wimg(img1, row, col1 + 8 * p, K1) = o;
     if (img2) *wimg(img2, row, col2 + 8 * p, K2) = o;
+    if (img3) *wimg(img3, row, col3 + 8 * p, K3) = o;
   }
 }
 
@@ -187,26 +188,43 @@ __global__ void k_wide_dist(Plan p, const float4* __restrict__ pos, const float*
 // ---- LayerNorm (eps 1e-6, no affine) + modulation of  a = x + gate * (y[yi] + y2[y2i] + ybias), one warp per row,
 // W <= 512 columns.  Serves norm1/norm2 of atoms and edges (models/mol_gnn.py:296-297, 307-308, 313-314) and the
 // input_lin LayerNorm of the coordinate update (:73-79, with the hoisted per-atom parts as y, y2).
-__global__ void k_wide_ln(WideLnArgs a) {
+// V = 0: every option is a run-time flag.  V = 1 / 2 / 3 fix the options of the three per-edge uses at compile time
+// (coordinate branch: fp16 x + two gathered fp16 addends, image only; norm2_edge: fp32 x + two gathered fp32 addends +
+// bias, gated, fp32 rows + image; norm1_edge: fp32 x, image only).
+template <int V>
+__global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int rows_pad = (a.M + 127) / 128 * 128;
   if (row >= rows_pad) return;
   const int npw = a.W >> 3, npk = a.Kimg >> 3;
-  const bool live = row < a.M && (!a.valid || a.valid[row] >= 0);
+  const bool x16 = V == 0 ? a.x_f16 != 0 : V == 1;
+  const bool y16 = V == 0 ? a.y_f16 != 0 : V == 1;
+  const bool has_y = V == 0 ? a.y != nullptr : V != 3;
+  const bool has_y2 = V == 0 ? a.y2 != nullptr : V != 3;
+  const bool has_bias = V == 0 ? a.ybias != nullptr : V == 2;
+  const bool has_gate = V == 0 ? a.off_gate >= 0 : V == 2;
+  const bool has_o32 = V == 0 ? a.out32 != nullptr : V == 2;
+  const bool has_yimg = V == 0 ? a.y_img != nullptr : false;
+  const bool has_img = V == 0 ? a.out_img != nullptr : true;
+  // every per-row index is loaded up front (independent loads: one round trip instead of a dependent chain)
+  const bool inb = row < a.M;
+  const int vld = (inb && a.valid) ? __ldg(a.valid + row) : 0;
+  const int mol = inb ? __ldg(a.row_mol + row) : 0;
+  const int iy = (inb && has_y) ? (a.yi ? __ldg(a.yi + row) : row) : 0;
+  const int iy2 = (inb && has_y2) ? (a.y2i ? __ldg(a.y2i + row) : row) : 0;
+  const bool live = inb && vld >= 0;
   if (!live) {
     for (int p = lane; p < npk; p += 32) {
-      if (a.out_img) *wimg(a.out_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
-      if (a.y_img) *wimg(a.y_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
-      if (a.out32 && row < a.M && 8 * p < a.ldo) {
+      if (has_img) *wimg(a.out_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
+      if (has_yimg) *wimg(a.y_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
+      if (has_o32 && row < a.M && 8 * p < a.ldo) {
         *reinterpret_cast<float4*>(a.out32 + (size_t)row * a.ldo + 8 * p) = make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(a.out32 + (size_t)row * a.ldo + 8 * p + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     return;
   }
-  const float* t = a.tab + (size_t)a.row_mol[row] * a.ld_tab;
-  const int iy = a.y ? (a.yi ? a.yi[row] : row) : 0;
-  const int iy2 = a.y2 ? (a.y2i ? a.y2i[row] : row) : 0;
+  const float* t = a.tab + (size_t)mol * a.ld_tab;
   float v[2][8];
   float s = 0.f;
 #pragma unroll
@@ -215,24 +233,24 @@ __global__ void k_wide_ln(WideLnArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
     if (p < npw) {
-      wload8x(a.x, a.x_f16 != 0, row, a.ldx, 8 * p, v[k]);
-      if (a.y) {
+      wload8x(a.x, x16, row, a.ldx, 8 * p, v[k]);
+      if (has_y) {
         float y[8];
-        wload8x(a.y, a.y_f16 != 0, iy, a.ldy, 8 * p, y);
-        if (a.y_img) *wimg(a.y_img, row, 8 * p, a.Kimg) = wpack8(y);
-        if (a.y2) {
+        wload8x(a.y, y16, iy, a.ldy, 8 * p, y);
+        if (has_yimg) *wimg(a.y_img, row, 8 * p, a.Kimg) = wpack8(y);
+        if (has_y2) {
           float y2[8];
-          wload8x(a.y2, a.y_f16 != 0, iy2, a.ldy2, 8 * p, y2);
+          wload8x(a.y2, y16, iy2, a.ldy2, 8 * p, y2);
 #pragma unroll
           for (int i = 0; i < 8; ++i) y[i] += y2[i];
         }
-        if (a.ybias) {
+        if (has_bias) {
           float yb[8];
           wldg8(a.ybias + 8 * p, yb);
 #pragma unroll
           for (int i = 0; i < 8; ++i) y[i] += yb[i];
         }
-        if (a.off_gate >= 0) {
+        if (has_gate) {
           float gt[8];
           wldg8(t + a.off_gate + 8 * p, gt);
 #pragma unroll
@@ -244,7 +262,7 @@ __global__ void k_wide_ln(WideLnArgs a) {
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += v[k][i];
-    } else if (p < npk && a.y_img) {
+    } else if (p < npk && has_yimg) {
       *wimg(a.y_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
@@ -272,11 +290,11 @@ __global__ void k_wide_ln(WideLnArgs a) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
     }
-    if (a.out32 && 8 * p < a.ldo) {
+    if (has_o32 && 8 * p < a.ldo) {
       *reinterpret_cast<float4*>(a.out32 + (size_t)row * a.ldo + 8 * p) = make_float4(o[0], o[1], o[2], o[3]);
       *reinterpret_cast<float4*>(a.out32 + (size_t)row * a.ldo + 8 * p + 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
-    if (a.out_img) *wimg(a.out_img, row, 8 * p, a.Kimg) = wpack8(o);
+    if (has_img) *wimg(a.out_img, row, 8 * p, a.Kimg) = wpack8(o);
   }
 }
 
@@ -410,8 +428,8 @@ cudaError_t launch_wide_embed_in(const WideEmbedArgs& a, cudaStream_t st) {
   return WIDE_OK();
 }
 cudaError_t launch_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1,
-                            void* img2, int K2, int col2, cudaStream_t st) {
-  k_wide_put<<<(M + 7) / 8, 256, 0, st>>>(src, ld, M, W, valid, img1, K1, col1, img2, K2, col2);
+                            void* img2, int K2, int col2, void* img3, int K3, int col3, cudaStream_t st) {
+  k_wide_put<<<(M + 7) / 8, 256, 0, st>>>(src, ld, M, W, valid, img1, K1, col1, img2, K2, col2, img3, K3, col3);
   return WIDE_OK();
 }
 cudaError_t launch_wide_dist(const Plan& p, const float* pos, const float* tab, int ld_tab, int off_gbf, const float* gbf,
@@ -422,7 +440,11 @@ cudaError_t launch_wide_dist(const Plan& p, const float* pos, const float* tab, 
 }
 cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st) {
   const int rows_pad = (a.M + 127) / 128 * 128;
-  k_wide_ln<<<rows_pad / 8, 256, 0, st>>>(a);
+  const bool edge_img_only = a.out_img && !a.out32 && !a.y_img && !a.ybias && a.off_gate < 0;
+  if (edge_img_only && a.x_f16 && a.y && a.y2 && a.y_f16) k_wide_ln<1><<<rows_pad / 8, 256, 0, st>>>(a);
+  else if (a.out_img && a.out32 && !a.y_img && !a.x_f16 && a.y && a.y2 && !a.y_f16 && a.ybias && a.off_gate >= 0) k_wide_ln<2><<<rows_pad / 8, 256, 0, st>>>(a);
+  else if (edge_img_only && !a.x_f16 && !a.y) k_wide_ln<3><<<rows_pad / 8, 256, 0, st>>>(a);
+  else k_wide_ln<0><<<rows_pad / 8, 256, 0, st>>>(a);
   return WIDE_OK();
 }
 cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st) {

@@ -66,27 +66,25 @@ def pack_wide(pk, sd, d, add_lin):
     wep[:, ed:ed + 2 * d.ch] = we[:, :2 * d.ch]
     add_lin('edge_emb', wep, Bv('edge_emb'), 128)
     # ---- edge heads: layer 0 of edge_exist_mlp | edge_type_mlp is linear in the concatenated edge hiddens
-    # cat[e0, edge_0(e_1), ..] (reference models/mol_gnn.py:567-574), so the edge_i projections are folded into it and
-    # the heads' first hidden state H is accumulated block by block:  H = W0[:, :ed] e0 + sum_l (W0[:, s_l] We_l) e_l + b.
+    # cat[e0, edge_0(e_1), ..] (reference models/mol_gnn.py:567-574), so the edge_i projections are folded into it:
+    # H = W0[:, :ed] e0 + sum_l (W0[:, s_l] We_l) e_l + b is ONE GEMM over the operand [e0 | e_1 | .. | e_L] (slots of
+    # EDP columns, written block by block), K = (L + 1) EDP.
     w0 = torch.cat([W('edge_exist_mlp.0'), W('edge_type_mlp.0')], dim=0)            # [2ed, ed + L ce]
     b0 = torch.cat([Bv('edge_exist_mlp.0'), Bv('edge_type_mlp.0')]).clone()
     hp = ceil_to(2 * ed, 128)
-    wh = z(2 * ed, 2 * ed)
-    wh[:, ed:] = w0[:, :ed]                                   # operand [dist | e] of block 0: the e columns
+    wh = z(2 * ed, (L + 1) * EDP)
+    wh[:, :ed] = w0[:, :ed]
     for l in range(L):
         sl = w0[:, ed + l * d.ce:ed + (l + 1) * d.ce]
         b0 += sl @ Bv(f'edge_{l}')
-        wf = z(2 * ed, 2 * ed)
-        wf[:, :ed] = sl @ W(f'edge_{l}')                      # operand [e | dist]: the e columns
-        add_lin(f'b{l}.hfold', wf, None, 128, n_pad=hp)
-    add_lin('h0', wh, b0, 128, n_pad=hp)
+        wh[:, (l + 1) * EDP:(l + 1) * EDP + ed] = sl @ W(f'edge_{l}')
+    add_lin('hcat', wh, b0, 128, n_pad=hp)
     w2 = z(ed, hp)
     w2[:ed // 2, :ed] = W('edge_exist_mlp.2')
     w2[ed // 2:, ed:2 * ed] = W('edge_type_mlp.2')
     add_lin('ehead2', w2, torch.cat([Bv('edge_exist_mlp.2'), Bv('edge_type_mlp.2')]), 128)
     pk.add('ehead4.w', torch.cat([W('edge_exist_mlp.4'), W('edge_type_mlp.4')], dim=0))     # [ch, ed / 2]
     pk.add('ehead4.b', torch.cat([Bv('edge_exist_mlp.4'), Bv('edge_type_mlp.4')]))
-    pk.add('ones', torch.ones(hp, device=dev))
     pk.meta['hp'] = hp
     # ---- blocks
     scales = []
@@ -163,7 +161,7 @@ class WideWorkspace:
         self.ldg = meta['qkp'] + D
         self.G = torch.zeros(R, self.ldg, device=dev, dtype=torch.float16)
         self.f3_img = eimg(meta['f3p'])
-        self.H = zf(R, meta['hp'])
+        self.EH = eimg((d.L + 1) * EDP)                       # operand of the edge heads: [e0 | e_1 | .. | e_L]
         self.H_img = eimg(meta['hp'])
         self.X2 = zf(R, EDP)
         self.U = torch.zeros(R, D, device=dev, dtype=torch.float16)          # input_lin edge part (pre-LayerNorm)
@@ -171,7 +169,6 @@ class WideWorkspace:
         self.c3 = zf(R, 64)
         self.extra = torch.zeros(R, device=dev, dtype=torch.uint8)
         self.flags = torch.zeros(4, device=dev, dtype=torch.int32)            # [0] dist flag, [1] nan flag
-        self.ones = torch.ones(1, meta['hp'], device=dev).expand(B, meta['hp'])      # gate rows of the H accumulation
         # first edge row / partner count of every packed atom (groups are contiguous rows of one tile)
         rows = torch.arange(R, device=dev, dtype=torch.int32)
         ok = plan.row_g >= 0
@@ -234,8 +231,9 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
     _lib.call('jodo_wide_embed_in', ctypes.byref(ea), st)
     ilin('edge_emb', ws.A0, R, C32=ws.e32)
     K2 = 2 * ed
-    _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.A1), _c(K2), _c(ed), None, _c(0),
-              _c(0), st)
+    KH = (d.L + 1) * EDP
+    _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.A1), _c(K2), _c(ed), P(ws.EH), _c(KH),
+              _c(0), None, _c(0), _c(0), st)
 
     h = ws.ah[:, :D]
     stride = tab_layer_stride(D)
@@ -248,8 +246,6 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         # distance features into the [dist | e] and [e | dist] operands; block edge_emb; norm1_edge; g0 | g1
         _lib.call('jodo_wide_dist', ctypes.byref(ps), P(pin), P(ws.tab), _c(ld_tab), _c(og), P(pk[p + 'gbf']), _c(EDP),
                   _c(ed), P(ws.A1), _c(K2), _c(0), P(ws.A4), _c(K2), _c(ed), st)
-        if l == 0:
-            ilin('h0', ws.A1, R, C32=ws.H)
         ilin(p + 'emb', ws.A1, R, C32=ws.e1)
         ln(R, ed, EDP, ws.e1, (oe, oe + ed), plan.row_mol, out_img=ws.en_img, valid=plan.row_g, tag='e1')
         ilin(p + 'g01', ws.en_img, R, bias=False, epi=_lib.EPI_ACT, act_out=_lib.ACT_TANH, C16=ws.G)
@@ -275,9 +271,7 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         ilin(p + 'ff4', ws.f3_img, R, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.row_mol,
              C32=ws.e32)
         _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.A4), _c(K2), _c(0), P(ws.A1),
-                  _c(K2), _c(ed), st)
-        ilin(p + 'hfold', ws.A4, R, bias=False, epi=_lib.EPI_GATED_RES, aux=ws.H, gate=ws.ones, row_mol=plan.row_mol,
-             C32=ws.H)
+                  _c(K2), _c(ed), P(ws.EH), _c(KH), _c((l + 1) * EDP), st)
         # coordinate update
         ilin(p + 'equi_in', ws.A4, R, bias=False, C16=ws.U)
         ln(R, D, D, ws.U, (oq, oq + D), plan.row_mol, out_img=ws.u_img, y=ws.AB, yi=plan.row_g, y2=ws.AB[:, D:],
@@ -298,8 +292,7 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
     out_x = torch.zeros(B, N, 3 + d.inn, device=xh.device, dtype=torch.float32)
     _lib.call('jodo_node_out', P(ws.pos[d.L & 1]), P(ws.ap), _c(ws.ap.stride(0)), ctypes.byref(ps),
               ctypes.c_void_p(ws.flags.data_ptr() + 4), _c(d.inn), P(out_x), st)
-    hp = meta['hp']
-    _lib.call('jodo_act_image', P(ws.H), _c(hp), _c(R), _c(hp), _c(_lib.ACT_SILU), P(ws.H_img), st)
+    ilin('hcat', ws.EH, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.H_img)
     ilin('ehead2', ws.H_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, C32=ws.X2)
     tmp = torch.zeros(B, N, N, d.ch, device=xh.device, dtype=torch.float32)
     _lib.call('jodo_wide_head_out', ctypes.byref(ps), P(ws.X2), _c(EDP), _c(ed // 2), P(pk['ehead4.w']), P(pk['ehead4.b']),
@@ -307,6 +300,6 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
     out_e = torch.empty_like(tmp)
     _lib.call('jodo_sym_edges', P(tmp), P(out_e), _c(B), _c(N), _c(d.ch), st)
     if dbg is not None:
-        dbg.update(tab=ws.tab.clone(), temb=ws.temb.clone(), ah=ws.ah.clone(), H=ws.H.clone(), extra=ws.extra.clone(),
+        dbg.update(tab=ws.tab.clone(), temb=ws.temb.clone(), ah=ws.ah.clone(), extra=ws.extra.clone(),
                    plan=plan, flags=ws.flags.clone())
     return out_x, out_e
