@@ -320,13 +320,17 @@ def run_b200(args):
     pk = peaks()
     kf = roofline.per_edge_kernel_flops(d)
     kb = roofline.per_edge_kernel_bytes(d)
+    kh = {}                                             # HBM-bound row kernels of the wide path
+    if getattr(model, 'wide', False):
+        kf, kb, kh = roofline.wide_kernel_flops(d), {}, roofline.wide_kernel_bytes(d)
     kernels = {}
     for name, (t, c) in sorted(per.items(), key=lambda kv: -kv[1][0]):
         avg_ms = t / c
         ent = {'launches_per_step': c // reps // (2 if dpm else 1), 'avg_ms': round(avg_ms, 4), 'share': round(t / total_traced, 4)}
         if name in kf:
             ent['tflops'] = round(kf[name] * tot['edges'] / (avg_ms * 1e-3) / 1e12, 2)
-            ent['gbs'] = round(kb[name] * tot['edges'] / (avg_ms * 1e-3) / 1e9, 1)
+        if name in kb or name in kh:
+            ent['gbs'] = round((kb.get(name) or kh[name]) * tot['edges'] / (avg_ms * 1e-3) / 1e9, 1)
         kernels[name] = ent
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -340,6 +344,10 @@ def run_b200(args):
                 'frac': ach / pk['tf_sustained'], 'traffic': traffic,
                 'peak_source': pk['src'] + ' bf16 dense sustained (kernels run kind::f16, same nominal rate)',
                 'share_of_step': per[top][0] / total_traced}
+    elif top in kh:
+        ach = kh[top] * tot['edges'] / (per[top][0] / per[top][1] * 1e-3) / 1e9
+        roof = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
+                'traffic': traffic, 'peak_source': pk['src'] + ' HBM copy bandwidth', 'share_of_step': per[top][0] / total_traced}
     whole = {'tflops': tot['flops'] * K / (ms * 1e-3) / 1e12, 'hbm_gbs_alg': tot['bytes'] * K / (ms * 1e-3) / 1e9}
     whole['tensor_frac'] = whole['tflops'] / pk['tf_sustained']
     whole['hbm_frac'] = whole['hbm_gbs_alg'] / pk['hbm']

@@ -33,6 +33,34 @@ def per_edge_kernel_bytes(d):
     }
 
 
+def wide_kernel_flops(d):
+    """Wide path (nf = 384): algorithmic FLOP per real directed edge for one launch of each per-edge GEMM."""
+    D, ed, qk, r, X = d.D, d.ed, d.qk, d.r, d.X
+    return {
+        'jodo_imglinear:emb': mm(2 * ed, ed),
+        'jodo_imglinear:g01': mm(ed, qk) + mm(ed, D),
+        'jodo_imglinear:ff3': mm(ed, r * ed),
+        'jodo_imglinear:ff4': mm(r * ed, ed),
+        'jodo_imglinear:equi_in': mm(2 * ed, D),
+        'jodo_imglinear:c0': mm(D, D),
+        'jodo_imglinear:c2': mm(D, 1 + X),
+    }
+
+
+def wide_kernel_bytes(d):
+    """Wide path: algorithmic HBM bytes per real directed edge for one launch of each row kernel -- the rows it must
+    read and write once (per-atom operands and per-molecule tables are L2-resident and not counted)."""
+    D, ed, qk = d.D, d.ed, d.qk
+    return {
+        'jodo_wide_ln:equi': 2 * D + 2 * D,                 # fp16 pre-LayerNorm rows in, fp16 operand image out
+        'jodo_wide_ln:e2': 4 * ed + 4 * ed + 2 * ed,        # fp32 edge state in, fp32 e2 + fp16 image out
+        'jodo_wide_ln:e1': 4 * ed + 2 * ed,
+        'jodo_wide_attn': 2 * (qk + D) + 1,                 # tanh(lin_edge0 | lin_edge1) rows + adjacency bits
+        'jodo_wide_dist': 2 * 2 * ed,
+        'jodo_wide_put': 4 * ed + 3 * 2 * ed,
+    }
+
+
 def flops_alg(n, d):
     """F_alg(n) of SURVEY.md §8d: algorithmic FLOP of one denoiser call on one molecule of n atoms."""
     D, ed, T, L, r, qk, inn, ch, cn, ce, X = d.D, d.ed, d.T, d.L, d.r, d.qk, d.inn, d.ch, d.cn, d.ce, d.X

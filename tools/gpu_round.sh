@@ -11,6 +11,7 @@ tail -5 $OUT/pytest_gpu.log
 timeout 600 python bench.py --steps 30 --warmup 5 > $OUT/bench_qm9.json 2> $OUT/bench_qm9.err; echo "bench qm9 rc=$?"
 timeout 600 python bench.py --workload geom --steps 20 --warmup 3 > $OUT/bench_geom.json 2> $OUT/bench_geom.err; echo "bench geom rc=$?"
 timeout 600 python bench.py --workload geom_l10 --steps 20 --warmup 3 --no-cpu-baseline > $OUT/bench_geom_l10.json 2> $OUT/bench_geom_l10.err; echo "bench geom_l10 rc=$?"
+timeout 600 python bench.py --workload geom_large --steps 10 --warmup 3 > $OUT/bench_geom_large.json 2> $OUT/bench_geom_large.err; echo "bench geom_large rc=$?"
 timeout 600 python bench.py --workload qm9_cond --steps 20 --warmup 4 > $OUT/bench_qm9_cond.json 2> $OUT/bench_qm9_cond.err; echo "bench qm9_cond rc=$?"
 timeout 300 python bench.py --impl reference --steps 4 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "bench ref rc=$?"
 kill $SMI

@@ -4,5 +4,10 @@ OUT=gpurun_out/sanitize
 mkdir -p $OUT
 for tool in memcheck racecheck synccheck; do
   timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/$tool.log 2>&1
-  echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke:" $OUT/$tool.log | tail -3
+  echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke" $OUT/$tool.log | tail -3
+done
+# the nf = 384 wide path (row kernels of csrc/wide.cu + the GEMM)
+for tool in memcheck racecheck; do
+  timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke('geom_large')" > $OUT/wide_$tool.log 2>&1
+  echo "wide $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke" $OUT/wide_$tool.log | tail -3
 done
