@@ -255,6 +255,7 @@ typedef struct jodo_wide_attn_args {                    /* TransMixLayer message
   const uint16_t* G; int ldg, g1_off;                          /* fp16 rows per edge: tanh(lin_edge0) at 0, tanh(lin_edge1) at g1_off */
   const uint8_t* extra;
   float* hnode;                           /* out [Nn, D] */
+  int max_gl;                             /* largest partner count (sizes the per-CTA logit buffer; <= 255) */
 } jodo_wide_attn_args;
 
 int jodo_wide_embed_in(const jodo_wide_embed_args* a, void* stream);

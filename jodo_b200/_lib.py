@@ -151,7 +151,7 @@ class WideLnArgs(ctypes.Structure):
 class WideAttnArgs(ctypes.Structure):
     _fields_ = [('Nn', _I), ('D', _I), ('H', _I), ('X', _I), ('sc', _I), ('grp_row0', _P), ('grp_len', _P), ('row_j', _P),
                 ('qkv', _P), ('ldq', _I), ('k_off', _I), ('v_off', _I), ('G', _P), ('ldg', _I), ('g1_off', _I),
-                ('extra', _P), ('hnode', _P)]
+                ('extra', _P), ('hnode', _P), ('max_gl', _I)]
 
 
 def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None, row_mol=None,

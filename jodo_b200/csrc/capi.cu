@@ -205,6 +205,7 @@ int jodo_wide_attn(const jodo_wide_attn_args* a, void* stream) {
   if (a->Nn <= 0 || a->D <= 0 || a->H <= 0 || a->H > 32 || a->X < 0 || a->X >= a->H || a->X > 8 || a->D % a->H || a->sc <= 0 ||
       (a->D / a->H) % 4 || (((a->H - a->X) * a->sc) & 1) || (a->ldq % 4) || (a->ldg % 4) || (a->k_off % 2) || (a->v_off % 4) || (a->g1_off % 4))
     return fail("jodo_wide_attn: bad sizes (needs D / H % 4 == 0, an even q/k width, 8-byte aligned row parts)");
+  if (a->max_gl < 1 || a->max_gl > 255) return fail("jodo_wide_attn: max_gl must be in [1, 255]");
   if (!a->grp_row0 || !a->grp_len || !a->row_j || !a->qkv || !a->G || !a->extra || !a->hnode) return fail("jodo_wide_attn: null buffer");
   JODO_LAUNCH(jodo::launch_wide_attn(*a, S(stream)), "jodo_wide_attn");
 }

@@ -311,8 +311,8 @@ __global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
   const int qkp = (qk + 31) & ~31;
   float* qs = wsm;                          // [qkp] q of the target, pre-scaled
   float* prod = qs + qkp;                   // [4 warps][qkp]
-  float* lg = prod + 4 * qkp;               // [128][H] logits -> alpha
-  int* js = reinterpret_cast<int*>(lg + 128 * H);   // [128] source atoms
+  float* lg = prod + 4 * qkp;               // [max_gl][H] logits -> alpha
+  int* js = reinterpret_cast<int*>(lg + a.max_gl * H);   // [max_gl] source atoms
   if (gl <= 0) {
     for (int c = tid; c < D; c += WA_THREADS) a.hnode[(size_t)g * D + c] = 0.f;
     return;
@@ -449,7 +449,7 @@ cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st) {
 }
 cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st) {
   const int S = a.H - a.X, qkp = (S * a.sc + 31) & ~31;
-  const size_t smem = (size_t)(5 * qkp + 128 * a.H) * sizeof(float) + 128 * sizeof(int);
+  const size_t smem = (size_t)(5 * qkp + a.max_gl * a.H) * sizeof(float) + a.max_gl * sizeof(int);
   k_wide_attn<<<a.Nn, WA_THREADS, smem, st>>>(a);
   return WIDE_OK();
 }

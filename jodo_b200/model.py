@@ -112,54 +112,59 @@ class _DGTBase(nn.Module):
         self._spec = param_spec(config)
         build_param_tree(self, self._spec)
         self.load_state_dict(synth_state_dict(self._spec, seed=int(getattr(config, 'seed', 0))))
-        self._packed = None
+        self._packed = {}
         self._packed_key = None
+        self._fp_pending = None
+        self.force_wide = False    # tests: run an nf = 256 model through the wide path
         self._plans = {}
         self.debug = None          # set to a dict to capture intermediates (tests)
 
     # ---- caches -------------------------------------------------------------------------------------
     def refresh_weights(self):
         """Drop the packed weight images; the next call re-derives them from the parameters."""
-        self._packed = None
+        self._packed = {}
         self._fp_pending = None
 
     @staticmethod
     def _fingerprint(params):
         return torch.stack(torch._foreach_norm(params))          # one 2-norm per parameter tensor, on the device
 
-    def _weights(self):
-        """Packed fp16 operand images of the parameters.  They are re-derived when a parameter is replaced or written
-        in place through the tensor itself (optimizer steps, ``load_state_dict``, ``p.copy_``: ``_version`` changes) or
-        after ``refresh_weights()`` / ``invalidate_packed_weights()``.  Writes through ``p.data`` (the reference's
-        ``ExponentialMovingAverage.copy_to`` / ``restore``, models/ema.py:55, 77) bypass the version counter;
-        wrap those with ``watch_data_writers``.  As a backstop every call enqueues a fingerprint of the parameters
-        (no host sync); a later call that finds it different from the one taken at pack time raises."""
+    def _weights(self, use_wide=None):
+        """Packed fp16 operand images of the parameters (one set per path: fused edge-tile kernels / wide path).  They
+        are re-derived when a parameter is replaced or written in place through the tensor itself (optimizer steps,
+        ``load_state_dict``, ``p.copy_``: ``_version`` changes) or after ``refresh_weights()`` /
+        ``invalidate_packed_weights()``.  Writes through ``p.data`` (the reference's
+        ``ExponentialMovingAverage.copy_to`` / ``restore``, models/ema.py:55, 77) bypass the version counter; wrap those
+        with ``watch_data_writers``.  As a backstop every call enqueues a fingerprint of the parameters (no host sync);
+        a later call that finds it different from the one taken at pack time raises."""
+        use_wide = self.wide if use_wide is None else use_wide
         params = list(self.parameters())
         key = tuple((p.data_ptr(), p._version) for p in params) + (_WEIGHT_EPOCH[0],)
-        pend = getattr(self, '_fp_pending', None)
+        if key != self._packed_key:
+            self._packed, self._packed_key, self._fp_pending = {}, key, None
+        pend = self._fp_pending
         if pend is not None and pend.query():
             self._fp_pending = None
-            if self._packed is not None and key == self._packed_key and not torch.equal(self._fp_host, self._packed_fp):
-                self._packed = None
+            if self._packed and not torch.equal(self._fp_host, self._packed_fp):
+                self._packed = {}
                 raise _lib.JodoError('parameters were modified through .data after the weight images were packed, so '
                                      'earlier calls used stale weights; call model.refresh_weights() after such writes '
                                      '(or wrap the writer with jodo_b200.model.watch_data_writers)')
-        if self._packed is None or key != self._packed_key:
+        if use_wide not in self._packed:
             sd = {k: v for k, v in self.state_dict().items()}
-            dev = params[0].device
-            self._packed = pack_model(sd, self.dims, dev)
-            self._packed_key = key
-            self._packed_fp = self._fingerprint(params).cpu()
-            self._fp_host = torch.empty_like(self._packed_fp).pin_memory()
-            self._fp_pending = None
+            if not self._packed:
+                self._packed_fp = self._fingerprint(params).cpu()
+                self._fp_host = torch.empty_like(self._packed_fp).pin_memory()
+                self._fp_pending = None
+            self._packed[use_wide] = pack_model(sd, self.dims, params[0].device, fused=not use_wide)
         elif self._fp_pending is None:
             self._fp_host.copy_(self._fingerprint(params), non_blocking=True)
             self._fp_pending = torch.cuda.Event()
             self._fp_pending.record()
-        return self._packed
+        return self._packed[use_wide]
 
     def _plan(self, node_mask, edge_mask):
-        key = (node_mask.data_ptr(), tuple(node_mask.shape), node_mask._version, edge_mask.data_ptr())
+        key = (node_mask.data_ptr(), tuple(node_mask.shape), node_mask._version, edge_mask.data_ptr(), self.force_wide)
         hit = self._plans.get(key)
         if hit is None:
             plan = Plan(node_mask)
@@ -169,11 +174,16 @@ class _DGTBase(nn.Module):
             if not torch.equal((edge_mask.reshape(B, N, N) > 0).float(), want):
                 raise ValueError('edge_mask must be node_mask x node_mask without the diagonal '
                                  '(reference sampling.py:197-199)')
-            ws = (wide.WideWorkspace if self.wide else _Workspace)(plan, self.dims, self._weights().meta, node_mask.device)
+            use_wide = self.wide or self.force_wide or plan.loose
+            if use_wide and not self.wide:
+                why = wide.supported(self.dims)
+                if why:
+                    raise NotImplementedError('jodo_b200 wide path (molecules with more than 129 atoms): ' + why)
+            ws = (wide.WideWorkspace if use_wide else _Workspace)(plan, self.dims, self._weights(use_wide).meta, node_mask.device)
             if len(self._plans) > 4:
                 self._plans.clear()
             # the masks are kept alive with the entry so that the allocator cannot hand their addresses to new masks
-            hit = self._plans[key] = (plan, ws, _lib.plan_struct(plan), node_mask, edge_mask)
+            hit = self._plans[key] = (plan, ws, _lib.plan_struct(plan), node_mask, edge_mask, use_wide)
         return hit
 
     # ---- forward ------------------------------------------------------------------------------------
@@ -190,9 +200,10 @@ class _DGTBase(nn.Module):
         d = self.dims
         if d.cond_ch and context is None:
             raise ValueError('cond_DGT_concat needs a context')
-        pk = self._weights()
+        hit = self._plan(node_mask, edge_mask)
+        plan, ws, ps, use_wide = hit[0], hit[1], hit[2], hit[5]
+        pk = self._weights(use_wide)
         meta = pk.meta
-        plan, ws, ps = self._plan(node_mask, edge_mask)[:3]
         B, N = plan.B, plan.N
         st = _lib.stream_ptr()
         L = _lib.lib()
@@ -201,7 +212,7 @@ class _DGTBase(nn.Module):
         xh, edge_x, noise_level = c32(xh), c32(edge_x), c32(noise_level)
         if cond_x is not None:
             cond_x, cond_edge_x = c32(cond_x), c32(cond_edge_x)
-        if self.wide:
+        if use_wide:
             return wide.forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_edge_x, context)
         D, T, ld_tab = d.D, d.T, meta['ld_tab']
 

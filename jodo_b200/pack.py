@@ -169,11 +169,13 @@ def _gbf_table4(sd, prefix, dev):
     return out.reshape(-1)
 
 
-def pack_model(sd, dims, device):
+def pack_model(sd, dims, device, fused=None):
     """sd: name -> tensor (reference names, no 'module.' prefix); dims: jodo_b200.params.Dims."""
     d = dims
     D, ed, T, L = d.D, d.ed, d.T, d.L
-    fused = D == 256                       # fused edge-tile kernels; other sizes take the wide path (jodo_b200/wide.py)
+    if fused is None:
+        fused = D == 256                   # fused edge-tile kernels; other sizes take the wide path (jodo_b200/wide.py)
+    assert not fused or D == 256, 'the fused edge-tile kernels are built for nf = 256'
     ntb = 256 if D % 256 == 0 else 128     # N tile of the wide per-molecule / per-atom GEMMs
     sd = {k: v.detach().to(device, torch.float32) for k, v in sd.items()}
     pk = Packed(device)

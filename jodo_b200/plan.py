@@ -21,11 +21,16 @@ import torch
 TILE = 128
 MAX_GROUPS = 64          # groups per tile (the attention kernel's group-sum MMA has 64 output slots)
 WINDOW = 256             # open tiles considered by the best-fit packer
+MAX_LOOSE = 255          # largest group of a loose plan (the wide attention kernel keeps one group's logits in shared memory)
 
 
 class Plan:
-    def __init__(self, node_mask: torch.Tensor, device=None):
-        """node_mask: [B, N, 1] or [B, N] (0/1).  Built on the host (one D2H copy of the mask)."""
+    def __init__(self, node_mask: torch.Tensor, device=None, loose=None):
+        """node_mask: [B, N, 1] or [B, N] (0/1).  Built on the host (one D2H copy of the mask).
+
+        loose: groups are laid out back to back and may straddle tiles -- the layout of the wide path
+        (jodo_b200/wide.py), whose row kernels do not need a group inside one tile; it lifts the 129-atom limit of the
+        fused edge-tile kernels.  None = loose only when some molecule has more than TILE + 1 atoms."""
         m = node_mask.detach()
         if m.dim() == 3:
             m = m[..., 0]
@@ -34,8 +39,12 @@ class Plan:
         self.B, self.N = B, N
         n = m.sum(1).astype(np.int64)
         self.n_nodes = n
-        if n.max(initial=0) - 1 > TILE:
-            raise ValueError(f'molecules with more than {TILE + 1} atoms are not supported (got {int(n.max())})')
+        if loose is None:
+            loose = bool(n.max(initial=0) - 1 > TILE)
+        self.loose = loose
+        if n.max(initial=0) - 1 > (MAX_LOOSE if loose else TILE):
+            raise ValueError(f'molecules with more than {(MAX_LOOSE if loose else TILE) + 1} atoms are not supported '
+                             f'(got {int(n.max())})')
         if n.min(initial=1) < 1:
             raise ValueError('every molecule needs at least one atom')
         bb, ii = np.nonzero(m)                                   # (b, i) lexicographic == packed order
@@ -55,7 +64,14 @@ class Plan:
         open_tiles = []                                          # [tile id, rows used, groups]
         ngroups = []
         n_tiles = 0
-        for b in range(B):
+        if loose:
+            g_off = np.zeros(self.Nn + 1, dtype=np.int64)
+            np.cumsum(gl_node, out=g_off[1:])
+            g_tile[:] = g_off[:-1] // TILE
+            g_start[:] = g_off[:-1] % TILE                       # the group continues into the next tile(s)
+            n_tiles = int((g_off[-1] + TILE - 1) // TILE)
+            ngroups = [0] * n_tiles
+        for b in range(0 if not loose else B, B):
             gl = int(n[b]) - 1
             if gl <= 0:
                 continue
@@ -109,7 +125,8 @@ class Plan:
             rows = g_tile[v] * TILE + g_start[v] + k
             row_g[rows] = v
             row_j[rows] = j
-            row_meta[rows] = (g_start[v] | (gl_node[v] << 8) | (g_idx[v] << 16)).astype(np.uint32)
+            if not loose:                                        # (start row, length, group index) inside the tile
+                row_meta[rows] = (g_start[v] | (gl_node[v] << 8) | (g_idx[v] << 16)).astype(np.uint32)
             row_mol[rows] = node_mol[v]
         self.utilization = tot / float(R)
         dev = device if device is not None else node_mask.device
@@ -122,6 +139,9 @@ class Plan:
         self.row_meta = t(row_meta.view(np.int32))
         self.tile_ngroups = t(np.asarray(ngroups, dtype=np.int32))
         self.row_mol = t(row_mol)
+        self.grp_row0 = t((g_tile * TILE + g_start).astype(np.int32))      # first edge row / partner count per packed atom
+        self.grp_len = t(gl_node.astype(np.int32))
+        self.max_group = int(gl_node.max(initial=0))
         self.device = dev
 
     # ---- helpers used by tests (pure index bookkeeping) -------------------------------------------

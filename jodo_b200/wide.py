@@ -169,14 +169,7 @@ class WideWorkspace:
         self.c3 = zf(R, 64)
         self.extra = torch.zeros(R, device=dev, dtype=torch.uint8)
         self.flags = torch.zeros(4, device=dev, dtype=torch.int32)            # [0] dist flag, [1] nan flag
-        # first edge row / partner count of every packed atom (groups are contiguous rows of one tile)
-        rows = torch.arange(R, device=dev, dtype=torch.int32)
-        ok = plan.row_g >= 0
-        first = (rows & ~127) + (plan.row_meta & 255)
-        self.grp_row0 = torch.zeros(Nn, device=dev, dtype=torch.int32)
-        self.grp_len = torch.zeros(Nn, device=dev, dtype=torch.int32)
-        self.grp_row0[plan.row_g[ok].long()] = first[ok]
-        self.grp_len[plan.row_g[ok].long()] = ((plan.row_meta[ok] >> 8) & 255)
+        self.grp_row0, self.grp_len = plan.grp_row0, plan.grp_len
 
 
 def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_edge_x, context):
@@ -253,7 +246,8 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         ln(Nn, D, D, h, (o, o + D), plan.node_mol, out_img=ws.hn_img, tag='h1')
         ilin(p + 'qkv', ws.hn_img, Nn, C16=ws.qkv)
         aa = _lib.WideAttnArgs(Nn, D, d.H, d.X, d.sc, dp(ws.grp_row0), dp(ws.grp_len), dp(plan.row_j), dp(ws.qkv), ws.ldq,
-                               meta['qkp'], 2 * meta['qkp'], dp(ws.G), ws.ldg, meta['qkp'], dp(ws.extra), dp(ws.hnode))
+                               meta['qkp'], 2 * meta['qkp'], dp(ws.G), ws.ldg, meta['qkp'], dp(ws.extra), dp(ws.hnode),
+                               max(plan.max_group, 1))
         _lib.call('jodo_wide_attn', ctypes.byref(aa), st)
         # node path
         ln(Nn, D, D, h, (o + 3 * D, o + 4 * D), plan.node_mol, out_img=ws.h2_img, out32=ws.h2, y=ws.hnode, gate=o + 2 * D,

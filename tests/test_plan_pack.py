@@ -54,9 +54,44 @@ def test_plan_invariants(n_list):
         assert torch.equal(p.rows_to_dense(p.dense_to_rows(dense, gf), gf), dense)
 
 
+@pytest.mark.parametrize('n_list', [[130], [181, 40, 2, 1], [256, 3], [5, 9, 1]])
+def test_loose_plan_lifts_the_tile_limit(n_list):
+    """Molecules with more than 129 atoms (GEOM-Drugs goes to 181): groups back to back, straddling tiles -- the layout
+    of the wide path.  Same enumeration, same group tables."""
+    m = _mask(n_list)
+    p = Plan(m, loose=True if max(n_list) <= 129 else None)
+    assert p.loose
+    n = np.array(n_list)
+    assert p.n_edges == int((n * (n - 1)).sum()) and p.n_tiles == max(1, -(-p.n_edges // TILE))
+    row_g, row_j = p.row_g.numpy(), p.row_j.numpy()
+    valid = row_g >= 0
+    assert valid[:p.n_edges].all() and not valid[p.n_edges:].any()          # no holes
+    r0, gl = p.grp_row0.numpy(), p.grp_len.numpy()
+    mol = p.node_mol.numpy()
+    assert p.max_group == int(n.max()) - 1
+    for g in range(p.Nn):
+        assert gl[g] == n[mol[g]] - 1
+        rows = np.arange(r0[g], r0[g] + gl[g])
+        assert (row_g[rows] == g).all() and (np.diff(row_j[rows]) > 0).all()
+        assert (p.row_mol.numpy()[rows] == mol[g]).all()
+    dense = torch.randn(p.B, p.N, p.N, 2) * (m * m.transpose(1, 2)).unsqueeze(-1) * (1 - torch.eye(p.N))[None, :, :, None]
+    assert torch.equal(p.rows_to_dense(p.dense_to_rows(dense)), dense)
+
+
+def test_tight_plan_group_tables():
+    p = Plan(_mask([2, 9, 1, 17, 29, 3]))
+    assert not p.loose
+    row_g = p.row_g.numpy()
+    for g in range(p.Nn):
+        rows = np.arange(p.grp_row0[g], p.grp_row0[g] + p.grp_len[g])
+        assert (row_g[rows] == g).all()
+
+
 def test_plan_rejects_oversized_and_empty_molecules():
     with pytest.raises(ValueError):
-        Plan(_mask([130]))
+        Plan(_mask([130]), loose=False)
+    with pytest.raises(ValueError):
+        Plan(_mask([257]))
     with pytest.raises(ValueError):
         Plan(_mask([0, 4], N=4))
 
