@@ -18,9 +18,10 @@ namespace {
 
 constexpr int WCHUNK = 128 * 128;      // bytes of one image chunk: [128 rows][64 fp16]
 
-__device__ __forceinline__ float wsum(float v) {
+template <int LANES>
+__device__ __forceinline__ float wsum(float v, unsigned mask) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
 // address of the 16-byte piece holding columns [col8, col8 + 8) of `row` in an image with K columns
@@ -137,13 +138,13 @@ __global__ void k_wide_embed_in(WideEmbedArgs a) {
 }
 
 // ---- fp32 rows -> fp16 pieces at a column offset of up to three images (the edge part of the next block's
-// [dist | e] operand, of this block's [e | dist] operand, and this block's slot of the edge heads' operand).  One warp per row, W % 8 == 0.
+// [dist | e] operand, of this block's [e | dist] operand, and this block's slot of the edge heads' operand).  W % 8 == 0.
 __global__ void k_wide_put(const float* __restrict__ src, int ld, int M, int W, const int* __restrict__ valid,
                            void* img1, int K1, int col1, void* img2, int K2, int col2, void* img3, int K3, int col3) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= M) return;
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + ((threadIdx.x >> 4) & 1), lane = threadIdx.x & 15;
+  if (row >= M) return;                                          // two rows per warp, 16 lanes each
   const bool live = !valid || valid[row] >= 0;
-  for (int p = lane; p < (W >> 3); p += 32) {
+  for (int p = lane; p < (W >> 3); p += 16) {
     float v[8];
     if (live) wload8(src + (size_t)row * ld + 8 * p, v);
     else {
@@ -162,8 +163,8 @@ __global__ void k_wide_put(const float* __restrict__ src, int ld, int M, int W, 
 __global__ void k_wide_dist(Plan p, const float4* __restrict__ pos, const float* __restrict__ tab, int ld_tab,
                             int off_gbf, const float* __restrict__ gbf, int ld_gbf, int ed, void* img1, int K1, int col1,
                             void* img2, int K2, int col2) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= p.n_tiles * 128) return;
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + ((threadIdx.x >> 4) & 1), lane = threadIdx.x & 15;
+  if (row >= p.n_tiles * 128) return;                            // two rows per warp, 16 lanes each
   const int g = p.row_g[row];
   float x = 0.f;
   if (g >= 0) {
@@ -172,7 +173,7 @@ __global__ void k_wide_dist(Plan p, const float4* __restrict__ pos, const float*
     const float* tr = tab + (size_t)p.row_mol[row] * ld_tab + off_gbf;
     x = (dx * dx + dy * dy + dz * dz) * tr[0] + tr[1];
   }
-  for (int q = lane; q < (ed >> 3); q += 32) {
+  for (int q = lane; q < (ed >> 3); q += 16) {
     float v[8];
     if (g >= 0) wgbf8(x, gbf, ld_gbf, 8 * q, ed, v);
     else {
@@ -191,9 +192,14 @@ __global__ void k_wide_dist(Plan p, const float4* __restrict__ pos, const float*
 // V = 0: every option is a run-time flag.  V = 1 / 2 / 3 fix the options of the three per-edge uses at compile time
 // (coordinate branch: fp16 x + two gathered fp16 addends, image only; norm2_edge: fp32 x + two gathered fp32 addends +
 // bias, gated, fp32 rows + image; norm1_edge: fp32 x, image only).
-template <int V>
+// LANES = 32: one warp per row (up to 64 pieces); LANES = 16: two rows per warp (up to 16 pieces each: the per-edge
+// rows of width ed <= 128, where a full warp would leave most lanes idle).
+template <int V, int LANES>
 __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LANES;
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + ((threadIdx.x & 31) / LANES);
+  const int lane = threadIdx.x & (LANES - 1);
+  const unsigned hm = LANES == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));     // the lanes of this row
   const int rows_pad = (a.M + 127) / 128 * 128;
   if (row >= rows_pad) return;
   const int npw = a.W >> 3, npk = a.Kimg >> 3;
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
   const int iy2 = (inb && has_y2) ? (a.y2i ? __ldg(a.y2i + row) : row) : 0;
   const bool live = inb && vld >= 0;
   if (!live) {
-    for (int p = lane; p < npk; p += 32) {
+    for (int p = lane; p < npk; p += LANES) {
       if (has_img) *wimg(a.out_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
       if (has_yimg) *wimg(a.y_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
       if (has_o32 && row < a.M && 8 * p < a.ldo) {
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    const int p = lane + 32 * k;
+    const int p = lane + LANES * k;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
     if (p < npw) {
@@ -266,18 +272,18 @@ __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
       *wimg(a.y_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  const float mean = wsum(s) / (float)a.W;
+  const float mean = wsum<LANES>(s, hm) / (float)a.W;
   float q = 0.f;
 #pragma unroll
   for (int k = 0; k < 2; ++k)
-    if (lane + 32 * k < npw) {
+    if (lane + LANES * k < npw) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; q += d * d; }
     }
-  const float rstd = rsqrtf(wsum(q) / (float)a.W + 1e-6f);
+  const float rstd = rsqrtf(wsum<LANES>(q, hm) / (float)a.W + 1e-6f);
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    const int p = lane + 32 * k;
+    const int p = lane + LANES * k;
     if (p >= npk) continue;
     float o[8];
     if (p < npw) {
@@ -429,22 +435,29 @@ cudaError_t launch_wide_embed_in(const WideEmbedArgs& a, cudaStream_t st) {
 }
 cudaError_t launch_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1,
                             void* img2, int K2, int col2, void* img3, int K3, int col3, cudaStream_t st) {
-  k_wide_put<<<(M + 7) / 8, 256, 0, st>>>(src, ld, M, W, valid, img1, K1, col1, img2, K2, col2, img3, K3, col3);
+  k_wide_put<<<(M + 15) / 16, 256, 0, st>>>(src, ld, M, W, valid, img1, K1, col1, img2, K2, col2, img3, K3, col3);
   return WIDE_OK();
 }
 cudaError_t launch_wide_dist(const Plan& p, const float* pos, const float* tab, int ld_tab, int off_gbf, const float* gbf,
                              int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, cudaStream_t st) {
-  k_wide_dist<<<p.n_tiles * 128 / 8, 256, 0, st>>>(p, reinterpret_cast<const float4*>(pos), tab, ld_tab, off_gbf, gbf,
+  k_wide_dist<<<p.n_tiles * 128 / 16, 256, 0, st>>>(p, reinterpret_cast<const float4*>(pos), tab, ld_tab, off_gbf, gbf,
                                                    ld_gbf, ed, img1, K1, col1, img2, K2, col2);
   return WIDE_OK();
 }
 cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st) {
   const int rows_pad = (a.M + 127) / 128 * 128;
   const bool edge_img_only = a.out_img && !a.out32 && !a.y_img && !a.ybias && a.off_gate < 0;
-  if (edge_img_only && a.x_f16 && a.y && a.y2 && a.y_f16) k_wide_ln<1><<<rows_pad / 8, 256, 0, st>>>(a);
-  else if (a.out_img && a.out32 && !a.y_img && !a.x_f16 && a.y && a.y2 && !a.y_f16 && a.ybias && a.off_gate >= 0) k_wide_ln<2><<<rows_pad / 8, 256, 0, st>>>(a);
-  else if (edge_img_only && !a.x_f16 && !a.y) k_wide_ln<3><<<rows_pad / 8, 256, 0, st>>>(a);
-  else k_wide_ln<0><<<rows_pad / 8, 256, 0, st>>>(a);
+  const bool narrow = a.Kimg <= 128;                 // two rows per warp
+  const int g32 = rows_pad / 8, g16 = rows_pad / 16;
+  if (edge_img_only && a.x_f16 && a.y && a.y2 && a.y_f16 && !narrow) k_wide_ln<1, 32><<<g32, 256, 0, st>>>(a);
+  else if (a.out_img && a.out32 && !a.y_img && !a.x_f16 && a.y && a.y2 && !a.y_f16 && a.ybias && a.off_gate >= 0) {
+    if (narrow) k_wide_ln<2, 16><<<g16, 256, 0, st>>>(a);
+    else k_wide_ln<2, 32><<<g32, 256, 0, st>>>(a);
+  } else if (edge_img_only && !a.x_f16 && !a.y) {
+    if (narrow) k_wide_ln<3, 16><<<g16, 256, 0, st>>>(a);
+    else k_wide_ln<3, 32><<<g32, 256, 0, st>>>(a);
+  } else if (narrow) k_wide_ln<0, 16><<<g16, 256, 0, st>>>(a);
+  else k_wide_ln<0, 32><<<g32, 256, 0, st>>>(a);
   return WIDE_OK();
 }
 cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st) {
