@@ -194,7 +194,7 @@ __global__ void k_wide_dist(Plan p, const float4* __restrict__ pos, const float*
 // bias, gated, fp32 rows + image; norm1_edge: fp32 x, image only).
 // LANES = 32: one warp per row (up to 64 pieces); LANES = 16: two rows per warp (up to 16 pieces each: the per-edge
 // rows of width ed <= 128, where a full warp would leave most lanes idle).
-template <int V, int LANES>
+template <int V, int LANES, int KP = 2>      // KP pieces of 8 columns per lane: LANES * KP * 8 >= Kimg
 __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
   constexpr int RPW = 32 / LANES;
   const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + ((threadIdx.x & 31) / LANES);
@@ -231,10 +231,10 @@ __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
     return;
   }
   const float* t = a.tab + (size_t)mol * a.ld_tab;
-  float v[2][8];
+  float v[KP][8];
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < KP; ++k) {
     const int p = lane + LANES * k;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
@@ -275,14 +275,14 @@ __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
   const float mean = wsum<LANES>(s, hm) / (float)a.W;
   float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < KP; ++k)
     if (lane + LANES * k < npw) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; q += d * d; }
     }
   const float rstd = rsqrtf(wsum<LANES>(q, hm) / (float)a.W + 1e-6f);
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < KP; ++k) {
     const int p = lane + LANES * k;
     if (p >= npk) continue;
     float o[8];
@@ -449,7 +449,10 @@ cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st) {
   const bool edge_img_only = a.out_img && !a.out32 && !a.y_img && !a.ybias && a.off_gate < 0;
   const bool narrow = a.Kimg <= 128;                 // two rows per warp
   const int g32 = rows_pad / 8, g16 = rows_pad / 16;
-  if (edge_img_only && a.x_f16 && a.y && a.y2 && a.y_f16 && !narrow) k_wide_ln<1, 32><<<g32, 256, 0, st>>>(a);
+  if (edge_img_only && a.x_f16 && a.y && a.y2 && a.y_f16 && !narrow) {
+    if (a.Kimg <= 384) k_wide_ln<1, 16, 3><<<g16, 256, 0, st>>>(a);      // two rows per warp, three pieces per lane
+    else k_wide_ln<1, 32><<<g32, 256, 0, st>>>(a);
+  }
   else if (a.out_img && a.out32 && !a.y_img && !a.x_f16 && a.y && a.y2 && !a.y_f16 && a.ybias && a.off_gate >= 0) {
     if (narrow) k_wide_ln<2, 16><<<g16, 256, 0, st>>>(a);
     else k_wide_ln<2, 32><<<g32, 256, 0, st>>>(a);

@@ -88,8 +88,9 @@ def test_full_size_e3_equivariance(cfg_name, B, max_n):
     xr, er = _call(model, b, xh=move(b['xh']).cuda(), cond_x=move(b['cond_x']).cuda())
     want = x.clone()
     want[..., :3] = x[..., :3] @ Q.t().cuda()
-    # the rotated problem rounds differently in the fp16 operands: tolerance of one forward
-    assert _rel(xr[..., :3], want[..., :3]) < TOL
+    # the rotated problem rounds differently in the fp16 operands, so the two sides carry independent errors of one
+    # forward each; positions (perturbed coord_norm.scale = 0.3, sums over up to 79 partners) get 2 TOL
+    assert _rel(xr[..., :3], want[..., :3]) < 2 * TOL
     assert _rel(xr[..., 3:], x[..., 3:]) < TOL
     assert _rel(er, e) < TOL
 
