@@ -76,6 +76,31 @@ def test_bad_arguments_fail_before_any_launch(lib):
     assert lib.jodo_imglinear(ctypes.byref(a), None) == 1 and b'multiple of 64' in lib.jodo_last_error_string()
     e = _lib.EdgeUpdateArgs()
     assert lib.jodo_edge_update(ctypes.byref(e), None) == 1
+    # wide path (nf = 384)
+    assert lib.jodo_wide_ln(None, None) == 1 and lib.jodo_wide_attn(None, None) == 1 and lib.jodo_wide_embed_in(None, None) == 1
+    w = _lib.WideLnArgs()
+    w.M, w.W, w.Kimg = 128, 100, 128
+    assert lib.jodo_wide_ln(ctypes.byref(w), None) == 1 and b'bad sizes' in lib.jodo_last_error_string()
+    t = _lib.WideAttnArgs()
+    t.Nn, t.D, t.H, t.X, t.sc, t.max_gl = 10, 384, 16, 2, 27, 300
+    assert lib.jodo_wide_attn(ctypes.byref(t), None) == 1 and b'max_gl' in lib.jodo_last_error_string()
+    t.max_gl, t.H = 80, 64
+    assert lib.jodo_wide_attn(ctypes.byref(t), None) == 1 and b'bad sizes' in lib.jodo_last_error_string()
+    assert lib.jodo_wide_put(None, 0, 0, 0, None, None, 0, 0, None, 0, 0, None, 0, 0, None) == 1
+    assert lib.jodo_wide_dist(None, None, None, 0, 0, None, 0, 0, None, 0, 0, None, 0, 0, None) == 1
+    assert lib.jodo_wide_equi_out(None, None, None, None, 0, None, 0, ctypes.c_float(0), None, None, 0, None) == 1
+    assert lib.jodo_wide_head_out(None, None, 0, 0, None, None, 0, None, None) == 1
+
+
+def test_unsupported_sizes_raise_by_name():
+    """nf = 256 -> fused kernels, multiples of 128 up to 512 -> wide path, anything else names the key."""
+    from jodo_b200 import configs
+    from jodo_b200.model import MODELS
+    cfg = configs.NAMED['geom_large']()
+    assert MODELS[cfg.model.name](cfg).wide
+    cfg.model.nf = 320
+    with pytest.raises(NotImplementedError, match='model.nf'):
+        MODELS[cfg.model.name](cfg)
 
 
 def test_product_path_has_no_cpu_fallback():
