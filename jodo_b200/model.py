@@ -23,6 +23,7 @@ from .plan import Plan
 
 _c = ctypes.c_int
 _WEIGHT_EPOCH = [0]
+FINGERPRINT_EVERY = 16      # calls between two parameter fingerprints (the backstop against writes through .data)
 
 
 def invalidate_packed_weights():
@@ -115,6 +116,7 @@ class _DGTBase(nn.Module):
         self._packed = {}
         self._packed_key = None
         self._fp_pending = None
+        self._fp_tick = 0
         self.force_wide = False    # tests: run an nf = 256 model through the wide path
         self._plans = {}
         self.debug = None          # set to a dict to capture intermediates (tests)
@@ -135,8 +137,8 @@ class _DGTBase(nn.Module):
         ``load_state_dict``, ``p.copy_``: ``_version`` changes) or after ``refresh_weights()`` /
         ``invalidate_packed_weights()``.  Writes through ``p.data`` (the reference's
         ``ExponentialMovingAverage.copy_to`` / ``restore``, models/ema.py:55, 77) bypass the version counter; wrap those
-        with ``watch_data_writers``.  As a backstop every call enqueues a fingerprint of the parameters (no host sync);
-        a later call that finds it different from the one taken at pack time raises."""
+        with ``watch_data_writers``.  As a backstop every FINGERPRINT_EVERY-th call enqueues a fingerprint of the
+        parameters (no host sync); a later call that finds it different from the one taken at pack time raises."""
         use_wide = self.wide if use_wide is None else use_wide
         params = list(self.parameters())
         key = tuple((p.data_ptr(), p._version) for p in params) + (_WEIGHT_EPOCH[0],)
@@ -150,6 +152,7 @@ class _DGTBase(nn.Module):
                 raise _lib.JodoError('parameters were modified through .data after the weight images were packed, so '
                                      'earlier calls used stale weights; call model.refresh_weights() after such writes '
                                      '(or wrap the writer with jodo_b200.model.watch_data_writers)')
+        self._fp_tick += 1
         if use_wide not in self._packed:
             sd = {k: v for k, v in self.state_dict().items()}
             if not self._packed:
@@ -157,7 +160,7 @@ class _DGTBase(nn.Module):
                 self._fp_host = torch.empty_like(self._packed_fp).pin_memory()
                 self._fp_pending = None
             self._packed[use_wide] = pack_model(sd, self.dims, params[0].device, fused=not use_wide)
-        elif self._fp_pending is None:
+        elif self._fp_pending is None and self._fp_tick % FINGERPRINT_EVERY == 0:
             self._fp_host.copy_(self._fingerprint(params), non_blocking=True)
             self._fp_pending = torch.cuda.Event()
             self._fp_pending.record()

@@ -75,7 +75,7 @@ def test_data_writes_need_refresh_and_are_caught():
     # backstop: an unannounced .data write is reported by a later call instead of being used silently forever
     _scale_some(model, 1.25, through_data=True)
     with pytest.raises(_lib.JodoError):
-        for _ in range(4):
+        for _ in range(40):
             _call(model, inp)
             torch.cuda.synchronize()
     x3, _ = _call(model, inp)                                 # the error dropped the stale images

@@ -21,4 +21,8 @@ for k in k_attn k_equi k_edge_update k_imglinear; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 12 -c 2 -f -o $OUT/prof_$k \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/prof_$k.log 2>&1; echo "ncu $k rc=$?"
 done
+for k in k_wide_ln k_wide_attn; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -f -o $OUT/prof_$k \
+      python bench.py --workload geom_large --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/prof_$k.log 2>&1; echo "ncu $k rc=$?"
+done
 cat $OUT/bench_qm9.json | head -c 3000
