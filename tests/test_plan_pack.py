@@ -81,9 +81,9 @@ def test_loose_plan_lifts_the_tile_limit(n_list):
 def test_tight_plan_group_tables():
     p = Plan(_mask([2, 9, 1, 17, 29, 3]))
     assert not p.loose
-    row_g = p.row_g.numpy()
+    row_g, r0, gl = p.row_g.numpy(), p.grp_row0.numpy(), p.grp_len.numpy()
     for g in range(p.Nn):
-        rows = np.arange(p.grp_row0[g], p.grp_row0[g] + p.grp_len[g])
+        rows = np.arange(r0[g], r0[g] + gl[g])
         assert (row_g[rows] == g).all()
 
 
