@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 6
+#define JODO_ABI_VERSION 7
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -206,11 +206,13 @@ int jodo_sym_edges(const float* tmp, float* out, int B, int N, int ch, void* str
 
 /* Fused posterior-mean update + noise of one ancestral reverse step (reference sampling.py:569-589 with the noise
  * construction of models/utils.py:67-99): dense [B,N,F] / [B,N,N,ch] tensors, raw standard-normal draws supplied by
- * the caller ([B,N,3], [B,N,F-3], [B,ch,N,N]); writes x_new, x_mean, e_new, e_mean. */
+ * the caller ([B,N,3], [B,N,F-3], [B,ch,N,N]); writes x_new, x_mean, e_new, e_mean.  coef_dev, when not null, is a
+ * device array {c_x, c_pred, sigma} that overrides the by-value coefficients: a captured CUDA graph of one reverse step
+ * is replayed with per-step coefficients written into it (jodo_b200/sampler.py, graph=True). */
 int jodo_ancestral_update(const float* x, const float* pred, const float* raw_pos, const float* raw_feat,
                           const float* node_mask, const float* edge_x, const float* edge_pred, const float* raw_edge,
                           const float* edge_mask, int B, int N, int F, int ch, float c_x, float c_pred, float sigma,
-                          float* x_new, float* x_mean, float* e_new, float* e_mean, void* stream);
+                          const float* coef_dev, float* x_new, float* x_mean, float* e_new, float* e_mean, void* stream);
 
 /* edge-tile kernels (tcgen05 + TMEM + bulk-copied operand images); see the structs above */
 int jodo_edge_embed(const jodo_edge_embed_args* a, void* stream);

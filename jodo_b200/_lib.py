@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 6:
+        if _lib.jodo_abi_version() != 7:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 

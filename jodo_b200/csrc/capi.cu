@@ -108,13 +108,13 @@ int jodo_sym_edges(const float* tmp, float* out, int B, int N, int ch, void* str
 int jodo_ancestral_update(const float* x, const float* pred, const float* raw_pos, const float* raw_feat,
                           const float* node_mask, const float* edge_x, const float* edge_pred, const float* raw_edge,
                           const float* edge_mask, int B, int N, int F, int ch, float c_x, float c_pred, float sigma,
-                          float* x_new, float* x_mean, float* e_new, float* e_mean, void* stream) {
+                          const float* coef_dev, float* x_new, float* x_mean, float* e_new, float* e_mean, void* stream) {
   if (B <= 0 || N <= 0 || F <= 3 || ch <= 0) return fail("jodo_ancestral_update: bad sizes");
   if (!x || !pred || !raw_pos || !raw_feat || !node_mask || !edge_x || !edge_pred || !raw_edge || !edge_mask || !x_new ||
       !x_mean || !e_new || !e_mean)
     return fail("jodo_ancestral_update: null pointer");
   JODO_LAUNCH(jodo::launch_ancestral_update(x, pred, raw_pos, raw_feat, node_mask, edge_x, edge_pred, raw_edge, edge_mask, B, N,
-                                            F, ch, c_x, c_pred, sigma, x_new, x_mean, e_new, e_mean, S(stream)),
+                                            F, ch, c_x, c_pred, sigma, coef_dev, x_new, x_mean, e_new, e_mean, S(stream)),
               "jodo_ancestral_update");
 }
 

@@ -77,7 +77,8 @@ cudaError_t launch_sym_edges(const float* tmp, float* out, int B, int N, int ch,
 cudaError_t launch_ancestral_update(const float* x, const float* pred, const float* raw_pos, const float* raw_feat,
                                     const float* node_mask, const float* ex, const float* epred, const float* raw_edge,
                                     const float* edge_mask, int B, int N, int F, int ch, float c_x, float c_p, float sigma,
-                                    float* x_new, float* x_mean, float* e_new, float* e_mean, cudaStream_t st);
+                                    const float* coef, float* x_new, float* x_mean, float* e_new, float* e_mean,
+                                    cudaStream_t st);
 
 // ---- edge-tile kernels (edge_kernels.cu); all built for nf = 256 (ed = 64, 14+2 heads) --------------
 using EdgeEmbedArgs = ::jodo_edge_embed_args;

@@ -22,7 +22,9 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // one warp per molecule
 __global__ void k_ancestral_nodes(const float* __restrict__ x, const float* __restrict__ pred, const float* __restrict__ raw_pos,
                                   const float* __restrict__ raw_feat, const float* __restrict__ node_mask, int B, int N, int F,
-                                  float c_x, float c_p, float sigma, float* __restrict__ x_new, float* __restrict__ x_mean) {
+                                  float c_x, float c_p, float sigma, const float* __restrict__ coef,
+                                  float* __restrict__ x_new, float* __restrict__ x_mean) {
+  if (coef) { c_x = coef[0]; c_p = coef[1]; sigma = coef[2]; }     // per-step coefficients of a replayed CUDA graph
   const int b = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -54,7 +56,8 @@ __global__ void k_ancestral_nodes(const float* __restrict__ x, const float* __re
 
 __global__ void k_ancestral_edges(const float* __restrict__ ex, const float* __restrict__ epred, const float* __restrict__ raw,
                                   const float* __restrict__ edge_mask, int B, int N, int ch, float c_x, float c_p, float sigma,
-                                  float* __restrict__ e_new, float* __restrict__ e_mean) {
+                                  const float* __restrict__ coef, float* __restrict__ e_new, float* __restrict__ e_mean) {
+  if (coef) { c_x = coef[0]; c_p = coef[1]; sigma = coef[2]; }
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [B, N, N]
   const long long total = (long long)B * N * N;
   if (idx >= total) return;
@@ -79,13 +82,14 @@ __global__ void k_ancestral_edges(const float* __restrict__ ex, const float* __r
 cudaError_t launch_ancestral_update(const float* x, const float* pred, const float* raw_pos, const float* raw_feat,
                                     const float* node_mask, const float* ex, const float* epred, const float* raw_edge,
                                     const float* edge_mask, int B, int N, int F, int ch, float c_x, float c_p, float sigma,
-                                    float* x_new, float* x_mean, float* e_new, float* e_mean, cudaStream_t st) {
-  k_ancestral_nodes<<<(B + 7) / 8, 256, 0, st>>>(x, pred, raw_pos, raw_feat, node_mask, B, N, F, c_x, c_p, sigma, x_new, x_mean);
+                                    const float* coef, float* x_new, float* x_mean, float* e_new, float* e_mean,
+                                    cudaStream_t st) {
+  k_ancestral_nodes<<<(B + 7) / 8, 256, 0, st>>>(x, pred, raw_pos, raw_feat, node_mask, B, N, F, c_x, c_p, sigma, coef, x_new, x_mean);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const long long total = (long long)B * N * N;
   k_ancestral_edges<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ex, epred, raw_edge, edge_mask, B, N, ch, c_x, c_p, sigma,
-                                                                    e_new, e_mean);
+                                                                    coef, e_new, e_mean);
   return cudaGetLastError();
 }
 

@@ -144,7 +144,8 @@ class _DGTBase(nn.Module):
         key = tuple((p.data_ptr(), p._version) for p in params) + (_WEIGHT_EPOCH[0],)
         if key != self._packed_key:
             self._packed, self._packed_key, self._fp_pending = {}, key, None
-        pend = self._fp_pending
+        capturing = torch.cuda.is_current_stream_capturing()      # CUDA-graph capture: no event queries, no D2H copies
+        pend = None if capturing else self._fp_pending
         if pend is not None and pend.query():
             self._fp_pending = None
             if self._packed and not torch.equal(self._fp_host, self._packed_fp):
@@ -160,7 +161,7 @@ class _DGTBase(nn.Module):
                 self._fp_host = torch.empty_like(self._packed_fp).pin_memory()
                 self._fp_pending = None
             self._packed[use_wide] = pack_model(sd, self.dims, params[0].device, fused=not use_wide)
-        elif self._fp_pending is None and self._fp_tick % FINGERPRINT_EVERY == 0:
+        elif self._fp_pending is None and self._fp_tick % FINGERPRINT_EVERY == 0 and not capturing:
             self._fp_host.copy_(self._fingerprint(params), non_blocking=True)
             self._fp_pending = torch.cuda.Event()
             self._fp_pending.record()

@@ -135,7 +135,7 @@ class AncestralSampler:
         edge_new = edge_mean + sigma * ze
         return x_new, edge_new, x_mean, edge_mean, pred, edge_pred
 
-    def _fused_update(self, x, edge_x, pred, edge_pred, node_mask, edge_mask, c_x, c_pred, sigma):
+    def _fused_update(self, x, edge_x, pred, edge_pred, node_mask, edge_mask, c_x, c_pred, sigma, coef_dev=None):
         """Posterior mean + noise in two launches of libjodo_b200 (jodo_ancestral_update) instead of ~30 torch
         kernels; the raw normal draws are the same torch.randn calls, in the same order, as node_noise / edge_noise."""
         import ctypes
@@ -154,12 +154,19 @@ class AncestralSampler:
         f = ctypes.c_float
         _lib.call('jodo_ancestral_update', _lib.ptr(x), _lib.ptr(pred), _lib.ptr(raw_pos), _lib.ptr(raw_feat), _lib.ptr(nm),
                   _lib.ptr(edge_x), _lib.ptr(edge_pred), _lib.ptr(raw_edge), _lib.ptr(em), ctypes.c_int(bs), ctypes.c_int(N),
-                  ctypes.c_int(F_), ctypes.c_int(ch), f(c_x), f(c_pred), f(sigma), _lib.ptr(x_new), _lib.ptr(x_mean),
+                  ctypes.c_int(F_), ctypes.c_int(ch), f(c_x), f(c_pred), f(sigma), _lib.ptr(coef_dev), _lib.ptr(x_new), _lib.ptr(x_mean),
                   _lib.ptr(e_new), _lib.ptr(e_mean), _lib.stream_ptr())
         return x_new, e_new, x_mean, e_mean, pred, edge_pred
 
     @torch.no_grad()
-    def sampling(self, model, z_T, node_mask, edge_mask, edge_z_T, context=None):
+    def sampling(self, model, z_T, node_mask, edge_mask, edge_z_T, context=None, graph=False):
+        """The whole reverse chain (reference sampling.py:530-596).  graph=True captures one self-conditioned reverse
+        step (denoiser call + noise draws + fused update + hand-off copies) into a CUDA graph after two eager steps and
+        replays it for the rest of the chain: per step the host issues one 16-byte coefficient copy and one graph
+        launch instead of ~160 kernel launches, which is what bounds small batches.  Same kernels, same torch.randn
+        stream as the eager chain."""
+        if graph:
+            return self._sampling_graphed(model, z_T, node_mask, edge_mask, edge_z_T, context)
         x, edge_x = z_T, edge_z_T
         cond_x = cond_edge_x = None
         x_mean = edge_mean = None
@@ -167,6 +174,49 @@ class AncestralSampler:
             x, edge_x, x_mean, edge_mean, cond_x, cond_edge_x = self.step(
                 model, i, x, edge_x, node_mask, edge_mask, cond_x, cond_edge_x, context)
         return x_mean, edge_mean
+
+    def _sampling_graphed(self, model, z_T, node_mask, edge_mask, edge_z_T, context):
+        if not (z_T.is_cuda and self.fused and self.noise_fn is None and self.generator is None):
+            raise ValueError('graph=True needs CUDA tensors, the fused update and the default CUDA generator')
+        n = len(self.t_array)
+        c32 = lambda t: t.contiguous().float()
+        x, edge_x = c32(z_T), c32(edge_z_T)
+        cond_x = cond_edge_x = None
+        x_mean = edge_mean = None
+        eager = min(2, n)                       # step 0 takes the first-call path (no self-conditioning); step 1 warms
+        for i in range(eager):                  # up every workspace of the self-conditioned path
+            x, edge_x, x_mean, edge_mean, cond_x, cond_edge_x = self.step(
+                model, i, x, edge_x, node_mask, edge_mask, cond_x, cond_edge_x, context)
+        if n <= eager:
+            return x_mean, edge_mean
+        dev = x.device
+        bs = x.shape[0]
+        table = torch.tensor([[float(v) for v in self.coef[i]] for i in range(n)], device=dev, dtype=torch.float32)
+        coef = torch.zeros(4, device=dev, dtype=torch.float32)            # {c_x, c_pred, sigma, noise level} of the step
+        sx, sex, scx, scex = x.clone(), edge_x.clone(), c32(cond_x).clone(), c32(cond_edge_x).clone()
+        vec_t = torch.zeros(bs, device=dev)                               # ignored by the model (reference mol_gnn.py:534)
+        ctx = None if context is None else c32(context).clone()
+
+        def one_step():
+            nl = coef[3:4].expand(bs)
+            pred, edge_pred = model(vec_t, sx, node_mask, edge_mask, edge_x=sex, noise_level=nl, cond_x=scx,
+                                    cond_edge_x=scex, context=ctx)
+            out = self._fused_update(sx, sex, pred, edge_pred, node_mask, edge_mask, 0.0, 0.0, 0.0, coef_dev=coef)
+            sx.copy_(out[0]); sex.copy_(out[1]); scx.copy_(pred); scex.copy_(edge_pred)
+            return out[2], out[3]
+
+        coef.copy_(table[eager])
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):           # capture needs a non-default stream; nothing runs during capture
+            with torch.cuda.graph(g, stream=side):
+                xm, em = one_step()
+        torch.cuda.current_stream().wait_stream(side)
+        for i in range(eager, n):
+            coef.copy_(table[i])
+            g.replay()
+        return xm.clone(), em.clone()
 
 
 def position_noise(B, N, node_mask, generator=None):
