@@ -227,7 +227,8 @@ int jodo_edge_head(const jodo_edge_head_args* a, void* stream);
  * K-major SWIZZLE_128B images jodo_imglinear reads: [rows / 128][K / 64][128 rows][128 B]. */
 typedef struct jodo_wide_embed_args {                   /* model-level edge inputs (reference models/mol_gnn.py:517-557) */
   jodo_plan p;
-  const float* edge_x; const float* cond_edge_x; const float* cond_x;   /* dense inputs; cond_* null on the first call */
+  const float* edge_x; const float* cond_edge_x; const float* cond_x;   /* dense inputs; cond_* null on the first call; cond_x
+                                             also null for 2-D models (no coordinates: ed = 0, no distance part) */
   int ch, inn, ed; float edge_th, spatial_cut;
   int* dist_flag;                         /* device int (out): any cond distance != 0 (models/mol_gnn.py:544) */
   const float* tab; int ld_tab;           /* per-molecule tables (model-level GBF 1 + scale, shift at [0], [1]) */

@@ -69,6 +69,23 @@ def geom_uncond(n_layers=8, nf=256):
     return _base('DGT_concat', 16, 3, nf, n_layers, 4, 3., 181, [-2., 3.], 'geom_with_h_1', 512)
 
 
+def moses_2d():
+    """configs/vpsde_moses_2d_jodo.py: the 2-D-only model DGT_concat_2D (no coordinates: no distance features, no
+    coordinate update, one adjacency head), reference models/mol_gnn.py:797-947."""
+    c = _base('DGT_concat_2D', 7, 3, 256, 8, 2, 0., 27, None, 'moses', 2000)
+    c.exp_type = 'vpsde'
+    c.only_2D = True
+    c.data = Config(atom_types=7, max_node=27, compress_edge=True, centered=True, info_name='moses')
+    m = c.model
+    m.include_fc_charge = False
+    m.normalize_factors = '1, 2, 2, 1'
+    m.time_dim = 1024
+    m.n_extra_heads = 1
+    for k in ('dist_gbf', 'gbf_name', 'CoM', 'spatial_cut_off'):
+        del m[k]
+    return c
+
+
 def tiny(nf=64, n_layers=2, atom_types=5, edge_ch=2, mlp_ratio=2, cond=False):
     """Small architecture for fast CPU tests of the oracle (not a reference config)."""
     c = _base('cond_DGT_concat' if cond else 'DGT_concat', atom_types, edge_ch, nf, n_layers,
@@ -84,4 +101,5 @@ NAMED = {
     'geom_l8': lambda: geom_uncond(8, 256),
     'geom_l10': lambda: geom_uncond(10, 256),
     'geom_large': lambda: geom_uncond(10, 384),
+    'moses_2d': moses_2d,
 }

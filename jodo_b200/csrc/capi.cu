@@ -169,9 +169,9 @@ static bool img_ok(const void* img, int K, int col, int W) {
 int jodo_wide_embed_in(const jodo_wide_embed_args* a, void* stream) {
   if (!a) return fail("jodo_wide_embed_in: null args");
   if (const char* m = check_plan(a->p)) return fail(m);
-  if (a->ch < 1 || a->ed <= 0 || a->ed % 8 || a->ed + 2 * a->ch > a->K) return fail("jodo_wide_embed_in: bad sizes");
+  if (a->ch < 1 || a->ed < 0 || a->ed % 8 || a->ed + 2 * a->ch > a->K) return fail("jodo_wide_embed_in: bad sizes");
   if (!img_ok(a->img, a->K, 0, a->K) || !a->edge_x || !a->extra || !a->dist_flag || !a->tab || !a->gbf) return fail("jodo_wide_embed_in: bad buffers");
-  if ((a->cond_x == nullptr) != (a->cond_edge_x == nullptr)) return fail("jodo_wide_embed_in: cond_x / cond_edge_x must come together");
+  if (a->cond_x && !a->cond_edge_x) return fail("jodo_wide_embed_in: cond_x needs cond_edge_x");     /* 2-D models: cond_edge_x alone */
   JODO_LAUNCH(jodo::launch_wide_embed_in(*a, S(stream)), "jodo_wide_embed_in");
 }
 int jodo_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1, void* img2, int K2,
@@ -203,8 +203,8 @@ int jodo_wide_ln(const jodo_wide_ln_args* a, void* stream) {
 int jodo_wide_attn(const jodo_wide_attn_args* a, void* stream) {
   if (!a) return fail("jodo_wide_attn: null args");
   if (a->Nn <= 0 || a->D <= 0 || a->H <= 0 || a->H > 32 || a->X < 0 || a->X >= a->H || a->X > 8 || a->D % a->H || a->sc <= 0 ||
-      (a->D / a->H) % 4 || (((a->H - a->X) * a->sc) & 1) || (a->ldq % 4) || (a->ldg % 4) || (a->k_off % 2) || (a->v_off % 4) || (a->g1_off % 4))
-    return fail("jodo_wide_attn: bad sizes (needs D / H % 4 == 0, an even q/k width, 8-byte aligned row parts)");
+      (a->D / a->H) % 4 || (a->ldq % 4) || (a->ldg % 4) || (a->k_off % 2) || (a->v_off % 4) || (a->g1_off % 4))
+    return fail("jodo_wide_attn: bad sizes (needs D / H % 4 == 0 and 8-byte aligned row parts, q/k parts padded to an even width)");
   if (a->max_gl < 1 || a->max_gl > 255) return fail("jodo_wide_attn: max_gl must be in [1, 255]");
   if (!a->grp_row0 || !a->grp_len || !a->row_j || !a->qkv || !a->G || !a->extra || !a->hnode) return fail("jodo_wide_attn: null buffer");
   JODO_LAUNCH(jodo::launch_wide_attn(*a, S(stream)), "jodo_wide_attn");

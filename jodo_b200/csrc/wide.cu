@@ -325,14 +325,14 @@ __global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
   }
   const float inv = rsqrtf((float)C);
   const uint16_t* qrow = a.qkv + (size_t)g * a.ldq;
-  for (int c = tid; c < qk; c += WA_THREADS) qs[c] = h2f(qrow[c]) * inv;
+  for (int c = tid; c < qkp; c += WA_THREADS) qs[c] = c < qk ? h2f(qrow[c]) * inv : 0.f;
   for (int i = tid; i < gl; i += WA_THREADS) js[i] = a.row_j[row0 + i];
   __syncthreads();
   for (int i = warp; i < gl; i += 4) {
     const __half2* krow = reinterpret_cast<const __half2*>(a.qkv + (size_t)js[i] * a.ldq + a.k_off);
     const __half2* grow = reinterpret_cast<const __half2*>(a.G + (size_t)(row0 + i) * a.ldg);
     float* pr = prod + warp * qkp;
-    for (int c = lane; c < (qk >> 1); c += 32) {                  // qk is even
+    for (int c = lane; c < ((qk + 1) >> 1); c += 32) {            // an odd qk reads one zero pad column of the rows
       const float2 kk = __half22float2(krow[c]), gg = __half22float2(grow[c]);
       pr[2 * c] = qs[2 * c] * kk.x * gg.x;
       pr[2 * c + 1] = qs[2 * c + 1] * kk.y * gg.y;

@@ -97,7 +97,8 @@ class _DGTBase(nn.Module):
         super().__init__()
         check_supported(config)
         self.dims = dims_from_config(config)
-        self.wide = self.dims.D != 256      # nf = 256: fused edge-tile kernels; other sizes: GEMM + row-kernel path (wide.py)
+        # nf = 256: fused edge-tile kernels; other sizes and the 2-D model: GEMM + row-kernel path (wide.py)
+        self.wide = self.dims.D != 256 or self.dims.two_d
         if self.wide:
             why = wide.supported(self.dims)
             if why:
@@ -108,7 +109,7 @@ class _DGTBase(nn.Module):
             if self.dims.ce % 4 or self.dims.ce > 16:
                 raise NotImplementedError('unsupported n_layers (edge hidden slice must be a multiple of 4 <= 16)')
         self.edge_th = float(config.model.edge_quan_th)
-        self.spatial_cut_off = float(config.model.spatial_cut_off)
+        self.spatial_cut_off = float(getattr(config.model, 'spatial_cut_off', 0.))
         self.n_layers = self.dims.L
         self._spec = param_spec(config)
         build_param_tree(self, self._spec)
@@ -335,7 +336,13 @@ class Cond_DGT_concat(_DGTBase):
     """B200-native drop-in for the reference ``Cond_DGT_concat`` (models/mol_gnn.py:597-794)."""
 
 
-MODELS = {'DGT_concat': DGT_concat, 'cond_DGT_concat': Cond_DGT_concat}
+class DGT_concat_2D(_DGTBase):
+    """B200-native drop-in for the reference ``DGT_concat_2D`` (models/mol_gnn.py:797-947; MOSES / ZINC250k configs):
+    atom features and bonds only -- ``xh`` is ``[B, N, in]``, the return is ``(atom_pred [B,N,in], e_hat)``.  Runs
+    on the wide path without the distance features and the coordinate branch, with one adjacency head."""
+
+
+MODELS = {'DGT_concat': DGT_concat, 'cond_DGT_concat': Cond_DGT_concat, 'DGT_concat_2D': DGT_concat_2D}
 
 
 def create_model(config, device='cuda'):

@@ -208,15 +208,18 @@ def pack_model(sd, dims, device, fused=None):
     ld_tab = ceil_to(TAB_HEAD + L * stride, 256)
     wt, bt = z(ld_tab, T), z(ld_tab)
     # Every "scale" column gets +1 on its bias: the kernels modulate with one FMA, x * (1 + scale) + shift.
-    wt[0:2], bt[0:2] = W('dist_layer.time_mlp.1'), Bv('dist_layer.time_mlp.1')
-    bt[0] += 1.0                                              # GBF time MLP chunks as (scale, shift)
+    if not d.two_d:
+        wt[0:2], bt[0:2] = W('dist_layer.time_mlp.1'), Bv('dist_layer.time_mlp.1')
+        bt[0] += 1.0                                          # GBF time MLP chunks as (scale, shift)
     for l in range(L):
         b = f'e_block_{l}'
         o = TAB_HEAD + l * stride
-        for name, n, scales in ((f'{b}.node_time_mlp.1', 6 * D, ((D, 2 * D), (4 * D, 5 * D))),
-                                (f'{b}.edge_time_mlp.1', 6 * ed, ((ed, 2 * ed), (4 * ed, 5 * ed))),
-                                (f'{b}.equi_update.time_mlp.1', 2 * D, ((D, 2 * D),)),
-                                (f'{b}.dist_layer.time_mlp.1', 2, ((0, 1),))):
+        chunks = [(f'{b}.node_time_mlp.1', 6 * D, ((D, 2 * D), (4 * D, 5 * D))),
+                  (f'{b}.edge_time_mlp.1', 6 * ed, ((ed, 2 * ed), (4 * ed, 5 * ed)))]
+        if not d.two_d:                                       # the 2-D model has no coordinate branch / distance features
+            chunks += [(f'{b}.equi_update.time_mlp.1', 2 * D, ((D, 2 * D),)),
+                       (f'{b}.dist_layer.time_mlp.1', 2, ((0, 1),))]
+        for name, n, scales in chunks:
             wt[o:o + n], bt[o:o + n] = W(name), Bv(name)
             for s0, s1 in scales:                             # chunk order: shift, scale, gate (AdaLN); scale, shift (GBF)
                 bt[o + s0:o + s1] += 1.0

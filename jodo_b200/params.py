@@ -38,6 +38,7 @@ class Dims:
     cn: int         # 2D // L
     ce: int         # 2ed // L
     cond_ch: int    # 0 for the unconditional model
+    two_d: bool = False   # DGT_concat_2D: no coordinates (xh = atom features only)
 
     @property
     def node_cat(self):
@@ -57,7 +58,10 @@ def dims_from_config(config) -> Dims:
     L = int(m.n_layers)
     ed = D // 4
     cond = str(m.name).startswith('cond')
-    return Dims(D=D, ed=ed, T=4 * D, L=L, r=int(m.mlp_ratio), H=H, X=X, S=S, sc=D // S,
+    two_d = str(m.name) == 'DGT_concat_2D'
+    if two_d and int(getattr(m, 'time_dim', 4 * D)) != 4 * D:
+        raise NotImplementedError('DGT_concat_2D: model.time_dim must be 4 * model.nf')
+    return Dims(two_d=two_d, D=D, ed=ed, T=4 * D, L=L, r=int(m.mlp_ratio), H=H, X=X, S=S, sc=D // S,
                 qk=S * (D // S), C=D // H, inn=int(d.atom_types) + int(m.include_fc_charge),
                 ch=int(m.edge_ch), cn=(2 * D) // L, ce=(2 * ed) // L,
                 cond_ch=int(m.cond_ch) if cond else 0)
@@ -66,17 +70,19 @@ def dims_from_config(config) -> Dims:
 def check_supported(config):
     """Variants of the reference model this implementation covers."""
     m = config.model
-    if m.name not in ('DGT_concat', 'cond_DGT_concat'):
+    if m.name not in ('DGT_concat', 'cond_DGT_concat', 'DGT_concat_2D'):
         raise ValueError(f'unsupported model.name {m.name!r}')
-    need = dict(cond_time=True, dist_gbf=True, gbf_name='CondGaussianLayer', softmax_inf=True,
-                pred_data=True, CoM=True)
+    two_d = m.name == 'DGT_concat_2D'
+    need = dict(cond_time=True, softmax_inf=True, pred_data=True)
+    if not two_d:
+        need.update(dist_gbf=True, gbf_name='CondGaussianLayer', CoM=True)
     for k, v in need.items():
         if getattr(m, k) != v:
             raise ValueError(f'unsupported config.model.{k}={getattr(m, k)!r} (hot path covers {v!r})')
     if getattr(m, 'trans_name', 'TransMixLayer') != 'TransMixLayer':
         raise ValueError('unsupported trans_name')
-    if int(m.n_extra_heads) != 2:
-        raise ValueError('hot path covers n_extra_heads == 2 (all reference configs)')
+    if int(m.n_extra_heads) != (1 if two_d else 2):
+        raise ValueError('hot path covers n_extra_heads == 2 (1 for DGT_concat_2D), as in all reference configs')
 
 
 def _lin(name, out_f, in_f, bias=True):
@@ -91,9 +97,42 @@ def _gbf(name, d: Dims):
         _lin(f'{name}.time_mlp.1', 2, d.T)
 
 
+def param_spec_2d(d: Dims):
+    """DGT_concat_2D.__init__ / EquivariantMixBlock_2D.__init__ (reference models/mol_gnn.py:801-866, 328-363)."""
+    D, ed, T = d.D, d.ed, d.T
+    spec = _lin('node_emb', D, 2 * d.inn) + _lin('edge_emb', ed, 2 * d.ch)
+    for i in range(d.L):
+        b = f'e_block_{i}'
+        spec += _lin(f'{b}.node2edge_lin', ed, D)
+        spec += _lin(f'{b}.attn_mpnn.lin_key', d.qk, D)
+        spec += _lin(f'{b}.attn_mpnn.lin_query', d.qk, D)
+        spec += _lin(f'{b}.attn_mpnn.lin_value', D, D)
+        spec += _lin(f'{b}.attn_mpnn.lin_edge0', d.qk, ed, bias=False)
+        spec += _lin(f'{b}.attn_mpnn.lin_edge1', D, ed, bias=False)
+        spec += _lin(f'{b}.ff_linear1', D * d.r, D)
+        spec += _lin(f'{b}.ff_linear2', D, D * d.r)
+        spec += _lin(f'{b}.ff_linear3', ed * d.r, ed)
+        spec += _lin(f'{b}.ff_linear4', ed, ed * d.r)
+        spec += _lin(f'{b}.node_time_mlp.1', 6 * D, T)
+        spec += _lin(f'{b}.edge_time_mlp.1', 6 * ed, T)
+        spec += _lin(f'node_{i}', d.cn, D)
+        spec += _lin(f'edge_{i}', d.ce, ed)
+    spec += _lin('node_pred_mlp.0', D, d.node_cat) + _lin('node_pred_mlp.2', D // 2, D) + \
+        _lin('node_pred_mlp.4', d.inn, D // 2)
+    spec += _lin('edge_type_mlp.0', ed, d.edge_cat) + _lin('edge_type_mlp.2', ed // 2, ed) + \
+        _lin('edge_type_mlp.4', d.ch - 1, ed // 2)
+    spec += _lin('edge_exist_mlp.0', ed, d.edge_cat) + _lin('edge_exist_mlp.2', ed // 2, ed) + \
+        _lin('edge_exist_mlp.4', 1, ed // 2)
+    spec += [('time_mlp.0.weights', (8,))]
+    spec += _lin('time_mlp.1', T, 17) + _lin('time_mlp.3', T, T)
+    return spec
+
+
 def param_spec(config):
     """Ordered [(name, shape)] exactly as the reference module registers them."""
     d = dims_from_config(config)
+    if d.two_d:
+        return param_spec_2d(d)
     D, ed, T = d.D, d.ed, d.T
     spec = []
     spec += _lin('node_emb', D, 2 * d.inn)

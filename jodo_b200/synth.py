@@ -75,7 +75,9 @@ def make_batch(config, batch, seed=42, max_n=None, n_nodes=None, self_cond=False
     node_mask, edge_mask = make_masks(n_nodes, N)
     node_mask, edge_mask = node_mask.to(dtype), edge_mask.to(dtype)
     out = dict(n_nodes=n_nodes, node_mask=node_mask, edge_mask=edge_mask)
-    out['xh'] = node_noise(B, N, inn, node_mask, gen, dtype=dtype)
+    two_d = bool(getattr(config, 'only_2D', False))          # 2-D models: xh = atom features only (no coordinates)
+    feat_noise = lambda: torch.randn((B, N, inn), generator=gen, dtype=dtype) * node_mask
+    out['xh'] = feat_noise() if two_d else node_noise(B, N, inn, node_mask, gen, dtype=dtype)
     out['edge_x'] = edge_noise(B, N, ch, edge_mask, gen, dtype=dtype)
     if noise_level is None:
         nl = torch.empty(B, dtype=dtype).uniform_(-6.0, 6.0, generator=gen)
@@ -84,8 +86,11 @@ def make_batch(config, batch, seed=42, max_n=None, n_nodes=None, self_cond=False
     out['noise_level'] = nl
     out['t'] = torch.rand(B, generator=gen, dtype=dtype)
     if self_cond:
-        cx = node_noise(B, N, inn, node_mask, gen, dtype=dtype)
-        cx[..., :3] = cx[..., :3] * 1.5
+        if two_d:
+            cx = feat_noise()
+        else:
+            cx = node_noise(B, N, inn, node_mask, gen, dtype=dtype)
+            cx[..., :3] = cx[..., :3] * 1.5
         out['cond_x'] = cx
         out['cond_edge_x'] = edge_noise(B, N, ch, edge_mask, gen, dtype=dtype) * 0.7
     else:

@@ -26,7 +26,7 @@ def supported(d) -> str | None:
         return f'model.nf must be a multiple of 128 up to 512 (got {d.D})'
     if d.ed % 8 or d.ed > EDP:
         return f'edge width nf/4 must be a multiple of 8 up to {EDP} (got {d.ed})'
-    if d.H > 32 or d.D % d.H or (d.D // d.H) % 4 or d.qk % 2:
+    if d.H > 32 or d.D % d.H or (d.D // d.H) % 4:
         return f'n_heads must divide nf into head widths that are multiples of 4, at most 32 heads (got {d.H})'
     if 2 * d.ch + d.ed > EDP:
         return f'edge_ch too large for the embedding image (got {d.ch})'
@@ -58,13 +58,17 @@ def pack_wide(pk, sd, d, add_lin):
     z = lambda *s: torch.zeros(*s, device=dev)
     qkp = ceil_to(d.qk, 128)
     pk.meta.update(qkp=qkp, wide=True)
-    # ---- model level: edge_emb on [dist0 (ed) | edge_x (ch) | cond_edge_x (ch)]
-    pk.add('gbf', _gbf_consts(sd, 'dist_layer', dev))
+    # ---- model level: edge_emb on [dist0 (ed) | edge_x (ch) | cond_edge_x (ch)]; 2-D model: [edge_x | cond_edge_x]
     we = W('edge_emb')                                         # [ed, 2ch + ed]: [edge_x | cond_edge_x | dist]
-    wep = z(ed, EDP)
-    wep[:, :ed] = we[:, 2 * d.ch:]
-    wep[:, ed:ed + 2 * d.ch] = we[:, :2 * d.ch]
-    add_lin('edge_emb', wep, Bv('edge_emb'), 128)
+    if d.two_d:
+        pk.add('gbf', z(3 * EDP))
+        add_lin('edge_emb', we, Bv('edge_emb'), 128)           # K = 64
+    else:
+        pk.add('gbf', _gbf_consts(sd, 'dist_layer', dev))
+        wep = z(ed, EDP)
+        wep[:, :ed] = we[:, 2 * d.ch:]
+        wep[:, ed:ed + 2 * d.ch] = we[:, :2 * d.ch]
+        add_lin('edge_emb', wep, Bv('edge_emb'), 128)
     # ---- edge heads: layer 0 of edge_exist_mlp | edge_type_mlp is linear in the concatenated edge hiddens
     # cat[e0, edge_0(e_1), ..] (reference models/mol_gnn.py:567-574), so the edge_i projections are folded into it:
     # H = W0[:, :ed] e0 + sum_l (W0[:, s_l] We_l) e_l + b is ONE GEMM over the operand [e0 | e_1 | .. | e_L] (slots of
@@ -104,23 +108,24 @@ def pack_wide(pk, sd, d, add_lin):
         pk.add(p + 'n2e.bias', nb)
         add_lin(p + 'ff1', W(f'{b}.ff_linear1'), Bv(f'{b}.ff_linear1'), 128)
         add_lin(p + 'ff2', W(f'{b}.ff_linear2'), Bv(f'{b}.ff_linear2'), 128)
-        wi = W(f'{b}.equi_update.input_lin')                   # [D, 2D + 2ed]: [h_row | h_col | e | dist]
-        add_lin(p + 'ab', torch.cat([wi[:, :D], wi[:, D:2 * D]], dim=0),
-                torch.cat([Bv(f'{b}.equi_update.input_lin'), z(D)]), 128)      # input_lin bias rides on the h[row] part
         add_lin(p + 'node_l', W(f'node_{l}'), Bv(f'node_{l}'), 128)
-        pk.add(p + 'gbf', _gbf_consts(sd, f'{b}.dist_layer', dev))
-        add_lin(p + 'emb', W(f'{b}.edge_emb'), Bv(f'{b}.edge_emb'), 128)                    # K = 2ed: [dist | e]
+        if not d.two_d:
+            wi = W(f'{b}.equi_update.input_lin')               # [D, 2D + 2ed]: [h_row | h_col | e | dist]
+            add_lin(p + 'ab', torch.cat([wi[:, :D], wi[:, D:2 * D]], dim=0),
+                    torch.cat([Bv(f'{b}.equi_update.input_lin'), z(D)]), 128)  # input_lin bias rides on the h[row] part
+            pk.add(p + 'gbf', _gbf_consts(sd, f'{b}.dist_layer', dev))
+            add_lin(p + 'emb', W(f'{b}.edge_emb'), Bv(f'{b}.edge_emb'), 128)                # K = 2ed: [dist | e]
+            add_lin(p + 'equi_in', wi[:, 2 * D:].contiguous(), None, 128)                   # K = 2ed: [e | dist]
+            add_lin(p + 'c0', W(f'{b}.equi_update.coord_mlp.0'), Bv(f'{b}.equi_update.coord_mlp.0'), 128)
+            add_lin(p + 'c2', W(f'{b}.equi_update.coord_mlp.2'), None, 64)                  # N = 64 (1 + X real)
+            scales.append(sd[f'{b}.equi_update.coord_norm.scale'].reshape(()))
         wg = z(qkp + D, EDP)
         wg[:d.qk, :ed] = W(f'{b}.attn_mpnn.lin_edge0')
         wg[qkp:, :ed] = W(f'{b}.attn_mpnn.lin_edge1')
         add_lin(p + 'g01', wg, None, 128)
         add_lin(p + 'ff3', pad2(W(f'{b}.ff_linear3'), f3p, EDP), Bv(f'{b}.ff_linear3'), 128, n_pad=f3p)
         add_lin(p + 'ff4', pad2(W(f'{b}.ff_linear4'), ed, f3p), Bv(f'{b}.ff_linear4'), 128)
-        add_lin(p + 'equi_in', wi[:, 2 * D:].contiguous(), None, 128)                       # K = 2ed: [e | dist]
-        add_lin(p + 'c0', W(f'{b}.equi_update.coord_mlp.0'), Bv(f'{b}.equi_update.coord_mlp.0'), 128)
-        add_lin(p + 'c2', W(f'{b}.equi_update.coord_mlp.2'), None, 64)                      # N = 64 (1 + X real)
-        scales.append(sd[f'{b}.equi_update.coord_norm.scale'].reshape(()))
-    pk.meta['coord_scale'] = [float(s) for s in torch.stack(scales).cpu()]
+    pk.meta['coord_scale'] = [float(s) for s in torch.stack(scales).cpu()] if scales else []
 
 
 class WideWorkspace:
@@ -152,11 +157,15 @@ class WideWorkspace:
         self.qkv = torch.zeros(Nn, self.ldq, device=dev, dtype=torch.float16)
         self.hnode, self.h2 = zf(Nn, D), f(Nn, D)
         self.P = zf(Nn, EDP)
-        self.AB = torch.zeros(Nn, 2 * D, device=dev, dtype=torch.float16)    # hoisted input_lin parts, gathered per edge
+        if not d.two_d:
+            self.AB = torch.zeros(Nn, 2 * D, device=dev, dtype=torch.float16)    # hoisted input_lin parts, gathered per edge
         self.n1, self.n2, self.ap = f(Nn, D), f(Nn, meta['npred2']['N']), f(Nn, meta['npred4']['N'])
         # per edge row
-        self.A0, self.A1, self.A4 = eimg(EDP), eimg(2 * d.ed), eimg(2 * d.ed)
-        self.e32, self.e1, self.e2 = zf(R, EDP), zf(R, EDP), zf(R, EDP)
+        self.A0 = eimg(64 if d.two_d else EDP)
+        if not d.two_d:
+            self.A1, self.A4 = eimg(2 * d.ed), eimg(2 * d.ed)
+            self.e1 = zf(R, EDP)
+        self.e32, self.e2 = zf(R, EDP), zf(R, EDP)
         self.en_img, self.e2_img = eimg(EDP), eimg(EDP)
         self.ldg = meta['qkp'] + D
         self.G = torch.zeros(R, self.ldg, device=dev, dtype=torch.float16)
@@ -164,9 +173,11 @@ class WideWorkspace:
         self.EH = eimg((d.L + 1) * EDP)                       # operand of the edge heads: [e0 | e_1 | .. | e_L]
         self.H_img = eimg(meta['hp'])
         self.X2 = zf(R, EDP)
-        self.U = torch.zeros(R, D, device=dev, dtype=torch.float16)          # input_lin edge part (pre-LayerNorm)
-        self.u_img, self.c0_img = eimg(D), eimg(D)
-        self.c3 = zf(R, 64)
+        if not d.two_d:
+            self.U = torch.zeros(R, D, device=dev, dtype=torch.float16)      # input_lin edge part (pre-LayerNorm)
+            self.u_img, self.c0_img = eimg(D), eimg(D)
+            self.c3 = zf(R, 64)
+        self.node_dense_l = plan.node_dense.long()
         self.extra = torch.zeros(R, device=dev, dtype=torch.uint8)
         self.flags = torch.zeros(4, device=dev, dtype=torch.int32)            # [0] dist flag, [1] nan flag
         self.grp_row0, self.grp_len = plan.grp_row0, plan.grp_len
@@ -215,18 +226,28 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
     _lib.call('jodo_act_image', P(ws.temb), _c(T), _c(B), _c(T), _c(_lib.ACT_SILU), P(ws.temb_img), st)
     ilin('tab', ws.temb_img, B, C32=ws.tab)
     # ---- per atom
-    _lib.call('jodo_gather_nodes', P(xh), P(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin), P(ws.xin), P(ws.pos[0]), st)
+    if d.two_d:                                   # no coordinates: xh = atom features [B, N, in] (mol_gnn.py:883, 897-899)
+        ws.xin.zero_()
+        ws.xin[:, :d.inn] = xh.reshape(B * N, d.inn)[ws.node_dense_l]
+        if cond_x is not None:
+            ws.xin[:, d.inn:2 * d.inn] = cond_x.reshape(B * N, d.inn)[ws.node_dense_l]
+    else:
+        _lib.call('jodo_gather_nodes', P(xh), P(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin), P(ws.xin), P(ws.pos[0]), st)
     lin('node_emb', ws.xin, ws.ah[:, :D])
     # ---- per edge: model-level embedding, adjacency heads
-    ea = _lib.WideEmbedArgs(ps, dp(edge_x), dp(cond_edge_x), dp(cond_x), d.ch, d.inn, ed, self.edge_th,
-                            self.spatial_cut_off, dp(ws.flags), dp(ws.tab), ld_tab, pk.ptr('gbf'), EDP, dp(ws.A0), EDP,
-                            dp(ws.extra))
+    ea = _lib.WideEmbedArgs(ps, dp(edge_x), dp(cond_edge_x), 0 if d.two_d else dp(cond_x), d.ch, d.inn,
+                            0 if d.two_d else ed, self.edge_th, self.spatial_cut_off, dp(ws.flags), dp(ws.tab), ld_tab,
+                            pk.ptr('gbf'), EDP, dp(ws.A0), 64 if d.two_d else EDP, dp(ws.extra))
     _lib.call('jodo_wide_embed_in', ctypes.byref(ea), st)
     ilin('edge_emb', ws.A0, R, C32=ws.e32)
     K2 = 2 * ed
     KH = (d.L + 1) * EDP
-    _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.A1), _c(K2), _c(ed), P(ws.EH), _c(KH),
-              _c(0), None, _c(0), _c(0), st)
+    if d.two_d:
+        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.EH), _c(KH), _c(0), None, _c(0),
+                  _c(0), None, _c(0), _c(0), st)
+    else:
+        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.A1), _c(K2), _c(ed), P(ws.EH),
+                  _c(KH), _c(0), None, _c(0), _c(0), st)
 
     h = ws.ah[:, :D]
     stride = tab_layer_stride(D)
@@ -237,10 +258,13 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         pin, pout = ws.pos[l & 1], ws.pos[(l + 1) & 1]
         hout = ws.h[l & 1]
         # distance features into the [dist | e] and [e | dist] operands; block edge_emb; norm1_edge; g0 | g1
-        _lib.call('jodo_wide_dist', ctypes.byref(ps), P(pin), P(ws.tab), _c(ld_tab), _c(og), P(pk[p + 'gbf']), _c(EDP),
-                  _c(ed), P(ws.A1), _c(K2), _c(0), P(ws.A4), _c(K2), _c(ed), st)
-        ilin(p + 'emb', ws.A1, R, C32=ws.e1)
-        ln(R, ed, EDP, ws.e1, (oe, oe + ed), plan.row_mol, out_img=ws.en_img, valid=plan.row_g, tag='e1')
+        if d.two_d:                               # EquivariantMixBlock_2D: norm1_edge on the block input (mol_gnn.py:391)
+            ln(R, ed, EDP, ws.e32, (oe, oe + ed), plan.row_mol, out_img=ws.en_img, valid=plan.row_g, tag='e1')
+        else:
+            _lib.call('jodo_wide_dist', ctypes.byref(ps), P(pin), P(ws.tab), _c(ld_tab), _c(og), P(pk[p + 'gbf']), _c(EDP),
+                      _c(ed), P(ws.A1), _c(K2), _c(0), P(ws.A4), _c(K2), _c(ed), st)
+            ilin(p + 'emb', ws.A1, R, C32=ws.e1)
+            ln(R, ed, EDP, ws.e1, (oe, oe + ed), plan.row_mol, out_img=ws.en_img, valid=plan.row_g, tag='e1')
         ilin(p + 'g01', ws.en_img, R, bias=False, epi=_lib.EPI_ACT, act_out=_lib.ACT_TANH, C16=ws.G)
         # attention
         ln(Nn, D, D, h, (o, o + D), plan.node_mol, out_img=ws.hn_img, tag='h1')
@@ -256,7 +280,8 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         ilin(p + 'ff1', ws.h2_img, Nn, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.ff_img)
         ilin(p + 'ff2', ws.ff_img, Nn, epi=_lib.EPI_GATED_RES, aux=ws.h2, gate=ws.tab[:, o + 5 * D:], row_mol=plan.node_mol,
              C32=hout, Cimg=ws.hout_img)
-        ilin(p + 'ab', ws.hout_img, Nn, C16=ws.AB)
+        if not d.two_d:
+            ilin(p + 'ab', ws.hout_img, Nn, C16=ws.AB)
         ilin(p + 'node_l', ws.hout_img, Nn, C32=ws.ah[:, D + l * meta['cnp']:])
         # edge path: e2 = norm2(e + gate * node2edge(hnode[r] + hnode[c])), e_out = e2 + gate * FFN(e2)
         ln(R, ed, EDP, ws.e32, (oe + 3 * ed, oe + 4 * ed), plan.row_mol, out_img=ws.e2_img, out32=ws.e2, y=ws.P,
@@ -264,6 +289,13 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         ilin(p + 'ff3', ws.e2_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.f3_img)
         ilin(p + 'ff4', ws.f3_img, R, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.row_mol,
              C32=ws.e32)
+        if d.two_d:
+            _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.EH), _c(KH), _c((l + 1) * EDP),
+                      None, _c(0), _c(0), None, _c(0), _c(0), st)
+            if dbg is not None:
+                dbg.setdefault('blocks', []).append(dict(hnode=ws.hnode.clone(), h=hout.clone(), e=ws.e32.clone()))
+            h = hout
+            continue
         _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.A4), _c(K2), _c(0), P(ws.A1),
                   _c(K2), _c(ed), P(ws.EH), _c(KH), _c((l + 1) * EDP), st)
         # coordinate update
@@ -283,9 +315,14 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
     lin('npred0', ws.ah, ws.n1, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)
     lin('npred2', ws.n1, ws.n2, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU)
     lin('npred4', ws.n2, ws.ap)
-    out_x = torch.zeros(B, N, 3 + d.inn, device=xh.device, dtype=torch.float32)
-    _lib.call('jodo_node_out', P(ws.pos[d.L & 1]), P(ws.ap), _c(ws.ap.stride(0)), ctypes.byref(ps),
-              ctypes.c_void_p(ws.flags.data_ptr() + 4), _c(d.inn), P(out_x), st)
+    if d.two_d:                                   # atom_pred * node_mask (mol_gnn.py:933): padding stays zero
+        out_x = torch.zeros(B * N, d.inn, device=xh.device, dtype=torch.float32)
+        out_x[ws.node_dense_l] = ws.ap[:, :d.inn]
+        out_x = out_x.reshape(B, N, d.inn)
+    else:
+        out_x = torch.zeros(B, N, 3 + d.inn, device=xh.device, dtype=torch.float32)
+        _lib.call('jodo_node_out', P(ws.pos[d.L & 1]), P(ws.ap), _c(ws.ap.stride(0)), ctypes.byref(ps),
+                  ctypes.c_void_p(ws.flags.data_ptr() + 4), _c(d.inn), P(out_x), st)
     ilin('hcat', ws.EH, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.H_img)
     ilin('ehead2', ws.H_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, C32=ws.X2)
     tmp = torch.zeros(B, N, N, d.ch, device=xh.device, dtype=torch.float32)

@@ -144,6 +144,55 @@ def mix_block(sd, prefix, pos, h, e, extra, m, em, st, dims, trace=None):
     return hout, eout, pos
 
 
+def mix_block_2d(sd, prefix, h, e, extra, m, em, st, dims):
+    """EquivariantMixBlock_2D.forward (models/mol_gnn.py:372-408): the block without coordinates."""
+    nt = _lin(sd, prefix + '.node_time_mlp.1', st)
+    et = _lin(sd, prefix + '.edge_time_mlp.1', st)
+    nsm, ncm, ngm, nsf, ncf, ngf = [t[:, None, :] for t in nt.chunk(6, dim=1)]
+    esm, ecm, egm, esf, ecf, egf = [t[:, None, None, :] for t in et.chunk(6, dim=1)]
+    hn = _modulate(_ln(h), nsm, ncm)                                  # :390
+    en = _modulate(_ln(e), esm, ecm)                                  # :391 (norm1_edge on the block input itself)
+    hnode = trans_mix(sd, prefix + '.attn_mpnn', hn, en, extra, em, dims)          # :394
+    hedge = _lin(sd, prefix + '.node2edge_lin', hnode[:, :, None, :] + hnode[:, None, :, :])  # :395-396
+    h1 = h + ngm * hnode
+    h2 = _modulate(_ln(h1), nsf, ncf) * m                             # :399
+    hout = (h2 + ngf * _lin(sd, prefix + '.ff_linear2', F.silu(_lin(sd, prefix + '.ff_linear1', h2)))) * m
+    e2 = _modulate(_ln(e + egm * hedge), esf, ecf)                    # :402-403
+    eout = e2 + egf * _lin(sd, prefix + '.ff_linear4', F.silu(_lin(sd, prefix + '.ff_linear3', e2)))
+    return hout, eout
+
+
+@torch.no_grad()
+def dgt2d_forward(sd, config, t, xh, node_mask, edge_mask, context=None, edge_x=None, noise_level=None,
+                  cond_x=None, cond_edge_x=None):
+    """DGT_concat_2D.forward (models/mol_gnn.py:868-947): atom features and bonds only."""
+    dims = dims_of(config)
+    B, N, _ = xh.shape
+    dt = xh.dtype
+    m = node_mask.to(dt)
+    em = edge_mask.reshape(B, N, N, 1).to(dt)
+    if cond_x is None:                                                # :887-890
+        cond_x = torch.zeros_like(xh)
+        cond_edge_x = torch.zeros_like(edge_x)
+        adj2d = torch.ones_like(em)
+    else:                                                             # :892-895
+        adj2d = (cond_edge_x[..., 0:1] >= config.model.edge_quan_th).to(dt)
+    temb = time_embedding(sd, noise_level.to(dt))                     # :902-904
+    st = F.silu(temb)
+    extra = adj2d * em
+    h = _lin(sd, 'node_emb', torch.cat([xh, cond_x], dim=-1))          # :898-899, 918
+    e = _lin(sd, 'edge_emb', torch.cat([edge_x, cond_edge_x], dim=-1))             # :915, 919
+    atom_hids, edge_hids = [h], [e]
+    for i in range(dims['L']):                                        # :924-928
+        h, e = mix_block_2d(sd, f'e_block_{i}', h, e, extra, m, em, st, dims)
+        atom_hids.append(_lin(sd, f'node_{i}', h))
+        edge_hids.append(_lin(sd, f'edge_{i}', e))
+    atom_pred = _mlp3(sd, 'node_pred_mlp', torch.cat(atom_hids, dim=-1)) * m       # :933
+    eh = torch.cat(edge_hids, dim=-1)
+    ep = torch.cat([_mlp3(sd, 'edge_exist_mlp', eh), _mlp3(sd, 'edge_type_mlp', eh)], dim=-1) * em   # :934-939
+    return atom_pred, 0.5 * (ep + ep.permute(0, 2, 1, 3))             # :940
+
+
 def _mlp3(sd, name, x):
     return _lin(sd, name + '.4', F.silu(_lin(sd, name + '.2', F.silu(_lin(sd, name + '.0', x)))))
 
@@ -160,6 +209,8 @@ def dgt_forward(sd, config, t, xh, node_mask, edge_mask, context=None, edge_x=No
                 cond_x=None, cond_edge_x=None, collect=None, trace=None):
     """DGT_concat.forward (models/mol_gnn.py:491-594) / Cond_DGT_concat.forward (:687-794).
     `collect`, if a list, receives (h, e, pos) after every block for stage-level debugging."""
+    if str(config.model.name) == 'DGT_concat_2D':
+        return dgt2d_forward(sd, config, t, xh, node_mask, edge_mask, context, edge_x, noise_level, cond_x, cond_edge_x)
     dims = dims_of(config)
     B, N, _ = xh.shape
     dt = xh.dtype

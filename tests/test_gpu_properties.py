@@ -178,3 +178,45 @@ def test_wide_path_on_nf256_goldens(name):
     x, e = _call(model, g['inputs'])
     rx, re_ = g['ref_fp64']
     assert _rel(x.cpu().double(), rx) < TOL and _rel(e.cpu().double(), re_) < TOL
+
+
+def test_2d_model_full_size_invariants():
+    """DGT_concat_2D (reference configs/vpsde_moses_2d_jodo.py, eval batch 2000): structural invariants, batch
+    permutation, padding width; prints the device time of one evaluation."""
+    cfg, model = _model('moses_2d')
+    B = 2000
+    b = synth.make_batch(cfg, B, seed=3, self_cond=True)
+    x, e = _call(model, b)
+    nm = b['node_mask'].cuda()
+    N = nm.shape[1]
+    em = b['edge_mask'].cuda().reshape(B, N, N, 1)
+    assert x.shape == (B, N, 7) and torch.isfinite(x).all() and torch.isfinite(e).all()
+    assert float((x * (1 - nm)).abs().max()) == 0.0 and float((e * (1 - em)).abs().max()) == 0.0
+    assert float((e - e.permute(0, 2, 1, 3)).abs().max()) == 0.0
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+    bp = {k: (v[perm] if torch.is_tensor(v) and v.shape[0] == B else v) for k, v in b.items()}
+    bp['edge_mask'] = b['edge_mask'].reshape(B, N * N, 1)[perm].reshape(B * N * N, 1)
+    xp, ep = _call(model, bp)
+    assert _rel(xp, x[perm.cuda()]) < 1e-4 and _rel(ep, e[perm.cuda()]) < 1e-4
+    dv = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}      # resident inputs, one plan
+    _call(model, dv)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        _call(model, dv)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f'moses_2d B={B}: {e0.elapsed_time(e1) / 5:.2f} ms per evaluation')
+    # small sub-batch against the oracle
+    idx = torch.arange(6)
+    n = b['n_nodes'][idx]
+    Ns = int(n.max())
+    nm_s, em_s = synth.make_masks(n, Ns)
+    sub = dict(t=b['t'][idx], xh=b['xh'][idx][:, :Ns], node_mask=nm_s, edge_mask=em_s, edge_x=b['edge_x'][idx][:, :Ns, :Ns],
+               noise_level=b['noise_level'][idx], cond_x=b['cond_x'][idx][:, :Ns], cond_edge_x=b['cond_edge_x'][idx][:, :Ns, :Ns],
+               context=None)
+    xs, es = _call(model, sub)
+    assert _rel(xs, x[:6, :Ns]) < 1e-4 and _rel(es, e[:6, :Ns, :Ns]) < 1e-4
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ox, oe = _oracle(cfg, sd, sub)
+    assert _rel(xs.cpu().double(), ox) < TOL and _rel(es.cpu().double(), oe) < TOL
