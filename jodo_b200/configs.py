@@ -63,6 +63,13 @@ def qm9_cond():
     return c
 
 
+def qm9_cond_multi():
+    """configs/vpsde_qm9_cond_multi_jodo.py: cond_DGT_concat conditioned on two properties (cond_ch = 2)."""
+    c = qm9_cond()
+    c.model.cond_ch = 2
+    return c
+
+
 def geom_uncond(n_layers=8, nf=256):
     """configs/vpsde_geom_uncond_jodo.py; BASELINE config 3 quotes n_layers=8 (the file's
     default is 10), config 4 quotes nf=384."""
@@ -98,6 +105,7 @@ def tiny(nf=64, n_layers=2, atom_types=5, edge_ch=2, mlp_ratio=2, cond=False):
 NAMED = {
     'qm9_uncond': qm9_uncond,
     'qm9_cond': qm9_cond,
+    'qm9_cond_multi': qm9_cond_multi,
     'geom_l8': lambda: geom_uncond(8, 256),
     'geom_l10': lambda: geom_uncond(10, 256),
     'geom_large': lambda: geom_uncond(10, 384),

@@ -96,5 +96,6 @@ def make_batch(config, batch, seed=42, max_n=None, n_nodes=None, self_cond=False
     else:
         out['cond_x'] = None
         out['cond_edge_x'] = None
-    out['context'] = torch.randn(B, 1, generator=gen, dtype=dtype) if context else None
+    cond_ch = int(getattr(config.model, 'cond_ch', 1))
+    out['context'] = torch.randn(B, cond_ch, generator=gen, dtype=dtype) if context else None
     return out

@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 TOL = 5e-3
 CASES = ['qm9_first', 'qm9_first_default_init', 'qm9_selfcond', 'qm9_cond_ctx', 'geom_l8', 'geom_l10_first',
          'geom_large',          # nf = 384: the wide path (jodo_b200/wide.py)
+         'qm9_cond_multi',      # cond_DGT_concat with two properties (cond_ch = 2)
          'moses_2d', 'moses_2d_first']          # DGT_concat_2D (no coordinates) on the wide path
 
 

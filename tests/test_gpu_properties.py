@@ -220,3 +220,18 @@ def test_2d_model_full_size_invariants():
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     ox, oe = _oracle(cfg, sd, sub)
     assert _rel(xs.cpu().double(), ox) < TOL and _rel(es.cpu().double(), oe) < TOL
+
+
+def test_two_property_conditioning_against_oracle():
+    """configs/vpsde_qm9_cond_multi_jodo.py: cond_DGT_concat with cond_ch = 2 (two normalised properties per molecule)."""
+    cfg = configs.NAMED['qm9_cond']()
+    cfg.model.cond_ch = 2
+    sd = synth_state_dict(param_spec(cfg), seed=4, perturb=True)
+    model = MODELS[cfg.model.name](cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    b = synth.make_batch(cfg, 5, seed=10, n_nodes=[9, 4, 17, 1, 12], self_cond=True)
+    b['context'] = torch.randn(5, 2, generator=torch.Generator().manual_seed(3))
+    x, e = _call(model, b)
+    ox, oe = _oracle(cfg, sd, b)
+    assert _rel(x.cpu().double(), ox) < TOL and _rel(e.cpu().double(), oe) < TOL

@@ -63,7 +63,7 @@ def test_masked_entries_exactly_zero_and_symmetric():
     assert float((e * (1 - em.double())).abs().max()) == 0.0
 
 
-@pytest.mark.parametrize('cfg_name', ['qm9_uncond', 'qm9_cond', 'geom_l8', 'geom_l10', 'geom_large', 'moses_2d'])
+@pytest.mark.parametrize('cfg_name', ['qm9_uncond', 'qm9_cond', 'geom_l8', 'geom_l10', 'geom_large', 'moses_2d', 'qm9_cond_multi'])
 def test_param_tree_matches_reference(cfg_name):
     with open(os.path.join(GOLDEN, f'param_tree_{cfg_name}.json')) as f:
         ref = [(k, tuple(s)) for k, s in json.load(f)]
