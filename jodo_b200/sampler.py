@@ -126,7 +126,7 @@ class AncestralSampler:
         if self.noise_fn is not None:
             zn, ze = self.noise_fn(i, 'node'), self.noise_fn(i, 'edge')
         else:
-            zn = node_noise(bs, N, x.shape[2] - 3, node_mask, self.generator)
+            zn = self._node_noise(bs, N, x.shape[2], node_mask)
             ze = None
         x_new = x_mean + sigma * zn
         edge_mean = c_x * edge_x + c_pred * edge_pred
@@ -134,6 +134,9 @@ class AncestralSampler:
             ze = edge_noise(bs, N, edge_x.shape[-1], edge_mask, self.generator)
         edge_new = edge_mean + sigma * ze
         return x_new, edge_new, x_mean, edge_mean, pred, edge_pred
+
+    def _node_noise(self, bs, N, F_, node_mask):
+        return node_noise(bs, N, F_ - 3, node_mask, self.generator)
 
     def _fused_update(self, x, edge_x, pred, edge_pred, node_mask, edge_mask, c_x, c_pred, sigma, coef_dev=None):
         """Posterior mean + noise in two launches of libjodo_b200 (jodo_ancestral_update) instead of ~30 torch
@@ -217,6 +220,18 @@ class AncestralSampler:
             coef.copy_(table[i])
             g.replay()
         return xm.clone(), em.clone()
+
+
+class AncestralSampler2D(AncestralSampler):
+    """Ancestral sampling without 3-D positions (reference sampling.py:599-661, AncestralSampler_2D): the same
+    posterior-mean update with masked Gaussian node noise (sample_gaussian_with_mask, models/utils.py:77-80: no CoM
+    projection) and symmetric edge noise; drives ``DGT_concat_2D``."""
+
+    def __init__(self, schedule, time_steps, generator=None, noise_fn=None, s_array=None):
+        super().__init__(schedule, time_steps, generator=generator, noise_fn=noise_fn, s_array=s_array, fused=False)
+
+    def _node_noise(self, bs, N, F_, node_mask):
+        return torch.randn((bs, N, F_), device=node_mask.device, generator=self.generator) * node_mask
 
 
 def position_noise(B, N, node_mask, generator=None):

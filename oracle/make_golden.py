@@ -159,6 +159,49 @@ def run_sampler_case(ref):
     print('qm9_ancestral_chain:', tuple(x.shape), tuple(ex.shape), float(x.abs().max()))
 
 
+def run_sampler2d_case(ref):
+    """5 steps of the reference AncestralSampler_2D (sampling.py:599-661) with DGT_concat_2D, every noise draw recorded."""
+    ours = configs.NAMED['moses_2d']()
+    rcfg = ref_loader.load_config('vpsde_moses_2d_jodo')
+    model = ref.model_utils._MODELS[rcfg.model.name](rcfg)
+    model.load_state_dict(synth_state_dict(param_spec(ours), seed=6), strict=True)
+    model.eval()
+    ns = ref.noise_schedule.NoiseScheduleVP(rcfg.sde.schedule, continuous_beta_0=rcfg.sde.continuous_beta_0,
+                                            continuous_beta_1=rcfg.sde.continuous_beta_1)
+    time_steps = torch.linspace(ns.T, 1e-3, 1000)
+    sel = torch.tensor([0, 1, 500, 998, 999])
+    sampler = ref.sampling.AncestralSampler_2D(ns, time_steps[sel], True, True)
+    s_full = torch.cat([time_steps[1:], torch.zeros(1)])
+    sampler.s_array = s_full[sel]
+    batch = synth.make_batch(ours, 3, seed=12, n_nodes=[9, 20, 14])
+    rec = {'node': [], 'edge': []}
+    orig_n, orig_e = ref.sampling.sample_gaussian_with_mask, ref.sampling.sample_symmetric_edge_feature_noise
+
+    def rec_n(*a, **k):
+        v = orig_n(*a, **k)
+        rec['node'].append(v.clone())
+        return v
+
+    def rec_e(*a, **k):
+        v = orig_e(*a, **k)
+        rec['edge'].append(v.clone())
+        return v
+
+    ref.sampling.sample_gaussian_with_mask = rec_n
+    ref.sampling.sample_symmetric_edge_feature_noise = rec_e
+    torch.manual_seed(321)
+    try:
+        with torch.no_grad():
+            x, ex = sampler.sampling(model, batch['xh'], batch['node_mask'], batch['edge_mask'], batch['edge_x'], None)
+    finally:
+        ref.sampling.sample_gaussian_with_mask = orig_n
+        ref.sampling.sample_symmetric_edge_feature_noise = orig_e
+    out = dict(case='moses_2d_chain', config='moses_2d', weights=dict(seed=6), inputs=batch, t=time_steps[sel],
+               s=s_full[sel], noise_node=rec['node'], noise_edge=rec['edge'], x_mean=x, edge_x_mean=ex, seed=321)
+    torch.save(out, os.path.join(GOLD, 'moses_2d_chain.pt'))
+    print('moses_2d_chain:', tuple(x.shape), tuple(ex.shape), float(x.abs().max()), len(rec['node']), len(rec['edge']))
+
+
 def run_dpm_case(ref):
     """3 outer steps (6 model evaluations) of the reference DPM_Solver_hybrid ('singlestep_fixed', order 2,
     mix_dpm_solver.py:285-335) on the conditional QM9 model with a context, recording every position-noise draw."""
@@ -225,6 +268,8 @@ def main():
             run_case(ref, name)
     if not only or 'chain' in only:
         run_sampler_case(ref)
+    if not only or 'chain2d' in only:
+        run_sampler2d_case(ref)
     if not only or 'dpm' in only:
         run_dpm_case(ref)
     if not only or 'post' in only:

@@ -260,3 +260,44 @@ def test_graph_captured_chain_equals_eager_chain(cfg_name):
     print(f'{cfg_name}: eager {dt[0] * 1e3:.1f} ms, graphed {dt[1] * 1e3:.1f} ms for {len(grid)} steps of 48 molecules')
     assert torch.isfinite(res[0][0]).all()
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+def test_product_2d_sampler_replays_reference_chain():
+    """AncestralSampler2D driving the 2-D oracle against the chain recorded from the reference's AncestralSampler_2D +
+    DGT_concat_2D (tests/golden/moses_2d_chain.pt): replayed noise, then the same generator stream."""
+    g, cfg = load_golden('moses_2d_chain')
+    model = _oracle_model(golden_weights(g, cfg), cfg, torch.float32)
+    b = g['inputs']
+    noise = lambda i, kind: g['noise_node'][i] if kind == 'node' else g['noise_edge'][i]
+    smp = S.AncestralSampler2D(S.CosineVP(), g['t'], noise_fn=noise, s_array=g['s'])
+    xm, em = smp.sampling(model, b['xh'], b['node_mask'], b['edge_mask'], b['edge_x'])
+    assert float((xm - g['x_mean']).abs().max()) < 2e-4 * float(g['x_mean'].abs().max())
+    assert float((em - g['edge_x_mean']).abs().max()) < 2e-4 * float(g['edge_x_mean'].abs().max())
+    # own draws: masked Gaussian node noise then symmetric edge noise per step, one generator (sampling.py:644-659)
+    gen = torch.Generator().manual_seed(g['seed'])
+    smp = S.AncestralSampler2D(S.CosineVP(), g['t'], generator=gen, s_array=g['s'])
+    B, N, F_ = b['xh'].shape
+    for i in range(len(g['t'])):
+        assert torch.equal(smp._node_noise(B, N, F_, b['node_mask']), g['noise_node'][i])
+        assert torch.equal(S.edge_noise(B, N, b['edge_x'].shape[-1], b['edge_mask'], gen), g['noise_edge'][i])
+
+
+@pytest.mark.gpu
+def test_cuda_2d_chain():
+    """The same 2-D chain with the CUDA DGT_concat_2D behind the product sampler (replayed noise, 5 free-running
+    steps: loose tolerance as for the 3-D chain, exact invariants)."""
+    from jodo_b200.model import MODELS
+    g, cfg = load_golden('moses_2d_chain')
+    model = MODELS[cfg.model.name](cfg)
+    model.load_state_dict(golden_weights(g, cfg), strict=True)
+    model = model.cuda().eval()
+    b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in g['inputs'].items()}
+    noise = lambda i, kind: (g['noise_node'][i] if kind == 'node' else g['noise_edge'][i]).cuda()
+    smp = S.AncestralSampler2D(S.CosineVP(), g['t'], noise_fn=noise, s_array=g['s'])
+    xm, em = smp.sampling(model, b['xh'], b['node_mask'], b['edge_mask'], b['edge_x'])
+    xm, em = xm.cpu(), em.cpu()
+    assert float((xm - g['x_mean']).abs().max()) < 2e-2 * float(g['x_mean'].abs().max())
+    assert float((em - g['edge_x_mean']).abs().max()) < 2e-2 * float(g['edge_x_mean'].abs().max())
+    nm = g['inputs']['node_mask']
+    assert float((xm * (1 - nm)).abs().max()) == 0.0
+    assert float((em - em.permute(0, 2, 1, 3)).abs().max()) == 0.0
