@@ -23,7 +23,8 @@ def inverse_scale(config, pos, atom_type, fc_charge, node_mask, edge_type=None, 
     """utils.get_data_inverse_scaler(config)(...) of the reference (utils.py:88-103)."""
     pos_norm, atom_norm, fc_norm, edge_norm = normalize_factors(config)
     centered = config.data.centered
-    pos = pos * pos_norm * node_mask
+    if pos is not None:                         # 2-D models carry no coordinates (utils.py:96-97)
+        pos = pos * pos_norm * node_mask
     atom_type = atom_type * atom_norm
     fc_charge = fc_charge * fc_norm * node_mask
     if centered:
@@ -57,6 +58,11 @@ def post_process(config, xh, node_mask, edge_x=None, edge_mask=None):
     h_int = torch.round(h_int).long() * node_mask
     if edge_x is None:
         return pos, h_cat, h_int
+    return pos, h_cat, h_int, _bond_orders(config, h_edge)
+
+
+def _bond_orders(config, h_edge):
+    """Unnormalised edge channels -> bond orders 0..4 (sampling.py:75-95 = :120-142)."""
     if config.data.compress_edge:
         exist = (h_edge[..., 0] >= 0.5).to(h_edge.dtype)
         t = h_edge[..., 1] * 3.
@@ -72,7 +78,36 @@ def post_process(config, xh, node_mask, edge_x=None, edge_mask=None):
     else:
         any_on = torch.sum(h_edge > 0.5, dim=-1) != 0
         h_edge = any_on * (torch.argmax(h_edge, dim=-1) + 1.0)
-    return pos, h_cat, h_int, h_edge
+    return h_edge
+
+
+def post_process_2d(config, xh, node_mask, edge_x, edge_mask):
+    """sampling.post_process_2D (sampling.py:100-144): the same without coordinates (xh = atom features [+ charge])."""
+    atom_types = int(config.data.atom_types)
+    if bool(config.model.include_fc_charge):
+        h_int, h_cat = xh[:, :, -1:], xh[:, :, :-1]
+    else:
+        h_int, h_cat = torch.zeros(0, device=xh.device), xh
+    assert h_cat.shape[-1] == atom_types
+    _, h_cat, h_int, h_edge = inverse_scale(config, None, h_cat, h_int, node_mask, edge_x, edge_mask)
+    h_cat = F.one_hot(torch.argmax(h_cat, dim=2), atom_types) * node_mask
+    h_int = torch.round(h_int).long() * node_mask
+    return h_cat, h_int, _bond_orders(config, h_edge)
+
+
+def mol_process_2d(one_hot, formal_charges, n_nodes, edge_types):
+    """sampling.mol_process_2D (sampling.py:35-50) with one device-to-host transfer per tensor: list of
+    (None, atom_type, edge_type, fc)."""
+    atom_type_all = one_hot.argmax(2).detach().cpu()
+    edge_all = edge_types.detach().cpu()
+    n = [int(v) for v in n_nodes]
+    if formal_charges.shape[-1] != 0:
+        fc_all = formal_charges[..., 0].long().detach().cpu()
+        fcs = [fc_all[i, :n[i]] for i in range(len(n))]
+    else:
+        fc_all = formal_charges.detach().cpu()
+        fcs = [fc_all[i][:n[i]] for i in range(len(n))]
+    return [(None, atom_type_all[i, :n[i]], edge_all[i, :n[i], :n[i]], fcs[i]) for i in range(len(n))]
 
 
 def mol_process(one_hot, x, formal_charges, n_nodes, edge_types=None):

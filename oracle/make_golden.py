@@ -254,6 +254,16 @@ def run_postprocess_case(ref):
         mols = ref.sampling.mol_process(one_hot, pos, fc, b['n_nodes'], edge)
         out[cfg_name] = dict(xh=xh, edge_x=ex, node_mask=b['node_mask'], edge_mask=b['edge_mask'], n_nodes=b['n_nodes'],
                              pos=pos, one_hot=one_hot, fc=fc, edge=edge, mols=mols)
+    ours = configs.NAMED['moses_2d']()                         # 2-D: post_process_2D + mol_process_2D (sampling.py:35-50, 100-144)
+    rcfg = ref_loader.load_config('vpsde_moses_2d_jodo')
+    b = synth.make_batch(ours, 6, seed=32)
+    xh, ex = b['xh'] * 0.8, b['edge_x'] * 0.9
+    inv = ref.utils.get_data_inverse_scaler(rcfg)
+    one_hot, fc, edge = ref.sampling.post_process_2D(xh.clone(), rcfg.data.atom_types, rcfg.model.include_fc_charge,
+                                                     b['node_mask'], inv, ex.clone(), b['edge_mask'], rcfg.data.compress_edge)
+    mols = ref.sampling.mol_process_2D(one_hot, fc, b['n_nodes'], edge)
+    out['moses_2d'] = dict(xh=xh, edge_x=ex, node_mask=b['node_mask'], edge_mask=b['edge_mask'], n_nodes=b['n_nodes'],
+                           one_hot=one_hot, fc=fc, edge=edge, mols=mols)
     torch.save(out, os.path.join(GOLD, 'postprocess.pt'))
     print('postprocess:', {k: tuple(v['edge'].shape) for k, v in out.items()})
 

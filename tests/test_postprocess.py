@@ -8,7 +8,7 @@ import torch
 
 from helpers import GOLDEN
 from jodo_b200 import configs
-from jodo_b200.postprocess import mol_process, post_process
+from jodo_b200.postprocess import mol_process, mol_process_2d, post_process, post_process_2d
 
 
 @pytest.mark.parametrize('cfg_name', ['qm9_uncond', 'geom_l8'])
@@ -25,6 +25,21 @@ def test_post_process_matches_reference(cfg_name):
     assert len(mols) == len(g['mols'])
     for (p, a, e, c), (rp, ra, re_, rc) in zip(mols, g['mols']):
         assert torch.equal(p, rp) and torch.equal(a, ra) and torch.equal(e, re_) and torch.equal(c, rc)
+
+
+def test_post_process_2d_matches_reference():
+    """post_process_2D / mol_process_2D of the reference (sampling.py:35-50, 100-144) on a MOSES-shaped final state
+    (7 atom types, no charges, 3 compressed edge channels incl. aromatic)."""
+    g = torch.load(os.path.join(GOLDEN, 'postprocess.pt'), weights_only=False)['moses_2d']
+    cfg = configs.NAMED['moses_2d']()
+    one_hot, fc, edge = post_process_2d(cfg, g['xh'].clone(), g['node_mask'], g['edge_x'].clone(), g['edge_mask'])
+    assert torch.equal(one_hot, g['one_hot']) and torch.equal(fc, g['fc']) and torch.equal(edge, g['edge'])
+    assert 4. in edge.unique().tolist()                        # aromatic bonds occur in the fixture
+    mols = mol_process_2d(one_hot, fc, g['n_nodes'], edge)
+    assert len(mols) == len(g['mols'])
+    for (p, a, e, c), (rp, ra, re_, rc) in zip(mols, g['mols']):
+        assert p is None and rp is None
+        assert torch.equal(a, ra) and torch.equal(e, re_) and torch.equal(c, rc)
 
 
 def test_mol_process_without_edges_and_charges():
