@@ -50,6 +50,7 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--no-graph', action='store_true', help='time the eager step instead of the CUDA-graph replay')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='qm9', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch override (debug)')
@@ -189,6 +190,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group('nccl', device_id=dev)
     cfg_name, batch, max_n, desc = WORKLOADS[args.workload]
     if args.batch:
@@ -202,7 +204,8 @@ def run_b200(args):
     tot = roofline.batch_totals(n_nodes, d)
     node_mask, edge_mask = b['node_mask'].to(dev), b['edge_mask'].to(dev)
     grid = torch.linspace(0.9946, 1e-3, 1000)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    torch.cuda.manual_seed(1234 + rank)                   # the samplers draw from the default CUDA generator
+    gen = None
     smp = S.AncestralSampler(S.CosineVP(), grid, generator=gen)
     K, W = args.steps, args.warmup
     dpm = args.workload == 'qm9_cond'
@@ -238,6 +241,16 @@ def run_b200(args):
 
     for i in range(W):
         step(i)
+    # One reverse step captured into a CUDA graph and replayed (same kernels, same random stream; removes the host
+    # launch gaps between the ~125 kernels of a step).  Falls back to the eager step if the capture fails.
+    graphed, graph_note = None, 'eager'
+    if not dpm and not args.no_graph and W >= 2:
+        try:
+            graphed = S.GraphedAncestralStep(smp, model, state['x'], state['ex'], state['cx'], state['cex'], node_mask, edge_mask)
+            graphed.run(W - 1)                             # one untimed replay
+            graph_note = 'cuda graph replay'
+        except Exception as exc:                           # noqa: BLE001
+            graphed, graph_note = None, 'eager (graph capture failed: %s)' % str(exc)[:120]
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -249,13 +262,20 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(W, W + K):
-        step(i)
+        if graphed is not None:
+            graphed.run(i)
+        else:
+            step(i)
     e1.record()
     barrier()
     if prof:
         torch.cuda.cudart().cudaProfilerStop()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     launches = _lib.LAUNCHES - l0
+    if graphed is not None:
+        launches = graphed.launches_per_step * K           # replays do not pass through the ctypes binding
+        state.update(x=graphed.x, ex=graphed.edge_x, cx=graphed.cond_x, cex=graphed.cond_edge_x, xm=graphed.x_mean,
+                     em=graphed.edge_mean)
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -273,6 +293,20 @@ def run_b200(args):
         d2h = sum(v.numel() * 4 for v in outh.values())
 
         def e2e_step(i):
+            if graphed is not None:                      # host buffers -> the graph's static inputs -> replay -> host
+                graphed.x.copy_(host['x'], non_blocking=True)
+                graphed.edge_x.copy_(host['ex'], non_blocking=True)
+                graphed.cond_x.copy_(host['cx'], non_blocking=True)
+                graphed.cond_edge_x.copy_(host['cex'], non_blocking=True)
+                graphed.run(i)
+                outh['x'].copy_(graphed.x, non_blocking=True)
+                outh['ex'].copy_(graphed.edge_x, non_blocking=True)
+                outh['cx'].copy_(graphed.cond_x, non_blocking=True)
+                outh['cex'].copy_(graphed.cond_edge_x, non_blocking=True)
+                torch.cuda.current_stream().synchronize()       # the caller reads the result on the host
+                for k in host:
+                    host[k], outh[k] = outh[k], host[k]
+                return
             dv = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
             if dpm:
                 sol.cond_x, sol.cond_edge_x = dv['cx'], dv['cex']
@@ -374,7 +408,7 @@ def run_b200(args):
             'dtype': 'f16 operands (tf32 mantissa) / f32 accumulate + f32 elementwise', 'data': 'synthetic',
             'config': {'workload': desc, 'per_gpu_batch': batch, 'N': N, 'atoms': tot['atoms'], 'edges': tot['edges'],
                        'arch': cfg_name, 'weights': 'random init (seed 42)', 'l2': 'inputs larger than L2 '
-                       '(edge state %.0f MB per step)' % (tot['bytes'] / 1e6), 'parallelism': f'dp{world} (independent molecules)'},
+                       '(edge state %.0f MB per step)' % (tot['bytes'] / 1e6), 'parallelism': f'dp{world} (independent molecules)', 'step_launch': graph_note},
             'e2e': e2e, 'gpu_launches': launches, 'clocks': clk, 'roofline': roof, 'whole_step': whole,
             'kernels': kernels, 'cpu_baseline': cpu, 'finite': ok, 'gathered': gathered,
         }

@@ -179,8 +179,6 @@ class AncestralSampler:
         return x_mean, edge_mean
 
     def _sampling_graphed(self, model, z_T, node_mask, edge_mask, edge_z_T, context):
-        if not (z_T.is_cuda and self.fused and self.noise_fn is None and self.generator is None):
-            raise ValueError('graph=True needs CUDA tensors, the fused update and the default CUDA generator')
         n = len(self.t_array)
         c32 = lambda t: t.contiguous().float()
         x, edge_x = c32(z_T), c32(edge_z_T)
@@ -192,34 +190,57 @@ class AncestralSampler:
                 model, i, x, edge_x, node_mask, edge_mask, cond_x, cond_edge_x, context)
         if n <= eager:
             return x_mean, edge_mean
-        dev = x.device
-        bs = x.shape[0]
-        table = torch.tensor([[float(v) for v in self.coef[i]] for i in range(n)], device=dev, dtype=torch.float32)
-        coef = torch.zeros(4, device=dev, dtype=torch.float32)            # {c_x, c_pred, sigma, noise level} of the step
-        sx, sex, scx, scex = x.clone(), edge_x.clone(), c32(cond_x).clone(), c32(cond_edge_x).clone()
+        gs = GraphedAncestralStep(self, model, x, edge_x, cond_x, cond_edge_x, node_mask, edge_mask, context)
+        for i in range(eager, n):
+            gs.run(i)
+        return gs.x_mean.clone(), gs.edge_mean.clone()
+
+
+class GraphedAncestralStep:
+    """One self-conditioned reverse step of an AncestralSampler (denoiser call + noise draws + fused update + hand-off
+    copies) captured into a CUDA graph.  ``run(i)`` writes the coefficients of step i into device memory and replays
+    the graph; the state lives in the static buffers x, edge_x, cond_x, cond_edge_x (inputs of the next step) and
+    x_mean, edge_mean.  The model must have run the self-conditioned path once with these masks before (workspaces and
+    the plan are created outside the capture)."""
+
+    def __init__(self, sampler, model, x, edge_x, cond_x, cond_edge_x, node_mask, edge_mask, context=None):
+        if not (x.is_cuda and sampler.fused and sampler.noise_fn is None and sampler.generator is None):
+            raise ValueError('the graph-captured step needs CUDA tensors, the fused update and the default CUDA generator')
+        if cond_x is None:
+            raise ValueError('capture the self-conditioned step: run the first reverse step eagerly')
+        from . import _lib
+        c32 = lambda t: t.contiguous().float()
+        dev, bs = x.device, x.shape[0]
+        n = len(sampler.t_array)
+        self.table = torch.tensor([[float(v) for v in sampler.coef[i]] for i in range(n)], device=dev, dtype=torch.float32)
+        self.coef = torch.zeros(4, device=dev, dtype=torch.float32)       # {c_x, c_pred, sigma, noise level} of the step
+        self.x, self.edge_x = c32(x).clone(), c32(edge_x).clone()
+        self.cond_x, self.cond_edge_x = c32(cond_x).clone(), c32(cond_edge_x).clone()
         vec_t = torch.zeros(bs, device=dev)                               # ignored by the model (reference mol_gnn.py:534)
         ctx = None if context is None else c32(context).clone()
 
         def one_step():
-            nl = coef[3:4].expand(bs)
-            pred, edge_pred = model(vec_t, sx, node_mask, edge_mask, edge_x=sex, noise_level=nl, cond_x=scx,
-                                    cond_edge_x=scex, context=ctx)
-            out = self._fused_update(sx, sex, pred, edge_pred, node_mask, edge_mask, 0.0, 0.0, 0.0, coef_dev=coef)
-            sx.copy_(out[0]); sex.copy_(out[1]); scx.copy_(pred); scex.copy_(edge_pred)
+            nl = self.coef[3:4].expand(bs)
+            pred, edge_pred = model(vec_t, self.x, node_mask, edge_mask, edge_x=self.edge_x, noise_level=nl,
+                                    cond_x=self.cond_x, cond_edge_x=self.cond_edge_x, context=ctx)
+            out = sampler._fused_update(self.x, self.edge_x, pred, edge_pred, node_mask, edge_mask, 0.0, 0.0, 0.0,
+                                        coef_dev=self.coef)
+            self.x.copy_(out[0]); self.edge_x.copy_(out[1]); self.cond_x.copy_(pred); self.cond_edge_x.copy_(edge_pred)
             return out[2], out[3]
 
-        coef.copy_(table[eager])
-        g = torch.cuda.CUDAGraph()
+        self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        l0 = _lib.LAUNCHES
         with torch.cuda.stream(side):           # capture needs a non-default stream; nothing runs during capture
-            with torch.cuda.graph(g, stream=side):
-                xm, em = one_step()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.x_mean, self.edge_mean = one_step()
         torch.cuda.current_stream().wait_stream(side)
-        for i in range(eager, n):
-            coef.copy_(table[i])
-            g.replay()
-        return xm.clone(), em.clone()
+        self.launches_per_step = _lib.LAUNCHES - l0      # kernels of ours inside one replay
+
+    def run(self, i):
+        self.coef.copy_(self.table[i])
+        self.graph.replay()
 
 
 class AncestralSampler2D(AncestralSampler):
