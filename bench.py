@@ -190,8 +190,19 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # keep NCCL's version banner off stdout (one JSON line)
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on stdout while the communicator comes up (the image sets NCCL_DEBUG=VERSION);
+        # stdout must carry one JSON line, so file descriptor 1 points at stderr during the initialisation
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     cfg_name, batch, max_n, desc = WORKLOADS[args.workload]
     if args.batch:
         batch = args.batch
