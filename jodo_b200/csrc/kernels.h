@@ -48,13 +48,6 @@ __host__ __device__ constexpr int tab_gbf(int D) { return 6 * D + 6 * (D / 4) + 
 // 128 rows; every group = all (n-1) partners of one atom, never split across tiles.
 using Plan = ::jodo_plan;
 
-struct ModelDims {
-  int D, ed, T, L, r, S, sc, qk, C, inn, ch, cn, ce, cond_ch;
-  int ld_tab;                            // floats per molecule in the table buffer
-  int ld_ah;                             // row stride of the concatenated atom hidden buffer
-  int keh;                               // columns (multiple of 32) of the concatenated edge hidden image
-};
-
 // ---- node / molecule elementwise kernels (node_kernels.cu) -----------------------------------------
 cudaError_t launch_time_features(const float* nl, const float* w, float* feat, int B, cudaStream_t st);
 cudaError_t launch_cond_in(const float* ctx, const float* w0, const float* b0, float* out, int rows, int D, cudaStream_t st);
