@@ -14,8 +14,9 @@ One JSON line on stdout (rank 0).  `value` = whole-job throughput with state res
 `e2e` = same step driven through the public API with HOST (pinned) buffers, H2D of the step's inputs
 and D2H of its results inside the timed region; `roofline` = the dominant kernel against the measured
 peak; `cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
---impl reference times the CPU implementation (oracle port of the reference; the Python reference
-itself cannot travel to the GPU box) on rank 0 only.
+--impl reference times the reference's own CPU implementation on rank 0 only: the unmodified reference
+modules from oracle/_ref/reference (staged by build(), git-ignored, travels with gpurun) -- kind "reference";
+only if those are absent, the oracle port -- kind "port".
 """
 import argparse
 import json
@@ -154,6 +155,76 @@ def cpu_step_rate(cfg, wl, n_steps, threads):
     return bs * n_steps / dt, f'{bs} molecules (same histogram, seed 42) x {n_steps} ancestral steps, oracle port fp32'
 
 
+REF_FILES = {'qm9': ('vpsde_qm9_uncond_jodo', {}), 'geom': ('vpsde_geom_uncond_jodo', {'n_layers': 8}),
+             'geom_l10': ('vpsde_geom_uncond_jodo', {}), 'geom_large': ('vpsde_geom_uncond_jodo', {'nf': 384}),
+             'qm9_cond': ('vpsde_qm9_cond_jodo', {})}
+
+
+def reference_step_rate(cfg, wl, n_steps, threads):
+    """CPU arm, kind "reference": the UNMODIFIED reference modules (models/mol_gnn.py, models/layers.py, sampling.py,
+    mix_dpm_solver.py, diffusion/noise_schedule.py from /root/reference or its byte-identical staged copy under
+    oracle/_ref/reference) through the PyG/scatter shim, fp32, all host threads, driving the reference's own sampler
+    loop on a bounded sample of the workload.  Returns (mol-steps/s, sample description) or None when the reference
+    sources are not present."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return None
+    from jodo_b200 import synth
+    from jodo_b200.params import param_spec, synth_state_dict
+    torch.set_num_threads(threads)
+    ref = ref_loader.load()
+    fname, over = REF_FILES[wl]
+    rcfg = ref_loader.load_config(fname)
+    for k, v in over.items():
+        rcfg.model[k] = v
+    rcfg.device = torch.device('cpu')
+    bs = CPU_SAMPLE[wl]
+    _, _, max_n, _ = WORKLOADS[wl]
+    b = synth.make_batch(cfg, bs, seed=42, max_n=max_n)
+    model = ref.model_utils.create_model(rcfg)                # registry + DataParallel wrap (models/utils.py:24-28)
+    sd = synth_state_dict(param_spec(cfg), seed=int(cfg.seed))
+    model.load_state_dict({'module.' + k: v for k, v in sd.items()}, strict=True)
+    model.eval()
+    ns = ref.noise_schedule.NoiseScheduleVP(rcfg.sde.schedule, continuous_beta_0=rcfg.sde.continuous_beta_0,
+                                            continuous_beta_1=rcfg.sde.continuous_beta_1)
+    torch.manual_seed(1)
+    src = 'staged copy oracle/_ref/reference' if ref_loader.is_staged_copy() else ref_loader.REF_ROOT
+    with torch.no_grad():
+        if wl == 'qm9_cond':
+            ctx = torch.randn(bs, 1, generator=torch.Generator().manual_seed(2))
+            n_eval = max(2, n_steps - n_steps % 2)
+            rcfg.sampling.method = 'fast'
+            rcfg.sampling.dpm_solver_method, rcfg.sampling.dpm_solver_order = 'singlestep_fixed', 2
+            rcfg.sampling.steps = 2
+            ref.mix_dpm_solver.DPM_Solver_hybrid(ns, rcfg).sampling(model, b['xh'], b['node_mask'], b['edge_mask'], b['edge_x'], ctx)
+            rcfg.sampling.steps = n_eval
+            sol = ref.mix_dpm_solver.DPM_Solver_hybrid(ns, rcfg)
+            t0 = time.perf_counter()
+            sol.sampling(model, b['xh'], b['node_mask'], b['edge_mask'], b['edge_x'], ctx)
+            dt = time.perf_counter() - t0
+            return bs * n_eval / dt, (f'{bs} molecules (same histogram, seed 42) x {n_eval} model evaluations of the reference '
+                                      f'DPM_Solver_hybrid.sampling, unmodified reference fp32 ({src})')
+        grid = torch.linspace(ns.T, 1e-3, 1000)
+        mk = lambda ts: ref.sampling.AncestralSampler(ns, ts, rcfg.model.pred_data, rcfg.pred_edge, rcfg.model.self_cond,
+                                                      ref.utils.get_self_cond_fn(rcfg))
+        mk(grid[:2]).sampling(model, b['xh'], b['node_mask'], b['edge_mask'], b['edge_x'], None)          # warm-up
+        smp = mk(grid[:n_steps])
+        t0 = time.perf_counter()
+        smp.sampling(model, b['xh'], b['node_mask'], b['edge_mask'], b['edge_x'], None)
+        dt = time.perf_counter() - t0
+    return bs * n_steps / dt, (f'{bs} molecules (same histogram, seed 42) x {n_steps} steps of the reference '
+                               f'AncestralSampler.sampling, unmodified reference fp32 ({src})')
+
+
+def cpu_arm(cfg, wl, n_steps, threads):
+    """(rate, sample, kind): the unmodified reference when its sources travelled, else the oracle port."""
+    r = reference_step_rate(cfg, wl, n_steps, threads)
+    if r is not None:
+        return r[0], r[1], 'reference'
+    rate, sample = cpu_step_rate(cfg, wl, n_steps, threads)
+    return rate, sample, 'port'
+
+
 def run_reference(args):
     from jodo_b200 import configs
     rank = int(os.environ.get('RANK', '0'))
@@ -164,14 +235,14 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     n = max(1, args.steps)
     t0 = time.perf_counter()
-    rate, sample = cpu_step_rate(cfg, args.workload, n, threads)
+    rate, sample, kind = cpu_arm(cfg, args.workload, n, threads)
     wall = time.perf_counter() - t0
     out = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * CPU_SAMPLE[args.workload] / rate, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': desc, 'per_gpu_batch': batch},
-        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample},
         'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'wall_s': wall,
     }
@@ -409,8 +480,8 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, sample = cpu_step_rate(cfg, args.workload, 24 if args.workload == 'qm9' else 40, threads)
-        cpu = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample}
+        rate, sample, kind = cpu_arm(cfg, args.workload, 24 if args.workload == 'qm9' else 40, threads)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample}
 
     if rank == 0:
         out = {

@@ -93,12 +93,18 @@ class _Workspace:
 
 
 class _DGTBase(nn.Module):
+    VARIANT = None      # set by the subclasses: the variant is the class's, whatever name the registry knows it under
+
     def __init__(self, config):
         super().__init__()
-        check_supported(config)
-        self.dims = dims_from_config(config)
-        # nf = 256: fused edge-tile kernels; other sizes and the 2-D model: GEMM + row-kernel path (wide.py)
-        self.wide = self.dims.D != 256 or self.dims.two_d
+        check_supported(config, self.VARIANT)
+        self.dims = dims_from_config(config, self.VARIANT)
+        # nf = 256 with the 14 + 2 head layout of every reference config: fused edge-tile kernels (csrc/attn.cu and
+        # equi.cu hard-code 7 learned heads of 18 channels per half, 16-column value heads, the /3 adjacency mean);
+        # other sizes, other head layouts and the 2-D model: GEMM + row-kernel path (wide.py), which takes H / X / sc
+        # as arguments
+        d_ = self.dims
+        self.wide = d_.two_d or not (d_.D == 256 and d_.H == 16 and d_.X == 2 and d_.S == 14 and d_.sc == 18 and d_.C == 16)
         if self.wide:
             why = wide.supported(self.dims)
             if why:
@@ -111,7 +117,7 @@ class _DGTBase(nn.Module):
         self.edge_th = float(config.model.edge_quan_th)
         self.spatial_cut_off = float(getattr(config.model, 'spatial_cut_off', 0.))
         self.n_layers = self.dims.L
-        self._spec = param_spec(config)
+        self._spec = param_spec(config, self.VARIANT)
         build_param_tree(self, self._spec)
         self.load_state_dict(synth_state_dict(self._spec, seed=int(getattr(config, 'seed', 0))))
         self._packed = {}
@@ -196,6 +202,13 @@ class _DGTBase(nn.Module):
     def forward(self, t, xh, node_mask, edge_mask, context=None, *args, **kwargs):
         if self.training:
             raise RuntimeError('jodo_b200 implements the inference path (call model.eval())')
+        if getattr(self, '_is_replica', False):
+            # torch.nn.DataParallel over several devices (reference models/utils.py:27 with > 1 visible GPU) calls
+            # per-device replicas from worker threads; replicas have no parameters() and would share this module's
+            # packed images, plans and workspaces across devices
+            raise _lib.JodoError('jodo_b200 modules cannot be replicated by torch.nn.DataParallel over several devices: '
+                                 'run one process per GPU (torchrun; sampler.shard_molecules / gather_samples) or '
+                                 'restrict the process to one device (CUDA_VISIBLE_DEVICES)')
         edge_x = kwargs['edge_x']
         noise_level = kwargs['noise_level']
         cond_x = kwargs.get('cond_x')
@@ -330,16 +343,19 @@ class _DGTBase(nn.Module):
 
 class DGT_concat(_DGTBase):
     """B200-native drop-in for the reference ``DGT_concat`` (models/mol_gnn.py:410-594)."""
+    VARIANT = 'uncond'
 
 
 class Cond_DGT_concat(_DGTBase):
     """B200-native drop-in for the reference ``Cond_DGT_concat`` (models/mol_gnn.py:597-794)."""
+    VARIANT = 'cond'
 
 
 class DGT_concat_2D(_DGTBase):
     """B200-native drop-in for the reference ``DGT_concat_2D`` (models/mol_gnn.py:797-947; MOSES / ZINC250k configs):
     atom features and bonds only -- ``xh`` is ``[B, N, in]``, the return is ``(atom_pred [B,N,in], e_hat)``.  Runs
     on the wide path without the distance features and the coordinate branch, with one adjacency head."""
+    VARIANT = '2d'
 
 
 MODELS = {'DGT_concat': DGT_concat, 'cond_DGT_concat': Cond_DGT_concat, 'DGT_concat_2D': DGT_concat_2D}

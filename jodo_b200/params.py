@@ -49,16 +49,36 @@ class Dims:
         return self.ce * self.L + self.ed
 
 
-def dims_from_config(config) -> Dims:
+VARIANTS = ('uncond', 'cond', '2d', 'sim')
+_NAME_TO_VARIANT = {'DGT_concat': 'uncond', 'cond_DGT_concat': 'cond', 'DGT_concat_2D': '2d', 'DGT_concat_sim': 'sim'}
+
+
+def variant_of(config, variant=None):
+    """Which reference class the config selects.  A model class passes its own ``variant``; stand-alone callers
+    (tests, tools) get it from ``config.model.name``, with any registry suffix such as ``_b200`` ignored
+    (reference models/utils.py:24-25 resolves the class by that name)."""
+    if variant is not None:
+        if variant not in VARIANTS:
+            raise ValueError(f'unknown variant {variant!r}')
+        return variant
+    name = str(config.model.name)
+    for base in sorted(_NAME_TO_VARIANT, key=len, reverse=True):
+        if name == base or (name.startswith(base + '_') and name[len(base) + 1:] not in ('2D', 'sim')):
+            return _NAME_TO_VARIANT[base]
+    raise ValueError(f'unsupported model.name {name!r}')
+
+
+def dims_from_config(config, variant=None) -> Dims:
     m, d = config.model, config.data
+    variant = variant_of(config, variant)
     D = int(m.nf)
     H = int(m.n_heads)
     X = int(m.n_extra_heads)
     S = H - X
     L = int(m.n_layers)
     ed = D // 4
-    cond = str(m.name).startswith('cond')
-    two_d = str(m.name) == 'DGT_concat_2D'
+    cond = variant == 'cond'
+    two_d = variant == '2d'
     if two_d and int(getattr(m, 'time_dim', 4 * D)) != 4 * D:
         raise NotImplementedError('DGT_concat_2D: model.time_dim must be 4 * model.nf')
     return Dims(two_d=two_d, D=D, ed=ed, T=4 * D, L=L, r=int(m.mlp_ratio), H=H, X=X, S=S, sc=D // S,
@@ -67,12 +87,14 @@ def dims_from_config(config) -> Dims:
                 cond_ch=int(m.cond_ch) if cond else 0)
 
 
-def check_supported(config):
-    """Variants of the reference model this implementation covers."""
+def check_supported(config, variant=None):
+    """Variants of the reference model this implementation covers.  The variant is the
+    CLASS's (the registry may know it under any name, e.g. ``DGT_concat_b200``), not ``config.model.name``."""
     m = config.model
-    if m.name not in ('DGT_concat', 'cond_DGT_concat', 'DGT_concat_2D'):
-        raise ValueError(f'unsupported model.name {m.name!r}')
-    two_d = m.name == 'DGT_concat_2D'
+    variant = variant_of(config, variant)
+    if variant == 'sim':
+        raise NotImplementedError('jodo_b200: the DGT_concat_sim variant (reference models/mol_gnn.py:949) is not built')
+    two_d = variant == '2d'
     need = dict(cond_time=True, softmax_inf=True, pred_data=True)
     if not two_d:
         need.update(dist_gbf=True, gbf_name='CondGaussianLayer', CoM=True)
@@ -128,9 +150,9 @@ def param_spec_2d(d: Dims):
     return spec
 
 
-def param_spec(config):
+def param_spec(config, variant=None):
     """Ordered [(name, shape)] exactly as the reference module registers them."""
-    d = dims_from_config(config)
+    d = dims_from_config(config, variant)
     if d.two_d:
         return param_spec_2d(d)
     D, ed, T = d.D, d.ed, d.T

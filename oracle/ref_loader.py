@@ -1,5 +1,7 @@
-"""ORACLE tooling (test infrastructure): import the UNMODIFIED reference modules in the build
-container.  /root/reference does not exist on the GPU box; nothing that runs there imports this.
+"""ORACLE tooling (test infrastructure): import the UNMODIFIED reference modules -- from /root/reference in
+the build container, else from the byte-identical staged copy under oracle/_ref/reference
+(oracle/stage_ref.py; git-ignored, travels to the GPU box).  Only tests/, smoke() and the reference arm
+of bench.py import this; the product package never does.
 
 The reference needs torch_geometric / torch_scatter / ml_collections, none installable offline;
 oracle/shim provides pure-torch stand-ins for the handful of entry points the DGT hot path uses
@@ -10,12 +12,28 @@ import importlib.util
 import os
 import sys
 
-REF_ROOT = os.environ.get('JODO_REFERENCE_ROOT', '/root/reference')
-SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'shim')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED = os.path.join(_HERE, '_ref', 'reference')
+SHIM = os.path.join(_HERE, 'shim')
+
+
+def _pick_root():
+    env = os.environ.get('JODO_REFERENCE_ROOT')
+    for cand in ([env] if env else []) + ['/root/reference', STAGED]:
+        if cand and os.path.isdir(os.path.join(cand, 'models')):
+            return cand
+    return env or '/root/reference'
+
+
+REF_ROOT = _pick_root()
 
 
 def available():
     return os.path.isdir(os.path.join(REF_ROOT, 'models'))
+
+
+def is_staged_copy():
+    return os.path.abspath(REF_ROOT) == os.path.abspath(STAGED)
 
 
 def load():
@@ -34,7 +52,17 @@ def load():
     ns.utils = importlib.import_module('utils')
     ns.sampling = importlib.import_module('sampling')
     ns.mix_dpm_solver = importlib.import_module('mix_dpm_solver')
+    ns.ema = importlib.import_module('models.ema')
+    ns.node_distribution = importlib.import_module('models.node_distribution')
     return ns
+
+
+def load_datasets_config():
+    """datasets/datasets_config.py by file path (the `datasets` package itself needs PyG + rdkit)."""
+    spec = importlib.util.spec_from_file_location('ref_datasets_config', os.path.join(REF_ROOT, 'datasets', 'datasets_config.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def load_config(fname):

@@ -1,0 +1,109 @@
+"""Test-side harness that drives the UNMODIFIED reference the way reference run_lib.vpsde_edge_evaluate does
+(run_lib.py:163-227): registry -> create_model (DataParallel wrap) -> strict checkpoint load through the
+`module.` prefix -> ExponentialMovingAverage.copy_to -> get_sampling_fn(...)(model).
+
+run_lib.py itself cannot be imported (PyG datasets, rdkit, fcd_torch, moses at import time), so the few
+lines of vpsde_edge_evaluate that matter are restated here around the reference's own functions.
+Test infrastructure: imports oracle/ (ref_loader + shim), never used by the product path.
+"""
+import contextlib
+import random
+
+import torch
+
+from jodo_b200.params import synth_state_dict
+from oracle import ref_loader
+
+REF_CONFIG_FILE = {'qm9_uncond': 'vpsde_qm9_uncond_jodo', 'qm9_cond': 'vpsde_qm9_cond_jodo',
+                   'moses_2d': 'vpsde_moses_2d_jodo', 'geom': 'vpsde_geom_uncond_jodo'}
+
+
+def reference():
+    """The reference modules (from /root/reference or the staged byte-identical copy), with the jodo_b200 classes
+    registered under '<name>_b200' and the EMA writers watched, exactly as INTEGRATION.md tells a maintainer to."""
+    ref = ref_loader.load()
+    from jodo_b200.model import register_into_reference, watch_data_writers
+    register_into_reference(ref.model_utils)
+    watch_data_writers(ref.ema.ExponentialMovingAverage)
+    return ref
+
+
+@contextlib.contextmanager
+def replayed_randn(seed):
+    """Every torch.randn of the reference sampler (models/utils.py:67-99) draws from one CPU generator and is then
+    moved to the requested device, so a CUDA run and a CPU run see identical noise."""
+    g = torch.Generator().manual_seed(seed)
+    real = torch.randn
+
+    def fake(*size, device=None, dtype=None, **kw):
+        if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)):
+            size = tuple(size[0])
+        out = real(size, generator=g, dtype=dtype)
+        return out.to(device) if device is not None else out
+
+    torch.randn = fake
+    try:
+        yield
+    finally:
+        torch.randn = real
+
+
+def make_config(ref_cfg_file, device, model_name=None, steps=None, batch=None, **model_overrides):
+    cfg = ref_loader.load_config(ref_cfg_file)
+    cfg.device = torch.device(device)
+    if model_name:
+        cfg.model.name = model_name
+    if steps:
+        cfg.sampling.steps = steps
+    if batch:
+        cfg.eval.batch_size = batch
+    for k, v in model_overrides.items():
+        cfg.model[k] = v
+    return cfg
+
+
+def build_model(ref, cfg, weights, via_ema=True, single_device=True):
+    """create_model (reference models/utils.py:24-28) + restore_checkpoint's strict load (utils.py:15-19) +
+    ema.copy_to (run_lib.py:222).  `weights`: state dict without the DataParallel prefix; with via_ema the model is
+    first loaded with DIFFERENT weights and `weights` arrive through the positional EMA copy."""
+    model = ref.model_utils.create_model(cfg)
+    assert isinstance(model, torch.nn.DataParallel)
+    if single_device and torch.cuda.device_count() > 1 and cfg.device.type == 'cuda':
+        model = torch.nn.DataParallel(model.module, device_ids=[cfg.device.index or 0])
+    names = [k for k, _ in model.module.named_parameters()]
+    if via_ema:
+        other = {k: v + 0.25 for k, v in weights.items()}
+        model.load_state_dict({'module.' + k: v for k, v in other.items()}, strict=True)
+        ema = ref.ema.ExponentialMovingAverage(model.parameters(), decay=0.999)
+        ema.load_state_dict(dict(decay=0.999, num_updates=1,          # as restore_checkpoint does (utils.py:18, ema.py:82-85)
+                                 shadow_params=[weights[k].to(cfg.device).clone() for k in names]))
+        ema.copy_to(model.parameters())
+    else:
+        model.load_state_dict({'module.' + k: v for k, v in weights.items()}, strict=True)
+    return model
+
+
+def sampling_fn_for(ref, cfg, batch, n_samples, info_name=None):
+    """get_node_dist + NoiseScheduleVP + inverse scaler + get_sampling_fn, as run_lib.py:174-203."""
+    dc = ref_loader.load_datasets_config()
+    info = dc.get_dataset_info(info_name or cfg.data.info_name)
+    nodes_dist = ref.node_distribution.get_node_dist(info)
+    ns = ref.noise_schedule.NoiseScheduleVP(cfg.sde.schedule, continuous_beta_0=cfg.sde.continuous_beta_0,
+                                            continuous_beta_1=cfg.sde.continuous_beta_1)
+    inv = ref.utils.get_data_inverse_scaler(cfg)
+    return ref.sampling.get_sampling_fn(cfg, ns, nodes_dist, batch, n_samples, inv)
+
+
+def run_sampling(ref, cfg, model, batch, n_samples, seed=0):
+    """processed_mols of reference sampling_fn(model) with every random draw pinned (n_nodes, noise, final shuffle)."""
+    fn = sampling_fn_for(ref, cfg, batch, n_samples)
+    torch.manual_seed(seed)
+    random.seed(seed)
+    with replayed_randn(seed + 1):
+        mols = fn(model)
+    return mols
+
+
+def synth_weights(model_module, seed=0, perturb=True):
+    spec = [(k, tuple(v.shape)) for k, v in model_module.state_dict().items()]
+    return synth_state_dict(spec, seed=seed, perturb=perturb)
