@@ -184,6 +184,10 @@ def reference_step_rate(cfg, wl, n_steps, threads):
     model = ref.model_utils.create_model(rcfg)                # registry + DataParallel wrap (models/utils.py:24-28)
     sd = synth_state_dict(param_spec(cfg), seed=int(cfg.seed))
     model.load_state_dict({'module.' + k: v for k, v in sd.items()}, strict=True)
+    if torch.cuda.is_available():
+        # On a CPU-only host DataParallel calls the module directly; on a GPU box it would scatter the CPU inputs to
+        # cuda:0 while the parameters stay on the CPU.  The CPU arm calls the (unmodified) module itself.
+        model = model.module
     model.eval()
     ns = ref.noise_schedule.NoiseScheduleVP(rcfg.sde.schedule, continuous_beta_0=rcfg.sde.continuous_beta_0,
                                             continuous_beta_1=rcfg.sde.continuous_beta_1)

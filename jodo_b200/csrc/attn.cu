@@ -395,12 +395,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(const __grid_constant__ 
 }  // namespace
 
 cudaError_t launch_attn(const AttnArgs& a, int num_sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static DevAttr attr = {};
+  cudaError_t e0 = ensure_dyn_smem(k_attn, AT_SMEM, attr);
+  if (e0 != cudaSuccess) return e0;
+  if ((e0 = const_tables_acquire(st)) != cudaSuccess) return e0;
   if (a.nonuni) {     // row 0 of the table feeds the uniform fast path: edge (shift, scale)_msa and the GBF pair
     cudaError_t e = cudaMemcpyToSymbolAsync(c_atmod, a.tab + a.tab_off + tab_edge(D_), sizeof(float) * 128, 0,
                                             cudaMemcpyDeviceToDevice, st);
@@ -411,7 +409,8 @@ cudaError_t launch_attn(const AttnArgs& a, int num_sms, cudaStream_t st) {
   }
   const int grid = a.p.n_tiles < 2 * num_sms ? (a.p.n_tiles + 1) / 2 : num_sms;
   k_attn<<<grid, AT_THREADS, AT_SMEM, st>>>(a);
-  return cudaGetLastError();
+  if ((e0 = cudaGetLastError()) != cudaSuccess) return e0;
+  return const_tables_release(st);
 }
 
 }  // namespace jodo

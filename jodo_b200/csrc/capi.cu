@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 namespace {
 thread_local char g_err[512] = "";
@@ -16,6 +17,45 @@ int cuda_fail(cudaError_t e, const char* where) {
   return JODO_ERR_CUDA;
 }
 }  // namespace
+
+// ---- constant-table stream guard (kernels.h) ---------------------------------------------------------
+namespace jodo {
+namespace {
+struct ConstGuard { cudaStream_t last; cudaEvent_t ev; bool have; };
+ConstGuard g_guard[MAX_DEVICES] = {};
+std::mutex g_guard_mu;
+bool capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
+}  // namespace
+cudaError_t const_tables_acquire(cudaStream_t st) {
+  if (capturing(st)) return cudaSuccess;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return cudaSuccess;
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  ConstGuard& g = g_guard[dev];
+  if (g.have && g.last != st) return cudaStreamWaitEvent(st, g.ev, 0);
+  return cudaSuccess;
+}
+cudaError_t const_tables_release(cudaStream_t st) {
+  if (capturing(st)) return cudaSuccess;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return cudaSuccess;
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  ConstGuard& g = g_guard[dev];
+  if (!g.ev) {
+    cudaError_t e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(g.ev, st);
+  if (e != cudaSuccess) return e;
+  g.last = st;
+  g.have = true;
+  return cudaSuccess;
+}
+}  // namespace jodo
 
 extern "C" {
 
@@ -38,15 +78,17 @@ int jodo_rowlinear(const float* A, int lda, int M, int K, const void* Wimg, cons
     return e__ == cudaSuccess ? JODO_OK : cuda_fail(e__, name);  \
   } while (0)
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+static int num_sms() {                      // of the CURRENT device (cached per device)
+  static int n[jodo::MAX_DEVICES] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= jodo::MAX_DEVICES) dev = 0;
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 

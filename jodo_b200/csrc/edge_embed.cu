@@ -159,12 +159,9 @@ cudaError_t launch_dist_flag(const EdgeEmbedArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_edge_embed(const EdgeEmbedArgs& a, int num_sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_edge_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, EE_SMEM);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static DevAttr attr = {};
+  cudaError_t e0 = ensure_dyn_smem(k_edge_embed, EE_SMEM, attr);
+  if (e0 != cudaSuccess) return e0;
   const int grid = a.p.n_tiles < 2 * num_sms ? a.p.n_tiles : 2 * num_sms;
   k_edge_embed<<<grid, ET, EE_SMEM, st>>>(a);
   return cudaGetLastError();

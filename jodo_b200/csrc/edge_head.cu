@@ -132,12 +132,9 @@ __global__ void __launch_bounds__(EH_THREADS, 1) k_edge_head(EdgeHeadArgs a) {
 
 cudaError_t launch_edge_head(const EdgeHeadArgs& a, int num_sms, cudaStream_t st) {
   if (a.keh != EH_KEH || a.ch < 1 || a.ch > 8) return cudaErrorInvalidValue;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_edge_head, cudaFuncAttributeMaxDynamicSharedMemorySize, EH_SMEM);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static DevAttr attr = {};
+  cudaError_t e0 = ensure_dyn_smem(k_edge_head, EH_SMEM, attr);
+  if (e0 != cudaSuccess) return e0;
   const int grid = a.p.n_tiles < 2 * num_sms ? (a.p.n_tiles + 1) / 2 : num_sms;
   k_edge_head<<<grid, EH_THREADS, EH_SMEM, st>>>(a);
   return cudaGetLastError();

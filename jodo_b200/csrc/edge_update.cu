@@ -269,14 +269,11 @@ __global__ void __launch_bounds__(EU_THREADS, 1) k_edge_update(const __grid_cons
 
 cudaError_t launch_edge_update(const EdgeUpdateArgs& a, int num_sms, cudaStream_t st) {
   if ((a.r != 2 && a.r != 4) || a.ce < 1 || a.ce > 16) return cudaErrorInvalidValue;
-  static int attr_bytes[5] = {0, 0, 0, 0, 0};
+  static DevAttr attr2 = {}, attr4 = {};
   const int bytes = eu_smem(a.r);
-  if (attr_bytes[a.r] < bytes) {
-    cudaError_t e = a.r == 2 ? cudaFuncSetAttribute(k_edge_update<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
-                             : cudaFuncSetAttribute(k_edge_update<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    attr_bytes[a.r] = bytes;
-  }
+  cudaError_t e0 = a.r == 2 ? ensure_dyn_smem(k_edge_update<2>, bytes, attr2) : ensure_dyn_smem(k_edge_update<4>, bytes, attr4);
+  if (e0 != cudaSuccess) return e0;
+  if ((e0 = const_tables_acquire(st)) != cudaSuccess) return e0;
   if (a.nonuni) {     // row 0 of the edge AdaLN table feeds the uniform fast path
     cudaError_t e = cudaMemcpyToSymbolAsync(c_eumod, a.tab + a.tab_off + tab_edge(D_), sizeof(float) * 384, 0,
                                             cudaMemcpyDeviceToDevice, st);
@@ -285,7 +282,8 @@ cudaError_t launch_edge_update(const EdgeUpdateArgs& a, int num_sms, cudaStream_
   const int grid = a.p.n_tiles < 2 * num_sms ? (a.p.n_tiles + 1) / 2 : num_sms;
   if (a.r == 2) k_edge_update<2><<<grid, EU_THREADS, bytes, st>>>(a);
   else k_edge_update<4><<<grid, EU_THREADS, bytes, st>>>(a);
-  return cudaGetLastError();
+  if ((e0 = cudaGetLastError()) != cudaSuccess) return e0;
+  return const_tables_release(st);
 }
 
 }  // namespace jodo

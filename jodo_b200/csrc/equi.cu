@@ -410,12 +410,10 @@ extern "C" int jodo_debug_equi_phases(long long* out16, int reset) {
 #endif
 
 cudaError_t launch_equi(const EquiArgs& a, int num_sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_equi, cudaFuncAttributeMaxDynamicSharedMemorySize, EQ_SMEM);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static DevAttr attr = {};
+  cudaError_t e0 = ensure_dyn_smem(k_equi, EQ_SMEM, attr);
+  if (e0 != cudaSuccess) return e0;
+  if ((e0 = const_tables_acquire(st)) != cudaSuccess) return e0;
   if (a.nonuni) {     // row 0 of the table feeds the uniform fast path (harmless when the batch is not uniform)
     cudaError_t e = cudaMemcpyToSymbolAsync(c_eqmod, a.tab + a.tab_off + tab_equi(D_), sizeof(float) * 528, 0,
                                             cudaMemcpyDeviceToDevice, st);
@@ -423,7 +421,8 @@ cudaError_t launch_equi(const EquiArgs& a, int num_sms, cudaStream_t st) {
   }
   const int grid = a.p.n_tiles < num_sms ? a.p.n_tiles : num_sms;
   k_equi<<<grid, EQ_THREADS, EQ_SMEM, st>>>(a);
-  return cudaGetLastError();
+  if ((e0 = cudaGetLastError()) != cudaSuccess) return e0;
+  return const_tables_release(st);
 }
 
 }  // namespace jodo

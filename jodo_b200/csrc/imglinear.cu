@@ -255,12 +255,9 @@ const char* check_imglinear(const ImgLinearArgs& a) {
 namespace {
 template <int MODE, int ACT = ACT_SILU>
 cudaError_t launch_mode(const ImgLinearArgs& a, int grid, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_imglinear<MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, IL_SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static DevAttr attr = {};
+  cudaError_t e0 = ensure_dyn_smem(k_imglinear<MODE, ACT>, IL_SMEM, attr);
+  if (e0 != cudaSuccess) return e0;
   k_imglinear<MODE, ACT><<<grid, IL_THREADS, IL_SMEM, stream>>>(a);
   return cudaGetLastError();
 }

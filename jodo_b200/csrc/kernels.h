@@ -6,6 +6,32 @@
 
 namespace jodo {
 
+// ---- per-device launch state -------------------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: every launcher remembers, per
+// device, the opt-in it has already made (a process may drive several devices, e.g. under torch.nn.DataParallel or
+// when a test moves a model from cuda:0 to cuda:1).
+constexpr int MAX_DEVICES = 64;
+struct DevAttr { int bytes[MAX_DEVICES]; };
+template <typename F>
+inline cudaError_t ensure_dyn_smem(F kernel, int bytes, DevAttr& cache) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < MAX_DEVICES && cache.bytes[dev] >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < MAX_DEVICES) cache.bytes[dev] = bytes;
+  return e;
+}
+// The uniform-conditioning rows of the edge kernels live in __constant__ tables (one copy per device, shared by all
+// streams) that are refreshed by a device-to-device copy in front of each launch.  const_tables_acquire makes `st` wait
+// for the last launch that read the tables when that was enqueued on ANOTHER stream; const_tables_release records the
+// launch just made.  Two streams driving jodo_b200 models concurrently are therefore serialised at these launches
+// instead of reading each other's rows.  Inside a stream capture neither call adds anything (cross-stream event
+// dependencies would break capture isolation): a captured graph must not be replayed concurrently with other
+// jodo_b200 work on the same device.
+cudaError_t const_tables_acquire(cudaStream_t st);
+cudaError_t const_tables_release(cudaStream_t st);
+
 enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_TANH = 3 };
 enum { EPI_STORE = 0, EPI_ACT = 1, EPI_ADD = 2, EPI_GATED_RES = 3 };
 

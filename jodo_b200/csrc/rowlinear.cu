@@ -202,12 +202,9 @@ const char* check_rowlinear(const RowLinearArgs& a) {
 }
 
 cudaError_t launch_rowlinear(const RowLinearArgs& a, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_rowlinear, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static DevAttr attr = {};
+  cudaError_t e0 = ensure_dyn_smem(k_rowlinear, RL_SMEM, attr);
+  if (e0 != cudaSuccess) return e0;
   dim3 grid((a.M + TILE_ROWS - 1) / TILE_ROWS, a.N / a.NT);
   k_rowlinear<<<grid, RL_THREADS, RL_SMEM, stream>>>(a);
   return cudaGetLastError();

@@ -93,6 +93,7 @@ class _Workspace:
 
 
 class _DGTBase(nn.Module):
+    MAX_PLANS = 4       # cached (plan, workspace) entries, least recently used evicted first
     VARIANT = None      # set by the subclasses: the variant is the class's, whatever name the registry knows it under
 
     def __init__(self, config):
@@ -174,9 +175,19 @@ class _DGTBase(nn.Module):
             self._fp_pending.record()
         return self._packed[use_wide]
 
+    def graph_token(self, node_mask, edge_mask):
+        """What a CUDA graph captured over this model's launches depends on: the (plan, workspace, masks) cache entry and
+        the packed weight images.  The holder keeps the returned objects alive (raw pointers into them are baked into
+        the graph) and compares `graph_token(...)` identity-wise before each replay (sampler.GraphedAncestralStep)."""
+        hit = self._plan(node_mask, edge_mask)
+        return hit, self._weights(hit[5])
+
     def _plan(self, node_mask, edge_mask):
-        key = (node_mask.data_ptr(), tuple(node_mask.shape), node_mask._version, edge_mask.data_ptr(), self.force_wide)
+        key = (node_mask.data_ptr(), tuple(node_mask.shape), node_mask._version, edge_mask.data_ptr(),
+               tuple(edge_mask.shape), edge_mask._version, self.force_wide)
         hit = self._plans.get(key)
+        if hit is not None:
+            self._plans[key] = self._plans.pop(key)          # most recently used last
         if hit is None:
             plan = Plan(node_mask)
             B, N = plan.B, plan.N
@@ -191,8 +202,8 @@ class _DGTBase(nn.Module):
                 if why:
                     raise NotImplementedError('jodo_b200 wide path (molecules with more than 129 atoms): ' + why)
             ws = (wide.WideWorkspace if use_wide else _Workspace)(plan, self.dims, self._weights(use_wide).meta, node_mask.device)
-            if len(self._plans) > 4:
-                self._plans.clear()
+            while len(self._plans) >= self.MAX_PLANS:        # each entry pins a workspace (GBs at B = 2500): evict the
+                self._plans.pop(next(iter(self._plans)))     # least recently used one, never the whole cache
             # the masks are kept alive with the entry so that the allocator cannot hand their addresses to new masks
             hit = self._plans[key] = (plan, ws, _lib.plan_struct(plan), node_mask, edge_mask, use_wide)
         return hit

@@ -218,6 +218,7 @@ class GraphedAncestralStep:
         self.cond_x, self.cond_edge_x = c32(cond_x).clone(), c32(cond_edge_x).clone()
         vec_t = torch.zeros(bs, device=dev)                               # ignored by the model (reference mol_gnn.py:534)
         ctx = None if context is None else c32(context).clone()
+        self._static = (vec_t, ctx)     # read by the captured kernels on every replay: must outlive this constructor
 
         def one_step():
             nl = self.coef[3:4].expand(bs)
@@ -237,8 +238,17 @@ class GraphedAncestralStep:
                 self.x_mean, self.edge_mean = one_step()
         torch.cuda.current_stream().wait_stream(side)
         self.launches_per_step = _lib.LAUNCHES - l0      # kernels of ours inside one replay
+        # the graph holds raw pointers into the model's per-mask workspace and packed weight images: keep both alive and
+        # refuse to replay once the model has dropped either (plan-cache eviction, weight reload / EMA swap)
+        self._model, self._masks = model, (node_mask, edge_mask)
+        self._token = model.graph_token(node_mask, edge_mask) if hasattr(model, 'graph_token') else None
 
     def run(self, i):
+        if self._token is not None:
+            hit, packed = self._model.graph_token(*self._masks)
+            if hit is not self._token[0] or packed is not self._token[1]:
+                raise RuntimeError('GraphedAncestralStep: the model re-packed its weights or evicted the workspace this '
+                                   'graph was captured on; capture a new step')
         self.coef.copy_(self.table[i])
         self.graph.replay()
 

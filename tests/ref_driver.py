@@ -62,6 +62,17 @@ def make_config(ref_cfg_file, device, model_name=None, steps=None, batch=None, *
     return cfg
 
 
+class _Direct(torch.nn.Module):
+    """What torch.nn.DataParallel is on a host without GPUs: `.module` + a direct call."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)
+
+
 def build_model(ref, cfg, weights, via_ema=True, single_device=True):
     """create_model (reference models/utils.py:24-28) + restore_checkpoint's strict load (utils.py:15-19) +
     ema.copy_to (run_lib.py:222).  `weights`: state dict without the DataParallel prefix; with via_ema the model is
@@ -70,6 +81,10 @@ def build_model(ref, cfg, weights, via_ema=True, single_device=True):
     assert isinstance(model, torch.nn.DataParallel)
     if single_device and torch.cuda.device_count() > 1 and cfg.device.type == 'cuda':
         model = torch.nn.DataParallel(model.module, device_ids=[cfg.device.index or 0])
+    if cfg.device.type == 'cpu' and torch.cuda.is_available():
+        # a CPU model on a GPU box: DataParallel would scatter the CPU inputs to cuda:0 (on a CPU-only host it calls the
+        # module directly); keep the `module.` prefix of the state dict with a pass-through wrapper
+        model = _Direct(model.module)
     names = [k for k, _ in model.module.named_parameters()]
     if via_ema:
         other = {k: v + 0.25 for k, v in weights.items()}
