@@ -185,9 +185,9 @@ def reference_step_rate(cfg, wl, n_steps, threads):
     sd = synth_state_dict(param_spec(cfg), seed=int(cfg.seed))
     model.load_state_dict({'module.' + k: v for k, v in sd.items()}, strict=True)
     if torch.cuda.is_available():
-        # On a CPU-only host DataParallel calls the module directly; on a GPU box it would scatter the CPU inputs to
-        # cuda:0 while the parameters stay on the CPU.  The CPU arm calls the (unmodified) module itself.
-        model = model.module
+        # On a CPU-only host DataParallel calls the module directly; on a GPU box its constructor moves the module to
+        # cuda:0 and scatters the inputs there.  The CPU arm calls the (unmodified) module itself, back on the CPU.
+        model = model.module.to('cpu')
     model.eval()
     ns = ref.noise_schedule.NoiseScheduleVP(rcfg.sde.schedule, continuous_beta_0=rcfg.sde.continuous_beta_0,
                                             continuous_beta_1=rcfg.sde.continuous_beta_1)

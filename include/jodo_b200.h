@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 7
+#define JODO_ABI_VERSION 8
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -94,9 +94,16 @@ typedef struct jodo_plan {
   const uint32_t* row_meta;              /* group start row (8b) | group length (8b) << 8 | group index in tile (8b) << 16 */
   const int* tile_ngroups;               /* [n_tiles] */
   const int* row_mol;                    /* [n_tiles*128] molecule of the row's group atom (0 on padding rows) */
+  const int* row_pair;                   /* [n_tiles*128] row of the unordered pair {g, j} in the PAIR plan (-1 = padding), or
+                                            null.  The edge state is symmetric in (g, j) (the reference's edge ops are pointwise
+                                            on symmetric inputs, models/mol_gnn.py:284-317), so it is stored once per pair:
+                                            jodo_edge_embed / jodo_edge_update / jodo_edge_head run on a second jodo_plan whose
+                                            rows are the pairs i < j of every molecule (row_g = i, row_j = j, no groups,
+                                            row_pair = null), and jodo_attn / jodo_equi, which work per directed edge, gather
+                                            their fp16 operand rows and adjacency bits through row_pair. */
 } jodo_plan;
 
-/* Edge state between kernels (per tile of 128 rows):
+/* Edge state between kernels (per tile of 128 PAIR rows):
  *   e32  fp32 master copy, piece-major [16 pieces of 4 columns][128 rows][16 B] (32 KB per tile) -- the residual
  *        stream, written by jodo_edge_embed, read and rewritten in place by jodo_edge_update (row-per-thread, coalesced);
  *   e16  fp16 operand copy, image [128 rows][64 cols] (16 KB per tile) -- what the tensor-core kernels load;
@@ -115,6 +122,8 @@ typedef struct jodo_edge_embed_args {                    /* model-level edge emb
   void* eh; size_t eh_tile_bytes;         /* out: chunk 0 of the edge-hidden image */
   uint8_t* extra;                         /* out: [R] bit0 = 2-D adjacency head, bit1 = spatial adjacency head */
   const int* nonuni;                      /* device flag of jodo_uniform_flag or null: 0 = read table row 0 */
+  int* mol_bad;                           /* [B] or null: a non-finite edge_x / cond_edge_x / cond position entry is replaced by
+                                             0 and marks its molecule (see jodo_gather_nodes) */
 } jodo_edge_embed_args;
 
 typedef struct jodo_attn_args {                         /* TransMixLayer on edge tiles (reference models/layers.py:131-186) */
@@ -176,15 +185,22 @@ typedef struct jodo_edge_head_args {                     /* edge_exist_mlp | edg
   const void* w2_img; const float* b2;    /* block-diag [exist.2 ; type.2] fp16 image (N=64, K=128) */
   const float* w4; const float* b4;       /* [ch, 32] rows: exist.4, type.4...; bias [ch] */
   int ch;
-  float* out_dense;                       /* [B,N,N,ch], zero-filled by the caller */
+  float* out_dense;                       /* [B,N,N,ch], zero-filled by the caller; a pair row writes [b,i,j,:] and [b,j,i,:]
+                                             (the reference's 0.5 (e + e^T), models/mol_gnn.py:579, of two identical values) */
+  const int* mol_bad;                     /* [B] or null: molecules marked by jodo_gather_nodes / jodo_edge_embed get NaN */
 } jodo_edge_head_args;
 
 
 /* per-atom / per-molecule elementwise kernels */
 int jodo_time_features(const float* noise_level, const float* w8, float* feat64, int B, void* stream);  /* [B, 64] */
 int jodo_cond_in(const float* ctx, const float* w0, const float* b0, float* out, int rows, int D, void* stream);
+/* mol_bad ([B] ints, may be null): NaN isolation.  The reference lets a non-finite input poison its own molecule and
+ * then zeroes ALL positions of the batch (models/mol_gnn.py:587-589).  The edge-tile kernels reduce over the rows of
+ * a tile with a tensor-core product, where 0 x NaN would leak into other molecules that share the tile, so non-finite
+ * inputs are replaced by 0 at the two input kernels, their molecule is marked here, and jodo_node_out / jodo_edge_head
+ * write NaN for marked molecules and treat any mark as the batch-global NaN condition. */
 int jodo_gather_nodes(const float* xh, const float* cond_x, const jodo_plan* p, int inn, int kin, float* xin, float* pos4,
-                      void* stream);
+                      int* mol_bad, void* stream);
 int jodo_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
                 int off_shift, int off_scale, const jodo_plan* p, float* out, int ldo, void* stream);
 /* jodo_ln_mod with fp16 operand-image outputs (D = 256): out_img = image of LN(x + gate*y)*(1+scale)+shift,
@@ -200,8 +216,8 @@ int jodo_act_image(const float* rows, int ld, int M, int K, int act, void* img, 
  * over the batch (sampling.py:549), in which case every per-molecule AdaLN row is the same row. */
 int jodo_uniform_flag(const float* rows, int B, int T, int* nonuni, void* stream);
 int jodo_com(float* pos4, const jodo_plan* p, void* stream);
-int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, int inn,
-                  float* out_dense, void* stream);
+int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, const int* mol_bad,
+                  int inn, float* out_dense, void* stream);
 int jodo_sym_edges(const float* tmp, float* out, int B, int N, int ch, void* stream);
 
 /* Fused posterior-mean update + noise of one ancestral reverse step (reference sampling.py:569-589 with the noise

@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 7:
+        if _lib.jodo_abi_version() != 8:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -94,14 +94,15 @@ _Z = ctypes.c_size_t
 
 class PlanStruct(ctypes.Structure):
     _fields_ = [('B', _I), ('Nn', _I), ('n_tiles', _I), ('N', _I), ('node_mol', _P), ('node_dense', _P),
-                ('mol_start', _P), ('row_g', _P), ('row_j', _P), ('row_meta', _P), ('tile_ngroups', _P), ('row_mol', _P)]
+                ('mol_start', _P), ('row_g', _P), ('row_j', _P), ('row_meta', _P), ('tile_ngroups', _P), ('row_mol', _P),
+                ('row_pair', _P)]
 
 
 class EdgeEmbedArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('edge_x', _P), ('cond_edge_x', _P), ('cond_x', _P), ('ch', _I), ('inn', _I),
                 ('edge_th', _F), ('spatial_cut', _F), ('dist_flag', _P), ('tab', _P), ('ld_tab', _I), ('gbf', _P),
                 ('w_img', _P), ('bias', _P), ('e32', _P), ('e16', _P), ('eh', _P), ('eh_tile_bytes', _Z), ('extra', _P),
-                ('nonuni', _P)]
+                ('nonuni', _P), ('mol_bad', _P)]
 
 
 class AttnArgs(ctypes.Structure):
@@ -126,7 +127,7 @@ class EquiArgs(ctypes.Structure):
 
 class EdgeHeadArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('eh', _P), ('eh_tile_bytes', _Z), ('keh', _I), ('w0_img', _P), ('b0', _P),
-                ('w2_img', _P), ('b2', _P), ('w4', _P), ('b4', _P), ('ch', _I), ('out_dense', _P)]
+                ('w2_img', _P), ('b2', _P), ('w4', _P), ('b4', _P), ('ch', _I), ('out_dense', _P), ('mol_bad', _P)]
 
 
 class ImgLinearArgs(ctypes.Structure):
@@ -175,9 +176,18 @@ def dp(t):
 
 
 def plan_struct(plan):
+    """The directed-edge plan (groups inside tiles), with the map onto the pair rows."""
     return PlanStruct(plan.B, plan.Nn, plan.n_tiles, plan.N, dp(plan.node_mol), dp(plan.node_dense),
                       dp(plan.mol_start), dp(plan.row_g), dp(plan.row_j), dp(plan.row_meta), dp(plan.tile_ngroups),
-                      dp(plan.row_mol))
+                      dp(plan.row_mol), dp(plan.row_pair))
+
+
+def pair_plan_struct(plan):
+    """The pair plan: rows = unordered pairs i < j (row_g = i, row_j = j), no groups, no pair map.  What the kernels
+    that own the symmetric edge state run on (jodo_edge_embed, jodo_edge_update, jodo_edge_head)."""
+    return PlanStruct(plan.B, plan.Nn, plan.n_pair_tiles, plan.N, dp(plan.node_mol), dp(plan.node_dense),
+                      dp(plan.mol_start), dp(plan.pair_i), dp(plan.pair_j), dp(plan.pair_meta), dp(plan.pair_ngroups),
+                      dp(plan.pair_mol), 0)
 
 
 def call(name, *args, tag=None):

@@ -5,7 +5,9 @@
 // logits with 1/sqrt(out_channels), two adjacency heads first, PyG softmax over the sources of a target,
 // lin_edge1/tanh gated values, sum onto the target).
 //
-// A tile holds complete groups: group atom g = attention TARGET c, partner j = SOURCE r.
+// A tile holds complete groups: group atom g = attention TARGET c, partner j = SOURCE r.  The block-input edge features
+// and the adjacency bits are stored once per unordered pair (they are symmetric); every directed row fetches its pair's
+// row through the plan's row_pair map.
 // Per tile:  A0 = [GBF(d) | e]  --MMA1--> e1 --LN/modulate--> en  --MMA2--> g0 --(logits)--  --MMA3--> g1 --(messages)
 //   (fp16 operand images, fp32 accumulation; e1, g0 and g1 reuse the same 256 TMEM columns one after the other, the
 //   g1 MMA runs under the softmax)
@@ -85,17 +87,15 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
   const uint32_t tm = c.tm;
   uint32_t ind_prev = 0xFFFFFFFFu;                  // byte offset of this row's 1.0 in the indicator image
   const float4* pos = reinterpret_cast<const float4*>(a.pos);
-  uint32_t par_m = 0, par_e = 0;
+  uint32_t par_m = 0;
 
-  if (lt == 0 && c.tile0 < c.tile1) {
-    mbar_expect_tx(c.bar_e, CHUNK_BYTES_A);
-    bulk_g2s(A0 + CHUNK_BYTES_A, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)c.tile0 * CHUNK_BYTES_A, CHUNK_BYTES_A, c.bar_e);
-  }
+  // the e chunk of a tile = its rows' pair rows, gathered from the pair-row store one tile ahead (edge_common.cuh)
+  if (c.tile0 < c.tile1) gather_e16_rows(A0 + CHUNK_BYTES_A, a.e16, a.p.row_pair + (size_t)c.tile0 * TILE_ROWS, lt, AT_GROUP);
   // row metadata of a tile is fetched one tile ahead
   const int tfirst = min(c.tile0, a.p.n_tiles - 1);
   RowInfo rn = load_row(a.p, tfirst, row);
   int ngn = a.p.tile_ngroups[tfirst];
-  uint8_t exn = a.extra[(size_t)tfirst * TILE_ROWS + row];
+  uint8_t exn = a.extra[rn.pr];
   for (int tile = c.tile0; tile < c.tile1; tile += 2) {
     const RowInfo r = rn;
     const int ng = ngn;
@@ -125,18 +125,17 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
       const int nt_ = tile + 2 < c.tile1 ? tile + 2 : tile;
       rn = load_row(a.p, nt_, row);
       ngn = a.p.tile_ngroups[nt_];
-      exn = a.extra[(size_t)nt_ * TILE_ROWS + row];
+      exn = a.extra[rn.pr];
     }
+    cp_async_wait_all();                                 // this thread's share of the gathered e chunk has landed
     fence_async_smem();
     at_group_sync(c.grp);
     if (lt == 0) {
       if (tile == c.tile0) mbar_wait(c.bar_w, 0);
-      mbar_wait(c.bar_e, par_e);
       tc_fence_after();
       mma_tile_h(tm, smem_u32(A0), smem_u32(c.WE), 64, 2, false);                   // e1 = edge_emb([dist | e])
       umma_commit(c.bar_m);
     }
-    par_e ^= 1;
     mbar_wait(c.bar_m, par_m);
     par_m ^= 1;
     tc_fence_after();
@@ -150,10 +149,8 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
         ind_prev = 0xFFFFFFFFu;
       }
     }
-    if (lt == 0 && tile + 2 < c.tile1) {               // the e chunk is consumed: prefetch this group's next tile
-      mbar_expect_tx(c.bar_e, CHUNK_BYTES_A);
-      bulk_g2s(A0 + CHUNK_BYTES_A, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 2) * CHUNK_BYTES_A, CHUNK_BYTES_A, c.bar_e);
-    }
+    if (tile + 2 < c.tile1)                             // the e chunk is consumed: gather this group's next tile
+      gather_e16_rows(A0 + CHUNK_BYTES_A, a.e16, a.p.row_pair + (size_t)(tile + 2) * TILE_ROWS, lt, AT_GROUP);
 
     // ---- en = LN(e1) * (1 + scale_msa) + shift_msa  -> A0 chunk 0
     {

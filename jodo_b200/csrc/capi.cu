@@ -101,9 +101,9 @@ int jodo_cond_in(const float* ctx, const float* w0, const float* b0, float* out,
   JODO_LAUNCH(jodo::launch_cond_in(ctx, w0, b0, out, rows, D, S(stream)), "jodo_cond_in");
 }
 int jodo_gather_nodes(const float* xh, const float* cond_x, const jodo_plan* p, int inn, int kin, float* xin, float* pos4,
-                      void* stream) {
+                      int* mol_bad, void* stream) {
   if (!p || p->Nn <= 0 || kin < 2 * inn) return fail("jodo_gather_nodes: bad sizes");
-  JODO_LAUNCH(jodo::launch_gather_nodes(xh, cond_x, *p, inn, kin, xin, pos4, S(stream)), "jodo_gather_nodes");
+  JODO_LAUNCH(jodo::launch_gather_nodes(xh, cond_x, *p, inn, kin, xin, pos4, mol_bad, S(stream)), "jodo_gather_nodes");
 }
 int jodo_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab, int off_gate,
                 int off_shift, int off_scale, const jodo_plan* p, float* out, int ldo, void* stream) {
@@ -135,13 +135,13 @@ int jodo_uniform_flag(const float* rows, int B, int T, int* nonuni, void* stream
   JODO_LAUNCH(jodo::launch_uniform_flag(rows, B, T, nonuni, S(stream)), "jodo_uniform_flag");
 }
 int jodo_com(float* pos4, const jodo_plan* p, void* stream) { JODO_LAUNCH(jodo::launch_com(pos4, *p, S(stream)), "jodo_com"); }
-int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, int inn,
-                  float* out_dense, void* stream) {
+int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, const int* mol_bad,
+                  int inn, float* out_dense, void* stream) {
   cudaError_t e = cudaMemsetAsync(nan_flag, 0, sizeof(int), S(stream));
   if (e != cudaSuccess) return cuda_fail(e, "jodo_node_out");
-  e = jodo::launch_nan_flag(pos4, p->Nn, nan_flag, S(stream));
+  e = jodo::launch_nan_flag(pos4, p->Nn, mol_bad, p->B, nan_flag, S(stream));
   if (e != cudaSuccess) return cuda_fail(e, "jodo_node_out");
-  JODO_LAUNCH(jodo::launch_node_out(pos4, atom_pred, ldp, *p, nan_flag, inn, out_dense, S(stream)), "jodo_node_out");
+  JODO_LAUNCH(jodo::launch_node_out(pos4, atom_pred, ldp, *p, nan_flag, mol_bad, inn, out_dense, S(stream)), "jodo_node_out");
 }
 int jodo_sym_edges(const float* tmp, float* out, int B, int N, int ch, void* stream) {
   JODO_LAUNCH(jodo::launch_sym_edges(tmp, out, B, N, ch, S(stream)), "jodo_sym_edges");
@@ -181,6 +181,7 @@ int jodo_attn(const jodo_attn_args* a, void* stream) {
   if (const char* m = check_plan(a->p)) return fail(m);
   if (a->ldq < a->p.Nn || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_attn: bad strides");
   if (!a->e16 || !a->hnode) return fail("jodo_attn: null buffer");
+  if (!a->p.row_pair) return fail("jodo_attn: the plan needs row_pair (the edge state is stored per unordered pair)");
   JODO_LAUNCH(jodo::launch_attn(*a, num_sms(), S(stream)), "jodo_attn");
 }
 int jodo_edge_update(const jodo_edge_update_args* a, void* stream) {
@@ -196,6 +197,7 @@ int jodo_equi(const jodo_equi_args* a, void* stream) {
   if (!a) return fail("jodo_equi: null args");
   if (const char* m = check_plan(a->p)) return fail(m);
   if (a->ldab < a->p.Nn || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_equi: bad strides");
+  if (!a->p.row_pair) return fail("jodo_equi: the plan needs row_pair (the edge state is stored per unordered pair)");
   JODO_LAUNCH(jodo::launch_equi(*a, num_sms(), S(stream)), "jodo_equi");
 }
 int jodo_edge_head(const jodo_edge_head_args* a, void* stream) {

@@ -2,7 +2,8 @@
 //
 // reference models/mol_gnn.py:517-557: self-conditioning features, cond_adj_2d / cond_adj_spatial,
 // dist0 = zeros if every cond distance is 0 else GBF(d0), e0 = edge_emb(cat[edge_x, cond_edge_x, dist0]).
-// Row (g, j) of a tile is the directed edge r=j -> c=g; inputs are gathered from the dense padded batch.
+// Rows are the unordered pairs (g, j), g < j, of the pair plan (the inputs are symmetric: edge_x[b, j, g] is read); inputs
+// are gathered from the dense padded batch.
 #include "edge_common.cuh"
 
 namespace jodo {
@@ -62,11 +63,13 @@ __global__ void __launch_bounds__(ET, 1) k_edge_embed(EdgeEmbedArgs a) {
     const int b = dg / N, ig = dg - b * N, ij = dj - b * N;
     const size_t eoff = (((size_t)b * N + ij) * N + ig) * ch;     // edge_x[b, r=j, c=g]
     float d0 = 0.f;
+    bool bad = false;                                  // a non-finite input of this row (NaN isolation, jodo_b200.h)
     if (a.cond_x && r.valid) {
       const float* cg = a.cond_x + (size_t)dg * w;
       const float* cj = a.cond_x + (size_t)dj * w;
       const float dx = cj[0] - cg[0], dy = cj[1] - cg[1], dz = cj[2] - cg[2];
       d0 = dx * dx + dy * dy + dz * dz;
+      if (!isfinite(d0)) { d0 = 0.f; bad = true; }
     }
     float v[64];
     if (use_gbf && r.valid) {
@@ -85,8 +88,11 @@ __global__ void __launch_bounds__(ET, 1) k_edge_embed(EdgeEmbedArgs a) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {          // ch <= 8
         if (i < ch) {
-          s[i] = a.edge_x[eoff + i];
-          const float cv = a.cond_edge_x ? a.cond_edge_x[eoff + i] : 0.f;
+          float xv = a.edge_x[eoff + i];
+          float cv = a.cond_edge_x ? a.cond_edge_x[eoff + i] : 0.f;
+          if (!isfinite(xv)) { xv = 0.f; bad = true; }
+          if (!isfinite(cv)) { cv = 0.f; bad = true; }
+          s[i] = xv;
           if (i == 0) c0 = cv;
           // second block of ch columns; indices are compile-time after unrolling both loops
 #pragma unroll
@@ -103,6 +109,7 @@ __global__ void __launch_bounds__(ET, 1) k_edge_embed(EdgeEmbedArgs a) {
       bits = (a2d ? 1 : 0) | (asp ? 2 : 0);
     }
     a.extra[(size_t)tile * TILE_ROWS + t] = bits;
+    if (bad && a.mol_bad) atomicOr(a.mol_bad + r.mol, 1);
 
     fence_async_smem();
     sync_tc();

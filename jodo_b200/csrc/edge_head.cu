@@ -3,7 +3,8 @@
 // reference models/mol_gnn.py:466-479 (two 3-layer MLPs with SiLU), :571-578 (cat of edge hiddens, cat of the
 // two outputs, scatter to the dense [B,N,N,ch] tensor).  Both MLPs share their input, so layer 0 is one
 // N=128 GEMM ([exist.0 ; type.0]), layer 2 one block-diagonal N=64 GEMM, layer 4 (32 -> 1 and 32 -> ch-1)
-// runs on the CUDA cores.  Row (g, j) is the directed edge r=j -> c=g and is written to out[b, i_j, i_g, :].
+// runs on the CUDA cores.  Rows are the unordered pairs (g, j) of the pair plan; each is written to out[b, i_j, i_g, :]
+// and out[b, i_g, i_j, :].
 // fp16 operand images; all weights resident; the next tile is bulk-copied while the current one is in the MLP.
 #include "edge_common.cuh"
 
@@ -116,9 +117,14 @@ __global__ void __launch_bounds__(EH_THREADS, 1) k_edge_head(EdgeHeadArgs a) {
       if (r.valid) {
         const int dg = a.p.node_dense[r.g], dj = a.p.node_dense[r.j];
         const int b = dg / N, ig = dg - b * N, ij = dj - b * N;
+        // a pair row serves both orientations: 0.5 (e[i,j] + e[j,i]) of the reference (models/mol_gnn.py:579) averages two
+        // values computed from identical (symmetric) features, i.e. is that value
         float* dst = a.out_dense + (((size_t)b * N + ij) * N + ig) * ch;
+        float* dst2 = a.out_dense + (((size_t)b * N + ig) * N + ij) * ch;
+        const bool bad = a.mol_bad != nullptr && a.mol_bad[r.mol] != 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) if (k < ch) dst[k] = o[k] + b4[k];
+        for (int k = 0; k < 8; ++k)
+          if (k < ch) { const float v = bad ? __int_as_float(0x7fc00000) : o[k] + b4[k]; dst[k] = v; dst2[k] = v; }
       }
     }
     group_sync();

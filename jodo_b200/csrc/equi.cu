@@ -169,14 +169,14 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
     for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
     if (tile0 < tile1) {
-      mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
-      bulk_g2s(U, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)tile0 * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
       mbar_expect_tx(&bars[2], 65536);
       bulk_g2s(X, a.win_img, 65536, &bars[2]);
     }
     mbar_expect_tx(&bars[0], 131072);
     bulk_g2s(smem + EQ_WC0, a.wc0_img, 131072, &bars[0]);
   }
+  // the e chunk of a tile = its rows' pair rows, gathered from the pair-row store one tile ahead (edge_common.cuh)
+  if (tile0 < tile1) gather_e16_rows(U, a.e16, a.p.row_pair + (size_t)tile0 * TILE_ROWS, t, EQ_THREADS);
   const bool uni = a.nonuni != nullptr && *a.nonuni == 0;
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   sync_tc();
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   const int tfirst = min(tile0, a.p.n_tiles - 1);
   RowInfo r = load_row(a.p, tfirst, row);
   int ng = a.p.tile_ngroups[tfirst];
-  uint8_t ex = a.extra[(size_t)tfirst * TILE_ROWS + row];
+  uint8_t ex = a.extra[r.pr];
   float4 pg = pos[r.g], pj = pos[r.j];
   uint4 dfh[2];
   RowInfo rn = r;
@@ -215,12 +215,12 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
     const int nt_ = min(tile + 1, tile1 - 1);
     rn = load_row(a.p, nt_, row);
     ngn = a.p.tile_ngroups[nt_];
-    exn = a.extra[(size_t)nt_ * TILE_ROWS + row];
+    exn = a.extra[rn.pr];
+    cp_async_wait_all();                           // this thread's share of the gathered e chunk has landed
     fence_async_smem();
     sync_tc();
     PHASE_MARK(0);
     if (t == 0) {
-      mbar_wait(&bars[1], par);
       PHASE_MARK(1);
       mbar_wait(&bars[2], par);
       PHASE_MARK(2);
@@ -285,11 +285,9 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       }
       tmem_wait_st();
       if (cq < 2) mbar_wait(&bars[5], par);      // the scratch aliases the GBF chunk: the whole input_lin MMA must be done
+      if (tile + 1 < tile1)                      // U chunk 0 is consumed: gather the next tile's e rows
+        gather_e16_rows(U, a.e16, a.p.row_pair + (size_t)(tile + 1) * TILE_ROWS, t, EQ_THREADS);
       if (t == 0) {
-        if (tile + 1 < tile1) {                  // U chunk 0 is consumed: prefetch the next e tile
-          mbar_expect_tx(&bars[1], CHUNK_BYTES_A);
-          bulk_g2s(U, reinterpret_cast<const uint8_t*>(a.e16) + (size_t)(tile + 1) * CHUNK_BYTES_A, CHUNK_BYTES_A, &bars[1]);
-        }
         mbar_expect_tx(&bars[8], 8192);          // the GBF chunk is consumed too: its tail takes the coord_mlp.2 image
         bulk_g2s(smem + EQ_W2, a.w2_img, 8192, &bars[8]);
       }

@@ -78,7 +78,7 @@ using Plan = ::jodo_plan;
 cudaError_t launch_time_features(const float* nl, const float* w, float* feat, int B, cudaStream_t st);
 cudaError_t launch_cond_in(const float* ctx, const float* w0, const float* b0, float* out, int rows, int D, cudaStream_t st);
 cudaError_t launch_gather_nodes(const float* xh, const float* cond_x, const Plan& p, int inn, int kin, float* xin,
-                                float* pos, cudaStream_t st);
+                                float* pos, int* mol_bad, cudaStream_t st);
 cudaError_t launch_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab,
                           int off_gate, int off_shift, int off_scale, const Plan& p, float* out, int ldo,
                           cudaStream_t st);
@@ -88,9 +88,9 @@ cudaError_t launch_ln_mod_img(const float* x, int ldx, const float* y, int ldy, 
 cudaError_t launch_act_image(const float* rows, int ld, int M, int K, int act, void* img, cudaStream_t st);
 cudaError_t launch_uniform_flag(const float* rows, int B, int T, int* nonuni, cudaStream_t st);
 cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st);
-cudaError_t launch_nan_flag(const float* pos, int Nn, int* flag, cudaStream_t st);
+cudaError_t launch_nan_flag(const float* pos, int Nn, const int* mol_bad, int B, int* flag, cudaStream_t st);
 cudaError_t launch_node_out(const float* pos, const float* atom_pred, int ldp, const Plan& p, const int* nan_flag,
-                            int inn, float* out, cudaStream_t st);
+                            const int* mol_bad, int inn, float* out, cudaStream_t st);
 cudaError_t launch_sym_edges(const float* tmp, float* out, int B, int N, int ch, cudaStream_t st);
 
 cudaError_t launch_ancestral_update(const float* x, const float* pred, const float* raw_pos, const float* raw_feat,

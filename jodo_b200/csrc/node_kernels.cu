@@ -43,9 +43,10 @@ __global__ void k_cond_in(const float* __restrict__ ctx, const float* __restrict
 
 // Packed node inputs from the dense padded batch: xin[v] = (h[b,i,:], cond_h[b,i,:], 0...), pos[v] = xh[b,i,0:3].
 // reference models/mol_gnn.py:509-510, 528-530.
+// mol_bad != null: non-finite inputs become 0 and mark their molecule (NaN isolation, include/jodo_b200.h).
 __global__ void k_gather_nodes(const float* __restrict__ xh, const float* __restrict__ cond_x,
-                               const int* __restrict__ node_dense, int Nn, int inn, int kin, float* __restrict__ xin,
-                               float4* __restrict__ pos) {
+                               const int* __restrict__ node_dense, const int* __restrict__ node_mol, int Nn, int inn, int kin,
+                               float* __restrict__ xin, float4* __restrict__ pos, int* __restrict__ mol_bad) {
   int v = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (v >= Nn) return;
@@ -53,13 +54,20 @@ __global__ void k_gather_nodes(const float* __restrict__ xh, const float* __rest
   const int w = 3 + inn;
   const float* x = xh + (size_t)row * w;
   const float* c = cond_x ? cond_x + (size_t)row * w : nullptr;
+  bool bad = false;
   for (int k = lane; k < kin; k += 32) {
     float val = 0.f;
     if (k < inn) val = x[3 + k];
     else if (k < 2 * inn) val = c ? c[3 + k - inn] : 0.f;
+    if (mol_bad && !isfinite(val)) { val = 0.f; bad = true; }
     xin[(size_t)v * kin + k] = val;
   }
-  if (lane == 0) pos[v] = make_float4(x[0], x[1], x[2], 0.f);
+  if (lane == 0) {
+    float4 p = make_float4(x[0], x[1], x[2], 0.f);
+    if (mol_bad && !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) { p = make_float4(0.f, 0.f, 0.f, 0.f); bad = true; }
+    pos[v] = p;
+  }
+  if (bad) atomicOr(mol_bad + node_mol[v], 1);
 }
 
 // out[v,:] = LN(x[v,:] + gate[mol]*y[v,:]) * (1 + scale[mol]) + shift[mol]      (one warp per atom)
@@ -214,8 +222,9 @@ __global__ void k_com(float4* __restrict__ pos_new, const int* __restrict__ mol_
 }
 
 // flag |= any NaN in pos   (batch-global guard, reference models/mol_gnn.py:587)
-__global__ void k_nan_flag(const float4* __restrict__ pos, int Nn, int* __restrict__ flag) {
+__global__ void k_nan_flag(const float4* __restrict__ pos, int Nn, const int* __restrict__ mol_bad, int B, int* __restrict__ flag) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mol_bad && v < B && mol_bad[v] != 0) atomicOr(flag, 1);      // a non-finite input: NaN positions in the reference
   if (v >= Nn) return;
   float4 p = pos[v];
   if (isnan(p.x) || isnan(p.y) || isnan(p.z)) atomicOr(flag, 1);
@@ -225,7 +234,8 @@ __global__ void k_nan_flag(const float4* __restrict__ pos, int Nn, int* __restri
 // logits; padded atoms stay 0 (the buffer is zero-filled by the caller).  reference models/mol_gnn.py:573,582-594.
 __global__ void k_node_out(const float4* __restrict__ pos, const float* __restrict__ atom_pred, int ldp,
                            const int* __restrict__ mol_start, const int* __restrict__ node_dense,
-                           const int* __restrict__ nan_flag, int B, int inn, float* __restrict__ out) {
+                           const int* __restrict__ nan_flag, const int* __restrict__ mol_bad, int B, int inn,
+                           float* __restrict__ out) {
   int b = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -241,7 +251,8 @@ __global__ void k_node_out(const float4* __restrict__ pos, const float* __restri
     float4 p = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : pos[v];
     float* o = out + (size_t)node_dense[v] * w;
     o[0] = p.x - sx; o[1] = p.y - sy; o[2] = p.z - sz;
-    for (int k = 0; k < inn; ++k) o[3 + k] = atom_pred[(size_t)v * ldp + k];
+    const bool bad = mol_bad != nullptr && mol_bad[b] != 0;      // the reference's logits of such a molecule are NaN
+    for (int k = 0; k < inn; ++k) o[3 + k] = bad ? __int_as_float(0x7fc00000) : atom_pred[(size_t)v * ldp + k];
   }
 }
 
@@ -272,9 +283,13 @@ cudaError_t launch_cond_in(const float* ctx, const float* w0, const float* b0, f
   return LAUNCH_OK();
 }
 cudaError_t launch_gather_nodes(const float* xh, const float* cond_x, const Plan& p, int inn, int kin, float* xin,
-                                float* pos, cudaStream_t st) {
-  k_gather_nodes<<<(p.Nn + 7) / 8, 256, 0, st>>>(xh, cond_x, p.node_dense, p.Nn, inn, kin, xin,
-                                                  reinterpret_cast<float4*>(pos));
+                                float* pos, int* mol_bad, cudaStream_t st) {
+  if (mol_bad) {
+    cudaError_t e = cudaMemsetAsync(mol_bad, 0, sizeof(int) * p.B, st);
+    if (e != cudaSuccess) return e;
+  }
+  k_gather_nodes<<<(p.Nn + 7) / 8, 256, 0, st>>>(xh, cond_x, p.node_dense, p.node_mol, p.Nn, inn, kin, xin,
+                                                  reinterpret_cast<float4*>(pos), mol_bad);
   return LAUNCH_OK();
 }
 cudaError_t launch_ln_mod(int D, const float* x, int ldx, const float* y, int ldy, const float* tab, int ld_tab,
@@ -313,14 +328,15 @@ cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st) {
   k_com<<<(p.B + 7) / 8, 256, 0, st>>>(reinterpret_cast<float4*>(pos_new), p.mol_start, p.B);
   return LAUNCH_OK();
 }
-cudaError_t launch_nan_flag(const float* pos, int Nn, int* flag, cudaStream_t st) {
-  k_nan_flag<<<(Nn + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(pos), Nn, flag);
+cudaError_t launch_nan_flag(const float* pos, int Nn, const int* mol_bad, int B, int* flag, cudaStream_t st) {
+  const int n = Nn > B ? Nn : B;
+  k_nan_flag<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(pos), Nn, mol_bad, B, flag);
   return LAUNCH_OK();
 }
 cudaError_t launch_node_out(const float* pos, const float* atom_pred, int ldp, const Plan& p, const int* nan_flag,
-                            int inn, float* out, cudaStream_t st) {
+                            const int* mol_bad, int inn, float* out, cudaStream_t st) {
   k_node_out<<<(p.B + 7) / 8, 256, 0, st>>>(reinterpret_cast<const float4*>(pos), atom_pred, ldp, p.mol_start,
-                                             p.node_dense, nan_flag, p.B, inn, out);
+                                             p.node_dense, nan_flag, mol_bad, p.B, inn, out);
   return LAUNCH_OK();
 }
 cudaError_t launch_sym_edges(const float* tmp, float* out, int B, int N, int ch, cudaStream_t st) {

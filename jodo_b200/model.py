@@ -55,7 +55,7 @@ class _Workspace:
     def __init__(self, plan: Plan, d, meta, dev):
         f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
         zf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
-        B, Nn, nt = plan.B, plan.Nn, plan.n_tiles
+        B, Nn, nt = plan.B, plan.Nn, plan.n_pair_tiles      # the edge state lives on PAIR tiles (plan.py)
         D, T = d.D, d.T
         self.feat = f(B, 64)
         self.t1 = f(B, T)
@@ -89,7 +89,8 @@ class _Workspace:
         self.e = torch.zeros(nt * 8192, device=dev, dtype=torch.float32)      # fp32 edge state, 32 KB per tile
         self.e16 = torch.zeros(nt * 8192, device=dev, dtype=torch.float16)    # fp16 operand copy, 16 KB per tile
         self.extra = torch.zeros(nt * 128, device=dev, dtype=torch.uint8)
-        self.flags = torch.zeros(4, device=dev, dtype=torch.int32)            # [0] dist flag, [1] nan flag
+        self.flags = torch.zeros(4, device=dev, dtype=torch.int32)            # [0] dist flag, [1] nan flag, [2] non-uniform
+        self.mol_bad = torch.zeros(B, device=dev, dtype=torch.int32)          # molecules with a non-finite input (NaN isolation)
 
 
 class _DGTBase(nn.Module):
@@ -205,7 +206,8 @@ class _DGTBase(nn.Module):
             while len(self._plans) >= self.MAX_PLANS:        # each entry pins a workspace (GBs at B = 2500): evict the
                 self._plans.pop(next(iter(self._plans)))     # least recently used one, never the whole cache
             # the masks are kept alive with the entry so that the allocator cannot hand their addresses to new masks
-            hit = self._plans[key] = (plan, ws, _lib.plan_struct(plan), node_mask, edge_mask, use_wide)
+            hit = self._plans[key] = (plan, ws, _lib.plan_struct(plan), node_mask, edge_mask, use_wide,
+                                      _lib.pair_plan_struct(plan))
         return hit
 
     # ---- forward ------------------------------------------------------------------------------------
@@ -230,7 +232,7 @@ class _DGTBase(nn.Module):
         if d.cond_ch and context is None:
             raise ValueError('cond_DGT_concat needs a context')
         hit = self._plan(node_mask, edge_mask)
-        plan, ws, ps, use_wide = hit[0], hit[1], hit[2], hit[5]
+        plan, ws, ps, use_wide, pps = hit[0], hit[1], hit[2], hit[5], hit[6]
         pk = self._weights(use_wide)
         meta = pk.meta
         B, N = plan.B, plan.N
@@ -280,13 +282,15 @@ class _DGTBase(nn.Module):
                            tag='jodo_imglinear:tab', skip_if_zero=nonuni)
         # ---- per atom: packed inputs, node embedding (slice 0 of the concatenated atom hiddens)
         _lib.call('jodo_gather_nodes', _lib.ptr(xh), _lib.ptr(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin),
-                  _lib.ptr(ws.xin), _lib.ptr(ws.pos[0]), st)
+                  _lib.ptr(ws.xin), _lib.ptr(ws.pos[0]), _lib.ptr(ws.mol_bad), st)
         lin('node_emb', ws.xin, ws.ah[:, :D])
         # ---- per edge: model-level embedding + adjacency heads
-        ea = _lib.EdgeEmbedArgs(ps, _lib.dp(edge_x), _lib.dp(cond_edge_x), _lib.dp(cond_x), d.ch, d.inn, self.edge_th,
+        # ---- per unordered pair (the edge state is symmetric): model-level embedding + adjacency bits
+        ea = _lib.EdgeEmbedArgs(pps, _lib.dp(edge_x), _lib.dp(cond_edge_x), _lib.dp(cond_x), d.ch, d.inn, self.edge_th,
                                 self.spatial_cut_off, _lib.dp(ws.flags), _lib.dp(ws.tab), ld_tab, pk.ptr('gbf'),
                                 pk.ptr('edge_emb.img'), pk.ptr('edge_emb.b'), _lib.dp(ws.e), _lib.dp(ws.e16),
-                                _lib.dp(ws.eh), ws.eh_tile_bytes, _lib.dp(ws.extra), ws.flags.data_ptr() + 8)
+                                _lib.dp(ws.eh), ws.eh_tile_bytes, _lib.dp(ws.extra), ws.flags.data_ptr() + 8,
+                                _lib.dp(ws.mol_bad))
         _lib.call('jodo_edge_embed', ctypes.byref(ea), st)
 
         h = ws.ah[:, :D]
@@ -316,7 +320,7 @@ class _DGTBase(nn.Module):
             ilin(p + 'ab', ws.hout_img, C16=ws.ab)
             ilin(p + 'node_l', ws.hout_img, C32=ws.ah[:, D + l * meta['cnp']:])
             # edge path
-            ua = _lib.EdgeUpdateArgs(ps, _lib.dp(ws.e), _lib.dp(ws.e16), _lib.dp(ws.pbuf), plan.Nn,
+            ua = _lib.EdgeUpdateArgs(pps, _lib.dp(ws.e), _lib.dp(ws.e16), _lib.dp(ws.pbuf), plan.Nn,
                                      _lib.dp(ws.tab), ld_tab, off, d.r, pk.ptr(p + 'ff3.img'), pk.ptr(p + 'ff4.img'),
                                      pk.ptr(p + 'edge_l.img'), _lib.dp(ws.eh), ws.eh_tile_bytes, d.ed + l * d.ce, d.ce,
                                      ws.flags.data_ptr() + 8, pk.host[p + 'n2e.bias'], pk.host[p + 'ff3.b'],
@@ -338,14 +342,13 @@ class _DGTBase(nn.Module):
         lin('npred4', ws.n2, ws.ap)
         out_x = torch.zeros(B, N, 3 + d.inn, device=xh.device, dtype=torch.float32)
         _lib.call('jodo_node_out', _lib.ptr(ws.pos[d.L & 1]), _lib.ptr(ws.ap), _c(ws.ap.stride(0)), ctypes.byref(ps),
-                  ctypes.c_void_p(ws.flags.data_ptr() + 4), _c(d.inn), _lib.ptr(out_x), st)
-        tmp = torch.zeros(B, N, N, d.ch, device=xh.device, dtype=torch.float32)
-        ha = _lib.EdgeHeadArgs(ps, _lib.dp(ws.eh), ws.eh_tile_bytes, meta['keh'], pk.ptr('ehead0.img'), pk.ptr('ehead0.b'),
+                  ctypes.c_void_p(ws.flags.data_ptr() + 4), _lib.ptr(ws.mol_bad), _c(d.inn), _lib.ptr(out_x), st)
+        # every pair row writes both orientations: the reference's 0.5 (e + e^T) (mol_gnn.py:579) of two identical values
+        out_e = torch.zeros(B, N, N, d.ch, device=xh.device, dtype=torch.float32)
+        ha = _lib.EdgeHeadArgs(pps, _lib.dp(ws.eh), ws.eh_tile_bytes, meta['keh'], pk.ptr('ehead0.img'), pk.ptr('ehead0.b'),
                                pk.ptr('ehead2.img'), pk.ptr('ehead2.b'), pk.ptr('ehead4.w'), pk.ptr('ehead4.b'), d.ch,
-                               _lib.dp(tmp))
+                               _lib.dp(out_e), _lib.dp(ws.mol_bad))
         _lib.call('jodo_edge_head', ctypes.byref(ha), st)
-        out_e = torch.empty_like(tmp)
-        _lib.call('jodo_sym_edges', _lib.ptr(tmp), _lib.ptr(out_e), _c(B), _c(N), _c(d.ch), st)
         if dbg is not None:
             dbg.update(tab=ws.tab.clone(), temb=ws.temb.clone(), ah=ws.ah.clone(), eh=ws.eh.clone(),
                        extra=ws.extra.clone(), plan=plan, flags=ws.flags.clone())

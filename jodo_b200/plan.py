@@ -143,6 +143,61 @@ class Plan:
         self.grp_len = t(gl_node.astype(np.int32))
         self.max_group = int(gl_node.max(initial=0))
         self.device = dev
+        # ---- pair rows: the edge STATE (e32 / e16 / eh / adjacency bits) is symmetric in (g, j) (SURVEY.md quirk 5), so
+        # it is stored and updated once per unordered pair {i < j}: pairs of a molecule in (i, j) lexicographic order,
+        # molecules back to back, 128 rows per tile with no grouping constraint (the kernels that own the state --
+        # edge_embed, edge_update, edge_head -- are row-local).  The directed rows above point at their pair row
+        # through row_pair; attention and the coordinate update gather the fp16 operand rows through it.
+        npair = n * (n - 1) // 2
+        pair_start = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(npair, out=pair_start[1:])
+        P = int(pair_start[-1])
+        self.n_pairs = P
+        self.n_pair_tiles = max(1, (P + TILE - 1) // TILE)
+        RP = self.n_pair_tiles * TILE
+        pair_i = np.full(RP, -1, dtype=np.int32)
+        pair_j = np.full(RP, -1, dtype=np.int32)
+        pair_mol = np.zeros(RP, dtype=np.int32)
+        if P:
+            pm = np.repeat(np.arange(B), npair)                  # molecule of every pair row
+            q = np.arange(P) - pair_start[pm]                    # pair ordinal inside the molecule
+            nn_ = n[pm].astype(np.float64)
+            # q = i n - i (i + 1) / 2 + (j - i - 1)  ->  i = floor(((2 n - 1) - sqrt((2 n - 1)^2 - 8 q)) / 2)
+            ii_ = np.floor(((2 * nn_ - 1) - np.sqrt((2 * nn_ - 1) ** 2 - 8 * q)) / 2).astype(np.int64)
+            first_of = lambda i_: i_ * n[pm] - i_ * (i_ + 1) // 2
+            ii_ = np.where(first_of(ii_) > q, ii_ - 1, ii_)      # guard the floating-point floor
+            ii_ = np.where(first_of(ii_ + 1) <= q, ii_ + 1, ii_)
+            jj_ = q - first_of(ii_) + ii_ + 1
+            assert ((ii_ >= 0) & (jj_ > ii_) & (jj_ < n[pm])).all()
+            pair_i[:P] = mol_start[pm] + ii_
+            pair_j[:P] = mol_start[pm] + jj_
+            pair_mol[:P] = pm
+        row_pair = np.full(R, -1, dtype=np.int32)
+        if tot:
+            vg, vj = row_g[row_g >= 0].astype(np.int64), row_j[row_g >= 0].astype(np.int64)
+            mb = node_mol[vg].astype(np.int64)
+            lo = np.minimum(vg, vj) - mol_start[mb]
+            hi = np.maximum(vg, vj) - mol_start[mb]
+            row_pair[row_g >= 0] = (pair_start[mb] + lo * n[mb] - lo * (lo + 1) // 2 + (hi - lo - 1)).astype(np.int32)
+        self.row_pair = t(row_pair)
+        self.pair_i, self.pair_j, self.pair_mol = t(pair_i), t(pair_j), t(pair_mol)
+        self.pair_meta = t(np.zeros(RP, dtype=np.int32))
+        self.pair_ngroups = t(np.zeros(self.n_pair_tiles, dtype=np.int32))
+
+    # ---- pair-row helpers (tests) ------------------------------------------------------------------
+    def pairs_to_dense(self, rows: torch.Tensor) -> torch.Tensor:
+        """[n_pair_tiles * 128, C] pair rows -> dense symmetric [B, N, N, C] (diagonal and padding 0)."""
+        B, N = self.B, self.N
+        C = rows.shape[-1]
+        out = torch.zeros(B * N * N, C, dtype=rows.dtype, device=rows.device)
+        valid = self.pair_i >= 0
+        i = self.node_dense[self.pair_i[valid].long()].long()
+        j = self.node_dense[self.pair_j[valid].long()].long()
+        b = i // N
+        ii, jj = i % N, j % N
+        out[b * N * N + ii * N + jj] = rows[valid]
+        out[b * N * N + jj * N + ii] = rows[valid]
+        return out.reshape(B, N, N, C)
 
     # ---- helpers used by tests (pure index bookkeeping) -------------------------------------------
     def dense_to_rows(self, dense_bnn: torch.Tensor, group_first=True) -> torch.Tensor:

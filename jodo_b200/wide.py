@@ -232,7 +232,7 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         if cond_x is not None:
             ws.xin[:, d.inn:2 * d.inn] = cond_x.reshape(B * N, d.inn)[ws.node_dense_l]
     else:
-        _lib.call('jodo_gather_nodes', P(xh), P(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin), P(ws.xin), P(ws.pos[0]), st)
+        _lib.call('jodo_gather_nodes', P(xh), P(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin), P(ws.xin), P(ws.pos[0]), None, st)
     lin('node_emb', ws.xin, ws.ah[:, :D])
     # ---- per edge: model-level embedding, adjacency heads
     ea = _lib.WideEmbedArgs(ps, dp(edge_x), dp(cond_edge_x), 0 if d.two_d else dp(cond_x), d.ch, d.inn,
@@ -322,7 +322,7 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
     else:
         out_x = torch.zeros(B, N, 3 + d.inn, device=xh.device, dtype=torch.float32)
         _lib.call('jodo_node_out', P(ws.pos[d.L & 1]), P(ws.ap), _c(ws.ap.stride(0)), ctypes.byref(ps),
-                  ctypes.c_void_p(ws.flags.data_ptr() + 4), _c(d.inn), P(out_x), st)
+                  ctypes.c_void_p(ws.flags.data_ptr() + 4), None, _c(d.inn), P(out_x), st)
     ilin('hcat', ws.EH, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.H_img)
     ilin('ehead2', ws.H_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, C32=ws.X2)
     tmp = torch.zeros(B, N, N, d.ch, device=xh.device, dtype=torch.float32)

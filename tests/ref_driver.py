@@ -82,9 +82,9 @@ def build_model(ref, cfg, weights, via_ema=True, single_device=True):
     if single_device and torch.cuda.device_count() > 1 and cfg.device.type == 'cuda':
         model = torch.nn.DataParallel(model.module, device_ids=[cfg.device.index or 0])
     if cfg.device.type == 'cpu' and torch.cuda.is_available():
-        # a CPU model on a GPU box: DataParallel would scatter the CPU inputs to cuda:0 (on a CPU-only host it calls the
-        # module directly); keep the `module.` prefix of the state dict with a pass-through wrapper
-        model = _Direct(model.module)
+        # a CPU model on a GPU box: DataParallel's constructor moves the module to cuda:0 and scatters the inputs there
+        # (on a CPU-only host it calls the module directly); keep the `module.` prefix with a pass-through wrapper
+        model = _Direct(model.module.to('cpu'))
     names = [k for k, _ in model.module.named_parameters()]
     if via_ema:
         other = {k: v + 0.25 for k, v in weights.items()}

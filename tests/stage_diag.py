@@ -21,11 +21,11 @@ def tiles_to_dense(plan, img, k, tile_floats=None, group_first=True):
 
 
 def tiles_to_dense_h(plan, img, k, tile_halves, group_first=True):
-    """fp16 tile images [n_tiles][k/64][128][64] -> dense [B,N,N,k] (fp32)"""
-    nt = plan.n_tiles
+    """fp16 PAIR-tile images [n_pair_tiles][k/64][128][64] -> dense symmetric [B,N,N,k] (fp32)"""
+    nt = plan.n_pair_tiles
     img = img.reshape(nt, tile_halves)[:, :(k // 64) * 8192]
     rows = torch.stack([image_to_matrix_h(img[t], 128, k) for t in range(nt)]).reshape(nt * 128, k)
-    return plan.rows_to_dense(rows, group_first=group_first)
+    return plan.pairs_to_dense(rows)
 
 
 def act_image_to_rows(img, k):
@@ -58,8 +58,9 @@ def _fused_stages(model, dbg, trace, plan, inp, em, rep, D):
         rep.append((f'b{l}.v', rel(packed_to_dense(plan, b['qkv'].float()[:, 2 * D:]), ob['v'] * m)))
         rep.append((f'b{l}.hnode', rel(packed_to_dense(plan, b['hnode']), ob['hnode'] * m)))
         rep.append((f'b{l}.h', rel(packed_to_dense(plan, b['h']), ob['h'])))
-        e_rows = b['e'].reshape(plan.n_tiles, 16, 128, 4).permute(0, 2, 1, 3).reshape(plan.n_tiles * 128, 64)   # piece-major tiles
-        rep.append((f'b{l}.e', rel(plan.rows_to_dense(e_rows), ob['e'] * em)))
+        npt = plan.n_pair_tiles
+        e_rows = b['e'].reshape(npt, 16, 128, 4).permute(0, 2, 1, 3).reshape(npt * 128, 64)   # piece-major pair tiles
+        rep.append((f'b{l}.e', rel(plan.pairs_to_dense(e_rows), ob['e'] * em)))
         rep.append((f'b{l}.pos', rel(packed_to_dense(plan, b['pos'][:, :3]), ob['pos'])))
 
 
