@@ -89,13 +89,15 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
   const float4* pos = reinterpret_cast<const float4*>(a.pos);
   uint32_t par_m = 0;
 
-  // the e chunk of a tile = its rows' pair rows, gathered from the pair-row store one tile ahead (edge_common.cuh)
-  if (c.tile0 < c.tile1) gather_e16_rows(A0 + CHUNK_BYTES_A, a.e16, a.p.row_pair + (size_t)c.tile0 * TILE_ROWS, lt, AT_GROUP);
+
   // row metadata of a tile is fetched one tile ahead
   const int tfirst = min(c.tile0, a.p.n_tiles - 1);
   RowInfo rn = load_row(a.p, tfirst, row);
   int ngn = a.p.tile_ngroups[tfirst];
   uint8_t exn = a.extra[rn.pr];
+  // the e chunk of a tile = its rows' pair rows, gathered from the pair-row store one tile ahead (edge_common.cuh):
+  // the two warps that own a row quarter copy 16 of its rows each
+  if (c.tile0 < c.tile1) gather_e16_warp<16>(A0 + CHUNK_BYTES_A, a.e16, 32 * rq, 16 * HALF, rn.valid, rn.pr, lane);
   for (int tile = c.tile0; tile < c.tile1; tile += 2) {
     const RowInfo r = rn;
     const int ng = ngn;
@@ -149,8 +151,8 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
         ind_prev = 0xFFFFFFFFu;
       }
     }
-    if (tile + 2 < c.tile1)                             // the e chunk is consumed: gather this group's next tile
-      gather_e16_rows(A0 + CHUNK_BYTES_A, a.e16, a.p.row_pair + (size_t)(tile + 2) * TILE_ROWS, lt, AT_GROUP);
+    if (tile + 2 < c.tile1)                             // the e chunk is consumed: gather this group's next tile (rn)
+      gather_e16_warp<16>(A0 + CHUNK_BYTES_A, a.e16, 32 * rq, 16 * HALF, rn.valid, rn.pr, lane);
 
     // ---- en = LN(e1) * (1 + scale_msa) + shift_msa  -> A0 chunk 0
     {

@@ -36,25 +36,29 @@ __device__ __forceinline__ RowInfo load_row(const Plan& p, int tile, int t) {
 // ---- fp16 operand rows of a directed tile, gathered from the pair-row store ------------------------------------------
 // The store is a sequence of K-major SWIZZLE_128B tile images of 64 columns: pair row P occupies the 128 bytes at
 // P * 128, its 16-byte slot s holding piece s ^ (P & 7).  Row `row` of the destination chunk wants piece p at slot
-// p ^ (row & 7), i.e. source slot s goes to slot s ^ (P & 7) ^ (row & 7).  Thread lt of nthreads copies the 16-byte
-// pieces lt, lt + nthreads, ... of the 128 x 8 pieces with cp.async (no registers held across the copy); padding rows
-// are zero-filled so that they stay finite.  Completion: cp_async_wait_all() by every thread, then the usual
-// fence.proxy.async + barrier in front of the MMA that reads the chunk.
+// p ^ (row & 7), i.e. source slot s goes to slot s ^ (P & 7) ^ (row & 7).  A warp whose lane l holds the metadata of
+// tile row row0 + l (fetched one tile ahead anyway) copies NR of those rows, [row0 + sub0, row0 + sub0 + NR), four rows
+// = four whole 128-byte lines per cp.async instruction (eight lanes per row; P travels by shuffle), so no registers are
+// held across the copy and no line is touched twice; padding rows are zero-filled so that they stay finite.  Completion:
+// cp_async_wait_all() by every thread, then the usual fence.proxy.async + barrier in front of the MMA that reads the chunk.
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void gather_e16_rows(uint8_t* dst_chunk, const void* e16, const int* __restrict__ row_pair_tile,
-                                                int lt, int nthreads) {
-  const uint32_t d0 = smem_u32(dst_chunk);
-  for (int i = lt; i < TILE_ROWS * 8; i += nthreads) {
-    const int row = i >> 3, s = i & 7;
-    const int P = row_pair_tile[row];
-    if (P >= 0) {
-      cp_async16(d0 + row * 128 + ((s ^ (P & 7) ^ (row & 7)) << 4), static_cast<const uint8_t*>(e16) + (size_t)P * 128 + s * 16);
-    } else {
+template <int NR>
+__device__ __forceinline__ void gather_e16_warp(uint8_t* dst_chunk, const void* e16, int row0, int sub0, bool valid, int P, int lane) {
+  static_assert(NR % 4 == 0, "four rows per instruction");
+  const int s = lane & 7;
+  const int mine = valid ? P : -1;
+#pragma unroll
+  for (int k = 0; k < NR / 4; ++k) {
+    const int sub = sub0 + 4 * k + (lane >> 3);
+    const int Pk = __shfl_sync(0xffffffffu, mine, sub);
+    const int row = row0 + sub;
+    if (Pk >= 0)
+      cp_async16(smem_u32(dst_chunk) + row * 128 + ((s ^ ((Pk ^ row) & 7)) << 4), static_cast<const uint8_t*>(e16) + (size_t)Pk * 128 + s * 16);
+    else
       *reinterpret_cast<uint4*>(dst_chunk + row * 128 + (s << 4)) = make_uint4(0u, 0u, 0u, 0u);
-    }
   }
 }
 

@@ -175,8 +175,6 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
     mbar_expect_tx(&bars[0], 131072);
     bulk_g2s(smem + EQ_WC0, a.wc0_img, 131072, &bars[0]);
   }
-  // the e chunk of a tile = its rows' pair rows, gathered from the pair-row store one tile ahead (edge_common.cuh)
-  if (tile0 < tile1) gather_e16_rows(U, a.e16, a.p.row_pair + (size_t)tile0 * TILE_ROWS, t, EQ_THREADS);
   const bool uni = a.nonuni != nullptr && *a.nonuni == 0;
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   sync_tc();
@@ -194,6 +192,9 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   RowInfo r = load_row(a.p, tfirst, row);
   int ng = a.p.tile_ngroups[tfirst];
   uint8_t ex = a.extra[r.pr];
+  // the e chunk of a tile = its rows' pair rows, gathered from the pair-row store one tile ahead (edge_common.cuh):
+  // the four warps that own a row quarter copy 8 of its rows each
+  if (tile0 < tile1) gather_e16_warp<8>(U, a.e16, 32 * rq, 8 * cq, r.valid, r.pr, lane);
   float4 pg = pos[r.g], pj = pos[r.j];
   uint4 dfh[2];
   RowInfo rn = r;
@@ -285,8 +286,8 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       }
       tmem_wait_st();
       if (cq < 2) mbar_wait(&bars[5], par);      // the scratch aliases the GBF chunk: the whole input_lin MMA must be done
-      if (tile + 1 < tile1)                      // U chunk 0 is consumed: gather the next tile's e rows
-        gather_e16_rows(U, a.e16, a.p.row_pair + (size_t)(tile + 1) * TILE_ROWS, t, EQ_THREADS);
+      if (tile + 1 < tile1)                      // U chunk 0 is consumed: gather the next tile's e rows (rn)
+        gather_e16_warp<8>(U, a.e16, 32 * rq, 8 * cq, rn.valid, rn.pr, lane);
       if (t == 0) {
         mbar_expect_tx(&bars[8], 8192);          // the GBF chunk is consumed too: its tail takes the coord_mlp.2 image
         bulk_g2s(smem + EQ_W2, a.w2_img, 8192, &bars[8]);
