@@ -170,6 +170,8 @@ typedef struct jodo_equi_args {                         /* MultiCondEquiUpdate (
   const void* win_img;                    /* input_lin edge part fp16 image (N=256, K=128: [e | dist]) */
   const void* wc0_img;                    /* coord_mlp.0 fp16 image (N=256, K=256), pre-scaled by 1/2 */
   const void* w2_img;                     /* coord_mlp.2 fp16 image (N=16: rows 0..2 real, K=256) */
+  const void* w2_img32;                   /* the same padded to N=32 (the CTA-pair kernel feeds this MMA's A operand from tensor
+                                             memory, which needs N >= 32 with cta_group::2); null = single-CTA kernel only */
   float coord_scale;                      /* CoorsNorm.scale */
   const int* nonuni;                      /* device flag written by jodo_uniform_flag: 0 = every molecule has the same
                                              conditioning row (fast path reads row 0 through constant memory); may be null */

@@ -121,7 +121,7 @@ class EdgeUpdateArgs(ctypes.Structure):
 class EquiArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('e16', _P), ('pos_in', _P), ('pos_out', _P), ('AB', _P),
                 ('ldab', _I), ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P),
-                ('win_img', _P), ('wc0_img', _P), ('w2_img', _P), ('coord_scale', _F), ('nonuni', _P),
+                ('win_img', _P), ('wc0_img', _P), ('w2_img', _P), ('w2_img32', _P), ('coord_scale', _F), ('nonuni', _P),
                 ('gbf4', _F * 256), ('b0h', _F * 256)]
 
 

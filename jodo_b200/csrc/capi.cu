@@ -3,6 +3,7 @@
 #include "kernels.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -198,6 +199,11 @@ int jodo_equi(const jodo_equi_args* a, void* stream) {
   if (const char* m = check_plan(a->p)) return fail(m);
   if (a->ldab < a->p.Nn || a->ld_tab % 4 || a->tab_off % 4) return fail("jodo_equi: bad strides");
   if (!a->p.row_pair) return fail("jodo_equi: the plan needs row_pair (the edge state is stored per unordered pair)");
+  // The CTA-pair kernel (equi2.cu: cta_group::2, all weights resident, two-stage pipeline) is correct but measured no faster
+  // than the single-CTA kernel (0.41-0.45 ms vs 0.40 ms per launch at QM9 B = 2500: three pair rendezvous per tile at
+  // ~1.2 us each eat the overlap).  It stays selectable for A/B runs: JODO_EQUI_PAIR=1.
+  static const bool pair = std::getenv("JODO_EQUI_PAIR") != nullptr;
+  if (a->w2_img32 && pair) JODO_LAUNCH(jodo::launch_equi2(*a, num_sms(), S(stream)), "jodo_equi");
   JODO_LAUNCH(jodo::launch_equi(*a, num_sms(), S(stream)), "jodo_equi");
 }
 int jodo_edge_head(const jodo_edge_head_args* a, void* stream) {

@@ -83,11 +83,17 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Spin on the phase with parity `parity`.  A barrier that never completes is a bug; trap after ~4 s
-// instead of hanging the device.
+// A wait that has lasted ~2 s (4e9 SM cycles) is a protocol bug: trap instead of hanging the device.
+__device__ __forceinline__ bool mbar_timed_out(long long& t0) {
+  const long long now = clock64();
+  if (t0 == 0) { t0 = now; return false; }
+  return now - t0 > 4000000000ll;
+}
+// Spin on the phase with parity `parity`.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+  long long t0 = 0;
   // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint expires)
   // instead of burning issue slots that the CTA's other warp group could use
   for (uint32_t spin = 0; !done; ++spin) {
@@ -100,7 +106,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
-    if (!done && spin > (1u << 20)) __trap();      // a barrier that never completes is a bug: do not hang the device
+    if (!done && (spin & 255u) == 255u && mbar_timed_out(t0)) __trap();   // a barrier that never completes is a bug: do not hang the device
   }
 }
 
@@ -287,6 +293,104 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+
+// ---------------------------------------------------------------- CTA pairs (cta_group::2) and clusters
+// A cluster of two CTAs on the two SMs of a TPC runs one tcgen05.mma over M = 256 rows: each CTA supplies the A operand of
+// its own 128 rows and HALF of the B operand (N / 2 rows of W at the same shared-memory offset in both CTAs); the
+// accumulator of a CTA's 128 rows (all N columns) lands in its own tensor memory.  The leader (cluster rank 0) issues the
+// instruction; tcgen05.commit with .multicast arrives on the mbarrier at the same offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (count 1) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// wait with cluster-scope acquire (the arrivals may come from the peer CTA).  SPIN: poll with test_wait instead of suspending
+// in try_wait (the wake-up after a remote arrival is on the critical path of the one thread that then issues an MMA).
+template <bool SPIN = false>
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    if (SPIN) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(done)
+          : "r"(addr), "r"(parity)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(done)
+          : "r"(addr), "r"(parity), "r"(0x989680u)
+          : "memory");
+    }
+    if (!done && (spin & 255u) == 255u && mbar_timed_out(t0)) __trap();
+  }
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot) {   // the same warp index in both CTAs of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// kind::f16 instruction descriptor for the pair: M = 256 over both CTAs, N = n (all of it)
+__device__ __host__ constexpr uint32_t umma_idesc_f16_2sm(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// A operand from tensor memory (each CTA's own lanes), B halves from both CTAs' shared memory
+__device__ __forceinline__ void umma_f16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// all previously issued tcgen05.mma of this thread arrive (count 1) on `bar` in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 
 // TMEM address of (lane base of this warp, column)

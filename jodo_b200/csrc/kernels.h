@@ -111,7 +111,8 @@ using EdgeUpdateArgs = ::jodo_edge_update_args;
 cudaError_t launch_edge_update(const EdgeUpdateArgs& a, int num_sms, cudaStream_t st);
 
 using EquiArgs = ::jodo_equi_args;
-cudaError_t launch_equi(const EquiArgs& a, int num_sms, cudaStream_t st);
+cudaError_t launch_equi(const EquiArgs& a, int num_sms, cudaStream_t st);      // one tile in flight per SM (equi.cu)
+cudaError_t launch_equi2(const EquiArgs& a, int num_sms, cudaStream_t st);     // CTA pairs, two-stage pipeline (equi2.cu)
 
 using EdgeHeadArgs = ::jodo_edge_head_args;
 cudaError_t launch_edge_head(const EdgeHeadArgs& a, int num_sms, cudaStream_t st);

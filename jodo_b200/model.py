@@ -328,7 +328,8 @@ class _DGTBase(nn.Module):
             _lib.call('jodo_edge_update', ctypes.byref(ua), st)
             qa = _lib.EquiArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), plan.Nn,
                                _lib.dp(ws.tab), ld_tab, off, _lib.dp(ws.extra), pk.ptr(p + 'win.img'),
-                               pk.ptr(p + 'wc0h.img'), pk.ptr(p + 'w2.img'), meta['coord_scale'][l], ws.flags.data_ptr() + 8,
+                               pk.ptr(p + 'wc0h.img'), pk.ptr(p + 'w2.img'), pk.ptr(p + 'w2x.img'), meta['coord_scale'][l],
+                               ws.flags.data_ptr() + 8,
                                pk.host[p + 'gbf4'], pk.host[p + 'b0h'])
             _lib.call('jodo_equi', ctypes.byref(qa), st)
             _lib.call('jodo_com', _lib.ptr(pout), ctypes.byref(ps), st)

@@ -313,6 +313,7 @@ def pack_model(sd, dims, device, fused=None):
         pk.add(p + 'wc0h.img', weight_image_h(0.5 * W(f'{b}.equi_update.coord_mlp.0'), D))
         pk.add_host(p + 'b0h', 0.5 * Bv(f'{b}.equi_update.coord_mlp.0'))
         pk.add(p + 'w2.img', weight_image_h(pad2(W(f'{b}.equi_update.coord_mlp.2'), 16, D), 16))          # N = 16 (3 real)
+        pk.add(p + 'w2x.img', weight_image_h(pad2(W(f'{b}.equi_update.coord_mlp.2'), 32, D), 32))         # N = 32 (CTA-pair kernel)
         pk.add_host(p + 'gbf4', _gbf_table4(sd, f'{b}.dist_layer', device))
         scales.append(sd[f'{b}.equi_update.coord_norm.scale'].reshape(()))
     pk.meta['coord_scale'] = [float(s) for s in torch.stack(scales).cpu()]
