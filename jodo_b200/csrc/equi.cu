@@ -164,13 +164,14 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   const int per = (a.p.n_tiles + gridDim.x - 1) / gridDim.x;
   const int tile0 = blockIdx.x * per;
   const int tile1 = min(tile0 + per, a.p.n_tiles);
+  const uint8_t* win_img = static_cast<const uint8_t*>(a.win_img);   // (eight replicas to spread the per-tile re-fetch over L2: no gain)
 
   if (t == 0) {
     for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
     if (tile0 < tile1) {
       mbar_expect_tx(&bars[2], 65536);
-      bulk_g2s(X, a.win_img, 65536, &bars[2]);
+      bulk_g2s(X, win_img, 65536, &bars[2]);
     }
     mbar_expect_tx(&bars[0], 131072);
     bulk_g2s(smem + EQ_WC0, a.wc0_img, 131072, &bars[0]);
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
   if (tile0 < tile1) gather_e16_warp<8>(U, a.e16, 32 * rq, 8 * cq, r.valid, r.pr, lane);
   float4 pg = pos[r.g], pj = pos[r.j];
   uint4 dfh[2];
+  uint4 ab[8];                                    // A[g] + B[j] of this thread's 64 hidden units (fp16 pairs), one tile ahead
   RowInfo rn = r;
   int ngn = ng;
   uint8_t exn = ex;
@@ -238,26 +240,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
         umma_commit(&bars[hf ? 5 : 3]);
       }
     }
-    // under the MMA: hoisted input_lin parts (piece-major fp16 rows, bias folded into the g part), pre-added as half2
-    uint4 ab[8];
-    {
-      const uint4* pa = static_cast<const uint4*>(a.AB) + (size_t)(8 * cq) * a.ldab + r.g;
-      const uint4* pb = static_cast<const uint4*>(a.AB) + (size_t)(32 + 8 * cq) * a.ldab + r.j;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint4 ua[4], ub[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { ua[i] = __ldg(pa + (size_t)(4 * h + i) * a.ldab); ub[i] = __ldg(pb + (size_t)(4 * h + i) * a.ldab); }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __half2* x2 = reinterpret_cast<__half2*>(&ua[i]);
-          const __half2* y2 = reinterpret_cast<const __half2*>(&ub[i]);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) x2[k] = __hadd2(x2[k], y2[k]);
-          ab[4 * h + i] = ua[i];
-        }
-      }
-    }
+    // the hoisted input_lin parts A[g] + B[j] of this tile were gathered (and pre-added as half2) one tile ahead
     mbar_wait(&bars[cq < 2 ? 3 : 5], par);
     PHASE_MARK(3);
     tc_fence_after();
@@ -330,6 +313,26 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       const float gsc = uni ? c_eqmod[512] : trn[tab_gbf(D_)], gsh = uni ? c_eqmod[513] : trn[tab_gbf(D_) + 1];
       EQ_DISPATCH(eq_gbf, a, sq_dist(pgn, pjn), gsc, gsh, dfh);
     }
+    // ... and its hoisted input_lin parts (piece-major fp16 rows, bias folded into the g part), pre-added as half2: the
+    // gather (1 KB per edge from L2) runs under the coord_mlp.0 MMA instead of in front of pass 1
+    {
+      const uint4* pa = static_cast<const uint4*>(a.AB) + (size_t)(8 * cq) * a.ldab + rn.g;
+      const uint4* pb = static_cast<const uint4*>(a.AB) + (size_t)(32 + 8 * cq) * a.ldab + rn.j;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 ua[4], ub[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ua[i] = __ldg(pa + (size_t)(4 * h + i) * a.ldab); ub[i] = __ldg(pb + (size_t)(4 * h + i) * a.ldab); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half2* x2 = reinterpret_cast<__half2*>(&ua[i]);
+          const __half2* y2 = reinterpret_cast<const __half2*>(&ub[i]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) x2[k] = __hadd2(x2[k], y2[k]);
+          ab[4 * h + i] = ua[i];
+        }
+      }
+    }
     if (tile >= tile0) {
     mbar_wait(&bars[cq < 2 ? 4 : 6], par);
     PHASE_MARK(6);
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       mbar_wait(&bars[6], par);
       if (tile + 1 < tile1) {
         mbar_expect_tx(&bars[2], 65536);
-        bulk_g2s(X, a.win_img, 65536, &bars[2]);
+        bulk_g2s(X, win_img, 65536, &bars[2]);
       }
     }
     sync_tc();
