@@ -80,6 +80,25 @@ typedef struct jodo_imglinear_args {
 int jodo_imglinear(const jodo_imglinear_args* a, void* stream);
 
 
+/* ---- weight packing: reference parameters -> operand images / tables (replaces the per-tensor host code a framework
+ * would run at load time; reference side: the state dict of DGT_concat, models/mol_gnn.py:414-489).  An item copies the
+ * source sub-matrix src[rows, cols] (fp32, row-major, leading dimension src_ld) to (row0, col0) of a destination piece as
+ * dst = src * scale + add.  Destination kinds: JODO_PACK_F32 -- fp32 row-major with leading dimension dst_ld;
+ * JODO_PACK_IMG_F16 -- fp16 operand image [N/nt][k_pad/64][nt][128 B], K-major SWIZZLE_128B, saturating at +-65504;
+ * JODO_PACK_IMG_TF32 -- fp32 image [N/nt][k_pad/32][nt][128 B] rounded to tf32.  Padding = zero-filled destination.
+ * jodo_pack_weights runs ONE kernel over a device-resident item table; blk_item / blk_first (device, built by the host)
+ * map every thread block of 2048 source elements to its item and the item's first block. */
+#define JODO_PACK_F32 0
+#define JODO_PACK_IMG_F16 1
+#define JODO_PACK_IMG_TF32 2
+#define JODO_PACK_ELEMS_PER_BLOCK 2048
+typedef struct jodo_pack_item {
+  const float* src; int src_ld, rows, cols;
+  void* dst; int kind, dst_ld, nt, k_pad, row0, col0;
+  float scale, add;
+} jodo_pack_item;
+int jodo_pack_weights(const jodo_pack_item* items_dev, const int* blk_item_dev, const int* blk_first_dev, int n_blocks, void* stream);
+
 /* ---- varlen plan and argument blocks of the edge-tile kernels ------------------------------------
  * Atoms are packed (padding removed); directed edges live in tiles of 128 rows; a group = all partners
  * of one atom, never split across tiles (built by jodo_b200/plan.py once per node mask; replaces the

@@ -92,6 +92,14 @@ _F = ctypes.c_float
 _Z = ctypes.c_size_t
 
 
+PACK_ELEMS_PER_BLOCK = 2048        # JODO_PACK_ELEMS_PER_BLOCK
+
+
+class PackItem(ctypes.Structure):
+    _fields_ = [('src', _P), ('src_ld', _I), ('rows', _I), ('cols', _I), ('dst', _P), ('kind', _I), ('dst_ld', _I),
+                ('nt', _I), ('k_pad', _I), ('row0', _I), ('col0', _I), ('scale', _F), ('add', _F)]
+
+
 class PlanStruct(ctypes.Structure):
     _fields_ = [('B', _I), ('Nn', _I), ('n_tiles', _I), ('N', _I), ('node_mol', _P), ('node_dense', _P),
                 ('mol_start', _P), ('row_g', _P), ('row_j', _P), ('row_meta', _P), ('tile_ngroups', _P), ('row_mol', _P),

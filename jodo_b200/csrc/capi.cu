@@ -161,6 +161,11 @@ int jodo_ancestral_update(const float* x, const float* pred, const float* raw_po
               "jodo_ancestral_update");
 }
 
+int jodo_pack_weights(const jodo_pack_item* items_dev, const int* blk_item_dev, const int* blk_first_dev, int n_blocks, void* stream) {
+  if (n_blocks < 0 || (n_blocks > 0 && (!items_dev || !blk_item_dev || !blk_first_dev))) return fail("jodo_pack_weights: bad arguments");
+  JODO_LAUNCH(jodo::launch_pack_items(items_dev, blk_item_dev, blk_first_dev, n_blocks, S(stream)), "jodo_pack_weights");
+}
+
 static const char* check_plan(const jodo_plan& p) {
   if (p.B <= 0 || p.Nn <= 0 || p.n_tiles <= 0 || p.N <= 0) return "plan: empty";
   if (!p.node_mol || !p.node_dense || !p.mol_start || !p.row_g || !p.row_j || !p.row_meta || !p.tile_ngroups || !p.row_mol)

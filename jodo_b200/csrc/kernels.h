@@ -55,6 +55,8 @@ using ImgLinearArgs = ::jodo_imglinear_args;
 const char* check_imglinear(const ImgLinearArgs& a);
 cudaError_t launch_imglinear(const ImgLinearArgs& a, int num_sms, cudaStream_t stream);
 
+cudaError_t launch_pack_items(const jodo_pack_item* items, const int* blk_item, const int* blk_first, int n_blocks, cudaStream_t st);
+
 // ---- per-molecule AdaLN table layout (floats from the start of a molecule's table row) -------------
 // Every `scale` entry holds 1 + scale (the packer adds 1 to the bias of those columns), so modulation is one FMA.
 // [0,2)  model-level GBF (scale, shift); then per layer l at TAB_HEAD + l*tab_layer_stride(D):

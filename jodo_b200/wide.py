@@ -33,99 +33,77 @@ def supported(d) -> str | None:
     return None
 
 
-def _gbf_consts(sd, prefix, dev):
-    """{mu, sqrt(0.5 log2 e) / sg, 1 / (a sg)} x EDP (reference models/layers.py:291-295, 332-333):
-    exp(-0.5 ((x - mu) / sg)^2) / (a sg) = 2^(-((x - mu) c1)^2) c2.  Indexed by feature COLUMN: Gaussian k sits at
-    entry k + 1 (column 0 of the features is the raw x)."""
-    mu = sd[prefix + '.means.weight'].float().view(-1)
-    sg = sd[prefix + '.stds.weight'].float().view(-1).abs() + 1e-5
-    a = (2 * 3.14159) ** 0.5
-    out = torch.zeros(3, EDP, device=dev)
-    k = mu.numel()
-    out[0, 1:k + 1] = mu
-    out[1, 1:k + 1] = (0.5 * 1.4426950408889634) ** 0.5 / sg
-    out[2, 1:k + 1] = 1.0 / (a * sg)
-    return out.reshape(-1)
-
-
-def pack_wide(pk, sd, d, add_lin):
-    """Edge-level and per-block weights of the wide path (the molecule / atom level pieces are packed by
-    pack.pack_model).  Every GEMM runs with 128-column tiles; N and K are zero padded."""
+def pack_wide(pk, sd, d, add_lin, lin):
+    """Edge-level and per-block weights of the wide path, recorded on the packer of pack.pack_model (which packs the
+    molecule / atom level pieces).  Every GEMM runs with 128-column tiles; N and K are zero padded."""
+    from .pack import _gbf_all
     D, ed, L, r = d.D, d.ed, d.L, d.r
     dev = pk.device
     W = lambda n: sd[n + '.weight']
     Bv = lambda n: sd[n + '.bias']
-    z = lambda *s: torch.zeros(*s, device=dev)
     qkp = ceil_to(d.qk, 128)
     pk.meta.update(qkp=qkp, wide=True)
     # ---- model level: edge_emb on [dist0 (ed) | edge_x (ch) | cond_edge_x (ch)]; 2-D model: [edge_x | cond_edge_x]
     we = W('edge_emb')                                         # [ed, 2ch + ed]: [edge_x | cond_edge_x | dist]
     if d.two_d:
-        pk.add('gbf', z(3 * EDP))
-        add_lin('edge_emb', we, Bv('edge_emb'), 128)           # K = 64
+        pk.mat('gbf', 3, EDP, [])
+        lin('edge_emb', 'edge_emb', 128)                       # K = 64
     else:
-        pk.add('gbf', _gbf_consts(sd, 'dist_layer', dev))
-        wep = z(ed, EDP)
-        wep[:, :ed] = we[:, 2 * d.ch:]
-        wep[:, ed:ed + 2 * d.ch] = we[:, :2 * d.ch]
-        add_lin('edge_emb', wep, Bv('edge_emb'), 128)
+        # {mu, sqrt(0.5 log2 e) / sg, 1 / (a sg)} x EDP indexed by feature COLUMN: Gaussian k sits at entry k + 1 (column 0 of
+        # the features is the raw x)
+        mu, c1, c2 = _gbf_all(sd, ['dist_layer'] + [f'e_block_{l}.dist_layer' for l in range(L)], dev)
+        pk._keep += [mu, c1, c2]
+        pk.mat('gbf', 3, EDP, [(mu[0], 0, 1), (c1[0], 1, 1), (c2[0], 2, 1)])
+        add_lin('edge_emb', [(we[:, 2 * d.ch:], 0, 0), (we[:, :2 * d.ch], 0, ed)], [(Bv('edge_emb'), 0)], 128, ed, EDP)
     # ---- edge heads: layer 0 of edge_exist_mlp | edge_type_mlp is linear in the concatenated edge hiddens
     # cat[e0, edge_0(e_1), ..] (reference models/mol_gnn.py:567-574), so the edge_i projections are folded into it:
     # H = W0[:, :ed] e0 + sum_l (W0[:, s_l] We_l) e_l + b is ONE GEMM over the operand [e0 | e_1 | .. | e_L] (slots of
-    # EDP columns, written block by block), K = (L + 1) EDP.
-    w0 = torch.cat([W('edge_exist_mlp.0'), W('edge_type_mlp.0')], dim=0)            # [2ed, ed + L ce]
-    b0 = torch.cat([Bv('edge_exist_mlp.0'), Bv('edge_type_mlp.0')]).clone()
+    # EDP columns, written block by block), K = (L + 1) EDP.  The L small products run as two batched einsums.
+    f32 = lambda t: t.detach().to(dev, torch.float32)
+    w0 = torch.cat([f32(W('edge_exist_mlp.0')), f32(W('edge_type_mlp.0'))], dim=0)            # [2ed, ed + L ce]
+    sl = w0[:, ed:ed + L * d.ce].reshape(2 * ed, L, d.ce)
+    wl = torch.stack([f32(W(f'edge_{l}')) for l in range(L)])                                 # [L, ce, ed]
+    bl = torch.stack([f32(Bv(f'edge_{l}')) for l in range(L)])                                # [L, ce]
+    prod = torch.einsum('nlc,lce->nle', sl, wl).contiguous()                                  # [2ed, L, ed]
+    b0 = torch.cat([f32(Bv('edge_exist_mlp.0')), f32(Bv('edge_type_mlp.0'))]) + torch.einsum('nlc,lc->n', sl, bl)
+    pk._keep += [w0, prod, b0]
     hp = ceil_to(2 * ed, 128)
-    wh = z(2 * ed, (L + 1) * EDP)
-    wh[:, :ed] = w0[:, :ed]
-    for l in range(L):
-        sl = w0[:, ed + l * d.ce:ed + (l + 1) * d.ce]
-        b0 += sl @ Bv(f'edge_{l}')
-        wh[:, (l + 1) * EDP:(l + 1) * EDP + ed] = sl @ W(f'edge_{l}')
-    add_lin('hcat', wh, b0, 128, n_pad=hp)
-    w2 = z(ed, hp)
-    w2[:ed // 2, :ed] = W('edge_exist_mlp.2')
-    w2[ed // 2:, ed:2 * ed] = W('edge_type_mlp.2')
-    add_lin('ehead2', w2, torch.cat([Bv('edge_exist_mlp.2'), Bv('edge_type_mlp.2')]), 128)
-    pk.add('ehead4.w', torch.cat([W('edge_exist_mlp.4'), W('edge_type_mlp.4')], dim=0))     # [ch, ed / 2]
-    pk.add('ehead4.b', torch.cat([Bv('edge_exist_mlp.4'), Bv('edge_type_mlp.4')]))
+    add_lin('hcat', [(w0[:, :ed], 0, 0)] + [(prod[:, l, :], 0, (l + 1) * EDP) for l in range(L)], [(b0, 0)], 128, 2 * ed,
+            (L + 1) * EDP, n_pad=hp)
+    add_lin('ehead2', [(W('edge_exist_mlp.2'), 0, 0), (W('edge_type_mlp.2'), ed // 2, ed)],
+            [(Bv('edge_exist_mlp.2'), 0), (Bv('edge_type_mlp.2'), ed // 2)], 128, ed, hp)
+    pk.mat('ehead4.w', d.ch, ed // 2, [(W('edge_exist_mlp.4'), 0, 0), (W('edge_type_mlp.4'), 1, 0)])     # [ch, ed / 2]
+    pk.vec('ehead4.b', d.ch, [(Bv('edge_exist_mlp.4'), 0), (Bv('edge_type_mlp.4'), 1)])
     pk.meta['hp'] = hp
     # ---- blocks
-    scales = []
     f3p = ceil_to(ed * r, 128)
     pk.meta['f3p'] = f3p
     for l in range(L):
         b = f'e_block_{l}'
         p = f'b{l}.'
-        wq, bq = z(2 * qkp + D, D), z(2 * qkp + D)
-        wq[:d.qk], bq[:d.qk] = W(f'{b}.attn_mpnn.lin_query'), Bv(f'{b}.attn_mpnn.lin_query')
-        wq[qkp:qkp + d.qk], bq[qkp:qkp + d.qk] = W(f'{b}.attn_mpnn.lin_key'), Bv(f'{b}.attn_mpnn.lin_key')
-        wq[2 * qkp:], bq[2 * qkp:] = W(f'{b}.attn_mpnn.lin_value'), Bv(f'{b}.attn_mpnn.lin_value')
-        add_lin(p + 'qkv', wq, bq, 128)
-        add_lin(p + 'n2e', W(f'{b}.node2edge_lin'), None, 128)
-        nb = z(EDP)
-        nb[:ed] = Bv(f'{b}.node2edge_lin')
-        pk.add(p + 'n2e.bias', nb)
-        add_lin(p + 'ff1', W(f'{b}.ff_linear1'), Bv(f'{b}.ff_linear1'), 128)
-        add_lin(p + 'ff2', W(f'{b}.ff_linear2'), Bv(f'{b}.ff_linear2'), 128)
-        add_lin(p + 'node_l', W(f'node_{l}'), Bv(f'node_{l}'), 128)
+        add_lin(p + 'qkv',
+                [(W(f'{b}.attn_mpnn.lin_query'), 0, 0), (W(f'{b}.attn_mpnn.lin_key'), qkp, 0), (W(f'{b}.attn_mpnn.lin_value'), 2 * qkp, 0)],
+                [(Bv(f'{b}.attn_mpnn.lin_query'), 0), (Bv(f'{b}.attn_mpnn.lin_key'), qkp), (Bv(f'{b}.attn_mpnn.lin_value'), 2 * qkp)],
+                128, 2 * qkp + D, D)
+        lin(p + 'n2e', f'{b}.node2edge_lin', 128, bias=False)
+        pk.vec(p + 'n2e.bias', EDP, [(Bv(f'{b}.node2edge_lin'), 0)])
+        lin(p + 'ff1', f'{b}.ff_linear1', 128)
+        lin(p + 'ff2', f'{b}.ff_linear2', 128)
+        lin(p + 'node_l', f'node_{l}', 128)
         if not d.two_d:
-            wi = W(f'{b}.equi_update.input_lin')               # [D, 2D + 2ed]: [h_row | h_col | e | dist]
-            add_lin(p + 'ab', torch.cat([wi[:, :D], wi[:, D:2 * D]], dim=0),
-                    torch.cat([Bv(f'{b}.equi_update.input_lin'), z(D)]), 128)  # input_lin bias rides on the h[row] part
-            pk.add(p + 'gbf', _gbf_consts(sd, f'{b}.dist_layer', dev))
-            add_lin(p + 'emb', W(f'{b}.edge_emb'), Bv(f'{b}.edge_emb'), 128)                # K = 2ed: [dist | e]
-            add_lin(p + 'equi_in', wi[:, 2 * D:].contiguous(), None, 128)                   # K = 2ed: [e | dist]
-            add_lin(p + 'c0', W(f'{b}.equi_update.coord_mlp.0'), Bv(f'{b}.equi_update.coord_mlp.0'), 128)
-            add_lin(p + 'c2', W(f'{b}.equi_update.coord_mlp.2'), None, 64)                  # N = 64 (1 + X real)
-            scales.append(sd[f'{b}.equi_update.coord_norm.scale'].reshape(()))
-        wg = z(qkp + D, EDP)
-        wg[:d.qk, :ed] = W(f'{b}.attn_mpnn.lin_edge0')
-        wg[qkp:, :ed] = W(f'{b}.attn_mpnn.lin_edge1')
-        add_lin(p + 'g01', wg, None, 128)
-        add_lin(p + 'ff3', pad2(W(f'{b}.ff_linear3'), f3p, EDP), Bv(f'{b}.ff_linear3'), 128, n_pad=f3p)
-        add_lin(p + 'ff4', pad2(W(f'{b}.ff_linear4'), ed, f3p), Bv(f'{b}.ff_linear4'), 128)
-    pk.meta['coord_scale'] = [float(s) for s in torch.stack(scales).cpu()] if scales else []
+            wi, bi = W(f'{b}.equi_update.input_lin'), Bv(f'{b}.equi_update.input_lin')    # [D, 2D + 2ed]: [h_row | h_col | e | dist]
+            add_lin(p + 'ab', [(wi[:, :D], 0, 0), (wi[:, D:2 * D], D, 0)], [(bi, 0)], 128, 2 * D, D)   # bias rides on the h[row] part
+            pk.mat(p + 'gbf', 3, EDP, [(mu[1 + l], 0, 1), (c1[1 + l], 1, 1), (c2[1 + l], 2, 1)])
+            lin(p + 'emb', f'{b}.edge_emb', 128)                                            # K = 2ed: [dist | e]
+            add_lin(p + 'equi_in', [(wi[:, 2 * D:], 0, 0)], [], 128, D, 2 * ed)             # K = 2ed: [e | dist]
+            lin(p + 'c0', f'{b}.equi_update.coord_mlp.0', 128)
+            lin(p + 'c2', f'{b}.equi_update.coord_mlp.2', 64, bias=False)                   # N = 64 (1 + X real)
+        add_lin(p + 'g01', [(W(f'{b}.attn_mpnn.lin_edge0'), 0, 0), (W(f'{b}.attn_mpnn.lin_edge1'), qkp, 0)], [], 128, qkp + D, EDP)
+        add_lin(p + 'ff3', [(W(f'{b}.ff_linear3'), 0, 0)], [(Bv(f'{b}.ff_linear3'), 0)], 128, f3p, EDP, n_pad=f3p)
+        add_lin(p + 'ff4', [(W(f'{b}.ff_linear4'), 0, 0)], [(Bv(f'{b}.ff_linear4'), 0)], 128, ed, f3p)
+    if not d.two_d:
+        cs = torch.stack([f32(sd[f'e_block_{l}.equi_update.coord_norm.scale']).reshape(()) for l in range(L)])
+        pk.add_host('coord_scale', cs)
 
 
 class WideWorkspace:

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from jodo_b200 import configs, roofline
-from jodo_b200.pack import (image_to_matrix, image_to_matrix_h, matrix_to_image, pack_model, split_heads, weight_image,
+from jodo_b200.pack import (Packed, image_to_matrix, image_to_matrix_h, matrix_to_image, pack_model, pad2, weight_image,
                             weight_image_h)
 from jodo_b200.params import dims_from_config, param_spec, synth_state_dict
 from jodo_b200.plan import TILE, Plan
@@ -130,10 +130,43 @@ def test_fp32_image_round_trip_and_tf32_rounding():
 
 
 def test_split_heads_layout():
-    w = torch.arange(252 * 2, dtype=torch.float32).reshape(252, 2)
-    s = split_heads(w, 256, 252)
-    assert torch.equal(s[:126], w[:126]) and torch.equal(s[128:254], w[126:])
-    assert float(s[126:128].abs().sum()) == 0 and float(s[254:].abs().sum()) == 0
+    """lin_query / lin_key / lin_edge0 rows in the packed q | k | v image: heads 0..6 at rows [0, 126), heads 7..13 at rows
+    [128, 254) of every 256-row block, zeros elsewhere (csrc/attn.cu reads one 128-column half per warp group)."""
+    cfg = configs.NAMED['qm9_uncond']()
+    d = dims_from_config(cfg)
+    sd = synth_state_dict(param_spec(cfg), seed=1)
+    pk = pack_model(sd, d, 'cpu')
+    img = pk['b0.qkv.img'].view(torch.float16)
+    tiles = [image_to_matrix_h(img[t * 256 * 256:(t + 1) * 256 * 256], 256, 256) for t in range(3)]
+    wq = sd['e_block_0.attn_mpnn.lin_query.weight'].half().float()
+    wk = sd['e_block_0.attn_mpnn.lin_key.weight'].half().float()
+    for s_, w in ((tiles[0], wq), (tiles[1], wk)):
+        assert torch.equal(s_[:126], w[:126]) and torch.equal(s_[128:254], w[126:])
+        assert float(s_[126:128].abs().sum()) == 0 and float(s_[254:].abs().sum()) == 0
+    assert torch.equal(tiles[2], sd['e_block_0.attn_mpnn.lin_value.weight'].half().float())
+
+
+def test_recorded_pieces_equal_the_reference_layout_functions():
+    """The three destination formats of jodo_pack_weights (as emulated on the CPU) against the stand-alone layout
+    functions: a zero-padded matrix assembled from offset pieces, scaled, in N tiles."""
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(40, 70, generator=g), torch.randn(24, 50, generator=g) * 300.0
+    pk = Packed('cpu')
+    pk.image_h('h', 128, 192, 64, [(a, 3, 5), (b, 64, 128, 0.5)])
+    pk.image_tf32('t', 64, 96, 64, [(a[:, :60], 8, 32)])
+    pk.mat('m', 4, 80, [(a[0], 0, 0), (a[1, :10], 2, 7, 2.0, 1.0)], host=True)
+    pk.finish()
+    ref = torch.zeros(128, 192)
+    ref[3:43, 5:75] = a
+    ref[64:88, 128:178] = 0.5 * b
+    assert torch.equal(pk['h'].view(torch.int32), weight_image_h(ref, 64).view(torch.int32))
+    ref = torch.zeros(64, 96)
+    ref[8:48, 32:92] = a[:, :60]
+    assert torch.equal(pk['t'], weight_image(ref, 64))
+    ref = torch.zeros(4, 80)
+    ref[0, :70] = a[0]
+    ref[2, 7:17] = 2.0 * a[1, :10] + 1.0
+    assert torch.equal(pk['m'].reshape(4, 80), ref) and list(pk.host['m']) == ref.reshape(-1).tolist()
 
 
 @pytest.mark.parametrize('name', ['qm9_uncond', 'qm9_cond', 'geom_l8', 'geom_l10'])
