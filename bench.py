@@ -57,6 +57,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch override (debug)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the strong-scaling point (N > 1) and the other workloads (N = 1)')
     return ap.parse_args()
 
 
@@ -109,12 +110,6 @@ class ClockSampler:
 
 
 # ---- workload ----------------------------------------------------------------------------------------
-def make_state(cfg, batch, max_n, seed, device):
-    from jodo_b200 import synth
-    b = synth.make_batch(cfg, batch, seed=seed, max_n=max_n)
-    return b
-
-
 def cpu_step_rate(cfg, wl, n_steps, threads):
     """CPU arm: the oracle port (fp32, all host threads) driving the same ancestral step on a bounded
     sample of the workload.  Returns (mol-steps/s, sample description)."""
@@ -253,10 +248,124 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+class Workload:
+    """One workload on this rank: model, synthetic state, the (graph-replayed) step function."""
+
+    def __init__(self, wl, dev, world, rank, per_gpu_batch=None, global_batch=None, no_graph=False):
+        from jodo_b200 import configs, roofline, sampler as S, synth
+        from jodo_b200.model import create_model
+        self.S = S
+        self.wl = wl
+        cfg_name, batch, max_n, self.desc = WORKLOADS[wl]
+        self.cfg_name = cfg_name
+        batch = per_gpu_batch or batch
+        self.cfg = cfg = configs.NAMED[cfg_name]()
+        self.dpm = wl == 'qm9_cond'
+        # ONE global batch (seed 42) dealt over the ranks by sampler.shard_molecules, so that the per-rank sum of n (n - 1)
+        # -- the cost driver -- is balanced; each rank then draws its own noise for its molecules
+        total = global_batch if global_batch is not None else batch * world
+        gen = torch.Generator().manual_seed(42)
+        n_all = synth.sample_n_nodes(cfg.data.info_name, total, gen, max_n)
+        self.idx = S.shard_molecules(n_all, world, rank) if world > 1 else torch.arange(total)
+        self.total, self.batch = total, len(self.idx)
+        b = synth.make_batch(cfg, self.batch, seed=42 + rank, n_nodes=n_all[self.idx])
+        self.model = create_model(cfg, dev)
+        self.d = self.model.dims
+        self.n_nodes = b['n_nodes']
+        self.N = int(self.n_nodes.max())
+        self.tot = roofline.batch_totals(self.n_nodes, self.d)
+        self.node_mask, self.edge_mask = b['node_mask'].to(dev), b['edge_mask'].to(dev)
+        self.state = dict(x=b['xh'].to(dev), ex=b['edge_x'].to(dev), cx=None, cex=None)
+        torch.cuda.manual_seed(1234 + rank)                   # the samplers draw from the default CUDA generator
+        self.grid = torch.linspace(0.9946, 1e-3, 1000)
+        self.smp = S.AncestralSampler(S.CosineVP(), self.grid)
+        if self.dpm:
+            self.sol = S.DPMSolverSinglestep(S.CosineVP(), 50, order=2)
+            self.ogrid = self.sol.outer_grid(dev)
+            self.context = torch.randn(self.batch, 1, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
+        self.graphed, self.graph_note, self.no_graph = None, 'eager', no_graph
+
+    def step(self, i):
+        """Eager step i (ancestral: one reverse step; DPM: even i = one outer step of two evaluations, odd i = nothing)."""
+        st = self.state
+        if self.dpm:
+            if i % 2:
+                return
+            x, ex = self.sol.outer_step(self.model, i // 2, self.ogrid, st['x'], self.node_mask, self.edge_mask, st['ex'], self.context)
+            st.update(x=x, ex=ex, cx=self.sol.cond_x, cex=self.sol.cond_edge_x, xm=x, em=ex)
+            return
+        x, ex, xm, em, cx, cex = self.smp.step(self.model, i, st['x'], st['ex'], self.node_mask, self.edge_mask, st['cx'], st['cex'])
+        st.update(x=x, ex=ex, cx=cx, cex=cex, xm=xm, em=em)
+
+    def warm(self, W):
+        """W eager warm-up steps, then capture the step into a CUDA graph (same kernels, same random stream; removes the
+        host launch gaps between the ~125 kernels of a step).  Falls back to the eager step if the capture fails."""
+        S = self.S
+        for i in range(W):
+            self.step(i)
+        if self.no_graph or W < 2:
+            return
+        st = self.state
+        try:
+            if self.dpm:
+                self.graphed = S.GraphedDPMStep(self.sol, self.model, st['x'], st['ex'], self.node_mask, self.edge_mask,
+                                                self.context, self.ogrid)
+                self.graphed.run(W // 2 - 1)                   # one untimed replay
+            else:
+                self.graphed = S.GraphedAncestralStep(self.smp, self.model, st['x'], st['ex'], st['cx'], st['cex'],
+                                                      self.node_mask, self.edge_mask)
+                self.graphed.run(W - 1)
+            self.graph_note = 'cuda graph replay'
+        except Exception as exc:                               # noqa: BLE001
+            self.graphed, self.graph_note = None, 'eager (graph capture failed: %s)' % str(exc)[:120]
+
+    def run(self, i):
+        if self.graphed is None:
+            return self.step(i)
+        if self.dpm:
+            if i % 2 == 0:
+                self.graphed.run(i // 2)
+        else:
+            self.graphed.run(i)
+
+    def sync_state(self):
+        g = self.graphed
+        if g is None:
+            return
+        if self.dpm:
+            self.state.update(x=g.x, ex=g.edge_x, cx=g.cond_x, cex=g.cond_edge_x, xm=g.x, em=g.edge_x)
+        else:
+            self.state.update(x=g.x, ex=g.edge_x, cx=g.cond_x, cex=g.cond_edge_x, xm=g.x_mean, em=g.edge_mean)
+
+    def launches_per_step(self):
+        return None if self.graphed is None else self.graphed.launches_per_step / (2 if self.dpm else 1)
+
+
+def timed_steps(w, W, K, barrier, dev, prof=False):
+    """K steps after W, device-timed; returns this rank's milliseconds."""
+    from jodo_b200 import _lib
+    barrier()
+    l0 = _lib.LAUNCHES
+    if prof:
+        torch.cuda.cudart().cudaProfilerStart()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        w.run(i)
+    e1.record()
+    barrier()
+    if prof:
+        torch.cuda.cudart().cudaProfilerStop()
+    launches = _lib.LAUNCHES - l0
+    if w.graphed is not None:
+        launches = int(w.launches_per_step() * K)            # replays do not pass through the ctypes binding
+    w.sync_state()
+    return e0.elapsed_time(e1), launches
+
+
 def run_b200(args):
     import torch.distributed as dist
-    from jodo_b200 import _lib, configs, roofline, sampler as S, synth
-    from jodo_b200.model import create_model
+    from jodo_b200 import _lib, roofline, sampler as S
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -278,95 +387,43 @@ def run_b200(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    cfg_name, batch, max_n, desc = WORKLOADS[args.workload]
-    if args.batch:
-        batch = args.batch
-    cfg = configs.NAMED[cfg_name]()
-    model = create_model(cfg, dev)
-    d = model.dims
-    b = synth.make_batch(cfg, batch, seed=42 + rank, max_n=max_n)
-    n_nodes = b['n_nodes']
-    N = int(n_nodes.max())
-    tot = roofline.batch_totals(n_nodes, d)
-    node_mask, edge_mask = b['node_mask'].to(dev), b['edge_mask'].to(dev)
-    grid = torch.linspace(0.9946, 1e-3, 1000)
-    torch.cuda.manual_seed(1234 + rank)                   # the samplers draw from the default CUDA generator
-    gen = None
-    smp = S.AncestralSampler(S.CosineVP(), grid, generator=gen)
-    K, W = args.steps, args.warmup
-    dpm = args.workload == 'qm9_cond'
-    if dpm:
-        # a step = one model evaluation; the solver advances in outer steps of two evaluations (order 2)
-        if K % 2 or W % 2:
-            K, W = K + (K % 2), W + (W % 2)
-        if W + K > 50:
-            raise SystemExit('qm9_cond: warmup + steps must not exceed the 50 model evaluations of the chain')
-        sol = S.DPMSolverSinglestep(S.CosineVP(), 50, order=2, generator=gen)
-        ogrid = sol.outer_grid(dev)
-        context = torch.randn(batch, 1, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
-    elif W + K > len(grid):
-        raise SystemExit('warmup + steps must not exceed the 1000-step grid')
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def rank_stats(ms_local):
+        """(max, min) over ranks of a per-rank device time."""
+        t = torch.tensor([ms_local, -ms_local], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), -float(t[1])
+
+    K, W = args.steps, args.warmup
+    w = Workload(args.workload, dev, world, rank, per_gpu_batch=args.batch, no_graph=args.no_graph)
+    dpm, batch, d, tot, N, cfg, total_mols = w.dpm, w.batch, w.d, w.tot, w.N, w.cfg, w.total
+    if dpm:
+        # a step = one model evaluation; the solver advances in outer steps of two evaluations (order 2)
+        if K % 2 or W % 2:
+            K, W = K + (K % 2), W + (W % 2)
+        if W + K > 50:
+            raise SystemExit('qm9_cond: warmup + steps must not exceed the 50 model evaluations of the chain')
+    elif W + K > len(w.grid):
+        raise SystemExit('warmup + steps must not exceed the 1000-step grid')
+    w.warm(W)
+    state = w.state
+
     # ---- device-resident run ------------------------------------------------------------------------
-    state = dict(x=b['xh'].to(dev), ex=b['edge_x'].to(dev), cx=None, cex=None)
-
-    def step(i):
-        if dpm:
-            if i % 2:
-                return                                   # odd evaluation indices belong to the outer step of i - 1
-            x, ex = sol.outer_step(model, i // 2, ogrid, state['x'], node_mask, edge_mask, state['ex'], context)
-            state.update(x=x, ex=ex, cx=sol.cond_x, cex=sol.cond_edge_x, xm=x, em=ex)
-            return
-        x, ex, xm, em, cx, cex = smp.step(model, i, state['x'], state['ex'], node_mask, edge_mask, state['cx'], state['cex'])
-        state.update(x=x, ex=ex, cx=cx, cex=cex, xm=xm, em=em)
-
-    for i in range(W):
-        step(i)
-    # One reverse step captured into a CUDA graph and replayed (same kernels, same random stream; removes the host
-    # launch gaps between the ~125 kernels of a step).  Falls back to the eager step if the capture fails.
-    graphed, graph_note = None, 'eager'
-    if not dpm and not args.no_graph and W >= 2:
-        try:
-            graphed = S.GraphedAncestralStep(smp, model, state['x'], state['ex'], state['cx'], state['cex'], node_mask, edge_mask)
-            graphed.run(W - 1)                             # one untimed replay
-            graph_note = 'cuda graph replay'
-        except Exception as exc:                           # noqa: BLE001
-            graphed, graph_note = None, 'eager (graph capture failed: %s)' % str(exc)[:120]
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    l0 = _lib.LAUNCHES
-    prof = os.environ.get('JODO_CUDA_PROFILER') == '1'       # ncu --profile-from-start off: capture the timed region only
-    if prof:
-        torch.cuda.cudart().cudaProfilerStart()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(W, W + K):
-        if graphed is not None:
-            graphed.run(i)
-        else:
-            step(i)
-    e1.record()
-    barrier()
-    if prof:
-        torch.cuda.cudart().cudaProfilerStop()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    launches = _lib.LAUNCHES - l0
-    if graphed is not None:
-        launches = graphed.launches_per_step * K           # replays do not pass through the ctypes binding
-        state.update(x=graphed.x, ex=graphed.edge_x, cx=graphed.cond_x, cex=graphed.cond_edge_x, xm=graphed.x_mean,
-                     em=graphed.edge_mean)
+    ms_local, launches = timed_steps(w, W, K, barrier, dev, prof=os.environ.get('JODO_CUDA_PROFILER') == '1')
     clk = clocks.stop() if rank == 0 else None
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms)
+    ms, ms_min = rank_stats(ms_local)
+    graphed, graph_note = w.graphed, w.graph_note
     ok = bool(torch.isfinite(state['xm']).all()) and bool(torch.isfinite(state['em']).all())
+    model, node_mask, edge_mask = w.model, w.node_mask, w.edge_mask
 
     # ---- end to end: host buffers, H2D + D2H every step ------------------------------------------------
     e2e = None
@@ -374,36 +431,27 @@ def run_b200(args):
         pin = lambda t: t.detach().cpu().contiguous().pin_memory()
         host = dict(x=pin(state['x']), ex=pin(state['ex']), cx=pin(state['cx']), cex=pin(state['cex']))
         h2d = sum(v.numel() * 4 for v in host.values())
-        outh = dict(x=torch.empty_like(host['x']).pin_memory(), ex=torch.empty_like(host['ex']).pin_memory(),
-                    cx=torch.empty_like(host['cx']).pin_memory(), cex=torch.empty_like(host['cex']).pin_memory())
+        outh = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
         d2h = sum(v.numel() * 4 for v in outh.values())
+        names = dict(x='x', ex='edge_x', cx='cond_x', cex='cond_edge_x')
 
         def e2e_step(i):
             if graphed is not None:                      # host buffers -> the graph's static inputs -> replay -> host
-                graphed.x.copy_(host['x'], non_blocking=True)
-                graphed.edge_x.copy_(host['ex'], non_blocking=True)
-                graphed.cond_x.copy_(host['cx'], non_blocking=True)
-                graphed.cond_edge_x.copy_(host['cex'], non_blocking=True)
-                graphed.run(i)
-                outh['x'].copy_(graphed.x, non_blocking=True)
-                outh['ex'].copy_(graphed.edge_x, non_blocking=True)
-                outh['cx'].copy_(graphed.cond_x, non_blocking=True)
-                outh['cex'].copy_(graphed.cond_edge_x, non_blocking=True)
-                torch.cuda.current_stream().synchronize()       # the caller reads the result on the host
-                for k in host:
-                    host[k], outh[k] = outh[k], host[k]
-                return
-            dv = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            if dpm:
-                sol.cond_x, sol.cond_edge_x = dv['cx'], dv['cex']
-                x, ex = sol.outer_step(model, (i // 2) % 24, ogrid, dv['x'], node_mask, edge_mask, dv['ex'], context)
-                cx, cex = sol.cond_x, sol.cond_edge_x
+                for k, attr in names.items():
+                    getattr(graphed, attr).copy_(host[k], non_blocking=True)
+                graphed.run(min(i // 2, 23) if dpm else i)
+                for k, attr in names.items():
+                    outh[k].copy_(getattr(graphed, attr), non_blocking=True)
             else:
-                x, ex, _, _, cx, cex = smp.step(model, i, dv['x'], dv['ex'], node_mask, edge_mask, dv['cx'], dv['cex'])
-            outh['x'].copy_(x, non_blocking=True)
-            outh['ex'].copy_(ex, non_blocking=True)
-            outh['cx'].copy_(cx, non_blocking=True)
-            outh['cex'].copy_(cex, non_blocking=True)
+                dv = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                if dpm:
+                    w.sol.cond_x, w.sol.cond_edge_x = dv['cx'], dv['cex']
+                    x, ex = w.sol.outer_step(model, (i // 2) % 24, w.ogrid, dv['x'], node_mask, edge_mask, dv['ex'], w.context)
+                    cx, cex = w.sol.cond_x, w.sol.cond_edge_x
+                else:
+                    x, ex, _, _, cx, cex = w.smp.step(model, i, dv['x'], dv['ex'], node_mask, edge_mask, dv['cx'], dv['cex'])
+                for k, v in dict(x=x, ex=ex, cx=cx, cex=cex).items():
+                    outh[k].copy_(v, non_blocking=True)
             torch.cuda.current_stream().synchronize()           # the caller reads the result on the host
             for k in host:
                 host[k], outh[k] = outh[k], host[k]
@@ -421,14 +469,14 @@ def run_b200(args):
             dist.barrier()
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         evals = 2 if dpm else 1                         # model evaluations per e2e_step
-        e2e = {'value': batch * world * ke * evals / float(dt), 'unit': UNIT, 'h2d_bytes_per_step': h2d // evals,
+        e2e = {'value': w.total * ke * evals / float(dt), 'unit': UNIT, 'h2d_bytes_per_step': h2d // evals,
                'd2h_bytes_per_step': d2h // evals, 'steps': ke * evals}
 
     # ---- per-kernel device times (CUDA events around every C-ABI call, outside the timed region) -------
     _lib.TRACE = []
     reps = 3
     for i in range(reps):
-        step(W + K - (2 if dpm else 1))
+        w.step(W + K - (2 if dpm else 1))
     torch.cuda.synchronize()
     per = {}
     for name, a, z in _lib.TRACE:
@@ -468,18 +516,60 @@ def run_b200(args):
         ach = kh[top] * tot['edges'] / (per[top][0] / per[top][1] * 1e-3) / 1e9
         roof = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
                 'traffic': traffic, 'peak_source': pk['src'] + ' HBM copy bandwidth', 'share_of_step': per[top][0] / total_traced}
-    whole = {'tflops': tot['flops'] * K / (ms * 1e-3) / 1e12, 'hbm_gbs_alg': tot['bytes'] * K / (ms * 1e-3) / 1e9}
+    whole = {'tflops': tot['flops'] * K / (ms_local * 1e-3) / 1e12, 'hbm_gbs_alg': tot['bytes'] * K / (ms_local * 1e-3) / 1e9}
     whole['tensor_frac'] = whole['tflops'] / pk['tf_sustained']
     whole['hbm_frac'] = whole['hbm_gbs_alg'] / pk['hbm']
 
-    # ---- the one collective: gather the final samples ------------------------------------------------
-    gathered = None
+    # ---- the one collective: gather the final samples (timed on the device, max over ranks) -----------
+    gathered, gather_ms = None, None
     if world > 1:
         Ng = torch.tensor([N], device=dev)
         dist.all_reduce(Ng, op=dist.ReduceOp.MAX)
-        idx = torch.arange(batch) + rank * batch
-        gx, ge = S.gather_samples(state['xm'], state['em'], idx, batch * world, int(Ng))
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gx, ge = S.gather_samples(state['xm'], state['em'], w.idx, w.total, int(Ng))
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = rank_stats(g0.elapsed_time(g1))[0]
         gathered = [list(gx.shape), list(ge.shape)]
+        del gx, ge
+
+    # ---- strong-scaling point: the single-GPU batch dealt over all ranks ------------------------------
+    strong = None
+    if world > 1 and not args.no_extras:
+        total1 = WORKLOADS[args.workload][1]
+        del w, graphed, model, state
+        torch.cuda.empty_cache()
+        ws_ = Workload(args.workload, dev, world, rank, global_batch=total1, no_graph=args.no_graph)
+        ws_.warm(W)
+        t_loc, _ = timed_steps(ws_, W, K, barrier, dev)
+        t_max, t_min = rank_stats(t_loc)
+        strong = {'global_batch': total1, 'per_rank_batch': ws_.batch, 'ms_per_step': t_max / K, 'value': total1 * K / (t_max * 1e-3),
+                  'rank_ms_per_step_min': t_min / K, 'rank_ms_per_step_max': t_max / K, 'step_launch': ws_.graph_note}
+        del ws_
+        torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, short runs on one GPU (configs[2..4]) -----------------------------
+    others = None
+    if world == 1 and rank == 0 and not args.no_extras and args.workload == 'qm9':
+        others = {}
+        try:
+            del w, graphed, model, state
+        except NameError:
+            pass
+        for name, (k2, w2) in (('geom', (10, 4)), ('geom_large', (6, 4)), ('qm9_cond', (10, 4))):
+            torch.cuda.empty_cache()
+            try:
+                wo = Workload(name, dev, 1, 0)
+                wo.warm(w2)
+                t, nl = timed_steps(wo, w2, k2, barrier, dev)
+                others[name] = {'workload': wo.desc, 'ms_per_step': t / k2, 'value': wo.total * k2 / (t * 1e-3), 'steps': k2, 'warmup': w2,
+                                'step_launch': wo.graph_note, 'gpu_launches': nl,
+                                'tensor_frac': wo.tot['flops'] * k2 / (t * 1e-3) / 1e12 / pk['tf_sustained']}
+                del wo
+            except Exception as exc:                       # noqa: BLE001
+                others[name] = {'error': str(exc)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -489,14 +579,17 @@ def run_b200(args):
 
     if rank == 0:
         out = {
-            'metric': METRIC, 'value': batch * world * K / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': K,
+            'metric': METRIC, 'value': total_mols * K / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': K,
             'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f16 operands (tf32 mantissa) / f32 accumulate + f32 elementwise', 'data': 'synthetic',
-            'config': {'workload': desc, 'per_gpu_batch': batch, 'N': N, 'atoms': tot['atoms'], 'edges': tot['edges'],
-                       'arch': cfg_name, 'weights': 'random init (seed 42)', 'l2': 'inputs larger than L2 '
-                       '(edge state %.0f MB per step)' % (tot['bytes'] / 1e6), 'parallelism': f'dp{world} (independent molecules)', 'step_launch': graph_note},
+            'config': {'workload': WORKLOADS[args.workload][3], 'global_batch': total_mols, 'per_gpu_batch': batch, 'N': N, 'atoms': tot['atoms'], 'edges': tot['edges'],
+                       'arch': WORKLOADS[args.workload][0], 'weights': 'random init (seed 42)', 'l2': 'inputs larger than L2 '
+                       '(edge state %.0f MB per step)' % (tot['bytes'] / 1e6),
+                       'parallelism': f'dp{world} (independent molecules, one global batch dealt by size: sampler.shard_molecules)',
+                       'step_launch': graph_note},
             'e2e': e2e, 'gpu_launches': launches, 'clocks': clk, 'roofline': roof, 'whole_step': whole,
-            'kernels': kernels, 'cpu_baseline': cpu, 'finite': ok, 'gathered': gathered,
+            'rank_ms_per_step_min': ms_min / K, 'rank_ms_per_step_max': ms / K, 'gather_ms': gather_ms, 'strong': strong,
+            'workloads': others, 'kernels': kernels, 'cpu_baseline': cpu, 'finite': ok, 'gathered': gathered,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

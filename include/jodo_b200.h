@@ -251,6 +251,16 @@ int jodo_ancestral_update(const float* x, const float* pred, const float* raw_po
                           const float* edge_mask, int B, int N, int F, int ch, float c_x, float c_pred, float sigma,
                           const float* coef_dev, float* x_new, float* x_mean, float* e_new, float* e_mean, void* stream);
 
+/* Fused update of the DPM-Solver++ singlestep for joint 2D & 3D generation (reference mix_dpm_solver.py:93-150 with the
+ * stochastic position update of :44-59): atoms and bonds  out = a start - b P0 - c (P1 - P0)  (P1 = null: the intermediate
+ * update, c unused), positions  out = cx pos_in + cp pos_pred + sigma z  with z the CoM-free masked normal built from the
+ * caller's raw draws [B,N,3] (pos_pred = the positions of P1 when given, else of P0).  coef_dev = device array
+ * {a, b, c, cx, cp, sigma}.  pos_in has row stride ld_pos (3 for a bare [B,N,3] tensor, F for the first columns of x). */
+int jodo_dpm_update(const float* x_start, const float* pos_in, int ld_pos, const float* pred0, const float* pred1,
+                    const float* raw_pos, const float* node_mask, const float* edge_start, const float* edge_pred0,
+                    const float* edge_pred1, int B, int N, int F, int ch, const float* coef_dev, float* x_out, float* edge_out,
+                    void* stream);
+
 /* edge-tile kernels (tcgen05 + TMEM + bulk-copied operand images); see the structs above */
 int jodo_edge_embed(const jodo_edge_embed_args* a, void* stream);
 int jodo_attn(const jodo_attn_args* a, void* stream);

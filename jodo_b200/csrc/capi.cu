@@ -161,6 +161,19 @@ int jodo_ancestral_update(const float* x, const float* pred, const float* raw_po
               "jodo_ancestral_update");
 }
 
+int jodo_dpm_update(const float* x_start, const float* pos_in, int ld_pos, const float* pred0, const float* pred1,
+                    const float* raw_pos, const float* node_mask, const float* edge_start, const float* edge_pred0,
+                    const float* edge_pred1, int B, int N, int F, int ch, const float* coef_dev, float* x_out, float* edge_out,
+                    void* stream) {
+  if (B <= 0 || N <= 0 || F <= 3 || ch <= 0 || ld_pos < 3) return fail("jodo_dpm_update: bad sizes");
+  if (!x_start || !pos_in || !pred0 || !raw_pos || !node_mask || !edge_start || !edge_pred0 || !coef_dev || !x_out || !edge_out)
+    return fail("jodo_dpm_update: null pointer");
+  if ((pred1 == nullptr) != (edge_pred1 == nullptr)) return fail("jodo_dpm_update: pred1 / edge_pred1 must come together");
+  JODO_LAUNCH(jodo::launch_dpm_update(x_start, pos_in, ld_pos, pred0, pred1, raw_pos, node_mask, edge_start, edge_pred0,
+                                      edge_pred1, B, N, F, ch, coef_dev, x_out, edge_out, S(stream)),
+              "jodo_dpm_update");
+}
+
 int jodo_pack_weights(const jodo_pack_item* items_dev, const int* blk_item_dev, const int* blk_first_dev, int n_blocks, void* stream) {
   if (n_blocks < 0 || (n_blocks > 0 && (!items_dev || !blk_item_dev || !blk_first_dev))) return fail("jodo_pack_weights: bad arguments");
   JODO_LAUNCH(jodo::launch_pack_items(items_dev, blk_item_dev, blk_first_dev, n_blocks, S(stream)), "jodo_pack_weights");

@@ -101,6 +101,11 @@ cudaError_t launch_ancestral_update(const float* x, const float* pred, const flo
                                     const float* coef, float* x_new, float* x_mean, float* e_new, float* e_mean,
                                     cudaStream_t st);
 
+cudaError_t launch_dpm_update(const float* x_start, const float* pos_in, int ld_pos, const float* p0, const float* p1,
+                              const float* raw_pos, const float* node_mask, const float* e_start, const float* e0,
+                              const float* e1, int B, int N, int F, int ch, const float* coef, float* x_out, float* e_out,
+                              cudaStream_t st);
+
 // ---- edge-tile kernels (edge_kernels.cu); all built for nf = 256 (ed = 64, 14+2 heads) --------------
 using EdgeEmbedArgs = ::jodo_edge_embed_args;
 cudaError_t launch_dist_flag(const EdgeEmbedArgs& a, cudaStream_t st);

@@ -347,15 +347,95 @@ class DPMSolverSinglestep:
         pos_end = self._position_update(pos_s1, pred1[..., :3], node_mask, s1, t_end, last_step)
         return torch.cat([pos_end, atom_end], dim=-1), edge_end
 
+    # -- fused update (jodo_dpm_update) ------------------------------------------------------------------
+    def step_coefficients(self, step, grid):
+        """Device tensors (cA[6], cB[6], nl[2]) of outer step `step` for the order-2 singlestep: {a, b, c, cx, cp, sigma} of
+        the intermediate update t_start -> s1 and of the final update -> t_end, and the noise levels of the two model
+        evaluations.  Every scalar is produced by the torch expressions of `_second_update` / `_position_update` on the
+        grid's device, so the fused path sees the values the torch path computes."""
+        ns = self.ns
+        t_start, t_end = grid[step], grid[step + 1]
+        last = step == len(grid) - 2
+        inner = torch.linspace(t_start.item(), t_end.item(), self.order + 1).to(grid.device)
+        lam = ns.marginal_lambda(inner)
+        r1 = (lam[1] - lam[0]) / (lam[-1] - lam[0])
+        lambda_start, lambda_end = ns.marginal_lambda(t_start), ns.marginal_lambda(t_end)
+        h = lambda_end - lambda_start
+        s1 = ns.inverse_lambda(lambda_start + r1 * h)
+        sigma_start, sigma_s1, sigma_end = ns.marginal_std(t_start), ns.marginal_std(s1), ns.marginal_std(t_end)
+        alpha_s1, alpha_end = torch.exp(ns.marginal_log_mean_coeff(s1)), torch.exp(ns.marginal_log_mean_coeff(t_end))
+        phi_11, phi_1 = torch.expm1(-r1 * h), torch.expm1(-h)
+
+        def pos_coef(ta, tb, no_noise):
+            alpha_t, sigma_t = ns.marginal_prob(ta)
+            alpha_s, sigma_s = ns.marginal_prob(tb)
+            alpha_ts = alpha_t / alpha_s
+            sigma2_ts = sigma_t ** 2 - alpha_ts ** 2 * sigma_s ** 2
+            sigma = torch.sqrt(sigma2_ts) * sigma_s / sigma_t
+            return (alpha_ts * sigma_s ** 2 / sigma_t ** 2, alpha_s * sigma2_ts / sigma_t ** 2,
+                    torch.zeros_like(sigma) if no_noise else sigma)
+
+        z = torch.zeros((), device=grid.device)
+        f = lambda v: torch.as_tensor(v, device=grid.device, dtype=torch.float32).reshape(())
+        cA = torch.stack([f(sigma_s1 / sigma_start), f(alpha_s1 * phi_11), z, *map(f, pos_coef(t_start, s1, False))])
+        cB = torch.stack([f(sigma_end / sigma_start), f(alpha_end * phi_1), f((0.5 / r1) * (alpha_end * phi_1)),
+                          *map(f, pos_coef(s1, t_end, last))])
+        nl = torch.stack([f(ns.get_noise_level(t_start)), f(ns.get_noise_level(s1))])
+        return cA, cB, nl
+
+    def _fused_outer(self, model, x, node_mask, edge_mask, edge_x, context, cA, cB, nl, last=False, draw_last=False):
+        """One order-2 outer step with both updates fused into jodo_dpm_update (two launches each instead of ~40 torch
+        kernels); the raw normal draws are the torch.randn calls of `position_noise`, in the same order."""
+        import ctypes
+        from . import _lib
+        bs, N, F_ = x.shape
+        ch = edge_x.shape[-1]
+        dev = x.device
+        c32 = lambda t: t.contiguous().float()
+        x, edge_x, nm = c32(x), c32(edge_x), c32(node_mask)
+        vec_t = torch.zeros(bs, device=dev)                                # ignored by the model (reference mol_gnn.py:534)
+
+        def evaluate(xx, ee, k):
+            pred, edge_pred = model(vec_t, xx, node_mask, edge_mask, edge_x=ee, noise_level=nl[k:k + 1].expand(bs),
+                                    cond_x=self.cond_x, cond_edge_x=self.cond_edge_x, context=context)
+            self.cond_x, self.cond_edge_x = pred, edge_pred
+            self.n_evals += 1
+            return c32(pred), c32(edge_pred)
+
+        def update(pos_in, p0, p1, e0, e1, raw, coef):
+            xo, eo = torch.empty_like(x), torch.empty_like(edge_x)
+            _lib.call('jodo_dpm_update', _lib.ptr(x), _lib.ptr(pos_in), ctypes.c_int(F_), _lib.ptr(p0), _lib.ptr(p1), _lib.ptr(raw),
+                      _lib.ptr(nm), _lib.ptr(edge_x), _lib.ptr(e0), _lib.ptr(e1), ctypes.c_int(bs), ctypes.c_int(N), ctypes.c_int(F_),
+                      ctypes.c_int(ch), _lib.ptr(coef), _lib.ptr(xo), _lib.ptr(eo), _lib.stream_ptr())
+            return xo, eo
+
+        pred, edge_pred = evaluate(x, edge_x, 0)
+        raw1 = torch.randn((bs, N, 3), device=dev, generator=self.generator)
+        self.n_noise += 1
+        x_s1, e_s1 = update(x, pred, None, edge_pred, None, raw1, cA)
+        pred1, edge_pred1 = evaluate(x_s1, e_s1, 1)
+        if last and not draw_last:
+            raw2 = raw1                                                   # sigma = 0: the reference draws nothing on the last step
+        else:
+            raw2 = torch.randn((bs, N, 3), device=dev, generator=self.generator)
+            self.n_noise += 1
+        return update(x_s1, pred, pred1, edge_pred, edge_pred1, raw2, cB)
+
     # -- driver ---------------------------------------------------------------------------------------
     def outer_grid(self, device):
         K = self.steps // self.order
         return torch.linspace(self.ns.T, 1. / self.ns.total_N, K + 1).to(device)
 
-    def outer_step(self, model, step, grid, x, node_mask, edge_mask, edge_x, context=None):
-        """One outer step (= `order` model evaluations), mix_dpm_solver.py:322-334."""
+    def outer_step(self, model, step, grid, x, node_mask, edge_mask, edge_x, context=None, fused=None):
+        """One outer step (= `order` model evaluations), mix_dpm_solver.py:322-334.  fused (default: CUDA tensors, order 2,
+        default generator path): both updates through jodo_dpm_update."""
         t_start, t_end = grid[step], grid[step + 1]
         last = step == len(grid) - 2
+        if fused is None:
+            fused = x.is_cuda and self.order == 2 and self.noise_fn is None
+        if fused:
+            cA, cB, nl = self.step_coefficients(step, grid)
+            return self._fused_outer(model, x, node_mask, edge_mask, edge_x, context, cA, cB, nl, last)
         if self.order == 1:
             return self._first_update(model, x, node_mask, edge_mask, edge_x, context, t_start, t_end, last)
         inner = torch.linspace(t_start.item(), t_end.item(), self.order + 1).to(x.device)
@@ -364,13 +444,80 @@ class DPMSolverSinglestep:
         return self._second_update(model, x, node_mask, edge_mask, edge_x, context, t_start, t_end, last, r1)
 
     @torch.no_grad()
-    def sampling(self, model, x, node_mask, edge_mask, edge_x, context=None):
+    def sampling(self, model, x, node_mask, edge_mask, edge_x, context=None, graph=False, fused=None):
+        """The whole chain (mix_dpm_solver.py:304-376).  graph=True (order 2, CUDA): outer step 0 runs eagerly (its first
+        evaluation has no self-conditioning), then one outer step is captured into a CUDA graph and replayed with per-step
+        coefficients -- same kernels, same torch.randn stream as the eager fused chain, except that the replayed last step
+        also draws (and multiplies by sigma = 0) the noise the eager chain skips."""
         self.cond_x = self.cond_edge_x = None
         self.n_noise = self.n_evals = 0
         grid = self.outer_grid(x.device)
-        for step in range(len(grid) - 1):
-            x, edge_x = self.outer_step(model, step, grid, x, node_mask, edge_mask, edge_x, context)
+        n = len(grid) - 1
+        if graph and n > 1:
+            x, edge_x = self.outer_step(model, 0, grid, x, node_mask, edge_mask, edge_x, context, fused=True)
+            gs = GraphedDPMStep(self, model, x, edge_x, node_mask, edge_mask, context, grid)
+            for step in range(1, n):
+                gs.run(step)
+            return gs.x.clone(), gs.edge_x.clone()
+        for step in range(n):
+            x, edge_x = self.outer_step(model, step, grid, x, node_mask, edge_mask, edge_x, context, fused=fused)
         return x, edge_x
+
+
+class GraphedDPMStep:
+    """One order-2 outer step of a DPMSolverSinglestep (two denoiser calls + two noise draws + two fused updates + hand-off
+    copies) captured into a CUDA graph.  ``run(step)`` writes that step's 14 coefficients into device memory and replays.
+    State: x, edge_x (in and out), cond_x / cond_edge_x (the solver's self-conditioning).  The solver must have run one
+    outer step with this model and these masks before (self-conditioned path, workspaces, plan)."""
+
+    def __init__(self, solver, model, x, edge_x, node_mask, edge_mask, context, grid):
+        if not x.is_cuda or solver.order != 2 or solver.noise_fn is not None or solver.generator is not None:
+            raise ValueError('the graph-captured outer step needs CUDA tensors, order 2 and the default CUDA generator')
+        if solver.cond_x is None:
+            raise ValueError('capture after the first outer step: the first evaluation of a chain is not self-conditioned')
+        from . import _lib
+        c32 = lambda t: t.contiguous().float()
+        n = len(grid) - 1
+        rows = [torch.cat(solver.step_coefficients(k, grid)) for k in range(n)]
+        self.table = torch.stack(rows)                                     # [steps, 14] = cA | cB | nl
+        self.coef = torch.zeros(14, device=x.device, dtype=torch.float32)
+        self.x, self.edge_x = c32(x).clone(), c32(edge_x).clone()
+        self.cond_x, self.cond_edge_x = c32(solver.cond_x).clone(), c32(solver.cond_edge_x).clone()
+        ctx = None if context is None else c32(context).clone()
+        self._static = (ctx, node_mask, edge_mask)                         # read by the captured kernels on every replay
+        self.solver = solver
+
+        def one_step():
+            solver.cond_x, solver.cond_edge_x = self.cond_x, self.cond_edge_x
+            xo, eo = solver._fused_outer(model, self.x, node_mask, edge_mask, self.edge_x, ctx, self.coef[0:6], self.coef[6:12],
+                                         self.coef[12:14], last=True, draw_last=True)
+            self.x.copy_(xo); self.edge_x.copy_(eo)
+            self.cond_x.copy_(solver.cond_x); self.cond_edge_x.copy_(solver.cond_edge_x)
+
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        l0, e0, z0 = _lib.LAUNCHES, solver.n_evals, solver.n_noise
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(self.graph, stream=side):
+                one_step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.launches_per_step = _lib.LAUNCHES - l0
+        solver.n_evals, solver.n_noise = e0, z0                            # the capture ran nothing
+        solver.cond_x, solver.cond_edge_x = self.cond_x, self.cond_edge_x
+        self._model, self._masks = model, (node_mask, edge_mask)
+        self._token = model.graph_token(node_mask, edge_mask) if hasattr(model, 'graph_token') else None
+
+    def run(self, step):
+        if self._token is not None:
+            hit, packed = self._model.graph_token(*self._masks)
+            if hit is not self._token[0] or packed is not self._token[1]:
+                raise RuntimeError('GraphedDPMStep: the model re-packed its weights or evicted the workspace this graph was '
+                                   'captured on; capture a new step')
+        self.coef.copy_(self.table[step])
+        self.graph.replay()
+        self.solver.n_evals += 2
+        self.solver.n_noise += 2
 
 
 # ---- multi-GPU: shard independent molecules, gather final samples --------------------------------
