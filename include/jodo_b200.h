@@ -251,6 +251,12 @@ int jodo_ancestral_update(const float* x, const float* pred, const float* raw_po
                           const float* edge_mask, int B, int N, int F, int ch, float c_x, float c_pred, float sigma,
                           const float* coef_dev, float* x_new, float* x_mean, float* e_new, float* e_mean, void* stream);
 
+/* Tensor-core operands are fp16 (the mantissa of tf32) and saturate at +-65504 instead of overflowing.  The kernels that write
+ * the operands with an unbounded range -- the per-atom GEMM outputs the edge kernels gather (q | k | v, hoisted input_lin and
+ * node2edge_lin parts, activation images) and the fp16 copy of the edge state -- count every clamped store.  Synchronises the
+ * current device; *out = clamped stores since the last reset. */
+int jodo_saturation_count(unsigned long long* out, int reset);
+
 /* Fused update of the DPM-Solver++ singlestep for joint 2D & 3D generation (reference mix_dpm_solver.py:93-150 with the
  * stochastic position update of :44-59): atoms and bonds  out = a start - b P0 - c (P1 - P0)  (P1 = null: the intermediate
  * update, c unused), positions  out = cx pos_in + cp pos_pred + sigma z  with z the CoM-free masked normal built from the

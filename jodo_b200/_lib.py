@@ -178,6 +178,13 @@ def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, au
     check(_account(tag or 'jodo_imglinear', lambda: f(ctypes.byref(a), st)), 'jodo_imglinear')
 
 
+def saturation_count(reset=True):
+    """fp16 operand stores clamped at +-65504 since the last reset (include/jodo_b200.h: jodo_saturation_count); synchronises."""
+    out = ctypes.c_ulonglong(0)
+    check(lib().jodo_saturation_count(ctypes.byref(out), ctypes.c_int(1 if reset else 0)), 'jodo_saturation_count')
+    return int(out.value)
+
+
 def dp(t):
     """raw device address (int) of a tensor, 0 for None"""
     return 0 if t is None else t.data_ptr()

@@ -70,6 +70,13 @@ def qm9_cond_multi():
     return c
 
 
+def qm9_sim():
+    """DGT_concat_sim (reference models/mol_gnn.py:949) on the QM9 config: the variant without adjacency heads."""
+    c = qm9_uncond()
+    c.model.name = 'DGT_concat_sim'
+    return c
+
+
 def geom_uncond(n_layers=8, nf=256):
     """configs/vpsde_geom_uncond_jodo.py; BASELINE config 3 quotes n_layers=8 (the file's
     default is 10), config 4 quotes nf=384."""
@@ -106,6 +113,7 @@ NAMED = {
     'qm9_uncond': qm9_uncond,
     'qm9_cond': qm9_cond,
     'qm9_cond_multi': qm9_cond_multi,
+    'qm9_sim': qm9_sim,
     'geom_l8': lambda: geom_uncond(8, 256),
     'geom_l10': lambda: geom_uncond(10, 256),
     'geom_large': lambda: geom_uncond(10, 384),

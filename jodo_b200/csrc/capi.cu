@@ -161,6 +161,16 @@ int jodo_ancestral_update(const float* x, const float* pred, const float* raw_po
               "jodo_ancestral_update");
 }
 
+int jodo_saturation_count(unsigned long long* out, int reset) {
+  unsigned int a = 0, b = 0;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = jodo::sat_count_imglinear(&a, reset != 0);
+  if (e == cudaSuccess) e = jodo::sat_count_edge_update(&b, reset != 0);
+  if (e != cudaSuccess) return cuda_fail(e, "jodo_saturation_count");
+  if (out) *out = (unsigned long long)a + b;
+  return JODO_OK;
+}
+
 int jodo_dpm_update(const float* x_start, const float* pos_in, int ld_pos, const float* pred0, const float* pred1,
                     const float* raw_pos, const float* node_mask, const float* edge_start, const float* edge_pred0,
                     const float* edge_pred1, int B, int N, int F, int ch, const float* coef_dev, float* x_out, float* edge_out,

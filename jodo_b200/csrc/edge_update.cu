@@ -17,6 +17,9 @@
 
 namespace jodo {
 
+// rows of the fp32 edge state whose fp16 operand copy saturated (see jodo_saturation_count)
+__device__ unsigned int g_sat_edge_update;
+
 __constant__ float c_eumod[384];       // row 0 of the edge AdaLN table: (shift, scale, gate)_msa, (shift, scale, gate)_mlp
 
 namespace {
@@ -172,6 +175,12 @@ __device__ __forceinline__ void eu_group_loop(const EdgeUpdateArgs& a, const Gro
         const float g = UNI ? c_eumod[5 * ED_ + col] : gv[i];
         e2[i] = r.valid ? fmaf(g, y[i] + a.b4[col], e2[i]) : 0.f;
       }
+      {                                            // the fp16 operand copy of the edge state clamps at +-65504: count it
+        float mx = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fabsf(e2[i]));
+        if (mx > 65504.f) atomicAdd(&g_sat_edge_update, 1u);
+      }
       float4* dst = reinterpret_cast<float4*>(e32 + (size_t)tile * E_TILE_BYTES) + (8 * HALF) * 128 + row;
 #pragma unroll
       for (int p = 0; p < 8; ++p) dst[p * 128] = make_float4(e2[4 * p], e2[4 * p + 1], e2[4 * p + 2], e2[4 * p + 3]);
@@ -266,6 +275,12 @@ __global__ void __launch_bounds__(EU_THREADS, 1) k_edge_update(const __grid_cons
 }
 
 }  // namespace
+
+cudaError_t sat_count_edge_update(unsigned int* out, bool reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_sat_edge_update, sizeof(unsigned int));
+  if (e == cudaSuccess && reset) { const unsigned int z = 0; e = cudaMemcpyToSymbol(g_sat_edge_update, &z, sizeof(z)); }
+  return e;
+}
 
 cudaError_t launch_edge_update(const EdgeUpdateArgs& a, int num_sms, cudaStream_t st) {
   if ((a.r != 2 && a.r != 4) || a.ce < 1 || a.ce > 16) return cudaErrorInvalidValue;

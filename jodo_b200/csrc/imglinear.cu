@@ -18,6 +18,10 @@
 
 namespace jodo {
 
+// fp16 operands written by this kernel that exceeded +-65504 and were clamped (per-atom operands the edge kernels gather:
+// q | k | v, the hoisted input_lin / node2edge_lin parts, activation images).  Read through jodo_saturation_count.
+__device__ unsigned int g_sat_imglinear;
+
 namespace {
 
 constexpr int IL_THREADS = 320;
@@ -216,6 +220,8 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
           if (!live) o = make_float4(0.f, 0.f, 0.f, 0.f);
           if (has32 && live) *reinterpret_cast<float4*>(C32 + (size_t)gr * ldc32 + col) = o;
           const uint2 hh = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+          if ((has16 || hasimg) && fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))) > 65504.f)
+            atomicAdd(&g_sat_imglinear, 1u);       // an fp16 operand saturated (cvt.satfinite clamps silently): count it
           if (has16 && live) {
             if (c16_pm) *reinterpret_cast<uint2*>(C16 + ((size_t)(col >> 3) * ldc16 + gr) * 8 + (col & 7)) = hh;
             else *reinterpret_cast<uint2*>(C16 + (size_t)gr * ldc16 + col) = hh;
@@ -234,6 +240,12 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
 }
 
 }  // namespace
+
+cudaError_t sat_count_imglinear(unsigned int* out, bool reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_sat_imglinear, sizeof(unsigned int));
+  if (e == cudaSuccess && reset) { const unsigned int z = 0; e = cudaMemcpyToSymbol(g_sat_imglinear, &z, sizeof(z)); }
+  return e;
+}
 
 const char* check_imglinear(const ImgLinearArgs& a) {
   if (a.M <= 0) return "imglinear: M <= 0";

@@ -55,6 +55,8 @@ using ImgLinearArgs = ::jodo_imglinear_args;
 const char* check_imglinear(const ImgLinearArgs& a);
 cudaError_t launch_imglinear(const ImgLinearArgs& a, int num_sms, cudaStream_t stream);
 
+cudaError_t sat_count_imglinear(unsigned int* out, bool reset);
+cudaError_t sat_count_edge_update(unsigned int* out, bool reset);
 cudaError_t launch_pack_items(const jodo_pack_item* items, const int* blk_item, const int* blk_first, int n_blocks, cudaStream_t st);
 
 // ---- per-molecule AdaLN table layout (floats from the start of a molecule's table row) -------------

@@ -373,7 +373,15 @@ class DGT_concat_2D(_DGTBase):
     VARIANT = '2d'
 
 
-MODELS = {'DGT_concat': DGT_concat, 'cond_DGT_concat': Cond_DGT_concat, 'DGT_concat_2D': DGT_concat_2D}
+class DGT_concat_sim(_DGTBase):
+    """B200-native drop-in for the reference ``DGT_concat_sim`` (models/mol_gnn.py:949-1124): ``EquivariantBlock`` (:97) with
+    ``Trans_Layer`` attention (models/layers.py:13: all heads learned, no adjacency heads) and ``CondEquiUpdate`` (:16: one
+    coord_mlp output).  Runs on the wide path with zero extra heads."""
+    VARIANT = 'sim'
+
+
+MODELS = {'DGT_concat': DGT_concat, 'cond_DGT_concat': Cond_DGT_concat, 'DGT_concat_2D': DGT_concat_2D,
+          'DGT_concat_sim': DGT_concat_sim}
 
 
 def create_model(config, device='cuda'):

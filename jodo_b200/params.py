@@ -73,7 +73,9 @@ def dims_from_config(config, variant=None) -> Dims:
     variant = variant_of(config, variant)
     D = int(m.nf)
     H = int(m.n_heads)
-    X = int(m.n_extra_heads)
+    # DGT_concat_sim (reference models/mol_gnn.py:949, EquivariantBlock :97 + Trans_Layer, models/layers.py:13): every head is a
+    # learned head of D / H channels, no adjacency heads, coord_mlp.2 has one output -- whatever config.model.n_extra_heads says
+    X = 0 if variant == 'sim' else int(m.n_extra_heads)
     S = H - X
     L = int(m.n_layers)
     ed = D // 4
@@ -92,8 +94,6 @@ def check_supported(config, variant=None):
     CLASS's (the registry may know it under any name, e.g. ``DGT_concat_b200``), not ``config.model.name``."""
     m = config.model
     variant = variant_of(config, variant)
-    if variant == 'sim':
-        raise NotImplementedError('jodo_b200: the DGT_concat_sim variant (reference models/mol_gnn.py:949) is not built')
     two_d = variant == '2d'
     need = dict(cond_time=True, softmax_inf=True, pred_data=True)
     if not two_d:
@@ -103,7 +103,7 @@ def check_supported(config, variant=None):
             raise ValueError(f'unsupported config.model.{k}={getattr(m, k)!r} (hot path covers {v!r})')
     if getattr(m, 'trans_name', 'TransMixLayer') != 'TransMixLayer':
         raise ValueError('unsupported trans_name')
-    if int(m.n_extra_heads) != (1 if two_d else 2):
+    if variant != 'sim' and int(m.n_extra_heads) != (1 if two_d else 2):
         raise ValueError('hot path covers n_extra_heads == 2 (1 for DGT_concat_2D), as in all reference configs')
 
 

@@ -114,7 +114,7 @@ def equi_update(sd, prefix, hout, pos, eout, df, st, extra, em):
     inv = _modulate(_ln(_lin(sd, prefix + '.input_lin', u)), shift[:, None, None, :], scale[:, None, None, :])
     inv = torch.tanh(F.linear(F.silu(_lin(sd, prefix + '.coord_mlp.0', inv)),
                               sd[prefix + '.coord_mlp.2.weight'].to(inv.dtype)))    # :82
-    adjs = torch.cat([torch.ones_like(extra[..., :1]), extra], dim=-1)             # :85-86
+    adjs = torch.cat([torch.ones_like(inv[..., :1]), extra], dim=-1)               # :85-86 (CondEquiUpdate, :16-49: just the 1)
     inv = (inv * adjs).mean(-1, keepdim=True)                         # :87
     return pos + (dl * inv * em).sum(dim=2)                           # scatter-add on row (:90-92)
 
@@ -200,6 +200,8 @@ def _mlp3(sd, name, x):
 def dims_of(config):
     m, d = config.model, config.data
     D, H, X = int(m.nf), int(m.n_heads), int(m.n_extra_heads)
+    if str(m.name).startswith('DGT_concat_sim'):          # Trans_Layer / CondEquiUpdate: no adjacency heads (mol_gnn.py:949, :97, :16)
+        X = 0
     S = H - X
     return dict(D=D, H=H, X=X, S=S, sc=D // S, C=D // H, L=int(m.n_layers), ed=D // 4)
 
@@ -237,6 +239,8 @@ def dgt_forward(sd, config, t, xh, node_mask, edge_mask, context=None, edge_x=No
     else:
         dist0 = cond_gbf(sd, 'dist_layer', d0, st)                    # :547-548
     extra = torch.cat([adj2d, adjsp], dim=-1) * em                    # :552 (only real edges exist)
+    if dims['X'] == 0:                                                # DGT_concat_sim (:1030-1124): no structural heads at all
+        extra = extra[..., :0]
     e = _lin(sd, 'edge_emb', torch.cat([edge_x, cond_edge_x, dist0], dim=-1))      # :553,557
     h = _lin(sd, 'node_emb', h)                                       # :556
     atom_hids, edge_hids = [h], [e]

@@ -41,6 +41,8 @@ CASES = {
                    dict(n_nodes=[12, 6], seed=7, self_cond=True), dict(seed=5, perturb=True)),
     'qm9_cond_multi': ('qm9_cond_multi', 'vpsde_qm9_cond_multi_jodo', {},
                        dict(n_nodes=[7, 15, 3], seed=10, self_cond=True, context=True), dict(seed=8, perturb=True)),
+    'qm9_sim': ('qm9_sim', 'vpsde_qm9_uncond_jodo', {'name': 'DGT_concat_sim'},
+                dict(n_nodes=[5, 16, 9, 22], seed=12, self_cond=True), dict(seed=9, perturb=True)),
     'moses_2d': ('moses_2d', 'vpsde_moses_2d_jodo', {}, dict(n_nodes=[8, 27, 19, 23], seed=8, self_cond=True),
                  dict(seed=6)),
     'moses_2d_first': ('moses_2d', 'vpsde_moses_2d_jodo', {}, dict(n_nodes=[20, 11], seed=9), dict(seed=7)),

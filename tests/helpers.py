@@ -8,7 +8,7 @@ from jodo_b200.params import param_spec, synth_state_dict
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 FORWARD_CASES = ['qm9_first', 'qm9_first_default_init', 'qm9_selfcond', 'qm9_cond_ctx', 'geom_l8',
-                 'geom_l10_first', 'geom_large', 'moses_2d', 'moses_2d_first', 'qm9_cond_multi']
+                 'geom_l10_first', 'geom_large', 'moses_2d', 'moses_2d_first', 'qm9_cond_multi', 'qm9_sim']
 
 
 def load_golden(name):

@@ -2,8 +2,8 @@
 outputs of the unmodified reference and against the oracle.
 
 Tolerance: the kernels feed the tensor cores tf32 operands (10-bit mantissa) with fp32 accumulation;
-everything else is fp32.  One forward stays within 5e-3 of the fp64 reference, relative to the largest
-magnitude of the compared tensor (measured: ~1e-3).  Masked entries must be exactly zero and the edge
+everything else is fp32.  One forward stays within 2e-3 of the fp64 reference, relative to the largest
+magnitude of the compared tensor (measured: 2e-4 .. 1e-3; 3e-3 for the bonds of geom_l8).  Masked entries must be exactly zero and the edge
 output exactly symmetric."""
 import pytest
 import torch
@@ -13,11 +13,13 @@ from stage_diag import run_case
 
 pytestmark = pytest.mark.gpu
 
-TOL = 5e-3
+TOL = 2e-3            # measured 2e-4 .. 1e-3 on one forward
+TOL_CASE = {'geom_l8': 3e-3}          # bonds of the r = 4, 31-atom fixture: 2.4e-3
 CASES = ['qm9_first', 'qm9_first_default_init', 'qm9_selfcond', 'qm9_cond_ctx', 'geom_l8', 'geom_l10_first',
          'geom_large',          # nf = 384: the wide path (jodo_b200/wide.py)
          'qm9_cond_multi',      # cond_DGT_concat with two properties (cond_ch = 2)
-         'moses_2d', 'moses_2d_first']          # DGT_concat_2D (no coordinates) on the wide path
+         'moses_2d', 'moses_2d_first',          # DGT_concat_2D (no coordinates) on the wide path
+         'qm9_sim']                             # DGT_concat_sim (no adjacency heads) on the wide path
 
 
 @pytest.mark.parametrize('name', CASES)
@@ -29,7 +31,7 @@ def test_forward_matches_reference(name):
     B, N = rx.shape[:2]
     x, e = x.cpu(), e.cpu()
     worst = {k: v for k, v in rep if k.startswith('out.')}
-    assert all(v < TOL for v in worst.values()), (worst, rep)
+    assert all(v < TOL_CASE.get(name, TOL) for v in worst.values()), (worst, rep)
     # integer-exact properties
     nm = inp['node_mask']
     em = inp['edge_mask'].reshape(B, N, N, 1)

@@ -69,6 +69,19 @@ def test_registry_create_model_strict_load_and_ema(cfg_file, name):
 
 
 @needs_ref
+def test_sim_variant_matches_reference_tree():
+    """DGT_concat_sim (models/mol_gnn.py:949) is selected by name on the reference's QM9 config file."""
+    ref = R.reference()
+    theirs = ref.model_utils.create_model(R.make_config('vpsde_qm9_uncond_jodo', 'cpu', model_name='DGT_concat_sim'))
+    ours = ref.model_utils.create_model(R.make_config('vpsde_qm9_uncond_jodo', 'cpu', model_name='DGT_concat_sim_b200'))
+    assert isinstance(ours.module, MODELS['DGT_concat_sim']) and ours.module.wide and ours.module.dims.X == 0
+    a = [(k, tuple(v.shape)) for k, v in theirs.state_dict().items()]
+    b = [(k, tuple(v.shape)) for k, v in ours.state_dict().items()]
+    assert a == b
+    ours.load_state_dict(theirs.state_dict(), strict=True)
+
+
+@needs_ref
 def test_unsupported_variant_raises_cleanly():
     ref = R.reference()
     # nf = 256 with another head layout must not reach the fused kernels (they hard-code 14 + 2 heads): wide path
