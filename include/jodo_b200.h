@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 8
+#define JODO_ABI_VERSION 9
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -292,7 +292,7 @@ typedef struct jodo_wide_embed_args {                   /* model-level edge inpu
 
 typedef struct jodo_wide_ln_args {                      /* LayerNorm(eps 1e-6) + modulation of a = x + gate (y[yi] + y2[y2i] + ybias) */
   int M, W, Kimg;                         /* rows; real columns (W % 8 == 0, <= 512); image columns (>= W, % 64 == 0) */
-  const float* x; int ldx;
+  const float* x; int ldx; const int* xi; /* x rows (gathered through xi when given: directed rows reading their pair's row) */
   const float* y; int ldy; const int* yi; /* optional addend rows (gathered through yi when given) */
   const float* y2; int ldy2; const int* y2i;
   const float* ybias;                     /* optional [W] */
@@ -310,6 +310,7 @@ typedef struct jodo_wide_attn_args {                    /* TransMixLayer message
   const uint16_t* qkv; int ldq, k_off, v_off;                  /* fp16 rows per atom: q at 0, k at k_off, v at v_off */
   const uint16_t* G; int ldg, g1_off;                          /* fp16 rows per edge: tanh(lin_edge0) at 0, tanh(lin_edge1) at g1_off */
   const uint8_t* extra;
+  const int* row_pair;                    /* optional: G and extra are stored per unordered pair; row_pair[row] is the pair row of edge row `row` */
   float* hnode;                           /* out [Nn, D] */
   int max_gl;                             /* largest partner count (sizes the per-CTA logit buffer; <= 255) */
 } jodo_wide_attn_args;
@@ -322,10 +323,11 @@ int jodo_wide_dist(const jodo_plan* p, const float* pos4, const float* tab, int 
 int jodo_wide_ln(const jodo_wide_ln_args* a, void* stream);
 int jodo_wide_attn(const jodo_wide_attn_args* a, void* stream);
 int jodo_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
-                       const uint8_t* extra, int X, float coord_scale, const float* pos_in4, float* pos_out4, int Nn,
-                       void* stream);                           /* mol_gnn.py:82-92 */
+                       const uint8_t* extra, const int* row_pair, int X, float coord_scale, const float* pos_in4, float* pos_out4,
+                       int Nn, void* stream);                   /* mol_gnn.py:82-92; extra[row_pair[row]] when row_pair is given */
 int jodo_wide_head_out(const jodo_plan* p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,
-                       float* out_dense, void* stream);         /* mol_gnn.py:574-578 */
+                       int both, float* out_dense, void* stream);   /* mol_gnn.py:574-578; both != 0: p is the pair plan, every
+                                                                     row writes e_hat[b, i, j] and e_hat[b, j, i] */
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 8:
+        if _lib.jodo_abi_version() != 9:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -151,7 +151,7 @@ class WideEmbedArgs(ctypes.Structure):
 
 
 class WideLnArgs(ctypes.Structure):
-    _fields_ = [('M', _I), ('W', _I), ('Kimg', _I), ('x', _P), ('ldx', _I), ('y', _P), ('ldy', _I), ('yi', _P),
+    _fields_ = [('M', _I), ('W', _I), ('Kimg', _I), ('x', _P), ('ldx', _I), ('xi', _P), ('y', _P), ('ldy', _I), ('yi', _P),
                 ('y2', _P), ('ldy2', _I), ('y2i', _P), ('ybias', _P), ('tab', _P), ('ld_tab', _I), ('row_mol', _P),
                 ('off_gate', _I), ('off_shift', _I), ('off_scale', _I), ('valid', _P), ('out32', _P), ('ldo', _I),
                 ('out_img', _P), ('y_img', _P), ('x_f16', _I), ('y_f16', _I)]
@@ -160,7 +160,7 @@ class WideLnArgs(ctypes.Structure):
 class WideAttnArgs(ctypes.Structure):
     _fields_ = [('Nn', _I), ('D', _I), ('H', _I), ('X', _I), ('sc', _I), ('grp_row0', _P), ('grp_len', _P), ('row_j', _P),
                 ('qkv', _P), ('ldq', _I), ('k_off', _I), ('v_off', _I), ('G', _P), ('ldg', _I), ('g1_off', _I),
-                ('extra', _P), ('hnode', _P), ('max_gl', _I)]
+                ('extra', _P), ('row_pair', _P), ('hnode', _P), ('max_gl', _I)]
 
 
 def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None, row_mol=None,

@@ -123,12 +123,6 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
       }
       st_rowh<32>(A0, row, 0, 4 * HALF, df);       // padding rows: finite garbage, masked by alpha = 0 below
     }
-    {
-      const int nt_ = tile + 2 < c.tile1 ? tile + 2 : tile;
-      rn = load_row(a.p, nt_, row);
-      ngn = a.p.tile_ngroups[nt_];
-      exn = a.extra[rn.pr];
-    }
     cp_async_wait_all();                                 // this thread's share of the gathered e chunk has landed
     fence_async_smem();
     at_group_sync(c.grp);
@@ -151,8 +145,6 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
         ind_prev = 0xFFFFFFFFu;
       }
     }
-    if (tile + 2 < c.tile1)                             // the e chunk is consumed: gather this group's next tile (rn)
-      gather_e16_warp<16>(A0 + CHUNK_BYTES_A, a.e16, 32 * rq, 16 * HALF, rn.valid, rn.pr, lane);
 
     // ---- en = LN(e1) * (1 + scale_msa) + shift_msa  -> A0 chunk 0
     {
@@ -209,15 +201,18 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
         }
         float acc[16];
         tmem_ld16(tmem_addr(tm, 128 * HALF + 16 * ch), acc);
+        // q k straight from the packed fp16 pairs (FHFMA: exact fp32 product of two halves), no unpacking
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          float qf[8], kf[8];
-          unpack8(qc.u[i], qf);
-          unpack8(kc.u[i], kf);
+          const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&qc.u[i]);
+          const uint32_t* k2 = reinterpret_cast<const uint32_t*>(&kc.u[i]);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col = 16 * ch + 8 * i + e;
-            if (col < HQ) lg[col / SC] = fmaf(qf[e] * kf[e], tanh_fast(acc[8 * i + e]), lg[col / SC]);
+          for (int w = 0; w < 4; ++w) {
+            const int col = 16 * ch + 8 * i + 2 * w;          // SC and HQ are even: a pair never straddles two heads
+            if (col < HQ) {
+              lg[col / SC] = fmaf(fhfma_lo(q2[w], k2[w], 0.f), tanh_fast(acc[8 * i + 2 * w]), lg[col / SC]);
+              lg[col / SC] = fmaf(fhfma_hi(q2[w], k2[w], 0.f), tanh_fast(acc[8 * i + 2 * w + 1]), lg[col / SC]);
+            }
           }
         }
         if (ch < 7) { qc = qn; kc = kn; }
@@ -228,6 +223,13 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
 #pragma unroll
       for (int s = 0; s < 7; ++s) LG[row * 17 + 2 + 7 * HALF + s] = lg[s] * 0.25f;
     }
+    // row metadata of this group's next tile: loaded here (after the register-hungry logit loop, so that the prefetch is
+    // not spilled) and used below for the gather of the next e chunk, which MMA1 of this tile has long consumed
+    {
+      const int nt_ = tile + 2 < c.tile1 ? tile + 2 : tile;
+      rn = load_row(a.p, nt_, row);
+      ngn = a.p.tile_ngroups[nt_];
+    }
     at_group_sync(c.grp);                                  // logits visible; every g0 read done
     if (lt == 0) {
       mma_tile_h(tm, smem_u32(A0), smem_u32(c.W1), 256, 1, false);                  // g1 pre-activation, under the softmax
@@ -237,6 +239,9 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
     const uint4* vb = static_cast<const uint4*>(a.qkv) + (size_t)(64 + 16 * HALF) * a.ldq + r.j;
     H16 vc;
     vc.u[0] = __ldg(vb); vc.u[1] = __ldg(vb + a.ldq);
+    exn = a.extra[rn.pr];
+    if (tile + 2 < c.tile1)
+      gather_e16_warp<16>(A0 + CHUNK_BYTES_A, a.e16, 32 * rq, 16 * HALF, rn.valid, rn.pr, lane);
     // (group, head): max, exp in place, 1 / (sum + 1e-16)      (PyG softmax, models/layers.py:178).
     // Four lanes share one (group, head) and interleave its rows; ng * 64 is a whole number of warps.
     // Long groups (>= 32 rows) sum in four interleaved partial sums combined as (s0 + s1) + (s2 + s3), short ones
@@ -312,14 +317,18 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
         float acc[16];
         tmem_ld16(tmem_addr(tm, 128 * HALF + 16 * ch), acc);
         const float al = p == 0 ? alpha[cc] : alpha[4 + cc];
+        // msg = (v alpha) tanh(g1) on packed pairs: v is fp16 already, the message image is fp16 anyway
+        const uint32_t al2 = pack_h2(al, al);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          float vf[8];
-          unpack8(vc.u[i], vf);
+          const uint32_t* v2 = reinterpret_cast<const uint32_t*>(&vc.u[i]);
+          uint4 o;
+          uint32_t* o2 = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[8 * i + e] = (vf[e] * al) * tanh_fast(acc[8 * i + e]);
+          for (int w = 0; w < 4; ++w)
+            o2[w] = mul_h2(mul_h2(v2[w], al2), pack_h2(tanh_fast(acc[8 * i + 2 * w]), tanh_fast(acc[8 * i + 2 * w + 1])));
+          *reinterpret_cast<uint4*>(MI + img_piece(row, 0, 2 * cc + i, CHUNK_BYTES_A)) = o;
         }
-        st_rowh<16>(MI, row, 0, 2 * cc, acc);
         if (ch < 7) vc = vn;
       }
       fence_async_smem();

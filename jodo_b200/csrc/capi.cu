@@ -288,19 +288,19 @@ int jodo_wide_attn(const jodo_wide_attn_args* a, void* stream) {
   JODO_LAUNCH(jodo::launch_wide_attn(*a, S(stream)), "jodo_wide_attn");
 }
 int jodo_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
-                       const uint8_t* extra, int X, float coord_scale, const float* pos_in4, float* pos_out4, int Nn,
-                       void* stream) {
+                       const uint8_t* extra, const int* row_pair, int X, float coord_scale, const float* pos_in4, float* pos_out4,
+                       int Nn, void* stream) {
   if (!grp_row0 || !grp_len || !row_j || !c3 || !extra || !pos_in4 || !pos_out4 || Nn <= 0 || X < 0 || X > 8 || ldc < 1 + X)
     return fail("jodo_wide_equi_out: bad arguments");
-  JODO_LAUNCH(jodo::launch_wide_equi_out(grp_row0, grp_len, row_j, c3, ldc, extra, X, coord_scale, pos_in4, pos_out4, Nn, S(stream)),
+  JODO_LAUNCH(jodo::launch_wide_equi_out(grp_row0, grp_len, row_j, c3, ldc, extra, row_pair, X, coord_scale, pos_in4, pos_out4, Nn, S(stream)),
               "jodo_wide_equi_out");
 }
 int jodo_wide_head_out(const jodo_plan* p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,
-                       float* out_dense, void* stream) {
+                       int both, float* out_dense, void* stream) {
   if (!p) return fail("jodo_wide_head_out: null plan");
   if (const char* m = check_plan(*p)) return fail(m);
   if (!x || !w4 || !b4 || !out_dense || hw <= 0 || ch < 1 || ldx < 2 * hw) return fail("jodo_wide_head_out: bad arguments");
-  JODO_LAUNCH(jodo::launch_wide_head_out(*p, x, ldx, hw, w4, b4, ch, out_dense, S(stream)), "jodo_wide_head_out");
+  JODO_LAUNCH(jodo::launch_wide_head_out(*p, x, ldx, hw, w4, b4, ch, both, out_dense, S(stream)), "jodo_wide_head_out");
 }
 
 }  // extern "C"

@@ -295,6 +295,50 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return r;
 }
 
+// ---------------------------------------------------------------- packed-half CUDA-core math
+// The epilogues that feed fp16 operand images anyway do their elementwise math on fp16 pairs: one MUFU / FMA-pipe
+// instruction per two elements, and fp16 x fp16 + fp32 accumulation in one instruction (FHFMA, sm_100: fma.rn.f32.f16)
+// instead of two conversions and an FFMA.
+__device__ __forceinline__ uint32_t tanh_h2(uint32_t x) {
+  uint32_t y;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t mul_h2(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
+  return y;
+}
+__device__ __forceinline__ uint32_t fma_h2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t y;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(y) : "r"(a), "r"(b), "r"(c));
+  return y;
+}
+// c + a.lo * b.lo  /  c + a.hi * b.hi, products and sums in fp32
+__device__ __forceinline__ float fhfma_lo(uint32_t a, uint32_t b, float c) {
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.f16 %0, al, bl, %3;\n\t}"
+      : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fhfma_hi(uint32_t a, uint32_t b, float c) {
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.f16 %0, ah, bh, %3;\n\t}"
+      : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  return d;
+}
+// c + a.lo / c + a.hi (fp32 sum of an fp32 and one half of a packed pair: FHADD)
+__device__ __forceinline__ float fhadd_lo(uint32_t a, float c) {
+  float d;
+  asm("{\n\t.reg .b16 al, ah;\n\tmov.b32 {al, ah}, %1;\n\tadd.rn.f32.f16 %0, al, %2;\n\t}" : "=f"(d) : "r"(a), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fhadd_hi(uint32_t a, float c) {
+  float d;
+  asm("{\n\t.reg .b16 al, ah;\n\tmov.b32 {al, ah}, %1;\n\tadd.rn.f32.f16 %0, ah, %2;\n\t}" : "=f"(d) : "r"(a), "f"(c));
+  return d;
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2) and clusters
 // A cluster of two CTAs on the two SMs of a TPC runs one tcgen05.mma over M = 256 rows: each CTA supplies the A operand of
 // its own 128 rows and HALF of the B operand (N / 2 rows of W at the same shared-memory offset in both CTAs); the

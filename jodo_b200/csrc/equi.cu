@@ -255,14 +255,13 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
         tmem_ld16(tmem_addr(tm_x, cb + 16 * q), x);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          float uf[8];
-          unpack8(ab[2 * q + i], uf);
+          const uint32_t* u2 = reinterpret_cast<const uint32_t*>(&ab[2 * q + i]);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float v = x[8 * i + e] + uf[e];
-            x[8 * i + e] = v;
-            s1 += v;
-            s2 = fmaf(v, v, s2);
+          for (int w = 0; w < 4; ++w) {              // fp32 accumulator + one half of the packed pair in one instruction (FHADD)
+            const float v0 = fhadd_lo(u2[w], x[8 * i + 2 * w]), v1 = fhadd_hi(u2[w], x[8 * i + 2 * w + 1]);
+            x[8 * i + 2 * w] = v0; x[8 * i + 2 * w + 1] = v1;
+            s1 += v0; s2 = fmaf(v0, v0, s2);
+            s1 += v1; s2 = fmaf(v1, v1, s2);
           }
         }
         tmem_st16(tmem_addr(tm_x, cb + 16 * q), x);

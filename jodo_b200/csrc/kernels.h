@@ -138,9 +138,9 @@ cudaError_t launch_wide_dist(const Plan& p, const float* pos, const float* tab, 
 cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st);
 cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st);
 cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
-                                 const uint8_t* extra, int X, float coord_scale, const float* pos_in, float* pos_out, int Nn,
-                                 cudaStream_t st);
+                                 const uint8_t* extra, const int* row_pair, int X, float coord_scale, const float* pos_in,
+                                 float* pos_out, int Nn, cudaStream_t st);
 cudaError_t launch_wide_head_out(const Plan& p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,
-                                 float* out_dense, cudaStream_t st);
+                                 int both, float* out_dense, cudaStream_t st);
 
 }  // namespace jodo

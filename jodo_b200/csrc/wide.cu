@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
   const int mol = inb ? __ldg(a.row_mol + row) : 0;
   const int iy = (inb && has_y) ? (a.yi ? __ldg(a.yi + row) : row) : 0;
   const int iy2 = (inb && has_y2) ? (a.y2i ? __ldg(a.y2i + row) : row) : 0;
+  const int ix = (inb && a.xi) ? max(__ldg(a.xi + row), 0) : row;        // padding rows carry -1
   const bool live = inb && vld >= 0;
   if (!live) {
     for (int p = lane; p < npk; p += LANES) {
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
     if (p < npw) {
-      wload8x(a.x, x16, row, a.ldx, 8 * p, v[k]);
+      wload8x(a.x, x16, ix, a.ldx, 8 * p, v[k]);
       if (has_y) {
         float y[8];
         wload8x(a.y, y16, iy, a.ldy, 8 * p, y);
@@ -326,11 +327,15 @@ __global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
   const float inv = rsqrtf((float)C);
   const uint16_t* qrow = a.qkv + (size_t)g * a.ldq;
   for (int c = tid; c < qkp; c += WA_THREADS) qs[c] = c < qk ? h2f(qrow[c]) * inv : 0.f;
-  for (int i = tid; i < gl; i += WA_THREADS) js[i] = a.row_j[row0 + i];
+  int* ps = js + a.max_gl;                  // [max_gl] row of G / extra: the edge row itself or its pair's row
+  for (int i = tid; i < gl; i += WA_THREADS) {
+    js[i] = a.row_j[row0 + i];
+    ps[i] = a.row_pair ? a.row_pair[row0 + i] : row0 + i;
+  }
   __syncthreads();
   for (int i = warp; i < gl; i += 4) {
     const __half2* krow = reinterpret_cast<const __half2*>(a.qkv + (size_t)js[i] * a.ldq + a.k_off);
-    const __half2* grow = reinterpret_cast<const __half2*>(a.G + (size_t)(row0 + i) * a.ldg);
+    const __half2* grow = reinterpret_cast<const __half2*>(a.G + (size_t)ps[i] * a.ldg);
     float* pr = prod + warp * qkp;
     for (int c = lane; c < ((qk + 1) >> 1); c += 32) {            // an odd qk reads one zero pad column of the rows
       const float2 kk = __half22float2(krow[c]), gg = __half22float2(grow[c]);
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
       lg[i * H + X + lane] = s;
     } else if (lane - S < X) {
       const int x = lane - S;
-      lg[i * H + x] = ((a.extra[row0 + i] >> x) & 1) ? 1.0f : -1e10f;
+      lg[i * H + x] = ((a.extra[ps[i]] >> x) & 1) ? 1.0f : -1e10f;
     }
     __syncwarp();
   }
@@ -363,7 +368,7 @@ __global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < gl; ++i) {
       const uint2 vu = *reinterpret_cast<const uint2*>(a.qkv + (size_t)js[i] * a.ldq + a.v_off + c);
-      const uint2 gu = *reinterpret_cast<const uint2*>(a.G + (size_t)(row0 + i) * a.ldg + a.g1_off + c);
+      const uint2 gu = *reinterpret_cast<const uint2*>(a.G + (size_t)ps[i] * a.ldg + a.g1_off + c);
       const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vu.x)), v1 = __half22float2(*reinterpret_cast<const __half2*>(&vu.y));
       const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&gu.x)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&gu.y));
       const float al = lg[i * H + h];
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
 // pos_r += sum_c (pos_r - pos_c) / max(|.|, 1e-8) * scale * inv.  One thread per atom.
 __global__ void k_wide_equi_out(const int* __restrict__ grp_row0, const int* __restrict__ grp_len,
                                 const int* __restrict__ row_j, const float* __restrict__ c3, int ldc,
-                                const uint8_t* __restrict__ extra, int X, float coord_scale,
+                                const uint8_t* __restrict__ extra, const int* __restrict__ row_pair, int X, float coord_scale,
                                 const float4* __restrict__ pos_in, float4* __restrict__ pos_out, int Nn) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= Nn) return;
@@ -391,7 +396,7 @@ __global__ void k_wide_equi_out(const int* __restrict__ grp_row0, const int* __r
     const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
     const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
     const float* c = c3 + (size_t)R * ldc;
-    const uint8_t bits = extra[R];
+    const uint8_t bits = extra[row_pair ? row_pair[R] : R];
     float inv = tanhf(c[0]);
     for (int x = 0; x < X; ++x) inv += ((bits >> x) & 1) ? tanhf(c[1 + x]) : 0.f;
     const float f = coord_scale * inv / ((float)(1 + X) * nrm);
@@ -403,7 +408,7 @@ __global__ void k_wide_equi_out(const int* __restrict__ grp_row0, const int* __r
 // ---- last layer of edge_exist_mlp / edge_type_mlp (models/mol_gnn.py:574-578) + scatter to the dense grid.
 // x[row] = [SiLU hidden of exist (hw) | SiLU hidden of type (hw)]; w4 [ch][hw]: row 0 reads the first half.
 __global__ void k_wide_head_out(Plan p, const float* __restrict__ x, int ldx, int hw, const float* __restrict__ w4,
-                                const float* __restrict__ b4, int ch, float* __restrict__ out_dense) {
+                                const float* __restrict__ b4, int ch, int both, float* __restrict__ out_dense) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= p.n_tiles * 128) return;
   const int g = p.row_g[row];
@@ -412,12 +417,14 @@ __global__ void k_wide_head_out(Plan p, const float* __restrict__ x, int ldx, in
   const int dg = p.node_dense[g], dj = p.node_dense[p.row_j[row]];
   const int b = dg / N, ig = dg - b * N, ij = dj - b * N;
   float* dst = out_dense + (((size_t)b * N + ij) * N + ig) * ch;            // row (g, j) is the edge r = j -> c = g
+  float* dst2 = out_dense + (((size_t)b * N + ig) * N + ij) * ch;           // pair plan: the same value is e_hat[b, i, j] too
   const float* xr = x + (size_t)row * ldx;
   for (int k = 0; k < ch; ++k) {
     const float* xs = xr + (k == 0 ? 0 : hw);
     float o = b4[k];
     for (int i = 0; i < hw; ++i) o = fmaf(xs[i], w4[k * hw + i], o);
     dst[k] = o;
+    if (both) dst2[k] = o;
   }
 }
 
@@ -465,21 +472,21 @@ cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st) {
 }
 cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st) {
   const int S = a.H - a.X, qkp = (S * a.sc + 31) & ~31;
-  const size_t smem = (size_t)(5 * qkp + a.max_gl * a.H) * sizeof(float) + a.max_gl * sizeof(int);
+  const size_t smem = (size_t)(5 * qkp + a.max_gl * a.H) * sizeof(float) + 2 * a.max_gl * sizeof(int);
   k_wide_attn<<<a.Nn, WA_THREADS, smem, st>>>(a);
   return WIDE_OK();
 }
 cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
-                                 const uint8_t* extra, int X, float coord_scale, const float* pos_in, float* pos_out, int Nn,
-                                 cudaStream_t st) {
-  k_wide_equi_out<<<(Nn + 127) / 128, 128, 0, st>>>(grp_row0, grp_len, row_j, c3, ldc, extra, X, coord_scale,
+                                 const uint8_t* extra, const int* row_pair, int X, float coord_scale, const float* pos_in,
+                                 float* pos_out, int Nn, cudaStream_t st) {
+  k_wide_equi_out<<<(Nn + 127) / 128, 128, 0, st>>>(grp_row0, grp_len, row_j, c3, ldc, extra, row_pair, X, coord_scale,
                                                     reinterpret_cast<const float4*>(pos_in), reinterpret_cast<float4*>(pos_out), Nn);
   return WIDE_OK();
 }
 cudaError_t launch_wide_head_out(const Plan& p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,
-                                 float* out_dense, cudaStream_t st) {
+                                 int both, float* out_dense, cudaStream_t st) {
   const int R = p.n_tiles * 128;
-  k_wide_head_out<<<(R + 127) / 128, 128, 0, st>>>(p, x, ldx, hw, w4, b4, ch, out_dense);
+  k_wide_head_out<<<(R + 127) / 128, 128, 0, st>>>(p, x, ldx, hw, w4, b4, ch, both, out_dense);
   return WIDE_OK();
 }
 

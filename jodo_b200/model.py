@@ -244,7 +244,7 @@ class _DGTBase(nn.Module):
         if cond_x is not None:
             cond_x, cond_edge_x = c32(cond_x), c32(cond_edge_x)
         if use_wide:
-            return wide.forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_edge_x, context)
+            return wide.forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, cond_edge_x, context)
         D, T, ld_tab = d.D, d.T, meta['ld_tab']
 
         def lin(name, A, C, M=None, **kw):

@@ -138,33 +138,38 @@ class WideWorkspace:
         if not d.two_d:
             self.AB = torch.zeros(Nn, 2 * D, device=dev, dtype=torch.float16)    # hoisted input_lin parts, gathered per edge
         self.n1, self.n2, self.ap = f(Nn, D), f(Nn, meta['npred2']['N']), f(Nn, meta['npred4']['N'])
-        # per edge row
-        self.A0 = eimg(64 if d.two_d else EDP)
+        # The edge state and everything computed from it alone is symmetric in (r, c): those buffers
+        # have one row per UNORDERED pair (plan.pair_*), RP rows; the directed rows (R) read them through plan.row_pair.
+        # Only the coordinate branch behind input_lin (whose h[row] / h[col] parts are ordered) runs per directed row.
+        RP = plan.n_pair_tiles * 128
+        self.RP = RP
+        pimg = lambda k: torch.zeros(RP * k, device=dev, dtype=torch.float16)
+        self.A0 = pimg(64 if d.two_d else EDP)
         if not d.two_d:
-            self.A1, self.A4 = eimg(2 * d.ed), eimg(2 * d.ed)
-            self.e1 = zf(R, EDP)
-        self.e32, self.e2 = zf(R, EDP), zf(R, EDP)
-        self.en_img, self.e2_img = eimg(EDP), eimg(EDP)
+            self.A1, self.A4 = pimg(2 * d.ed), pimg(2 * d.ed)
+            self.e1 = zf(RP, EDP)
+        self.e32, self.e2 = zf(RP, EDP), zf(RP, EDP)
+        self.en_img, self.e2_img = pimg(EDP), pimg(EDP)
         self.ldg = meta['qkp'] + D
-        self.G = torch.zeros(R, self.ldg, device=dev, dtype=torch.float16)
-        self.f3_img = eimg(meta['f3p'])
-        self.EH = eimg((d.L + 1) * EDP)                       # operand of the edge heads: [e0 | e_1 | .. | e_L]
-        self.H_img = eimg(meta['hp'])
-        self.X2 = zf(R, EDP)
+        self.G = torch.zeros(RP, self.ldg, device=dev, dtype=torch.float16)
+        self.f3_img = pimg(meta['f3p'])
+        self.EH = pimg((d.L + 1) * EDP)                       # operand of the edge heads: [e0 | e_1 | .. | e_L]
+        self.H_img = pimg(meta['hp'])
+        self.X2 = zf(RP, EDP)
         if not d.two_d:
-            self.U = torch.zeros(R, D, device=dev, dtype=torch.float16)      # input_lin edge part (pre-LayerNorm)
-            self.u_img, self.c0_img = eimg(D), eimg(D)
+            self.U = torch.zeros(RP, D, device=dev, dtype=torch.float16)     # input_lin edge part (pre-LayerNorm), per pair
+            self.u_img, self.c0_img = eimg(D), eimg(D)                       # per directed row
             self.c3 = zf(R, 64)
         self.node_dense_l = plan.node_dense.long()
-        self.extra = torch.zeros(R, device=dev, dtype=torch.uint8)
+        self.extra = torch.zeros(RP, device=dev, dtype=torch.uint8)
         self.flags = torch.zeros(4, device=dev, dtype=torch.int32)            # [0] dist flag, [1] nan flag
         self.grp_row0, self.grp_len = plan.grp_row0, plan.grp_len
 
 
-def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_edge_x, context):
+def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, cond_edge_x, context):
     """The wide-path launch sequence of one denoiser evaluation (called by model._DGTBase.forward)."""
     d, meta = self.dims, pk.meta
-    B, N, Nn, R = plan.B, plan.N, plan.Nn, ws.R
+    B, N, Nn, R, RP = plan.B, plan.N, plan.Nn, ws.R, ws.RP
     D, T, ed, ld_tab = d.D, d.T, d.ed, meta['ld_tab']
     st = _lib.stream_ptr()
     P, dp = _lib.ptr, _lib.dp
@@ -181,9 +186,9 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
                        tag='jodo_imglinear:' + name.split('.')[-1], **kw)
 
     def ln(M, W, K, x, tab_off, row_mol, out_img=None, out32=None, y=None, yi=None, y2=None, y2i=None, ybias=None,
-           gate=-1, valid=None, y_img=None, tag=''):
+           gate=-1, valid=None, y_img=None, xi=None, tag=''):
         shift, scale = tab_off
-        a = _lib.WideLnArgs(M, W, K, dp(x), x.stride(0), dp(y), 0 if y is None else y.stride(0), dp(yi),
+        a = _lib.WideLnArgs(M, W, K, dp(x), x.stride(0), dp(xi), dp(y), 0 if y is None else y.stride(0), dp(yi),
                             dp(y2), 0 if y2 is None else y2.stride(0), dp(y2i), dp(ybias), dp(ws.tab), ld_tab, dp(row_mol),
                             gate, shift, scale, dp(valid), dp(out32), 0 if out32 is None else out32.stride(0),
                             dp(out_img), dp(y_img), int(x.dtype == torch.float16),
@@ -213,18 +218,19 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         _lib.call('jodo_gather_nodes', P(xh), P(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin), P(ws.xin), P(ws.pos[0]), None, st)
     lin('node_emb', ws.xin, ws.ah[:, :D])
     # ---- per edge: model-level embedding, adjacency heads
-    ea = _lib.WideEmbedArgs(ps, dp(edge_x), dp(cond_edge_x), 0 if d.two_d else dp(cond_x), d.ch, d.inn,
+    # ---- per unordered pair: model-level embedding, adjacency heads
+    ea = _lib.WideEmbedArgs(pps, dp(edge_x), dp(cond_edge_x), 0 if d.two_d else dp(cond_x), d.ch, d.inn,
                             0 if d.two_d else ed, self.edge_th, self.spatial_cut_off, dp(ws.flags), dp(ws.tab), ld_tab,
                             pk.ptr('gbf'), EDP, dp(ws.A0), 64 if d.two_d else EDP, dp(ws.extra))
     _lib.call('jodo_wide_embed_in', ctypes.byref(ea), st)
-    ilin('edge_emb', ws.A0, R, C32=ws.e32)
+    ilin('edge_emb', ws.A0, RP, C32=ws.e32)
     K2 = 2 * ed
     KH = (d.L + 1) * EDP
     if d.two_d:
-        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.EH), _c(KH), _c(0), None, _c(0),
+        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(RP), _c(ed), P(plan.pair_i), P(ws.EH), _c(KH), _c(0), None, _c(0),
                   _c(0), None, _c(0), _c(0), st)
     else:
-        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.A1), _c(K2), _c(ed), P(ws.EH),
+        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(RP), _c(ed), P(plan.pair_i), P(ws.A1), _c(K2), _c(ed), P(ws.EH),
                   _c(KH), _c(0), None, _c(0), _c(0), st)
 
     h = ws.ah[:, :D]
@@ -237,19 +243,19 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         hout = ws.h[l & 1]
         # distance features into the [dist | e] and [e | dist] operands; block edge_emb; norm1_edge; g0 | g1
         if d.two_d:                               # EquivariantMixBlock_2D: norm1_edge on the block input (mol_gnn.py:391)
-            ln(R, ed, EDP, ws.e32, (oe, oe + ed), plan.row_mol, out_img=ws.en_img, valid=plan.row_g, tag='e1')
+            ln(RP, ed, EDP, ws.e32, (oe, oe + ed), plan.pair_mol, out_img=ws.en_img, valid=plan.pair_i, tag='e1')
         else:
-            _lib.call('jodo_wide_dist', ctypes.byref(ps), P(pin), P(ws.tab), _c(ld_tab), _c(og), P(pk[p + 'gbf']), _c(EDP),
+            _lib.call('jodo_wide_dist', ctypes.byref(pps), P(pin), P(ws.tab), _c(ld_tab), _c(og), P(pk[p + 'gbf']), _c(EDP),
                       _c(ed), P(ws.A1), _c(K2), _c(0), P(ws.A4), _c(K2), _c(ed), st)
-            ilin(p + 'emb', ws.A1, R, C32=ws.e1)
-            ln(R, ed, EDP, ws.e1, (oe, oe + ed), plan.row_mol, out_img=ws.en_img, valid=plan.row_g, tag='e1')
-        ilin(p + 'g01', ws.en_img, R, bias=False, epi=_lib.EPI_ACT, act_out=_lib.ACT_TANH, C16=ws.G)
+            ilin(p + 'emb', ws.A1, RP, C32=ws.e1)
+            ln(RP, ed, EDP, ws.e1, (oe, oe + ed), plan.pair_mol, out_img=ws.en_img, valid=plan.pair_i, tag='e1')
+        ilin(p + 'g01', ws.en_img, RP, bias=False, epi=_lib.EPI_ACT, act_out=_lib.ACT_TANH, C16=ws.G)
         # attention
         ln(Nn, D, D, h, (o, o + D), plan.node_mol, out_img=ws.hn_img, tag='h1')
         ilin(p + 'qkv', ws.hn_img, Nn, C16=ws.qkv)
         aa = _lib.WideAttnArgs(Nn, D, d.H, d.X, d.sc, dp(ws.grp_row0), dp(ws.grp_len), dp(plan.row_j), dp(ws.qkv), ws.ldq,
-                               meta['qkp'], 2 * meta['qkp'], dp(ws.G), ws.ldg, meta['qkp'], dp(ws.extra), dp(ws.hnode),
-                               max(plan.max_group, 1))
+                               meta['qkp'], 2 * meta['qkp'], dp(ws.G), ws.ldg, meta['qkp'], dp(ws.extra), dp(plan.row_pair),
+                               dp(ws.hnode), max(plan.max_group, 1))
         _lib.call('jodo_wide_attn', ctypes.byref(aa), st)
         # node path
         ln(Nn, D, D, h, (o + 3 * D, o + 4 * D), plan.node_mol, out_img=ws.h2_img, out32=ws.h2, y=ws.hnode, gate=o + 2 * D,
@@ -262,28 +268,28 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
             ilin(p + 'ab', ws.hout_img, Nn, C16=ws.AB)
         ilin(p + 'node_l', ws.hout_img, Nn, C32=ws.ah[:, D + l * meta['cnp']:])
         # edge path: e2 = norm2(e + gate * node2edge(hnode[r] + hnode[c])), e_out = e2 + gate * FFN(e2)
-        ln(R, ed, EDP, ws.e32, (oe + 3 * ed, oe + 4 * ed), plan.row_mol, out_img=ws.e2_img, out32=ws.e2, y=ws.P,
-           yi=plan.row_g, y2=ws.P, y2i=plan.row_j, ybias=pk[p + 'n2e.bias'], gate=oe + 2 * ed, valid=plan.row_g, tag='e2')
-        ilin(p + 'ff3', ws.e2_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.f3_img)
-        ilin(p + 'ff4', ws.f3_img, R, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.row_mol,
+        ln(RP, ed, EDP, ws.e32, (oe + 3 * ed, oe + 4 * ed), plan.pair_mol, out_img=ws.e2_img, out32=ws.e2, y=ws.P,
+           yi=plan.pair_i, y2=ws.P, y2i=plan.pair_j, ybias=pk[p + 'n2e.bias'], gate=oe + 2 * ed, valid=plan.pair_i, tag='e2')
+        ilin(p + 'ff3', ws.e2_img, RP, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.f3_img)
+        ilin(p + 'ff4', ws.f3_img, RP, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.pair_mol,
              C32=ws.e32)
         if d.two_d:
-            _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.EH), _c(KH), _c((l + 1) * EDP),
+            _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(RP), _c(ed), P(plan.pair_i), P(ws.EH), _c(KH), _c((l + 1) * EDP),
                       None, _c(0), _c(0), None, _c(0), _c(0), st)
             if dbg is not None:
                 dbg.setdefault('blocks', []).append(dict(hnode=ws.hnode.clone(), h=hout.clone(), e=ws.e32.clone()))
             h = hout
             continue
-        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(R), _c(ed), P(plan.row_g), P(ws.A4), _c(K2), _c(0), P(ws.A1),
+        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(RP), _c(ed), P(plan.pair_i), P(ws.A4), _c(K2), _c(0), P(ws.A1),
                   _c(K2), _c(ed), P(ws.EH), _c(KH), _c((l + 1) * EDP), st)
-        # coordinate update
-        ilin(p + 'equi_in', ws.A4, R, bias=False, C16=ws.U)
+        # coordinate update: the [e | dist] part of input_lin per pair, everything behind the LayerNorm per directed row
+        ilin(p + 'equi_in', ws.A4, RP, bias=False, C16=ws.U)
         ln(R, D, D, ws.U, (oq, oq + D), plan.row_mol, out_img=ws.u_img, y=ws.AB, yi=plan.row_g, y2=ws.AB[:, D:],
-           y2i=plan.row_j, valid=plan.row_g, tag='equi')
+           y2i=plan.row_j, valid=plan.row_g, xi=plan.row_pair, tag='equi')
         ilin(p + 'c0', ws.u_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.c0_img)
         ilin(p + 'c2', ws.c0_img, R, bias=False, C32=ws.c3)
         _lib.call('jodo_wide_equi_out', P(ws.grp_row0), P(ws.grp_len), P(plan.row_j), P(ws.c3), _c(64), P(ws.extra),
-                  _c(d.X), ctypes.c_float(meta['coord_scale'][l]), P(pin), P(pout), _c(Nn), st)
+                  P(plan.row_pair), _c(d.X), ctypes.c_float(meta['coord_scale'][l]), P(pin), P(pout), _c(Nn), st)
         _lib.call('jodo_com', P(pout), ctypes.byref(ps), st)
         if dbg is not None:
             dbg.setdefault('blocks', []).append(dict(hnode=ws.hnode.clone(), h=hout.clone(), e=ws.e32.clone(),
@@ -301,13 +307,12 @@ def forward_wide(self, pk, plan, ws, ps, xh, edge_x, noise_level, cond_x, cond_e
         out_x = torch.zeros(B, N, 3 + d.inn, device=xh.device, dtype=torch.float32)
         _lib.call('jodo_node_out', P(ws.pos[d.L & 1]), P(ws.ap), _c(ws.ap.stride(0)), ctypes.byref(ps),
                   ctypes.c_void_p(ws.flags.data_ptr() + 4), None, _c(d.inn), P(out_x), st)
-    ilin('hcat', ws.EH, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.H_img)
-    ilin('ehead2', ws.H_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, C32=ws.X2)
-    tmp = torch.zeros(B, N, N, d.ch, device=xh.device, dtype=torch.float32)
-    _lib.call('jodo_wide_head_out', ctypes.byref(ps), P(ws.X2), _c(EDP), _c(ed // 2), P(pk['ehead4.w']), P(pk['ehead4.b']),
-              _c(d.ch), P(tmp), st)
-    out_e = torch.empty_like(tmp)
-    _lib.call('jodo_sym_edges', P(tmp), P(out_e), _c(B), _c(N), _c(d.ch), st)
+    ilin('hcat', ws.EH, RP, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.H_img)
+    ilin('ehead2', ws.H_img, RP, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, C32=ws.X2)
+    # every pair row writes both orientations: the reference's 0.5 (e + e^T) (mol_gnn.py:579) of two identical values
+    out_e = torch.zeros(B, N, N, d.ch, device=xh.device, dtype=torch.float32)
+    _lib.call('jodo_wide_head_out', ctypes.byref(pps), P(ws.X2), _c(EDP), _c(ed // 2), P(pk['ehead4.w']), P(pk['ehead4.b']),
+              _c(d.ch), _c(1), P(out_e), st)
     if dbg is not None:
         dbg.update(tab=ws.tab.clone(), temb=ws.temb.clone(), ah=ws.ah.clone(), extra=ws.extra.clone(),
                    plan=plan, flags=ws.flags.clone())
