@@ -492,13 +492,17 @@ def run_b200(args):
     if getattr(model, 'wide', False):
         kf, kb, kh = roofline.wide_kernel_flops(d), {}, roofline.wide_kernel_bytes(d)
     kernels = {}
+    # kernels that own the symmetric edge state run once per UNORDERED pair: half the rows of the directed-edge count
+    rows_of = lambda name: tot['edges'] * (0.5 if name in roofline.PAIR_KERNELS else 1.0)
     for name, (t, c) in sorted(per.items(), key=lambda kv: -kv[1][0]):
         avg_ms = t / c
         ent = {'launches_per_step': c // reps // (2 if dpm else 1), 'avg_ms': round(avg_ms, 4), 'share': round(t / total_traced, 4)}
         if name in kf:
-            ent['tflops'] = round(kf[name] * tot['edges'] / (avg_ms * 1e-3) / 1e12, 2)
+            ent['tflops'] = round(kf[name] * rows_of(name) / (avg_ms * 1e-3) / 1e12, 2)
         if name in kb or name in kh:
-            ent['gbs'] = round((kb.get(name) or kh[name]) * tot['edges'] / (avg_ms * 1e-3) / 1e9, 1)
+            ent['gbs'] = round((kb.get(name) or kh[name]) * rows_of(name) / (avg_ms * 1e-3) / 1e9, 1)
+        if name in roofline.PAIR_KERNELS:
+            ent['rows'] = 'pairs'
         kernels[name] = ent
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -507,13 +511,13 @@ def run_b200(args):
             traffic = json.load(f).get(args.workload, {}).get(top)
     roof = None
     if top in kf:
-        ach = kf[top] * tot['edges'] / (per[top][0] / per[top][1] * 1e-3) / 1e12
+        ach = kf[top] * rows_of(top) / (per[top][0] / per[top][1] * 1e-3) / 1e12
         roof = {'kernel': top, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
                 'frac': ach / pk['tf_sustained'], 'traffic': traffic,
                 'peak_source': pk['src'] + ' bf16 dense sustained (kernels run kind::f16, same nominal rate)',
                 'share_of_step': per[top][0] / total_traced}
     elif top in kh:
-        ach = kh[top] * tot['edges'] / (per[top][0] / per[top][1] * 1e-3) / 1e9
+        ach = kh[top] * rows_of(top) / (per[top][0] / per[top][1] * 1e-3) / 1e9
         roof = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach / pk['hbm'],
                 'traffic': traffic, 'peak_source': pk['src'] + ' HBM copy bandwidth', 'share_of_step': per[top][0] / total_traced}
     whole = {'tflops': tot['flops'] * K / (ms_local * 1e-3) / 1e12, 'hbm_gbs_alg': tot['bytes'] * K / (ms_local * 1e-3) / 1e9}

@@ -8,6 +8,14 @@ def mm(i, o):
     return 2 * i * o
 
 
+# Kernels that run once per UNORDERED pair (the edge state is symmetric): their per-row figures below
+# apply to edges / 2 rows.  The whole-step model (flops_alg / bytes_alg) stays the reference's per-directed-edge count.
+PAIR_KERNELS = frozenset({
+    'jodo_edge_embed', 'jodo_edge_update', 'jodo_edge_head',
+    'jodo_imglinear:emb', 'jodo_imglinear:g01', 'jodo_imglinear:ff3', 'jodo_imglinear:ff4', 'jodo_imglinear:equi_in',
+    'jodo_wide_ln:e2', 'jodo_wide_ln:e1', 'jodo_wide_dist', 'jodo_wide_put'})
+
+
 def per_edge_kernel_flops(d):
     """FLOP per real directed edge for ONE launch of each edge-tile kernel."""
     D, ed, qk, r, L, ce, ch, X = d.D, d.ed, d.qk, d.r, d.L, d.ce, d.ch, d.X
@@ -52,7 +60,7 @@ def wide_kernel_bytes(d):
     read and write once (per-atom operands and per-molecule tables are L2-resident and not counted)."""
     D, ed, qk = d.D, d.ed, d.qk
     return {
-        'jodo_wide_ln:equi': 2 * D + 2 * D,                 # fp16 pre-LayerNorm rows in, fp16 operand image out
+        'jodo_wide_ln:equi': 2 * D + 2 * D,                 # fp16 pre-LayerNorm rows (the pair's) in, fp16 operand image out
         'jodo_wide_ln:e2': 4 * ed + 4 * ed + 2 * ed,        # fp32 edge state in, fp32 e2 + fp16 image out
         'jodo_wide_ln:e1': 4 * ed + 2 * ed,
         'jodo_wide_attn': 2 * (qk + D) + 1,                 # tanh(lin_edge0 | lin_edge1) rows + adjacency bits

@@ -57,6 +57,19 @@ def load():
     return ns
 
 
+def load_cond_gen():
+    """The reference's property classifier modules by file path: cond_gen/model.py (EGNN) and cond_gen/utils.py
+    (get_adj_matrix_fn).  Both import nothing but torch; the package __init__ is bypassed (it pulls in the property
+    distribution, which needs the datasets)."""
+    ns = type('CondGen', (), {})()
+    for name in ('model', 'utils'):
+        spec = importlib.util.spec_from_file_location('ref_cond_gen_' + name, os.path.join(REF_ROOT, 'cond_gen', name + '.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        setattr(ns, name, mod)
+    return ns
+
+
 def load_datasets_config():
     """datasets/datasets_config.py by file path (the `datasets` package itself needs PyG + rdkit)."""
     spec = importlib.util.spec_from_file_location('ref_datasets_config', os.path.join(REF_ROOT, 'datasets', 'datasets_config.py'))

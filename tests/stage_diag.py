@@ -104,10 +104,10 @@ def run_case(name, device='cuda', verbose=True):
         ed = model.dims.ed
         m = inp['node_mask'].double()
         for l, (b, ob) in enumerate(zip(dbg['blocks'], trace['blocks'])):
-            rep.append((f'b{l}.e1', rel(plan.rows_to_dense(b['e1'][:, :ed], group_first=False), ob['e1'] * em)))
+            rep.append((f'b{l}.e1', rel(plan.pairs_to_dense(b['e1'][:, :ed]), ob['e1'] * em)))
             rep.append((f'b{l}.hnode', rel(packed_to_dense(plan, b['hnode']), ob['hnode'] * m)))
             rep.append((f'b{l}.h', rel(packed_to_dense(plan, b['h']), ob['h'])))
-            rep.append((f'b{l}.e', rel(plan.rows_to_dense(b['e'][:, :ed]), ob['e'] * em)))
+            rep.append((f'b{l}.e', rel(plan.pairs_to_dense(b['e'][:, :ed]), ob['e'] * em)))
             rep.append((f'b{l}.pos', rel(packed_to_dense(plan, b['pos'][:, :3]), ob['pos'])))
     else:
         _fused_stages(model, dbg, trace, plan, inp, em, rep, D)
