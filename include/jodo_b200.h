@@ -329,6 +329,22 @@ int jodo_wide_head_out(const jodo_plan* p, const float* x, int ldx, int hw, cons
                        int both, float* out_dense, void* stream);   /* mol_gnn.py:574-578; both != 0: p is the pair plan, every
                                                                      row writes e_hat[b, i, j] and e_hat[b, j, i] */
 
+/* ---- property classifier (reference cond_gen/model.py:26-220, EGNN of E_GCL_mask layers; called once per batch of
+ * conditional samples, sampling.py:363-367).  The linear layers run through jodo_rowlinear (packed atoms) and
+ * jodo_imglinear (the plan's directed edge rows: only real ordered pairs i != j, where the reference enumerates the full
+ * padded n x n graph with a Python triple loop, cond_gen/utils.py:18-40, and multiplies by the edge mask); these are
+ * the row kernels between them. */
+/* SiLU(P[g] + Q[j] + w_r |x_g - x_j|^2) -> fp16 operand image [n_tiles * 128][H]: edge_mlp.0 hoisted to per-atom
+ * parts PQ = [P | Q] (fp32 rows, leading dimension ldpq >= 2H), model.py:93-95, 126-131, 164-167.  H % 64 == 0, H <= 256. */
+int jodo_egnn_edge_in(const jodo_plan* p, const float* pos4, const float* PQ, int ldpq, int H, const float* wr, void* img,
+                      void* stream);
+/* agg[g] = sum over the rows of atom g of m * sigmoid(w_a . m + b_a) (w_a null: no attention gate), m = fp16 rows
+ * [rows][ldm] written by the edge_mlp.2 GEMM; model.py:132-139, 207.  agg: fp32 rows, 16-byte aligned. */
+int jodo_egnn_agg(const int* grp_row0, const int* grp_len, const void* M16, int ldm, int H, const float* wa, float ba,
+                  float* agg, int ldagg, int Nn, void* stream);
+/* out[b, :W] = sum of x[v, :W] over the packed atoms v of molecule b (model.py:66-68) */
+int jodo_mol_sum(const float* x, int ldx, int W, const int* mol_start, int B, float* out, int ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

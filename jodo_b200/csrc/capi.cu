@@ -303,4 +303,27 @@ int jodo_wide_head_out(const jodo_plan* p, const float* x, int ldx, int hw, cons
   JODO_LAUNCH(jodo::launch_wide_head_out(*p, x, ldx, hw, w4, b4, ch, both, out_dense, S(stream)), "jodo_wide_head_out");
 }
 
+// ---- property classifier
+int jodo_egnn_edge_in(const jodo_plan* p, const float* pos4, const float* PQ, int ldpq, int H, const float* wr, void* img,
+                      void* stream) {
+  if (!p) return fail("jodo_egnn_edge_in: null plan");
+  if (const char* m = check_plan(*p)) return fail(m);
+  if (H <= 0 || H % 64 || H > 256 || ldpq < 2 * H || ldpq % 4) return fail("jodo_egnn_edge_in: H must be a multiple of 64 up to 256, ldpq >= 2 H");
+  if (!pos4 || !PQ || !wr || !img || (reinterpret_cast<uintptr_t>(img) & 127) || (reinterpret_cast<uintptr_t>(PQ) & 15) ||
+      (reinterpret_cast<uintptr_t>(wr) & 15))
+    return fail("jodo_egnn_edge_in: bad buffers");
+  JODO_LAUNCH(jodo::launch_egnn_edge_in(*p, pos4, PQ, ldpq, H, wr, img, S(stream)), "jodo_egnn_edge_in");
+}
+int jodo_egnn_agg(const int* grp_row0, const int* grp_len, const void* M16, int ldm, int H, const float* wa, float ba,
+                  float* agg, int ldagg, int Nn, void* stream) {
+  if (!grp_row0 || !grp_len || !M16 || !agg || Nn <= 0) return fail("jodo_egnn_agg: null buffer");
+  if (H <= 0 || H % 8 || H > 256 || ldm < H || ldm % 8 || ldagg < H || ldagg % 4) return fail("jodo_egnn_agg: bad sizes (H % 8 == 0, H <= 256)");
+  if ((reinterpret_cast<uintptr_t>(M16) | reinterpret_cast<uintptr_t>(agg) | reinterpret_cast<uintptr_t>(wa)) & 15) return fail("jodo_egnn_agg: pointers must be 16-byte aligned");
+  JODO_LAUNCH(jodo::launch_egnn_agg(grp_row0, grp_len, M16, ldm, H, wa, ba, agg, ldagg, Nn, S(stream)), "jodo_egnn_agg");
+}
+int jodo_mol_sum(const float* x, int ldx, int W, const int* mol_start, int B, float* out, int ldo, void* stream) {
+  if (!x || !mol_start || !out || B <= 0 || W <= 0 || ldx < W || ldo < W) return fail("jodo_mol_sum: bad arguments");
+  JODO_LAUNCH(jodo::launch_mol_sum(x, ldx, W, mol_start, B, out, ldo, S(stream)), "jodo_mol_sum");
+}
+
 }  // extern "C"

@@ -143,4 +143,11 @@ cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const 
 cudaError_t launch_wide_head_out(const Plan& p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,
                                  int both, float* out_dense, cudaStream_t st);
 
+// ---- property classifier (egnn.cu)
+cudaError_t launch_egnn_edge_in(const Plan& p, const float* pos4, const float* PQ, int ldpq, int H, const float* wr, void* img,
+                                cudaStream_t st);
+cudaError_t launch_egnn_agg(const int* grp_row0, const int* grp_len, const void* M16, int ldm, int H, const float* wa, float ba,
+                            float* agg, int ldagg, int Nn, cudaStream_t st);
+cudaError_t launch_mol_sum(const float* x, int ldx, int W, const int* mol_start, int B, float* out, int ldo, cudaStream_t st);
+
 }  // namespace jodo

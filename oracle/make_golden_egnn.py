@@ -3,8 +3,7 @@
 
     python -m oracle.make_golden_egnn
 
-The fixture holds the state dict (fp32, seeded init, weights perturbed so that the attention gate and every branch
-are exercised), a ragged batch built the way sampling.py:330-337 builds masks, the reference output in fp32 and fp64,
+The fixture holds the (seed, gain) of the synthetic weights, the reference's parameter names, a ragged batch built the way sampling.py:330-337 builds masks, the reference output in fp32 and fp64,
 and the edge list of cond_gen/utils.get_adj_matrix for a small case."""
 import os
 import sys
@@ -16,6 +15,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
 from oracle import ref_loader  # noqa: E402
+from jodo_b200.classifier import egnn_param_spec, egnn_synth_state_dict  # noqa: E402
 
 
 def make_inputs(B, N, n_nodes, in_nf, gen):
@@ -36,13 +36,14 @@ def main():
     cg = ref_loader.load_cond_gen()
     out = {}
     for name, (nf, L, att, na) in {'egnn_qm9': (128, 7, True, False), 'egnn_small_attr': (64, 2, False, True)}.items():
-        torch.manual_seed(42)
         model = cg.model.EGNN(in_node_nf=5, in_edge_nf=0, hidden_nf=nf, device='cpu', n_layers=L, coords_weight=1.0,
                               attention=att, node_attr=na).eval()
+        # weights: the seeded synthetic init of jodo_b200.classifier (gain 1.5: gates and activations leave their linear
+        # range), regenerated from (seed, gain) by the tests instead of being stored
+        spec = egnn_param_spec(5, nf, L, att, na)
+        assert [k for k, _ in model.named_parameters()] == [k for k, _ in spec]
+        model.load_state_dict(egnn_synth_state_dict(spec, seed=42, gain=1.5), strict=True)
         gen = torch.Generator().manual_seed(7)
-        with torch.no_grad():
-            for p in model.parameters():                       # wider weights: gates and activations leave their linear range
-                p.mul_(1.5).add_(0.02 * torch.randn(p.shape, generator=gen))
         n_nodes = [9, 3, 14, 1, 12, 14]
         inp = make_inputs(len(n_nodes), max(n_nodes), n_nodes, 5, gen)
         edges = cg.utils.get_adj_matrix_fn()(inp['n_nodes'], len(n_nodes), 'cpu')
@@ -50,8 +51,7 @@ def main():
             y32 = model(edges=edges, edge_attr=None, **inp)
             m64 = model.double()
             y64 = m64(edges=edges, edge_attr=None, **{k: (v.double() if torch.is_tensor(v) else v) for k, v in inp.items()})
-        sd = {k: v.float().clone() for k, v in model.state_dict().items()}
-        out[name] = dict(args=dict(nf=nf, n_layers=L, attention=att, node_attr=na), state_dict=sd, inputs=inp,
+        out[name] = dict(args=dict(nf=nf, n_layers=L, attention=att, node_attr=na), weights=dict(seed=42, gain=1.5), inputs=inp,
                          n_per_mol=n_nodes, ref_fp32=y32.float(), ref_fp64=y64, param_names=[k for k, _ in model.named_parameters()])
     e = cg.utils.get_adj_matrix_fn()(4, 3, 'cpu')
     out['adj_4_3'] = [e[0].clone(), e[1].clone()]
