@@ -57,6 +57,8 @@ def parse():
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch override (debug)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--noise', default='torch', choices=['torch', 'philox'],
+                    help="ancestral noise: the reference's torch.randn stream (default) or Philox drawn inside the update kernels")
     ap.add_argument('--no-extras', action='store_true', help='skip the strong-scaling point (N > 1) and the other workloads (N = 1)')
     return ap.parse_args()
 
@@ -251,7 +253,7 @@ def run_reference(args):
 class Workload:
     """One workload on this rank: model, synthetic state, the (graph-replayed) step function."""
 
-    def __init__(self, wl, dev, world, rank, per_gpu_batch=None, global_batch=None, no_graph=False):
+    def __init__(self, wl, dev, world, rank, per_gpu_batch=None, global_batch=None, no_graph=False, noise='torch'):
         from jodo_b200 import configs, roofline, sampler as S, synth
         from jodo_b200.model import create_model
         self.S = S
@@ -278,7 +280,7 @@ class Workload:
         self.state = dict(x=b['xh'].to(dev), ex=b['edge_x'].to(dev), cx=None, cex=None)
         torch.cuda.manual_seed(1234 + rank)                   # the samplers draw from the default CUDA generator
         self.grid = torch.linspace(0.9946, 1e-3, 1000)
-        self.smp = S.AncestralSampler(S.CosineVP(), self.grid)
+        self.smp = S.AncestralSampler(S.CosineVP(), self.grid, noise=noise, seed=1234 + rank)
         if self.dpm:
             self.sol = S.DPMSolverSinglestep(S.CosineVP(), 50, order=2)
             self.ogrid = self.sol.outer_grid(dev)
@@ -401,7 +403,7 @@ def run_b200(args):
         return float(t[0]), -float(t[1])
 
     K, W = args.steps, args.warmup
-    w = Workload(args.workload, dev, world, rank, per_gpu_batch=args.batch, no_graph=args.no_graph)
+    w = Workload(args.workload, dev, world, rank, per_gpu_batch=args.batch, no_graph=args.no_graph, noise=args.noise)
     dpm, batch, d, tot, N, cfg, total_mols = w.dpm, w.batch, w.d, w.tot, w.N, w.cfg, w.total
     if dpm:
         # a step = one model evaluation; the solver advances in outer steps of two evaluations (order 2)
@@ -590,7 +592,8 @@ def run_b200(args):
                        'arch': WORKLOADS[args.workload][0], 'weights': 'random init (seed 42)', 'l2': 'inputs larger than L2 '
                        '(edge state %.0f MB per step)' % (tot['bytes'] / 1e6),
                        'parallelism': f'dp{world} (independent molecules, one global batch dealt by size: sampler.shard_molecules)',
-                       'step_launch': graph_note},
+                       'step_launch': graph_note,
+                       'noise': 'torch.randn in the reference call order' if args.noise == 'torch' or dpm else 'Philox4x32-10 inside the update kernels'},
             'e2e': e2e, 'gpu_launches': launches, 'clocks': clk, 'roofline': roof, 'whole_step': whole,
             'rank_ms_per_step_min': ms_min / K, 'rank_ms_per_step_max': ms / K, 'gather_ms': gather_ms, 'strong': strong,
             'workloads': others, 'kernels': kernels, 'cpu_baseline': cpu, 'finite': ok, 'gathered': gathered,

@@ -251,6 +251,19 @@ int jodo_ancestral_update(const float* x, const float* pred, const float* raw_po
                           const float* edge_mask, int B, int N, int F, int ch, float c_x, float c_pred, float sigma,
                           const float* coef_dev, float* x_new, float* x_mean, float* e_new, float* e_mean, void* stream);
 
+/* The same update with the noise drawn IN the kernels: Philox4x32-10 (counter = element index, step,
+ * stream; key = seed) + Box-Muller, so a step needs no raw-draw buffers and no generator launches.  This is a different
+ * random stream than the reference's torch.randn by construction; its parity chain is oracle/philox_ref.py (pinned on the
+ * published Philox known-answer vectors) -> jodo_philox_normal -> this call against jodo_ancestral_update fed with the
+ * oracle's draws.  coef_dev, when not null: {c_x, c_pred, sigma, (unused), step as a float}. */
+int jodo_ancestral_update_philox(const float* x, const float* pred, const float* node_mask, const float* edge_x,
+                                 const float* edge_pred, const float* edge_mask, int B, int N, int F, int ch, float c_x,
+                                 float c_pred, float sigma, const float* coef_dev, unsigned long long seed, unsigned int step,
+                                 float* x_new, float* x_mean, float* e_new, float* e_mean, void* stream);
+/* out[4 i .. 4 i + 3] = the four standard normals of counter (i, step, stream_id) under `seed`, i < n4 (tests, tools) */
+int jodo_philox_normal(unsigned long long n4, unsigned long long seed, unsigned int step, unsigned int stream_id, float* out,
+                       void* stream);
+
 /* Tensor-core operands are fp16 (the mantissa of tf32) and saturate at +-65504 instead of overflowing.  The kernels that write
  * the operands with an unbounded range -- the per-atom GEMM outputs the edge kernels gather (q | k | v, hoisted input_lin and
  * node2edge_lin parts, activation images) and the fp16 copy of the edge state -- count every clamped store.  Synchronises the

@@ -42,7 +42,7 @@ def check(rc, what):
 
 # ---- launch accounting / per-call device timing (bench.py, profiling) ------------------------------
 # kernels launched per C-ABI call (everything else launches exactly one)
-KERNELS_PER_CALL = {'jodo_edge_embed': 2, 'jodo_wide_embed_in': 2, 'jodo_node_out': 2, 'jodo_ancestral_update': 2, 'jodo_dpm_update': 2}     # (memsets / D2D constant uploads are not kernels)
+KERNELS_PER_CALL = {'jodo_edge_embed': 2, 'jodo_wide_embed_in': 2, 'jodo_node_out': 2, 'jodo_ancestral_update': 2, 'jodo_ancestral_update_philox': 2, 'jodo_dpm_update': 2}     # (memsets / D2D constant uploads are not kernels)
 LAUNCHES = 0           # kernels launched through this binding since import
 TRACE = None           # set to a list to record (name, start_event, end_event) around every call
 

@@ -157,8 +157,24 @@ int jodo_ancestral_update(const float* x, const float* pred, const float* raw_po
       !x_mean || !e_new || !e_mean)
     return fail("jodo_ancestral_update: null pointer");
   JODO_LAUNCH(jodo::launch_ancestral_update(x, pred, raw_pos, raw_feat, node_mask, edge_x, edge_pred, raw_edge, edge_mask, B, N,
-                                            F, ch, c_x, c_pred, sigma, coef_dev, x_new, x_mean, e_new, e_mean, S(stream)),
+                                            F, ch, c_x, c_pred, sigma, coef_dev, 0, 0ull, 0u, x_new, x_mean, e_new, e_mean, S(stream)),
               "jodo_ancestral_update");
+}
+int jodo_ancestral_update_philox(const float* x, const float* pred, const float* node_mask, const float* edge_x,
+                                 const float* edge_pred, const float* edge_mask, int B, int N, int F, int ch, float c_x,
+                                 float c_pred, float sigma, const float* coef_dev, unsigned long long seed, unsigned int step,
+                                 float* x_new, float* x_mean, float* e_new, float* e_mean, void* stream) {
+  if (B <= 0 || N <= 0 || F <= 3 || ch <= 0) return fail("jodo_ancestral_update_philox: bad sizes");
+  if (!x || !pred || !node_mask || !edge_x || !edge_pred || !edge_mask || !x_new || !x_mean || !e_new || !e_mean)
+    return fail("jodo_ancestral_update_philox: null pointer");
+  JODO_LAUNCH(jodo::launch_ancestral_update(x, pred, nullptr, nullptr, node_mask, edge_x, edge_pred, nullptr, edge_mask, B, N, F, ch,
+                                            c_x, c_pred, sigma, coef_dev, 1, seed, step, x_new, x_mean, e_new, e_mean, S(stream)),
+              "jodo_ancestral_update_philox");
+}
+int jodo_philox_normal(unsigned long long n4, unsigned long long seed, unsigned int step, unsigned int stream_id, float* out,
+                       void* stream) {
+  if (!out || n4 == 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return fail("jodo_philox_normal: bad arguments");
+  JODO_LAUNCH(jodo::launch_philox_normal(n4, seed, step, stream_id, out, S(stream)), "jodo_philox_normal");
 }
 
 int jodo_saturation_count(unsigned long long* out, int reset) {

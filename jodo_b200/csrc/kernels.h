@@ -100,8 +100,10 @@ cudaError_t launch_sym_edges(const float* tmp, float* out, int B, int N, int ch,
 cudaError_t launch_ancestral_update(const float* x, const float* pred, const float* raw_pos, const float* raw_feat,
                                     const float* node_mask, const float* ex, const float* epred, const float* raw_edge,
                                     const float* edge_mask, int B, int N, int F, int ch, float c_x, float c_p, float sigma,
-                                    const float* coef, float* x_new, float* x_mean, float* e_new, float* e_mean,
-                                    cudaStream_t st);
+                                    const float* coef, int philox, unsigned long long seed, unsigned int step, float* x_new,
+                                    float* x_mean, float* e_new, float* e_mean, cudaStream_t st);
+cudaError_t launch_philox_normal(unsigned long long n4, unsigned long long seed, unsigned int step, unsigned int stream_id,
+                                 float* out, cudaStream_t st);
 
 cudaError_t launch_dpm_update(const float* x_start, const float* pos_in, int ld_pos, const float* p0, const float* p1,
                               const float* raw_pos, const float* node_mask, const float* e_start, const float* e0,

@@ -102,7 +102,13 @@ class AncestralSampler:
     """Ancestral sampling for joint 2D & 3D generation (reference sampling.py:518-596) with
     self-conditioning ('ori' hand-off, reference utils.py:134-136)."""
 
-    def __init__(self, schedule, time_steps, generator=None, noise_fn=None, s_array=None, fused=True):
+    def __init__(self, schedule, time_steps, generator=None, noise_fn=None, s_array=None, fused=True, noise='torch', seed=0):
+        """noise='torch': the reference's torch.randn draws in the reference's call order (models/utils.py:67-99);
+        noise='philox': the draws are generated inside the fused update kernels (Philox4x32-10 keyed by `seed`, counter =
+        element / step) -- a different random stream with its own parity chain (tests/test_philox.py), no generator
+        launches and no raw-draw buffers."""
+        assert noise in ('torch', 'philox')
+        self.noise, self.seed = noise, int(seed)
         self.fused = fused                # CUDA tensors: fused update kernel (same random stream as the torch ops)
         self.schedule = schedule
         self.t_array = time_steps
@@ -121,7 +127,9 @@ class AncestralSampler:
         pred, edge_pred = model(vec_t, x, node_mask, edge_mask, edge_x=edge_x, noise_level=noise_level,
                                 cond_x=cond_x, cond_edge_x=cond_edge_x, context=context)
         if x.is_cuda and self.noise_fn is None and self.fused:
-            return self._fused_update(x, edge_x, pred, edge_pred, node_mask, edge_mask, c_x, c_pred, sigma)
+            return self._fused_update(x, edge_x, pred, edge_pred, node_mask, edge_mask, c_x, c_pred, sigma, step=i)
+        if self.noise == 'philox':
+            raise ValueError("noise='philox' draws inside the fused CUDA update: it needs CUDA tensors, fused=True and no noise_fn")
         x_mean = c_x * x + c_pred * pred
         if self.noise_fn is not None:
             zn, ze = self.noise_fn(i, 'node'), self.noise_fn(i, 'edge')
@@ -138,7 +146,7 @@ class AncestralSampler:
     def _node_noise(self, bs, N, F_, node_mask):
         return node_noise(bs, N, F_ - 3, node_mask, self.generator)
 
-    def _fused_update(self, x, edge_x, pred, edge_pred, node_mask, edge_mask, c_x, c_pred, sigma, coef_dev=None):
+    def _fused_update(self, x, edge_x, pred, edge_pred, node_mask, edge_mask, c_x, c_pred, sigma, coef_dev=None, step=0):
         """Posterior mean + noise in two launches of libjodo_b200 (jodo_ancestral_update) instead of ~30 torch
         kernels; the raw normal draws are the same torch.randn calls, in the same order, as node_noise / edge_noise."""
         import ctypes
@@ -146,15 +154,21 @@ class AncestralSampler:
         bs, N, F_ = x.shape
         ch = edge_x.shape[-1]
         dev = x.device
-        raw_pos = torch.randn((bs, N, 3), device=dev, generator=self.generator)
-        raw_feat = torch.randn((bs, N, F_ - 3), device=dev, generator=self.generator)
-        raw_edge = torch.randn((bs, ch, N, N), device=dev, generator=self.generator)
         c32 = lambda t: t.contiguous().float()
         x, edge_x, pred, edge_pred = c32(x), c32(edge_x), c32(pred), c32(edge_pred)
         nm, em = c32(node_mask), c32(edge_mask)
         x_new, x_mean = torch.empty_like(x), torch.empty_like(x)
         e_new, e_mean = torch.empty_like(edge_x), torch.empty_like(edge_x)
         f = ctypes.c_float
+        if self.noise == 'philox':
+            _lib.call('jodo_ancestral_update_philox', _lib.ptr(x), _lib.ptr(pred), _lib.ptr(nm), _lib.ptr(edge_x),
+                      _lib.ptr(edge_pred), _lib.ptr(em), ctypes.c_int(bs), ctypes.c_int(N), ctypes.c_int(F_), ctypes.c_int(ch),
+                      f(c_x), f(c_pred), f(sigma), _lib.ptr(coef_dev), ctypes.c_ulonglong(self.seed), ctypes.c_uint(step),
+                      _lib.ptr(x_new), _lib.ptr(x_mean), _lib.ptr(e_new), _lib.ptr(e_mean), _lib.stream_ptr())
+            return x_new, e_new, x_mean, e_mean, pred, edge_pred
+        raw_pos = torch.randn((bs, N, 3), device=dev, generator=self.generator)
+        raw_feat = torch.randn((bs, N, F_ - 3), device=dev, generator=self.generator)
+        raw_edge = torch.randn((bs, ch, N, N), device=dev, generator=self.generator)
         _lib.call('jodo_ancestral_update', _lib.ptr(x), _lib.ptr(pred), _lib.ptr(raw_pos), _lib.ptr(raw_feat), _lib.ptr(nm),
                   _lib.ptr(edge_x), _lib.ptr(edge_pred), _lib.ptr(raw_edge), _lib.ptr(em), ctypes.c_int(bs), ctypes.c_int(N),
                   ctypes.c_int(F_), ctypes.c_int(ch), f(c_x), f(c_pred), f(sigma), _lib.ptr(coef_dev), _lib.ptr(x_new), _lib.ptr(x_mean),
@@ -204,16 +218,17 @@ class GraphedAncestralStep:
     the plan are created outside the capture)."""
 
     def __init__(self, sampler, model, x, edge_x, cond_x, cond_edge_x, node_mask, edge_mask, context=None):
-        if not (x.is_cuda and sampler.fused and sampler.noise_fn is None and sampler.generator is None):
-            raise ValueError('the graph-captured step needs CUDA tensors, the fused update and the default CUDA generator')
+        if not (x.is_cuda and sampler.fused and sampler.noise_fn is None and (sampler.generator is None or sampler.noise == 'philox')):
+            raise ValueError('the graph-captured step needs CUDA tensors, the fused update and the default CUDA generator '
+                             "(or noise='philox')")
         if cond_x is None:
             raise ValueError('capture the self-conditioned step: run the first reverse step eagerly')
         from . import _lib
         c32 = lambda t: t.contiguous().float()
         dev, bs = x.device, x.shape[0]
         n = len(sampler.t_array)
-        self.table = torch.tensor([[float(v) for v in sampler.coef[i]] for i in range(n)], device=dev, dtype=torch.float32)
-        self.coef = torch.zeros(4, device=dev, dtype=torch.float32)       # {c_x, c_pred, sigma, noise level} of the step
+        self.table = torch.tensor([[float(v) for v in sampler.coef[i]] + [float(i)] for i in range(n)], device=dev, dtype=torch.float32)
+        self.coef = torch.zeros(5, device=dev, dtype=torch.float32)       # {c_x, c_pred, sigma, noise level, step} of the step
         self.x, self.edge_x = c32(x).clone(), c32(edge_x).clone()
         self.cond_x, self.cond_edge_x = c32(cond_x).clone(), c32(cond_edge_x).clone()
         vec_t = torch.zeros(bs, device=dev)                               # ignored by the model (reference mol_gnn.py:534)
