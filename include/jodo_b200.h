@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 9
+#define JODO_ABI_VERSION 10
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -197,7 +197,42 @@ typedef struct jodo_equi_args {                         /* MultiCondEquiUpdate (
   /* per-column constants passed BY VALUE so that they reach the FMA pipe as constant-bank operands: */
   float gbf4[256];                        /* GBF constants, {mu, c1, c2, 0} per feature column (entry 0 unused) */
   float b0h[256];                         /* coord_mlp.0 bias / 2 */
+  int skip_if_uniform;                    /* != 0: do nothing when *nonuni == 0 (jodo_equi_lin covers that case) */
 } jodo_equi_args;
+
+/* The same update under UNIFORM conditioning (every molecule carries the same noise level: always in unconditional
+ * sampling, reference sampling.py:549) with coord_mlp.0 composed into input_lin: LayerNorm without affine is C x / sigma
+ * (C = centering), so  coord_mlp.0(LN(x)(1 + scale) + shift) = (M x) / sigma + d  with  M = W0 diag(1 + scale) C,
+ * d = W0 shift + b0, and M x is linear in [h_row | h_col | e | dist].  jodo_equi_compose forms M W_in for every block
+ * from the step's table row (one launch per call); jodo_equi_lin then needs one K = 128 tensor-core product (N = 512:
+ * x for the row statistics, y = (M W_e)[e | dist]) per edge tile instead of the K = 128 and K = 256 products, the
+ * LayerNorm operand image and the coord_mlp.2 product of jodo_equi.  Both launches return at once when *nonuni != 0. */
+typedef struct jodo_equi_compose_item {   /* one per block; device array */
+  const float* w0; const float* b0;       /* coord_mlp.0 weight [256, 256] / bias, fp32 */
+  const float* wi; const float* bi;       /* input_lin weight [256, 640] ([h_row | h_col | e | dist]) / bias, fp32 */
+  const float* w2;                        /* coord_mlp.2 weight [3, 256], fp32 */
+  int tab_off;                            /* floats from the start of a table row to this block's equi (shift | 1 + scale) rows */
+  void* wce_img;                          /* out: fp16 image of (M W_e) / 2 (N = 256, K = 128), the layout of win_img */
+  void* ab_img;                           /* in/out: the per-atom GEMM's weight image (N = 1024 in tiles of 256, K = 256); tiles 2, 3
+                                             receive (M W_A) / 2 and (M W_B) / 2 */
+  float* ab_bias;                         /* in/out: its bias [1024]; entries [512, 768) receive (M b_in) / 2 */
+  float* consts;                          /* out [1026]: d / 2 | coord_mlp.2 rows | GBF (1 + scale, shift) of the step */
+} jodo_equi_compose_item;
+int jodo_equi_compose(const jodo_equi_compose_item* items_dev, int n_blocks, const float* tab_row0, const int* nonuni, void* stream);
+
+typedef struct jodo_equi_lin_args {
+  jodo_plan p;
+  const void* e16;
+  const float* pos_in; float* pos_out;
+  const void* AB; int ldab;               /* fp16 piece-major [128][ldab rows][8]: A | B | YA | YB (the per-atom GEMM with N = 1024) */
+  const uint8_t* extra;
+  const void* win_img; const void* wce_img;
+  const float* consts;                    /* the block's jodo_equi_compose_item.consts */
+  float coord_scale;
+  const int* nonuni;                      /* required */
+  float gbf4[256];
+} jodo_equi_lin_args;
+int jodo_equi_lin(const jodo_equi_lin_args* a, void* stream);
 
 typedef struct jodo_edge_head_args {                     /* edge_exist_mlp | edge_type_mlp (reference models/mol_gnn.py:466-479,574-578) */
   jodo_plan p;

@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 9:
+        if _lib.jodo_abi_version() != 10:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -130,7 +130,17 @@ class EquiArgs(ctypes.Structure):
     _fields_ = [('p', PlanStruct), ('e16', _P), ('pos_in', _P), ('pos_out', _P), ('AB', _P),
                 ('ldab', _I), ('tab', _P), ('ld_tab', _I), ('tab_off', _I), ('extra', _P),
                 ('win_img', _P), ('wc0_img', _P), ('w2_img', _P), ('w2_img32', _P), ('coord_scale', _F), ('nonuni', _P),
-                ('gbf4', _F * 256), ('b0h', _F * 256)]
+                ('gbf4', _F * 256), ('b0h', _F * 256), ('skip_if_uniform', _I)]
+
+
+class EquiComposeItem(ctypes.Structure):
+    _fields_ = [('w0', _P), ('b0', _P), ('wi', _P), ('bi', _P), ('w2', _P), ('tab_off', _I), ('wce_img', _P), ('ab_img', _P),
+                ('ab_bias', _P), ('consts', _P)]
+
+
+class EquiLinArgs(ctypes.Structure):
+    _fields_ = [('p', PlanStruct), ('e16', _P), ('pos_in', _P), ('pos_out', _P), ('AB', _P), ('ldab', _I), ('extra', _P),
+                ('win_img', _P), ('wce_img', _P), ('consts', _P), ('coord_scale', _F), ('nonuni', _P), ('gbf4', _F * 256)]
 
 
 class EdgeHeadArgs(ctypes.Structure):

@@ -250,6 +250,19 @@ int jodo_equi(const jodo_equi_args* a, void* stream) {
   if (a->w2_img32 && pair) JODO_LAUNCH(jodo::launch_equi2(*a, num_sms(), S(stream)), "jodo_equi");
   JODO_LAUNCH(jodo::launch_equi(*a, num_sms(), S(stream)), "jodo_equi");
 }
+int jodo_equi_compose(const jodo_equi_compose_item* items_dev, int n_blocks, const float* tab_row0, const int* nonuni, void* stream) {
+  if (!items_dev || n_blocks <= 0 || n_blocks > 64 || !tab_row0 || !nonuni) return fail("jodo_equi_compose: bad arguments");
+  JODO_LAUNCH(jodo::launch_equi_compose(items_dev, n_blocks, tab_row0, nonuni, S(stream)), "jodo_equi_compose");
+}
+int jodo_equi_lin(const jodo_equi_lin_args* a, void* stream) {
+  if (!a) return fail("jodo_equi_lin: null args");
+  if (const char* m = check_plan(a->p)) return fail(m);
+  if (a->ldab < a->p.Nn) return fail("jodo_equi_lin: bad strides");
+  if (!a->p.row_pair) return fail("jodo_equi_lin: the plan needs row_pair (the edge state is stored per unordered pair)");
+  if (!a->e16 || !a->pos_in || !a->pos_out || !a->AB || !a->extra || !a->win_img || !a->wce_img || !a->consts || !a->nonuni)
+    return fail("jodo_equi_lin: null buffer");
+  JODO_LAUNCH(jodo::launch_equi_lin(*a, num_sms(), S(stream)), "jodo_equi_lin");
+}
 int jodo_edge_head(const jodo_edge_head_args* a, void* stream) {
   if (!a) return fail("jodo_edge_head: null args");
   if (const char* m = check_plan(a->p)) return fail(m);

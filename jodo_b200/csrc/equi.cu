@@ -146,6 +146,7 @@ __device__ __forceinline__ void eq_silu_tm(const EquiArgs& a, uint32_t tm_c, uin
 }
 
 __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ EquiArgs a) {
+  if (a.skip_if_uniform && a.nonuni != nullptr && *a.nonuni == 0) return;     // uniform conditioning: equi_lin.cu does this block
   extern __shared__ __align__(1024) uint8_t smem[];
   require_smem_alignment(smem);
   uint8_t* X = smem + EQ_X;

@@ -125,6 +125,11 @@ using EquiArgs = ::jodo_equi_args;
 cudaError_t launch_equi(const EquiArgs& a, int num_sms, cudaStream_t st);      // one tile in flight per SM (equi.cu)
 cudaError_t launch_equi2(const EquiArgs& a, int num_sms, cudaStream_t st);     // CTA pairs, two-stage pipeline (equi2.cu)
 
+using EquiLinArgs = ::jodo_equi_lin_args;
+cudaError_t launch_equi_lin(const EquiLinArgs& a, int num_sms, cudaStream_t st);            // uniform conditioning (equi_lin.cu)
+cudaError_t launch_equi_compose(const jodo_equi_compose_item* items_dev, int L, const float* tab_row0, const int* nonuni,
+                                cudaStream_t st);
+
 using EdgeHeadArgs = ::jodo_edge_head_args;
 cudaError_t launch_edge_head(const EdgeHeadArgs& a, int num_sms, cudaStream_t st);
 

@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from . import _lib, wide
-from .pack import TAB_HEAD, pack_model, tab_layer_stride
+from .pack import EQUI_LIN, TAB_HEAD, pack_model, tab_layer_stride
 from .params import build_param_tree, check_supported, dims_from_config, param_spec, synth_state_dict
 from .plan import Plan
 
@@ -80,7 +80,7 @@ class _Workspace:
         self.hnode = zf(Nn, D)                             # atoms without partners are never written: stay 0
         self.pbuf = h16(8, Nn, 8)                           # piece-major hoisted node2edge_lin part
         self.h2 = f(Nn, D)
-        self.ab = h16(2 * D // 8, Nn, 8)                    # piece-major (csrc/edge_common.cuh)
+        self.ab = h16((4 if EQUI_LIN else 2) * D // 8, Nn, 8)    # piece-major (csrc/edge_common.cuh): A | B (| composed YA | YB)
         self.n1 = f(Nn, D)
         self.n2 = f(Nn, D // 2)
         self.ap = f(Nn, meta['npred4']['N'])
@@ -175,6 +175,23 @@ class _DGTBase(nn.Module):
             self._fp_pending = torch.cuda.Event()
             self._fp_pending.record()
         return self._packed[use_wide]
+
+    def _compose_items(self, pk):
+        """Device table of jodo_equi_compose_item, one per block (pointers into the packed buffer), built once per packing."""
+        t = getattr(pk, '_compose_table', None)
+        if t is None:
+            import numpy as np
+            d = self.dims
+            stride = tab_layer_stride(d.D)
+            arr = (_lib.EquiComposeItem * d.L)()
+            for l in range(d.L):
+                p = f'b{l}.'
+                arr[l] = _lib.EquiComposeItem(pk.ptr(p + 'c0.w32'), pk.ptr(p + 'c0.b32'), pk.ptr(p + 'wi.w32'), pk.ptr(p + 'wi.b32'),
+                                              pk.ptr(p + 'w2.w32'), TAB_HEAD + l * stride + 6 * d.D + 6 * d.ed, pk.ptr(p + 'wce.img'),
+                                              pk.ptr(p + 'ab.img'), pk.ptr(p + 'ab.b'), pk.ptr(p + 'eqc'))
+            t = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(pk.buf.device)
+            pk._compose_table = t
+        return t
 
     def graph_token(self, node_mask, edge_mask):
         """What a CUDA graph captured over this model's launches depends on: the (plan, workspace, masks) cache entry and
@@ -280,6 +297,9 @@ class _DGTBase(nn.Module):
             m = meta['tab']
             _lib.imglinear(ws.temb_img, B, m['K'], pk['tab.img'], pk['tab.b'], m['N'], m['NT'], C32=ws.tab, stream=st,
                            tag='jodo_imglinear:tab', skip_if_zero=nonuni)
+        if EQUI_LIN:   # uniform conditioning: coord_mlp.0 composed into input_lin for every block from the step's table row
+            _lib.call('jodo_equi_compose', ctypes.c_void_p(self._compose_items(pk).data_ptr()), _c(d.L), _lib.ptr(ws.tab),
+                      ctypes.c_void_p(nonuni), st)
         # ---- per atom: packed inputs, node embedding (slice 0 of the concatenated atom hiddens)
         _lib.call('jodo_gather_nodes', _lib.ptr(xh), _lib.ptr(cond_x), ctypes.byref(ps), _c(d.inn), _c(ws.kin),
                   _lib.ptr(ws.xin), _lib.ptr(ws.pos[0]), _lib.ptr(ws.mol_bad), st)
@@ -326,11 +346,17 @@ class _DGTBase(nn.Module):
                                      ws.flags.data_ptr() + 8, pk.host[p + 'n2e.bias'], pk.host[p + 'ff3.b'],
                                      pk.host[p + 'ff4.b'], pk.host[p + 'edge_l.b'])
             _lib.call('jodo_edge_update', ctypes.byref(ua), st)
+            # coordinate update (JODO_EQUI_LIN=1: the composed kernel under uniform conditioning, the general one
+            # otherwise; each tests the device flag and one of them returns at once)
+            if EQUI_LIN:
+                la = _lib.EquiLinArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), plan.Nn, _lib.dp(ws.extra),
+                                      pk.ptr(p + 'win.img'), pk.ptr(p + 'wce.img'), pk.ptr(p + 'eqc'), meta['coord_scale'][l],
+                                      nonuni, pk.host[p + 'gbf4'])
+                _lib.call('jodo_equi_lin', ctypes.byref(la), st)
             qa = _lib.EquiArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), plan.Nn,
                                _lib.dp(ws.tab), ld_tab, off, _lib.dp(ws.extra), pk.ptr(p + 'win.img'),
                                pk.ptr(p + 'wc0h.img'), pk.ptr(p + 'w2.img'), pk.ptr(p + 'w2x.img'), meta['coord_scale'][l],
-                               ws.flags.data_ptr() + 8,
-                               pk.host[p + 'gbf4'], pk.host[p + 'b0h'])
+                               nonuni, pk.host[p + 'gbf4'], pk.host[p + 'b0h'], 1 if EQUI_LIN else 0)
             _lib.call('jodo_equi', ctypes.byref(qa), st)
             _lib.call('jodo_com', _lib.ptr(pout), ctypes.byref(ps), st)
             if dbg is not None:

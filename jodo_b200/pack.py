@@ -87,6 +87,11 @@ def matrix_to_image(m: torch.Tensor) -> torch.Tensor:
 # Whole-model packing: reference state dict -> one flat fp32 device buffer + named offsets
 # =====================================================================================================
 TAB_HEAD = 16
+# A/B switch: the coordinate kernel with coord_mlp.0 composed into input_lin under uniform conditioning (csrc/equi_lin.cu).
+# Correct (parity-green), measured SLOWER than csrc/equi.cu on B200 (0.40 vs 0.37 ms per launch at QM9 B = 2500: it trades the
+# K = 256 tensor-core product, which was never the bound, for a second 1 KB-per-edge gather, which is); off by default.
+import os as _os
+EQUI_LIN = _os.environ.get('JODO_EQUI_LIN') == '1'
 
 
 def tab_layer_stride(D):
@@ -381,7 +386,20 @@ def pack_model(sd, dims, device, fused=None):
         lin(p + 'ff1', f'{b}.ff_linear1', 256)
         lin(p + 'ff2', f'{b}.ff_linear2', 128)                 # K = r D is deep: narrower tiles balance the SMs
         wi, bi = W(f'{b}.equi_update.input_lin'), Bv(f'{b}.equi_update.input_lin')      # [D, 2D + 2ed]: [h_row | h_col | e | dist]
-        add_lin(p + 'ab', [(wi[:, :D], 0, 0), (wi[:, D:2 * D], D, 0)], [(bi, 0)], 256, 2 * D, D)   # the bias rides on the h[row] part
+        # the bias rides on the h[row] part
+        if EQUI_LIN:
+            # N tiles 2, 3 (and bias [2D, 3D)) hold the same parts composed with coord_mlp.0 for the uniform-conditioning
+            # coordinate kernel; jodo_equi_compose rewrites them at every call (csrc/equi_lin.cu)
+            add_lin(p + 'ab', [(wi[:, :D], 0, 0), (wi[:, D:2 * D], D, 0)], [(bi, 0)], 256, 2 * D, D, n_pad=4 * D)
+            pk.mat(p + 'c0.w32', D, D, [(W(f'{b}.equi_update.coord_mlp.0'), 0, 0)])
+            pk.add(p + 'c0.b32', Bv(f'{b}.equi_update.coord_mlp.0'))
+            pk.mat(p + 'wi.w32', D, 2 * D + 2 * ed, [(wi, 0, 0)])
+            pk.add(p + 'wi.b32', bi)
+            pk.mat(p + 'w2.w32', 3, D, [(W(f'{b}.equi_update.coord_mlp.2'), 0, 0)])
+            pk.image_h(p + 'wce.img', D, 2 * ed, D, [])            # composed per call
+            pk.vec(p + 'eqc', 1040, [])                            # d / 2 | coord_mlp.2 rows | GBF pair of the step
+        else:
+            add_lin(p + 'ab', [(wi[:, :D], 0, 0), (wi[:, D:2 * D], D, 0)], [(bi, 0)], 256, 2 * D, D)
         lin(p + 'node_l', f'node_{l}', 64, n_pad=64)
         pk.mat(p + 'gbf', 3, 64, [(mu[1 + l], 0, 0), (c1[1 + l], 1, 0), (c2[1 + l], 2, 0)])
         pk.image_h(p + 'emb.img', ed, 2 * ed, ed, [(W(f'{b}.edge_emb'), 0, 0)])                    # [64, 128]: [dist | e]

@@ -64,6 +64,21 @@ def test_uniform_conditioning_fast_path_matches_general_path():
     flags_gen = int(next(iter(model._plans.values()))[1].flags[2])
     assert flags_uni == 0 and flags_gen == 1
     B = xa.shape[0]
-    # molecules 0..B-2 see bit-identical conditioning rows on both paths
-    assert float((xa[:B - 1] - xb[:B - 1]).abs().max()) < 1e-5 * float(xa.abs().max())
-    assert float((ea[:B - 1] - eb[:B - 1]).abs().max()) < 1e-5 * float(ea.abs().max())
+    # Molecules 0..B-2 see identical conditioning rows on both paths, and the kernels do the same arithmetic on them --
+    # except with JODO_EQUI_LIN=1, where the uniform path composes coord_mlp.0 into input_lin (csrc/equi_lin.cu) and
+    # the two agree to the fp16 operand rounding only.  Either way each path agrees with the fp64 oracle.
+    from jodo_b200.pack import EQUI_LIN
+    tol_ab = 1e-3 if EQUI_LIN else 1e-5
+    assert float((xa[:B - 1] - xb[:B - 1]).abs().max()) < tol_ab * float(xa.abs().max())
+    assert float((ea[:B - 1] - eb[:B - 1]).abs().max()) < tol_ab * float(ea.abs().max())
+    from helpers import oracle_forward
+    sd = golden_weights(g, cfg)
+    for nl_, (x_, e_), tag in ((nl, (xa, ea), 'uniform'), (nl2, (xb, eb), 'general')):
+        oi = dict(g['inputs'])
+        oi['noise_level'] = nl_.cpu()
+        ox, oe = oracle_forward(sd, cfg, oi, torch.float64)
+        ex = float((x_.double().cpu() - ox).abs().max() / ox.abs().max())
+        ee = float((e_.double().cpu() - oe).abs().max() / oe.abs().max())
+        px = float((x_.double().cpu() - ox)[..., :3].abs().max() / ox[..., :3].abs().max())
+        print(f'{tag} path vs fp64 oracle: x {ex:.2e} (positions {px:.2e})  e {ee:.2e}')
+        assert ex < TOL and ee < TOL and px < TOL

@@ -19,7 +19,7 @@ x, ex, cx, cex = b['xh'].to(dev), b['edge_x'].to(dev), None, None
 for i in range(3):
     x, ex, _, _, cx, cex = smp.step(model, i, x, ex, nm, em, cx, cex)
 L = _lib.lib()
-for name in ('equi2', 'equi', 'attn', 'edge_update'):
+for name in ('equi_lin', 'equi2', 'equi', 'attn', 'edge_update'):
     fn = getattr(L, f'jodo_debug_{name}_phases', None)
     if fn is None:
         continue
