@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 10
+#define JODO_ABI_VERSION 11
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -361,6 +361,9 @@ typedef struct jodo_wide_attn_args {                    /* TransMixLayer message
   const int* row_pair;                    /* optional: G and extra are stored per unordered pair; row_pair[row] is the pair row of edge row `row` */
   float* hnode;                           /* out [Nn, D] */
   int max_gl;                             /* largest partner count (sizes the per-CTA logit buffer; <= 255) */
+  const int* mol_start; int B, n_max;     /* optional ([B + 1] first packed atom per molecule, molecules, largest molecule): enables
+                                             the molecule-staged kernel (k | v of a molecule in shared memory, online softmax) for
+                                             the head layouts it is built for; otherwise one CTA per target atom */
 } jodo_wide_attn_args;
 
 int jodo_wide_embed_in(const jodo_wide_embed_args* a, void* stream);

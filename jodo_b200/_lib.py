@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 10:
+        if _lib.jodo_abi_version() != 11:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -170,7 +170,7 @@ class WideLnArgs(ctypes.Structure):
 class WideAttnArgs(ctypes.Structure):
     _fields_ = [('Nn', _I), ('D', _I), ('H', _I), ('X', _I), ('sc', _I), ('grp_row0', _P), ('grp_len', _P), ('row_j', _P),
                 ('qkv', _P), ('ldq', _I), ('k_off', _I), ('v_off', _I), ('G', _P), ('ldg', _I), ('g1_off', _I),
-                ('extra', _P), ('row_pair', _P), ('hnode', _P), ('max_gl', _I)]
+                ('extra', _P), ('row_pair', _P), ('hnode', _P), ('max_gl', _I), ('mol_start', _P), ('B', _I), ('n_max', _I)]
 
 
 def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None, row_mol=None,

@@ -9,6 +9,7 @@
 //
 // Reference lines restated: models/mol_gnn.py:270-322 (EquivariantMixBlock), :71-94 (MultiCondEquiUpdate),
 // models/layers.py:131-186 (TransMixLayer), :291-295,328-334 (CondGaussianLayer), models/mol_gnn.py:517-557, 571-579.
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -471,6 +472,8 @@ cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st) {
   return WIDE_OK();
 }
 cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st) {
+  static const bool per_target = std::getenv("JODO_WIDE_ATTN_PER_TARGET") != nullptr;       // A/B switch
+  if (!per_target && wide_attn_mol_ok(a)) return launch_wide_attn_mol(a, st);
   const int S = a.H - a.X, qkp = (S * a.sc + 31) & ~31;
   const size_t smem = (size_t)(5 * qkp + a.max_gl * a.H) * sizeof(float) + 2 * a.max_gl * sizeof(int);
   k_wide_attn<<<a.Nn, WA_THREADS, smem, st>>>(a);

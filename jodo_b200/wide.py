@@ -255,7 +255,7 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
         ilin(p + 'qkv', ws.hn_img, Nn, C16=ws.qkv)
         aa = _lib.WideAttnArgs(Nn, D, d.H, d.X, d.sc, dp(ws.grp_row0), dp(ws.grp_len), dp(plan.row_j), dp(ws.qkv), ws.ldq,
                                meta['qkp'], 2 * meta['qkp'], dp(ws.G), ws.ldg, meta['qkp'], dp(ws.extra), dp(plan.row_pair),
-                               dp(ws.hnode), max(plan.max_group, 1))
+                               dp(ws.hnode), max(plan.max_group, 1), dp(plan.mol_start), B, int(plan.n_nodes.max()))
         _lib.call('jodo_wide_attn', ctypes.byref(aa), st)
         # node path
         ln(Nn, D, D, h, (o + 3 * D, o + 4 * D), plan.node_mol, out_img=ws.h2_img, out32=ws.h2, y=ws.hnode, gate=o + 2 * D,
