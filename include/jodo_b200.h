@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 11
+#define JODO_ABI_VERSION 12
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -76,6 +76,18 @@ typedef struct jodo_imglinear_args {
   int c16_piece_major;                    /* != 0: C16 is [N/8][ldc16 rows][8] -- 16-byte column pieces with the rows of one
                                              piece contiguous, so that lanes gathering consecutive atoms read whole lines */
   void* Cimg;                             /* fp16 operand image output [ceil(M/128)][N/64][128][128 B] or null */
+  /* optional placement of the image output inside a wider image (0 = the defaults N, 0, N): the destination has cimg_k
+   * columns, output column c goes to column cimg_col0 + c, and only columns c < cimg_ncols are written (cimg_col0 % 8 == 0,
+   * cimg_ncols % 4 == 0).  Cimg2 (may be null): a second image destination with its own placement.  Used by the wide path:
+   * the edge FFN writes the new edge state straight into the [e | dist] operand of the next GEMMs and into its slot of the
+   * edge heads' operand (no separate conversion pass). */
+  int cimg_k, cimg_col0, cimg_ncols;
+  void* Cimg2; int cimg2_k, cimg2_col0, cimg2_ncols;
+  /* optional fused row dot products (JODO_EPI_ACT only, may be null): dot_out[row, 4 s + k] = sum over the columns of
+   * slot s of act(acc + bias)[row, c] * dot_w[k * N + c], k < 3, slot s = (column tile) * 2 + (column half): the caller adds
+   * the 2 N / NT slots.  coord_mlp.2 (three outputs, reference models/mol_gnn.py:66-69, 82) rides on coord_mlp.0's epilogue, so
+   * the SiLU output never goes to HBM.  With dot_out no other output is required. */
+  const float* dot_w; float* dot_out; int ld_dot;
 } jodo_imglinear_args;
 int jodo_imglinear(const jodo_imglinear_args* a, void* stream);
 
@@ -373,9 +385,10 @@ int jodo_wide_dist(const jodo_plan* p, const float* pos4, const float* tab, int 
                    int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, void* stream);   /* mol_gnn.py:284-286 */
 int jodo_wide_ln(const jodo_wide_ln_args* a, void* stream);
 int jodo_wide_attn(const jodo_wide_attn_args* a, void* stream);
-int jodo_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
+int jodo_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc, int nslots,
                        const uint8_t* extra, const int* row_pair, int X, float coord_scale, const float* pos_in4, float* pos_out4,
-                       int Nn, void* stream);                   /* mol_gnn.py:82-92; extra[row_pair[row]] when row_pair is given */
+                       int Nn, void* stream);                   /* mol_gnn.py:82-92; extra[row_pair[row]] when row_pair is given;
+                                                                   c3[row, 4 s + k], s < nslots: partial coord_mlp.2 outputs to add */
 int jodo_wide_head_out(const jodo_plan* p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,
                        int both, float* out_dense, void* stream);   /* mol_gnn.py:574-578; both != 0: p is the pair plan, every
                                                                      row writes e_hat[b, i, j] and e_hat[b, j, i] */

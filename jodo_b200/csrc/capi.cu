@@ -292,7 +292,7 @@ int jodo_wide_dist(const jodo_plan* p, const float* pos4, const float* tab, int 
   if (!p) return fail("jodo_wide_dist: null plan");
   if (const char* m = check_plan(*p)) return fail(m);
   if (!pos4 || !tab || !gbf || ed <= 0 || ed % 8 || ld_gbf < ed || ld_gbf % 4) return fail("jodo_wide_dist: bad arguments");
-  if (!img_ok(img1, K1, col1, ed) || !img_ok(img2, K2, col2, ed)) return fail("jodo_wide_dist: bad image");
+  if (!img_ok(img1, K1, col1, ed) || (img2 && !img_ok(img2, K2, col2, ed))) return fail("jodo_wide_dist: bad image");
   JODO_LAUNCH(jodo::launch_wide_dist(*p, pos4, tab, ld_tab, off_gbf, gbf, ld_gbf, ed, img1, K1, col1, img2, K2, col2, S(stream)),
               "jodo_wide_dist");
 }
@@ -316,12 +316,13 @@ int jodo_wide_attn(const jodo_wide_attn_args* a, void* stream) {
   if (!a->grp_row0 || !a->grp_len || !a->row_j || !a->qkv || !a->G || !a->extra || !a->hnode) return fail("jodo_wide_attn: null buffer");
   JODO_LAUNCH(jodo::launch_wide_attn(*a, S(stream)), "jodo_wide_attn");
 }
-int jodo_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
+int jodo_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc, int nslots,
                        const uint8_t* extra, const int* row_pair, int X, float coord_scale, const float* pos_in4, float* pos_out4,
                        int Nn, void* stream) {
-  if (!grp_row0 || !grp_len || !row_j || !c3 || !extra || !pos_in4 || !pos_out4 || Nn <= 0 || X < 0 || X > 8 || ldc < 1 + X)
+  if (!grp_row0 || !grp_len || !row_j || !c3 || !extra || !pos_in4 || !pos_out4 || Nn <= 0 || X < 0 || X > 2 || nslots < 1 ||
+      ldc < 4 * nslots || ldc < 1 + X)
     return fail("jodo_wide_equi_out: bad arguments");
-  JODO_LAUNCH(jodo::launch_wide_equi_out(grp_row0, grp_len, row_j, c3, ldc, extra, row_pair, X, coord_scale, pos_in4, pos_out4, Nn, S(stream)),
+  JODO_LAUNCH(jodo::launch_wide_equi_out(grp_row0, grp_len, row_j, c3, ldc, nslots, extra, row_pair, X, coord_scale, pos_in4, pos_out4, Nn, S(stream)),
               "jodo_wide_equi_out");
 }
 int jodo_wide_head_out(const jodo_plan* p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,

@@ -47,8 +47,10 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 
 // MODE < 0: every epilogue option is a run-time flag.  MODE >= 0 fixes them at compile time (the four combinations
 // a DGT block uses), which removes the predicated paths from the epilogue's dependent instruction stream:
-//   bits [0,2) epilogue | bit 2 fp32 rows | bit 3 fp16 rows | bit 4 fp16 image
-constexpr int il_mode(int epi, bool c32, bool c16, bool cimg) { return epi | (c32 ? 4 : 0) | (c16 ? 8 : 0) | (cimg ? 16 : 0); }
+//   bits [0,2) epilogue | bit 2 fp32 rows | bit 3 fp16 rows | bit 4 fp16 image | bit 5 second image | bit 6 fused row dots
+constexpr int il_mode(int epi, bool c32, bool c16, bool cimg, bool cimg2 = false, bool dot = false) {
+  return epi | (c32 ? 4 : 0) | (c16 ? 8 : 0) | (cimg ? 16 : 0) | (cimg2 ? 32 : 0) | (dot ? 64 : 0);
+}
 
 template <int MODE, int ACT = ACT_SILU>
 __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
@@ -144,6 +146,8 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
     const bool has32 = MODE < 0 ? a.C32 != nullptr : (MODE & 4) != 0;
     const bool has16 = MODE < 0 ? a.C16 != nullptr : (MODE & 8) != 0;
     const bool hasimg = MODE < 0 ? a.Cimg != nullptr : (MODE & 16) != 0;
+    const bool hasimg2 = MODE < 0 ? a.Cimg2 != nullptr : (MODE & 32) != 0;
+    const bool hasdot = MODE < 0 ? a.dot_out != nullptr : (MODE & 64) != 0;
     const int act = a.act_out;
     const float* __restrict__ bias = a.bias;
     const float* __restrict__ aux = a.aux;
@@ -151,7 +155,13 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
     float* __restrict__ C32 = a.C32;
     uint16_t* __restrict__ C16 = static_cast<uint16_t*>(a.C16);
     uint8_t* __restrict__ Cimg = static_cast<uint8_t*>(a.Cimg);
-    const int ld_aux = a.ld_aux, ld_gate = a.ld_gate, ldc32 = a.ldc32, ldc16 = a.ldc16, Mrows = a.M, nchunk_out = a.N / 64;
+    uint8_t* __restrict__ Cimg2 = static_cast<uint8_t*>(a.Cimg2);
+    const int ld_aux = a.ld_aux, ld_gate = a.ld_gate, ldc32 = a.ldc32, ldc16 = a.ldc16, Mrows = a.M;
+    // placement of the image outputs (normalised by the launcher: k = destination columns, col0 = first column, ncols = limit)
+    const int nco1 = a.cimg_k / 64, c01 = a.cimg_col0, nc1 = a.cimg_ncols;
+    const int nco2 = a.cimg2_k / 64, c02 = a.cimg2_col0, nc2 = a.cimg2_ncols;
+    const float* __restrict__ dot_w = a.dot_w;
+    float* __restrict__ dot_out = a.dot_out;
     const bool c16_pm = a.c16_piece_major != 0;
     const bool gate_row0 = a.nonuni != nullptr && *a.nonuni == 0;       // uniform conditioning: every molecule's gate row is row 0
     uint8_t* stg = stg_base + team * 2 * IL_STG_BUF;
@@ -166,6 +176,11 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) mol[it] = (!gate_row0 && (gr0 + 16 * it) < Mrows) ? __ldg(a.row_mol + gr0 + 16 * it) : 0;
       }
+      float dacc[8][3];                              // fused row dots: this thread's 8 rows x 3 outputs over the team's columns
+      if (hasdot) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) dacc[it][0] = dacc[it][1] = dacc[it][2] = 0.f;
+      }
       mbar_wait(&bar_tfull[ab], aph);
       tc_fence_after();
       for (int c0 = team * cw; c0 < (team + 1) * cw; c0 += 32, sb ^= 1u) {
@@ -174,6 +189,12 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
         // loads that do not depend on the accumulator go first
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + col));
+        float4 dw0, dw1, dw2;
+        if (hasdot) {
+          dw0 = __ldg(reinterpret_cast<const float4*>(dot_w + col));
+          dw1 = __ldg(reinterpret_cast<const float4*>(dot_w + a.N + col));
+          dw2 = __ldg(reinterpret_cast<const float4*>(dot_w + 2 * a.N + col));
+        }
         float4 y[8], g[8];
         if (epi == EPI_GATED_RES) {
 #pragma unroll
@@ -196,8 +217,10 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
         }
         named_bar_sync(1 + team, 128);             // staging buffer sb complete (the other buffer may still be read)
         const uint8_t* src = buf + r0 * IL_STG_ROW + c4 * 4;
-        uint8_t* img = hasimg ? Cimg + ((size_t)m * nchunk_out + (col >> 6)) * IL_A_STAGE + ((col & 4) << 1) : nullptr;
-        const int piece = (col & 63) >> 3;
+        const int colA = col + c01, colB = col + c02;
+        uint8_t* img = (hasimg && col < nc1) ? Cimg + ((size_t)m * nco1 + (colA >> 6)) * IL_A_STAGE + ((colA & 4) << 1) : nullptr;
+        uint8_t* img2 = (hasimg2 && col < nc2) ? Cimg2 + ((size_t)m * nco2 + (colB >> 6)) * IL_A_STAGE + ((colB & 4) << 1) : nullptr;
+        const int piece = (colA & 63) >> 3, piece2 = (colB & 63) >> 3;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r = r0 + 16 * it;
@@ -218,16 +241,55 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
             o.z = fmaf(g[it].z, o.z, y[it].z); o.w = fmaf(g[it].w, o.w, y[it].w);
           }
           if (!live) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (hasdot) {
+            dacc[it][0] = fmaf(o.x, dw0.x, fmaf(o.y, dw0.y, fmaf(o.z, dw0.z, fmaf(o.w, dw0.w, dacc[it][0]))));
+            dacc[it][1] = fmaf(o.x, dw1.x, fmaf(o.y, dw1.y, fmaf(o.z, dw1.z, fmaf(o.w, dw1.w, dacc[it][1]))));
+            dacc[it][2] = fmaf(o.x, dw2.x, fmaf(o.y, dw2.y, fmaf(o.z, dw2.z, fmaf(o.w, dw2.w, dacc[it][2]))));
+          }
           if (has32 && live) *reinterpret_cast<float4*>(C32 + (size_t)gr * ldc32 + col) = o;
           const uint2 hh = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
-          if ((has16 || hasimg) && fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))) > 65504.f)
+          if ((has16 || hasimg || hasimg2) && fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))) > 65504.f)
             atomicAdd(&g_sat_imglinear, 1u);       // an fp16 operand saturated (cvt.satfinite clamps silently): count it
           if (has16 && live) {
             if (c16_pm) *reinterpret_cast<uint2*>(C16 + ((size_t)(col >> 3) * ldc16 + gr) * 8 + (col & 7)) = hh;
             else *reinterpret_cast<uint2*>(C16 + (size_t)gr * ldc16 + col) = hh;
           }
-          if (hasimg) *reinterpret_cast<uint2*>(img + img_piece(r, 0, piece, IL_A_STAGE)) = hh;
+          if (hasimg && img) *reinterpret_cast<uint2*>(img + img_piece(r, 0, piece, IL_A_STAGE)) = hh;
+          if (hasimg2 && img2) *reinterpret_cast<uint2*>(img2 + img_piece(r, 0, piece2, IL_A_STAGE)) = hh;
         }
+      }
+      if (hasdot) {
+        // The 8 lanes of a row group hold partial sums of the same 8 rows x 3 outputs.  Butterfly with halving: after the
+        // exchanges over lane bits 2, 1, 0 (12 + 6 + 3 shuffles) lane s of the group holds the three complete sums of row s.
+        const int slot = n * 2 + team;
+        float w12[12], w6[6], w3[3];
+        {
+          const bool hi = (lane & 4) != 0;
+#pragma unroll
+          for (int i = 0; i < 12; ++i) {
+            const float lo_v = dacc[i / 3][i % 3], hi_v = dacc[4 + i / 3][i % 3];
+            const float keep = hi ? hi_v : lo_v, send = hi ? lo_v : hi_v;
+            w12[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+        }
+        {
+          const bool hi = (lane & 2) != 0;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const float keep = hi ? w12[6 + i] : w12[i], send = hi ? w12[i] : w12[6 + i];
+            w6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+        }
+        {
+          const bool hi = (lane & 1) != 0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float keep = hi ? w6[3 + i] : w6[i], send = hi ? w6[i] : w6[3 + i];
+            w3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+        }
+        const int gr = gr0 + 16 * (lane & 7);
+        if (gr < Mrows) *reinterpret_cast<float4*>(dot_out + (size_t)gr * a.ld_dot + 4 * slot) = make_float4(w3[0], w3[1], w3[2], 0.f);
       }
       tc_fence_before();
       __syncwarp();
@@ -254,7 +316,15 @@ const char* check_imglinear(const ImgLinearArgs& a) {
   if (a.N <= 0 || a.N % a.NT) return "imglinear: N must be a multiple of NT";
   if (!a.Aimg || !a.Wimg) return "imglinear: operand image missing";
   if ((reinterpret_cast<uintptr_t>(a.Aimg) | reinterpret_cast<uintptr_t>(a.Wimg)) & 127) return "imglinear: images must be 128-byte aligned";
-  if (!a.C32 && !a.C16 && !a.Cimg) return "imglinear: no output";
+  if (!a.C32 && !a.C16 && !a.Cimg && !a.dot_out) return "imglinear: no output";
+  if (a.dot_out && (!a.dot_w || a.epi != EPI_ACT || a.ld_dot < 4 * 2 * (a.N / a.NT) || (a.ld_dot % 4) || ((reinterpret_cast<uintptr_t>(a.dot_w) | reinterpret_cast<uintptr_t>(a.dot_out)) & 15)))
+    return "imglinear: fused row dots need dot_w, JODO_EPI_ACT and ld_dot >= 8 N / NT";
+  if (a.Cimg2 && !a.Cimg) return "imglinear: Cimg2 needs Cimg";
+  if (a.Cimg && a.cimg_k && ((a.cimg_k % 64) || (a.cimg_col0 % 8) || (a.cimg_ncols % 4) || a.cimg_col0 + a.cimg_ncols > a.cimg_k || a.cimg_ncols > a.N))
+    return "imglinear: bad placement of the image output";
+  if (a.Cimg2 && ((reinterpret_cast<uintptr_t>(a.Cimg2) & 127) || a.cimg2_k <= 0 || (a.cimg2_k % 64) || (a.cimg2_col0 % 8) || (a.cimg2_ncols % 4) ||
+                  a.cimg2_col0 + a.cimg2_ncols > a.cimg2_k || a.cimg2_ncols > a.N))
+    return "imglinear: bad placement of the second image output";
   if (a.C32 && ((a.ldc32 % 4) || (reinterpret_cast<uintptr_t>(a.C32) & 15))) return "imglinear: fp32 output must be 16-byte aligned rows";
   if (a.C16 && !a.c16_piece_major && ((a.ldc16 % 8) || (reinterpret_cast<uintptr_t>(a.C16) & 15))) return "imglinear: fp16 output must be 16-byte aligned rows";
   if (a.C16 && a.c16_piece_major && (a.ldc16 < a.M || (reinterpret_cast<uintptr_t>(a.C16) & 15))) return "imglinear: piece-major fp16 output needs ldc16 >= M rows";
@@ -275,10 +345,12 @@ cudaError_t launch_mode(const ImgLinearArgs& a, int grid, cudaStream_t stream) {
 }
 }  // namespace
 
-cudaError_t launch_imglinear(const ImgLinearArgs& a, int num_sms, cudaStream_t stream) {
+cudaError_t launch_imglinear(const ImgLinearArgs& a_in, int num_sms, cudaStream_t stream) {
+  ImgLinearArgs a = a_in;
+  if (a.cimg_k == 0) { a.cimg_k = a.N; a.cimg_col0 = 0; a.cimg_ncols = a.N; }       // default placement: the image is the output
   const int units = ((a.M + TILE_ROWS - 1) / TILE_ROWS) * (a.N / a.NT);
   const int grid = units < num_sms ? units : num_sms;
-  const int mode = il_mode(a.epi, a.C32 != nullptr, a.C16 != nullptr, a.Cimg != nullptr);
+  const int mode = il_mode(a.epi, a.C32 != nullptr, a.C16 != nullptr, a.Cimg != nullptr, a.Cimg2 != nullptr, a.dot_out != nullptr);
   const bool silu_or_none = a.epi != EPI_ACT || a.act_out == ACT_SILU;
   if (silu_or_none) {
     switch (mode) {
@@ -287,6 +359,8 @@ cudaError_t launch_imglinear(const ImgLinearArgs& a, int num_sms, cudaStream_t s
       case il_mode(EPI_ACT, false, false, true): return launch_mode<il_mode(EPI_ACT, false, false, true)>(a, grid, stream);          // ff_linear1
       case il_mode(EPI_GATED_RES, true, false, true): return launch_mode<il_mode(EPI_GATED_RES, true, false, true)>(a, grid, stream);  // ff_linear2
       case il_mode(EPI_GATED_RES, true, false, false): return launch_mode<il_mode(EPI_GATED_RES, true, false, false)>(a, grid, stream);  // wide: ff_linear4, head accumulation
+      case il_mode(EPI_GATED_RES, true, false, true, true): return launch_mode<il_mode(EPI_GATED_RES, true, false, true, true)>(a, grid, stream);  // wide: ff_linear4 -> e32 + [e | dist] + heads' operand
+      case il_mode(EPI_ACT, false, false, false, false, true): return launch_mode<il_mode(EPI_ACT, false, false, false, false, true)>(a, grid, stream);  // wide: coord_mlp.0 + coord_mlp.2 dots
       default: break;
     }
   } else if (a.act_out == ACT_TANH && mode == il_mode(EPI_ACT, false, true, false)) {

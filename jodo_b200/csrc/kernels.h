@@ -146,7 +146,7 @@ cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st);
 cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st);
 bool wide_attn_mol_ok(const WideAttnArgs& a);                                   // wide_attn.cu: molecule-staged variant
 cudaError_t launch_wide_attn_mol(const WideAttnArgs& a, cudaStream_t st);
-cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
+cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc, int nslots,
                                  const uint8_t* extra, const int* row_pair, int X, float coord_scale, const float* pos_in,
                                  float* pos_out, int Nn, cudaStream_t st);
 cudaError_t launch_wide_head_out(const Plan& p, const float* x, int ldx, int hw, const float* w4, const float* b4, int ch,

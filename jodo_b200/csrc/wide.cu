@@ -183,7 +183,7 @@ __global__ void k_wide_dist(Plan p, const float4* __restrict__ pos, const float*
     }
     const uint4 o = wpack8(v);
     *wimg(img1, row, col1 + 8 * q, K1) = o;
-    *wimg(img2, row, col2 + 8 * q, K2) = o;
+    if (img2) *wimg(img2, row, col2 + 8 * q, K2) = o;
   }
 }
 
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
 // ---- coordinate update tail (models/mol_gnn.py:82-92): inv = mean([1, extra] * tanh(coord_mlp.2 output)),
 // pos_r += sum_c (pos_r - pos_c) / max(|.|, 1e-8) * scale * inv.  One thread per atom.
 __global__ void k_wide_equi_out(const int* __restrict__ grp_row0, const int* __restrict__ grp_len,
-                                const int* __restrict__ row_j, const float* __restrict__ c3, int ldc,
+                                const int* __restrict__ row_j, const float* __restrict__ c3, int ldc, int nslots,
                                 const uint8_t* __restrict__ extra, const int* __restrict__ row_pair, int X, float coord_scale,
                                 const float4* __restrict__ pos_in, float4* __restrict__ pos_out, int Nn) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,8 +398,13 @@ __global__ void k_wide_equi_out(const int* __restrict__ grp_row0, const int* __r
     const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
     const float* c = c3 + (size_t)R * ldc;
     const uint8_t bits = extra[row_pair ? row_pair[R] : R];
-    float inv = tanhf(c[0]);
-    for (int x = 0; x < X; ++x) inv += ((bits >> x) & 1) ? tanhf(c[1 + x]) : 0.f;
+    float cs[3] = {0.f, 0.f, 0.f};                  // coord_mlp.2 outputs: the partial sums of the GEMM's column slots, in order
+    for (int s = 0; s < nslots; ++s) {
+      const float4 q = *reinterpret_cast<const float4*>(c + 4 * s);
+      cs[0] += q.x; cs[1] += q.y; cs[2] += q.z;
+    }
+    float inv = tanhf(cs[0]);
+    for (int x = 0; x < X; ++x) inv += ((bits >> x) & 1) ? tanhf(cs[1 + x]) : 0.f;
     const float f = coord_scale * inv / ((float)(1 + X) * nrm);
     sx = fmaf(dx, f, sx); sy = fmaf(dy, f, sy); sz = fmaf(dz, f, sz);
   }
@@ -479,10 +484,10 @@ cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st) {
   k_wide_attn<<<a.Nn, WA_THREADS, smem, st>>>(a);
   return WIDE_OK();
 }
-cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc,
+cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc, int nslots,
                                  const uint8_t* extra, const int* row_pair, int X, float coord_scale, const float* pos_in,
                                  float* pos_out, int Nn, cudaStream_t st) {
-  k_wide_equi_out<<<(Nn + 127) / 128, 128, 0, st>>>(grp_row0, grp_len, row_j, c3, ldc, extra, row_pair, X, coord_scale,
+  k_wide_equi_out<<<(Nn + 127) / 128, 128, 0, st>>>(grp_row0, grp_len, row_j, c3, ldc, nslots, extra, row_pair, X, coord_scale,
                                                     reinterpret_cast<const float4*>(pos_in), reinterpret_cast<float4*>(pos_out), Nn);
   return WIDE_OK();
 }

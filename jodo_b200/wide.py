@@ -94,10 +94,14 @@ def pack_wide(pk, sd, d, add_lin, lin):
             wi, bi = W(f'{b}.equi_update.input_lin'), Bv(f'{b}.equi_update.input_lin')    # [D, 2D + 2ed]: [h_row | h_col | e | dist]
             add_lin(p + 'ab', [(wi[:, :D], 0, 0), (wi[:, D:2 * D], D, 0)], [(bi, 0)], 128, 2 * D, D)   # bias rides on the h[row] part
             pk.mat(p + 'gbf', 3, EDP, [(mu[1 + l], 0, 1), (c1[1 + l], 1, 1), (c2[1 + l], 2, 1)])
-            lin(p + 'emb', f'{b}.edge_emb', 128)                                            # K = 2ed: [dist | e]
+            # block edge_emb reads cat[dist, e] (mol_gnn.py:287), input_lin's edge part cat[e, dist] (:72): the columns of the
+            # former are reordered so that both GEMMs read ONE operand image [e | dist] (K = 2ed)
+            we_l = W(f'{b}.edge_emb')
+            add_lin(p + 'emb', [(we_l[:, ed:], 0, 0), (we_l[:, :ed], 0, ed)], [(Bv(f'{b}.edge_emb'), 0)], 128, ed, 2 * ed)
             add_lin(p + 'equi_in', [(wi[:, 2 * D:], 0, 0)], [], 128, D, 2 * ed)             # K = 2ed: [e | dist]
             lin(p + 'c0', f'{b}.equi_update.coord_mlp.0', 128)
-            lin(p + 'c2', f'{b}.equi_update.coord_mlp.2', 64, bias=False)                   # N = 64 (1 + X real)
+            # coord_mlp.2 (1 + X outputs, no bias) rides on coord_mlp.0's epilogue as three fp32 row dots (rows beyond 1 + X zero)
+            pk.mat(p + 'c2.w32', 3, D, [(W(f'{b}.equi_update.coord_mlp.2'), 0, 0)])
         add_lin(p + 'g01', [(W(f'{b}.attn_mpnn.lin_edge0'), 0, 0), (W(f'{b}.attn_mpnn.lin_edge1'), qkp, 0)], [], 128, qkp + D, EDP)
         add_lin(p + 'ff3', [(W(f'{b}.ff_linear3'), 0, 0)], [(Bv(f'{b}.ff_linear3'), 0)], 128, f3p, EDP, n_pad=f3p)
         add_lin(p + 'ff4', [(W(f'{b}.ff_linear4'), 0, 0)], [(Bv(f'{b}.ff_linear4'), 0)], 128, ed, f3p)
@@ -146,7 +150,7 @@ class WideWorkspace:
         pimg = lambda k: torch.zeros(RP * k, device=dev, dtype=torch.float16)
         self.A0 = pimg(64 if d.two_d else EDP)
         if not d.two_d:
-            self.A1, self.A4 = pimg(2 * d.ed), pimg(2 * d.ed)
+            self.ED = pimg(2 * d.ed)                              # [e | dist]: operand of block edge_emb and of input_lin's edge part
             self.e1 = zf(RP, EDP)
         self.e32, self.e2 = zf(RP, EDP), zf(RP, EDP)
         self.en_img, self.e2_img = pimg(EDP), pimg(EDP)
@@ -158,8 +162,8 @@ class WideWorkspace:
         self.X2 = zf(RP, EDP)
         if not d.two_d:
             self.U = torch.zeros(RP, D, device=dev, dtype=torch.float16)     # input_lin edge part (pre-LayerNorm), per pair
-            self.u_img, self.c0_img = eimg(D), eimg(D)                       # per directed row
-            self.c3 = zf(R, 64)
+            self.u_img = eimg(D)                                              # per directed row
+            self.c3 = zf(R, 64)                                               # coord_mlp.2 partial outputs: [slot][4]
         self.node_dense_l = plan.node_dense.long()
         self.extra = torch.zeros(RP, device=dev, dtype=torch.uint8)
         self.flags = torch.zeros(4, device=dev, dtype=torch.int32)            # [0] dist flag, [1] nan flag
@@ -223,15 +227,14 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
                             0 if d.two_d else ed, self.edge_th, self.spatial_cut_off, dp(ws.flags), dp(ws.tab), ld_tab,
                             pk.ptr('gbf'), EDP, dp(ws.A0), 64 if d.two_d else EDP, dp(ws.extra))
     _lib.call('jodo_wide_embed_in', ctypes.byref(ea), st)
-    ilin('edge_emb', ws.A0, RP, C32=ws.e32)
     K2 = 2 * ed
     KH = (d.L + 1) * EDP
+    # the fp16 copies of the edge state are written by the GEMM that produces it: the e columns of the [e | dist] operand
+    # and the block's slot of the edge heads' operand (no separate conversion pass)
     if d.two_d:
-        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(RP), _c(ed), P(plan.pair_i), P(ws.EH), _c(KH), _c(0), None, _c(0),
-                  _c(0), None, _c(0), _c(0), st)
+        ilin('edge_emb', ws.A0, RP, C32=ws.e32, Cimg=ws.EH, cimg_place=(KH, 0, ed))
     else:
-        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(RP), _c(ed), P(plan.pair_i), P(ws.A1), _c(K2), _c(ed), P(ws.EH),
-                  _c(KH), _c(0), None, _c(0), _c(0), st)
+        ilin('edge_emb', ws.A0, RP, C32=ws.e32, Cimg=ws.ED, cimg_place=(K2, 0, ed), Cimg2=ws.EH, cimg2_place=(KH, 0, ed))
 
     h = ws.ah[:, :D]
     stride = tab_layer_stride(D)
@@ -246,8 +249,8 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
             ln(RP, ed, EDP, ws.e32, (oe, oe + ed), plan.pair_mol, out_img=ws.en_img, valid=plan.pair_i, tag='e1')
         else:
             _lib.call('jodo_wide_dist', ctypes.byref(pps), P(pin), P(ws.tab), _c(ld_tab), _c(og), P(pk[p + 'gbf']), _c(EDP),
-                      _c(ed), P(ws.A1), _c(K2), _c(0), P(ws.A4), _c(K2), _c(ed), st)
-            ilin(p + 'emb', ws.A1, RP, C32=ws.e1)
+                      _c(ed), P(ws.ED), _c(K2), _c(ed), None, _c(0), _c(0), st)
+            ilin(p + 'emb', ws.ED, RP, C32=ws.e1)
             ln(RP, ed, EDP, ws.e1, (oe, oe + ed), plan.pair_mol, out_img=ws.en_img, valid=plan.pair_i, tag='e1')
         ilin(p + 'g01', ws.en_img, RP, bias=False, epi=_lib.EPI_ACT, act_out=_lib.ACT_TANH, C16=ws.G)
         # attention
@@ -271,24 +274,21 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
         ln(RP, ed, EDP, ws.e32, (oe + 3 * ed, oe + 4 * ed), plan.pair_mol, out_img=ws.e2_img, out32=ws.e2, y=ws.P,
            yi=plan.pair_i, y2=ws.P, y2i=plan.pair_j, ybias=pk[p + 'n2e.bias'], gate=oe + 2 * ed, valid=plan.pair_i, tag='e2')
         ilin(p + 'ff3', ws.e2_img, RP, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.f3_img)
-        ilin(p + 'ff4', ws.f3_img, RP, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.pair_mol,
-             C32=ws.e32)
         if d.two_d:
-            _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(RP), _c(ed), P(plan.pair_i), P(ws.EH), _c(KH), _c((l + 1) * EDP),
-                      None, _c(0), _c(0), None, _c(0), _c(0), st)
+            ilin(p + 'ff4', ws.f3_img, RP, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.pair_mol,
+                 C32=ws.e32, Cimg=ws.EH, cimg_place=(KH, (l + 1) * EDP, ed))
             if dbg is not None:
                 dbg.setdefault('blocks', []).append(dict(hnode=ws.hnode.clone(), h=hout.clone(), e=ws.e32.clone()))
             h = hout
             continue
-        _lib.call('jodo_wide_put', P(ws.e32), _c(EDP), _c(RP), _c(ed), P(plan.pair_i), P(ws.A4), _c(K2), _c(0), P(ws.A1),
-                  _c(K2), _c(ed), P(ws.EH), _c(KH), _c((l + 1) * EDP), st)
+        ilin(p + 'ff4', ws.f3_img, RP, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.pair_mol,
+             C32=ws.e32, Cimg=ws.ED, cimg_place=(K2, 0, ed), Cimg2=ws.EH, cimg2_place=(KH, (l + 1) * EDP, ed))
         # coordinate update: the [e | dist] part of input_lin per pair, everything behind the LayerNorm per directed row
-        ilin(p + 'equi_in', ws.A4, RP, bias=False, C16=ws.U)
+        ilin(p + 'equi_in', ws.ED, RP, bias=False, C16=ws.U)
         ln(R, D, D, ws.U, (oq, oq + D), plan.row_mol, out_img=ws.u_img, y=ws.AB, yi=plan.row_g, y2=ws.AB[:, D:],
            y2i=plan.row_j, valid=plan.row_g, xi=plan.row_pair, tag='equi')
-        ilin(p + 'c0', ws.u_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.c0_img)
-        ilin(p + 'c2', ws.c0_img, R, bias=False, C32=ws.c3)
-        _lib.call('jodo_wide_equi_out', P(ws.grp_row0), P(ws.grp_len), P(plan.row_j), P(ws.c3), _c(64), P(ws.extra),
+        ilin(p + 'c0', ws.u_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, dot_w=pk[p + 'c2.w32'], dot_out=ws.c3)
+        _lib.call('jodo_wide_equi_out', P(ws.grp_row0), P(ws.grp_len), P(plan.row_j), P(ws.c3), _c(64), _c(2 * meta[p + 'c0']['N'] // meta[p + 'c0']['NT']), P(ws.extra),
                   P(plan.row_pair), _c(d.X), ctypes.c_float(meta['coord_scale'][l]), P(pin), P(pout), _c(Nn), st)
         _lib.call('jodo_com', P(pout), ctypes.byref(ps), st)
         if dbg is not None:

@@ -88,7 +88,7 @@ def test_bad_arguments_fail_before_any_launch(lib):
     assert lib.jodo_wide_attn(ctypes.byref(t), None) == 1 and b'bad sizes' in lib.jodo_last_error_string()
     assert lib.jodo_wide_put(None, 0, 0, 0, None, None, 0, 0, None, 0, 0, None, 0, 0, None) == 1
     assert lib.jodo_wide_dist(None, None, None, 0, 0, None, 0, 0, None, 0, 0, None, 0, 0, None) == 1
-    assert lib.jodo_wide_equi_out(None, None, None, None, 0, None, None, 0, ctypes.c_float(0), None, None, 0, None) == 1
+    assert lib.jodo_wide_equi_out(None, None, None, None, 0, 0, None, None, 0, ctypes.c_float(0), None, None, 0, None) == 1
     assert lib.jodo_wide_head_out(None, None, 0, 0, None, None, 0, 0, None, None) == 1
 
 
