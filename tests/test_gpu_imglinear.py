@@ -131,3 +131,60 @@ def test_ln_mod_img_matches_torch():
     yr = image_rows(yimg, D)
     assert torch.equal(yr[:Nn], y.half().float())
     assert float(yr[Nn:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize('M,K,N,NT,epi', [(1000, 256, 128, 128, 'gated'), (700, 128, 128, 128, 'store'), (260, 384, 384, 128, 'act')])
+def test_imglinear_placed_images_and_row_dots(M, K, N, NT, epi):
+    """Placed image outputs (the output columns written at an offset inside wider operand images, only the first
+    `ncols` columns, everything else untouched) and the fused row dot products of the activated output
+    (dot_out[row, 4 slot + k], slots = column tile x column half), against fp64 on the fp16-rounded operands."""
+    g = torch.Generator(device='cuda').manual_seed(M + N)
+    A = torch.randn(M, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) / K ** 0.5
+    b = torch.randn(N, device='cuda', generator=g)
+    Ai, Wi = act_image(A), weight_image_h(W, NT)
+    mt = (M + 127) // 128
+    ref = h(A) @ h(W).t() + b.double()
+    if epi == 'act':
+        dw = torch.randn(3, N, device='cuda', generator=g)
+        nslots = 2 * N // NT
+        dot = torch.full((M, 64), float('nan'), device='cuda')
+        _lib.imglinear(Ai, M, K, Wi, b, N, NT, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, dot_w=dw, dot_out=dot)
+        torch.cuda.synchronize()
+        act = ref * torch.sigmoid(ref)
+        want = act @ dw.double().t()
+        got = dot[:, :4 * nslots].double().reshape(M, nslots, 4)
+        assert float(got[..., 3].abs().max()) == 0.0
+        assert float((got[..., :3].sum(1) - want).abs().max()) < 2e-3 * float(want.abs().max())
+        # every slot is the dot over its own 64 (= NT / 2) columns
+        cw = NT // 2
+        for s in range(nslots):
+            ws_ = act[:, s * cw:(s + 1) * cw] @ dw.double()[:, s * cw:(s + 1) * cw].t()
+            assert float((got[:, s, :3] - ws_).abs().max()) < 2e-3 * float(want.abs().max())
+        return
+    k1, c1, n1 = 192, 0, 96                     # the [e | dist] operand: e columns only
+    k2, c2, n2 = 384, 128, 96                   # a slot of a wider operand
+    img1 = torch.full((mt * 128 * k1,), 7.0, device='cuda', dtype=torch.float16)
+    img2 = torch.full((mt * 128 * k2,), 7.0, device='cuda', dtype=torch.float16)
+    C32 = torch.empty(M, N, device='cuda')
+    kw = {}
+    if epi == 'gated':
+        aux = torch.randn(M, N, device='cuda', generator=g)
+        gate = torch.randn(5, N, device='cuda', generator=g)
+        rm = torch.randint(0, 5, (M,), device='cuda', generator=g, dtype=torch.int32)
+        kw = dict(epi=_lib.EPI_GATED_RES, aux=aux, gate=gate, row_mol=rm)
+        ref = aux.double() + gate.double()[rm.long()] * ref
+    _lib.imglinear(Ai, M, K, Wi, b, N, NT, C32=C32, Cimg=img1, cimg_place=(k1, c1, n1), Cimg2=img2, cimg2_place=(k2, c2, n2), **kw)
+    torch.cuda.synchronize()
+    assert float((C32.double() - ref).abs().max()) < 3e-4 * max(1.0, float(ref.abs().max()))
+    for img, k, c0, nc in ((img1, k1, c1, n1), (img2, k2, c2, n2)):
+        rows = image_rows(img, k)
+        assert float((rows[:M, c0:c0 + nc].double() - ref[:, :nc]).abs().max()) < 1e-2 * max(1.0, float(ref.abs().max()))
+        keep = torch.ones(k, dtype=torch.bool)
+        keep[c0:c0 + nc] = False
+        assert bool((rows[:, keep] == 7.0).all())            # nothing outside the placed columns is touched
+    # bad placements are refused before any launch
+    with pytest.raises(_lib.JodoError):
+        _lib.imglinear(Ai, M, K, Wi, b, N, NT, C32=C32, Cimg=img1, cimg_place=(k1, 4, n1))
+    with pytest.raises(_lib.JodoError):
+        _lib.imglinear(Ai, M, K, Wi, b, N, NT, C32=C32, Cimg=img1, cimg_place=(k1, 128, 96))
