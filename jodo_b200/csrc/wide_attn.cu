@@ -31,9 +31,11 @@ __device__ __forceinline__ void ld_halves(const uint16_t* p, uint32_t (&out)[N /
 template <int EQ, int EV>
 __global__ void __launch_bounds__(WM_THREADS) k_wide_attn_mol(WideAttnArgs a) {
   extern __shared__ __align__(16) uint8_t wm_smem[];
-  const int b = blockIdx.x;
+  // the target chunks of one molecule are adjacent in launch order: a pair's row is read by the CTA of either end, and the
+  // second read then hits L2 (with the molecule index fastest the re-read came from HBM: 1.23 GB per launch for 0.75 GB of rows)
+  const int b = blockIdx.y;
   const int a0 = a.mol_start[b], n = a.mol_start[b + 1] - a0;
-  const int t0 = blockIdx.y * WM_TG;
+  const int t0 = blockIdx.x * WM_TG;
   if (t0 >= n) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int KQ = 32 * EQ, KV = 32 * EV;                 // staged row widths (halves): padded q/k part, value part (= D)
@@ -157,7 +159,7 @@ cudaError_t launch_mol(const WideAttnArgs& a, size_t smem, cudaStream_t st) {
   static DevAttr attr = {};
   cudaError_t e = ensure_dyn_smem(k_wide_attn_mol<EQ, EV>, (int)smem, attr);
   if (e != cudaSuccess) return e;
-  k_wide_attn_mol<EQ, EV><<<dim3(a.B, (a.n_max + WM_TG - 1) / WM_TG), WM_THREADS, smem, st>>>(a);
+  k_wide_attn_mol<EQ, EV><<<dim3((a.n_max + WM_TG - 1) / WM_TG, a.B), WM_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -3,11 +3,15 @@
 OUT=gpurun_out/sanitize
 mkdir -p $OUT
 for tool in memcheck racecheck synccheck; do
-  timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/$tool.log 2>&1
+  timeout 1200 compute-sanitizer --tool $tool --report-api-errors no --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/$tool.log 2>&1
   echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke" $OUT/$tool.log | tail -3
 done
 # the nf = 384 wide path (row kernels of csrc/wide.cu + the GEMM)
 for tool in memcheck racecheck; do
-  timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke('geom_large')" > $OUT/wide_$tool.log 2>&1
+  timeout 1200 compute-sanitizer --tool $tool --report-api-errors no --print-limit 20 python -c "import __graft_entry__ as g; g.smoke('geom_large')" > $OUT/wide_$tool.log 2>&1
   echo "wide $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke" $OUT/wide_$tool.log | tail -3
 done
+# the property classifier's row kernels and the in-kernel Philox update (memcheck over their GPU unit tests)
+timeout 1200 compute-sanitizer --tool memcheck --report-api-errors no --print-limit 20 python -m pytest tests/test_classifier.py tests/test_philox.py -m gpu -q \
+    -k "fixture or oracle_draws or kernel_normals" > $OUT/extra_memcheck.log 2>&1
+echo "extra memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed" $OUT/extra_memcheck.log | tail -3
