@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 12
+#define JODO_ABI_VERSION 13
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -378,6 +378,17 @@ typedef struct jodo_wide_attn_args {                    /* TransMixLayer message
                                              the head layouts it is built for; otherwise one CTA per target atom */
 } jodo_wide_attn_args;
 
+typedef struct jodo_wide_equi_args {     /* fused coordinate branch: LN(input_lin) + modulation -> coord_mlp.0 -> SiLU -> coord_mlp.2 (mol_gnn.py:71-82) */
+  int M, D;                               /* directed edge rows; hidden size (256 or 384) */
+  const void* U; int ldu; const int* xi;  /* fp16 rows of input_lin's edge part (per pair when xi = row_pair is given) */
+  const void* AB; int ldab;               /* fp16 rows per atom: input_lin[:, :D] h + bias | input_lin[:, D:2D] h */
+  const int* row_g; const int* row_j; const int* row_mol;    /* row atom (< 0: padding row), col atom, molecule of every row */
+  const float* tab; int ld_tab, off_shift, off_scale;        /* per-molecule table (scale column holds 1 + scale) */
+  const void* Wimg; const float* bias;    /* coord_mlp.0: fp16 image [D / 128][D / 64][128][128 B], bias [D] */
+  const float* dot_w;                     /* coord_mlp.2 rows [3][D] fp32 (rows beyond 1 + X zero) */
+  float* out; int ld_out;                 /* out[row, 4 s + k], s < 2: partial coord_mlp.2 outputs of the two column halves */
+} jodo_wide_equi_args;
+int jodo_wide_equi(const jodo_wide_equi_args* a, void* stream);
 int jodo_wide_embed_in(const jodo_wide_embed_args* a, void* stream);
 int jodo_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1, void* img2, int K2,
                   int col2, void* img3, int K3, int col3, void* stream);   /* fp32 rows -> fp16 columns [col, col + W) of up to three images */

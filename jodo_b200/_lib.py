@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 12:
+        if _lib.jodo_abi_version() != 13:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -167,6 +167,12 @@ class WideLnArgs(ctypes.Structure):
                 ('y2', _P), ('ldy2', _I), ('y2i', _P), ('ybias', _P), ('tab', _P), ('ld_tab', _I), ('row_mol', _P),
                 ('off_gate', _I), ('off_shift', _I), ('off_scale', _I), ('valid', _P), ('out32', _P), ('ldo', _I),
                 ('out_img', _P), ('y_img', _P), ('x_f16', _I), ('y_f16', _I)]
+
+
+class WideEquiArgs(ctypes.Structure):
+    _fields_ = [('M', _I), ('D', _I), ('U', _P), ('ldu', _I), ('xi', _P), ('AB', _P), ('ldab', _I), ('row_g', _P), ('row_j', _P),
+                ('row_mol', _P), ('tab', _P), ('ld_tab', _I), ('off_shift', _I), ('off_scale', _I), ('Wimg', _P), ('bias', _P),
+                ('dot_w', _P), ('out', _P), ('ld_out', _I)]
 
 
 class WideAttnArgs(ctypes.Structure):

@@ -307,6 +307,11 @@ int jodo_wide_ln(const jodo_wide_ln_args* a, void* stream) {
   if (a->out32 && (a->ldo % 4)) return fail("jodo_wide_ln: bad output stride");
   JODO_LAUNCH(jodo::launch_wide_ln(*a, S(stream)), "jodo_wide_ln");
 }
+int jodo_wide_equi(const jodo_wide_equi_args* a, void* stream) {
+  if (!a) return fail("jodo_wide_equi: null args");
+  if (const char* m = jodo::check_wide_equi(*a)) return fail(m);
+  JODO_LAUNCH(jodo::launch_wide_equi(*a, num_sms(), S(stream)), "jodo_wide_equi");
+}
 int jodo_wide_attn(const jodo_wide_attn_args* a, void* stream) {
   if (!a) return fail("jodo_wide_attn: null args");
   if (a->Nn <= 0 || a->D <= 0 || a->H <= 0 || a->H > 32 || a->X < 0 || a->X >= a->H || a->X > 8 || a->D % a->H || a->sc <= 0 ||

@@ -55,8 +55,10 @@ constexpr int il_mode(int epi, bool c32, bool c16, bool cimg, bool cimg2 = false
 template <int MODE, int ACT = ACT_SILU>
 __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
   if (a.skip_if_zero && *a.skip_if_zero == 0) return;     // uniform conditioning: nothing to do (warp-uniform, before any setup)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // declared with its alignment (not aligned by pointer arithmetic): the compiler must see a shared-memory address, or every
+  // staging access below becomes a generic LD / ST instead of LDS / STS
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int nt = a.NT;
   const int stage_bytes = IL_A_STAGE + nt * 128;
   int stages = IL_RING_BYTES / stage_bytes;

@@ -144,6 +144,9 @@ cudaError_t launch_wide_dist(const Plan& p, const float* pos, const float* tab, 
                              int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, cudaStream_t st);
 cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st);
 cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st);
+using WideEquiArgs = ::jodo_wide_equi_args;
+const char* check_wide_equi(const WideEquiArgs& a);
+cudaError_t launch_wide_equi(const WideEquiArgs& a, int num_sms, cudaStream_t st);           // wide_equi.cu
 bool wide_attn_mol_ok(const WideAttnArgs& a);                                   // wide_attn.cu: molecule-staged variant
 cudaError_t launch_wide_attn_mol(const WideAttnArgs& a, cudaStream_t st);
 cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc, int nslots,

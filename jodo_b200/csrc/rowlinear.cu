@@ -36,8 +36,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 __global__ void __launch_bounds__(RL_THREADS, 2) k_rowlinear(RowLinearArgs a) {
   if (a.only_row0_if_zero && blockIdx.x > 0 && *a.only_row0_if_zero == 0) return;   // uniform conditioning: row 0 is every row
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // declared with its alignment (not aligned by pointer arithmetic): the compiler must see a shared-memory address, or every
+  // staging access below becomes a generic LD / ST instead of LDS / STS
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* a_buf = smem;                                   // RL_STAGES x 16 KB
   uint8_t* w_buf = smem + RL_STAGES * RL_A_STAGE;          // RL_STAGES x 32 KB
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(w_buf + RL_STAGES * RL_W_STAGE);   // [2] weights landed

@@ -44,8 +44,11 @@ __device__ __forceinline__ uint4 we_pack8(const float* v) {
 template <int KC>
 __global__ void __launch_bounds__(WE_THREADS, 1) k_wide_equi(WideEquiArgs a) {
   constexpr int D = 64 * KC, NTN = D / 128, PH = D / 16;       // PH = 16-byte pieces per half row
-  extern __shared__ uint8_t we_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(we_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int BT = PH % 6 == 0 ? 6 : 4;                      // pieces per load batch of the LayerNorm threads
+  // declared with its alignment (not aligned by pointer arithmetic): the compiler must see a shared-memory address, or every
+  // staging access below becomes a generic LD / ST instead of LDS / STS
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* A = smem;                                            // [KC][128][128 B]
   uint8_t* ring = A + KC * WE_CHUNK;                            // WE_STAGES weight chunks
   uint8_t* stg_base = ring + WE_STAGES * WE_CHUNK;
@@ -56,6 +59,7 @@ __global__ void __launch_bounds__(WE_THREADS, 1) k_wide_equi(WideEquiArgs a) {
   uint64_t* bar_tfull = bar_aempty + 1;                         // accumulators complete
   uint64_t* bar_tempty = bar_tfull + 1;                         // 8 arrivals: the epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 1);
+  float* mods = reinterpret_cast<float*>(stg_base + WE_STG_BYTES + 256);     // [2 D]: shift | 1 + scale of the tile's first molecule
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles = (a.M + TILE_ROWS - 1) / TILE_ROWS;
@@ -193,16 +197,29 @@ __global__ void __launch_bounds__(WE_THREADS, 1) k_wide_equi(WideEquiArgs a) {
       const uint4* pu = reinterpret_cast<const uint4*>(U + (size_t)pr * a.ldu) + half * PH;
       const uint4* pa = reinterpret_cast<const uint4*>(AB + (size_t)(valid ? g : 0) * a.ldab) + half * PH;
       const uint4* pb = reinterpret_cast<const uint4*>(AB + (size_t)j * a.ldab + D) + half * PH;
+      // the modulation rows (shift | 1 + scale) of the tile's first molecule, staged once per tile: most rows of a tile belong
+      // to it (a molecule of n atoms owns n (n - 1) consecutive rows); rows of other molecules read the table in HBM / L2
+      const int R0 = min(tile * TILE_ROWS, a.M - 1);
+      int m0 = 0;
+      {
+        const int g0 = __ldg(a.row_g + R0);
+        m0 = g0 >= 0 ? __ldg(a.row_mol + R0) : 0;
+      }
+      named_bar_sync(3, 256);                                  // the previous tile's pass 2 has read the staged rows
+      {
+        const float* t0 = a.tab + (size_t)m0 * a.ld_tab;
+        for (int c = tl; c < 2 * D; c += 256) mods[c] = c < D ? __ldg(t0 + a.off_shift + c) : __ldg(t0 + a.off_scale + c - D);
+      }
       mbar_wait(bar_aempty, (ti & 1u) ^ 1u);                   // the previous tile's MMAs have read the operand
-      // pass 1: v = u + a + b -> fp16 rows in the operand tile, row statistics in fp32
+      // pass 1: v = u + a + b -> fp16 rows in the operand tile, row statistics in fp32 (3 BT 16-byte loads in flight per thread)
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int i0 = 0; i0 < PH; i0 += 4) {
-        uint4 xu[4], xa[4], xb[4];
+      for (int i0 = 0; i0 < PH; i0 += BT) {
+        uint4 xu[BT], xa[BT], xb[BT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { xu[i] = __ldg(pu + i0 + i); xa[i] = __ldg(pa + i0 + i); xb[i] = __ldg(pb + i0 + i); }
+        for (int i = 0; i < BT; ++i) { xu[i] = __ldg(pu + i0 + i); xa[i] = __ldg(pa + i0 + i); xb[i] = __ldg(pb + i0 + i); }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < BT; ++i) {
           float u[8], va[8], vb[8];
           we_unpack8(xu[i], u); we_unpack8(xa[i], va); we_unpack8(xb[i], vb);
 #pragma unroll
@@ -219,24 +236,29 @@ __global__ void __launch_bounds__(WE_THREADS, 1) k_wide_equi(WideEquiArgs a) {
       s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
       const float mean = s1 * (1.0f / D);
       const float rstd = rsqrtf(fmaxf(s2 * (1.0f / D) - mean * mean, 0.f) + 1e-6f);
+      named_bar_sync(3, 256);                                  // staged modulation rows visible
       // pass 2: normalise + modulate in place (the table stores 1 + scale)
+      const bool own = mol == m0;
       const float* t = a.tab + (size_t)mol * a.ld_tab;
-#pragma unroll 1
-      for (int i0 = 0; i0 < PH; i0 += 2) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int gp = half * PH + i0 + i;
-          uint4* p = reinterpret_cast<uint4*>(A + (gp >> 3) * WE_CHUNK + row * 128 + (((gp & 7) ^ (row & 7)) << 4));
-          float v[8];
-          we_unpack8(*p, v);
-          const float4 sc0 = __ldg(reinterpret_cast<const float4*>(t + a.off_scale + 8 * gp)), sc1 = __ldg(reinterpret_cast<const float4*>(t + a.off_scale + 8 * gp + 4));
-          const float4 sh0 = __ldg(reinterpret_cast<const float4*>(t + a.off_shift + 8 * gp)), sh1 = __ldg(reinterpret_cast<const float4*>(t + a.off_shift + 8 * gp + 4));
-          const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-          const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = valid ? fmaf((v[e] - mean) * rstd, sc[e], sh[e]) : 0.f;
-          *p = we_pack8(v);
+#pragma unroll 2
+      for (int i = 0; i < PH; ++i) {
+        const int gp = half * PH + i;
+        uint4* p = reinterpret_cast<uint4*>(A + (gp >> 3) * WE_CHUNK + row * 128 + (((gp & 7) ^ (row & 7)) << 4));
+        float v[8];
+        we_unpack8(*p, v);
+        float4 sh0, sh1, sc0, sc1;
+        if (own) {
+          sh0 = *reinterpret_cast<const float4*>(mods + 8 * gp); sh1 = *reinterpret_cast<const float4*>(mods + 8 * gp + 4);
+          sc0 = *reinterpret_cast<const float4*>(mods + D + 8 * gp); sc1 = *reinterpret_cast<const float4*>(mods + D + 8 * gp + 4);
+        } else {
+          sh0 = __ldg(reinterpret_cast<const float4*>(t + a.off_shift + 8 * gp)); sh1 = __ldg(reinterpret_cast<const float4*>(t + a.off_shift + 8 * gp + 4));
+          sc0 = __ldg(reinterpret_cast<const float4*>(t + a.off_scale + 8 * gp)); sc1 = __ldg(reinterpret_cast<const float4*>(t + a.off_scale + 8 * gp + 4));
         }
+        const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+        const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = valid ? fmaf((v[e] - mean) * rstd, sc[e], sh[e]) : 0.f;
+        *p = we_pack8(v);
       }
       fence_async_smem();                                      // the tensor core reads these rows through the async proxy
       we_arrive(bar_afull);
@@ -247,7 +269,7 @@ __global__ void __launch_bounds__(WE_THREADS, 1) k_wide_equi(WideEquiArgs a) {
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
-constexpr int we_smem(int KC) { return 1024 + KC * WE_CHUNK + WE_STAGES * WE_CHUNK + WE_STG_BYTES + 256; }
+constexpr int we_smem(int KC) { return KC * WE_CHUNK + WE_STAGES * WE_CHUNK + WE_STG_BYTES + 256 + 2 * 64 * KC * 4; }
 static_assert(we_smem(6) <= 232448, "shared memory budget");
 
 template <int KC>

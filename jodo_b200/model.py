@@ -17,7 +17,8 @@ import torch
 from torch import nn
 
 from . import _lib, wide
-from .pack import EQUI_LIN, TAB_HEAD, pack_model, tab_layer_stride
+from . import pack as _pack
+from .pack import TAB_HEAD, pack_model, tab_layer_stride
 from .params import build_param_tree, check_supported, dims_from_config, param_spec, synth_state_dict
 from .plan import Plan
 
@@ -80,7 +81,7 @@ class _Workspace:
         self.hnode = zf(Nn, D)                             # atoms without partners are never written: stay 0
         self.pbuf = h16(8, Nn, 8)                           # piece-major hoisted node2edge_lin part
         self.h2 = f(Nn, D)
-        self.ab = h16((4 if EQUI_LIN else 2) * D // 8, Nn, 8)    # piece-major (csrc/edge_common.cuh): A | B (| composed YA | YB)
+        self.ab = h16((4 if _pack.EQUI_LIN else 2) * D // 8, Nn, 8)    # piece-major (csrc/edge_common.cuh): A | B (| composed YA | YB)
         self.n1 = f(Nn, D)
         self.n2 = f(Nn, D // 2)
         self.ap = f(Nn, meta['npred4']['N'])
@@ -297,7 +298,7 @@ class _DGTBase(nn.Module):
             m = meta['tab']
             _lib.imglinear(ws.temb_img, B, m['K'], pk['tab.img'], pk['tab.b'], m['N'], m['NT'], C32=ws.tab, stream=st,
                            tag='jodo_imglinear:tab', skip_if_zero=nonuni)
-        if EQUI_LIN:   # uniform conditioning: coord_mlp.0 composed into input_lin for every block from the step's table row
+        if _pack.EQUI_LIN:   # uniform conditioning: coord_mlp.0 composed into input_lin for every block from the step's table row
             _lib.call('jodo_equi_compose', ctypes.c_void_p(self._compose_items(pk).data_ptr()), _c(d.L), _lib.ptr(ws.tab),
                       ctypes.c_void_p(nonuni), st)
         # ---- per atom: packed inputs, node embedding (slice 0 of the concatenated atom hiddens)
@@ -348,7 +349,7 @@ class _DGTBase(nn.Module):
             _lib.call('jodo_edge_update', ctypes.byref(ua), st)
             # coordinate update (JODO_EQUI_LIN=1: the composed kernel under uniform conditioning, the general one
             # otherwise; each tests the device flag and one of them returns at once)
-            if EQUI_LIN:
+            if _pack.EQUI_LIN:
                 la = _lib.EquiLinArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), plan.Nn, _lib.dp(ws.extra),
                                       pk.ptr(p + 'win.img'), pk.ptr(p + 'wce.img'), pk.ptr(p + 'eqc'), meta['coord_scale'][l],
                                       nonuni, pk.host[p + 'gbf4'])
@@ -356,7 +357,7 @@ class _DGTBase(nn.Module):
             qa = _lib.EquiArgs(ps, _lib.dp(ws.e16), _lib.dp(pin), _lib.dp(pout), _lib.dp(ws.ab), plan.Nn,
                                _lib.dp(ws.tab), ld_tab, off, _lib.dp(ws.extra), pk.ptr(p + 'win.img'),
                                pk.ptr(p + 'wc0h.img'), pk.ptr(p + 'w2.img'), pk.ptr(p + 'w2x.img'), meta['coord_scale'][l],
-                               nonuni, pk.host[p + 'gbf4'], pk.host[p + 'b0h'], 1 if EQUI_LIN else 0)
+                               nonuni, pk.host[p + 'gbf4'], pk.host[p + 'b0h'], 1 if _pack.EQUI_LIN else 0)
             _lib.call('jodo_equi', ctypes.byref(qa), st)
             _lib.call('jodo_com', _lib.ptr(pout), ctypes.byref(ps), st)
             if dbg is not None:

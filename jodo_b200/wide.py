@@ -10,6 +10,7 @@ models/layers.py:131-186 (attention).
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -17,6 +18,11 @@ from . import _lib
 from .pack import TAB_HEAD, ceil_to, pad2, tab_layer_stride
 
 _c = ctypes.c_int
+# A/B switch: the coordinate branch as ONE kernel (LayerNorm warps producing coord_mlp.0's operand tile in shared memory,
+# csrc/wide_equi.cu).  Correct (parity-green), measured SLOWER than the LayerNorm row kernel + GEMM pair on B200 (1.4 vs 1.0 ms
+# per block at GEOM nf = 384, B = 512): eight LayerNorm warps per SM cannot keep enough gathers in flight, where the row kernel
+# runs at full occupancy.  Off by default.
+FUSED_EQUI = os.environ.get('JODO_WIDE_EQUI_FUSED') == '1'
 EDP = 128            # row stride (floats) of the per-edge fp32 buffers and K of the per-edge images (ed <= 128)
 
 
@@ -285,10 +291,21 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
              C32=ws.e32, Cimg=ws.ED, cimg_place=(K2, 0, ed), Cimg2=ws.EH, cimg2_place=(KH, (l + 1) * EDP, ed))
         # coordinate update: the [e | dist] part of input_lin per pair, everything behind the LayerNorm per directed row
         ilin(p + 'equi_in', ws.ED, RP, bias=False, C16=ws.U)
-        ln(R, D, D, ws.U, (oq, oq + D), plan.row_mol, out_img=ws.u_img, y=ws.AB, yi=plan.row_g, y2=ws.AB[:, D:],
-           y2i=plan.row_j, valid=plan.row_g, xi=plan.row_pair, tag='equi')
-        ilin(p + 'c0', ws.u_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, dot_w=pk[p + 'c2.w32'], dot_out=ws.c3)
-        _lib.call('jodo_wide_equi_out', P(ws.grp_row0), P(ws.grp_len), P(plan.row_j), P(ws.c3), _c(64), _c(2 * meta[p + 'c0']['N'] // meta[p + 'c0']['NT']), P(ws.extra),
+        mc0 = meta[p + 'c0']
+        if FUSED_EQUI and D in (256, 384) and mc0['NT'] == 128 and mc0['N'] == D:
+            # LayerNorm + modulation as the producer of coord_mlp.0's operand tile in shared memory, SiLU and the three
+            # coord_mlp.2 dots in its epilogue: no operand image in HBM (csrc/wide_equi.cu)
+            wa = _lib.WideEquiArgs(R, D, dp(ws.U), ws.U.stride(0), dp(plan.row_pair), dp(ws.AB), ws.AB.stride(0), dp(plan.row_g),
+                                   dp(plan.row_j), dp(plan.row_mol), dp(ws.tab), ld_tab, oq, oq + D, pk.ptr(p + 'c0.img'),
+                                   pk.ptr(p + 'c0.b'), pk.ptr(p + 'c2.w32'), dp(ws.c3), 64)
+            _lib.call('jodo_wide_equi', ctypes.byref(wa), st)
+            nslots = 2
+        else:
+            ln(R, D, D, ws.U, (oq, oq + D), plan.row_mol, out_img=ws.u_img, y=ws.AB, yi=plan.row_g, y2=ws.AB[:, D:],
+               y2i=plan.row_j, valid=plan.row_g, xi=plan.row_pair, tag='equi')
+            ilin(p + 'c0', ws.u_img, R, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, dot_w=pk[p + 'c2.w32'], dot_out=ws.c3)
+            nslots = 2 * mc0['N'] // mc0['NT']
+        _lib.call('jodo_wide_equi_out', P(ws.grp_row0), P(ws.grp_len), P(plan.row_j), P(ws.c3), _c(64), _c(nslots), P(ws.extra),
                   P(plan.row_pair), _c(d.X), ctypes.c_float(meta['coord_scale'][l]), P(pin), P(pout), _c(Nn), st)
         _lib.call('jodo_com', P(pout), ctypes.byref(ps), st)
         if dbg is not None:

@@ -67,8 +67,8 @@ def test_uniform_conditioning_fast_path_matches_general_path():
     # Molecules 0..B-2 see identical conditioning rows on both paths, and the kernels do the same arithmetic on them --
     # except with JODO_EQUI_LIN=1, where the uniform path composes coord_mlp.0 into input_lin (csrc/equi_lin.cu) and
     # the two agree to the fp16 operand rounding only.  Either way each path agrees with the fp64 oracle.
-    from jodo_b200.pack import EQUI_LIN
-    tol_ab = 1e-3 if EQUI_LIN else 1e-5
+    from jodo_b200 import pack as _pack
+    tol_ab = 1e-3 if _pack.EQUI_LIN else 1e-5
     assert float((xa[:B - 1] - xb[:B - 1]).abs().max()) < tol_ab * float(xa.abs().max())
     assert float((ea[:B - 1] - eb[:B - 1]).abs().max()) < tol_ab * float(ea.abs().max())
     from helpers import oracle_forward
@@ -82,3 +82,38 @@ def test_uniform_conditioning_fast_path_matches_general_path():
         px = float((x_.double().cpu() - ox)[..., :3].abs().max() / ox[..., :3].abs().max())
         print(f'{tag} path vs fp64 oracle: x {ex:.2e} (positions {px:.2e})  e {ee:.2e}')
         assert ex < TOL and ee < TOL and px < TOL
+
+
+def test_ab_variants_of_the_coordinate_kernels_stay_parity_green(monkeypatch):
+    """The two coordinate-branch variants that are kept for A/B runs but are off by default (measured slower on B200,
+    DESIGN.md section 5) compute the same function: coord_mlp.0 composed into input_lin under uniform conditioning
+    (csrc/equi_lin.cu, JODO_EQUI_LIN=1) on the nf = 256 path, and the fused LayerNorm -> coord_mlp.0 kernel of the wide path
+    (csrc/wide_equi.cu, JODO_WIDE_EQUI_FUSED=1) -- each against the fp64 oracle and against the default kernels."""
+    from helpers import golden_weights, oracle_forward
+    from jodo_b200 import pack as _pack, wide as _wide
+    from jodo_b200.model import MODELS
+
+    def run(name, uniform):
+        g, cfg = load_golden(name)
+        sd = golden_weights(g, cfg)
+        model = MODELS[cfg.model.name](cfg)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().eval()
+        inp = dict(g['inputs'])
+        if uniform:
+            inp['noise_level'] = torch.full_like(inp['noise_level'], 1.25)
+        dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+        x, e = model(dev['t'], dev['xh'], dev['node_mask'], dev['edge_mask'], noise_level=dev['noise_level'], edge_x=dev['edge_x'],
+                     cond_x=dev['cond_x'], cond_edge_x=dev['cond_edge_x'], context=dev['context'])
+        ox, oe = oracle_forward(sd, cfg, inp, torch.float64)
+        return x.double().cpu(), e.double().cpu(), ox, oe
+
+    for name, uniform, mod, flag in (('qm9_selfcond', True, _pack, 'EQUI_LIN'), ('geom_large', False, _wide, 'FUSED_EQUI')):
+        monkeypatch.setattr(mod, flag, False)
+        x0, e0, ox, oe = run(name, uniform)
+        monkeypatch.setattr(mod, flag, True)
+        x1, e1, _, _ = run(name, uniform)
+        ex, ee = float((x1 - ox).abs().max() / ox.abs().max()), float((e1 - oe).abs().max() / oe.abs().max())
+        dx = float((x1 - x0).abs().max() / ox.abs().max())
+        print(f'{name} [{flag}]: vs fp64 oracle x {ex:.2e} e {ee:.2e}; vs the default kernels x {dx:.2e}')
+        assert ex < TOL and ee < TOL and dx < TOL and dx > 0.0          # the variant really ran (different rounding)
