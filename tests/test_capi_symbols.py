@@ -59,7 +59,9 @@ def _struct_fields(name):
                                           ('jodo_equi_args', 'EquiArgs'), ('jodo_edge_head_args', 'EdgeHeadArgs'),
                                           ('jodo_imglinear_args', 'ImgLinearArgs'),
                                           ('jodo_wide_embed_args', 'WideEmbedArgs'), ('jodo_wide_ln_args', 'WideLnArgs'),
-                                          ('jodo_wide_attn_args', 'WideAttnArgs')])
+                                          ('jodo_wide_attn_args', 'WideAttnArgs'), ('jodo_wide_equi_args', 'WideEquiArgs'),
+                                          ('jodo_equi_lin_args', 'EquiLinArgs'), ('jodo_equi_compose_item', 'EquiComposeItem'),
+                                          ('jodo_pack_item', 'PackItem')])
 def test_ctypes_structs_mirror_header(cname, pytype):
     assert [f[0] for f in getattr(_lib, pytype)._fields_] == _struct_fields(cname)
 
@@ -76,6 +78,23 @@ def test_bad_arguments_fail_before_any_launch(lib):
     assert lib.jodo_imglinear(ctypes.byref(a), None) == 1 and b'multiple of 64' in lib.jodo_last_error_string()
     e = _lib.EdgeUpdateArgs()
     assert lib.jodo_edge_update(ctypes.byref(e), None) == 1
+    # round-2 entry points: classifier row kernels, in-kernel noise, opt-in coordinate variants
+    assert lib.jodo_egnn_edge_in(None, None, None, 0, 0, None, None, None) == 1
+    assert lib.jodo_egnn_agg(None, None, None, 0, 0, None, ctypes.c_float(0), None, 0, 0, None) == 1
+    assert lib.jodo_mol_sum(None, 0, 0, None, 0, None, 0, None) == 1
+    assert lib.jodo_philox_normal(ctypes.c_ulonglong(0), ctypes.c_ulonglong(0), 0, 0, None, None) == 1
+    assert lib.jodo_ancestral_update_philox(None, None, None, None, None, None, 0, 0, 0, 0, ctypes.c_float(0), ctypes.c_float(0),
+                                            ctypes.c_float(0), None, ctypes.c_ulonglong(0), 0, None, None, None, None, None) == 1
+    assert lib.jodo_equi_lin(None, None) == 1 and lib.jodo_equi_compose(None, 0, None, None, None) == 1
+    assert lib.jodo_wide_equi(None, None) == 1
+    q = _lib.WideEquiArgs()
+    q.M, q.D = 128, 320
+    assert lib.jodo_wide_equi(ctypes.byref(q), None) == 1 and b'D = 256 and D = 384' in lib.jodo_last_error_string()
+    i = _lib.ImgLinearArgs()
+    i.M, i.K, i.N, i.NT = 128, 64, 128, 128
+    i.Aimg = i.Wimg = 128
+    i.Cimg, i.cimg_k, i.cimg_col0, i.cimg_ncols = 128, 192, 4, 96
+    assert lib.jodo_imglinear(ctypes.byref(i), None) == 1 and b'placement' in lib.jodo_last_error_string()
     # wide path (nf = 384)
     assert lib.jodo_wide_ln(None, None) == 1 and lib.jodo_wide_attn(None, None) == 1 and lib.jodo_wide_embed_in(None, None) == 1
     w = _lib.WideLnArgs()
