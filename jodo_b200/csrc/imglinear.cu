@@ -51,6 +51,12 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 constexpr int il_mode(int epi, bool c32, bool c16, bool cimg, bool cimg2 = false, bool dot = false) {
   return epi | (c32 ? 4 : 0) | (c16 ? 8 : 0) | (cimg ? 16 : 0) | (cimg2 ? 32 : 0) | (dot ? 64 : 0);
 }
+// A mode of its own: JODO_EPI_STORE with ONLY the piece-major fp16 output (q | k | v and the hoisted parts the edge kernels
+// gather).  In that layout the 16 bytes of (piece, row) are contiguous over rows, which is the accumulator's own layout
+// (lane = row): every thread packs its 32 columns into four pieces and stores them directly -- consecutive lanes write
+// consecutive 16-byte slots, no staging through shared memory, no team barrier.  (The row-major pass wrote 16 sectors of
+// 16 useful bytes per store instruction here.)
+constexpr int IL_MODE_PM16 = 128;
 
 template <int MODE, int ACT = ACT_SILU>
 __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
     const int row = rq * 32 + lane;
     const int cw = nt / 2;                         // columns per team (32, 64 or 128)
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-    const int epi = MODE < 0 ? a.epi : (MODE & 3);
+    const int epi = MODE < 0 ? a.epi : (MODE == IL_MODE_PM16 ? EPI_STORE : (MODE & 3));
     const bool has32 = MODE < 0 ? a.C32 != nullptr : (MODE & 4) != 0;
     const bool has16 = MODE < 0 ? a.C16 != nullptr : (MODE & 8) != 0;
     const bool hasimg = MODE < 0 ? a.Cimg != nullptr : (MODE & 16) != 0;
@@ -185,6 +191,38 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
       }
       mbar_wait(&bar_tfull[ab], aph);
       tc_fence_after();
+      if (MODE == IL_MODE_PM16) {
+        const int gr = m * TILE_ROWS + row;
+        for (int c0 = team * cw; c0 < (team + 1) * cw; c0 += 32) {
+          const int colb = n * nt + c0;
+          float x[32];
+          tmem_ld32(tmem + ab * 256u + ((uint32_t)rq << 21) + (uint32_t)c0, x);
+          if (bias) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + colb) + p);
+              x[4 * p] += b.x; x[4 * p + 1] += b.y; x[4 * p + 2] += b.z; x[4 * p + 3] += b.w;
+            }
+          }
+          float mx = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fabsf(x[i]));
+          if (mx > 65504.f) atomicAdd(&g_sat_imglinear, 1u);
+          if (gr < Mrows) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              uint4 o;
+              o.x = pack_h2(x[8 * p], x[8 * p + 1]); o.y = pack_h2(x[8 * p + 2], x[8 * p + 3]);
+              o.z = pack_h2(x[8 * p + 4], x[8 * p + 5]); o.w = pack_h2(x[8 * p + 6], x[8 * p + 7]);
+              *reinterpret_cast<uint4*>(C16 + ((size_t)((colb >> 3) + p) * ldc16 + gr) * 8) = o;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(&bar_tempty[ab]);
+        continue;
+      }
       for (int c0 = team * cw; c0 < (team + 1) * cw; c0 += 32, sb ^= 1u) {
         uint8_t* buf = stg + sb * IL_STG_BUF;
         const int col = n * nt + c0 + c4;
@@ -354,6 +392,8 @@ cudaError_t launch_imglinear(const ImgLinearArgs& a_in, int num_sms, cudaStream_
   const int grid = units < num_sms ? units : num_sms;
   const int mode = il_mode(a.epi, a.C32 != nullptr, a.C16 != nullptr, a.Cimg != nullptr, a.Cimg2 != nullptr, a.dot_out != nullptr);
   const bool silu_or_none = a.epi != EPI_ACT || a.act_out == ACT_SILU;
+  if (a.epi == EPI_STORE && a.C16 && a.c16_piece_major && !a.C32 && !a.Cimg && !a.dot_out)
+    return launch_mode<IL_MODE_PM16>(a, grid, stream);                                                                              // q|k|v, hoisted parts (fused path)
   if (silu_or_none) {
     switch (mode) {
       case il_mode(EPI_STORE, false, true, false): return launch_mode<il_mode(EPI_STORE, false, true, false)>(a, grid, stream);      // q|k|v, hoisted parts
