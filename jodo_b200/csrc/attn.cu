@@ -27,6 +27,13 @@ namespace jodo {
 
 __constant__ float c_atmod[130];        // row 0 of the table: edge shift_msa[64], scale_msa[64], then GBF scale, shift
 
+#ifdef JODO_PHASE_TIMING
+__device__ long long g_attn_phase[16];
+#define AT_MARK(i) do { if (c.lt == 0 && c.grp == 0 && HALF == 0 && blockIdx.x == 0) { long long c_ = clock64(); g_attn_phase[i] += c_ - ph_last; ph_last = c_; } } while (0)
+#else
+#define AT_MARK(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int AT_THREADS = 512;
@@ -98,6 +105,9 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
   // the e chunk of a tile = its rows' pair rows, gathered from the pair-row store one tile ahead (edge_common.cuh):
   // the two warps that own a row quarter copy 16 of its rows each
   if (c.tile0 < c.tile1) gather_e16_warp<16>(A0 + CHUNK_BYTES_A, a.e16, 32 * rq, 16 * HALF, rn.valid, rn.pr, lane);
+#ifdef JODO_PHASE_TIMING
+  long long ph_last = clock64();
+#endif
   for (int tile = c.tile0; tile < c.tile1; tile += 2) {
     const RowInfo r = rn;
     const int ng = ngn;
@@ -123,9 +133,11 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
       }
       st_rowh<32>(A0, row, 0, 4 * HALF, df);       // padding rows: finite garbage, masked by alpha = 0 below
     }
+    AT_MARK(0);
     cp_async_wait_all();                                 // this thread's share of the gathered e chunk has landed
     fence_async_smem();
     at_group_sync(c.grp);
+    AT_MARK(1);
     if (lt == 0) {
       if (tile == c.tile0) mbar_wait(c.bar_w, 0);
       tc_fence_after();
@@ -133,6 +145,7 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
       umma_commit(c.bar_m);
     }
     mbar_wait(c.bar_m, par_m);
+    AT_MARK(2);
     par_m ^= 1;
     tc_fence_after();
     // row -> group indicator for the aggregation MMA: B[slot][row] = 1 (K-major image, two chunks of 64 rows)
@@ -173,7 +186,9 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
       st_rowh<32>(A0, row, 0, 4 * HALF, x);
     }
     fence_async_smem();
+    AT_MARK(3);
     at_group_sync(c.grp);
+    AT_MARK(4);
     if (lt == 0) {
       mma_tile_h(tm, smem_u32(A0), smem_u32(c.W0), 256, 1, false);                  // g0 pre-activation
       umma_commit(c.bar_m);
@@ -187,6 +202,7 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
       qc.u[0] = __ldg(qb); qc.u[1] = __ldg(qb + a.ldq);
       kc.u[0] = __ldg(kb); kc.u[1] = __ldg(kb + a.ldq);
       mbar_wait(c.bar_m, par_m);
+      AT_MARK(5);
       par_m ^= 1;
       tc_fence_after();
       float lg[7];
@@ -230,7 +246,9 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
       rn = load_row(a.p, nt_, row);
       ngn = a.p.tile_ngroups[nt_];
     }
+    AT_MARK(6);
     at_group_sync(c.grp);                                  // logits visible; every g0 read done
+    AT_MARK(7);
     if (lt == 0) {
       mma_tile_h(tm, smem_u32(A0), smem_u32(c.W1), 256, 1, false);                  // g1 pre-activation, under the softmax
       umma_commit(c.bar_m);
@@ -243,59 +261,35 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
     if (tile + 2 < c.tile1)
       gather_e16_warp<16>(A0 + CHUNK_BYTES_A, a.e16, 32 * rq, 16 * HALF, rn.valid, rn.pr, lane);
     // (group, head): max, exp in place, 1 / (sum + 1e-16)      (PyG softmax, models/layers.py:178).
-    // Four lanes share one (group, head) and interleave its rows; ng * 64 is a whole number of warps.
-    // Long groups (>= 32 rows) sum in four interleaved partial sums combined as (s0 + s1) + (s2 + s3), short ones
-    // sequentially: the arithmetic depends on the group alone.  The work distribution depends on the tile: with few
-    // groups (<= 4: GEOM-sized molecules) four lanes share a (group, head) and take one partial sum each, otherwise
-    // one lane does it all  [same-box A/B: 8 % either way].
-    if (ng <= 4) {
-      for (int it = lt; it < ng * 64; it += AT_GROUP) {
-        const int sub = it & 3, gi = it >> 6, h = (it >> 2) & 15;
+    {
+      // L lanes share a (group, head): lane `sub` takes the rows sub, sub + L, ... of the group.  Every group sums its
+      // exponentials in FOUR interleaved partial sums combined as (s0 + s1) + (s2 + s3), whatever L is (zeros are added
+      // where a lane holds no part), so the arithmetic depends on the group alone and not on what else shares the tile.
+      const int shl = ng <= 4 ? 2 : (ng <= 8 ? 1 : 0);       // ng * 16 << shl is a whole number of warps when shl > 0
+      const int L = 1 << shl;
+      for (int it = lt; it < ((ng * 16) << shl); it += AT_GROUP) {
+        const int sub = it & (L - 1), item = it >> shl, gi = item >> 4, h = item & 15;
         const int gs = gt_meta[gi] & 255u, gl = (gt_meta[gi] >> 8) & 255u;
-        const bool wide = gl >= 32;
-        const int r0 = gs + (wide ? sub : (sub == 0 ? 0 : gl)), st = wide ? 4 : 1;
         float m = -INFINITY;
-        for (int rr = r0; rr < gs + gl; rr += st) m = fmaxf(m, LG[rr * 17 + h]);
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        float sm = 0.f;
-        for (int rr = r0; rr < gs + gl; rr += st) {
+        for (int rr = gs + sub; rr < gs + gl; rr += L) m = fmaxf(m, LG[rr * 17 + h]);
+        if (shl >= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        if (shl == 2) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int rr = gs + sub; rr < gs + gl; rr += L) {
           const float e = ex2_fast((LG[rr * 17 + h] - m) * 1.4426950408889634f);
           LG[rr * 17 + h] = e;
-          sm += e;
+          const int k = (rr - gs) & 3;
+          s4[0] += k == 0 ? e : 0.f; s4[1] += k == 1 ? e : 0.f; s4[2] += k == 2 ? e : 0.f; s4[3] += k == 3 ? e : 0.f;
         }
-        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-        sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-        if (sub == 0) GI[gi * 16 + h] = 1.0f / (sm + 1e-16f);
-      }
-    } else {
-      for (int it = lt; it < ng * 16; it += AT_GROUP) {
-        const int gi = it >> 4, h = it & 15;
-        const int gs = gt_meta[gi] & 255u, gl = (gt_meta[gi] >> 8) & 255u;
-        float m = -INFINITY;
-        for (int rr = gs; rr < gs + gl; ++rr) m = fmaxf(m, LG[rr * 17 + h]);
-        float sm;
-        if (gl >= 32) {
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int rr = gs; rr < gs + gl; ++rr) {
-            const float e = ex2_fast((LG[rr * 17 + h] - m) * 1.4426950408889634f);
-            LG[rr * 17 + h] = e;
-            const int k = (rr - gs) & 3;
-            s4[0] += k == 0 ? e : 0.f; s4[1] += k == 1 ? e : 0.f; s4[2] += k == 2 ? e : 0.f; s4[3] += k == 3 ? e : 0.f;
-          }
-          sm = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        } else {
-          sm = 0.f;
-          for (int rr = gs; rr < gs + gl; ++rr) {
-            const float e = ex2_fast((LG[rr * 17 + h] - m) * 1.4426950408889634f);
-            LG[rr * 17 + h] = e;
-            sm += e;
-          }
-        }
-        GI[gi * 16 + h] = 1.0f / (sm + 1e-16f);
+        float s01 = s4[0] + s4[1], s23 = s4[2] + s4[3];
+        if (shl >= 1) { s01 += __shfl_xor_sync(0xffffffffu, s01, 1); s23 += __shfl_xor_sync(0xffffffffu, s23, 1); }
+        if (shl == 2) { s01 += __shfl_xor_sync(0xffffffffu, s01, 2); s23 += __shfl_xor_sync(0xffffffffu, s23, 2); }
+        if (sub == 0) GI[gi * 16 + h] = 1.0f / ((s01 + s23) + 1e-16f);
       }
     }
+    AT_MARK(8);
     named_bar_sync(1 + c.grp, AT_GROUP);
+    AT_MARK(9);
     float alpha[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) alpha[h] = r.valid ? LG[row * 17 + 8 * HALF + h] * GI[r.gi * 16 + 8 * HALF + h] : 0.f;
@@ -305,6 +299,7 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
     // (A = message image, MN-major: M = 128 value columns of this pass, K = 128 rows; B = indicator, N = 64 slots).
     // Two passes of 64 columns per half; D^T(p) lands in TMEM columns [64p, 64p+64), whose g1 values are consumed by then.
     mbar_wait(c.bar_m, par_m);
+    AT_MARK(10);
     par_m ^= 1;
     tc_fence_after();
 #pragma unroll 1
@@ -332,7 +327,9 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
         if (ch < 7) vc = vn;
       }
       fence_async_smem();
+      AT_MARK(11);
       at_group_sync(c.grp);
+      AT_MARK(12);
       if (lt == 0) {
         const uint32_t idesc = umma_idesc_f16_amn(64);
         const uint32_t sa = smem_u32(A0), lbo = (uint32_t)G_MIB, sb = smem_u32(IND);
@@ -342,6 +339,7 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
         umma_commit(c.bar_m);
       }
       mbar_wait(c.bar_m, par_m);
+      AT_MARK(13);
       par_m ^= 1;
       tc_fence_after();
       // D^T lanes = value columns (lanes 0..63: half 0, 64..127: half 1); this warp drains slots [32 HALF, 32 HALF + 32)
@@ -355,6 +353,7 @@ __device__ __forceinline__ void at_group_loop(const AttnArgs& a, const AtCtx& c)
       }
     }
     tc_fence_before();                                       // g1 reads are ordered before the next tile's MMA1 by its group_sync
+    AT_MARK(14);
   }
 }
 
@@ -401,6 +400,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_attn(const __grid_constant__ 
 }
 
 }  // namespace
+
+#ifdef JODO_PHASE_TIMING
+extern "C" int jodo_debug_attn_phases(long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  if (out16) cudaMemcpyFromSymbol(out16, g_attn_phase, sizeof(long long) * 16);
+  if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_attn_phase, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 cudaError_t launch_attn(const AttnArgs& a, int num_sms, cudaStream_t st) {
   static DevAttr attr = {};
