@@ -219,7 +219,6 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
     const int nt_ = min(tile + 1, tile1 - 1);
     rn = load_row(a.p, nt_, row);
     ngn = a.p.tile_ngroups[nt_];
-    exn = a.extra[rn.pr];
     cp_async_wait_all();                           // this thread's share of the gathered e chunk has landed
     fence_async_smem();
     sync_tc();
@@ -269,6 +268,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) k_equi(const __grid_constant__ 
       }
       tmem_wait_st();
       if (cq < 2) mbar_wait(&bars[5], par);      // the scratch aliases the GBF chunk: the whole input_lin MMA must be done
+      exn = a.extra[rn.pr];                      // (a dependent load behind row_pair: issued here, where rn has long arrived)
       if (tile + 1 < tile1)                      // U chunk 0 is consumed: gather the next tile's e rows (rn)
         gather_e16_warp<8>(U, a.e16, 32 * rq, 8 * cq, rn.valid, rn.pr, lane);
       if (t == 0) {
