@@ -381,17 +381,19 @@ __global__ void __launch_bounds__(WA_THREADS) k_wide_attn(WideAttnArgs a) {
 }
 
 // ---- coordinate update tail (models/mol_gnn.py:82-92): inv = mean([1, extra] * tanh(coord_mlp.2 output)),
-// pos_r += sum_c (pos_r - pos_c) / max(|.|, 1e-8) * scale * inv.  One thread per atom.
-__global__ void k_wide_equi_out(const int* __restrict__ grp_row0, const int* __restrict__ grp_len,
-                                const int* __restrict__ row_j, const float* __restrict__ c3, int ldc, int nslots,
-                                const uint8_t* __restrict__ extra, const int* __restrict__ row_pair, int X, float coord_scale,
-                                const float4* __restrict__ pos_in, float4* __restrict__ pos_out, int Nn) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+// pos_r += sum_c (pos_r - pos_c) / max(|.|, 1e-8) * scale * inv.  One WARP per atom: lanes over its partner rows (a thread per
+// atom walked ~n rows serially with 22 k threads in flight), fixed-order shuffle tree for the three sums.
+__global__ void __launch_bounds__(256) k_wide_equi_out(const int* __restrict__ grp_row0, const int* __restrict__ grp_len,
+                                                       const int* __restrict__ row_j, const float* __restrict__ c3, int ldc, int nslots,
+                                                       const uint8_t* __restrict__ extra, const int* __restrict__ row_pair, int X,
+                                                       float coord_scale, const float4* __restrict__ pos_in,
+                                                       float4* __restrict__ pos_out, int Nn) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (g >= Nn) return;
   const float4 p = pos_in[g];
   float sx = 0.f, sy = 0.f, sz = 0.f;
   const int r0 = grp_row0[g], gl = grp_len[g];
-  for (int i = 0; i < gl; ++i) {
+  for (int i = lane; i < gl; i += 32) {
     const int R = r0 + i;
     const float4 q = pos_in[row_j[R]];
     const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
@@ -400,15 +402,21 @@ __global__ void k_wide_equi_out(const int* __restrict__ grp_row0, const int* __r
     const uint8_t bits = extra[row_pair ? row_pair[R] : R];
     float cs[3] = {0.f, 0.f, 0.f};                  // coord_mlp.2 outputs: the partial sums of the GEMM's column slots, in order
     for (int s = 0; s < nslots; ++s) {
-      const float4 q = *reinterpret_cast<const float4*>(c + 4 * s);
-      cs[0] += q.x; cs[1] += q.y; cs[2] += q.z;
+      const float4 v = *reinterpret_cast<const float4*>(c + 4 * s);
+      cs[0] += v.x; cs[1] += v.y; cs[2] += v.z;
     }
     float inv = tanhf(cs[0]);
     for (int x = 0; x < X; ++x) inv += ((bits >> x) & 1) ? tanhf(cs[1 + x]) : 0.f;
     const float f = coord_scale * inv / ((float)(1 + X) * nrm);
     sx = fmaf(dx, f, sx); sy = fmaf(dy, f, sy); sz = fmaf(dz, f, sz);
   }
-  pos_out[g] = make_float4(p.x + sx, p.y + sy, p.z + sz, 0.f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    sz += __shfl_xor_sync(0xffffffffu, sz, o);
+  }
+  if (lane == 0) pos_out[g] = make_float4(p.x + sx, p.y + sy, p.z + sz, 0.f);
 }
 
 // ---- last layer of edge_exist_mlp / edge_type_mlp (models/mol_gnn.py:574-578) + scatter to the dense grid.
@@ -487,7 +495,7 @@ cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st) {
 cudaError_t launch_wide_equi_out(const int* grp_row0, const int* grp_len, const int* row_j, const float* c3, int ldc, int nslots,
                                  const uint8_t* extra, const int* row_pair, int X, float coord_scale, const float* pos_in,
                                  float* pos_out, int Nn, cudaStream_t st) {
-  k_wide_equi_out<<<(Nn + 127) / 128, 128, 0, st>>>(grp_row0, grp_len, row_j, c3, ldc, nslots, extra, row_pair, X, coord_scale,
+  k_wide_equi_out<<<(Nn + 7) / 8, 256, 0, st>>>(grp_row0, grp_len, row_j, c3, ldc, nslots, extra, row_pair, X, coord_scale,
                                                     reinterpret_cast<const float4*>(pos_in), reinterpret_cast<float4*>(pos_out), Nn);
   return WIDE_OK();
 }
