@@ -329,7 +329,7 @@ def pack_model(sd, dims, device, fused=None):
         for name, n, scales in chunks:                        # chunk order: shift, scale, gate (AdaLN); scale, shift (GBF)
             tab_rows(name, o, n, scales)
             o += n
-    add_lin('tab', wp, bp, 256, ld_tab, T)                    # ld_tab is a multiple of 256
+    add_lin('tab', wp, bp, 128, ld_tab, T)                    # ld_tab is a multiple of 256; 128-column tiles: 154 CTAs for the one-row-tile launch
     pk.meta['ld_tab'] = ld_tab
     # ---- atom level
     lin('node_emb', 'node_emb', ntb)
