@@ -15,7 +15,7 @@ import os
 import torch
 
 from . import _lib
-from .pack import TAB_HEAD, ceil_to, pad2, tab_layer_stride
+from .pack import TAB_HEAD, ceil_to, tab_layer_stride
 
 _c = ctypes.c_int
 # A/B switch: the coordinate branch as ONE kernel (LayerNorm warps producing coord_mlp.0's operand tile in shared memory,
