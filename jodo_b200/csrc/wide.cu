@@ -234,55 +234,68 @@ __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
   }
   const float* t = a.tab + (size_t)mol * a.ld_tab;
   float v[KP][8];
-  float s = 0.f;
+  float s = 0.f, q = 0.f;                   // one pass: sum and sum of squares (as the fused edge kernels do)
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
     const int p = lane + LANES * k;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
     if (p < npw) {
-      wload8x(a.x, x16, ix, a.ldx, 8 * p, v[k]);
-      if (has_y) {
-        float y[8];
-        wload8x(a.y, y16, iy, a.ldy, 8 * p, y);
-        if (has_yimg) *wimg(a.y_img, row, 8 * p, a.Kimg) = wpack8(y);
-        if (has_y2) {
-          float y2[8];
-          wload8x(a.y2, y16, iy2, a.ldy2, 8 * p, y2);
+      if (V == 1) {
+        // coordinate branch: three fp16 rows.  The two hoisted parts are pre-added as half2 (as in the fused kernel) and the
+        // halves enter the fp32 sum through FHADD -- 20 instructions per piece instead of 24 conversions + 16 adds
+        const uint4 ux = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.x) + (size_t)ix * a.ldx + 8 * p);
+        uint4 uy = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.y) + (size_t)iy * a.ldy + 8 * p);
+        const uint4 uz = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.y2) + (size_t)iy2 * a.ldy2 + 8 * p);
+        __half2* hy = reinterpret_cast<__half2*>(&uy);
+        const __half2* hz = reinterpret_cast<const __half2*>(&uz);
+        const uint32_t* wx = reinterpret_cast<const uint32_t*>(&ux);
+        const uint32_t* wy = reinterpret_cast<const uint32_t*>(&uy);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] += y2[i];
+        for (int i = 0; i < 4; ++i) {
+          hy[i] = __hadd2(hy[i], hz[i]);
+          v[k][2 * i] = fhadd_lo(wx[i], fhadd_lo(wy[i], 0.f));
+          v[k][2 * i + 1] = fhadd_hi(wx[i], fhadd_hi(wy[i], 0.f));
         }
-        if (has_bias) {
-          float yb[8];
-          wldg8(a.ybias + 8 * p, yb);
+      } else {
+        wload8x(a.x, x16, ix, a.ldx, 8 * p, v[k]);
+        if (has_y) {
+          float y[8];
+          wload8x(a.y, y16, iy, a.ldy, 8 * p, y);
+          if (has_yimg) *wimg(a.y_img, row, 8 * p, a.Kimg) = wpack8(y);
+          if (has_y2) {
+            float y2[8];
+            wload8x(a.y2, y16, iy2, a.ldy2, 8 * p, y2);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] += yb[i];
-        }
-        if (has_gate) {
-          float gt[8];
-          wldg8(t + a.off_gate + 8 * p, gt);
+            for (int i = 0; i < 8; ++i) y[i] += y2[i];
+          }
+          if (has_bias) {
+            float yb[8];
+            wldg8(a.ybias + 8 * p, yb);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[k][i] = fmaf(gt[i], y[i], v[k][i]);
-        } else {
+            for (int i = 0; i < 8; ++i) y[i] += yb[i];
+          }
+          if (has_gate) {
+            float gt[8];
+            wldg8(t + a.off_gate + 8 * p, gt);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[k][i] += y[i];
+            for (int i = 0; i < 8; ++i) v[k][i] = fmaf(gt[i], y[i], v[k][i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[k][i] += y[i];
+          }
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += v[k][i];
+      for (int i = 0; i < 8; ++i) { s += v[k][i]; q = fmaf(v[k][i], v[k][i], q); }
     } else if (p < npk && has_yimg) {
       *wimg(a.y_img, row, 8 * p, a.Kimg) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  const float mean = wsum<LANES>(s, hm) / (float)a.W;
-  float q = 0.f;
-#pragma unroll
-  for (int k = 0; k < KP; ++k)
-    if (lane + LANES * k < npw) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; q += d * d; }
-    }
-  const float rstd = rsqrtf(wsum<LANES>(q, hm) / (float)a.W + 1e-6f);
+  const float inv_w = 1.0f / (float)a.W;
+  const float mean = wsum<LANES>(s, hm) * inv_w;
+  const float rstd = rsqrtf(fmaxf(wsum<LANES>(q, hm) * inv_w - mean * mean, 0.f) + 1e-6f);
+  const float nmr = -mean * rstd;
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
     const int p = lane + LANES * k;
@@ -293,7 +306,7 @@ __global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
       wldg8(t + a.off_scale + 8 * p, sc);     // the table stores 1 + scale
       wldg8(t + a.off_shift + 8 * p, sh);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf((v[k][i] - mean) * rstd, sc[i], sh[i]);
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(fmaf(v[k][i], rstd, nmr), sc[i], sh[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
