@@ -195,8 +195,11 @@ __global__ void k_wide_dist(Plan p, const float4* __restrict__ pos, const float*
 // bias, gated, fp32 rows + image; norm1_edge: fp32 x, image only).
 // LANES = 32: one warp per row (up to 64 pieces); LANES = 16: two rows per warp (up to 16 pieces each: the per-edge
 // rows of width ed <= 128, where a full warp would leave most lanes idle).
+// The compiled two-rows-per-warp variants are held to 40 registers (six 256-thread blocks per SM): the kernel waits on two
+// dependent round trips per row (row indices, then the gathered rows), so residency buys more than the few spilled values
+// cost (coordinate-branch LayerNorm 0.557 -> 0.488 ms per launch at GEOM nf = 384).
 template <int V, int LANES, int KP = 2>      // KP pieces of 8 columns per lane: LANES * KP * 8 >= Kimg
-__global__ void __launch_bounds__(256) k_wide_ln(WideLnArgs a) {
+__global__ void __launch_bounds__(256, (V >= 1 && LANES == 16) ? 6 : 1) k_wide_ln(WideLnArgs a) {
   constexpr int RPW = 32 / LANES;
   const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + ((threadIdx.x & 31) / LANES);
   const int lane = threadIdx.x & (LANES - 1);
