@@ -86,7 +86,9 @@ typedef struct jodo_imglinear_args {
   /* optional fused row dot products (JODO_EPI_ACT only, may be null): dot_out[row, 4 s + k] = sum over the columns of
    * slot s of act(acc + bias)[row, c] * dot_w[k * N + c], k < 3, slot s = (column tile) * 2 + (column half): the caller adds
    * the 2 N / NT slots.  coord_mlp.2 (three outputs, reference models/mol_gnn.py:66-69, 82) rides on coord_mlp.0's epilogue, so
-   * the SiLU output never goes to HBM.  With dot_out no other output is required. */
+   * the SiLU output never goes to HBM.  With dot_out no other output is required.  With dot_out as the ONLY output, SiLU,
+   * NT >= 128 and N <= 512 the launch runs k_imglinear_dot2 (two 128-row tiles share every weight chunk: half the L2 bytes per
+   * FLOP; 16 epilogue warps reading tensor memory directly); NT = 192 is accepted in that mode only. */
   const float* dot_w; float* dot_out; int ld_dot;
 } jodo_imglinear_args;
 int jodo_imglinear(const jodo_imglinear_args* a, void* stream);

@@ -13,6 +13,7 @@
 //
 // A CTA walks work units (128-row tile, NT-column tile) with the column tile fastest, so the CTAs that share an A
 // tile run at the same time and re-read it from L2.  The epilogue of unit i overlaps the main loop of unit i+1.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -341,6 +342,142 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused-row-dots GEMM of the wide path's coordinate branch (coord_mlp.0 -> SiLU -> coord_mlp.2 dots; reference
+// models/mol_gnn.py:84-88), rows = directed edges.  With K = N = D the streaming kernel above moves (A tile + W tile) per
+// 128 x NT output tile through L2 -- 64 FLOP per byte at NT = 128, which is the L2 bandwidth cap of the chip (~6300 B/clk),
+// not the tensor pipe.  Here a work unit is TWO 128-row tiles x one NT-column tile (NT = 192 at D = 384, 256 at D = 256 / 512):
+// every W chunk is fetched once for both row tiles (two MMAs per chunk into two accumulators), and the epilogue has no
+// HBM output except the dots, so it needs no row-major staging: 16 epilogue warps read their rows straight from tensor
+// memory (lane = row; warp = lane quarter x {row tile, column half}), with the per-column constants (bias, the three dot
+// weights) broadcast from a shared-memory table.
+constexpr int ID_EPI_WARPS = 16;
+constexpr int ID_THREADS = 64 + 32 * ID_EPI_WARPS;
+constexpr int ID_RING_BYTES = 196608;                // 3 stages at NT = 192 / 256, 4 at NT = 128
+constexpr int ID_CTAB_BYTES = 8192;                  // float4 per output column, N <= 512
+constexpr int ID_SMEM = ID_RING_BYTES + ID_CTAB_BYTES + 512;
+static_assert(ID_SMEM <= 232448, "shared memory budget");
+
+__global__ void __launch_bounds__(ID_THREADS, 1) k_imglinear_dot2(ImgLinearArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int nt = a.NT;
+  const int stage_bytes = 2 * IL_A_STAGE + nt * 128;
+  int stages = ID_RING_BYTES / stage_bytes;
+  if (stages > IL_MAX_STAGES) stages = IL_MAX_STAGES;
+  float4* ctab = reinterpret_cast<float4*>(smem + ID_RING_BYTES);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + ID_RING_BYTES + ID_CTAB_BYTES);
+  uint64_t* bar_empty = bar_full + IL_MAX_STAGES;
+  uint64_t* bar_tfull = bar_empty + IL_MAX_STAGES;
+  uint64_t* bar_tempty = bar_tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = a.K / 64;
+  const int ntn = a.N / nt;
+  const int mt = (a.M + TILE_ROWS - 1) / TILE_ROWS;
+  const int units = ((mt + 1) / 2) * ntn;
+
+  if (tid == 0) {
+    for (int s = 0; s < IL_MAX_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, ID_EPI_WARPS);
+    fence_barrier_init();
+  }
+  for (int c = tid; c < a.N; c += ID_THREADS)
+    ctab[c] = make_float4(a.bias ? __ldg(a.bias + c) : 0.f, __ldg(a.dot_w + c), __ldg(a.dot_w + a.N + c), __ldg(a.dot_w + 2 * a.N + c));
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint8_t* Aimg = static_cast<const uint8_t*>(a.Aimg);
+      const uint8_t* Wimg = static_cast<const uint8_t*>(a.Wimg);
+      const uint32_t wbytes = (uint32_t)nt * 128u;
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int pr = u / ntn, n = u - pr * ntn;
+        const int m0 = 2 * pr, m1 = min(2 * pr + 1, mt - 1);    // odd tail: the second accumulator repeats the first tile (not stored)
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1u;
+          mbar_wait(&bar_empty[s], ph ^ 1u);
+          uint8_t* dst = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&bar_full[s], 2 * IL_A_STAGE + wbytes);
+          bulk_g2s(dst, Aimg + ((size_t)m0 * nk + kc) * IL_A_STAGE, IL_A_STAGE, &bar_full[s]);
+          bulk_g2s(dst + IL_A_STAGE, Aimg + ((size_t)m1 * nk + kc) * IL_A_STAGE, IL_A_STAGE, &bar_full[s]);
+          bulk_g2s(dst + 2 * IL_A_STAGE, Wimg + ((size_t)n * nk + kc) * wbytes, wbytes, &bar_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(nt);
+      uint32_t it = 0, ai = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++ai) {
+        mbar_wait(bar_tempty, (ai & 1u) ^ 1u);
+        tc_fence_after();
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1u;
+          mbar_wait(&bar_full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sw = sa + 2 * IL_A_STAGE;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t wd = umma_desc_sw128(sw + kk * 32);
+            umma_f16(tmem, umma_desc_sw128(sa + kk * 32), wd, idesc, (kc | kk) ? 1u : 0u);
+            umma_f16(tmem + 256u, umma_desc_sw128(sa + IL_A_STAGE + kk * 32), wd, idesc, (kc | kk) ? 1u : 0u);
+          }
+          umma_commit(&bar_empty[s]);
+        }
+        umma_commit(bar_tfull);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int rq = warp & 3;                       // TMEM lane quarter this warp may read
+    const int q = ew >> 2;                         // (row tile, column half): warps 4q+2 .. 4q+5 cover the four lane quarters
+    const int tile = q >> 1, half = q & 1;
+    const int cw = nt / 2;                         // 64, 96 or 128 columns per warp: chunks of 32
+    const int row = rq * 32 + lane;
+    const uint32_t tbase = tmem + (uint32_t)tile * 256u + ((uint32_t)rq << 21) + (uint32_t)(half * cw);
+    uint32_t ai = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ai) {
+      const int pr = u / ntn, n = u - pr * ntn;
+      const int m = 2 * pr + tile;
+      const float4* ct = ctab + n * nt + half * cw;
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+      mbar_wait(bar_tfull, ai & 1u);
+      tc_fence_after();
+      for (int c0 = 0; c0 < cw; c0 += 32) {
+        float x[32];
+        tmem_ld32(tbase + (uint32_t)c0, x);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float4 k = ct[c0 + i];             // (bias, w0, w1, w2) of this column: one broadcast LDS.128
+          const float s = silu_fast(x[i] + k.x);
+          d0 = fmaf(s, k.y, d0); d1 = fmaf(s, k.z, d1); d2 = fmaf(s, k.w, d2);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(bar_tempty);  // the accumulators are drained: the next unit's MMAs may start
+      const int gr = m * TILE_ROWS + row;
+      if (m < mt && gr < a.M)
+        *reinterpret_cast<float4*>(a.dot_out + (size_t)gr * a.ld_dot + 4 * (n * 2 + half)) = make_float4(d0, d1, d2, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
 }  // namespace
 
 cudaError_t sat_count_imglinear(unsigned int* out, bool reset) {
@@ -352,7 +489,8 @@ cudaError_t sat_count_imglinear(unsigned int* out, bool reset) {
 const char* check_imglinear(const ImgLinearArgs& a) {
   if (a.M <= 0) return "imglinear: M <= 0";
   if (a.K <= 0 || a.K % 64) return "imglinear: K must be a positive multiple of 64";
-  if (!(a.NT == 64 || a.NT == 128 || a.NT == 256)) return "imglinear: NT must be 64/128/256";
+  const bool dot_only = a.dot_out && !a.C32 && !a.C16 && !a.Cimg;
+  if (!(a.NT == 64 || a.NT == 128 || a.NT == 256 || (a.NT == 192 && dot_only))) return "imglinear: NT must be 64/128/256 (192: fused row dots only)";
   if (a.N <= 0 || a.N % a.NT) return "imglinear: N must be a multiple of NT";
   if (!a.Aimg || !a.Wimg) return "imglinear: operand image missing";
   if ((reinterpret_cast<uintptr_t>(a.Aimg) | reinterpret_cast<uintptr_t>(a.Wimg)) & 127) return "imglinear: images must be 128-byte aligned";
@@ -392,6 +530,18 @@ cudaError_t launch_imglinear(const ImgLinearArgs& a_in, int num_sms, cudaStream_
   const int grid = units < num_sms ? units : num_sms;
   const int mode = il_mode(a.epi, a.C32 != nullptr, a.C16 != nullptr, a.Cimg != nullptr, a.Cimg2 != nullptr, a.dot_out != nullptr);
   const bool silu_or_none = a.epi != EPI_ACT || a.act_out == ACT_SILU;
+  if (mode == il_mode(EPI_ACT, false, false, false, false, true) && a.act_out == ACT_SILU && a.NT >= 128 && a.N <= 512) {
+    // wide: coord_mlp.0 + coord_mlp.2 dots -- two row tiles per W chunk, 16 epilogue warps (JODO_DOT_LEGACY=1: the streaming kernel)
+    static const bool legacy = [] { const char* e = getenv("JODO_DOT_LEGACY"); return e && e[0] == '1'; }();
+    if (!legacy || a.NT == 192) {
+      static DevAttr attr = {};
+      cudaError_t e0 = ensure_dyn_smem(k_imglinear_dot2, ID_SMEM, attr);
+      if (e0 != cudaSuccess) return e0;
+      const int u2 = ((a.M + 2 * TILE_ROWS - 1) / (2 * TILE_ROWS)) * (a.N / a.NT);
+      k_imglinear_dot2<<<u2 < num_sms ? u2 : num_sms, ID_THREADS, ID_SMEM, stream>>>(a);
+      return cudaGetLastError();
+    }
+  }
   if (a.epi == EPI_STORE && a.C16 && a.c16_piece_major && !a.C32 && !a.Cimg && !a.dot_out)
     return launch_mode<IL_MODE_PM16>(a, grid, stream);                                                                              // q|k|v, hoisted parts (fused path)
   if (silu_or_none) {

@@ -23,6 +23,17 @@ _c = ctypes.c_int
 # per block at GEOM nf = 384, B = 512): eight LayerNorm warps per SM cannot keep enough gathers in flight, where the row kernel
 # runs at full occupancy.  Off by default.
 FUSED_EQUI = os.environ.get('JODO_WIDE_EQUI_FUSED') == '1'
+# column tile of coord_mlp.0 (fused-row-dots GEMM, csrc/imglinear.cu k_imglinear_dot2: two row tiles share every W chunk, so the
+# widest tile that divides D and fits two accumulators in tensor memory moves the fewest L2 bytes per FLOP); JODO_C0_NT: A/B
+C0_NT = int(os.environ.get('JODO_C0_NT', '0'))
+
+
+def c0_tile(D):
+    if C0_NT or FUSED_EQUI:                   # the fused variant (csrc/wide_equi.cu) is built for 128-column tiles
+        return C0_NT or 128
+    return 256 if D % 256 == 0 else (192 if D % 192 == 0 else 128)
+
+
 EDP = 128            # row stride (floats) of the per-edge fp32 buffers and K of the per-edge images (ed <= 128)
 
 
@@ -105,7 +116,7 @@ def pack_wide(pk, sd, d, add_lin, lin):
             we_l = W(f'{b}.edge_emb')
             add_lin(p + 'emb', [(we_l[:, ed:], 0, 0), (we_l[:, :ed], 0, ed)], [(Bv(f'{b}.edge_emb'), 0)], 128, ed, 2 * ed)
             add_lin(p + 'equi_in', [(wi[:, 2 * D:], 0, 0)], [], 128, D, 2 * ed)             # K = 2ed: [e | dist]
-            lin(p + 'c0', f'{b}.equi_update.coord_mlp.0', 128)
+            lin(p + 'c0', f'{b}.equi_update.coord_mlp.0', c0_tile(D))
             # coord_mlp.2 (1 + X outputs, no bias) rides on coord_mlp.0's epilogue as three fp32 row dots (rows beyond 1 + X zero)
             pk.mat(p + 'c2.w32', 3, D, [(W(f'{b}.equi_update.coord_mlp.2'), 0, 0)])
         add_lin(p + 'g01', [(W(f'{b}.attn_mpnn.lin_edge0'), 0, 0), (W(f'{b}.attn_mpnn.lin_edge1'), qkp, 0)], [], 128, qkp + D, EDP)

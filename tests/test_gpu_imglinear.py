@@ -133,7 +133,8 @@ def test_ln_mod_img_matches_torch():
     assert float(yr[Nn:].abs().sum()) == 0.0
 
 
-@pytest.mark.parametrize('M,K,N,NT,epi', [(1000, 256, 128, 128, 'gated'), (700, 128, 128, 128, 'store'), (260, 384, 384, 128, 'act')])
+@pytest.mark.parametrize('M,K,N,NT,epi', [(1000, 256, 128, 128, 'gated'), (700, 128, 128, 128, 'store'), (260, 384, 384, 128, 'act'),
+                                            (700, 384, 384, 192, 'act'), (390, 256, 512, 256, 'act'), (128, 128, 256, 256, 'act')])
 def test_imglinear_placed_images_and_row_dots(M, K, N, NT, epi):
     """Placed image outputs (the output columns written at an offset inside wider operand images, only the first
     `ncols` columns, everything else untouched) and the fused row dot products of the activated output
@@ -156,7 +157,7 @@ def test_imglinear_placed_images_and_row_dots(M, K, N, NT, epi):
         got = dot[:, :4 * nslots].double().reshape(M, nslots, 4)
         assert float(got[..., 3].abs().max()) == 0.0
         assert float((got[..., :3].sum(1) - want).abs().max()) < 2e-3 * float(want.abs().max())
-        # every slot is the dot over its own 64 (= NT / 2) columns
+        # every slot is the dot over its own NT / 2 columns
         cw = NT // 2
         for s in range(nslots):
             ws_ = act[:, s * cw:(s + 1) * cw] @ dw.double()[:, s * cw:(s + 1) * cw].t()

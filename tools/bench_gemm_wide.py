@@ -23,7 +23,14 @@ shapes = {  # name: (K, N, NT, outputs, act)
     'c0 img silu': (384, 384, 128, ('Cimg',), _lib.ACT_SILU),
     'ff3 img silu': (128, 384, 128, ('Cimg',), _lib.ACT_SILU),
     'emb c32': (192, 128, 128, ('C32',), None),
+    'c0 dots nt128': (384, 384, 128, ('dot',), _lib.ACT_SILU),
+    'c0 dots nt192': (384, 384, 192, ('dot',), _lib.ACT_SILU),
+    'c0 dots D256 nt256': (256, 256, 256, ('dot',), _lib.ACT_SILU),
 }
+only = os.environ.get('ONLY')
+if only:
+    shapes = {k: v for k, v in shapes.items() if only in k}
+dw = None
 for name, (K, N, NT, outs, act) in shapes.items():
     W = weight_image_h(torch.randn(N, K, device=dev) / K ** 0.5, NT)
     b = torch.randn(N, device=dev)
@@ -33,14 +40,19 @@ for name, (K, N, NT, outs, act) in shapes.items():
         if 'C16' in outs: d['C16'] = torch.empty(M, N, device=dev, dtype=torch.float16)
         if 'C32' in outs: d['C32'] = torch.empty(M, N, device=dev)
         if 'Cimg' in outs: d['Cimg'] = torch.empty(mt * 128 * N, device=dev, dtype=torch.float16)
+        if 'dot' in outs: d['dot_out'] = torch.zeros(M, 64, device=dev); d['dot_w'] = torch.randn(3, N, device=dev)
         sets.append(d)
 
     def run(d):
-        kw = {k: d[k] for k in ('C16', 'C32', 'Cimg') if k in d}
+        kw = {k: d[k] for k in ('C16', 'C32', 'Cimg', 'dot_out', 'dot_w') if k in d}
         if act is not None:
             kw.update(epi=_lib.EPI_ACT, act_out=act)
         _lib.imglinear(d['A'], M, K, W, b, N, NT, **kw)
-    for d in sets: run(d)
+    try:
+        for d in sets: run(d)
+    except _lib.JodoError as e:
+        print(f'{name:20s} refused: {e}')
+        continue
     torch.cuda.synchronize()
     reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
