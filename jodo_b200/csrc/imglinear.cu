@@ -25,14 +25,16 @@ __device__ unsigned int g_sat_imglinear;
 
 namespace {
 
-constexpr int IL_THREADS = 320;
-constexpr int IL_EPI_WARPS = 8;
+// Epilogue warps: 8 (two column-half teams, double-buffered staging) or 16 (four column-quarter teams, one staging
+// buffer each -- the same shared memory; NT >= 128).  The GEMMs here are short in K, so a 128 x NT tile's epilogue
+// (activation, packing, stores) takes longer than its MMAs: with 16 warps it keeps up (k_imglinear<MODE, ACT, 16>).
+constexpr int il_threads(int ew) { return 64 + 32 * ew; }
 constexpr int IL_A_STAGE = TILE_ROWS * 128;          // 16 KB: [128 rows][64 fp16]
 constexpr int IL_RING_BYTES = 147456;                // 144 KB of stages (3 x 48 KB at NT = 256)
 constexpr int IL_MAX_STAGES = 6;
 constexpr int IL_STG_ROW = 144;                      // staging row: 32 fp32 + 16 bytes of padding (conflict-free both ways)
 constexpr int IL_STG_BUF = TILE_ROWS * IL_STG_ROW;   // 18 KB
-constexpr int IL_STG_BYTES = 2 * 2 * IL_STG_BUF;     // 2 column-half teams x 2 buffers
+constexpr int IL_STG_BYTES = 2 * 2 * IL_STG_BUF;     // 2 column-half teams x 2 buffers, or 4 column-quarter teams x 1
 constexpr int IL_SMEM = 1024 + IL_RING_BYTES + IL_STG_BYTES + 512;
 static_assert(IL_SMEM <= 232448, "shared memory budget");
 
@@ -59,8 +61,9 @@ constexpr int il_mode(int epi, bool c32, bool c16, bool cimg, bool cimg2 = false
 // 16 useful bytes per store instruction here.)
 constexpr int IL_MODE_PM16 = 128;
 
-template <int MODE, int ACT = ACT_SILU>
-__global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
+template <int MODE, int ACT = ACT_SILU, int EW = 8>
+__global__ void __launch_bounds__(il_threads(EW), 1) k_imglinear(ImgLinearArgs a) {
+  constexpr int NTEAM = EW / 4, NBUF = EW == 8 ? 2 : 1;
   if (a.skip_if_zero && *a.skip_if_zero == 0) return;     // uniform conditioning: nothing to do (warp-uniform, before any setup)
   // declared with its alignment (not aligned by pointer arithmetic): the compiler must see a shared-memory address, or every
   // staging access below becomes a generic LD / ST instead of LDS / STS
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < IL_MAX_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], IL_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], EW); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -146,10 +149,10 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
     // one row, so that bias / residual / gate loads and every store are coalesced.
     const int ew = warp - 2;
     const int rq = warp & 3;                       // TMEM lane quarter this warp may read
-    const int team = ew >> 2;                      // column half
+    const int team = ew >> 2;                      // column half (quarter with 16 warps)
     const int wt = ((rq - 2) & 3);                 // warp index inside the team (0..3), any bijection works
     const int row = rq * 32 + lane;
-    const int cw = nt / 2;                         // columns per team (32, 64 or 128)
+    const int cw = nt / NTEAM;                     // columns per team (32, 64 or 128)
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     const int epi = MODE < 0 ? a.epi : (MODE == IL_MODE_PM16 ? EPI_STORE : (MODE & 3));
     const bool has32 = MODE < 0 ? a.C32 != nullptr : (MODE & 4) != 0;
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
     float* __restrict__ dot_out = a.dot_out;
     const bool c16_pm = a.c16_piece_major != 0;
     const bool gate_row0 = a.nonuni != nullptr && *a.nonuni == 0;       // uniform conditioning: every molecule's gate row is row 0
-    uint8_t* stg = stg_base + team * 2 * IL_STG_BUF;
+    uint8_t* stg = stg_base + team * NBUF * IL_STG_BUF;
     const int r0 = wt * 4 + rsub;                  // this thread's rows in the row-major pass: r0 + 16 * it
     uint32_t ai = 0, sb = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++ai) {
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
         if (lane == 0) mbar_arrive_cta(&bar_tempty[ab]);
         continue;
       }
-      for (int c0 = team * cw; c0 < (team + 1) * cw; c0 += 32, sb ^= 1u) {
+      for (int c0 = team * cw; c0 < (team + 1) * cw; c0 += 32, sb = (NBUF == 2 ? sb ^ 1u : 0u)) {
         uint8_t* buf = stg + sb * IL_STG_BUF;
         const int col = n * nt + c0 + c4;
         // loads that do not depend on the accumulator go first
@@ -236,8 +239,10 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
           dw1 = __ldg(reinterpret_cast<const float4*>(dot_w + a.N + col));
           dw2 = __ldg(reinterpret_cast<const float4*>(dot_w + 2 * a.N + col));
         }
-        float4 y[8], g[8];
-        if (epi == EPI_GATED_RES) {
+        // residual / gate rows: loaded ahead of the accumulator with 8 warps; with 16 warps (96 registers) inside the row loop
+        constexpr bool PREFETCH = EW == 8;
+        float4 y[PREFETCH ? 8 : 1], g[PREFETCH ? 8 : 1];
+        if (PREFETCH && epi == EPI_GATED_RES) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int gr = gr0 + 16 * it;
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
         {
           float x[32];
           tmem_ld32(tmem + ab * 256u + ((uint32_t)rq << 21) + (uint32_t)c0, x);
+          if (NBUF == 1) named_bar_sync(1 + team, 128);   // one buffer per team: the row-major pass of the previous chunk is done
 #pragma unroll
           for (int p = 0; p < 8; ++p)
             *reinterpret_cast<float4*>(buf + row * IL_STG_ROW + p * 16) = make_float4(x[4 * p], x[4 * p + 1], x[4 * p + 2], x[4 * p + 3]);
@@ -278,8 +284,14 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
               o.x = act_apply(o.x, act); o.y = act_apply(o.y, act); o.z = act_apply(o.z, act); o.w = act_apply(o.w, act);
             }
           } else if (epi == EPI_GATED_RES) {        // out = res + gate[mol] * (acc + bias)
-            o.x = fmaf(g[it].x, o.x, y[it].x); o.y = fmaf(g[it].y, o.y, y[it].y);
-            o.z = fmaf(g[it].z, o.z, y[it].z); o.w = fmaf(g[it].w, o.w, y[it].w);
+            float4 yy, gg;
+            if (PREFETCH) { yy = y[it]; gg = g[it]; }
+            else if (live) {
+              yy = *reinterpret_cast<const float4*>(aux + (size_t)gr * ld_aux + col);
+              gg = __ldg(reinterpret_cast<const float4*>(gate + (size_t)mol[it] * ld_gate + col));
+            } else { yy = gg = make_float4(0.f, 0.f, 0.f, 0.f); }
+            o.x = fmaf(gg.x, o.x, yy.x); o.y = fmaf(gg.y, o.y, yy.y);
+            o.z = fmaf(gg.z, o.z, yy.z); o.w = fmaf(gg.w, o.w, yy.w);
           }
           if (!live) o = make_float4(0.f, 0.f, 0.f, 0.f);
           if (hasdot) {
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(IL_THREADS, 1) k_imglinear(ImgLinearArgs a) {
       if (hasdot) {
         // The 8 lanes of a row group hold partial sums of the same 8 rows x 3 outputs.  Butterfly with halving: after the
         // exchanges over lane bits 2, 1, 0 (12 + 6 + 3 shuffles) lane s of the group holds the three complete sums of row s.
-        const int slot = n * 2 + team;
+        const int slot = n * NTEAM + team;
         float w12[12], w6[6], w3[3];
         {
           const bool hi = (lane & 4) != 0;
@@ -513,13 +525,25 @@ const char* check_imglinear(const ImgLinearArgs& a) {
 }
 
 namespace {
-template <int MODE, int ACT = ACT_SILU>
-cudaError_t launch_mode(const ImgLinearArgs& a, int grid, cudaStream_t stream) {
+template <int MODE, int ACT, int EW>
+cudaError_t launch_mode_ew(const ImgLinearArgs& a, int grid, cudaStream_t stream) {
   static DevAttr attr = {};
-  cudaError_t e0 = ensure_dyn_smem(k_imglinear<MODE, ACT>, IL_SMEM, attr);
+  cudaError_t e0 = ensure_dyn_smem(k_imglinear<MODE, ACT, EW>, IL_SMEM, attr);
   if (e0 != cudaSuccess) return e0;
-  k_imglinear<MODE, ACT><<<grid, IL_THREADS, IL_SMEM, stream>>>(a);
+  k_imglinear<MODE, ACT, EW><<<grid, il_threads(EW), IL_SMEM, stream>>>(a);
   return cudaGetLastError();
+}
+// WIDE_OK: this compiled mode also exists with 16 epilogue warps (taken when NT >= 128; JODO_IL_EPI8=1: always 8).  Measured on
+// B200 (GEOM nf = 384): tanh(lin_edge0 | lin_edge1) 0.299 -> 0.253 ms, ff_linear3 0.160 -> 0.132, input_lin edge part 0.145 -> 0.134.
+// The gated-residual modes stay on 8 warps: without the registers to prefetch their residual / gate rows they got slower
+// (ff_linear2 0.041 -> 0.050 ms, ff_linear4 0.210 -> 0.232).
+template <int MODE, int ACT = ACT_SILU, bool WIDE_OK = false>
+cudaError_t launch_mode(const ImgLinearArgs& a, int grid, cudaStream_t stream) {
+  if (WIDE_OK) {
+    static const bool epi8 = [] { const char* e = getenv("JODO_IL_EPI8"); return e && e[0] == '1'; }();
+    if (a.NT >= 128 && !epi8) return launch_mode_ew<MODE, ACT, WIDE_OK ? 16 : 8>(a, grid, stream);
+  }
+  return launch_mode_ew<MODE, ACT, 8>(a, grid, stream);
 }
 }  // namespace
 
@@ -543,12 +567,12 @@ cudaError_t launch_imglinear(const ImgLinearArgs& a_in, int num_sms, cudaStream_
     }
   }
   if (a.epi == EPI_STORE && a.C16 && a.c16_piece_major && !a.C32 && !a.Cimg && !a.dot_out)
-    return launch_mode<IL_MODE_PM16>(a, grid, stream);                                                                              // q|k|v, hoisted parts (fused path)
+    return launch_mode<IL_MODE_PM16, ACT_SILU, true>(a, grid, stream);                                                                              // q|k|v, hoisted parts (fused path)
   if (silu_or_none) {
     switch (mode) {
-      case il_mode(EPI_STORE, false, true, false): return launch_mode<il_mode(EPI_STORE, false, true, false)>(a, grid, stream);      // q|k|v, hoisted parts
-      case il_mode(EPI_STORE, true, false, false): return launch_mode<il_mode(EPI_STORE, true, false, false)>(a, grid, stream);      // node_i
-      case il_mode(EPI_ACT, false, false, true): return launch_mode<il_mode(EPI_ACT, false, false, true)>(a, grid, stream);          // ff_linear1
+      case il_mode(EPI_STORE, false, true, false): return launch_mode<il_mode(EPI_STORE, false, true, false), ACT_SILU, true>(a, grid, stream);      // q|k|v, hoisted parts
+      case il_mode(EPI_STORE, true, false, false): return launch_mode<il_mode(EPI_STORE, true, false, false), ACT_SILU, true>(a, grid, stream);      // node_i
+      case il_mode(EPI_ACT, false, false, true): return launch_mode<il_mode(EPI_ACT, false, false, true), ACT_SILU, true>(a, grid, stream);          // ff_linear1
       case il_mode(EPI_GATED_RES, true, false, true): return launch_mode<il_mode(EPI_GATED_RES, true, false, true)>(a, grid, stream);  // ff_linear2
       case il_mode(EPI_GATED_RES, true, false, false): return launch_mode<il_mode(EPI_GATED_RES, true, false, false)>(a, grid, stream);  // wide: ff_linear4, head accumulation
       case il_mode(EPI_GATED_RES, true, false, true, true): return launch_mode<il_mode(EPI_GATED_RES, true, false, true, true)>(a, grid, stream);  // wide: ff_linear4 -> e32 + [e | dist] + heads' operand
@@ -556,7 +580,7 @@ cudaError_t launch_imglinear(const ImgLinearArgs& a_in, int num_sms, cudaStream_
       default: break;
     }
   } else if (a.act_out == ACT_TANH && mode == il_mode(EPI_ACT, false, true, false)) {
-    return launch_mode<il_mode(EPI_ACT, false, true, false), ACT_TANH>(a, grid, stream);                                            // wide: tanh(lin_edge0 | lin_edge1)
+    return launch_mode<il_mode(EPI_ACT, false, true, false), ACT_TANH, true>(a, grid, stream);                                            // wide: tanh(lin_edge0 | lin_edge1)
   }
   return launch_mode<-1>(a, grid, stream);
 }
