@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 13
+#define JODO_ABI_VERSION 14
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -391,6 +391,20 @@ typedef struct jodo_wide_equi_args {     /* fused coordinate branch: LN(input_li
   float* out; int ld_out;                 /* out[row, 4 s + k], s < 2: partial coord_mlp.2 outputs of the two column halves */
 } jodo_wide_equi_args;
 int jodo_wide_equi(const jodo_wide_equi_args* a, void* stream);
+typedef struct jodo_wide_ffn_args {      /* edge FFN of one block on pair rows, one kernel (csrc/wide_ffn.cu): norm2_edge + modulation of
+                                             e + gate * (P[i] + P[j] + b), ff_linear3, SiLU, ff_linear4, gated residual (mol_gnn.py:304-317) */
+  int M, ed, H;                           /* pair rows (whole 128-row tiles), edge width (32 / 64 / 96), hidden width r * ed, r = 2 or 4 */
+  float* e32; int lde;                    /* in / out: fp32 edge state rows */
+  const float* P; int ldp;                /* hoisted node2edge_lin per atom: fp32 rows without the bias */
+  const int* pair_i; const int* pair_j; const int* pair_mol;   /* atoms of the pair (pair_i < 0: padding row -> zeros), molecule */
+  const float* n2e_bias;                  /* [ed] */
+  const float* tab; int ld_tab, off_gate, off_shift, off_scale, off_gate2;   /* per-molecule table (scale column holds 1 + scale) */
+  const void* w3_img; const float* b3;    /* ff_linear3: fp16 image [ceil(ed / 64)][H][128 B] and bias [H], both pre-scaled by 1/2 (SiLU = h + h tanh h) */
+  const void* w4_img; const float* b4;    /* ff_linear4: fp16 image [H / 64][ed][128 B], bias [ed] */
+  void* img1; int k1, col1;               /* fp16 copies of the new state: columns [col, col + ed) of operand images with k columns (may be null) */
+  void* img2; int k2, col2;
+} jodo_wide_ffn_args;
+int jodo_wide_edge_ffn(const jodo_wide_ffn_args* a, void* stream);
 int jodo_wide_embed_in(const jodo_wide_embed_args* a, void* stream);
 int jodo_wide_put(const float* src, int ld, int M, int W, const int* valid, void* img1, int K1, int col1, void* img2, int K2,
                   int col2, void* img3, int K3, int col3, void* stream);   /* fp32 rows -> fp16 columns [col, col + W) of up to three images */

