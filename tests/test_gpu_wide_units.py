@@ -88,3 +88,75 @@ def test_molecule_staged_attention_matches_per_target_kernel_and_fp64(n_list, D,
     print(f'n={n_list} D={D} X={X}: per-target {e1:.2e}  molecule-staged {e2:.2e} (of max |hnode| {scale:.2f})')
     assert e1 < 2e-5 and e2 < 2e-5                      # fp32 math on identical fp16 operands
     assert bool(torch.isfinite(staged).all())
+
+
+# ---- fused edge FFN (csrc/wide_ffn.cu): every compiled size against fp64 on the fp16-rounded operands
+def _ffn_reference(e, P, pi, pj, mol, nb, tab, offs, w3, b3, w4, b4, ed):
+    """reference models/mol_gnn.py:304-305, 313-317 in fp64; the two GEMM operands (e2, the SiLU output, both weights) are
+    rounded to fp16 as the kernel stores them."""
+    h = lambda x: x.half().double()
+    og, osh, osc, og2 = offs
+    valid = pi >= 0
+    i, j = pi.clamp(min=0).long(), pj.clamp(min=0).long()
+    t = tab.double()[mol.long()]
+    v = e.double()[:, :ed] + t[:, og:og + ed] * (P.double()[i, :ed] + P.double()[j, :ed] + nb.double())
+    mu = v.mean(1, keepdim=True)
+    var = (v * v).mean(1, keepdim=True) - mu * mu
+    e2 = (v - mu) / torch.sqrt(var.clamp(min=0) + 1e-6) * t[:, osc:osc + ed] + t[:, osh:osh + ed]      # the table stores 1 + scale
+    hid = h(e2) @ h(w3).t() + b3.double()
+    act = hid * torch.sigmoid(hid)
+    y = h(act) @ h(w4).t() + b4.double()
+    out = e2 + t[:, og2:og2 + ed] * y
+    out[~valid] = 0
+    return out
+
+
+@pytest.mark.parametrize('ed,r,tiles', [(32, 2, 3), (64, 2, 5), (96, 2, 4), (32, 4, 2), (64, 4, 7), (96, 4, 1), (96, 4, 13), (96, 4, 700)])
+def test_fused_edge_ffn_matches_fp64(ed, r, tiles):
+    from jodo_b200.pack import weight_image_h
+    g = torch.Generator(device='cuda').manual_seed(ed * 100 + r * 10 + tiles)
+    rn = lambda *s: torch.randn(*s, device='cuda', generator=g)
+    M, H, Nn, B, EDP = tiles * 128, r * ed, 300, 7, 128
+    e32 = torch.zeros(M, EDP, device='cuda')
+    e32[:, :ed] = rn(M, ed)
+    P = torch.zeros(Nn, EDP, device='cuda')
+    P[:, :ed] = rn(Nn, ed)
+    pi = torch.randint(0, Nn, (M,), device='cuda', generator=g, dtype=torch.int32)
+    pj = torch.randint(0, Nn, (M,), device='cuda', generator=g, dtype=torch.int32)
+    pi[torch.rand(M, device='cuda', generator=g) < 0.05] = -1                       # padding rows anywhere
+    pi[-17:] = -1
+    mol = torch.randint(0, B, (M,), device='cuda', generator=g, dtype=torch.int32).sort().values.int()
+    nb = rn(ed)
+    ld_tab = 16 + 6 * ed
+    tab = rn(B, ld_tab)
+    tab[:, 16 + 2 * ed:16 + 3 * ed] += 1.0                                          # (1 + scale) column
+    offs = (16, 16 + ed, 16 + 2 * ed, 16 + 3 * ed)                                  # gate, shift, scale, gate2
+    w3, b3 = rn(H, ed) / ed ** 0.5, rn(H)
+    w4, b4 = rn(ed, H) / H ** 0.5, rn(ed)
+    k3 = (ed + 63) // 64 * 64
+    w3p = torch.zeros(H, k3, device='cuda')
+    w3p[:, :ed] = 0.5 * w3
+    w3i, w4i = weight_image_h(w3p, H), weight_image_h(w4, ed)
+    b3h = (0.5 * b3).contiguous()
+    k1, c1, k2, c2 = 192, 0, 384, 128
+    img1 = torch.full((tiles * 128 * k1,), 7.0, device='cuda', dtype=torch.float16)
+    img2 = torch.full((tiles * 128 * k2,), 7.0, device='cuda', dtype=torch.float16)
+    want = _ffn_reference(e32, P, pi, pj, mol, nb, tab, offs, w3, b3, w4, b4, ed)
+    e_in = e32.clone()
+    dp = _lib.dp
+    a = _lib.WideFfnArgs(M, ed, H, dp(e32), EDP, dp(P), EDP, dp(pi), dp(pj), dp(mol), dp(nb), dp(tab), ld_tab, offs[0], offs[1], offs[2],
+                         offs[3], dp(w3i), dp(b3h), dp(w4i), dp(b4), dp(img1), k1, c1, dp(img2), k2, c2)
+    _lib.call('jodo_wide_edge_ffn', ctypes.byref(a), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    err = float((e32[:, :ed].double() - want).abs().max()) / scale
+    print(f'ed={ed} r={r} tiles={tiles}: {err:.2e} of max |e_out| {scale:.2f}')
+    assert err < 2e-3                                                               # two fp16-operand GEMMs, fp32 accumulation
+    assert bool((e32[:, ed:] == e_in[:, ed:]).all())                                # the padding columns are not touched
+    from test_gpu_imglinear import image_rows
+    for img, k, c0 in ((img1, k1, c1), (img2, k2, c2)):
+        rows = image_rows(img, k)
+        assert float((rows[:, c0:c0 + ed].double() - e32[:, :ed].double()).abs().max()) <= 1e-3 * max(1.0, scale)     # fp16 copy of the new state
+        keep = torch.ones(k, dtype=torch.bool)
+        keep[c0:c0 + ed] = False
+        assert bool((rows[:, keep] == 7.0).all())                                   # nothing outside the placed columns
