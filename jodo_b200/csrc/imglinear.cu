@@ -381,20 +381,23 @@ __global__ void __launch_bounds__(ID_THREADS, 1) k_imglinear_dot2(ImgLinearArgs 
   float4* ctab = reinterpret_cast<float4*>(smem + ID_RING_BYTES);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + ID_RING_BYTES + ID_CTAB_BYTES);
   uint64_t* bar_empty = bar_full + IL_MAX_STAGES;
-  uint64_t* bar_tfull = bar_empty + IL_MAX_STAGES;
-  uint64_t* bar_tempty = bar_tfull + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 1);
+  uint64_t* bar_tfull = bar_empty + IL_MAX_STAGES;            // [2]
+  uint64_t* bar_tempty = bar_tfull + 2;                        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = a.K / 64;
   const int ntn = a.N / nt;
   const int mt = (a.M + TILE_ROWS - 1) / TILE_ROWS;
   const int units = ((mt + 1) / 2) * ntn;
+  // accumulators: NT = 128 -- two sets of (tile 0, tile 1) at columns 0 | 128 and 256 | 384, so the epilogue of one unit runs
+  // under the MMAs of the next; wider tiles -- one set at columns 0 | 256
+  const uint32_t nbuf = nt <= 128 ? 2u : 1u;
+  const uint32_t tile_cols = nt <= 128 ? 128u : 256u;
 
   if (tid == 0) {
     for (int s = 0; s < IL_MAX_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    mbar_init(bar_tfull, 1);
-    mbar_init(bar_tempty, ID_EPI_WARPS);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], ID_EPI_WARPS); }
     fence_barrier_init();
   }
   for (int c = tid; c < a.N; c += ID_THREADS)
@@ -431,7 +434,9 @@ __global__ void __launch_bounds__(ID_THREADS, 1) k_imglinear_dot2(ImgLinearArgs 
       const uint32_t idesc = umma_idesc_f16(nt);
       uint32_t it = 0, ai = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++ai) {
-        mbar_wait(bar_tempty, (ai & 1u) ^ 1u);
+        const uint32_t ab = ai % nbuf, aph = (ai / nbuf) & 1u;
+        const uint32_t td = tmem + ab * 256u;
+        mbar_wait(&bar_tempty[ab], aph ^ 1u);
         tc_fence_after();
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % stages;
@@ -443,12 +448,12 @@ __global__ void __launch_bounds__(ID_THREADS, 1) k_imglinear_dot2(ImgLinearArgs 
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t wd = umma_desc_sw128(sw + kk * 32);
-            umma_f16(tmem, umma_desc_sw128(sa + kk * 32), wd, idesc, (kc | kk) ? 1u : 0u);
-            umma_f16(tmem + 256u, umma_desc_sw128(sa + IL_A_STAGE + kk * 32), wd, idesc, (kc | kk) ? 1u : 0u);
+            umma_f16(td, umma_desc_sw128(sa + kk * 32), wd, idesc, (kc | kk) ? 1u : 0u);
+            umma_f16(td + tile_cols, umma_desc_sw128(sa + IL_A_STAGE + kk * 32), wd, idesc, (kc | kk) ? 1u : 0u);
           }
           umma_commit(&bar_empty[s]);
         }
-        umma_commit(bar_tfull);
+        umma_commit(&bar_tfull[ab]);
       }
     }
   } else {
@@ -458,14 +463,16 @@ __global__ void __launch_bounds__(ID_THREADS, 1) k_imglinear_dot2(ImgLinearArgs 
     const int tile = q >> 1, half = q & 1;
     const int cw = nt / 2;                         // 64, 96 or 128 columns per warp: chunks of 32
     const int row = rq * 32 + lane;
-    const uint32_t tbase = tmem + (uint32_t)tile * 256u + ((uint32_t)rq << 21) + (uint32_t)(half * cw);
+    const uint32_t tbase0 = tmem + (uint32_t)tile * tile_cols + ((uint32_t)rq << 21) + (uint32_t)(half * cw);
     uint32_t ai = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++ai) {
       const int pr = u / ntn, n = u - pr * ntn;
       const int m = 2 * pr + tile;
       const float4* ct = ctab + n * nt + half * cw;
       float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-      mbar_wait(bar_tfull, ai & 1u);
+      const uint32_t ab = ai % nbuf, aph = (ai / nbuf) & 1u;
+      const uint32_t tbase = tbase0 + ab * 256u;
+      mbar_wait(&bar_tfull[ab], aph);
       tc_fence_after();
       for (int c0 = 0; c0 < cw; c0 += 32) {
         float x[32];
@@ -479,7 +486,7 @@ __global__ void __launch_bounds__(ID_THREADS, 1) k_imglinear_dot2(ImgLinearArgs 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cta(bar_tempty);  // the accumulators are drained: the next unit's MMAs may start
+      if (lane == 0) mbar_arrive_cta(&bar_tempty[ab]);  // this accumulator set is drained
       const int gr = m * TILE_ROWS + row;
       if (m < mt && gr < a.M)
         *reinterpret_cast<float4*>(a.dot_out + (size_t)gr * a.ld_dot + 4 * (n * 2 + half)) = make_float4(d0, d1, d2, 0.f);
