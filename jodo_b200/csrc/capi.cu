@@ -341,6 +341,8 @@ int jodo_wide_head_out(const jodo_plan* p, const float* x, int ldx, int hw, cons
   if (!p) return fail("jodo_wide_head_out: null plan");
   if (const char* m = check_plan(*p)) return fail(m);
   if (!x || !w4 || !b4 || !out_dense || hw <= 0 || ch < 1 || ldx < 2 * hw) return fail("jodo_wide_head_out: bad arguments");
+  if (ch > 8 || (hw % 4) || (ldx % 4) || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w4)) & 15))
+    return fail("jodo_wide_head_out: at most 8 outputs; hw, ldx multiples of 4; x and w4 16-byte aligned");
   JODO_LAUNCH(jodo::launch_wide_head_out(*p, x, ldx, hw, w4, b4, ch, both, out_dense, S(stream)), "jodo_wide_head_out");
 }
 
