@@ -285,6 +285,12 @@ int jodo_act_image(const float* rows, int ld, int M, int K, int act, void* img, 
  * temb (noise level [+ context], reference models/mol_gnn.py:534, 728-734): the samplers broadcast one noise level
  * over the batch (sampling.py:549), in which case every per-molecule AdaLN row is the same row. */
 int jodo_uniform_flag(const float* rows, int B, int T, int* nonuni, void* stream);
+/* out[n] = act_in(A[0, :]) . W[n, :] + bias[n] for n < N: ROW 0 of the rowlinear product as a matrix-vector kernel on the same
+ * fp16 weight image (activation rounded to fp16 like the GEMM's operand), executed only while *run_if_zero == 0 (null: always).  The per-molecule AdaLN table under uniform
+ * conditioning (every molecule carries the same noise level and context, as in sampling: reference sampling.py:549), where
+ * all consumers read row 0; the all-rows GEMM (jodo_imglinear with skip_if_zero) covers the other case. */
+int jodo_row0_linear(const float* A, int K, const void* Wimg, int NT, int N, const float* bias, int act_in, float* out,
+                     const int* run_if_zero, void* stream);
 int jodo_com(float* pos4, const jodo_plan* p, void* stream);
 int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, const int* mol_bad,
                   int inn, float* out_dense, void* stream);

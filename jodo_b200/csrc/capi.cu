@@ -131,6 +131,14 @@ int jodo_act_image(const float* rows, int ld, int M, int K, int act, void* img, 
   if (!rows || !img || M <= 0 || K <= 0 || (K % 64) || (ld % 4)) return fail("jodo_act_image: bad arguments");
   JODO_LAUNCH(jodo::launch_act_image(rows, ld, M, K, act, img, S(stream)), "jodo_act_image");
 }
+int jodo_row0_linear(const float* A, int K, const void* Wimg, int NT, int N, const float* bias, int act_in, float* out,
+                     const int* run_if_zero, void* stream) {
+  if (!A || !Wimg || !out || K <= 0 || (K % 64) || K > 8192 || N <= 0 || NT <= 0 || (NT % 8) || (N % NT))
+    return fail("jodo_row0_linear: bad arguments (K a multiple of 64 up to 8192, N a multiple of NT)");
+  if (reinterpret_cast<uintptr_t>(Wimg) & 15) return fail("jodo_row0_linear: the weight image must be 16-byte aligned");
+  if (act_in != JODO_ACT_NONE && act_in != JODO_ACT_SILU) return fail("jodo_row0_linear: act_in must be none or SiLU");
+  JODO_LAUNCH(jodo::launch_row0_linear(A, K, Wimg, NT, N, bias, act_in, out, run_if_zero, S(stream)), "jodo_row0_linear");
+}
 int jodo_uniform_flag(const float* rows, int B, int T, int* nonuni, void* stream) {
   if (!rows || !nonuni || B <= 0 || T <= 0) return fail("jodo_uniform_flag: bad arguments");
   JODO_LAUNCH(jodo::launch_uniform_flag(rows, B, T, nonuni, S(stream)), "jodo_uniform_flag");

@@ -91,6 +91,8 @@ cudaError_t launch_ln_mod_img(const float* x, int ldx, const float* y, int ldy, 
                               void* y_img, const int* nonuni, cudaStream_t st);
 cudaError_t launch_act_image(const float* rows, int ld, int M, int K, int act, void* img, cudaStream_t st);
 cudaError_t launch_uniform_flag(const float* rows, int B, int T, int* nonuni, cudaStream_t st);
+cudaError_t launch_row0_linear(const float* A, int K, const void* Wimg, int nt, int N, const float* bias, int act_in, float* out,
+                               const int* run_if_zero, cudaStream_t st);
 cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st);
 cudaError_t launch_nan_flag(const float* pos, int Nn, const int* mol_bad, int B, int* flag, cudaStream_t st);
 cudaError_t launch_node_out(const float* pos, const float* atom_pred, int ldp, const Plan& p, const int* nan_flag,

@@ -1,5 +1,6 @@
 // Per-atom / per-molecule elementwise kernels around the tensor-core row-linears.
 // All tensors are in the packed (varlen) atom layout of kernels.h::Plan unless noted "dense".
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -199,6 +200,42 @@ __global__ void k_uniform_flag(const float* __restrict__ rows, int B, int T, int
   if (__float_as_uint(rows[i]) != __float_as_uint(rows[c])) *nonuni = 1;
 }
 
+// Row 0 of  C = act_in(A) W^T + bias  as a matrix-vector product, run only while *run_if_zero == 0 (uniform conditioning:
+// every molecule's AdaLN row equals row 0, which is all the consumers read).  W is the fp16 operand image of the GEMM
+// kernels, [N / nt][K / 64][nt rows][128 B] with the 16-byte pieces of a row XOR-swizzled by (row & 7); one warp per output
+// column, a lane takes one piece (8 weights) of four consecutive K chunks per step, x = act_in(A[0]) staged in shared memory.
+// Replaces a 128-row tensor-core tile per 128 columns whose K loop is a latency chain (0.07 - 0.1 ms for the [1024 x 19712] table).
+__global__ void __launch_bounds__(256) k_row0_linear(const float* __restrict__ A, int K, const uint8_t* __restrict__ Wimg, int nt, int N,
+                                                     const float* __restrict__ bias, int act_in, float* __restrict__ out,
+                                                     const int* __restrict__ run_if_zero) {
+  if (run_if_zero && *run_if_zero != 0) return;
+  extern __shared__ float xs[];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float v = A[k];
+    // rounded to fp16 exactly as the GEMM path stores its activation operand: the two paths then differ by accumulation order only
+    xs[k] = __half2float(__float2half_rn(fminf(fmaxf(act_in == ACT_SILU ? v / (1.0f + __expf(-v)) : v, -65504.f), 65504.f)));
+  }
+  __syncthreads();
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const int tile = n / nt, r = n - tile * nt, nkc = K >> 6;
+  const uint8_t* wrow = Wimg + ((size_t)tile * nkc * nt + r) * 128;
+  const int piece = lane & 7;
+  float acc = 0.f;
+  for (int kc = lane >> 3; kc < nkc; kc += 4) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(wrow + (size_t)kc * nt * 128 + ((piece ^ (r & 7)) << 4)));
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+    const float* x = xs + 64 * kc + 8 * piece;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 w = __half22float2(h[i]);
+      acc = fmaf(w.x, x[2 * i], fmaf(w.y, x[2 * i + 1], acc));
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[n] = acc + (bias ? bias[n] : 0.f);
+}
+
 // Per-molecule centre-of-mass removal of the block's coordinate update, in place on pos_new
 // (remove_mean_with_mask, reference models/utils.py:38-45; call site models/mol_gnn.py:565-566).
 // A single-atom molecule has no edges, so no kernel wrote pos_new for it: x - mean(x) = 0.
@@ -322,6 +359,11 @@ cudaError_t launch_uniform_flag(const float* rows, int B, int T, int* nonuni, cu
   if (e != cudaSuccess) return e;
   const long long total = (long long)B * T;
   k_uniform_flag<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rows, B, T, nonuni);
+  return LAUNCH_OK();
+}
+cudaError_t launch_row0_linear(const float* A, int K, const void* Wimg, int nt, int N, const float* bias, int act_in, float* out,
+                               const int* run_if_zero, cudaStream_t st) {
+  k_row0_linear<<<(N + 7) / 8, 256, K * sizeof(float), st>>>(A, K, static_cast<const uint8_t*>(Wimg), nt, N, bias, act_in, out, run_if_zero);
   return LAUNCH_OK();
 }
 cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st) {

@@ -290,14 +290,14 @@ class _DGTBase(nn.Module):
         # flags[2] = 1 unless every molecule carries the same conditioning row (the samplers broadcast one noise level)
         _lib.call('jodo_uniform_flag', _lib.ptr(ws.temb), _c(B), _c(T), ctypes.c_void_p(ws.flags.data_ptr() + 8), st)
         nonuni = ws.flags.data_ptr() + 8
-        # all AdaLN rows: the first 128 molecules always (register-staged GEMM: row 0 serves the uniform fast path),
-        # every molecule through the persistent GEMM only when the conditioning is not uniform (device-side skip)
-        lin('tab', ws.temb, ws.tab, M=min(B, 128), act_in=_lib.ACT_SILU)
-        if B > 128:
-            _lib.call('jodo_act_image', _lib.ptr(ws.temb), _c(T), _c(B), _c(T), _c(_lib.ACT_SILU), _lib.ptr(ws.temb_img), st)
-            m = meta['tab']
-            _lib.imglinear(ws.temb_img, B, m['K'], pk['tab.img'], pk['tab.b'], m['N'], m['NT'], C32=ws.tab, stream=st,
-                           tag='jodo_imglinear:tab', skip_if_zero=nonuni)
+        # all AdaLN rows.  Uniform conditioning: row 0 as a matrix-vector product (every consumer reads row 0); otherwise every
+        # molecule's row through the persistent GEMM.  Each tests the device flag, one of them returns at once.
+        m = meta['tab']
+        _lib.call('jodo_row0_linear', _lib.ptr(ws.temb), _c(T), ctypes.c_void_p(pk.ptr('tab.img')), _c(m['NT']), _c(m['N']),
+                  _lib.ptr(pk['tab.b']), _c(_lib.ACT_SILU), _lib.ptr(ws.tab), ctypes.c_void_p(nonuni), st)
+        _lib.call('jodo_act_image', _lib.ptr(ws.temb), _c(T), _c(B), _c(T), _c(_lib.ACT_SILU), _lib.ptr(ws.temb_img), st)
+        _lib.imglinear(ws.temb_img, B, m['K'], pk['tab.img'], pk['tab.b'], m['N'], m['NT'], C32=ws.tab, stream=st,
+                       tag='jodo_imglinear:tab', skip_if_zero=nonuni)
         if _pack.EQUI_LIN:   # uniform conditioning: coord_mlp.0 composed into input_lin for every block from the step's table row
             _lib.call('jodo_equi_compose', ctypes.c_void_p(self._compose_items(pk).data_ptr()), _c(d.L), _lib.ptr(ws.tab),
                       ctypes.c_void_p(nonuni), st)

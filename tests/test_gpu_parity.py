@@ -45,7 +45,7 @@ def test_forward_matches_reference(name):
 
 def test_uniform_conditioning_fast_path_matches_general_path():
     """All molecules at one noise level (what the samplers feed, sampling.py:549) take the device-detected fast path
-    (row 0 of the AdaLN table through constant memory, table GEMM on one row tile); perturbing one molecule's noise
+    (row 0 of the AdaLN table through constant memory, the table as one matrix-vector product); perturbing one molecule's noise
     level forces the general per-molecule path; the other molecules must come out the same on both paths."""
     from helpers import golden_weights
     from jodo_b200.model import MODELS
@@ -64,11 +64,13 @@ def test_uniform_conditioning_fast_path_matches_general_path():
     flags_gen = int(next(iter(model._plans.values()))[1].flags[2])
     assert flags_uni == 0 and flags_gen == 1
     B = xa.shape[0]
-    # Molecules 0..B-2 see identical conditioning rows on both paths, and the kernels do the same arithmetic on them --
-    # except with JODO_EQUI_LIN=1, where the uniform path composes coord_mlp.0 into input_lin (csrc/equi_lin.cu) and
-    # the two agree to the fp16 operand rounding only.  Either way each path agrees with the fp64 oracle.
+    # Molecules 0..B-2 see the same conditioning on both paths.  Their AdaLN rows come from two kernels -- row 0 as a matrix-vector
+    # product on the uniform path (jodo_row0_linear), every row through the tensor-core GEMM on the general one: same fp16-rounded
+    # operands, different fp32 summation order -- so the rows agree to ~1e-6 and the outputs to the occasional flipped fp16
+    # operand rounding downstream (measured 5e-5 of max |x|); with JODO_EQUI_LIN=1 the uniform path also composes coord_mlp.0
+    # into input_lin (csrc/equi_lin.cu).  Either way each path agrees with the fp64 oracle.
     from jodo_b200 import pack as _pack
-    tol_ab = 1e-3 if _pack.EQUI_LIN else 1e-5
+    tol_ab = 1e-3 if _pack.EQUI_LIN else 5e-4
     assert float((xa[:B - 1] - xb[:B - 1]).abs().max()) < tol_ab * float(xa.abs().max())
     assert float((ea[:B - 1] - eb[:B - 1]).abs().max()) < tol_ab * float(ea.abs().max())
     from helpers import oracle_forward

@@ -62,3 +62,34 @@ def test_rowlinear_rejects_bad_args():
     A = torch.zeros(8, 40, device='cuda')
     with pytest.raises(_lib.JodoError):
         _lib.rowlinear(A, 40, A, None, A, 16, 16)
+
+
+@pytest.mark.parametrize('K,N,NT,act', [(1024, 19712, 128, 'silu'), (64, 256, 256, None), (256, 768, 192, 'silu')])
+def test_row0_linear_matches_fp64_and_obeys_the_flag(K, N, NT, act):
+    """jodo_row0_linear: row 0 of the rowlinear product on the same weight image (fp16-rounded operands, fp32 accumulation), run only
+    while the device flag reads 0."""
+    import ctypes
+    g = torch.Generator(device='cuda').manual_seed(K + N)
+    A = torch.randn(5, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) / K ** 0.5
+    b = torch.randn(N, device='cuda', generator=g)
+    Wi = weight_image_h(W, NT)
+    out = torch.full((3, N), 7.0, device='cuda')
+    flag = torch.zeros(1, device='cuda', dtype=torch.int32)
+    c = ctypes.c_int
+
+    def run():
+        _lib.call('jodo_row0_linear', _lib.ptr(A), c(K), _lib.ptr(Wi), c(NT), c(N), _lib.ptr(b), c(_lib.ACT_SILU if act else 0),
+                  _lib.ptr(out), _lib.ptr(flag), _lib.stream_ptr())
+        torch.cuda.synchronize()
+    run()
+    x = A[0].double()
+    if act:
+        x = torch.nn.functional.silu(x)
+    ref = W.half().double() @ x.float().half().double() + b.double()                  # both operands fp16-rounded, as in the GEMM
+    assert float((out[0].double() - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+    assert bool((out[1:] == 7.0).all())
+    out.fill_(7.0)
+    flag.fill_(1)                                             # conditioning not uniform: the all-rows GEMM owns the table
+    run()
+    assert bool((out == 7.0).all())
