@@ -13,7 +13,7 @@ def mm(i, o):
 PAIR_KERNELS = frozenset({
     'jodo_edge_embed', 'jodo_edge_update', 'jodo_edge_head',
     'jodo_imglinear:emb', 'jodo_imglinear:g01', 'jodo_imglinear:ff3', 'jodo_imglinear:ff4', 'jodo_imglinear:equi_in',
-    'jodo_wide_ln:e2', 'jodo_wide_ln:e1', 'jodo_wide_dist', 'jodo_wide_put'})
+    'jodo_wide_ln:e2', 'jodo_wide_ln:e1', 'jodo_wide_dist', 'jodo_wide_put', 'jodo_wide_edge_ffn'})
 
 
 def per_edge_kernel_flops(d):
@@ -52,6 +52,7 @@ def wide_kernel_flops(d):
         'jodo_imglinear:equi_in': mm(2 * ed, D),
         'jodo_imglinear:c0': mm(D, D),
         'jodo_imglinear:c2': mm(D, 1 + X),
+        'jodo_wide_edge_ffn': mm(ed, r * ed) + mm(r * ed, ed),
     }
 
 
@@ -66,6 +67,7 @@ def wide_kernel_bytes(d):
         'jodo_wide_attn': 2 * (qk + D) + 1,                 # tanh(lin_edge0 | lin_edge1) rows + adjacency bits
         'jodo_wide_dist': 2 * 2 * ed,
         'jodo_wide_put': 4 * ed + 3 * 2 * ed,
+        'jodo_wide_edge_ffn': 4 * ed + 4 * ed + 2 * 2 * ed,  # fp32 edge state in and out, two fp16 copies of the new state
     }
 
 
