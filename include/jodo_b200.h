@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 14
+#define JODO_ABI_VERSION 15
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -370,6 +370,8 @@ typedef struct jodo_wide_ln_args {                      /* LayerNorm(eps 1e-6) +
   float* out32; int ldo;                  /* optional modulated fp32 rows (columns [W, min(Kimg, ldo)) are zeroed) */
   void* out_img; void* y_img;             /* fp16 images of the result / of y (either may be null) */
   int x_f16, y_f16;                       /* != 0: x / (y and y2) are fp16 rows (strides in elements, % 8 == 0) */
+  const int* nonuni;                      /* device flag of jodo_uniform_flag or null: 0 = every row reads table row 0 (uniform
+                                             conditioning: the rows are L1-resident and no longer depend on the row_mol load) */
 } jodo_wide_ln_args;
 
 typedef struct jodo_wide_attn_args {                    /* TransMixLayer message + aggregation (reference models/layers.py:157-186) */
@@ -409,6 +411,7 @@ typedef struct jodo_wide_ffn_args {      /* edge FFN of one block on pair rows, 
   const void* w4_img; const float* b4;    /* ff_linear4: fp16 image [H / 64][ed][128 B], bias [ed] */
   void* img1; int k1, col1;               /* fp16 copies of the new state: columns [col, col + ed) of operand images with k columns (may be null) */
   void* img2; int k2, col2;
+  const int* nonuni;                      /* device flag of jodo_uniform_flag or null: 0 = every row reads table row 0 */
 } jodo_wide_ffn_args;
 int jodo_wide_edge_ffn(const jodo_wide_ffn_args* a, void* stream);
 int jodo_wide_embed_in(const jodo_wide_embed_args* a, void* stream);

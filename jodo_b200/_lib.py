@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 14:
+        if _lib.jodo_abi_version() != 15:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -166,7 +166,7 @@ class WideLnArgs(ctypes.Structure):
     _fields_ = [('M', _I), ('W', _I), ('Kimg', _I), ('x', _P), ('ldx', _I), ('xi', _P), ('y', _P), ('ldy', _I), ('yi', _P),
                 ('y2', _P), ('ldy2', _I), ('y2i', _P), ('ybias', _P), ('tab', _P), ('ld_tab', _I), ('row_mol', _P),
                 ('off_gate', _I), ('off_shift', _I), ('off_scale', _I), ('valid', _P), ('out32', _P), ('ldo', _I),
-                ('out_img', _P), ('y_img', _P), ('x_f16', _I), ('y_f16', _I)]
+                ('out_img', _P), ('y_img', _P), ('x_f16', _I), ('y_f16', _I), ('nonuni', _P)]
 
 
 class WideEquiArgs(ctypes.Structure):
@@ -179,7 +179,7 @@ class WideFfnArgs(ctypes.Structure):
     _fields_ = [('M', _I), ('ed', _I), ('H', _I), ('e32', _P), ('lde', _I), ('P', _P), ('ldp', _I), ('pair_i', _P), ('pair_j', _P),
                 ('pair_mol', _P), ('n2e_bias', _P), ('tab', _P), ('ld_tab', _I), ('off_gate', _I), ('off_shift', _I),
                 ('off_scale', _I), ('off_gate2', _I), ('w3_img', _P), ('b3', _P), ('w4_img', _P), ('b4', _P), ('img1', _P),
-                ('k1', _I), ('col1', _I), ('img2', _P), ('k2', _I), ('col2', _I)]
+                ('k1', _I), ('col1', _I), ('img2', _P), ('k2', _I), ('col2', _I), ('nonuni', _P)]
 
 
 class WideAttnArgs(ctypes.Structure):

@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(256, (V >= 1 && LANES == 16) ? 6 : 1) k_wide_l
   // every per-row index is loaded up front (independent loads: one round trip instead of a dependent chain)
   const bool inb = row < a.M;
   const int vld = (inb && a.valid) ? __ldg(a.valid + row) : 0;
-  const int mol = inb ? __ldg(a.row_mol + row) : 0;
+  const bool uni = a.nonuni != nullptr && *a.nonuni == 0;     // uniform conditioning: every molecule's table row is row 0
+  const int mol = (inb && !uni) ? __ldg(a.row_mol + row) : 0;
   const int iy = (inb && has_y) ? (a.yi ? __ldg(a.yi + row) : row) : 0;
   const int iy2 = (inb && has_y2) ? (a.y2i ? __ldg(a.y2i + row) : row) : 0;
   const int ix = (inb && a.xi) ? max(__ldg(a.xi + row), 0) : row;        // padding rows carry -1

@@ -229,7 +229,7 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
                             dp(y2), 0 if y2 is None else y2.stride(0), dp(y2i), dp(ybias), dp(ws.tab), ld_tab, dp(row_mol),
                             gate, shift, scale, dp(valid), dp(out32), 0 if out32 is None else out32.stride(0),
                             dp(out_img), dp(y_img), int(x.dtype == torch.float16),
-                            int(y is not None and y.dtype == torch.float16))
+                            int(y is not None and y.dtype == torch.float16), nonuni)
         _lib.call('jodo_wide_ln', ctypes.byref(a), st, tag='jodo_wide_ln:' + tag)
 
     # ---- per molecule: noise-level embedding (+ context) and all AdaLN tables
@@ -243,6 +243,10 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
         lin('time3', ws.t1, ws.temb, epi=_lib.EPI_ADD, aux=ws.ctx)
     else:
         lin('time3', ws.t1, ws.temb)
+    # flags[2] = 1 unless every molecule carries the same conditioning row (the samplers broadcast one noise level): the row
+    # kernels then read table row 0 for every row (L1-resident, and the loads no longer wait for the row's molecule index)
+    nonuni = ws.flags.data_ptr() + 8
+    _lib.call('jodo_uniform_flag', P(ws.temb), _c(B), _c(T), ctypes.c_void_p(nonuni), st)
     _lib.call('jodo_act_image', P(ws.temb), _c(T), _c(B), _c(T), _c(_lib.ACT_SILU), P(ws.temb_img), st)
     ilin('tab', ws.temb_img, B, C32=ws.tab)
     # ---- per atom
@@ -299,7 +303,7 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
         ilin(p + 'n2e', ws.hnode_img, Nn, bias=False, C32=ws.P)
         ilin(p + 'ff1', ws.h2_img, Nn, epi=_lib.EPI_ACT, act_out=_lib.ACT_SILU, Cimg=ws.ff_img)
         ilin(p + 'ff2', ws.ff_img, Nn, epi=_lib.EPI_GATED_RES, aux=ws.h2, gate=ws.tab[:, o + 5 * D:], row_mol=plan.node_mol,
-             C32=hout, Cimg=ws.hout_img)
+             C32=hout, Cimg=ws.hout_img, nonuni=nonuni)
         if not d.two_d:
             ilin(p + 'ab', ws.hout_img, Nn, C16=ws.AB)
         ilin(p + 'node_l', ws.hout_img, Nn, C32=ws.ah[:, D + l * meta['cnp']:])
@@ -312,7 +316,7 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
             fa = _lib.WideFfnArgs(RP, ed, d.r * ed, dp(ws.e32), ws.e32.stride(0), dp(ws.P), ws.P.stride(0), dp(plan.pair_i),
                                   dp(plan.pair_j), dp(plan.pair_mol), pk.ptr(p + 'n2e.bias'), dp(ws.tab), ld_tab, oe + 2 * ed,
                                   oe + 3 * ed, oe + 4 * ed, oe + 5 * ed, pk.ptr(p + 'ff3f.img'), pk.ptr(p + 'ff3f.b'),
-                                  pk.ptr(p + 'ff4f.img'), pk.ptr(p + 'ff4f.b'), dp(i1), k1, c1, dp(i2), k2, c2)
+                                  pk.ptr(p + 'ff4f.img'), pk.ptr(p + 'ff4f.b'), dp(i1), k1, c1, dp(i2), k2, c2, nonuni)
             _lib.call('jodo_wide_edge_ffn', ctypes.byref(fa), st)
         else:
             ln(RP, ed, EDP, ws.e32, (oe + 3 * ed, oe + 4 * ed), plan.pair_mol, out_img=ws.e2_img, out32=ws.e2, y=ws.P,
@@ -322,7 +326,7 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
             if len(imgs) > 1:
                 kw.update(Cimg2=imgs[1][0], cimg2_place=(imgs[1][1], imgs[1][2], ed))
             ilin(p + 'ff4', ws.f3_img, RP, epi=_lib.EPI_GATED_RES, aux=ws.e2, gate=ws.tab[:, oe + 5 * ed:], row_mol=plan.pair_mol,
-                 C32=ws.e32, **kw)
+                 C32=ws.e32, nonuni=nonuni, **kw)
         if d.two_d:
             if dbg is not None:
                 dbg.setdefault('blocks', []).append(dict(hnode=ws.hnode.clone(), h=hout.clone(), e=ws.e32.clone()))

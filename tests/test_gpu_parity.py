@@ -43,13 +43,14 @@ def test_forward_matches_reference(name):
         assert float(x[..., :3].sum(1).abs().max()) < 1e-4
 
 
-def test_uniform_conditioning_fast_path_matches_general_path():
+@pytest.mark.parametrize('name', ['qm9_selfcond', 'geom_large'])
+def test_uniform_conditioning_fast_path_matches_general_path(name):
     """All molecules at one noise level (what the samplers feed, sampling.py:549) take the device-detected fast path
     (row 0 of the AdaLN table through constant memory, the table as one matrix-vector product); perturbing one molecule's noise
     level forces the general per-molecule path; the other molecules must come out the same on both paths."""
     from helpers import golden_weights
     from jodo_b200.model import MODELS
-    g, cfg = load_golden('qm9_selfcond')
+    g, cfg = load_golden(name)            # geom_large: the wide path, whose row kernels read table row 0 under the same flag
     model = MODELS[cfg.model.name](cfg)
     model.load_state_dict(golden_weights(g, cfg), strict=True)
     model = model.cuda().eval()
