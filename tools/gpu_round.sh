@@ -20,7 +20,7 @@ for k in k_attn k_equi k_edge_update; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 12 -c 1 -f -o $OUT/prof_$k \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > $OUT/prof_$k.log 2>&1; echo "ncu $k rc=$?"
 done
-for k in k_wide_ln k_wide_attn_mol; do
+for k in k_wide_ln k_wide_attn_mol k_imglinear_dot2 k_wide_ffn_stream; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -f -o $OUT/prof_$k \
       python bench.py --workload geom_large --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > $OUT/prof_$k.log 2>&1; echo "ncu $k rc=$?"
 done
