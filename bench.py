@@ -12,7 +12,9 @@ in the loop, one NCCL all_gather of the final samples after the timed region.
 
 One JSON line on stdout (rank 0).  `value` = whole-job throughput with state resident in HBM;
 `e2e` = same step driven through the public API with HOST (pinned) buffers, H2D of the step's inputs
-and D2H of its results inside the timed region; `roofline` = the dominant kernel against the measured
+and D2H of its results inside the timed region -- through sampler.HostPipelinedSteps (two half-batches of
+independent molecules, the copies of one half under the kernels of the other; `e2e.in_line_value` = one
+batch with the copies in line); `roofline` = the dominant kernel against the measured
 peak; `cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
 --impl reference times the reference's own CPU implementation on rank 0 only: the unmodified reference
 modules from oracle/_ref/reference (staged by build(), git-ignored, travels with gpurun) -- kind "reference";
@@ -57,6 +59,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch override (debug)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-pipeline', action='store_true', help='e2e with the host copies in line (one batch) instead of sampler.HostPipelinedSteps')
     ap.add_argument('--noise', default='torch', choices=['torch', 'philox'],
                     help="ancestral noise: the reference's torch.randn stream (default) or Philox drawn inside the update kernels")
     ap.add_argument('--no-extras', action='store_true', help='skip the strong-scaling point (N > 1) and the other workloads (N = 1)')
@@ -472,7 +475,44 @@ def run_b200(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         evals = 2 if dpm else 1                         # model evaluations per e2e_step
         e2e = {'value': w.total * ke * evals / float(dt), 'unit': UNIT, 'h2d_bytes_per_step': h2d // evals,
-               'd2h_bytes_per_step': d2h // evals, 'steps': ke * evals}
+               'd2h_bytes_per_step': d2h // evals, 'steps': ke * evals, 'copies': 'in line'}
+        # The same state and the same bytes through the public pipelined API (sampler.HostPipelinedSteps): the batch as two
+        # halves of independent molecules, each with its own captured step and pinned host state; the copies of one half
+        # run under the kernels of the other.  Every step still moves every input host -> device and every result back.
+        if graphed is not None and not dpm and not args.no_pipeline and batch >= 2:
+            S = w.S
+            N_, ch_ = node_mask.shape[1], state['ex'].shape[-1]
+            em3 = edge_mask.reshape(batch, N_, N_)
+            steps_p, hosts_p = [], []
+            for idx in S.split_for_pipeline(w.n_nodes, 2):
+                idx = idx.to(dev)
+                nm = node_mask[idx].contiguous()
+                em = em3[idx].reshape(-1, 1).contiguous()
+                sp = {k: state[k][idx].contiguous() for k in ('x', 'ex', 'cx', 'cex')}
+                # the model runs the self-conditioned path once on these masks (plan, workspaces) before the capture
+                w.smp.step(model, W + K - 1, sp['x'], sp['ex'], nm, em, sp['cx'], sp['cex'])
+                steps_p.append(S.GraphedAncestralStep(w.smp, model, sp['x'], sp['ex'], sp['cx'], sp['cex'], nm, em))
+                hosts_p.append({k: pin(v) for k, v in sp.items()})
+            pipe = S.HostPipelinedSteps(steps_p, hosts_p)
+            for i in range(2):
+                pipe.run(W + K - 1)
+            pipe.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(ke):
+                pipe.run(W + K - 1)
+            pipe.synchronize()
+            torch.cuda.synchronize()
+            dtp = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.barrier()
+                dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+            ok = ok and all(bool(torch.isfinite(h[k]).all()) for h in hosts_p for k in h)
+            e2e.update(in_line_value=e2e['value'], value=w.total * ke / float(dtp), h2d_bytes_per_step=pipe.bytes_per_step,
+                       d2h_bytes_per_step=pipe.bytes_per_step,
+                       copies='pipelined: two half-batches, the H2D / D2H of one half under the kernels of the other '
+                              '(sampler.HostPipelinedSteps); in_line_value = one batch with the copies in line')
+            del pipe, steps_p, hosts_p
 
     # ---- per-kernel device times (CUDA events around every C-ABI call, outside the timed region) -------
     _lib.TRACE = []

@@ -268,6 +268,71 @@ class GraphedAncestralStep:
         self.graph.replay()
 
 
+class HostPipelinedSteps:
+    """Reverse steps of a batch whose state lives in pinned HOST buffers, with the host <-> device copies hidden behind the
+    compute.  The caller hands over the batch as several PARTS of independent molecules (``split_for_pipeline``: two halves
+    with balanced cost), each with its own graph-captured step (``GraphedAncestralStep`` on the part's masks) and its own
+    pinned host tensors ``{'x', 'ex', 'cx', 'cex'}``.  ``run(i)`` advances every part by reverse step ``i``: for each part
+    host -> device copy of its inputs, graph replay, device -> host copy of its results, on three streams ordered by
+    events --
+
+        h2d stream      in(A,i)   in(B,i)              in(A,i+1)   in(B,i+1)
+        compute stream       [ step A,i ][ step B,i ][ step A,i+1 ][ step B,i+1 ]
+        d2h stream                      out(A,i)     out(B,i)       out(A,i+1)
+
+    -- so the copies of one part run under the kernels of the other and the compute stream never waits for PCIe (a step of
+    the whole batch with the copies in line costs compute + 2 x 39 MB / 55 GB/s at QM9 B = 2500).  Nothing is reordered
+    inside a part: its step i + 1 reads the host buffers its step i wrote (the device-side dependency in(p,i+1) after
+    out(p,i) is an event, not a host sync).  ``synchronize()`` makes every result visible to the host.  Results are
+    bit-identical to replaying the same parts one after the other with the copies in line (tests/test_sampler.py)."""
+
+    NAMES = (('x', 'x'), ('ex', 'edge_x'), ('cx', 'cond_x'), ('cex', 'cond_edge_x'))
+
+    def __init__(self, steps, hosts):
+        if len(steps) != len(hosts) or not steps:
+            raise ValueError('one host state per captured step')
+        for h in hosts:
+            for k, _ in self.NAMES:
+                if not h[k].is_pinned():
+                    raise ValueError('host buffers must be pinned (the copies are asynchronous)')
+        self.steps, self.hosts = list(steps), list(hosts)
+        self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        mk = lambda: [torch.cuda.Event() for _ in steps]
+        self.ev_in, self.ev_done, self.ev_out = mk(), mk(), mk()
+        self._started = False
+        self.bytes_per_step = sum(h[k].numel() * h[k].element_size() for h in hosts for k, _ in self.NAMES)
+
+    def run(self, i):
+        cur = torch.cuda.current_stream()
+        if not self._started:
+            self.h2d.wait_stream(cur)                    # whatever produced the device state so far is complete
+        for p, (gs, host) in enumerate(zip(self.steps, self.hosts)):
+            with torch.cuda.stream(self.h2d):
+                if self._started:
+                    self.h2d.wait_event(self.ev_out[p])  # the part's previous results have left its device buffers
+                for k, attr in self.NAMES:
+                    getattr(gs, attr).copy_(host[k], non_blocking=True)
+                self.ev_in[p].record(self.h2d)
+            cur.wait_event(self.ev_in[p])
+            gs.run(i)
+            self.ev_done[p].record(cur)
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(self.ev_done[p])
+                for k, attr in self.NAMES:
+                    host[k].copy_(getattr(gs, attr), non_blocking=True)
+                self.ev_out[p].record(self.d2h)
+        self._started = True
+
+    def synchronize(self):
+        for e in self.ev_out:
+            e.synchronize()
+
+
+def split_for_pipeline(n_nodes, parts=2):
+    """Index tensors of `parts` sub-batches with balanced cost (the dealing of shard_molecules)."""
+    return [shard_molecules(n_nodes, parts, r) for r in range(parts)]
+
+
 class AncestralSampler2D(AncestralSampler):
     """Ancestral sampling without 3-D positions (reference sampling.py:599-661, AncestralSampler_2D): the same
     posterior-mean update with masked Gaussian node noise (sample_gaussian_with_mask, models/utils.py:77-80: no CoM

@@ -359,3 +359,63 @@ def test_graph_captured_dpm_chain_equals_eager_chain():
     print(f'dpm chain: eager {dt[0] * 1e3:.1f} ms, graphed {dt[1] * 1e3:.1f} ms for 20 evaluations of 48 molecules')
     assert torch.isfinite(res[0][0]).all()
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+@pytest.mark.gpu
+def test_host_pipelined_steps_equal_in_line_copies():
+    """sampler.HostPipelinedSteps (state in pinned host buffers, two half-batches, the copies of one half under the kernels of
+    the other) against the same two captured steps replayed one after the other with the copies in line: the same replays in
+    the same order (same torch.randn stream), so the host state agrees bit for bit after several steps; and the halves are
+    the dealing of shard_molecules."""
+    from jodo_b200 import configs, synth
+    from jodo_b200.model import MODELS
+    cfg = configs.NAMED['qm9_uncond']()
+    model = MODELS[cfg.model.name](cfg).cuda().eval()
+    B = 40
+    b = synth.make_batch(cfg, B, seed=33)
+    d = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+    N = d['node_mask'].shape[1]
+    grid = torch.linspace(0.9946, 1e-3, 1000)[::100]
+    parts = S.split_for_pipeline(b['n_nodes'], 2)
+    assert sorted(torch.cat(parts).tolist()) == list(range(B)) and abs(len(parts[0]) - len(parts[1])) <= 1
+    pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+
+    def build():
+        torch.manual_seed(77)
+        smp = S.AncestralSampler(S.CosineVP(), grid)
+        steps, hosts = [], []
+        for idx in parts:
+            idx = idx.cuda()
+            nm = d['node_mask'][idx].contiguous()
+            em = d['edge_mask'].reshape(B, N, N)[idx].reshape(-1, 1).contiguous()
+            x, ex = d['xh'][idx].contiguous(), d['edge_x'][idx].contiguous()
+            cx = cex = None
+            for i in range(2):                                 # first call, then the self-conditioned path (plan, workspaces)
+                x, ex, _, _, cx, cex = smp.step(model, i, x, ex, nm, em, cx, cex)
+            steps.append(S.GraphedAncestralStep(smp, model, x, ex, cx, cex, nm, em))
+            hosts.append(dict(x=pin(x), ex=pin(ex), cx=pin(cx), cex=pin(cex)))
+        return steps, hosts
+
+    # in line: copy in, replay, copy out, part after part
+    steps, hosts = build()
+    for i in range(2, 6):
+        for gs, h in zip(steps, hosts):
+            for k, attr in S.HostPipelinedSteps.NAMES:
+                getattr(gs, attr).copy_(h[k], non_blocking=True)
+            gs.run(i)
+            for k, attr in S.HostPipelinedSteps.NAMES:
+                h[k].copy_(getattr(gs, attr), non_blocking=True)
+            torch.cuda.synchronize()
+    want = [{k: v.clone() for k, v in h.items()} for h in hosts]
+    # pipelined
+    steps, hosts = build()
+    pipe = S.HostPipelinedSteps(steps, hosts)
+    for i in range(2, 6):
+        pipe.run(i)
+    pipe.synchronize()
+    for h, w_ in zip(hosts, want):
+        for k in h:
+            assert torch.isfinite(h[k]).all()
+            assert torch.equal(h[k], w_[k]), k
+    with pytest.raises(ValueError):
+        S.HostPipelinedSteps(steps, [{k: v.clone() for k, v in h.items()} for h in hosts])      # unpinned host buffers
