@@ -479,7 +479,7 @@ def run_b200(args):
         # The same state and the same bytes through the public pipelined API (sampler.HostPipelinedSteps): the batch as two
         # halves of independent molecules, each with its own captured step and pinned host state; the copies of one half
         # run under the kernels of the other.  Every step still moves every input host -> device and every result back.
-        if graphed is not None and not dpm and not args.no_pipeline and batch >= 2:
+        if graphed is not None and not args.no_pipeline and batch >= 2:
             S = w.S
             N_, ch_ = node_mask.shape[1], state['ex'].shape[-1]
             em3 = edge_mask.reshape(batch, N_, N_)
@@ -490,17 +490,25 @@ def run_b200(args):
                 em = em3[idx].reshape(-1, 1).contiguous()
                 sp = {k: state[k][idx].contiguous() for k in ('x', 'ex', 'cx', 'cex')}
                 # the model runs the self-conditioned path once on these masks (plan, workspaces) before the capture
-                w.smp.step(model, W + K - 1, sp['x'], sp['ex'], nm, em, sp['cx'], sp['cex'])
-                steps_p.append(S.GraphedAncestralStep(w.smp, model, sp['x'], sp['ex'], sp['cx'], sp['cex'], nm, em))
+                if dpm:
+                    sol_p = S.DPMSolverSinglestep(S.CosineVP(), 50, order=2)
+                    ctx_p = w.context[idx].contiguous()
+                    sol_p.cond_x, sol_p.cond_edge_x = sp['cx'], sp['cex']
+                    sol_p.outer_step(model, 1, w.ogrid, sp['x'], nm, em, sp['ex'], ctx_p)
+                    steps_p.append(S.GraphedDPMStep(sol_p, model, sp['x'], sp['ex'], nm, em, ctx_p, w.ogrid))
+                else:
+                    w.smp.step(model, W + K - 1, sp['x'], sp['ex'], nm, em, sp['cx'], sp['cex'])
+                    steps_p.append(S.GraphedAncestralStep(w.smp, model, sp['x'], sp['ex'], sp['cx'], sp['cex'], nm, em))
                 hosts_p.append({k: pin(v) for k, v in sp.items()})
             pipe = S.HostPipelinedSteps(steps_p, hosts_p)
+            si = min((W + K - 1) // 2, 23) if dpm else W + K - 1          # DPM: an outer step of two evaluations
             for i in range(2):
-                pipe.run(W + K - 1)
+                pipe.run(si)
             pipe.synchronize()
             barrier()
             t0 = time.perf_counter()
             for i in range(ke):
-                pipe.run(W + K - 1)
+                pipe.run(si)
             pipe.synchronize()
             torch.cuda.synchronize()
             dtp = torch.tensor([time.perf_counter() - t0], device=dev)
@@ -508,8 +516,8 @@ def run_b200(args):
                 dist.barrier()
                 dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
             ok = ok and all(bool(torch.isfinite(h[k]).all()) for h in hosts_p for k in h)
-            e2e.update(in_line_value=e2e['value'], value=w.total * ke / float(dtp), h2d_bytes_per_step=pipe.bytes_per_step,
-                       d2h_bytes_per_step=pipe.bytes_per_step,
+            e2e.update(in_line_value=e2e['value'], value=w.total * ke * evals / float(dtp), h2d_bytes_per_step=pipe.bytes_per_step // evals,
+                       d2h_bytes_per_step=pipe.bytes_per_step // evals,
                        copies='pipelined: two half-batches, the H2D / D2H of one half under the kernels of the other '
                               '(sampler.HostPipelinedSteps); in_line_value = one batch with the copies in line')
             del pipe, steps_p, hosts_p
