@@ -1,8 +1,11 @@
-OUT=gpurun_out/r02l; mkdir -p $OUT
-timeout 600 python bench.py --workload qm9_cond --steps 20 --warmup 4 --no-extras > $OUT/bench_qm9_cond.json 2> $OUT/bench_qm9_cond.err; echo "bench qm9_cond rc=$?"; tail -3 $OUT/bench_qm9_cond.err
-python - <<PY
+OUT=gpurun_out/s3r; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_sampler.py tests/test_gpu_parity.py tests/test_gpu_imglinear.py tests/test_gpu_rowlinear.py -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $OUT/pytest.log
+for v in pdl nopdl; do
+  if [ $v = nopdl ]; then export JODO_NO_PDL=1; fi
+  timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > $OUT/bench_qm9_$v.json 2> $OUT/bench_qm9_$v.err; echo "bench $v rc=$?"; tail -2 $OUT/bench_qm9_$v.err
+  python - <<PY
 import json
-for w in ('qm9_cond',):
-    d=json.load(open('$OUT/bench_%s.json' % w))
-    print(w, 'ms/step', round(d['ms_per_step'],3), 'value', round(d['value']), 'e2e', round(d['e2e']['value']), 'in line', d['e2e'].get('in_line_value') and round(d['e2e']['in_line_value']), 'finite', d.get('finite'), d['e2e'])
+d=json.load(open('$OUT/bench_qm9_$v.json'))
+print('$v ms/step', round(d['ms_per_step'],3), 'value', round(d['value']), 'e2e', round(d['e2e']['value']), 'in line', round(d['e2e']['in_line_value']))
 PY
+done
