@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 15
+#define JODO_ABI_VERSION 16
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -48,10 +48,10 @@ int jodo_abi_version(void);
  * operands the edge kernels gather (q | k | v, the hoisted input_lin parts, the hoisted node2edge_lin part). */
 int jodo_rowlinear(const float* A, int lda, int M, int K, const void* Wimg, const float* bias, void* C, int ldc,
                    int N, int NT, int act_in, int epi, int act_out, const float* aux, int ld_aux, const float* gate,
-                   int ld_gate, const int* row_mol, int out_f16, const int* only_row0_if_zero, void* stream);
-/* only_row0_if_zero (may be null): device flag of jodo_uniform_flag; when it reads 0 only the first 128-row tile is
- * computed -- used for the per-molecule AdaLN table, whose rows are all equal to row 0 under uniform conditioning
- * (every consumer then reads row 0). */
+                   int ld_gate, const int* row_mol, int out_f16, const int* skip_if_zero, void* stream);
+/* skip_if_zero (may be null): device flag of jodo_uniform_flag; when it reads 0 the launch does nothing -- under uniform
+ * conditioning the per-molecule rows (noise-level embedding, AdaLN table) are all equal to row 0, which jodo_row0_linear
+ * computes and every consumer reads. */
 
 
 /* Persistent, TMA-fed variant of jodo_rowlinear for the per-atom GEMMs of a DGT block: the activation operand is
@@ -285,12 +285,12 @@ int jodo_act_image(const float* rows, int ld, int M, int K, int act, void* img, 
  * temb (noise level [+ context], reference models/mol_gnn.py:534, 728-734): the samplers broadcast one noise level
  * over the batch (sampling.py:549), in which case every per-molecule AdaLN row is the same row. */
 int jodo_uniform_flag(const float* rows, int B, int T, int* nonuni, void* stream);
-/* out[n] = act_in(A[0, :]) . W[n, :] + bias[n] for n < N: ROW 0 of the rowlinear product as a matrix-vector kernel on the same
+/* out[n] = act_out(act_in(A[0, :]) . W[n, :] + bias[n]) + aux[n] for n < N: ROW 0 of the rowlinear product as a matrix-vector kernel on the same
  * fp16 weight image (activation rounded to fp16 like the GEMM's operand), executed only while *run_if_zero == 0 (null: always).  The per-molecule AdaLN table under uniform
  * conditioning (every molecule carries the same noise level and context, as in sampling: reference sampling.py:549), where
  * all consumers read row 0; the all-rows GEMM (jodo_imglinear with skip_if_zero) covers the other case. */
-int jodo_row0_linear(const float* A, int K, const void* Wimg, int NT, int N, const float* bias, int act_in, float* out,
-                     const int* run_if_zero, void* stream);
+int jodo_row0_linear(const float* A, int K, const void* Wimg, int NT, int N, const float* bias, int act_in, int act_out,
+                     const float* aux, float* out, const int* run_if_zero, void* stream);   /* act_out: none / GELU; aux (may be null): row added after the activation */
 int jodo_com(float* pos4, const jodo_plan* p, void* stream);
 int jodo_node_out(const float* pos4, const float* atom_pred, int ldp, const jodo_plan* p, int* nan_flag, const int* mol_bad,
                   int inn, float* out_dense, void* stream);

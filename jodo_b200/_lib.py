@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 15:
+        if _lib.jodo_abi_version() != 16:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -72,7 +72,7 @@ def stream_ptr():
 
 
 def rowlinear(A, K, Wimg, bias, C, N, NT, act_in=ACT_NONE, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None,
-              row_mol=None, M=None, stream=None, tag=None, out_f16=False, only_row0_if_zero=None):
+              row_mol=None, M=None, stream=None, tag=None, out_f16=False, skip_if_zero=None):
     """C[:, :N] = epi(act_in(A[:, :K]) W^T + bias); A, C, aux, gate are 2-D row-major views (stride(1)==1)."""
     M = A.shape[0] if M is None else M
     f = lib().jodo_rowlinear
@@ -81,7 +81,7 @@ def rowlinear(A, K, Wimg, bias, C, N, NT, act_in=ACT_NONE, epi=EPI_STORE, act_ou
         ptr(A), c_int(A.stride(0)), c_int(M), c_int(K), ptr(Wimg), ptr(bias), ptr(C), c_int(C.stride(0)), c_int(N),
         c_int(NT), c_int(act_in), c_int(epi), c_int(act_out), ptr(aux), c_int(0 if aux is None else aux.stride(0)),
         ptr(gate), c_int(0 if gate is None else gate.stride(0)), ptr(row_mol), c_int(1 if out_f16 else 0),
-        ctypes.c_void_p(only_row0_if_zero), st))
+        ctypes.c_void_p(skip_if_zero), st))
     check(rc, 'jodo_rowlinear')
 
 

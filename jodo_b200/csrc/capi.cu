@@ -65,9 +65,9 @@ int jodo_abi_version(void) { return JODO_ABI_VERSION; }
 
 int jodo_rowlinear(const float* A, int lda, int M, int K, const void* Wimg, const float* bias, void* C, int ldc,
                    int N, int NT, int act_in, int epi, int act_out, const float* aux, int ld_aux, const float* gate,
-                   int ld_gate, const int* row_mol, int out_f16, const int* only_row0_if_zero, void* stream) {
+                   int ld_gate, const int* row_mol, int out_f16, const int* skip_if_zero, void* stream) {
   jodo::RowLinearArgs a{A, lda, M, K, static_cast<const float*>(Wimg), bias, C, ldc, N, NT, act_in, epi, act_out, aux, ld_aux,
-                        gate, ld_gate, row_mol, out_f16, only_row0_if_zero};
+                        gate, ld_gate, row_mol, out_f16, skip_if_zero};
   if (const char* m = jodo::check_rowlinear(a)) return fail(m);
   cudaError_t e = jodo::launch_rowlinear(a, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? JODO_OK : cuda_fail(e, "jodo_rowlinear");
@@ -131,13 +131,14 @@ int jodo_act_image(const float* rows, int ld, int M, int K, int act, void* img, 
   if (!rows || !img || M <= 0 || K <= 0 || (K % 64) || (ld % 4)) return fail("jodo_act_image: bad arguments");
   JODO_LAUNCH(jodo::launch_act_image(rows, ld, M, K, act, img, S(stream)), "jodo_act_image");
 }
-int jodo_row0_linear(const float* A, int K, const void* Wimg, int NT, int N, const float* bias, int act_in, float* out,
-                     const int* run_if_zero, void* stream) {
+int jodo_row0_linear(const float* A, int K, const void* Wimg, int NT, int N, const float* bias, int act_in, int act_out,
+                     const float* aux, float* out, const int* run_if_zero, void* stream) {
   if (!A || !Wimg || !out || K <= 0 || (K % 64) || K > 8192 || N <= 0 || NT <= 0 || (NT % 8) || (N % NT))
     return fail("jodo_row0_linear: bad arguments (K a multiple of 64 up to 8192, N a multiple of NT)");
   if (reinterpret_cast<uintptr_t>(Wimg) & 15) return fail("jodo_row0_linear: the weight image must be 16-byte aligned");
   if (act_in != JODO_ACT_NONE && act_in != JODO_ACT_SILU) return fail("jodo_row0_linear: act_in must be none or SiLU");
-  JODO_LAUNCH(jodo::launch_row0_linear(A, K, Wimg, NT, N, bias, act_in, out, run_if_zero, S(stream)), "jodo_row0_linear");
+  if (act_out != JODO_ACT_NONE && act_out != JODO_ACT_GELU) return fail("jodo_row0_linear: act_out must be none or GELU");
+  JODO_LAUNCH(jodo::launch_row0_linear(A, K, Wimg, NT, N, bias, act_in, act_out, aux, out, run_if_zero, S(stream)), "jodo_row0_linear");
 }
 int jodo_uniform_flag(const float* rows, int B, int T, int* nonuni, void* stream) {
   if (!rows || !nonuni || B <= 0 || T <= 0) return fail("jodo_uniform_flag: bad arguments");

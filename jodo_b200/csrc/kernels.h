@@ -46,7 +46,7 @@ struct RowLinearArgs {
   const float* gate; int ld_gate;               // EPI_GATED_RES: gate[row_mol[row], col]
   const int* row_mol;
   int out_f16;                                  // EPI_STORE only: write fp16 (saturating) instead of fp32
-  const int* only_row0_if_zero;                 // device flag: 0 = compute the first row tile only
+  const int* skip_if_zero;                      // device flag: 0 = the launch does nothing
 };
 const char* check_rowlinear(const RowLinearArgs& a);
 cudaError_t launch_rowlinear(const RowLinearArgs& a, cudaStream_t stream);
@@ -91,8 +91,8 @@ cudaError_t launch_ln_mod_img(const float* x, int ldx, const float* y, int ldy, 
                               void* y_img, const int* nonuni, cudaStream_t st);
 cudaError_t launch_act_image(const float* rows, int ld, int M, int K, int act, void* img, cudaStream_t st);
 cudaError_t launch_uniform_flag(const float* rows, int B, int T, int* nonuni, cudaStream_t st);
-cudaError_t launch_row0_linear(const float* A, int K, const void* Wimg, int nt, int N, const float* bias, int act_in, float* out,
-                               const int* run_if_zero, cudaStream_t st);
+cudaError_t launch_row0_linear(const float* A, int K, const void* Wimg, int nt, int N, const float* bias, int act_in, int act_out,
+                               const float* aux, float* out, const int* run_if_zero, cudaStream_t st);
 cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st);
 cudaError_t launch_nan_flag(const float* pos, int Nn, const int* mol_bad, int B, int* flag, cudaStream_t st);
 cudaError_t launch_node_out(const float* pos, const float* atom_pred, int ldp, const Plan& p, const int* nan_flag,

@@ -206,7 +206,8 @@ __global__ void k_uniform_flag(const float* __restrict__ rows, int B, int T, int
 // column, a lane takes one piece (8 weights) of four consecutive K chunks per step, x = act_in(A[0]) staged in shared memory.
 // Replaces a 128-row tensor-core tile per 128 columns whose K loop is a latency chain (0.07 - 0.1 ms for the [1024 x 19712] table).
 __global__ void __launch_bounds__(256) k_row0_linear(const float* __restrict__ A, int K, const uint8_t* __restrict__ Wimg, int nt, int N,
-                                                     const float* __restrict__ bias, int act_in, float* __restrict__ out,
+                                                     const float* __restrict__ bias, int act_in, int act_out,
+                                                     const float* __restrict__ aux, float* __restrict__ out,
                                                      const int* __restrict__ run_if_zero) {
   if (run_if_zero && *run_if_zero != 0) return;
   extern __shared__ float xs[];
@@ -233,7 +234,11 @@ __global__ void __launch_bounds__(256) k_row0_linear(const float* __restrict__ A
     }
   }
   acc = warp_sum(acc);
-  if (lane == 0) out[n] = acc + (bias ? bias[n] : 0.f);
+  if (lane == 0) {
+    float v = acc + (bias ? bias[n] : 0.f);
+    if (act_out == ACT_GELU) v = gelu_f(v);
+    out[n] = v + (aux ? aux[n] : 0.f);
+  }
 }
 
 // Per-molecule centre-of-mass removal of the block's coordinate update, in place on pos_new
@@ -361,9 +366,10 @@ cudaError_t launch_uniform_flag(const float* rows, int B, int T, int* nonuni, cu
   k_uniform_flag<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rows, B, T, nonuni);
   return LAUNCH_OK();
 }
-cudaError_t launch_row0_linear(const float* A, int K, const void* Wimg, int nt, int N, const float* bias, int act_in, float* out,
-                               const int* run_if_zero, cudaStream_t st) {
-  k_row0_linear<<<(N + 7) / 8, 256, K * sizeof(float), st>>>(A, K, static_cast<const uint8_t*>(Wimg), nt, N, bias, act_in, out, run_if_zero);
+cudaError_t launch_row0_linear(const float* A, int K, const void* Wimg, int nt, int N, const float* bias, int act_in, int act_out,
+                               const float* aux, float* out, const int* run_if_zero, cudaStream_t st) {
+  k_row0_linear<<<(N + 7) / 8, 256, K * sizeof(float), st>>>(A, K, static_cast<const uint8_t*>(Wimg), nt, N, bias, act_in, act_out, aux, out,
+                                                             run_if_zero);
   return LAUNCH_OK();
 }
 cudaError_t launch_com(float* pos_new, const Plan& p, cudaStream_t st) {

@@ -35,7 +35,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 __global__ void __launch_bounds__(RL_THREADS, 2) k_rowlinear(RowLinearArgs a) {
-  if (a.only_row0_if_zero && blockIdx.x > 0 && *a.only_row0_if_zero == 0) return;   // uniform conditioning: row 0 is every row
+  if (a.skip_if_zero && *a.skip_if_zero == 0) return;   // uniform conditioning: jodo_row0_linear computes row 0, which is every row
   // declared with its alignment (not aligned by pointer arithmetic): the compiler must see a shared-memory address, or every
   // staging access below becomes a generic LD / ST instead of LDS / STS
   extern __shared__ __align__(1024) uint8_t smem[];

@@ -276,25 +276,38 @@ class _DGTBase(nn.Module):
                            tag=tag or ('jodo_imglinear:' + name.split('.')[-1]), **kw)
 
         # ---- per molecule: noise-level embedding (+ context) and all AdaLN tables
+        # flags[2] = 1 unless every molecule carries the same conditioning row (the samplers broadcast one noise level)
+        nonuni = ws.flags.data_ptr() + 8
         _lib.call('jodo_time_features', _lib.ptr(noise_level), _lib.ptr(pk['time.w8']), _lib.ptr(ws.feat), _c(B), st)
-        lin('time1', ws.feat, ws.t1, epi=_lib.EPI_ACT, act_out=_lib.ACT_GELU)
         if d.cond_ch:
+            lin('time1', ws.feat, ws.t1, epi=_lib.EPI_ACT, act_out=_lib.ACT_GELU)
             ctx = c32(context).reshape(B * d.cond_ch)
             _lib.call('jodo_cond_in', _lib.ptr(ctx), _lib.ptr(pk['cond0.w']), _lib.ptr(pk['cond0.b']), _lib.ptr(ws.c1),
                       _c(B * d.cond_ch), _c(D), st)
             lin('cond2', ws.c1, ws.c2)
             lin('condlin', ws.c2.view(B, d.cond_ch * D), ws.ctx)
             lin('time3', ws.t1, ws.temb, epi=_lib.EPI_ADD, aux=ws.ctx)
+            _lib.call('jodo_uniform_flag', _lib.ptr(ws.temb), _c(B), _c(T), ctypes.c_void_p(nonuni), st)
         else:
-            lin('time3', ws.t1, ws.temb)
-        # flags[2] = 1 unless every molecule carries the same conditioning row (the samplers broadcast one noise level)
-        _lib.call('jodo_uniform_flag', _lib.ptr(ws.temb), _c(B), _c(T), ctypes.c_void_p(ws.flags.data_ptr() + 8), st)
-        nonuni = ws.flags.data_ptr() + 8
+            # No context: the rows depend on the noise level alone, so the flag is taken from the INPUT and, when it reads
+            # uniform, the two layers of time_mlp run for row 0 only, as matrix-vector products on the GEMMs' weight images
+            # (a 128-row tensor-core tile per layer is a 16-chunk latency chain: 0.03 + 0.05 ms); the GEMMs return at once.
+            _lib.call('jodo_uniform_flag', _lib.ptr(noise_level), _c(B), _c(1), ctypes.c_void_p(nonuni), st)
+            for name, src, dst, act in (('time1', ws.feat, ws.t1, _lib.ACT_GELU), ('time3', ws.t1, ws.temb, _lib.ACT_NONE)):
+                m = meta[name]
+                _lib.call('jodo_row0_linear', _lib.ptr(src), _c(m['K']), ctypes.c_void_p(pk.ptr(name + '.img')), _c(m['NT']),
+                          _c(m['N']), _lib.ptr(pk[name + '.b']), _c(_lib.ACT_NONE), _c(act), None, _lib.ptr(dst),
+                          ctypes.c_void_p(nonuni), st, tag='jodo_row0_linear:' + name)
+                if act:
+                    lin(name, src, dst, epi=_lib.EPI_ACT, act_out=act, skip_if_zero=nonuni)
+                else:
+                    lin(name, src, dst, skip_if_zero=nonuni)
         # all AdaLN rows.  Uniform conditioning: row 0 as a matrix-vector product (every consumer reads row 0); otherwise every
         # molecule's row through the persistent GEMM.  Each tests the device flag, one of them returns at once.
         m = meta['tab']
         _lib.call('jodo_row0_linear', _lib.ptr(ws.temb), _c(T), ctypes.c_void_p(pk.ptr('tab.img')), _c(m['NT']), _c(m['N']),
-                  _lib.ptr(pk['tab.b']), _c(_lib.ACT_SILU), _lib.ptr(ws.tab), ctypes.c_void_p(nonuni), st)
+                  _lib.ptr(pk['tab.b']), _c(_lib.ACT_SILU), _c(_lib.ACT_NONE), None, _lib.ptr(ws.tab), ctypes.c_void_p(nonuni), st,
+                  tag='jodo_row0_linear:tab')
         _lib.call('jodo_act_image', _lib.ptr(ws.temb), _c(T), _c(B), _c(T), _c(_lib.ACT_SILU), _lib.ptr(ws.temb_img), st)
         _lib.imglinear(ws.temb_img, B, m['K'], pk['tab.img'], pk['tab.b'], m['N'], m['NT'], C32=ws.tab, stream=st,
                        tag='jodo_imglinear:tab', skip_if_zero=nonuni)

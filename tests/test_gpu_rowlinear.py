@@ -75,18 +75,22 @@ def test_row0_linear_matches_fp64_and_obeys_the_flag(K, N, NT, act):
     b = torch.randn(N, device='cuda', generator=g)
     Wi = weight_image_h(W, NT)
     out = torch.full((3, N), 7.0, device='cuda')
+    gelu = K == 64                                            # the time_mlp.1 shape: GELU on the output, plus an added row
+    aux = torch.randn(N, device='cuda', generator=g)
     flag = torch.zeros(1, device='cuda', dtype=torch.int32)
     c = ctypes.c_int
 
     def run():
         _lib.call('jodo_row0_linear', _lib.ptr(A), c(K), _lib.ptr(Wi), c(NT), c(N), _lib.ptr(b), c(_lib.ACT_SILU if act else 0),
-                  _lib.ptr(out), _lib.ptr(flag), _lib.stream_ptr())
+                  c(_lib.ACT_GELU if gelu else 0), _lib.ptr(aux) if gelu else None, _lib.ptr(out), _lib.ptr(flag), _lib.stream_ptr())
         torch.cuda.synchronize()
     run()
     x = A[0].double()
     if act:
         x = torch.nn.functional.silu(x)
     ref = W.half().double() @ x.float().half().double() + b.double()                  # both operands fp16-rounded, as in the GEMM
+    if gelu:
+        ref = torch.nn.functional.gelu(ref) + aux.double()
     assert float((out[0].double() - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
     assert bool((out[1:] == 7.0).all())
     out.fill_(7.0)
