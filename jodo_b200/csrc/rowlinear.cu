@@ -67,10 +67,12 @@ __global__ void __launch_bounds__(RL_THREADS, 2) k_rowlinear(RowLinearArgs a) {
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.Wimg) + (size_t)blockIdx.y * nk * nt * 128;
   const uint32_t w_chunk_bytes = (uint32_t)nt * 128u;
 
-  // activation chunk: 16 threads cover the 64 columns of one row, a pass covers 16 rows, 8 passes
+  // activation chunk: 16 threads cover the 64 columns of one row, a pass covers 16 rows, 8 passes.  Two register sets: the
+  // chunk after next is requested as soon as a set has been stored, so a chunk's global loads have a whole loop iteration
+  // (one tensor-core round trip) to land instead of the few instructions between two iterations.
   const int c4 = tid & 15, r0 = tid >> 4;
-  float4 v[8];
-  auto load_chunk = [&](int kc) {
+  float4 va[8], vb[8];
+  auto load_chunk = [&](int kc, float4 (&v)[8]) {
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
       const int gr = m0 + p * 16 + r0;
@@ -78,11 +80,11 @@ __global__ void __launch_bounds__(RL_THREADS, 2) k_rowlinear(RowLinearArgs a) {
                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  load_chunk(0);
+  load_chunk(0, va);
+  if (nk > 1) load_chunk(1, vb);
 
   uint32_t par_m[RL_STAGES] = {0, 0}, par_w[RL_STAGES] = {0, 0}, par_a[RL_STAGES] = {0, 0};
-  for (int kc = 0; kc < nk; ++kc) {
-    const int s = kc & 1;
+  auto step = [&](int kc, int s, float4 (&v)[8]) {      // s = kc & 1 as a literal: the parities stay in registers
     if (kc >= RL_STAGES) {                       // stage s is free once the MMAs of chunk kc-2 completed
       mbar_wait(&bar_m[s], par_m[s]);
       par_m[s] ^= 1;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(RL_THREADS, 2) k_rowlinear(RowLinearArgs a) {
     }
     fence_async_smem();
     mbar_arrive(&bar_a[s]);
-    if (kc + 1 < nk) load_chunk(kc + 1);
+    if (kc + 2 < nk) load_chunk(kc + 2, v);
     if (tid == 0) {
       mbar_wait(&bar_a[s], par_a[s]);
       mbar_wait(&bar_w[s], par_w[s]);
@@ -114,6 +116,10 @@ __global__ void __launch_bounds__(RL_THREADS, 2) k_rowlinear(RowLinearArgs a) {
     }
     par_a[s] ^= 1;
     par_w[s] ^= 1;
+  };
+  for (int kc = 0; kc < nk; kc += 2) {
+    step(kc, 0, va);
+    if (kc + 1 < nk) step(kc + 1, 1, vb);
   }
   // the last commit covers every earlier MMA
   {
