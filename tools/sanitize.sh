@@ -15,3 +15,9 @@ done
 timeout 1200 compute-sanitizer --tool memcheck --report-api-errors no --print-limit 20 python -m pytest tests/test_classifier.py tests/test_philox.py -m gpu -q \
     -k "fixture or oracle_draws or kernel_normals" > $OUT/extra_memcheck.log 2>&1
 echo "extra memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed" $OUT/extra_memcheck.log | tail -3
+# the fused wide-path edge FFN in every compiled size, the row-0 matrix-vector kernel, the dots-only GEMM (unit tests)
+for tool in memcheck racecheck; do
+  timeout 1200 compute-sanitizer --tool $tool --report-api-errors no --print-limit 20 python -m pytest tests/test_gpu_wide_units.py tests/test_gpu_rowlinear.py \
+      tests/test_gpu_imglinear.py -m gpu -q -k "(fused_edge_ffn and not 700) or row0_linear or row_dots" > $OUT/units_$tool.log 2>&1
+  echo "units $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" $OUT/units_$tool.log | tail -3
+done
