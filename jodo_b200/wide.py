@@ -128,7 +128,9 @@ def pack_wide(pk, sd, d, add_lin, lin):
             lin(p + 'c0', f'{b}.equi_update.coord_mlp.0', c0_tile(D))
             # coord_mlp.2 (1 + X outputs, no bias) rides on coord_mlp.0's epilogue as three fp32 row dots (rows beyond 1 + X zero)
             pk.mat(p + 'c2.w32', 3, D, [(W(f'{b}.equi_update.coord_mlp.2'), 0, 0)])
-        add_lin(p + 'g01', [(W(f'{b}.attn_mpnn.lin_edge0'), 0, 0), (W(f'{b}.attn_mpnn.lin_edge1'), qkp, 0)], [], 128, qkp + D, EDP)
+        # 256-column tiles where they divide the width: 243 vs 266 us per launch at nf = 384 (tools/bench_gemm_wide.py)
+        add_lin(p + 'g01', [(W(f'{b}.attn_mpnn.lin_edge0'), 0, 0), (W(f'{b}.attn_mpnn.lin_edge1'), qkp, 0)], [],
+                256 if (qkp + D) % 256 == 0 else 128, qkp + D, EDP)
         add_lin(p + 'ff3', [(W(f'{b}.ff_linear3'), 0, 0)], [(Bv(f'{b}.ff_linear3'), 0)], 128, f3p, EDP, n_pad=f3p)
         add_lin(p + 'ff4', [(W(f'{b}.ff_linear4'), 0, 0)], [(Bv(f'{b}.ff_linear4'), 0)], 128, ed, f3p)
         if ffn_fused(d):
