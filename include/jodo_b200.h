@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define JODO_ABI_VERSION 16
+#define JODO_ABI_VERSION 17
 
 #define JODO_OK 0
 #define JODO_ERR_ARG 1   /* invalid argument (shape, alignment, unsupported size) */
@@ -32,6 +32,7 @@ extern "C" {
 #define JODO_EPI_ACT 1        /* C = act_out(acc + bias) */
 #define JODO_EPI_ADD 2        /* C = acc + bias + aux */
 #define JODO_EPI_GATED_RES 3  /* C = aux + gate[row_mol[row]] * (acc + bias) */
+#define JODO_EPI_LN_MOD 4     /* jodo_imglinear only: image = LayerNorm(acc + bias) * (1 + scale) + shift per row (see ln_* fields) */
 
 const char* jodo_last_error_string(void);
 int jodo_abi_version(void);
@@ -90,6 +91,12 @@ typedef struct jodo_imglinear_args {
    * NT >= 128 and N <= 512 the launch runs k_imglinear_dot2 (two 128-row tiles share every weight chunk: half the L2 bytes per
    * FLOP; 16 epilogue warps reading tensor memory directly); NT = 192 is accepted in that mode only. */
   const float* dot_w; float* dot_out; int ld_dot;
+  /* JODO_EPI_LN_MOD (N = NT = 128, the only output is Cimg with the default placement): LayerNorm (eps 1e-6, no affine) over
+   * the first ln_cols columns of acc + bias, then x * tab[mol, ln_off_scale + c] + tab[mol, ln_off_shift + c] with tab = gate /
+   * ld_gate / row_mol / nonuni as for the gated epilogue (the scale columns hold 1 + scale); columns >= ln_cols and rows with
+   * ln_valid[row] < 0 are written as zeros.  The wide path's block edge_emb + norm1_edge (reference models/mol_gnn.py:287,
+   * 296-297) in one launch: the fp32 edge_emb output never goes to HBM. */
+  const int* ln_valid; int ln_cols, ln_off_shift, ln_off_scale;
 } jodo_imglinear_args;
 int jodo_imglinear(const jodo_imglinear_args* a, void* stream);
 

@@ -15,7 +15,7 @@ c_fp = ctypes.c_void_p
 c_int = ctypes.c_int
 
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
-EPI_STORE, EPI_ACT, EPI_ADD, EPI_GATED_RES = 0, 1, 2, 3
+EPI_STORE, EPI_ACT, EPI_ADD, EPI_GATED_RES, EPI_LN_MOD = 0, 1, 2, 3, 4
 
 
 class JodoError(RuntimeError):
@@ -30,7 +30,7 @@ def lib():
                             f'(there is no CPU or PyTorch fallback for the DGT hot path)')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.jodo_last_error_string.restype = ctypes.c_char_p
-        if _lib.jodo_abi_version() != 16:
+        if _lib.jodo_abi_version() != 17:
             raise JodoError('libjodo_b200.so ABI version mismatch; rebuild')
     return _lib
 
@@ -153,7 +153,8 @@ class ImgLinearArgs(ctypes.Structure):
                 ('act_out', _I), ('aux', _P), ('ld_aux', _I), ('gate', _P), ('ld_gate', _I), ('row_mol', _P), ('nonuni', _P),
                 ('skip_if_zero', _P), ('C32', _P), ('ldc32', _I), ('C16', _P), ('ldc16', _I), ('c16_piece_major', _I), ('Cimg', _P),
                 ('cimg_k', _I), ('cimg_col0', _I), ('cimg_ncols', _I), ('Cimg2', _P), ('cimg2_k', _I), ('cimg2_col0', _I),
-                ('cimg2_ncols', _I), ('dot_w', _P), ('dot_out', _P), ('ld_dot', _I)]
+                ('cimg2_ncols', _I), ('dot_w', _P), ('dot_out', _P), ('ld_dot', _I), ('ln_valid', _P), ('ln_cols', _I),
+                ('ln_off_shift', _I), ('ln_off_scale', _I)]
 
 
 class WideEmbedArgs(ctypes.Structure):
@@ -190,7 +191,7 @@ class WideAttnArgs(ctypes.Structure):
 
 def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, aux=None, gate=None, row_mol=None,
               C32=None, C16=None, Cimg=None, stream=None, tag=None, nonuni=0, skip_if_zero=0, cimg_place=None, Cimg2=None,
-              cimg2_place=None, dot_w=None, dot_out=None):
+              cimg2_place=None, dot_w=None, dot_out=None, ln=None, ln_valid=None):
     """Persistent TMA-fed GEMM on an fp16 activation image (include/jodo_b200.h: jodo_imglinear).
     C32 / C16 are 2-D row-major views (stride(1) == 1) -- or C16 a contiguous 3-D [N/8, rows, 8] tensor for the
     piece-major layout the edge kernels gather from; Cimg a flat fp16 image buffer."""
@@ -200,7 +201,7 @@ def imglinear(Aimg, M, K, Wimg, bias, N, NT, epi=EPI_STORE, act_out=ACT_NONE, au
                       skip_if_zero, dp(C32), 0 if C32 is None else C32.stride(0), dp(C16),
                       0 if C16 is None else (C16.shape[1] if pm else C16.stride(0)), 1 if pm else 0, dp(Cimg),
                       *(cimg_place or (0, 0, 0)), dp(Cimg2), *(cimg2_place or (0, 0, 0)), dp(dot_w), dp(dot_out),
-                      0 if dot_out is None else dot_out.stride(0))
+                      0 if dot_out is None else dot_out.stride(0), dp(ln_valid), *(ln or (0, 0, 0)))      # ln = (cols, off_shift, off_scale)
     st = stream if stream is not None else stream_ptr()
     f = lib().jodo_imglinear
     check(_account(tag or 'jodo_imglinear', lambda: f(ctypes.byref(a), st)), 'jodo_imglinear')

@@ -60,6 +60,10 @@ constexpr int il_mode(int epi, bool c32, bool c16, bool cimg, bool cimg2 = false
 // consecutive 16-byte slots, no staging through shared memory, no team barrier.  (The row-major pass wrote 16 sectors of
 // 16 useful bytes per store instruction here.)
 constexpr int IL_MODE_PM16 = 128;
+// JODO_EPI_LN_MOD: LayerNorm + modulation of the accumulator row, written as the fp16 operand image of the next GEMM (16
+// epilogue warps, N = NT = 128: warp = lane quarter x 32-column quarter, one chunk per thread; the row statistics cross
+// the four column quarters through shared memory and one barrier of the 16 warps).
+constexpr int IL_MODE_LN = 256;
 
 template <int MODE, int ACT = ACT_SILU, int EW = 8>
 __global__ void __launch_bounds__(il_threads(EW), 1) k_imglinear(ImgLinearArgs a) {
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(il_threads(EW), 1) k_imglinear(ImgLinearArgs a
     const int row = rq * 32 + lane;
     const int cw = nt / NTEAM;                     // columns per team (32, 64 or 128)
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-    const int epi = MODE < 0 ? a.epi : (MODE == IL_MODE_PM16 ? EPI_STORE : (MODE & 3));
+    const int epi = MODE < 0 ? a.epi : ((MODE == IL_MODE_PM16 || MODE == IL_MODE_LN) ? EPI_STORE : (MODE & 3));
     const bool has32 = MODE < 0 ? a.C32 != nullptr : (MODE & 4) != 0;
     const bool has16 = MODE < 0 ? a.C16 != nullptr : (MODE & 8) != 0;
     const bool hasimg = MODE < 0 ? a.Cimg != nullptr : (MODE & 16) != 0;
@@ -195,6 +199,58 @@ __global__ void __launch_bounds__(il_threads(EW), 1) k_imglinear(ImgLinearArgs a
       }
       mbar_wait(&bar_tfull[ab], aph);
       tc_fence_after();
+      if (MODE == IL_MODE_LN) {
+        const int gr = m * TILE_ROWS + row;
+        const int c0 = team * 32, W = a.ln_cols;
+        float x[32];
+        tmem_ld32(tmem + ab * 256u + ((uint32_t)rq << 21) + (uint32_t)c0, x);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(&bar_tempty[ab]);     // the accumulator is in registers: the next unit's MMAs may start
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + c0) + p);
+          x[4 * p] += bv.x; x[4 * p + 1] += bv.y; x[4 * p + 2] += bv.z; x[4 * p + 3] += bv.w;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (c0 + 4 * p + i < W) { s += x[4 * p + i]; q = fmaf(x[4 * p + i], x[4 * p + i], q); }
+          }
+        }
+        // partial sums of the four column quarters; two buffers by unit parity (a warp may be one unit ahead of another)
+        float2* lns = reinterpret_cast<float2*>(stg_base) + (ai & 1u) * (TILE_ROWS * 4);
+        lns[row * 4 + team] = make_float2(s, q);
+        named_bar_sync(1, 32 * EW);
+        const float4 p01 = *reinterpret_cast<const float4*>(&lns[row * 4]);
+        const float4 p23 = *reinterpret_cast<const float4*>(&lns[row * 4 + 2]);
+        const float inv_w = 1.0f / (float)W;
+        const float mean = (p01.x + p01.z + p23.x + p23.z) * inv_w;
+        const float rstd = rsqrtf(fmaxf((p01.y + p01.w + p23.y + p23.w) * inv_w - mean * mean, 0.f) + 1e-6f);
+        const float nmr = -mean * rstd;
+        const bool live = gr < Mrows && (!a.ln_valid || __ldg(a.ln_valid + gr) >= 0);
+        const int mol_ = (live && !gate_row0) ? __ldg(a.row_mol + gr) : 0;
+        const float* t = gate + (size_t)mol_ * ld_gate;
+        uint8_t* dst = Cimg + (size_t)m * 2 * IL_A_STAGE + (size_t)(c0 >> 6) * IL_A_STAGE;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int col = c0 + 8 * p;
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (live && col < W) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(t + a.ln_off_scale + col));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(t + a.ln_off_scale + col + 4));
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(t + a.ln_off_shift + col));
+            const float4 h1 = __ldg(reinterpret_cast<const float4*>(t + a.ln_off_shift + col + 4));
+            const float* v = &x[8 * p];
+            o.x = pack_h2(fmaf(fmaf(v[0], rstd, nmr), s0.x, h0.x), fmaf(fmaf(v[1], rstd, nmr), s0.y, h0.y));
+            o.y = pack_h2(fmaf(fmaf(v[2], rstd, nmr), s0.z, h0.z), fmaf(fmaf(v[3], rstd, nmr), s0.w, h0.w));
+            o.z = pack_h2(fmaf(fmaf(v[4], rstd, nmr), s1.x, h1.x), fmaf(fmaf(v[5], rstd, nmr), s1.y, h1.y));
+            o.w = pack_h2(fmaf(fmaf(v[6], rstd, nmr), s1.z, h1.z), fmaf(fmaf(v[7], rstd, nmr), s1.w, h1.w));
+          }
+          *reinterpret_cast<uint4*>(dst + img_piece(row, 0, ((col & 63) >> 3), IL_A_STAGE)) = o;
+        }
+        continue;
+      }
       if (MODE == IL_MODE_PM16) {
         const int gr = m * TILE_ROWS + row;
         for (int c0 = team * cw; c0 < (team + 1) * cw; c0 += 32) {
@@ -514,6 +570,15 @@ const char* check_imglinear(const ImgLinearArgs& a) {
   if (!a.Aimg || !a.Wimg) return "imglinear: operand image missing";
   if ((reinterpret_cast<uintptr_t>(a.Aimg) | reinterpret_cast<uintptr_t>(a.Wimg)) & 127) return "imglinear: images must be 128-byte aligned";
   if (!a.C32 && !a.C16 && !a.Cimg && !a.dot_out) return "imglinear: no output";
+  if (a.epi == EPI_LN_MOD) {
+    if (a.N != 128 || a.NT != 128 || !a.Cimg || a.C32 || a.C16 || a.Cimg2 || a.dot_out || a.cimg_k)
+      return "imglinear: JODO_EPI_LN_MOD needs N = NT = 128 and the image output alone (default placement)";
+    if (a.ln_cols <= 0 || a.ln_cols > 128 || (a.ln_cols % 8) || !a.gate || !a.row_mol || (a.ld_gate % 4) || (a.ln_off_shift % 4) ||
+        (a.ln_off_scale % 4) || (reinterpret_cast<uintptr_t>(a.gate) & 15))
+      return "imglinear: JODO_EPI_LN_MOD needs ln_cols % 8 == 0 (<= 128), the table (gate, ld_gate, row_mol) and 16-byte aligned offsets";
+    if (reinterpret_cast<uintptr_t>(a.Cimg) & 127) return "imglinear: image output must be 128-byte aligned";
+    return nullptr;
+  }
   if (a.dot_out && (!a.dot_w || a.epi != EPI_ACT || a.ld_dot < 4 * 2 * (a.N / a.NT) || (a.ld_dot % 4) || ((reinterpret_cast<uintptr_t>(a.dot_w) | reinterpret_cast<uintptr_t>(a.dot_out)) & 15)))
     return "imglinear: fused row dots need dot_w, JODO_EPI_ACT and ld_dot >= 8 N / NT";
   if (a.Cimg2 && !a.Cimg) return "imglinear: Cimg2 needs Cimg";
@@ -561,6 +626,7 @@ cudaError_t launch_imglinear(const ImgLinearArgs& a_in, int num_sms, cudaStream_
   const int grid = units < num_sms ? units : num_sms;
   const int mode = il_mode(a.epi, a.C32 != nullptr, a.C16 != nullptr, a.Cimg != nullptr, a.Cimg2 != nullptr, a.dot_out != nullptr);
   const bool silu_or_none = a.epi != EPI_ACT || a.act_out == ACT_SILU;
+  if (a.epi == EPI_LN_MOD) return launch_mode_ew<IL_MODE_LN, ACT_SILU, 16>(a, grid, stream);
   if (mode == il_mode(EPI_ACT, false, false, false, false, true) && a.act_out == ACT_SILU && a.NT >= 128 && a.N <= 512) {
     // wide: coord_mlp.0 + coord_mlp.2 dots -- two row tiles per W chunk, 16 epilogue warps (JODO_DOT_LEGACY=1: the streaming kernel)
     static const bool legacy = [] { const char* e = getenv("JODO_DOT_LEGACY"); return e && e[0] == '1'; }();

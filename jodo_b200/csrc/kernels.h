@@ -33,7 +33,7 @@ cudaError_t const_tables_acquire(cudaStream_t st);
 cudaError_t const_tables_release(cudaStream_t st);
 
 enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_TANH = 3 };
-enum { EPI_STORE = 0, EPI_ACT = 1, EPI_ADD = 2, EPI_GATED_RES = 3 };
+enum { EPI_STORE = 0, EPI_ACT = 1, EPI_ADD = 2, EPI_GATED_RES = 3, EPI_LN_MOD = 4 };
 
 struct RowLinearArgs {
   const float* A; int lda; int M; int K;        // activations, row-major, K % 32 == 0 (zero padded)

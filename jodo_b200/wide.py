@@ -41,6 +41,10 @@ EDP = 128            # row stride (floats) of the per-edge fp32 buffers and K of
 FFN_UNFUSED = os.environ.get('JODO_WIDE_FFN_UNFUSED') == '1'
 
 
+# A/B switch: block edge_emb as a plain GEMM followed by the LayerNorm row kernel (before the JODO_EPI_LN_MOD epilogue)
+EMB_LN_UNFUSED = os.environ.get('JODO_WIDE_EMB_LN_UNFUSED') == '1'
+
+
 def ffn_fused(d) -> bool:
     """Sizes csrc/wide_ffn.cu is built for (both weight images + two tiles in shared memory, r ed <= 256 TMEM columns)."""
     return d.r in (2, 4) and d.ed in (32, 64, 96)
@@ -289,8 +293,14 @@ def forward_wide(self, pk, plan, ws, ps, pps, xh, edge_x, noise_level, cond_x, c
         else:
             _lib.call('jodo_wide_dist', ctypes.byref(pps), P(pin), P(ws.tab), _c(ld_tab), _c(og), P(pk[p + 'gbf']), _c(EDP),
                       _c(ed), P(ws.ED), _c(K2), _c(ed), None, _c(0), _c(0), st)
-            ilin(p + 'emb', ws.ED, RP, C32=ws.e1)
-            ln(RP, ed, EDP, ws.e1, (oe, oe + ed), plan.pair_mol, out_img=ws.en_img, valid=plan.pair_i, tag='e1')
+            me = meta[p + 'emb']
+            if me['N'] == 128 and me['NT'] == 128 and EDP == 128 and dbg is None and not EMB_LN_UNFUSED:
+                # block edge_emb with norm1_edge + modulation as its epilogue: the fp32 edge_emb output never goes to HBM
+                ilin(p + 'emb', ws.ED, RP, epi=_lib.EPI_LN_MOD, Cimg=ws.en_img, gate=ws.tab, row_mol=plan.pair_mol, nonuni=nonuni,
+                     ln=(ed, oe, oe + ed), ln_valid=plan.pair_i)
+            else:
+                ilin(p + 'emb', ws.ED, RP, C32=ws.e1)
+                ln(RP, ed, EDP, ws.e1, (oe, oe + ed), plan.pair_mol, out_img=ws.en_img, valid=plan.pair_i, tag='e1')
         ilin(p + 'g01', ws.en_img, RP, bias=False, epi=_lib.EPI_ACT, act_out=_lib.ACT_TANH, C16=ws.G)
         # attention
         ln(Nn, D, D, h, (o, o + D), plan.node_mol, out_img=ws.hn_img, tag='h1')

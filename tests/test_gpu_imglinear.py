@@ -189,3 +189,42 @@ def test_imglinear_placed_images_and_row_dots(M, K, N, NT, epi):
         _lib.imglinear(Ai, M, K, Wi, b, N, NT, C32=C32, Cimg=img1, cimg_place=(k1, 4, n1))
     with pytest.raises(_lib.JodoError):
         _lib.imglinear(Ai, M, K, Wi, b, N, NT, C32=C32, Cimg=img1, cimg_place=(k1, 128, 96))
+
+
+@pytest.mark.parametrize('M,K,W', [(1000, 256, 96), (128, 192, 64), (389, 128, 128)])
+def test_imglinear_layernorm_modulate_epilogue(M, K, W):
+    """JODO_EPI_LN_MOD: LayerNorm (eps 1e-6) over the first W columns of acc + bias, modulation by the per-molecule table
+    row, written as the fp16 operand image; columns >= W and padding rows are zeros; uniform flag -> row 0 for every row."""
+    g = torch.Generator(device='cuda').manual_seed(M + W)
+    N = NT = 128
+    A = torch.randn(M, K, device='cuda', generator=g)
+    Wt = torch.zeros(N, K, device='cuda')
+    Wt[:W] = torch.randn(W, K, device='cuda', generator=g) / K ** 0.5
+    b = torch.zeros(N, device='cuda')
+    b[:W] = torch.randn(W, device='cuda', generator=g)
+    B, ld = 6, 16 + 2 * 128
+    tab = torch.randn(B, ld, device='cuda', generator=g)
+    mol = torch.randint(0, B, (M,), device='cuda', generator=g, dtype=torch.int32)
+    valid = torch.zeros(M, device='cuda', dtype=torch.int32)
+    valid[::11] = -1
+    Ai, Wi = act_image(A), weight_image_h(Wt, NT)
+    mt = (M + 127) // 128
+    x = (h(A) @ h(Wt).t() + b.double())[:, :W]
+    mu = x.mean(1, keepdim=True)
+    var = (x * x).mean(1, keepdim=True) - mu * mu
+    nrm = (x - mu) / torch.sqrt(var.clamp(min=0) + 1e-6)
+    for uni in (False, True):
+        flag = torch.tensor([0 if uni else 1], device='cuda', dtype=torch.int32)
+        t = tab.double()[torch.zeros_like(mol).long() if uni else mol.long()]
+        want = nrm * t[:, 16 + 128:16 + 128 + W] + t[:, 16:16 + W]
+        want[valid < 0] = 0
+        img = torch.full((mt * 128 * N,), 7.0, device='cuda', dtype=torch.float16)
+        _lib.imglinear(Ai, M, K, Wi, b, N, NT, epi=_lib.EPI_LN_MOD, Cimg=img, gate=tab, row_mol=mol, nonuni=flag.data_ptr(),
+                       ln=(W, 16, 16 + 128), ln_valid=valid)
+        torch.cuda.synchronize()
+        rows = image_rows(img, N)
+        assert float((rows[:M, :W].double() - want).abs().max()) < 2e-3 * max(1.0, float(want.abs().max()))
+        assert float(rows[:M, W:].abs().max()) == 0.0 if W < N else True
+        assert float(rows[:M][valid < 0].abs().max()) == 0.0
+    with pytest.raises(_lib.JodoError):
+        _lib.imglinear(Ai, M, K, Wi, b, N, NT, epi=_lib.EPI_LN_MOD, Cimg=img, gate=tab, row_mol=mol, ln=(W + 4, 16, 16 + 128))
