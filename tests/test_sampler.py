@@ -419,3 +419,17 @@ def test_host_pipelined_steps_equal_in_line_copies():
             assert torch.equal(h[k], w_[k]), k
     with pytest.raises(ValueError):
         S.HostPipelinedSteps(steps, [{k: v.clone() for k, v in h.items()} for h in hosts])      # unpinned host buffers
+
+
+def test_split_for_pipeline_is_a_balanced_partition():
+    """Host logic of the pipelined host-state API: the parts are a partition of the batch, equal in size up to one molecule
+    and balanced in cost (sum of n (n - 1), the dealing of shard_molecules)."""
+    g = torch.Generator().manual_seed(3)
+    n = torch.randint(3, 30, (501,), generator=g)
+    for parts in (2, 3):
+        idx = S.split_for_pipeline(n, parts)
+        assert sorted(torch.cat(idx).tolist()) == list(range(len(n)))
+        sizes = [len(i) for i in idx]
+        assert max(sizes) - min(sizes) <= 1
+        cost = [float((n[i] * (n[i] - 1)).sum()) for i in idx]
+        assert (max(cost) - min(cost)) / max(cost) < 0.02
