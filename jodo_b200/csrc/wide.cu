@@ -160,12 +160,14 @@ __global__ void k_wide_put(const float* __restrict__ src, int ld, int M, int W, 
 }
 
 // ---- per-block distance features (models/mol_gnn.py:284-286): written as columns [col1, col1 + ed) of the
-// [dist | e] operand and [col2, col2 + ed) of the [e | dist] operand.  One warp per row.
+// [dist | e] operand and [col2, col2 + ed) of the [e | dist] operand.
 __global__ void k_wide_dist(Plan p, const float4* __restrict__ pos, const float* __restrict__ tab, int ld_tab,
                             int off_gbf, const float* __restrict__ gbf, int ld_gbf, int ed, void* img1, int K1, int col1,
                             void* img2, int K2, int col2) {
-  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + ((threadIdx.x >> 4) & 1), lane = threadIdx.x & 15;
-  if (row >= p.n_tiles * 128) return;                            // two rows per warp, 16 lanes each
+  // four rows per warp, 8 lanes each (ed / 8 <= 16 pieces: one or two per lane): the kernel waits on two dependent round
+  // trips per row (atom indices, then positions), so rows in flight per warp are what it is bound by
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + ((threadIdx.x >> 3) & 3), lane = threadIdx.x & 7;
+  if (row >= p.n_tiles * 128) return;
   const int g = p.row_g[row];
   float x = 0.f;
   if (g >= 0) {
@@ -174,7 +176,7 @@ __global__ void k_wide_dist(Plan p, const float4* __restrict__ pos, const float*
     const float* tr = tab + (size_t)p.row_mol[row] * ld_tab + off_gbf;
     x = (dx * dx + dy * dy + dz * dz) * tr[0] + tr[1];
   }
-  for (int q = lane; q < (ed >> 3); q += 16) {
+  for (int q = lane; q < (ed >> 3); q += 8) {
     float v[8];
     if (g >= 0) wgbf8(x, gbf, ld_gbf, 8 * q, ed, v);
     else {
@@ -505,7 +507,7 @@ cudaError_t launch_wide_put(const float* src, int ld, int M, int W, const int* v
 }
 cudaError_t launch_wide_dist(const Plan& p, const float* pos, const float* tab, int ld_tab, int off_gbf, const float* gbf,
                              int ld_gbf, int ed, void* img1, int K1, int col1, void* img2, int K2, int col2, cudaStream_t st) {
-  k_wide_dist<<<p.n_tiles * 128 / 16, 256, 0, st>>>(p, reinterpret_cast<const float4*>(pos), tab, ld_tab, off_gbf, gbf,
+  k_wide_dist<<<p.n_tiles * 128 / 32, 256, 0, st>>>(p, reinterpret_cast<const float4*>(pos), tab, ld_tab, off_gbf, gbf,
                                                    ld_gbf, ed, img1, K1, col1, img2, K2, col2);
   return WIDE_OK();
 }
