@@ -100,6 +100,14 @@ def test_bad_arguments_fail_before_any_launch(lib):
     i.Aimg = i.Wimg = 128
     i.Cimg, i.cimg_k, i.cimg_col0, i.cimg_ncols = 128, 192, 4, 96
     assert lib.jodo_imglinear(ctypes.byref(i), None) == 1 and b'placement' in lib.jodo_last_error_string()
+    # the LayerNorm + modulation epilogue is built for N = NT = 128 with the image output alone; NT = 192 for the dots-only mode
+    n = _lib.ImgLinearArgs()
+    n.M, n.K, n.N, n.NT, n.epi = 128, 64, 256, 128, _lib.EPI_LN_MOD
+    n.Aimg = n.Wimg = n.Cimg = 128
+    assert lib.jodo_imglinear(ctypes.byref(n), None) == 1 and b'JODO_EPI_LN_MOD' in lib.jodo_last_error_string()
+    n.N, n.NT, n.epi = 192, 192, _lib.EPI_STORE
+    assert lib.jodo_imglinear(ctypes.byref(n), None) == 1 and b'192: fused row dots only' in lib.jodo_last_error_string()
+    assert lib.jodo_row0_linear(None, 64, None, 64, 64, None, 0, 0, None, None, None, None) == 1
     # wide path (nf = 384)
     assert lib.jodo_wide_ln(None, None) == 1 and lib.jodo_wide_attn(None, None) == 1 and lib.jodo_wide_embed_in(None, None) == 1
     w = _lib.WideLnArgs()
